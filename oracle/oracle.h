@@ -1,0 +1,50 @@
+/* TEST INFRASTRUCTURE — plain-C restatement of LibGeoDecomp's per-timestep cell update for the
+ * models in oracle/models/. It is a checker: only tests/, __graft_entry__.smoke() and
+ * bench.py's cpu_baseline / --impl reference legs may load it. The product (libb200geo.so)
+ * never links or calls it.
+ *
+ * Pinning: every function here is validated bit-for-bit against the reference's own
+ * SerialSimulator built from /root/reference (oracle/_ref/lgd_ref_*, see oracle/Makefile)
+ * by tests/test_oracle_pinning.py, and against the committed fixtures under tests/golden/
+ * that those binaries generated (tests/golden/make_golden.py).
+ *
+ * All grids are dense, x fastest, [nz][ny][nx]; multi-member cells are member-major
+ * (member m starts at byte offset cells * sum(sizeof(previous members))), which is the byte
+ * stream SoAGrid::saveRegion produces for a box region (storage/soagrid.h:523-576,
+ * lib/libflatarray/include/libflatarray/detail/save_functor.hpp:44-58).
+ */
+#ifndef B200GEO_ORACLE_H
+#define B200GEO_ORACLE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* kind: 6, 7 or 27 (oracle/models/jacobi.h). torus: 0 = Cube (edge constant), 1 = Torus. */
+int oracle_jacobi(int kind, int torus, int nx, int ny, int nz, int steps, double edge,
+                  const double *in, double *out);
+
+/* Conway's Game of Life on 1-byte cells (oracle/models/conway.h). */
+int oracle_gol(int torus, int nx, int ny, int steps, int edge_alive,
+               const uint8_t *in, uint8_t *out);
+
+/* D3Q19 BGK, float, 24 members (19 populations, density, velocityX/Y/Z, int state);
+ * Cube topology, edge cell = LBMCellF() (oracle/models/lbm.h). Raw member-major in/out. */
+int oracle_lbm(int nx, int ny, int nz, int steps, const void *in_raw, void *out_raw);
+
+/* Member-major (de)serialisation of a list of streaks {x, y, z, endX}, restating
+ * SoAGrid::saveRegion/loadRegion (storage/soagrid.h:523-576). grid_raw is a dense member-major
+ * grid of nx*ny*nz cells; buf holds sum(streak lengths) cells, member-major. */
+int oracle_save_region(int nx, int ny, int nz, int n_members, const int *member_bytes,
+                       const void *grid_raw, const int *streaks, int n_streaks, void *buf);
+int oracle_load_region(int nx, int ny, int nz, int n_members, const int *member_bytes,
+                       void *grid_raw, const int *streaks, int n_streaks, const void *buf);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif

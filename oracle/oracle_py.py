@@ -1,0 +1,114 @@
+"""TEST INFRASTRUCTURE — ctypes access to oracle/liboracle.so (the C restatement) and a runner
+for the reference-built binaries under oracle/_ref/. Only tests/, __graft_entry__.smoke() and
+bench.py's cpu_baseline / --impl reference legs may import this module."""
+import ctypes
+import json
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+_lib = None
+
+
+def build():
+    subprocess.run(["make", "-C", HERE, "liboracle.so"], check=True, capture_output=True)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        path = os.path.join(HERE, "liboracle.so")
+        if not os.path.exists(path):
+            build()
+        _lib = ctypes.CDLL(path)
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def jacobi(kind, torus, grid, steps, edge=0.0):
+    g = np.ascontiguousarray(grid, dtype=np.float64)
+    nz, ny, nx = g.shape
+    out = np.empty_like(g)
+    rc = lib().oracle_jacobi(kind, int(torus), nx, ny, nz, steps, ctypes.c_double(edge), _p(g), _p(out))
+    assert rc == 0, rc
+    return out
+
+
+def gol(torus, grid, steps, edge_alive=0):
+    g = np.ascontiguousarray(grid, dtype=np.uint8)
+    ny, nx = g.shape
+    out = np.empty_like(g)
+    rc = lib().oracle_gol(int(torus), nx, ny, steps, int(edge_alive), _p(g), _p(out))
+    assert rc == 0, rc
+    return out
+
+
+def lbm(raw, steps):
+    g = np.ascontiguousarray(raw, dtype=np.float32)
+    m, nz, ny, nx = g.shape
+    assert m == 24
+    out = np.empty_like(g)
+    rc = lib().oracle_lbm(nx, ny, nz, steps, _p(g), _p(out))
+    assert rc == 0, rc
+    return out
+
+
+def _region(fn, grid_raw, dims, member_bytes, streaks, buf):
+    nx, ny, nz = dims
+    mb = np.asarray(member_bytes, dtype=np.int32)
+    st = np.ascontiguousarray(streaks, dtype=np.int32).reshape(-1, 4)
+    rc = fn(nx, ny, nz, len(mb), _p(mb), _p(grid_raw), _p(st), len(st), _p(buf))
+    assert rc == 0, rc
+
+
+def save_region(grid_raw, dims, member_bytes, streaks):
+    st = np.asarray(streaks, dtype=np.int32).reshape(-1, 4)
+    count = int((st[:, 3] - st[:, 0]).sum())
+    buf = np.zeros(count * int(sum(member_bytes)), dtype=np.uint8)
+    _region(lib().oracle_save_region, grid_raw, dims, member_bytes, st, buf)
+    return buf
+
+
+def load_region(grid_raw, dims, member_bytes, streaks, buf):
+    _region(lib().oracle_load_region, grid_raw, dims, member_bytes, streaks, np.ascontiguousarray(buf))
+
+
+# ------------------------------------------------------------------ reference binaries
+
+def ref_binary(model):
+    return os.path.join(HERE, "_ref", "lgd_ref_" + model)
+
+
+def have_ref(model):
+    return os.access(ref_binary(model), os.X_OK)
+
+
+def run_ref(model, raw_in, dims, steps, omp=False, edge=None, threads=None, want_output=True):
+    """Run the reference's own SerialSimulator/OpenMPSimulator on raw_in (any numpy array whose
+    bytes are the member-major grid); returns (raw_out_bytes as uint8 array, stats dict)."""
+    nx, ny, nz = dims
+    env = dict(os.environ)
+    if omp:
+        env["OMP_PROC_BIND"] = "true"
+        env["OMP_PLACES"] = "cores"
+        if threads:
+            env["OMP_NUM_THREADS"] = str(threads)
+    with tempfile.TemporaryDirectory() as tmp:
+        fin, fout = os.path.join(tmp, "in.raw"), os.path.join(tmp, "out.raw")
+        np.ascontiguousarray(raw_in).tofile(fin)
+        cmd = [ref_binary(model), model, str(nx), str(ny), str(nz), str(steps), fin,
+               fout if want_output else "-"]
+        if omp:
+            cmd.append("--omp")
+        if edge is not None:
+            cmd += ["--edge", repr(float(edge))]
+        res = subprocess.run(cmd, env=env, check=True, capture_output=True, text=True)
+        stats = json.loads(res.stdout.strip().splitlines()[-1])
+        out = np.fromfile(fout, dtype=np.uint8) if want_output else None
+    return out, stats
