@@ -1,0 +1,168 @@
+/* b200geo — C ABI of the B200-native cell-update engine (libb200geo.so).
+ *
+ * LibGeoDecomp has no FFI boundary of its own: back-ends plug in as C++ templates
+ * (Simulator<CELL> subclasses, parallelization/cudasimulator.h:298; Stepper<CELL> subclasses,
+ * parallelization/nesting/cudastepper.h:256). This header is the seam a maintainer binds
+ * instead: plain pointers, sizes and status codes, called only by the header-only façade
+ * templates in include/libgeodecomp_b200/ (B200Simulator<CELL>, B200Grid<CELL>) and by the
+ * ctypes mirror in libgeodecomp_b200/capi.py. Each entry point names the reference interface it
+ * replaces. Paths are relative to /root/reference/src/libgeodecomp/.
+ *
+ * Conventions
+ *  - every function returns B200GEO_OK (0) or a negative b200geo_status; the façade maps them to
+ *    the reference's exceptions (std::invalid_argument, std::logic_error, std::out_of_range,
+ *    std::runtime_error("CUDA error"), misc/cudautil.h:48-55). b200geo_last_error() has the text.
+ *  - coordinates are interior cell coordinates, x fastest; 2-D grids use dim[2] = 1.
+ *  - a streak is int32 {x, y, z, endX} (geometry/streak.h:16-84, half open in x).
+ *  - "member-major" buffers are byte-compatible with SoAGrid::saveRegion / loadRegion
+ *    (storage/soagrid.h:523-576, storage/serializationbuffer.h:61-101): for each member in
+ *    registration order all cells of the region, tightly packed.
+ *  - a `stream` argument is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *  - not re-entrant per handle; one host thread drives one device. There is NO CPU fallback:
+ *    without a usable CUDA device every compute entry point returns B200GEO_ERR_CUDA.
+ */
+#ifndef B200GEO_H
+#define B200GEO_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200GEO_MAX_MEMBERS 32
+
+typedef enum {
+    B200GEO_OK = 0,
+    B200GEO_ERR_INVALID = -1,      /* -> std::invalid_argument */
+    B200GEO_ERR_LOGIC = -2,        /* -> std::logic_error (unsupported combination) */
+    B200GEO_ERR_OUT_OF_RANGE = -3, /* -> std::out_of_range (e.g. particle capacity exceeded, storage/fixedarray.h:77-83) */
+    B200GEO_ERR_CUDA = -4,         /* -> std::runtime_error("CUDA error") */
+    B200GEO_ERR_NOMEM = -5         /* -> std::bad_alloc */
+} b200geo_status;
+
+/* MemoryLocation::Location, storage/memorylocation.h:11-14 */
+typedef enum { B200GEO_HOST = 0, B200GEO_CUDA_DEVICE = 1 } b200geo_location;
+
+/* Hand-written kernel families; B200KernelBinding<CELL> maps a user cell type to one of these. */
+typedef enum {
+    B200GEO_KERNEL_JACOBI6 = 1,  /* 6-point mean, f64; src/examples/jacobi3d/main.cpp:30-39 */
+    B200GEO_KERNEL_JACOBI7 = 2,  /* 7-point mean, f64; src/testbed/performancetests/main.cpp:1292-1299 */
+    B200GEO_KERNEL_JACOBI27 = 3, /* 27-point mean over Moore<3,1>, f64; oracle/models/jacobi.h */
+    B200GEO_KERNEL_GOL = 4,      /* Conway's Life, 1-byte cells; src/examples/gameoflife/main.cpp:36-59 */
+    B200GEO_KERNEL_LBM_D3Q19 = 5,/* D3Q19 BGK + wall states, f32; src/examples/latticeboltzmann/main.cpp:62-229 */
+    B200GEO_KERNEL_NBODY = 6     /* BoxCell short-range n-body; storage/boxcell.h:112-174 */
+} b200geo_kernel;
+
+/* What a ghost (padding) layer on one side of one axis holds. */
+typedef enum {
+    B200GEO_GHOST_EDGE = 0, /* the constant edge cell of a Cube axis (storage/soagrid.h:578-584) */
+    B200GEO_GHOST_WRAP = 1, /* periodic image of this grid's own far side (Torus axis on one device) */
+    B200GEO_GHOST_PEER = 2  /* cells owned by a neighbouring subdomain, filled by the halo exchange */
+} b200geo_ghost_mode;
+
+/* Describes one device-resident double-buffered SoA grid. Replaces the ctor arguments of
+ * SoAGrid (storage/soagrid.h:344-427) / CUDASoAGrid (storage/cudasoagrid.h:116) plus the SoA
+ * member table LIBFLATARRAY_REGISTER_SOA generates (lib/libflatarray/.../macros.hpp:101-126). */
+typedef struct {
+    int32_t dim[3];                            /* interior extent */
+    int32_t ghost[3];                          /* ghost width per axis (>= stencil radius where used, 0 otherwise) */
+    int32_t ghost_mode[3][2];                  /* b200geo_ghost_mode per axis and side (0 = low, 1 = high) */
+    int32_t n_members;
+    int32_t member_bytes[B200GEO_MAX_MEMBERS]; /* 1, 2, 4 or 8; array members are listed element by element */
+} b200geo_grid_desc;
+
+typedef struct b200geo_grid b200geo_grid;
+
+/* ---- library ---------------------------------------------------------------------------- */
+const char *b200geo_version(void);
+const char *b200geo_last_error(void);
+/* number of CUDA devices, or a negative status (no driver / no device). */
+int b200geo_device_count(void);
+/* number of kernels this library has launched so far in this process (bench.py: gpu_launches). */
+uint64_t b200geo_launch_count(void);
+
+/* ---- grid life cycle: replaces SoAGrid::SoAGrid/resize (storage/soagrid.h:380-427) -------- */
+int b200geo_grid_create(const b200geo_grid_desc *desc, int device, b200geo_grid **out);
+int b200geo_grid_destroy(b200geo_grid *g);
+/* bytes of one of the two buffers (padded layout) */
+int b200geo_grid_buffer_bytes(const b200geo_grid *g, uint64_t *bytes);
+/* layout query for one member: row pitch and plane pitch in elements, and the element offset of
+ * interior cell (0,0,0) from the member's base pointer */
+int b200geo_grid_layout(const b200geo_grid *g, int member, int64_t *pitch_x, int64_t *pitch_plane,
+                        int64_t *origin_offset);
+/* device pointer of member `member` in the current (which = 0) or the scratch (which = 1) buffer */
+int b200geo_grid_member_ptr(const b200geo_grid *g, int member, int which, void **ptr);
+
+/* SoAGrid::setEdge/getEdge (storage/soagrid.h:486-499): cell = aggregated member bytes in
+ * registration order; rewrites every EDGE ghost layer of BOTH buffers. */
+int b200geo_grid_set_edge(b200geo_grid *g, const void *cell, void *stream);
+int b200geo_grid_get_edge(const b200geo_grid *g, void *cell);
+
+/* ---- bulk I/O --------------------------------------------------------------------------- */
+/* GridBase::loadMember/saveMember (storage/gridbase.h:217-261) for a box: dense [dz][dy][dx]
+ * array of one member <-> grid. `both` != 0 writes both buffers (SerialSimulator initialises
+ * both grids, parallelization/serialsimulator.h:54-57). Host buffers may be pageable or pinned. */
+int b200geo_grid_load_member(b200geo_grid *g, int member, const int32_t origin[3], const int32_t dim[3],
+                             const void *src, int location, int both, void *stream);
+int b200geo_grid_save_member(const b200geo_grid *g, int member, const int32_t origin[3], const int32_t dim[3],
+                             void *dst, int location, void *stream);
+/* GridBase::loadRegion/saveRegion(std::vector<char>) (storage/gridbase.h:32-50, soagrid.h:523-576,
+ * LFA detail/save_functor.hpp:26-66 which launches one kernel PER STREAK on CUDA): here one
+ * launch per call for any number of streaks. buf is member-major. */
+int b200geo_grid_load_region(b200geo_grid *g, const int32_t *streaks, int n_streaks,
+                             const void *buf, int location, int both, void *stream);
+int b200geo_grid_save_region(const b200geo_grid *g, const int32_t *streaks, int n_streaks,
+                             void *buf, int location, void *stream);
+
+/* ---- the hot path ----------------------------------------------------------------------- */
+/* n_steps x { UpdateFunctor over the whole grid; swap } = SerialSimulator::nanoStep
+ * (parallelization/serialsimulator.h:132-139, storage/updatefunctor.h:403-428) on the device.
+ * WRAP ghost layers are refreshed internally before every sweep; PEER layers must have been
+ * filled by the caller (b200geo_halo_*): with ghost width G on a PEER side up to G steps may be
+ * taken between two exchanges (the rim is recomputed redundantly, as
+ * parallelization/nesting/vanillastepper.h:157-225 does). params: kernel specific, may be NULL. */
+int b200geo_step(b200geo_grid *g, int kernel, const void *params, uint32_t first_nano_step,
+                 uint32_t n_steps, void *stream);
+/* Same, restricted to a box of interior coordinates (ghost cells addressable with negative
+ * coordinates); does not swap. Used for rim-first / interior-overlapped schedules
+ * (parallelization/stripingsimulator.h:269-286). */
+int b200geo_update_box(b200geo_grid *g, int kernel, const void *params, uint32_t nano_step,
+                       const int32_t origin[3], const int32_t dim[3], void *stream);
+int b200geo_swap(b200geo_grid *g);
+/* Re-materialise the periodic images of WRAP axes in the current buffer (done automatically by
+ * b200geo_step; needed before b200geo_update_box on Torus axes). */
+int b200geo_refresh_ghosts(b200geo_grid *g, void *stream);
+int b200geo_sync(void *stream);
+
+/* ---- halo exchange (replaces PatchLink::Accepter::put / Provider::get,
+ *      communication/patchlink.h:127-151,218-244, for slab partitions along the last axis,
+ *      geometry/partitions/stripingpartition.h:57-62) --------------------------------------- */
+/* Device address and byte count of the contiguous block of `width` whole padded planes of one
+ * member: kind 0 = the outermost OWNED planes on `side` (what a neighbour needs = inner ghost
+ * zone), kind 1 = the GHOST planes on `side` (outer ghost zone). Buffer = current. */
+int b200geo_halo_block(const b200geo_grid *g, int member, int side, int kind, int width,
+                       void **ptr, uint64_t *bytes);
+/* CUDA-IPC plumbing for direct NVLink P2P between one-process-per-GPU ranks. */
+int b200geo_grid_ipc_export(const b200geo_grid *g, int which, void *handle64);
+int b200geo_grid_ipc_open(b200geo_grid *g, int side, int which, const void *handle64);
+/* Push this grid's owned boundary planes (all members, `width` planes) into the PEER ghost
+ * planes of the neighbour opened on `side` with plain device-to-device copies over NVLink. */
+int b200geo_halo_push(b200geo_grid *g, int side, int width, void *stream);
+/* Tell the grid that `width` ghost planes on PEER side `side` of the current buffer are valid
+ * (called after an exchange done by the caller, e.g. NCCL send/recv into b200geo_halo_block). */
+int b200geo_halo_mark_valid(b200geo_grid *g, int side, int width);
+
+/* ---- statistics: Simulator::gatherStatistics / Chronometer (misc/chronometer.h:142-150) ---- */
+/* out[0] = device seconds spent in update kernels (TimeComputeInner), out[1] = seconds in ghost
+ * refresh / halo copies (TimeComputeGhost + TimeCommunication), out[2] = number of sweeps. Uses
+ * CUDA events recorded around b200geo_step when enabled. */
+int b200geo_stats_enable(b200geo_grid *g, int on);
+int b200geo_stats(b200geo_grid *g, double out[3]);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif

@@ -1,0 +1,516 @@
+// libb200geo.so — grid life cycle, bulk I/O, step dispatch and halo plumbing behind the C ABI
+// declared in include/b200geo.h. The hot kernels live in jacobi.cu, gol.cu, lbm.cu, region.cu.
+#include "grid.h"
+
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+namespace b200geo {
+
+static thread_local std::string g_last_error;
+static std::atomic<uint64_t> g_launches(0);
+
+int fail(int status, const std::string& msg)
+{
+    g_last_error = msg;
+    return status;
+}
+
+int check_cuda(cudaError_t e, const char *what)
+{
+    if (e == cudaSuccess) return 0;
+    g_last_error = std::string("CUDA error: ") + cudaGetErrorString(e) + " in " + what;
+    return B200GEO_ERR_CUDA;
+}
+
+void count_launch(uint64_t n)
+{
+    g_launches += n;
+}
+
+static int64_t round_up(int64_t v, int64_t a)
+{
+    return (v + a - 1) / a * a;
+}
+
+static bool valid_box(const b200geo_grid *g, const int32_t o[3], const int32_t d[3])
+{
+    for (int i = 0; i < 3; ++i) {
+        if (d[i] < 0 || o[i] < -g->g[i] || o[i] + d[i] > g->d[i] + g->g[i]) return false;
+    }
+    return true;
+}
+
+}
+
+using namespace b200geo;
+
+extern "C" {
+
+const char *b200geo_version(void)
+{
+    return "b200geo 0.1 (sm_100a)";
+}
+
+const char *b200geo_last_error(void)
+{
+    return g_last_error.c_str();
+}
+
+int b200geo_device_count(void)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) return check_cuda(e, "cudaGetDeviceCount");
+    return n;
+}
+
+uint64_t b200geo_launch_count(void)
+{
+    return g_launches.load();
+}
+
+int b200geo_grid_create(const b200geo_grid_desc *desc, int device, b200geo_grid **out)
+{
+    if (!desc || !out) return fail(B200GEO_ERR_INVALID, "null argument");
+    if (desc->n_members < 1 || desc->n_members > B200GEO_MAX_MEMBERS)
+        return fail(B200GEO_ERR_INVALID, "n_members out of range");
+    for (int i = 0; i < 3; ++i) {
+        if (desc->dim[i] < 1) return fail(B200GEO_ERR_INVALID, "grid dimension must be >= 1");
+        if (desc->ghost[i] < 0 || desc->ghost[i] > 16) return fail(B200GEO_ERR_INVALID, "ghost width out of range");
+        for (int s = 0; s < 2; ++s) {
+            int mode = desc->ghost_mode[i][s];
+            if (mode < B200GEO_GHOST_EDGE || mode > B200GEO_GHOST_PEER)
+                return fail(B200GEO_ERR_INVALID, "bad ghost mode");
+            if (mode == B200GEO_GHOST_PEER && i != 2)
+                return fail(B200GEO_ERR_LOGIC, "PEER ghost layers are supported on the last axis only (slab partition)");
+            if (mode == B200GEO_GHOST_WRAP && desc->ghost[i] > desc->dim[i])
+                return fail(B200GEO_ERR_INVALID, "wrap ghost wider than the grid");
+        }
+        if ((desc->ghost_mode[i][0] == B200GEO_GHOST_WRAP) != (desc->ghost_mode[i][1] == B200GEO_GHOST_WRAP))
+            return fail(B200GEO_ERR_INVALID, "WRAP must be set on both sides of an axis");
+    }
+    B200GEO_CUDA(cudaSetDevice(device));
+
+    b200geo_grid *g = new (std::nothrow) b200geo_grid();
+    if (!g) return fail(B200GEO_ERR_NOMEM, "out of host memory");
+    memset(g, 0, sizeof(*g));
+    g->desc = *desc;
+    g->device = device;
+    g->n = desc->n_members;
+    for (int i = 0; i < 3; ++i) {
+        g->d[i] = desc->dim[i];
+        g->g[i] = desc->ghost[i];
+    }
+    int64_t off = 0;
+    int cell = 0;
+    for (int m = 0; m < g->n; ++m) {
+        int e = desc->member_bytes[m];
+        if (e != 1 && e != 2 && e != 4 && e != 8) {
+            delete g;
+            return fail(B200GEO_ERR_INVALID, "member size must be 1, 2, 4 or 8 bytes");
+        }
+        MemberLayout& L = g->m[m];
+        L.elem = e;
+        L.lead = 128 / e;
+        if (g->g[0] > L.lead) {
+            delete g;
+            return fail(B200GEO_ERR_INVALID, "x ghost wider than the 128-byte lead-in");
+        }
+        L.pitch = round_up((int64_t)(L.lead + g->d[0] + g->g[0]) * e, 128) / e;
+        L.plane = L.pitch * (g->d[1] + 2 * g->g[1]);
+        L.origin = (int64_t)g->g[2] * L.plane + (int64_t)g->g[1] * L.pitch + L.lead;
+        // 128 B of slack: vector accesses of partially valid groups may touch the bytes just past
+        // the last row (never stored to, values never used)
+        L.bytes = round_up(L.plane * (g->d[2] + 2 * g->g[2]) * e + 128, 256);
+        L.offset = off;
+        L.edge_offset = cell;
+        off += L.bytes;
+        cell += e;
+    }
+    g->buffer_bytes = off;
+    g->cell_bytes = cell;
+    for (int b = 0; b < 2; ++b) {
+        cudaError_t e = cudaMalloc((void **)&g->buf[b], (size_t)off);
+        if (e != cudaSuccess) {
+            if (b == 1) cudaFree(g->buf[0]);
+            delete g;
+            cudaGetLastError();
+            return fail(B200GEO_ERR_NOMEM, std::string("cudaMalloc failed: ") + cudaGetErrorString(e));
+        }
+    }
+    // zero-fill: the edge cell defaults to all-zero bytes until set_edge is called
+    cudaMemset(g->buf[0], 0, (size_t)off);
+    cudaMemset(g->buf[1], 0, (size_t)off);
+    for (int i = 0; i < 4; ++i) cudaEventCreate(&g->ev[i]);
+    *out = g;
+    return B200GEO_OK;
+}
+
+int b200geo_grid_destroy(b200geo_grid *g)
+{
+    if (!g) return B200GEO_OK;
+    cudaSetDevice(g->device);
+    for (int s = 0; s < 2; ++s)
+        for (int w = 0; w < 2; ++w)
+            if (g->peer_buf[s][w]) cudaIpcCloseMemHandle(g->peer_buf[s][w]);
+    cudaFree(g->buf[0]);
+    cudaFree(g->buf[1]);
+    if (g->scratch) cudaFree(g->scratch);
+    for (int i = 0; i < 4; ++i) cudaEventDestroy(g->ev[i]);
+    delete g;
+    return B200GEO_OK;
+}
+
+int b200geo_grid_buffer_bytes(const b200geo_grid *g, uint64_t *bytes)
+{
+    if (!g || !bytes) return fail(B200GEO_ERR_INVALID, "null argument");
+    *bytes = (uint64_t)g->buffer_bytes;
+    return B200GEO_OK;
+}
+
+int b200geo_grid_layout(const b200geo_grid *g, int member, int64_t *pitch_x, int64_t *pitch_plane,
+                        int64_t *origin_offset)
+{
+    if (!g || member < 0 || member >= g->n) return fail(B200GEO_ERR_INVALID, "bad member");
+    if (pitch_x) *pitch_x = g->m[member].pitch;
+    if (pitch_plane) *pitch_plane = g->m[member].plane;
+    if (origin_offset) *origin_offset = g->m[member].origin;
+    return B200GEO_OK;
+}
+
+int b200geo_grid_member_ptr(const b200geo_grid *g, int member, int which, void **ptr)
+{
+    if (!g || !ptr || member < 0 || member >= g->n || (which != 0 && which != 1))
+        return fail(B200GEO_ERR_INVALID, "bad member");
+    *ptr = g->member_ptr(member, which);
+    return B200GEO_OK;
+}
+
+int b200geo_grid_set_edge(b200geo_grid *g, const void *cell, void *stream)
+{
+    if (!g || !cell) return fail(B200GEO_ERR_INVALID, "null argument");
+    memcpy(g->edge, cell, g->cell_bytes);
+    B200GEO_CUDA(cudaSetDevice(g->device));
+    int rc = fill_edge(g, 0, (cudaStream_t)stream);
+    if (rc) return rc;
+    return fill_edge(g, 1, (cudaStream_t)stream);
+}
+
+int b200geo_grid_get_edge(const b200geo_grid *g, void *cell)
+{
+    if (!g || !cell) return fail(B200GEO_ERR_INVALID, "null argument");
+    memcpy(cell, g->edge, g->cell_bytes);
+    return B200GEO_OK;
+}
+
+static int member_copy(const b200geo_grid *g, int member, const int32_t o[3], const int32_t d[3],
+                       void *dense, int location, bool to_grid, int which, cudaStream_t s)
+{
+    const MemberLayout& L = g->m[member];
+    if (d[0] == 0 || d[1] == 0 || d[2] == 0) return B200GEO_OK;
+    cudaMemcpy3DParms p;
+    memset(&p, 0, sizeof(p));
+    cudaPitchedPtr dense_ptr = make_cudaPitchedPtr(dense, (size_t)d[0] * L.elem, (size_t)d[0] * L.elem, d[1]);
+    cudaPitchedPtr grid_ptr = make_cudaPitchedPtr(g->member_ptr(member, which), (size_t)L.pitch * L.elem,
+                                                  (size_t)L.pitch * L.elem, g->d[1] + 2 * g->g[1]);
+    cudaPos grid_pos = make_cudaPos((size_t)(L.lead + o[0]) * L.elem, o[1] + g->g[1], o[2] + g->g[2]);
+    if (to_grid) {
+        p.srcPtr = dense_ptr;
+        p.dstPtr = grid_ptr;
+        p.dstPos = grid_pos;
+        p.kind = location == B200GEO_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+    } else {
+        p.srcPtr = grid_ptr;
+        p.srcPos = grid_pos;
+        p.dstPtr = dense_ptr;
+        p.kind = location == B200GEO_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+    }
+    p.extent = make_cudaExtent((size_t)d[0] * L.elem, d[1], d[2]);
+    B200GEO_CUDA(cudaMemcpy3DAsync(&p, s));
+    return B200GEO_OK;
+}
+
+int b200geo_grid_load_member(b200geo_grid *g, int member, const int32_t origin[3], const int32_t dim[3],
+                             const void *src, int location, int both, void *stream)
+{
+    if (!g || !src || !origin || !dim) return fail(B200GEO_ERR_INVALID, "null argument");
+    if (member < 0 || member >= g->n) return fail(B200GEO_ERR_INVALID, "bad member index");
+    if (!valid_box(g, origin, dim)) return fail(B200GEO_ERR_INVALID, "box outside the grid");
+    B200GEO_CUDA(cudaSetDevice(g->device));
+    int rc = member_copy(g, member, origin, dim, const_cast<void *>(src), location, true, 0, (cudaStream_t)stream);
+    if (rc == 0 && both)
+        rc = member_copy(g, member, origin, dim, const_cast<void *>(src), location, true, 1, (cudaStream_t)stream);
+    return rc;
+}
+
+int b200geo_grid_save_member(const b200geo_grid *g, int member, const int32_t origin[3], const int32_t dim[3],
+                             void *dst, int location, void *stream)
+{
+    if (!g || !dst || !origin || !dim) return fail(B200GEO_ERR_INVALID, "null argument");
+    if (member < 0 || member >= g->n) return fail(B200GEO_ERR_INVALID, "bad member index");
+    if (!valid_box(g, origin, dim)) return fail(B200GEO_ERR_INVALID, "box outside the grid");
+    B200GEO_CUDA(cudaSetDevice(g->device));
+    return member_copy(g, member, origin, dim, dst, location, false, 0, (cudaStream_t)stream);
+}
+
+static int region_io(b200geo_grid *g, const int32_t *streaks, int n_streaks, void *buf, int location,
+                     bool save, int both, cudaStream_t s)
+{
+    if (!g || (n_streaks > 0 && (!streaks || !buf))) return fail(B200GEO_ERR_INVALID, "null argument");
+    if (n_streaks <= 0) return B200GEO_OK;
+    int64_t count = 0;
+    for (int i = 0; i < n_streaks; ++i) {
+        const int32_t *k = streaks + 4 * i;
+        if (k[3] < k[0] || k[0] < -g->g[0] || k[3] > g->d[0] + g->g[0] ||
+            k[1] < -g->g[1] || k[1] >= g->d[1] + g->g[1] || k[2] < -g->g[2] || k[2] >= g->d[2] + g->g[2])
+            return fail(B200GEO_ERR_INVALID, "streak outside the grid");
+        count += k[3] - k[0];
+    }
+    B200GEO_CUDA(cudaSetDevice(g->device));
+    char *dev = (char *)buf;
+    size_t bytes = (size_t)count * g->cell_bytes;
+    char *staging = 0;
+    if (location == B200GEO_HOST) {
+        B200GEO_CUDA(cudaMalloc((void **)&staging, bytes ? bytes : 1));
+        dev = staging;
+        if (!save) {
+            cudaError_t e = cudaMemcpyAsync(dev, buf, bytes, cudaMemcpyHostToDevice, s);
+            if (e != cudaSuccess) { cudaFree(staging); return check_cuda(e, "cudaMemcpyAsync"); }
+        }
+    }
+    int rc = copy_region(g, streaks, n_streaks, dev, count, save, 0, s);
+    if (rc == 0 && !save && both) rc = copy_region(g, streaks, n_streaks, dev, count, false, 1, s);
+    if (rc == 0 && location == B200GEO_HOST && save)
+        rc = check_cuda(cudaMemcpyAsync(buf, dev, bytes, cudaMemcpyDeviceToHost, s), "cudaMemcpyAsync");
+    if (staging) {
+        cudaStreamSynchronize(s);
+        cudaFree(staging);
+    }
+    return rc;
+}
+
+int b200geo_grid_load_region(b200geo_grid *g, const int32_t *streaks, int n_streaks,
+                             const void *buf, int location, int both, void *stream)
+{
+    return region_io(g, streaks, n_streaks, const_cast<void *>(buf), location, false, both, (cudaStream_t)stream);
+}
+
+int b200geo_grid_save_region(const b200geo_grid *g, const int32_t *streaks, int n_streaks,
+                             void *buf, int location, void *stream)
+{
+    return region_io(const_cast<b200geo_grid *>(g), streaks, n_streaks, buf, location, true, 0, (cudaStream_t)stream);
+}
+
+static int dispatch(b200geo_grid *g, int kernel, const void *params, const Box& box, bool last, cudaStream_t s)
+{
+    if (box.x1 <= box.x0 || box.y1 <= box.y0 || box.z1 <= box.z0) return B200GEO_OK;
+    switch (kernel) {
+    case B200GEO_KERNEL_JACOBI6:
+        return sweep_jacobi(g, 6, box, s);
+    case B200GEO_KERNEL_JACOBI7:
+        return sweep_jacobi(g, 7, box, s);
+    case B200GEO_KERNEL_JACOBI27:
+        return sweep_jacobi(g, 27, box, s);
+    case B200GEO_KERNEL_GOL:
+        return sweep_gol(g, box, s);
+    case B200GEO_KERNEL_LBM_D3Q19: {
+        // params: int32 store_macroscopic_every_step (default 0 = only on the last sweep of a call)
+        bool every = params && *(const int32_t *)params != 0;
+        return sweep_lbm(g, box, every || last, s);
+    }
+    default:
+        return fail(B200GEO_ERR_LOGIC, "no kernel bound for this id");
+    }
+}
+
+static int check_kernel_grid(const b200geo_grid *g, int kernel)
+{
+    switch (kernel) {
+    case B200GEO_KERNEL_JACOBI6:
+    case B200GEO_KERNEL_JACOBI7:
+    case B200GEO_KERNEL_JACOBI27:
+        if (g->n != 1 || g->m[0].elem != 8) return fail(B200GEO_ERR_INVALID, "Jacobi kernels need one f64 member");
+        for (int i = 0; i < 3; ++i)
+            if (g->g[i] < 1) return fail(B200GEO_ERR_INVALID, "Jacobi kernels need ghost width >= 1 on all axes");
+        return 0;
+    case B200GEO_KERNEL_GOL:
+        if (g->n != 1 || g->m[0].elem != 1) return fail(B200GEO_ERR_INVALID, "GoL kernel needs one 1-byte member");
+        if (g->d[2] != 1 || g->g[0] < 1 || g->g[1] < 1) return fail(B200GEO_ERR_INVALID, "GoL kernel needs a 2-D grid with ghost width >= 1");
+        return 0;
+    case B200GEO_KERNEL_LBM_D3Q19:
+        if (g->n != 24) return fail(B200GEO_ERR_INVALID, "LBM kernel needs 24 members");
+        for (int m = 0; m < 24; ++m)
+            if (g->m[m].elem != 4) return fail(B200GEO_ERR_INVALID, "LBM kernel needs 4-byte members");
+        for (int i = 0; i < 3; ++i)
+            if (g->g[i] < 1) return fail(B200GEO_ERR_INVALID, "LBM kernel needs ghost width >= 1 on all axes");
+        return 0;
+    default:
+        return fail(B200GEO_ERR_LOGIC, "no kernel bound for this id");
+    }
+}
+
+int b200geo_step(b200geo_grid *g, int kernel, const void *params, uint32_t first_nano_step,
+                 uint32_t n_steps, void *stream)
+{
+    (void)first_nano_step;  // none of the bound models depends on the nano step index
+    if (!g) return fail(B200GEO_ERR_INVALID, "null grid");
+    int rc = check_kernel_grid(g, kernel);
+    if (rc) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    B200GEO_CUDA(cudaSetDevice(g->device));
+    if (g->stats_on) cudaEventRecord(g->ev[0], s);
+    for (uint32_t t = 0; t < n_steps; ++t) {
+        Box box = {0, 0, 0, g->d[0], g->d[1], g->d[2]};
+        for (int side = 0; side < 2; ++side) {
+            if (g->desc.ghost_mode[2][side] != B200GEO_GHOST_PEER) continue;
+            if (g->peer_valid[side] < 1)
+                return fail(B200GEO_ERR_LOGIC, "ghost zone exhausted: exchange halos before stepping");
+            int extra = g->peer_valid[side] - 1;
+            if (side == 0) box.z0 -= extra; else box.z1 += extra;
+        }
+        rc = refresh_wrap(g, s);
+        if (rc) return rc;
+        rc = dispatch(g, kernel, params, box, t + 1 == n_steps, s);
+        if (rc) return rc;
+        g->cur ^= 1;
+        for (int side = 0; side < 2; ++side)
+            if (g->desc.ghost_mode[2][side] == B200GEO_GHOST_PEER) --g->peer_valid[side];
+        ++g->sweeps;
+    }
+    if (g->stats_on) {
+        cudaEventRecord(g->ev[1], s);
+        B200GEO_CUDA(cudaEventSynchronize(g->ev[1]));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, g->ev[0], g->ev[1]);
+        g->t_update += 1e-3 * ms;
+    }
+    return B200GEO_OK;
+}
+
+int b200geo_update_box(b200geo_grid *g, int kernel, const void *params, uint32_t nano_step,
+                       const int32_t origin[3], const int32_t dim[3], void *stream)
+{
+    (void)nano_step;
+    if (!g || !origin || !dim) return fail(B200GEO_ERR_INVALID, "null argument");
+    int rc = check_kernel_grid(g, kernel);
+    if (rc) return rc;
+    // the updated box may reach into PEER ghost planes but must leave one ring of readable cells
+    for (int i = 0; i < 3; ++i) {
+        int lo = (i == 2) ? -(g->g[i] - 1) : 0, hi = g->d[i] + ((i == 2) ? g->g[i] - 1 : 0);
+        if (dim[i] < 0 || origin[i] < lo || origin[i] + dim[i] > hi) return fail(B200GEO_ERR_INVALID, "box outside the updatable area");
+    }
+    B200GEO_CUDA(cudaSetDevice(g->device));
+    Box box = {origin[0], origin[1], origin[2], origin[0] + dim[0], origin[1] + dim[1], origin[2] + dim[2]};
+    return dispatch(g, kernel, params, box, true, (cudaStream_t)stream);
+}
+
+int b200geo_swap(b200geo_grid *g)
+{
+    if (!g) return fail(B200GEO_ERR_INVALID, "null grid");
+    g->cur ^= 1;
+    ++g->sweeps;
+    return B200GEO_OK;
+}
+
+int b200geo_refresh_ghosts(b200geo_grid *g, void *stream)
+{
+    if (!g) return fail(B200GEO_ERR_INVALID, "null grid");
+    B200GEO_CUDA(cudaSetDevice(g->device));
+    return refresh_wrap(g, (cudaStream_t)stream);
+}
+
+int b200geo_sync(void *stream)
+{
+    B200GEO_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    return B200GEO_OK;
+}
+
+int b200geo_halo_block(const b200geo_grid *g, int member, int side, int kind, int width,
+                       void **ptr, uint64_t *bytes)
+{
+    if (!g || !ptr || !bytes) return fail(B200GEO_ERR_INVALID, "null argument");
+    if (member < 0 || member >= g->n || (side != 0 && side != 1) || (kind != 0 && kind != 1))
+        return fail(B200GEO_ERR_INVALID, "bad member/side/kind");
+    if (width < 1 || width > g->g[2] || width > g->d[2]) return fail(B200GEO_ERR_INVALID, "bad halo width");
+    const MemberLayout& L = g->m[member];
+    int64_t zplane;  // padded plane index of the first plane of the block
+    if (kind == 0) zplane = side == 0 ? g->g[2] : g->g[2] + g->d[2] - width;
+    else           zplane = side == 0 ? g->g[2] - width : g->g[2] + g->d[2];
+    *ptr = g->member_ptr(member, 0) + zplane * L.plane * L.elem;
+    *bytes = (uint64_t)width * L.plane * L.elem;
+    return B200GEO_OK;
+}
+
+int b200geo_halo_mark_valid(b200geo_grid *g, int side, int width)
+{
+    if (!g || (side != 0 && side != 1) || width < 0 || width > g->g[2]) return fail(B200GEO_ERR_INVALID, "bad side/width");
+    g->peer_valid[side] = width;
+    return B200GEO_OK;
+}
+
+int b200geo_grid_ipc_export(const b200geo_grid *g, int which, void *handle64)
+{
+    if (!g || !handle64 || (which != 0 && which != 1)) return fail(B200GEO_ERR_INVALID, "bad argument");
+    B200GEO_CUDA(cudaSetDevice(g->device));
+    cudaIpcMemHandle_t h;
+    // `which` is absolute here (buffer 0 / 1), not relative to the current buffer
+    B200GEO_CUDA(cudaIpcGetMemHandle(&h, g->buf[which]));
+    memcpy(handle64, &h, sizeof(h));
+    return B200GEO_OK;
+}
+
+int b200geo_grid_ipc_open(b200geo_grid *g, int side, int which, const void *handle64)
+{
+    if (!g || !handle64 || (side != 0 && side != 1) || (which != 0 && which != 1))
+        return fail(B200GEO_ERR_INVALID, "bad argument");
+    B200GEO_CUDA(cudaSetDevice(g->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, sizeof(h));
+    void *p = 0;
+    B200GEO_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    g->peer_buf[side][which] = (char *)p;
+    return B200GEO_OK;
+}
+
+int b200geo_halo_push(b200geo_grid *g, int side, int width, void *stream)
+{
+    if (!g || (side != 0 && side != 1)) return fail(B200GEO_ERR_INVALID, "bad argument");
+    if (width < 1 || width > g->g[2] || width > g->d[2]) return fail(B200GEO_ERR_INVALID, "bad halo width");
+    // both ranks step in lock step, so the neighbour's current buffer has the same index as ours
+    char *peer = g->peer_buf[side][g->cur];
+    if (!peer) return fail(B200GEO_ERR_LOGIC, "no peer buffer opened on this side");
+    B200GEO_CUDA(cudaSetDevice(g->device));
+    for (int m = 0; m < g->n; ++m) {
+        const MemberLayout& L = g->m[m];
+        int64_t src_plane = side == 0 ? g->g[2] : g->g[2] + g->d[2] - width;
+        // our low-side boundary lands in the neighbour's high-side ghost planes and vice versa
+        int64_t dst_plane = side == 0 ? g->g[2] + g->d[2] : g->g[2] - width;
+        size_t bytes = (size_t)width * L.plane * L.elem;
+        B200GEO_CUDA(cudaMemcpyAsync(peer + L.offset + dst_plane * L.plane * L.elem,
+                                     g->buf[g->cur] + L.offset + src_plane * L.plane * L.elem,
+                                     bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    }
+    return B200GEO_OK;
+}
+
+int b200geo_stats_enable(b200geo_grid *g, int on)
+{
+    if (!g) return fail(B200GEO_ERR_INVALID, "null grid");
+    g->stats_on = on != 0;
+    return B200GEO_OK;
+}
+
+int b200geo_stats(b200geo_grid *g, double out[3])
+{
+    if (!g || !out) return fail(B200GEO_ERR_INVALID, "null argument");
+    out[0] = g->t_update;
+    out[1] = g->t_ghost;
+    out[2] = (double)g->sweeps;
+    return B200GEO_OK;
+}
+
+}

@@ -1,0 +1,82 @@
+// Internal definitions shared by the translation units of libb200geo.so.
+#ifndef B200GEO_CSRC_GRID_H
+#define B200GEO_CSRC_GRID_H
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+
+#include "../../include/b200geo.h"
+
+namespace b200geo {
+
+// Device layout of one member array (HBM): [nz + 2gz][ny + 2gy][pitch] elements, x fastest.
+// Every row starts on a 128-byte boundary and interior cell x = 0 sits exactly 128 bytes into
+// the row, so 128-bit vector accesses to interior cells are aligned and a warp's 32 x 16 B
+// requests coalesce into whole 128 B lines. Low-side x ghosts live at the end of the 128 B
+// lead-in, high-side x ghosts directly behind the interior.
+struct MemberLayout {
+    int elem;            // bytes per element
+    int lead;            // elements before interior x = 0 in a row (= 128 / elem)
+    int64_t pitch;       // elements per row
+    int64_t plane;       // elements per plane = pitch * (ny + 2gy)
+    int64_t origin;      // element offset of interior (0,0,0)
+    int64_t bytes;       // bytes of the whole member array (256 B aligned)
+    int64_t offset;      // byte offset of the member inside a buffer
+    int edge_offset;     // byte offset of this member inside an aggregated cell
+};
+
+struct Box {
+    int x0, y0, z0, x1, y1, z1;  // half open, interior coordinates
+};
+
+}
+
+struct b200geo_grid {
+    b200geo_grid_desc desc;
+    int device;
+    int n, g[3], d[3];
+    b200geo::MemberLayout m[B200GEO_MAX_MEMBERS];
+    int64_t buffer_bytes;
+    char *buf[2];        // buf[cur] = current, buf[cur ^ 1] = scratch
+    int cur;
+    int cell_bytes;
+    unsigned char edge[8 * B200GEO_MAX_MEMBERS];
+    int peer_valid[2];   // valid ghost planes per z side (PEER sides)
+    char *peer_buf[2][2];   // [side][which]: IPC-mapped buffers of the z neighbours
+    bool stats_on;
+    cudaEvent_t ev[4];
+    double t_update, t_ghost;
+    uint64_t sweeps;
+    void *scratch;       // small device scratch (streak lists etc.)
+    size_t scratch_bytes;
+
+    char *member_ptr(int member, int which) const { return buf[cur ^ which] + m[member].offset; }
+};
+
+namespace b200geo {
+
+int fail(int status, const std::string& msg);
+int check_cuda(cudaError_t e, const char *what);
+void count_launch(uint64_t n = 1);
+
+// kernel families (one translation unit each)
+int sweep_jacobi(b200geo_grid *g, int kind, const Box& box, cudaStream_t s);
+int sweep_gol(b200geo_grid *g, const Box& box, cudaStream_t s);
+int sweep_lbm(b200geo_grid *g, const Box& box, bool store_macroscopic, cudaStream_t s);
+
+// ghost maintenance and (de)serialisation kernels (region.cu)
+int fill_edge(b200geo_grid *g, int which, cudaStream_t s);
+int refresh_wrap(b200geo_grid *g, cudaStream_t s);
+int copy_region(b200geo_grid *g, const int32_t *streaks, int n_streaks, char *dev_buf, int64_t count,
+                bool save, int which, cudaStream_t s);
+
+#define B200GEO_CUDA(call)                                                    \
+    do {                                                                      \
+        int b200geo_rc_ = ::b200geo::check_cuda((call), #call);               \
+        if (b200geo_rc_ != 0) return b200geo_rc_;                             \
+    } while (0)
+
+}
+
+#endif

@@ -1,0 +1,176 @@
+// D3Q19 BGK lattice-Boltzmann sweep, f32, 24-member SoA cell (B200GEO_KERNEL_LBM_D3Q19).
+//
+// Replaces the per-cell update of the reference's LBM model (pull scheme + six wall states,
+// src/examples/latticeboltzmann/main.cpp:62-229; SoA member set of
+// src/testbed/performancetests/main.cpp:1796-1986) for the cell in oracle/models/lbm.h. The
+// expression trees below are that cell's, term by term; this translation unit is compiled with
+// -fmad=false and the oracle with -ffp-contract=off, so results are bit-identical.
+//
+// Roofline: HBM-bound. 19 populations read + 19 written = 152 B per lattice update, + 4 B of
+// state read; density / velocity (16 B) are written only on the last sweep of a b200geo_step
+// call unless params says otherwise (the reference cell stores them every step, 168 B/update) —
+// nothing reads them on the update path, so the final grid is identical either way.
+// Wall cells copy themselves and overwrite five populations; their density/velocity and every
+// cell's state never change, so they are not rewritten (both buffers hold them from the load).
+#include "grid.h"
+
+namespace b200geo {
+
+namespace {
+
+enum { C, N, E, W, S, T, B, NW, SW, NE, SE, TW, BW, TE, BE, TN, BN, TS, BS, DENSITY, VELX, VELY, VELZ, STATE };
+enum { LIQUID, WEST_NOSLIP, EAST_NOSLIP, TOP, BOTTOM, NORTH_ACC, SOUTH_NOSLIP };
+
+#define GET_COMP(X, Y, Z, COMP) src[(int64_t)(COMP) * mstride + i + (X) + (Y) * pitch + (Z) * plane]
+#define PUT(COMP) dst[(int64_t)(COMP) * mstride + i]
+#define SQR(X) ((X) * (X))
+
+template<bool MACRO>
+__global__ void __launch_bounds__(128)
+lbm_kernel(const float *__restrict__ src, float *__restrict__ dst, int64_t pitch, int64_t plane,
+           int64_t mstride, Box box)
+{
+    const int x = box.x0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= box.x1) return;
+    const int y = box.y0 + blockIdx.y, z = box.z0 + blockIdx.z;
+    const int64_t i = (int64_t)z * plane + (int64_t)y * pitch + x;
+
+    const int s = __float_as_int(GET_COMP(0, 0, 0, STATE));
+    if (s != LIQUID) {
+#pragma unroll
+        for (int m = 0; m < 19; ++m) PUT(m) = GET_COMP(0, 0, 0, m);
+        switch (s) {
+        case WEST_NOSLIP:
+            PUT(E)  = GET_COMP(1, 0,  0, W);
+            PUT(NE) = GET_COMP(1, 1,  0, SW);
+            PUT(SE) = GET_COMP(1,-1,  0, NW);
+            PUT(TE) = GET_COMP(1, 0,  1, BW);
+            PUT(BE) = GET_COMP(1, 0, -1, TW);
+            break;
+        case EAST_NOSLIP:
+            PUT(W)  = GET_COMP(-1, 0, 0, E);
+            PUT(NW) = GET_COMP(-1, 0, 1, SE);
+            PUT(SW) = GET_COMP(-1,-1, 0, NE);
+            PUT(TW) = GET_COMP(-1, 0, 1, BE);
+            PUT(BW) = GET_COMP(-1, 0,-1, TE);
+            break;
+        case TOP:
+            PUT(B)  = GET_COMP(0, 0,-1, T);
+            PUT(BE) = GET_COMP(1, 0,-1, TW);
+            PUT(BW) = GET_COMP(-1,0,-1, TE);
+            PUT(BN) = GET_COMP(0, 1,-1, TS);
+            PUT(BS) = GET_COMP(0,-1,-1, TN);
+            break;
+        case BOTTOM:
+            PUT(T)  = GET_COMP(0, 0, 1, B);
+            PUT(TE) = GET_COMP(1, 0, 1, BW);
+            PUT(TW) = GET_COMP(-1,0, 1, BE);
+            PUT(TN) = GET_COMP(0, 1, 1, BS);
+            PUT(TS) = GET_COMP(0,-1, 1, BN);
+            break;
+        case NORTH_ACC: {
+            const float w_1 = 0.01f;
+            PUT(S)  = GET_COMP(0,-1, 0, N);
+            PUT(SE) = GET_COMP(1,-1, 0, NW) + 6.0f * w_1 * 0.1f;
+            PUT(SW) = GET_COMP(-1,-1,0, NE) - 6.0f * w_1 * 0.1f;
+            PUT(TS) = GET_COMP(0,-1, 1, BN);
+            PUT(BS) = GET_COMP(0,-1,-1, TN);
+            break;
+        }
+        case SOUTH_NOSLIP:
+            PUT(N)  = GET_COMP(0, 1, 0, S);
+            PUT(NE) = GET_COMP(1, 1, 0, SW);
+            PUT(NW) = GET_COMP(-1,1, 0, SE);
+            PUT(TN) = GET_COMP(0, 1, 1, BS);
+            PUT(BN) = GET_COMP(0, 1,-1, TS);
+            break;
+        }
+        return;
+    }
+
+    const float omega     = (float)(1.0 / 1.7);
+    const float omega_trm = 1.0f - omega;
+    const float omega_w0  = (float)(3.0 * 1.0 / 3.0)  * omega;
+    const float omega_w1  = (float)(3.0 * 1.0 / 18.0) * omega;
+    const float omega_w2  = (float)(3.0 * 1.0 / 36.0) * omega;
+    const float one_third = (float)(1.0 / 3.0);
+
+    // every population is read exactly once (pull scheme)
+    const float fC  = GET_COMP( 0, 0, 0, C);
+    const float fN  = GET_COMP( 0,-1, 0, N),  fS  = GET_COMP( 0, 1, 0, S);
+    const float fE  = GET_COMP(-1, 0, 0, E),  fW  = GET_COMP( 1, 0, 0, W);
+    const float fT  = GET_COMP( 0, 0,-1, T),  fB  = GET_COMP( 0, 0, 1, B);
+    const float fNW = GET_COMP( 1,-1, 0, NW), fSW = GET_COMP( 1, 1, 0, SW);
+    const float fNE = GET_COMP(-1,-1, 0, NE), fSE = GET_COMP(-1, 1, 0, SE);
+    const float fTW = GET_COMP( 1, 0,-1, TW), fBW = GET_COMP( 1, 0, 1, BW);
+    const float fTE = GET_COMP(-1, 0,-1, TE), fBE = GET_COMP(-1, 0, 1, BE);
+    const float fTN = GET_COMP( 0,-1,-1, TN), fBN = GET_COMP( 0,-1, 1, BN);
+    const float fTS = GET_COMP( 0, 1,-1, TS), fBS = GET_COMP( 0, 1, 1, BS);
+
+    float velX, velY, velZ;
+    velX = fE + fNE + fSE + fTE + fBE;
+    velY = fN + fNW + fTN + fBN;
+    velZ = fT + fTS + fTW;
+
+    const float rho = fC + fS + fW + fB + fSW + fBS + fBW + velX + velY + velZ;
+    velX = velX - fW - fNW - fSW - fTW - fBW;
+    velY = velY + fNE - fS - fSW - fSE - fTS - fBS;
+    velZ = velZ + fTN + fTE - fB - fBN - fBS - fBW - fBE;
+
+    if (MACRO) {
+        PUT(DENSITY) = rho;
+        PUT(VELX) = velX;
+        PUT(VELY) = velY;
+        PUT(VELZ) = velZ;
+    }
+
+    const float dir_indep_trm = one_third * rho - 0.5f * (velX * velX + velY * velY + velZ * velZ);
+
+    PUT(C)  = omega_trm * fC + omega_w0 * (dir_indep_trm);
+
+    PUT(NW) = omega_trm * fNW + omega_w2 * (dir_indep_trm - (velX - velY) + 1.5f * SQR(velX - velY));
+    PUT(SE) = omega_trm * fSE + omega_w2 * (dir_indep_trm + (velX - velY) + 1.5f * SQR(velX - velY));
+    PUT(NE) = omega_trm * fNE + omega_w2 * (dir_indep_trm + (velX + velY) + 1.5f * SQR(velX + velY));
+    PUT(SW) = omega_trm * fSW + omega_w2 * (dir_indep_trm - (velX + velY) + 1.5f * SQR(velX + velY));
+
+    PUT(TW) = omega_trm * fTW + omega_w2 * (dir_indep_trm - (velX - velZ) + 1.5f * SQR(velX - velZ));
+    PUT(BE) = omega_trm * fBE + omega_w2 * (dir_indep_trm + (velX - velZ) + 1.5f * SQR(velX - velZ));
+    PUT(TE) = omega_trm * fTE + omega_w2 * (dir_indep_trm + (velX + velZ) + 1.5f * SQR(velX + velZ));
+    PUT(BW) = omega_trm * fBW + omega_w2 * (dir_indep_trm - (velX + velZ) + 1.5f * SQR(velX + velZ));
+
+    PUT(TS) = omega_trm * fTS + omega_w2 * (dir_indep_trm - (velY - velZ) + 1.5f * SQR(velY - velZ));
+    PUT(BN) = omega_trm * fBN + omega_w2 * (dir_indep_trm + (velY - velZ) + 1.5f * SQR(velY - velZ));
+    PUT(TN) = omega_trm * fTN + omega_w2 * (dir_indep_trm + (velY + velZ) + 1.5f * SQR(velY + velZ));
+    PUT(BS) = omega_trm * fBS + omega_w2 * (dir_indep_trm - (velY + velZ) + 1.5f * SQR(velY + velZ));
+
+    PUT(N) = omega_trm * fN + omega_w1 * (dir_indep_trm + velY + 1.5f * SQR(velY));
+    PUT(S) = omega_trm * fS + omega_w1 * (dir_indep_trm - velY + 1.5f * SQR(velY));
+    PUT(E) = omega_trm * fE + omega_w1 * (dir_indep_trm + velX + 1.5f * SQR(velX));
+    PUT(W) = omega_trm * fW + omega_w1 * (dir_indep_trm - velX + 1.5f * SQR(velX));
+    PUT(T) = omega_trm * fT + omega_w1 * (dir_indep_trm + velZ + 1.5f * SQR(velZ));
+    PUT(B) = omega_trm * fB + omega_w1 * (dir_indep_trm - velZ + 1.5f * SQR(velZ));
+}
+
+#undef GET_COMP
+#undef PUT
+#undef SQR
+
+}
+
+int sweep_lbm(b200geo_grid *g, const Box& box, bool store_macroscopic, cudaStream_t s)
+{
+    const MemberLayout& L = g->m[0];
+    int64_t mstride = g->m[1].offset / 4;
+    const float *src = (const float *)g->member_ptr(0, 0) + L.origin;
+    float *dst = (float *)g->member_ptr(0, 1) + L.origin;
+    dim3 grid((box.x1 - box.x0 + 127) / 128, box.y1 - box.y0, box.z1 - box.z0);
+    if (grid.y > 65535 || grid.z > 65535) return fail(B200GEO_ERR_OUT_OF_RANGE, "grid dimension too large");
+    if (store_macroscopic)
+        lbm_kernel<true><<<grid, 128, 0, s>>>(src, dst, L.pitch, L.plane, mstride, box);
+    else
+        lbm_kernel<false><<<grid, 128, 0, s>>>(src, dst, L.pitch, L.plane, mstride, box);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "lbm sweep");
+}
+
+}

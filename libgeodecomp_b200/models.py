@@ -1,0 +1,71 @@
+"""Model bindings: the Python twin of B200KernelBinding<CELL> (include/libgeodecomp_b200/).
+
+A binding states what the reference learns from Cell::API (misc/apitraits.h:191-1168) and from
+LIBFLATARRAY_REGISTER_SOA — dimensionality, topology, stencil radius, nano steps, the SoA member
+table in registration order — plus which hand-written kernel family implements the cell's
+update()/updateLineX(). The cell classes themselves live in oracle/models/*.h.
+"""
+import numpy as np
+
+from . import capi
+
+
+class CellModel:
+    def __init__(self, name, dim, topology, members, kernel, edge=None, nano_steps=1, radius=1, ref_model=None):
+        self.name, self.dim, self.topology = name, dim, topology
+        self.members = [(n, np.dtype(t)) for n, t in members]
+        self.kernel, self.nano_steps, self.radius = kernel, nano_steps, radius
+        self.ref_model = ref_model or name.lower()
+        self.cell_dtype = np.dtype([(n, t) for n, t in self.members])
+        self.default_cell = np.zeros((), dtype=self.cell_dtype)
+        if edge:
+            for k, v in edge.items():
+                self.default_cell[k] = v
+
+    @property
+    def member_bytes(self):
+        return [t.itemsize for _, t in self.members]
+
+    @property
+    def wraps(self):
+        return self.topology == "torus"
+
+    def member_index(self, name):
+        for i, (n, _) in enumerate(self.members):
+            if n == name:
+                return i
+        raise ValueError("no member %r in %s" % (name, self.name))
+
+    def cell_to_bytes(self, cell):
+        c = np.zeros((), dtype=self.cell_dtype)
+        if isinstance(cell, np.void) or (isinstance(cell, np.ndarray) and cell.dtype == self.cell_dtype):
+            c = cell
+        elif isinstance(cell, dict):
+            c = self.default_cell.copy()
+            for k, v in cell.items():
+                c[k] = v
+        else:  # scalar for single-member cells, else a sequence in registration order
+            vals = cell if isinstance(cell, (tuple, list)) else (cell,)
+            for (n, _), v in zip(self.members, vals):
+                c[n] = v
+        return b"".join(np.asarray(c[n]).tobytes() for n, _ in self.members)
+
+
+_F64 = [("temp", "f8")]
+_LBM = [(n, "f4") for n in ["C", "N", "E", "W", "S", "T", "B", "NW", "SW", "NE", "SE", "TW", "BW", "TE", "BE",
+                            "TN", "BN", "TS", "BS", "density", "velocityX", "velocityY", "velocityZ"]] + [("state", "i4")]
+
+Jacobi6Cube = CellModel("Jacobi6Cube", 3, "cube", _F64, capi.KERNEL_JACOBI6)
+Jacobi6Torus = CellModel("Jacobi6Torus", 3, "torus", _F64, capi.KERNEL_JACOBI6)
+Jacobi7Cube = CellModel("Jacobi7Cube", 3, "cube", _F64, capi.KERNEL_JACOBI7)
+Jacobi7Torus = CellModel("Jacobi7Torus", 3, "torus", _F64, capi.KERNEL_JACOBI7)
+Jacobi27Cube = CellModel("Jacobi27Cube", 3, "cube", _F64, capi.KERNEL_JACOBI27)
+Jacobi27Torus = CellModel("Jacobi27Torus", 3, "torus", _F64, capi.KERNEL_JACOBI27)
+ConwayCube = CellModel("ConwayCube", 2, "cube", [("alive", "u1")], capi.KERNEL_GOL)
+ConwayTorus = CellModel("ConwayTorus", 2, "torus", [("alive", "u1")], capi.KERNEL_GOL)
+# edge cell = LBMCellF(): C = 1, density = 1 (oracle/models/lbm.h)
+LBMCellF = CellModel("LBMCellF", 3, "cube", _LBM, capi.KERNEL_LBM_D3Q19, edge={"C": 1.0, "density": 1.0},
+                     ref_model="lbm")
+
+ALL = {m.name: m for m in [Jacobi6Cube, Jacobi6Torus, Jacobi7Cube, Jacobi7Torus, Jacobi27Cube, Jacobi27Torus,
+                           ConwayCube, ConwayTorus, LBMCellF]}

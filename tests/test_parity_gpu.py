@@ -1,0 +1,112 @@
+"""Parity of the CUDA path (through the C ABI / B200Simulator) against the oracle.
+
+Bit-exact for every model: Jacobi has no a*b+c site, GoL is integer, and the LBM kernels are
+compiled -fmad=false against a -ffp-contract=off oracle (tolerance 0)."""
+import numpy as np
+import pytest
+
+from libgeodecomp_b200 import capi, models, synth
+from libgeodecomp_b200.simulator import B200Grid, B200Simulator, SimpleInitializer
+
+pytestmark = pytest.mark.gpu
+
+
+class MemberInit(SimpleInitializer):
+    def __init__(self, dims, steps, members, edge=None):
+        SimpleInitializer.__init__(self, dims, steps)
+        self.members, self.edge = members, edge
+
+    def grid(self, target):
+        if self.edge is not None:
+            target.setEdge(self.edge)
+        for name, arr in self.members.items():
+            target.loadMember(name, arr)
+
+
+def run_jacobi(kind, torus, shape, steps, edge=0.0):
+    nz, ny, nx = shape
+    data = synth.jacobi_grid(nx, ny, nz)
+    model = models.ALL["Jacobi%d%s" % (kind, "Torus" if torus else "Cube")]
+    sim = B200Simulator(MemberInit((nx, ny, nz), steps, {"temp": data}, edge=edge), model)
+    sim.run()
+    assert sim.getStep() == steps
+    return data, sim.getGrid().saveMember("temp")
+
+
+@pytest.mark.parametrize("kind", [6, 7, 27])
+@pytest.mark.parametrize("torus", [False, True])
+@pytest.mark.parametrize("shape", [(18, 20, 24), (7, 5, 3), (16, 33, 129), (1, 1, 1), (40, 24, 130)])
+def test_jacobi_bit_exact(oracle, kind, torus, shape):
+    data, got = run_jacobi(kind, torus, shape, 6, edge=0.25)
+    want = oracle.jacobi(kind, torus, data, 6, edge=0.25)
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("kind", [7, 27])
+def test_jacobi_config1_128cubed_100_steps(oracle, kind):
+    """BASELINE.json config 1: 128^3 double, 100 steps, Cube and the example's Torus."""
+    data, got = run_jacobi(kind, False, (128, 128, 128), 100)
+    assert np.array_equal(got, oracle.jacobi(kind, False, data, 100))
+
+
+def test_jacobi6_example_torus_128(oracle):
+    data, got = run_jacobi(6, True, (128, 128, 128), 30)
+    assert np.array_equal(got, oracle.jacobi(6, True, data, 30))
+
+
+@pytest.mark.parametrize("torus", [False, True])
+@pytest.mark.parametrize("shape", [(130, 150), (1, 1), (3, 17), (64, 2048), (100, 16), (37, 4099)])
+def test_gol_bit_exact(oracle, torus, shape):
+    ny, nx = shape
+    g = synth.gol_grid(nx, ny)
+    model = models.ConwayTorus if torus else models.ConwayCube
+    sim = B200Simulator(MemberInit((nx, ny), 20, {"alive": g}), model)
+    sim.run()
+    assert np.array_equal(sim.getGrid().saveMember("alive"), oracle.gol(torus, g, 20))
+
+
+def test_gol_2048_64_steps(oracle):
+    g = synth.gol_grid(2048, 2048)
+    sim = B200Simulator(MemberInit((2048, 2048), 64, {"alive": g}), models.ConwayCube)
+    sim.run()
+    assert np.array_equal(sim.getGrid().saveMember("alive"), oracle.gol(False, g, 64))
+
+
+def test_gol_alive_edge(oracle):
+    g = synth.gol_grid(70, 50)
+    sim = B200Simulator(MemberInit((70, 50), 9, {"alive": g}, edge=1), models.ConwayCube)
+    sim.run()
+    assert np.array_equal(sim.getGrid().saveMember("alive"), oracle.gol(False, g, 9, edge_alive=1))
+
+
+def lbm_members(raw):
+    out = {}
+    for m, (name, t) in enumerate(models.LBMCellF.members):
+        out[name] = raw[m].view(t)
+    return out
+
+
+@pytest.mark.parametrize("shape,steps", [((16, 18, 20), 12), ((5, 4, 3), 5), ((64, 64, 64), 100), ((24, 20, 130), 7)])
+def test_lbm_bit_exact(oracle, shape, steps):
+    nz, ny, nx = shape
+    raw = synth.lbm_grid(nx, ny, nz, noise=0.01)
+    sim = B200Simulator(MemberInit((nx, ny, nz), steps, lbm_members(raw)), models.LBMCellF)
+    sim.run()
+    want = oracle.lbm(raw, steps)
+    grid = sim.getGrid()
+    for m, (name, t) in enumerate(models.LBMCellF.members):
+        got = grid.saveMember(name)
+        assert np.array_equal(got.view(np.int32), want[m].view(np.int32)), name
+
+
+def test_lbm_macroscopics_every_step_equals_lazy(oracle):
+    raw = synth.lbm_grid(20, 12, 10, noise=0.01)
+    grid = B200Grid(models.LBMCellF, (20, 12, 10))
+    for name, arr in lbm_members(raw).items():
+        grid.loadMember(name, arr)
+    every = np.array([1], dtype=np.int32)
+    for _ in range(5):
+        grid.dev.step(capi.KERNEL_LBM_D3Q19, 1, params=every)
+    want = oracle.lbm(raw, 5)
+    for m, (name, t) in enumerate(models.LBMCellF.members):
+        assert np.array_equal(grid.saveMember(name).view(np.int32), want[m].view(np.int32)), name
