@@ -1,0 +1,387 @@
+#!/usr/bin/env python
+"""Benchmark of the cell-update hot path (BASELINE.json metric: GLUPS, % of HBM roofline).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload jacobi27|jacobi7|lbm|gol|jacobi7_128]
+  python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...     (N > 1)
+  python bench.py --impl reference ...      the reference's own CPU implementation (oracle/_ref)
+
+A bench "step" is one sweep of the update over the whole (per-rank) grid. The headline workload is
+BASELINE.json config 3 (Jacobi 27-point, 1024^3 f64 per GPU, slabs along z, halo exchange between
+slab neighbours; weak scaling: the global grid is 1024 x 1024 x 1024N). The grids (2 x 8.9 GB) are
+far larger than the 126 MB L2, so no explicit L2 flush is needed between timed iterations.
+
+value  = lattice updates of ALL ranks / max-over-ranks device time, inputs resident in HBM.
+e2e    = the same metric through the public API (StripedSimulator.run(): Initializer::grid from
+         PINNED HOST memory -> K steps -> Writer pulling the final grid back to host memory), all
+         host<->device copies inside the timed region; h2d/d2h bytes are per step (total / K).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {
+    # name: (model, per-rank dims (x, y, z), algorithmic bytes per update, dtype, ref model)
+    "jacobi27": ("Jacobi27Cube", (1024, 1024, 1024), 16, "f64", "jacobi27cube"),
+    "jacobi7": ("Jacobi7Cube", (1024, 1024, 1024), 16, "f64", "jacobi7cube"),
+    "jacobi7_128": ("Jacobi7Cube", (128, 128, 128), 16, "f64", "jacobi7cube"),
+    "lbm": ("LBMCellF", (512, 512, 512), 152, "f32", "lbm"),
+    "gol": ("ConwayCube", (16384, 16384), 2, "u8", "conwaycube"),
+}
+DESCRIPTION = {
+    "jacobi27": "Jacobi3D 27-point 1024^3 double per GPU, slab decomposition along z, halo exchange (BASELINE.json configs[2])",
+    "jacobi7": "Jacobi3D 7-point 1024^3 double per GPU, slab decomposition along z",
+    "jacobi7_128": "Jacobi3D 7-point 128^3 double (BASELINE.json configs[0], L2-resident)",
+    "lbm": "LBM D3Q19 BGK lid-driven cavity 512^3 float SoA per GPU (BASELINE.json configs[3])",
+    "gol": "Conway Game of Life 16384^2 char grid (BASELINE.json configs[1])",
+}
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.proc, self.lines, self.begin = index, None, [], 0
+
+    def mark_begin(self):
+        self.begin = len(self.lines)
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.thread.join(timeout=2)
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        lines = self.lines[self.begin:] or self.lines[-3:]
+        for line in lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx = float(parts[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def synth_members(workload, dims, z0, nz_total):
+    """Synthetic input for one rank as {member: dense array}; cheap enough for 1024^3."""
+    from libgeodecomp_b200 import models, synth
+    name = WORKLOADS[workload][0]
+    model = models.ALL[name]
+    if name.startswith("Jacobi"):
+        nx, ny, nz = dims
+        tile = min(nz, 32)   # generate a 32-plane block and repeat it along z (generation speed)
+        block = synth.jacobi_grid(nx, ny, tile, seed=42 + z0)
+        reps = (nz + tile - 1) // tile
+        return model, {"temp": np.concatenate([block] * reps, axis=0)[:nz]}
+    if name == "LBMCellF":
+        nx, ny, nz = dims
+        raw = synth.lbm_grid(nx, ny, nz, z0=z0, nz_total=nz_total)
+        return model, {n: raw[m].view(t) for m, (n, t) in enumerate(model.members)}
+    nx, ny = dims
+    tile = min(ny, 1024)
+    block = synth.gol_grid(nx, tile)
+    return model, {"alive": np.concatenate([block] * ((ny + tile - 1) // tile), axis=0)[:ny]}
+
+
+def run_cpu_reference(workload, steps, warmup, threads=None):
+    """Time the reference's own SerialSimulator/OpenMPSimulator (oracle/_ref) on a bounded sample of
+    the workload. Returns (glups, dict)."""
+    from oracle import oracle_py
+    from libgeodecomp_b200 import synth
+    model_name, dims, _, _, ref_model = WORKLOADS[workload]
+    cores = threads or os.cpu_count()
+    if workload in ("jacobi27", "jacobi7"):
+        sdims, sample = (1024, 1024, 32), "1024x1024x32 slab of the 1024^3 grid"
+        raw = synth.jacobi_grid(*sdims)
+    elif workload == "jacobi7_128":
+        sdims, sample = (128, 128, 128), "full 128^3 grid"
+        raw = synth.jacobi_grid(*sdims)
+    elif workload == "lbm":
+        sdims, sample = (512, 512, 8), "512x512x8 slab of the 512^3 grid"
+        raw = synth.lbm_grid(*sdims)
+    else:
+        sdims, sample = (16384, 256, 1), "16384x256 strip of the 16384^2 grid"
+        raw = synth.gol_grid(sdims[0], sdims[1])
+    if oracle_py.have_ref(ref_model):
+        if warmup:
+            oracle_py.run_ref(ref_model, raw, sdims, warmup, omp=True, threads=cores, want_output=False)
+        _, st = oracle_py.run_ref(ref_model, raw, sdims, steps, omp=True, threads=cores, want_output=False)
+        glups = st["glups_compute"]
+        info = {"kind": "reference", "cores": cores, "simulator": st["simulator"],
+                "sample": "%s x %d steps, reference OpenMPSimulator built from /root/reference, TimeCompute interval" % (sample, steps),
+                "seconds": st["time_compute_s"]}
+    else:
+        fn = {"jacobi27": lambda: oracle_py.jacobi(27, False, raw, steps),
+              "jacobi7": lambda: oracle_py.jacobi(7, False, raw, steps),
+              "jacobi7_128": lambda: oracle_py.jacobi(7, False, raw, steps),
+              "lbm": lambda: oracle_py.lbm(raw, steps),
+              "gol": lambda: oracle_py.gol(False, raw, steps)}[workload]
+        t0 = time.perf_counter()
+        fn()
+        dt = time.perf_counter() - t0
+        glups = 1e-9 * steps * float(np.prod(sdims)) / dt
+        info = {"kind": "port", "cores": cores, "sample": "%s x %d steps, C restatement (oracle/oracle.c, OpenMP)" % (sample, steps),
+                "seconds": dt}
+    info.update({"value": glups, "unit": "GLUPS"})
+    return glups, info
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    t0 = time.perf_counter()
+    glups, info = run_cpu_reference(args.workload, args.steps, args.warmup)
+    model_name, dims, _, dtype, _ = WORKLOADS[args.workload]
+    line = {
+        "impl": "reference", "metric": "GLUPS (giga lattice updates/s)", "value": glups, "unit": "GLUPS",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * info["seconds"] / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": dtype, "data": "synthetic",
+        "config": {"workload": DESCRIPTION[args.workload], "model": model_name,
+                   "note": "CPU reference on the host cores of this box; bounded sample, see cpu_baseline.sample"},
+        "cpu_baseline": info,
+        "e2e": {"value": glups, "unit": "GLUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "wall_s": time.perf_counter() - t0,
+    }
+    print(json.dumps(line))
+
+
+def bench_device(workload, args, rank, world, dist, torch, with_e2e=True, with_clocks=True):
+    """Returns a dict with value / roofline / e2e for one workload."""
+    from libgeodecomp_b200 import capi
+    from libgeodecomp_b200.simulator import SimpleInitializer, Writer
+    from libgeodecomp_b200.striping import StripedSimulator
+
+    model_name, dims, alg_bytes, dtype, _ = WORKLOADS[workload]
+    last = len(dims) - 1
+    gdims = list(dims)
+    gdims[last] = dims[last] * world
+    z0 = dims[last] * rank
+    model, members = synth_members(workload, dims, z0, gdims[last])
+    cells_rank = float(np.prod(dims))
+    cells_all = cells_rank * world
+    K, W = args.steps, args.warmup
+
+    # pinned host copies of this rank's input (e2e uploads come from these)
+    pinned = {}
+    for n, a in members.items():
+        t = torch.from_numpy(np.ascontiguousarray(a))
+        pinned[n] = t.pin_memory() if with_e2e else t
+    members = None
+    host_out = {n: torch.empty_like(t).pin_memory() if with_e2e else None for n, t in pinned.items()}
+
+    class Init(SimpleInitializer):
+        def grid(self, target):
+            (o, d) = target.boundingBox()
+            for n, t in pinned.items():
+                target.loadMember(n, t.numpy(), origin=o)
+
+    class PullWriter(Writer):
+        """pulls the rank's final grid into pinned host memory at WRITER_ALL_DONE"""
+        def stepFinished(self, grid, step, event):
+            if event == 2:
+                for n, t in host_out.items():
+                    grid.saveMember(n, out=t.numpy())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sim = StripedSimulator(Init(gdims, K), model, rank=rank, world=world, ghost_width=args.ghost, device=torch.cuda.current_device(), dist=dist)
+    torch.cuda.synchronize()
+
+    # ---- device-resident throughput
+    sampler = ClockSampler(torch.cuda.current_device())
+    if with_clocks and rank == 0:
+        sampler.start()
+    sim.advance(W)
+    barrier()
+    sampler.mark_begin()
+    launches0 = capi.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    sim.advance(K)
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = capi.launch_count() - launches0
+    clocks = sampler.stop() if (with_clocks and rank == 0) else None
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = 1e-9 * cells_all * K / (1e-3 * ms)
+
+    # ---- dominant kernel alone (roofline): K sweeps without any exchange on a 1-rank-style step
+    peak, peak_src = peaks()
+    ev0.record()
+    n_roof = 0
+    while n_roof < K:
+        n = K - n_roof
+        if world > 1:   # no exchange here: the ghost planes are only declared valid (timing only)
+            n = min(n, sim.ghost_width)
+            for side in (0, 1):
+                if sim.grid.modes[last][side] == capi.GHOST_PEER:
+                    sim.grid.dev.halo_mark_valid(side, sim.ghost_width)
+        sim.grid.dev.step(model.kernel, n_steps=n)
+        n_roof += n
+    ev1.record()
+    torch.cuda.synchronize()
+    kms = ev0.elapsed_time(ev1) / n_roof
+    achieved = alg_bytes * cells_rank / (1e-3 * kms) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "kernel_ms": kms, "algorithmic_bytes_per_update": alg_bytes,
+                "peak_source": peak_src, "kernel": model_name}
+
+    out = {"workload": workload, "value": value, "ms_per_step": ms / K, "roofline": roofline, "dtype": dtype,
+           "gpu_launches": launches, "clocks": clocks, "model": model_name, "dims_per_gpu": list(dims),
+           "global_dims": gdims, "halo_bytes_per_exchange": sim.halo.bytes_per_exchange,
+           "ghost_width": sim.ghost_width}
+
+    # ---- end to end through the public API with host buffers
+    if with_e2e:
+        sim.writers = [PullWriter("", 1 << 30)]
+        barrier()
+        t0 = time.perf_counter()
+        ev0.record()
+        sim.run()
+        ev1.record()
+        barrier()
+        wall = time.perf_counter() - t0
+        e_ms = ev0.elapsed_time(ev1)
+        t = torch.tensor([max(e_ms, 0.0)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e_ms = float(t.item())
+        grid_bytes = sum(int(x.numel()) * x.element_size() for x in pinned.values())
+        out["e2e"] = {"value": 1e-9 * cells_all * K / (1e-3 * e_ms), "unit": "GLUPS",
+                      "h2d_bytes_per_step": grid_bytes * world / K, "d2h_bytes_per_step": grid_bytes * world / K,
+                      "ms_per_run": e_ms, "wall_ms_rank0": 1e3 * wall,
+                      "what": "StripedSimulator.run(): Initializer::grid from pinned host memory -> %d steps -> "
+                              "Writer pulls the final grid to pinned host memory" % K}
+    del sim
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200geo", choices=["b200geo", "reference"])
+    ap.add_argument("--workload", default="jacobi27", choices=sorted(WORKLOADS))
+    ap.add_argument("--ghost", type=int, default=1, help="ghost zone width = steps between halo exchanges (N > 1)")
+    ap.add_argument("--no-others", action="store_true", help="skip the secondary workloads (configs 0, 1, 3)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+
+    if args.impl == "reference":
+        reference_arm(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the b200geo hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    t_start = time.perf_counter()
+
+    main_res = bench_device(args.workload, args, rank, world, dist if world > 1 else None, torch)
+
+    others = []
+    if not args.no_others:
+        for w in ["jacobi7", "lbm", "gol", "jacobi7_128"]:
+            if w == args.workload:
+                continue
+            if world > 1 and w in ("gol", "jacobi7_128", "jacobi7"):
+                continue
+            r = bench_device(w, args, rank, world, dist if world > 1 else None, torch,
+                             with_e2e=(w in ("gol", "jacobi7_128")), with_clocks=False)
+            others.append({k: r[k] for k in ("workload", "value", "ms_per_step", "roofline", "dtype", "dims_per_gpu",
+                                             "global_dims", "gpu_launches") if k in r} | ({"e2e": r["e2e"]} if "e2e" in r else {}))
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        try:
+            _, cpu = run_cpu_reference(args.workload, 10, 1)
+        except Exception as e:  # the baseline is reported, never required for the GPU number
+            cpu = {"value": None, "unit": "GLUPS", "cores": os.cpu_count(), "kind": "reference", "sample": "failed: %r" % (e,)}
+
+    if rank == 0:
+        line = {
+            "metric": "GLUPS (giga lattice updates/s)", "value": main_res["value"], "unit": "GLUPS",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": main_res["ms_per_step"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": main_res["dtype"],
+            "data": "synthetic",
+            "config": {"workload": DESCRIPTION[args.workload], "model": main_res["model"],
+                       "dims_per_gpu": main_res["dims_per_gpu"], "global_dims": main_res["global_dims"],
+                       "partition": "z-slabs x%d" % world, "ghost_width": main_res["ghost_width"],
+                       "halo_bytes_per_exchange_per_rank": main_res["halo_bytes_per_exchange"],
+                       "l2": "grids (2 x %.1f GB per GPU) >> 126 MB L2, no flush needed" %
+                             (float(np.prod(main_res["dims_per_gpu"])) * {"f64": 8, "f32": 96, "u8": 1}[main_res["dtype"]] / 1e9)},
+            "roofline": main_res["roofline"], "e2e": main_res.get("e2e"), "gpu_launches": main_res["gpu_launches"],
+            "clocks": main_res["clocks"],
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        if others:
+            line["others"] = others
+        line["wall_s"] = time.perf_counter() - t_start
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

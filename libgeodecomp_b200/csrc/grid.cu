@@ -242,8 +242,19 @@ int b200geo_grid_load_member(b200geo_grid *g, int member, const int32_t origin[3
     if (!valid_box(g, origin, dim)) return fail(B200GEO_ERR_INVALID, "box outside the grid");
     B200GEO_CUDA(cudaSetDevice(g->device));
     int rc = member_copy(g, member, origin, dim, const_cast<void *>(src), location, true, 0, (cudaStream_t)stream);
-    if (rc == 0 && both)
-        rc = member_copy(g, member, origin, dim, const_cast<void *>(src), location, true, 1, (cudaStream_t)stream);
+    if (rc == 0 && both) {
+        // second buffer: device-to-device copy of the same box, not a second trip over PCIe
+        const MemberLayout& L = g->m[member];
+        cudaMemcpy3DParms p;
+        memset(&p, 0, sizeof(p));
+        size_t pitch = (size_t)L.pitch * L.elem;
+        p.srcPtr = make_cudaPitchedPtr(g->member_ptr(member, 0), pitch, pitch, g->d[1] + 2 * g->g[1]);
+        p.dstPtr = make_cudaPitchedPtr(g->member_ptr(member, 1), pitch, pitch, g->d[1] + 2 * g->g[1]);
+        p.srcPos = p.dstPos = make_cudaPos((size_t)(L.lead + origin[0]) * L.elem, origin[1] + g->g[1], origin[2] + g->g[2]);
+        p.extent = make_cudaExtent((size_t)dim[0] * L.elem, dim[1], dim[2]);
+        p.kind = cudaMemcpyDeviceToDevice;
+        if (dim[0] > 0 && dim[1] > 0 && dim[2] > 0) rc = check_cuda(cudaMemcpy3DAsync(&p, (cudaStream_t)stream), "cudaMemcpy3DAsync");
+    }
     return rc;
 }
 
