@@ -93,6 +93,12 @@ int b200geo_grid_create(const b200geo_grid_desc *desc, int device, b200geo_grid 
         if ((desc->ghost_mode[i][0] == B200GEO_GHOST_WRAP) != (desc->ghost_mode[i][1] == B200GEO_GHOST_WRAP))
             return fail(B200GEO_ERR_INVALID, "WRAP must be set on both sides of an axis");
     }
+    for (int m = 0; m < desc->n_members; ++m) {
+        int e = desc->member_bytes[m];
+        if (e != 1 && e != 2 && e != 4 && e != 8)
+            return fail(B200GEO_ERR_INVALID, "member size must be 1, 2, 4 or 8 bytes");
+        if (desc->ghost[0] > 128 / e) return fail(B200GEO_ERR_INVALID, "x ghost wider than the 128-byte lead-in");
+    }
     B200GEO_CUDA(cudaSetDevice(device));
 
     b200geo_grid *g = new (std::nothrow) b200geo_grid();

@@ -125,7 +125,7 @@ class B200Grid:
             ghost[last] = int(ghost_z)
         if z_modes is not None:
             modes[last] = list(z_modes)
-        engine = engine or capi
+        self.engine = engine = engine or capi
         self.dev = engine.DeviceGrid(self.dims, model.member_bytes, ghost=ghost, ghost_mode=modes, device=device)
         self.ghost, self.modes = ghost, modes
         self.setEdge(model.default_cell)
@@ -169,7 +169,7 @@ class B200Grid:
         for m, (n, t) in enumerate(self.model.members):
             v = np.zeros(1, dtype=t)
             self.dev.save_member(m, v, self._local3(coord), (1, 1, 1))
-            capi.sync()
+            self.engine.sync()
             out[n] = v[0]
         return out
 
@@ -178,7 +178,7 @@ class B200Grid:
         for m, (n, t) in enumerate(self.model.members):
             v = np.zeros(length, dtype=t)
             self.dev.save_member(m, v, self._local3(origin), (length, 1, 1))
-            capi.sync()
+            self.engine.sync()
             out[n] = v
         return out
 
@@ -210,7 +210,7 @@ class B200Grid:
         if out is None:
             out = np.empty(tuple(d[:self.model.dim])[::-1], dtype=t)
         self.dev.save_member(m, out, o, d, location=location)
-        capi.sync()
+        self.engine.sync()
         return out
 
     def _streaks3(self, streaks):
@@ -232,7 +232,7 @@ class B200Grid:
         n = int((st[:, 3] - st[:, 0]).sum())
         buf = np.zeros(n * self.model.cell_dtype.itemsize, dtype=np.uint8)
         self.dev.save_region(st, buf)
-        capi.sync()
+        self.engine.sync()
         return buf
 
     def loadRegion(self, buf, streaks):
@@ -242,7 +242,7 @@ class B200Grid:
         if buf.size != n * self.model.cell_dtype.itemsize:
             raise ValueError("buffer size does not match region")
         self.dev.load_region(st, buf)
-        capi.sync()
+        self.engine.sync()
 
     def to_raw(self):
         """whole interior as the member-major byte stream (one dense array per member)."""

@@ -1,0 +1,57 @@
+"""Worker for test_striping_gloo.py: one rank of a world_size-N gloo job on CPU."""
+import os
+import sys
+
+import numpy as np
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import cpu_engine  # noqa: E402
+from libgeodecomp_b200 import models, synth  # noqa: E402
+from libgeodecomp_b200.simulator import SimpleInitializer  # noqa: E402
+from libgeodecomp_b200.striping import StripedSimulator, slab_bounds  # noqa: E402
+from oracle import oracle_py  # noqa: E402
+
+
+class SlabInit(SimpleInitializer):
+    """initialises only the cells inside target.boundingBox() (io/initializer.h:38-44)"""
+
+    def __init__(self, data, steps, edge):
+        SimpleInitializer.__init__(self, data.shape[::-1], steps)
+        self.data, self.edge = data, edge
+
+    def grid(self, target):
+        (ox, oy, oz), (dx, dy, dz) = target.boundingBox()
+        target.setEdge(self.edge)
+        target.loadMember("temp", self.data[oz:oz + dz, oy:oy + dy, ox:ox + dx], origin=(ox, oy, oz))
+
+
+def main():
+    dist.init_process_group("gloo")
+    rank, world = dist.get_rank(), dist.get_world_size()
+    out_path = sys.argv[1]
+    failures = []
+    for kind, ghost, steps, shape in [(7, 1, 5, (12, 9, 10)), (27, 3, 7, (16, 6, 8)), (6, 2, 6, (13, 5, 4)), (27, 4, 9, (12, 4, 4))]:
+        nz, ny, nx = shape
+        data = synth.jacobi_grid(nx, ny, nz, seed=kind)
+        model = models.ALL["Jacobi%dCube" % kind]
+        sim = StripedSimulator(SlabInit(data, steps, 0.75), model, rank=rank, world=world, ghost_width=ghost,
+                               dist=dist, engine=cpu_engine)
+        sim.run()
+        assert sim.getStep() == steps
+        b = slab_bounds(nz, world)
+        mine = sim.getGrid().saveMember("temp")
+        want = oracle_py.jacobi(kind, False, data, steps, edge=0.75)[b[rank]:b[rank + 1]]
+        if mine.shape != want.shape or not np.array_equal(mine, want):
+            failures.append("kind %d ghost %d rank %d" % (kind, ghost, rank))
+    with open("%s.%d" % (out_path, rank), "w") as f:
+        f.write("FAIL " + "; ".join(failures) if failures else "OK")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,56 @@
+"""Generates tests/golden/*.npz by running the REFERENCE's own SerialSimulator (oracle/_ref/lgd_ref_*,
+built from /root/reference by oracle/Makefile) on small seeded inputs. Run in the build container:
+
+    make -C oracle ref && python tests/golden/make_golden.py
+
+The fixtures hold input and output so the tests do not depend on the generator staying unchanged.
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from libgeodecomp_b200 import synth  # noqa: E402
+from oracle import oracle_py  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def main():
+    cases = {}
+    for kind in (6, 7, 27):
+        for topo in ("cube", "torus"):
+            for (nx, ny, nz, steps) in [(12, 10, 8, 5), (33, 5, 7, 3)]:
+                g = synth.jacobi_grid(nx, ny, nz, seed=100 + kind)
+                edge = 0.5 if topo == "cube" else None
+                out, _ = oracle_py.run_ref("jacobi%d%s" % (kind, topo), g, (nx, ny, nz), steps, edge=edge)
+                key = "jacobi%d_%s_%dx%dx%d_s%d" % (kind, topo, nx, ny, nz, steps)
+                cases[key + "_in"] = g
+                cases[key + "_out"] = out.view(np.float64).reshape(g.shape)
+    np.savez_compressed(os.path.join(HERE, "jacobi.npz"), **cases)
+
+    cases = {}
+    for topo in ("cube", "torus"):
+        for (nx, ny, steps) in [(40, 30, 12), (17, 9, 30), (160, 90, 40)]:
+            g = synth.gol_grid(nx, ny, seed=3)
+            out, _ = oracle_py.run_ref("conway" + topo, g, (nx, ny, 1), steps)
+            key = "gol_%s_%dx%d_s%d" % (topo, nx, ny, steps)
+            cases[key + "_in"] = g
+            cases[key + "_out"] = out.reshape(g.shape)
+    np.savez_compressed(os.path.join(HERE, "gol.npz"), **cases)
+
+    cases = {}
+    for (nx, ny, nz, steps) in [(10, 8, 6, 9), (16, 5, 4, 4)]:
+        raw = synth.lbm_grid(nx, ny, nz, noise=0.02)
+        out, _ = oracle_py.run_ref("lbm", raw, (nx, ny, nz), steps)
+        key = "lbm_%dx%dx%d_s%d" % (nx, ny, nz, steps)
+        cases[key + "_in"] = raw
+        cases[key + "_out"] = out.view(np.float32).reshape(raw.shape)
+    np.savez_compressed(os.path.join(HERE, "lbm.npz"), **cases)
+    print("golden fixtures written to", HERE)
+
+
+if __name__ == "__main__":
+    main()
