@@ -80,6 +80,10 @@ const char *b200geo_version(void);
 const char *b200geo_last_error(void);
 /* number of CUDA devices, or a negative status (no driver / no device). */
 int b200geo_device_count(void);
+/* Launch / tiling parameters by name (the role misc/cudasimulationfactory.h:28-33 BlockDimX/Y/Z
+ * play for the reference's CUDASimulator). Unknown keys -> B200GEO_ERR_INVALID. Keys:
+ * "jacobi.zchunk", "jacobi.prefetch", "gol.rows", "lbm.block". value < 0 restores the default. */
+int b200geo_set_tuning(const char *key, int value);
 /* number of kernels this library has launched so far in this process (bench.py: gpu_launches). */
 uint64_t b200geo_launch_count(void);
 

@@ -44,6 +44,7 @@ SYMBOLS = [
     ("b200geo_last_error", ctypes.c_char_p, []),
     ("b200geo_device_count", ctypes.c_int, []),
     ("b200geo_launch_count", ctypes.c_uint64, []),
+    ("b200geo_set_tuning", ctypes.c_int, [ctypes.c_char_p, ctypes.c_int]),
     ("b200geo_grid_create", ctypes.c_int, [ctypes.POINTER(GridDesc), ctypes.c_int, ctypes.POINTER(_vp)]),
     ("b200geo_grid_destroy", ctypes.c_int, [_vp]),
     ("b200geo_grid_buffer_bytes", ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_uint64)]),
@@ -269,6 +270,10 @@ def sync(stream=None):
 
 def device_count():
     return lib().b200geo_device_count()
+
+
+def set_tuning(key, value):
+    check(lib().b200geo_set_tuning(key.encode(), int(value)))
 
 
 def launch_count():

@@ -91,7 +91,8 @@ int sweep_gol(b200geo_grid *g, const Box& box, cudaStream_t s)
     int ny = box.y1 - box.y0;
     int gx = (groups + 127) / 128;
     int rows = 64;
-    while (rows > 8 && (int64_t)gx * ((ny + rows - 1) / rows) < 148 * 8) rows /= 2;
+    while (rows > 8 && (int64_t)gx * ((ny + rows - 1) / rows) < 148 * 96) rows /= 2;
+    if (g_tuning.gol_rows > 0) rows = g_tuning.gol_rows;
     dim3 grid(gx, (ny + rows - 1) / rows);
     if (grid.y > 65535) return fail(B200GEO_ERR_OUT_OF_RANGE, "grid dimension too large");
     gol_kernel<<<grid, 128, 0, s>>>(src, dst, L.pitch, box, xa, rows, g->d[0] + g->g[0]);

@@ -10,6 +10,8 @@
 
 namespace b200geo {
 
+static const Tuning g_tuning_default = {0, -1, 0, 128};
+Tuning g_tuning = g_tuning_default;
 static thread_local std::string g_last_error;
 static std::atomic<uint64_t> g_launches(0);
 
@@ -66,6 +68,18 @@ int b200geo_device_count(void)
     cudaError_t e = cudaGetDeviceCount(&n);
     if (e != cudaSuccess) return check_cuda(e, "cudaGetDeviceCount");
     return n;
+}
+
+int b200geo_set_tuning(const char *key, int value)
+{
+    if (!key) return fail(B200GEO_ERR_INVALID, "null key");
+    std::string k(key);
+    if (k == "jacobi.zchunk") g_tuning.jacobi_zchunk = value < 0 ? g_tuning_default.jacobi_zchunk : value;
+    else if (k == "jacobi.prefetch") g_tuning.jacobi_prefetch = value;
+    else if (k == "gol.rows") g_tuning.gol_rows = value < 0 ? g_tuning_default.gol_rows : value;
+    else if (k == "lbm.block") g_tuning.lbm_block = value < 0 ? g_tuning_default.lbm_block : value;
+    else return fail(B200GEO_ERR_INVALID, "unknown tuning key " + k);
+    return B200GEO_OK;
 }
 
 uint64_t b200geo_launch_count(void)

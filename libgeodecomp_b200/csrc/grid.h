@@ -56,6 +56,14 @@ struct b200geo_grid {
 
 namespace b200geo {
 
+struct Tuning {
+    int jacobi_zchunk;    // planes per CTA along z (0 = automatic)
+    int jacobi_prefetch;  // L2 prefetch distance in planes (0 = off, < 0 = per-kernel default)
+    int gol_rows;         // rows per CTA (0 = automatic)
+    int lbm_block;        // threads per CTA
+};
+extern Tuning g_tuning;
+
 int fail(int status, const std::string& msg);
 int check_cuda(cudaError_t e, const char *what);
 void count_launch(uint64_t n = 1);

@@ -22,6 +22,12 @@ __device__ __forceinline__ double2 ld2(const double *p)
     return *reinterpret_cast<const double2 *>(p);
 }
 
+// pull a future plane's line from HBM into L2 without tying up a register or a scoreboard slot
+__device__ __forceinline__ void prefetch_l2(const double *p)
+{
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
 // (W + C) + E for the two cells of a pair in row p (p points at the pair's first cell)
 __device__ __forceinline__ double2 row_sum(const double *p)
 {
@@ -45,7 +51,7 @@ __device__ __forceinline__ double2 plane_sum(const double *p, int64_t pitch)
 template<int KIND>
 __global__ void __launch_bounds__(256)
 jacobi_kernel(const double *__restrict__ src, double *__restrict__ dst, int64_t pitch, int64_t plane,
-              Box box, int xa, int zchunk)
+              Box box, int xa, int zchunk, int pf, int zlast)
 {
     const int x = xa + 2 * (blockIdx.x * blockDim.x + threadIdx.x);
     const int y = box.y0 + blockIdx.y * blockDim.y + threadIdx.y;
@@ -60,6 +66,7 @@ jacobi_kernel(const double *__restrict__ src, double *__restrict__ dst, int64_t 
     if (KIND == 27) {
         double2 pm = plane_sum(p - plane, pitch), pc = plane_sum(p, pitch);
         for (int z = zb; z < ze; ++z, p += plane, q += plane) {
+            if (pf && z + pf <= zlast) prefetch_l2(p + (int64_t)pf * plane);
             double2 pp = plane_sum(p + plane, pitch);
             double2 r;
             r.x = ((pm.x + pc.x) + pp.x) * (1.0 / 27.0);
@@ -73,6 +80,7 @@ jacobi_kernel(const double *__restrict__ src, double *__restrict__ dst, int64_t 
     } else {
         double2 zm = ld2(p - plane), c = ld2(p);
         for (int z = zb; z < ze; ++z, p += plane, q += plane) {
+            if (pf && z + pf <= zlast) prefetch_l2(p + (int64_t)pf * plane);
             double2 zp = ld2(p + plane);
             double2 ym = ld2(p - pitch), yp = ld2(p + pitch);
             double w = p[-1], e = p[2];
@@ -109,12 +117,15 @@ int sweep_jacobi(b200geo_grid *g, int kind, const Box& box, cudaStream_t s)
     // enough z chunks for >= 8 CTAs per SM, but long enough to amortise the two-plane prologue
     int zchunk = 32;
     while (zchunk > 4 && (int64_t)gx * gy * ((nz + zchunk - 1) / zchunk) < 148 * 8) zchunk /= 2;
+    if (g_tuning.jacobi_zchunk > 0) zchunk = g_tuning.jacobi_zchunk;
+    // measured on B200 (profiles/r1b_tuning.md): +14% for the 7-point kernel, nothing for the 27-point one
+    int pf = g_tuning.jacobi_prefetch >= 0 ? g_tuning.jacobi_prefetch : (kind == 27 ? 0 : 2), zlast = g->d[2] + g->g[2] - 1;
     dim3 grid(gx, gy, (nz + zchunk - 1) / zchunk);
     if (grid.y > 65535 || grid.z > 65535) return fail(B200GEO_ERR_OUT_OF_RANGE, "grid dimension too large");
     switch (kind) {
-    case 6: jacobi_kernel<6><<<grid, block, 0, s>>>(src, dst, L.pitch, L.plane, box, xa, zchunk); break;
-    case 7: jacobi_kernel<7><<<grid, block, 0, s>>>(src, dst, L.pitch, L.plane, box, xa, zchunk); break;
-    default: jacobi_kernel<27><<<grid, block, 0, s>>>(src, dst, L.pitch, L.plane, box, xa, zchunk); break;
+    case 6: jacobi_kernel<6><<<grid, block, 0, s>>>(src, dst, L.pitch, L.plane, box, xa, zchunk, pf, zlast); break;
+    case 7: jacobi_kernel<7><<<grid, block, 0, s>>>(src, dst, L.pitch, L.plane, box, xa, zchunk, pf, zlast); break;
+    default: jacobi_kernel<27><<<grid, block, 0, s>>>(src, dst, L.pitch, L.plane, box, xa, zchunk, pf, zlast); break;
     }
     count_launch();
     return check_cuda(cudaGetLastError(), "jacobi sweep");
