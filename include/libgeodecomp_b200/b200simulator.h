@@ -1,0 +1,518 @@
+/* Header-only C++ façade: the drop-in boundary for existing LibGeoDecomp user code.
+ *
+ *   B200KernelBinding<CELL>  states which hand-written kernel family implements CELL::update /
+ *                            CELL::updateLineX and where CELL's members live (the SoA member table
+ *                            LIBFLATARRAY_REGISTER_SOA would generate, in registration order).
+ *   B200Grid<CELL>           a GridBase<CELL, DIM> (storage/gridbase.h:71-309) backed by the
+ *                            device-resident SoA grid of libb200geo.so — what Initializers, Writers
+ *                            and Steerers are handed; plays the role of CUDASoAGrid
+ *                            (storage/cudasoagrid.h:116).
+ *   B200Simulator<CELL>      a MonolithicSimulator<CELL> (parallelization/monolithicsimulator.h:17)
+ *                            with the event protocol of SerialSimulator
+ *                            (parallelization/serialsimulator.h:48-187); replaces CUDASimulator
+ *                            (parallelization/cudasimulator.h:298) for bound cells.
+ *
+ * Compiles against the UNCHANGED reference headers (-I<reference>/src -I<reference>/lib/libflatarray/include)
+ * and include/b200geo.h; links libb200geo.so. User models, Initializers, Writers and Steerers are
+ * used as they are; the only addition a user makes is one B200GEO_BIND_CELL line per model.
+ * Status codes of the C ABI are mapped to the reference's exceptions.
+ */
+#ifndef LIBGEODECOMP_B200_B200SIMULATOR_H
+#define LIBGEODECOMP_B200_B200SIMULATOR_H
+
+#include <libgeodecomp/io/initializer.h>
+#include <libgeodecomp/io/steerer.h>
+#include <libgeodecomp/io/writer.h>
+#include <libgeodecomp/misc/apitraits.h>
+#include <libgeodecomp/parallelization/monolithicsimulator.h>
+#include <libgeodecomp/storage/gridbase.h>
+
+#include <cstddef>
+#include <cstring>
+#include <new>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../b200geo.h"
+
+namespace LibGeoDecomp {
+
+/* One entry per SoA member, in registration order. */
+struct B200Member {
+    std::size_t offsetInCell;  /* offsetof(CELL, member) */
+    int bytes;                 /* sizeof(member) */
+};
+
+template<typename CELL>
+struct B200KernelBinding;      /* specialise with B200GEO_BIND_CELL */
+
+#define B200GEO_MEMBER_ENTRY(CELL, MEMBER) \
+    { offsetof(CELL, MEMBER), (int)sizeof(((CELL *)0)->MEMBER) },
+
+/* B200GEO_BIND_CELL(Cell, B200GEO_KERNEL_JACOBI7, B200GEO_MEMBER_ENTRY(Cell, temp)) */
+#define B200GEO_BIND_CELL(CELL, KERNEL_ID, ...)                                         \
+    namespace LibGeoDecomp {                                                            \
+    template<> struct B200KernelBinding<CELL> {                                         \
+        static int kernel() { return KERNEL_ID; }                                       \
+        static std::vector<B200Member> members()                                        \
+        {                                                                               \
+            B200Member tab[] = { __VA_ARGS__ };                                         \
+            return std::vector<B200Member>(tab, tab + sizeof(tab) / sizeof(tab[0]));    \
+        }                                                                               \
+    };                                                                                  \
+    }
+
+namespace B200Helpers {
+
+inline void check(int rc)
+{
+    if (rc >= 0) {
+        return;
+    }
+    std::string msg = b200geo_last_error();
+    switch (rc) {
+    case B200GEO_ERR_INVALID:
+        throw std::invalid_argument(msg);
+    case B200GEO_ERR_LOGIC:
+        throw std::logic_error(msg);
+    case B200GEO_ERR_OUT_OF_RANGE:
+        throw std::out_of_range(msg);
+    case B200GEO_ERR_NOMEM:
+        throw std::bad_alloc();
+    default:
+        throw std::runtime_error(msg.find("CUDA error") == 0 ? msg : "CUDA error: " + msg);
+    }
+}
+
+template<int DIM>
+inline void toStreak4(const Streak<DIM>& s, const Coord<DIM>& origin, int32_t *out)
+{
+    out[0] = s.origin[0] - origin[0];
+    out[1] = DIM > 1 ? s.origin[1] - origin[1] : 0;
+    out[2] = DIM > 2 ? s.origin[2] - origin[2] : 0;
+    out[3] = s.endX - origin[0];
+}
+
+}
+
+template<typename CELL>
+class B200Grid : public GridBase<CELL, APITraits::SelectTopology<CELL>::Value::DIM>
+{
+public:
+    typedef typename APITraits::SelectTopology<CELL>::Value Topology;
+    typedef typename APITraits::SelectStencil<CELL>::Value Stencil;
+    static const int DIM = Topology::DIM;
+    typedef GridBase<CELL, DIM> Base;
+
+    explicit B200Grid(const CoordBox<DIM>& box = CoordBox<DIM>(), const CELL& edgeCell = CELL(), int device = 0) :
+        Base(box.dimensions),
+        box(box),
+        edgeCell(edgeCell),
+        device(device),
+        handle(0),
+        members(B200KernelBinding<CELL>::members())
+    {
+        cellBytes = 0;
+        for (std::size_t m = 0; m < members.size(); ++m) {
+            cellBytes += members[m].bytes;
+        }
+        create();
+    }
+
+    virtual ~B200Grid()
+    {
+        b200geo_grid_destroy(handle);
+    }
+
+    b200geo_grid *raw()
+    {
+        return handle;
+    }
+
+    virtual void resize(const CoordBox<DIM>& newBox)
+    {
+        b200geo_grid_destroy(handle);
+        handle = 0;
+        box = newBox;
+        this->topoDimensions = newBox.dimensions;
+        create();
+    }
+
+    virtual void set(const Coord<DIM>& coord, const CELL& cell)
+    {
+        set(Streak<DIM>(coord, coord.x() + 1), &cell);
+    }
+
+    virtual void set(const Streak<DIM>& streak, const CELL *cells)
+    {
+        int n = streak.length();
+        if (n <= 0) {
+            return;
+        }
+        std::vector<char> buf((std::size_t)n * cellBytes);
+        std::size_t off = 0;
+        for (std::size_t m = 0; m < members.size(); ++m) {
+            for (int i = 0; i < n; ++i) {
+                std::memcpy(&buf[off + (std::size_t)i * members[m].bytes],
+                            reinterpret_cast<const char*>(cells + i) + members[m].offsetInCell, members[m].bytes);
+            }
+            off += (std::size_t)n * members[m].bytes;
+        }
+        int32_t s[4];
+        B200Helpers::toStreak4(streak, box.origin, s);
+        // both buffers: SerialSimulator initialises curGrid and newGrid alike (serialsimulator.h:54-57)
+        B200Helpers::check(b200geo_grid_load_region(handle, s, 1, buf.data(), B200GEO_HOST, 1, 0));
+    }
+
+    virtual CELL get(const Coord<DIM>& coord) const
+    {
+        CELL cell;
+        get(Streak<DIM>(coord, coord.x() + 1), &cell);
+        return cell;
+    }
+
+    virtual void get(const Streak<DIM>& streak, CELL *cells) const
+    {
+        int n = streak.length();
+        if (n <= 0) {
+            return;
+        }
+        std::vector<char> buf((std::size_t)n * cellBytes);
+        int32_t s[4];
+        B200Helpers::toStreak4(streak, box.origin, s);
+        B200Helpers::check(b200geo_grid_save_region(handle, s, 1, buf.data(), B200GEO_HOST, 0));
+        B200Helpers::check(b200geo_sync(0));
+        std::size_t off = 0;
+        for (std::size_t m = 0; m < members.size(); ++m) {
+            for (int i = 0; i < n; ++i) {
+                std::memcpy(reinterpret_cast<char*>(cells + i) + members[m].offsetInCell,
+                            &buf[off + (std::size_t)i * members[m].bytes], members[m].bytes);
+            }
+            off += (std::size_t)n * members[m].bytes;
+        }
+    }
+
+    virtual void setEdge(const CELL& cell)
+    {
+        edgeCell = cell;
+        std::vector<char> buf(cellBytes);
+        std::size_t off = 0;
+        for (std::size_t m = 0; m < members.size(); ++m) {
+            std::memcpy(&buf[off], reinterpret_cast<const char*>(&edgeCell) + members[m].offsetInCell, members[m].bytes);
+            off += members[m].bytes;
+        }
+        B200Helpers::check(b200geo_grid_set_edge(handle, buf.data(), 0));
+    }
+
+    virtual const CELL& getEdge() const
+    {
+        return edgeCell;
+    }
+
+    virtual CoordBox<DIM> boundingBox() const
+    {
+        return box;
+    }
+
+    /* member-major byte stream, byte-compatible with SoAGrid::saveRegion (storage/soagrid.h:523-547) */
+    virtual void saveRegion(std::vector<char> *buffer, const Region<DIM>& region, const Coord<DIM>& offset = Coord<DIM>()) const
+    {
+        std::vector<int32_t> streaks = flatten(region, offset);
+        buffer->resize(region.size() * cellBytes);
+        B200Helpers::check(b200geo_grid_save_region(handle, streaks.data(), (int)(streaks.size() / 4), buffer->data(), B200GEO_HOST, 0));
+        B200Helpers::check(b200geo_sync(0));
+    }
+
+    virtual void loadRegion(const std::vector<char>& buffer, const Region<DIM>& region, const Coord<DIM>& offset = Coord<DIM>())
+    {
+        if (buffer.size() != region.size() * cellBytes) {
+            throw std::invalid_argument("buffer size does not match region");
+        }
+        std::vector<int32_t> streaks = flatten(region, offset);
+        B200Helpers::check(b200geo_grid_load_region(handle, streaks.data(), (int)(streaks.size() / 4), buffer.data(), B200GEO_HOST, 1, 0));
+        B200Helpers::check(b200geo_sync(0));
+    }
+
+    /* the hot path: n sweeps + swaps on the device (SerialSimulator::nanoStep, serialsimulator.h:132-139) */
+    void update(unsigned firstNanoStep, unsigned sweeps)
+    {
+        B200Helpers::check(b200geo_step(handle, B200KernelBinding<CELL>::kernel(), 0, firstNanoStep, sweeps, 0));
+    }
+
+    void sync() const
+    {
+        B200Helpers::check(b200geo_sync(0));
+    }
+
+protected:
+    virtual void saveMemberImplementation(
+        char *target,
+        MemoryLocation::Location targetLocation,
+        const Selector<CELL>& selector,
+        const typename Region<DIM>::StreakIterator& begin,
+        const typename Region<DIM>::StreakIterator& end) const
+    {
+        int m = findMember(selector);
+        for (typename Region<DIM>::StreakIterator i = begin; i != end; ++i) {
+            int n = i->length();
+            if (m >= 0) {
+                int32_t s[4], o[3], d[3] = {n, 1, 1};
+                B200Helpers::toStreak4(*i, box.origin, s);
+                o[0] = s[0]; o[1] = s[1]; o[2] = s[2];
+                int loc = targetLocation == MemoryLocation::HOST ? B200GEO_HOST : B200GEO_CUDA_DEVICE;
+                B200Helpers::check(b200geo_grid_save_member(handle, m, o, d, target, loc, 0));
+            } else {
+                if (targetLocation != MemoryLocation::HOST) {
+                    throw std::logic_error("B200Grid: filtered selectors are only supported for host targets");
+                }
+                std::vector<CELL> cells(n);
+                get(*i, cells.data());
+                selector.copyMemberOut(cells.data(), MemoryLocation::HOST, target, MemoryLocation::HOST, n);
+            }
+            target += selector.sizeOfExternal() * n;
+        }
+        sync();
+    }
+
+    virtual void loadMemberImplementation(
+        const char *source,
+        MemoryLocation::Location sourceLocation,
+        const Selector<CELL>& selector,
+        const typename Region<DIM>::StreakIterator& begin,
+        const typename Region<DIM>::StreakIterator& end)
+    {
+        int m = findMember(selector);
+        for (typename Region<DIM>::StreakIterator i = begin; i != end; ++i) {
+            int n = i->length();
+            if (m >= 0) {
+                int32_t s[4], o[3], d[3] = {n, 1, 1};
+                B200Helpers::toStreak4(*i, box.origin, s);
+                o[0] = s[0]; o[1] = s[1]; o[2] = s[2];
+                int loc = sourceLocation == MemoryLocation::HOST ? B200GEO_HOST : B200GEO_CUDA_DEVICE;
+                B200Helpers::check(b200geo_grid_load_member(handle, m, o, d, source, loc, 1, 0));
+            } else {
+                if (sourceLocation != MemoryLocation::HOST) {
+                    throw std::logic_error("B200Grid: filtered selectors are only supported for host sources");
+                }
+                std::vector<CELL> cells(n);
+                get(*i, cells.data());
+                selector.copyMemberIn(source, MemoryLocation::HOST, cells.data(), MemoryLocation::HOST, n);
+                set(*i, cells.data());
+            }
+            source += selector.sizeOfExternal() * n;
+        }
+        sync();
+    }
+
+private:
+    CoordBox<DIM> box;
+    CELL edgeCell;
+    int device;
+    b200geo_grid *handle;
+    std::vector<B200Member> members;
+    int cellBytes;
+
+    void create()
+    {
+        b200geo_grid_desc desc;
+        std::memset(&desc, 0, sizeof(desc));
+        for (int i = 0; i < 3; ++i) {
+            bool used = i < DIM;
+            desc.dim[i] = used ? box.dimensions[i] : 1;
+            desc.ghost[i] = used ? Stencil::RADIUS : 0;
+            int mode = (used && Topology::wrapsAxis(i)) ? B200GEO_GHOST_WRAP : B200GEO_GHOST_EDGE;
+            desc.ghost_mode[i][0] = desc.ghost_mode[i][1] = mode;
+        }
+        if (members.size() > B200GEO_MAX_MEMBERS) {
+            throw std::out_of_range("too many SoA members");
+        }
+        desc.n_members = (int)members.size();
+        for (std::size_t m = 0; m < members.size(); ++m) {
+            desc.member_bytes[m] = members[m].bytes;
+        }
+        B200Helpers::check(b200geo_grid_create(&desc, device, &handle));
+        setEdge(edgeCell);
+    }
+
+    std::vector<int32_t> flatten(const Region<DIM>& region, const Coord<DIM>& offset) const
+    {
+        std::vector<int32_t> streaks;
+        streaks.reserve(region.numStreaks() * 4);
+        for (typename Region<DIM>::StreakIterator i = region.beginStreak(); i != region.endStreak(); ++i) {
+            Streak<DIM> s = *i;
+            s.origin += offset;
+            s.endX += offset.x();
+            int32_t v[4];
+            B200Helpers::toStreak4(s, box.origin, v);
+            streaks.insert(streaks.end(), v, v + 4);
+        }
+        return streaks;
+    }
+
+    /* plain pointer-to-member selectors of a bound member map straight onto one device array */
+    int findMember(const Selector<CELL>& selector) const
+    {
+        if (selector.sizeOfExternal() != selector.sizeOfMember() || selector.arity() != 1) {
+            return -1;
+        }
+        CELL probe = CELL();
+        for (std::size_t m = 0; m < members.size(); ++m) {
+            if ((std::size_t)members[m].bytes != selector.sizeOfMember()) {
+                continue;
+            }
+            /* identify the member by round-tripping a byte pattern through the selector */
+            CELL c = probe;
+            std::vector<char> pattern(members[m].bytes);
+            for (int b = 0; b < members[m].bytes; ++b) {
+                pattern[b] = (char)(0x5a + b);
+            }
+            std::memcpy(reinterpret_cast<char*>(&c) + members[m].offsetInCell, pattern.data(), members[m].bytes);
+            std::vector<char> out(members[m].bytes);
+            selector.copyMemberOut(&c, MemoryLocation::HOST, out.data(), MemoryLocation::HOST, 1);
+            if (std::memcmp(out.data(), pattern.data(), members[m].bytes) == 0) {
+                return (int)m;
+            }
+        }
+        return -1;
+    }
+};
+
+template<typename CELL>
+class B200Simulator : public MonolithicSimulator<CELL>
+{
+public:
+    typedef typename MonolithicSimulator<CELL>::Topology Topology;
+    typedef typename MonolithicSimulator<CELL>::WriterVector WriterVector;
+    typedef typename Steerer<CELL>::SteererFeedback SteererFeedback;
+    typedef B200Grid<CELL> GridType;
+    typedef GridBase<CELL, Topology::DIM> GridBaseType;
+    static const int DIM = Topology::DIM;
+    static const unsigned NANO_STEPS = APITraits::SelectNanoSteps<CELL>::VALUE;
+
+    using MonolithicSimulator<CELL>::chronometer;
+    using MonolithicSimulator<CELL>::getStep;
+    using MonolithicSimulator<CELL>::initializer;
+    using MonolithicSimulator<CELL>::gridDim;
+    using MonolithicSimulator<CELL>::steerers;
+    using MonolithicSimulator<CELL>::stepNum;
+    using MonolithicSimulator<CELL>::writers;
+
+    explicit B200Simulator(Initializer<CELL> *init, int device = 0) :
+        MonolithicSimulator<CELL>(init),
+        grid(CoordBox<DIM>(Coord<DIM>(), init->gridBox().dimensions), CELL(), device)
+    {
+        stepNum = init->startStep();
+        simArea << CoordBox<DIM>(Coord<DIM>(), init->gridBox().dimensions);
+        // both device buffers receive the initial state (serialsimulator.h:54-57)
+        initializer->grid(&grid);
+    }
+
+    /* one step, exactly like the reference (serialsimulator.h:70-93) */
+    virtual void step()
+    {
+        SteererFeedback feedback;
+        step(&feedback, false);
+    }
+
+    virtual void run()
+    {
+        initializer->grid(&grid);
+        stepNum = initializer->startStep();
+        for (unsigned i = 0; i < steerers.size(); i++) {
+            steerers[i]->setRegion(simArea);
+        }
+
+        SteererFeedback feedback;
+        handleInput(STEERER_INITIALIZED, &feedback);
+        handleOutput(WRITER_INITIALIZED);
+
+        for (; stepNum < initializer->maxSteps();) {
+            if (feedback.simulationEnded()) {
+                break;
+            }
+            step(&feedback, fuseSteps);
+        }
+
+        handleInput(STEERER_ALL_DONE, &feedback);
+        grid.sync();
+    }
+
+    virtual const GridBaseType *getGrid()
+    {
+        grid.sync();
+        return &grid;
+    }
+
+protected:
+    GridType grid;
+    Region<DIM> simArea;
+
+    void step(SteererFeedback *feedback, bool fuse)
+    {
+        TimeTotal t(&chronometer);
+        handleInput(STEERER_NEXT_STEP, feedback);
+
+        // inside run(): fuse every step up to the next observable event (writer / steerer period,
+        // maxSteps) into one engine call; with no plugins due this is the whole remaining run
+        unsigned steps = fuse ? stepsToNextEvent() : 1;
+        {
+            TimeCompute t(&chronometer);
+            grid.update(0, steps * NANO_STEPS);
+            if (steps > 1 || !writers.empty()) {
+                grid.sync();
+            }
+        }
+        stepNum += steps;
+
+        WriterEvent event = WRITER_STEP_FINISHED;
+        if (stepNum == initializer->maxSteps()) {
+            event = WRITER_ALL_DONE;
+        }
+        handleOutput(event);
+    }
+
+    unsigned stepsToNextEvent() const
+    {
+        unsigned max = initializer->maxSteps();
+        unsigned n = (stepNum < max) ? (max - stepNum) : 1;
+        for (unsigned i = 0; i < writers.size(); ++i) {
+            unsigned p = writers[i]->getPeriod();
+            n = (std::min)(n, p - stepNum % p);
+        }
+        for (unsigned i = 0; i < steerers.size(); ++i) {
+            unsigned p = steerers[i]->getPeriod();
+            n = (std::min)(n, p - stepNum % p);
+        }
+        return n > 0 ? n : 1;
+    }
+
+    void handleOutput(WriterEvent event)
+    {
+        TimeOutput t(&chronometer);
+        for (unsigned i = 0; i < writers.size(); i++) {
+            if ((event != WRITER_STEP_FINISHED) || ((getStep() % writers[i]->getPeriod()) == 0)) {
+                writers[i]->stepFinished(grid, getStep(), event);
+            }
+        }
+    }
+
+    void handleInput(SteererEvent event, SteererFeedback *feedback)
+    {
+        TimeInput t(&chronometer);
+        for (unsigned i = 0; i < steerers.size(); ++i) {
+            if ((event != STEERER_NEXT_STEP) || (stepNum % steerers[i]->getPeriod() == 0)) {
+                steerers[i]->nextStep(&grid, simArea, gridDim, getStep(), event, 0, true, feedback);
+            }
+        }
+    }
+
+public:
+    /* run() fuses the steps between two plugin events into one engine call (no observable
+     * difference: plugins see the same (step, event) sequence); set to false for one call per step. */
+    bool fuseSteps = true;
+};
+
+}
+
+#endif

@@ -1,0 +1,274 @@
+/* Drop-in test of the C++ façade: the SAME user models (oracle/models/*.h), the reference's own
+ * Initializer / MockWriter / MockSteerer / Selector / Region classes, and for every case the
+ * reference's SerialSimulator running beside B200Simulator in one process. Compiled HERE against
+ * /root/reference (tests/facade/Makefile) — the binary travels to the GPU box and is run by
+ * tests/test_facade_gpu.py. Exit code 0 = all checks passed. */
+#include <libgeodecomp/misc/testcell.h>
+#include <libgeodecomp/io/mocksteerer.h>
+#include <libgeodecomp/io/mockwriter.h>
+#include <libgeodecomp/io/simpleinitializer.h>
+#include <libgeodecomp/parallelization/serialsimulator.h>
+#include <libgeodecomp/storage/soagrid.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <iostream>
+
+#include "bindings.h"
+
+using namespace LibGeoDecomp;
+using namespace b200models;
+
+static int failures = 0;
+#define CHECK(COND)                                                                     \
+    do {                                                                                \
+        if (!(COND)) {                                                                  \
+            ++failures;                                                                 \
+            std::printf("FAILED %s:%d: %s\n", __FILE__, __LINE__, #COND);              \
+        }                                                                               \
+    } while (0)
+
+static uint64_t splitmix(uint64_t x)
+{
+    uint64_t z = x + 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+static double uniform(uint64_t i)
+{
+    return (double)(splitmix(i) >> 11) * (1.0 / 9007199254740992.0);
+}
+
+template<typename CELL> struct Seed;
+template<typename CELL> struct SeedJacobi {
+    static CELL make(uint64_t i) { return CELL(uniform(i)); }
+    static CELL edge() { return CELL(0.25); }
+};
+template<> struct Seed<Jacobi6Cube> : SeedJacobi<Jacobi6Cube> {};
+template<> struct Seed<Jacobi6Torus> : SeedJacobi<Jacobi6Torus> {};
+template<> struct Seed<Jacobi7Cube> : SeedJacobi<Jacobi7Cube> {};
+template<> struct Seed<Jacobi7Torus> : SeedJacobi<Jacobi7Torus> {};
+template<> struct Seed<Jacobi27Cube> : SeedJacobi<Jacobi27Cube> {};
+template<> struct Seed<Jacobi27Torus> : SeedJacobi<Jacobi27Torus> {};
+template<> struct Seed<ConwayCube> {
+    static ConwayCube make(uint64_t i) { return ConwayCube(uniform(i) < 0.35); }
+    static ConwayCube edge() { return ConwayCube(false); }
+};
+template<> struct Seed<ConwayTorus> {
+    static ConwayTorus make(uint64_t i) { return ConwayTorus(uniform(i) < 0.35); }
+    static ConwayTorus edge() { return ConwayTorus(false); }
+};
+
+template<typename CELL>
+class SeededInitializer : public SimpleInitializer<CELL>
+{
+public:
+    typedef typename SimpleInitializer<CELL>::Topology Topology;
+    static const int DIM = Topology::DIM;
+    using SimpleInitializer<CELL>::gridDimensions;
+
+    SeededInitializer(const Coord<DIM>& dim, unsigned steps) : SimpleInitializer<CELL>(dim, steps) {}
+
+    virtual void grid(GridBase<CELL, DIM> *ret)
+    {
+        CoordBox<DIM> box = ret->boundingBox();
+        ret->setEdge(Seed<CELL>::edge());
+        for (typename CoordBox<DIM>::Iterator i = box.begin(); i != box.end(); ++i) {
+            ret->set(*i, Seed<CELL>::make(i->toIndex(gridDimensions())));
+        }
+    }
+};
+
+class LBMInitializer : public SimpleInitializer<LBMCellF>
+{
+public:
+    LBMInitializer(const Coord<3>& dim, unsigned steps) : SimpleInitializer<LBMCellF>(dim, steps) {}
+
+    /* walls as src/examples/latticeboltzmann/main.cpp:249-287, rows written with set(Streak, cells) */
+    virtual void grid(GridBase<LBMCellF, 3> *ret)
+    {
+        CoordBox<3> box = ret->boundingBox();
+        Coord<3> size = gridDimensions();
+        std::vector<LBMCellF> row(box.dimensions.x());
+        for (int z = box.origin.z(); z < box.origin.z() + box.dimensions.z(); ++z) {
+            for (int y = box.origin.y(); y < box.origin.y() + box.dimensions.y(); ++y) {
+                for (int x = 0; x < box.dimensions.x(); ++x) {
+                    int gx = box.origin.x() + x;
+                    int s = LBMCellF::LIQUID;
+                    if (gx == 0) s = LBMCellF::WEST_NOSLIP;
+                    if (gx == size.x() - 1) s = LBMCellF::EAST_NOSLIP;
+                    if (y == 0) s = LBMCellF::SOUTH_NOSLIP;
+                    if (y == size.y() - 1) s = LBMCellF::NORTH_ACC;
+                    if (z == 0) s = LBMCellF::BOTTOM;
+                    if (z == size.z() - 1) s = LBMCellF::TOP;
+                    LBMCellF c(1.0f, s);
+                    uint64_t i = Coord<3>(gx, y, z).toIndex(size);
+                    c.N = 0.01f * (float)uniform(3 * i);
+                    c.TE = 0.01f * (float)uniform(3 * i + 1);
+                    c.BS = 0.01f * (float)uniform(3 * i + 2);
+                    row[x] = c;
+                }
+                ret->set(Streak<3>(Coord<3>(box.origin.x(), y, z), box.origin.x() + box.dimensions.x()), row.data());
+            }
+        }
+    }
+};
+
+template<typename CELL, typename INIT, int DIM>
+void compareWithSerialSimulator(const char *name, const Coord<DIM>& dim, unsigned steps)
+{
+    SerialSimulator<CELL> ref(new INIT(dim, steps));
+    B200Simulator<CELL> sim(new INIT(dim, steps));
+    ref.run();
+    sim.run();
+    CHECK(ref.getStep() == steps);
+    CHECK(sim.getStep() == steps);
+    const GridBase<CELL, DIM> *a = ref.getGrid();
+    const GridBase<CELL, DIM> *b = sim.getGrid();
+    CHECK(a->boundingBox() == b->boundingBox());
+    CHECK(a->getEdge() == b->getEdge());
+    long bad = 0;
+    CoordBox<DIM> box = a->boundingBox();
+    std::vector<CELL> ra(dim.x()), rb(dim.x());
+    for (typename CoordBox<DIM>::StreakIterator i = box.beginStreak(); i != box.endStreak(); ++i) {
+        a->get(*i, ra.data());
+        b->get(*i, rb.data());
+        for (int x = 0; x < dim.x(); ++x) {
+            if (!(ra[x] == rb[x])) ++bad;
+        }
+    }
+    CHECK(bad == 0);
+    std::printf("%-16s %s: %ld differing cells after %u steps\n", name, bad ? "MISMATCH" : "bit-exact", bad, steps);
+
+    // step() advances exactly one step, like the reference
+    B200Simulator<CELL> single(new INIT(dim, steps));
+    single.step();
+    CHECK(single.getStep() == 1);
+}
+
+template<typename SIM>
+void recordEvents(SIM& sim, std::vector<std::string> *log)
+{
+    typedef Jacobi7Cube CELL;
+    typedef MockWriter<CELL>::EventsStore WEvents;
+    typedef MockSteerer<CELL>::EventsStore SEvents;
+    SharedPtr<WEvents>::Type w1(new WEvents), w3(new WEvents);
+    SharedPtr<SEvents>::Type s2(new SEvents);
+    sim.addWriter(new MockWriter<CELL>(w1, 1));
+    sim.addWriter(new MockWriter<CELL>(w3, 3));
+    sim.addSteerer(new MockSteerer<CELL>(2, s2));
+    sim.run();
+    for (std::size_t i = 0; i < w1->size(); ++i) log->push_back("w1 " + (*w1)[i].toString());
+    for (std::size_t i = 0; i < w3->size(); ++i) log->push_back("w3 " + (*w3)[i].toString());
+    for (std::size_t i = 0; i < s2->size(); ++i) log->push_back("s2 " + (*s2)[i].toString());
+}
+
+void testEventProtocol()
+{
+    typedef Jacobi7Cube CELL;
+    std::vector<std::string> a, b;
+    {
+        SerialSimulator<CELL> ref(new SeededInitializer<CELL>(Coord<3>(8, 6, 5), 7));
+        recordEvents(ref, &a);
+    }
+    {
+        B200Simulator<CELL> sim(new SeededInitializer<CELL>(Coord<3>(8, 6, 5), 7));
+        recordEvents(sim, &b);
+    }
+    CHECK(a.size() > 10);
+    CHECK(a == b);
+    std::printf("event protocol: %zu writer/steerer events, %s\n", a.size(), a == b ? "identical" : "DIFFERENT");
+}
+
+void testRegionBytesMatchSoAGrid()
+{
+    typedef LBMCellF CELL;
+    Coord<3> dim(12, 7, 5);
+    CoordBox<3> box(Coord<3>(), dim);
+    SoAGrid<CELL, Topologies::Cube<3>::Topology> ref(box);
+    B200Grid<CELL> dev(box);
+    LBMInitializer init(dim, 1);
+    init.grid(&ref);
+    init.grid(&dev);
+
+    Region<3> region;
+    region << Streak<3>(Coord<3>(0, 0, 0), 12) << Streak<3>(Coord<3>(3, 2, 1), 9)
+           << Streak<3>(Coord<3>(11, 6, 4), 12) << Streak<3>(Coord<3>(1, 6, 3), 4);
+    std::vector<char> a, b;
+    ref.saveRegion(&a, region);
+    dev.saveRegion(&b, region);
+    CHECK(a.size() == b.size());
+    CHECK(a == b);
+
+    // loadRegion round trip: write the reference's bytes shifted by one cell in x, read back
+    Region<3> target;
+    target << Streak<3>(Coord<3>(2, 3, 2), 8);
+    Region<3> source;
+    source << Streak<3>(Coord<3>(3, 2, 1), 9);
+    std::vector<char> chunk;
+    ref.saveRegion(&chunk, source);
+    dev.loadRegion(chunk, target);
+    ref.loadRegion(chunk, target);
+    std::vector<char> c, d;
+    ref.saveRegion(&c, target);
+    dev.saveRegion(&d, target);
+    CHECK(c == d);
+    CHECK(ref.get(Coord<3>(4, 3, 2)) == dev.get(Coord<3>(4, 3, 2)));
+
+    bool thrown = false;
+    try {
+        std::vector<char> tooShort(3);
+        dev.loadRegion(tooShort, target);
+    } catch (const std::invalid_argument&) {
+        thrown = true;
+    }
+    CHECK(thrown);
+
+    // Selector-based member I/O (GridBase::saveMember / loadMember, storage/gridbase.h:217-261)
+    Selector<CELL> sel(&CELL::density, "density");
+    std::vector<float> da(region.size()), db(region.size());
+    ref.saveMember(da.data(), MemoryLocation::HOST, sel, region);
+    dev.saveMember(db.data(), MemoryLocation::HOST, sel, region);
+    CHECK(da == db);
+    for (std::size_t i = 0; i < da.size(); ++i) da[i] = 3.0f + i;
+    ref.loadMember(da.data(), MemoryLocation::HOST, sel, region);
+    dev.loadMember(da.data(), MemoryLocation::HOST, sel, region);
+    CHECK(ref.get(Coord<3>(5, 2, 1)) == dev.get(Coord<3>(5, 2, 1)));
+    bool wrongType = false;
+    try {
+        std::vector<double> wrong(region.size());
+        dev.saveMember(wrong.data(), MemoryLocation::HOST, sel, region);
+    } catch (const std::invalid_argument&) {
+        wrongType = true;
+    }
+    CHECK(wrongType);
+    std::printf("saveRegion/loadRegion/saveMember/loadMember vs SoAGrid: %s\n", (a == b && c == d) ? "byte-identical" : "DIFFERENT");
+}
+
+int main()
+{
+    try {
+        compareWithSerialSimulator<Jacobi7Cube, SeededInitializer<Jacobi7Cube>, 3>("Jacobi7Cube", Coord<3>(34, 9, 11), 9);
+        compareWithSerialSimulator<Jacobi7Torus, SeededInitializer<Jacobi7Torus>, 3>("Jacobi7Torus", Coord<3>(16, 5, 7), 6);
+        compareWithSerialSimulator<Jacobi27Cube, SeededInitializer<Jacobi27Cube>, 3>("Jacobi27Cube", Coord<3>(21, 10, 8), 7);
+        compareWithSerialSimulator<Jacobi27Torus, SeededInitializer<Jacobi27Torus>, 3>("Jacobi27Torus", Coord<3>(12, 6, 6), 5);
+        compareWithSerialSimulator<Jacobi6Cube, SeededInitializer<Jacobi6Cube>, 3>("Jacobi6Cube", Coord<3>(10, 12, 9), 8);
+        compareWithSerialSimulator<Jacobi6Torus, SeededInitializer<Jacobi6Torus>, 3>("Jacobi6Torus", Coord<3>(20, 6, 4), 8);
+        compareWithSerialSimulator<ConwayCube, SeededInitializer<ConwayCube>, 2>("ConwayCube", Coord<2>(70, 33), 25);
+        compareWithSerialSimulator<ConwayTorus, SeededInitializer<ConwayTorus>, 2>("ConwayTorus", Coord<2>(48, 20), 25);
+        compareWithSerialSimulator<LBMCellF, LBMInitializer, 3>("LBMCellF", Coord<3>(18, 12, 10), 15);
+        testEventProtocol();
+        testRegionBytesMatchSoAGrid();
+    } catch (const std::exception& e) {
+        std::printf("FAILED with exception: %s\n", e.what());
+        return 2;
+    }
+    if (failures) {
+        std::printf("%d check(s) FAILED\n", failures);
+        return 1;
+    }
+    std::printf("facade_test: all checks passed\n");
+    return 0;
+}
