@@ -99,7 +99,8 @@ int b200geo_grid_create(const b200geo_grid_desc *desc, int device, b200geo_grid 
             int mode = desc->ghost_mode[i][s];
             if (mode < B200GEO_GHOST_EDGE || mode > B200GEO_GHOST_PEER)
                 return fail(B200GEO_ERR_INVALID, "bad ghost mode");
-            if (mode == B200GEO_GHOST_PEER && i != 2)
+            int slab = (desc->dim[2] == 1 && desc->ghost[2] == 0) ? 1 : 2;
+            if (mode == B200GEO_GHOST_PEER && i != slab)
                 return fail(B200GEO_ERR_LOGIC, "PEER ghost layers are supported on the last axis only (slab partition)");
             if (mode == B200GEO_GHOST_WRAP && desc->ghost[i] > desc->dim[i])
                 return fail(B200GEO_ERR_INVALID, "wrap ghost wider than the grid");
@@ -125,6 +126,7 @@ int b200geo_grid_create(const b200geo_grid_desc *desc, int device, b200geo_grid 
         g->d[i] = desc->dim[i];
         g->g[i] = desc->ghost[i];
     }
+    g->slab_axis = (g->d[2] == 1 && g->g[2] == 0) ? 1 : 2;
     int64_t off = 0;
     int cell = 0;
     for (int m = 0; m < g->n; ++m) {
@@ -396,12 +398,14 @@ int b200geo_step(b200geo_grid *g, int kernel, const void *params, uint32_t first
     if (g->stats_on) cudaEventRecord(g->ev[0], s);
     for (uint32_t t = 0; t < n_steps; ++t) {
         Box box = {0, 0, 0, g->d[0], g->d[1], g->d[2]};
+        const int a = g->slab_axis;
         for (int side = 0; side < 2; ++side) {
-            if (g->desc.ghost_mode[2][side] != B200GEO_GHOST_PEER) continue;
+            if (g->desc.ghost_mode[a][side] != B200GEO_GHOST_PEER) continue;
             if (g->peer_valid[side] < 1)
                 return fail(B200GEO_ERR_LOGIC, "ghost zone exhausted: exchange halos before stepping");
             int extra = g->peer_valid[side] - 1;
-            if (side == 0) box.z0 -= extra; else box.z1 += extra;
+            if (a == 2) { if (side == 0) box.z0 -= extra; else box.z1 += extra; }
+            else        { if (side == 0) box.y0 -= extra; else box.y1 += extra; }
         }
         rc = refresh_wrap(g, s);
         if (rc) return rc;
@@ -409,7 +413,7 @@ int b200geo_step(b200geo_grid *g, int kernel, const void *params, uint32_t first
         if (rc) return rc;
         g->cur ^= 1;
         for (int side = 0; side < 2; ++side)
-            if (g->desc.ghost_mode[2][side] == B200GEO_GHOST_PEER) --g->peer_valid[side];
+            if (g->desc.ghost_mode[a][side] == B200GEO_GHOST_PEER) --g->peer_valid[side];
         ++g->sweeps;
     }
     if (g->stats_on) {
@@ -431,7 +435,8 @@ int b200geo_update_box(b200geo_grid *g, int kernel, const void *params, uint32_t
     if (rc) return rc;
     // the updated box may reach into PEER ghost planes but must leave one ring of readable cells
     for (int i = 0; i < 3; ++i) {
-        int lo = (i == 2) ? -(g->g[i] - 1) : 0, hi = g->d[i] + ((i == 2) ? g->g[i] - 1 : 0);
+        bool slab = i == g->slab_axis && g->g[i] > 0;
+        int lo = slab ? -(g->g[i] - 1) : 0, hi = g->d[i] + (slab ? g->g[i] - 1 : 0);
         if (dim[i] < 0 || origin[i] < lo || origin[i] + dim[i] > hi) return fail(B200GEO_ERR_INVALID, "box outside the updatable area");
     }
     B200GEO_CUDA(cudaSetDevice(g->device));
@@ -466,19 +471,20 @@ int b200geo_halo_block(const b200geo_grid *g, int member, int side, int kind, in
     if (!g || !ptr || !bytes) return fail(B200GEO_ERR_INVALID, "null argument");
     if (member < 0 || member >= g->n || (side != 0 && side != 1) || (kind != 0 && kind != 1))
         return fail(B200GEO_ERR_INVALID, "bad member/side/kind");
-    if (width < 1 || width > g->g[2] || width > g->d[2]) return fail(B200GEO_ERR_INVALID, "bad halo width");
+    const int a = g->slab_axis, gz = g->g[a], nz = g->d[a];
+    if (width < 1 || width > gz || width > nz) return fail(B200GEO_ERR_INVALID, "bad halo width");
     const MemberLayout& L = g->m[member];
-    int64_t zplane;  // padded plane index of the first plane of the block
-    if (kind == 0) zplane = side == 0 ? g->g[2] : g->g[2] + g->d[2] - width;
-    else           zplane = side == 0 ? g->g[2] - width : g->g[2] + g->d[2];
-    *ptr = g->member_ptr(member, 0) + zplane * L.plane * L.elem;
-    *bytes = (uint64_t)width * L.plane * L.elem;
+    int64_t zplane;  // padded slice index of the first slice of the block
+    if (kind == 0) zplane = side == 0 ? gz : gz + nz - width;
+    else           zplane = side == 0 ? gz - width : gz + nz;
+    *ptr = g->member_ptr(member, 0) + zplane * g->slice_elems(member) * L.elem;
+    *bytes = (uint64_t)width * g->slice_elems(member) * L.elem;
     return B200GEO_OK;
 }
 
 int b200geo_halo_mark_valid(b200geo_grid *g, int side, int width)
 {
-    if (!g || (side != 0 && side != 1) || width < 0 || width > g->g[2]) return fail(B200GEO_ERR_INVALID, "bad side/width");
+    if (!g || (side != 0 && side != 1) || width < 0 || width > g->g[g->slab_axis]) return fail(B200GEO_ERR_INVALID, "bad side/width");
     g->peer_valid[side] = width;
     return B200GEO_OK;
 }
@@ -510,19 +516,22 @@ int b200geo_grid_ipc_open(b200geo_grid *g, int side, int which, const void *hand
 int b200geo_halo_push(b200geo_grid *g, int side, int width, void *stream)
 {
     if (!g || (side != 0 && side != 1)) return fail(B200GEO_ERR_INVALID, "bad argument");
-    if (width < 1 || width > g->g[2] || width > g->d[2]) return fail(B200GEO_ERR_INVALID, "bad halo width");
+    const int a = g->slab_axis, gz = g->g[a], nz = g->d[a];
+    if (width < 1 || width > gz || width > nz) return fail(B200GEO_ERR_INVALID, "bad halo width");
     // both ranks step in lock step, so the neighbour's current buffer has the same index as ours
     char *peer = g->peer_buf[side][g->cur];
     if (!peer) return fail(B200GEO_ERR_LOGIC, "no peer buffer opened on this side");
     B200GEO_CUDA(cudaSetDevice(g->device));
     for (int m = 0; m < g->n; ++m) {
         const MemberLayout& L = g->m[m];
-        int64_t src_plane = side == 0 ? g->g[2] : g->g[2] + g->d[2] - width;
+        int64_t src_plane = side == 0 ? gz : gz + nz - width;
         // our low-side boundary lands in the neighbour's high-side ghost planes and vice versa
-        int64_t dst_plane = side == 0 ? g->g[2] + g->d[2] : g->g[2] - width;
-        size_t bytes = (size_t)width * L.plane * L.elem;
-        B200GEO_CUDA(cudaMemcpyAsync(peer + L.offset + dst_plane * L.plane * L.elem,
-                                     g->buf[g->cur] + L.offset + src_plane * L.plane * L.elem,
+        // (equal slab thickness on both sides is assumed for the peer's layout)
+        int64_t dst_plane = side == 0 ? gz + nz : gz - width;
+        int64_t slice = g->slice_elems(m);
+        size_t bytes = (size_t)width * slice * L.elem;
+        B200GEO_CUDA(cudaMemcpyAsync(peer + L.offset + dst_plane * slice * L.elem,
+                                     g->buf[g->cur] + L.offset + src_plane * slice * L.elem,
                                      bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
     }
     return B200GEO_OK;

@@ -36,6 +36,7 @@ struct b200geo_grid {
     b200geo_grid_desc desc;
     int device;
     int n, g[3], d[3];
+    int slab_axis;       // axis slabs are cut along: the last used axis (2, or 1 for 2-D grids)
     b200geo::MemberLayout m[B200GEO_MAX_MEMBERS];
     int64_t buffer_bytes;
     char *buf[2];        // buf[cur] = current, buf[cur ^ 1] = scratch
@@ -52,6 +53,8 @@ struct b200geo_grid {
     size_t scratch_bytes;
 
     char *member_ptr(int member, int which) const { return buf[cur ^ which] + m[member].offset; }
+    // elements per slice (plane, or row for 2-D grids) along the slab axis
+    int64_t slice_elems(int member) const { return slab_axis == 2 ? m[member].plane : m[member].pitch; }
 };
 
 namespace b200geo {

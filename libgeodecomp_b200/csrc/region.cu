@@ -105,9 +105,12 @@ int refresh_wrap(b200geo_grid *g, cudaStream_t s)
     for (int m = 0; m < g->n; ++m) {
         const MemberLayout& L = g->m[m];
         int lead = L.lead;
-        if (wx) {  // interior rows of every plane (ghost planes included: they may hold peer data)
-            launch_copy_box(g, m, lead + nx - gx, gy, 0, lead - gx, gy, 0, gx, ny, pz, s);
-            launch_copy_box(g, m, lead, gy, 0, lead + nx, gy, 0, gx, ny, pz, s);
+        if (wx) {  // interior rows of every plane (ghost planes included: they may hold peer data);
+                   // for 2-D slabs the PEER ghost ROWS hold peer data and need their x images as well
+            bool peer_rows = mode[1][0] == B200GEO_GHOST_PEER || mode[1][1] == B200GEO_GHOST_PEER;
+            int y0 = peer_rows ? 0 : gy, rows = peer_rows ? ny + 2 * gy : ny;
+            launch_copy_box(g, m, lead + nx - gx, y0, 0, lead - gx, y0, 0, gx, rows, pz, s);
+            launch_copy_box(g, m, lead, y0, 0, lead + nx, y0, 0, gx, rows, pz, s);
         }
         if (wy) {  // whole padded rows, so that the corners pick up the x images
             int w = nx + 2 * gx;

@@ -43,8 +43,11 @@ class HaloExchanger:
             return
         ops, keep = [], []
         nbytes = 0
-        # post receives first, then sends; one batched group = one NCCL launch
-        for side, peer in ((0, self.low), (1, self.high)):
+        # post receives first, then sends; one batched group = one NCCL launch. Messages between one
+        # pair of ranks match in posting order, and on a periodic 2-rank ring both neighbours are the
+        # same rank: a neighbour's LOW-side send (posted first) belongs in our HIGH ghost, so the
+        # high-side receive is posted first.
+        for side, peer in ((1, self.high), (0, self.low)):
             if peer is None:
                 continue
             for m in self.members:

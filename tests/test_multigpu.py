@@ -34,4 +34,5 @@ def test_striped_simulator_nccl(tmp_path, world):
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
     for rank in range(world):
-        assert open("%s.%d" % (out, rank)).read() == "OK"
+        content = open("%s.%d" % (out, rank)).read()
+        assert content == "OK", content

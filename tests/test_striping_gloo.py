@@ -49,4 +49,5 @@ def test_striped_simulator_matches_single_domain(tmp_path, world):
         logs.append(o)
     for rank, p in enumerate(procs):
         assert p.returncode == 0, logs[rank][-3000:]
-        assert open("%s.%d" % (out, rank)).read() == "OK"
+        content = open("%s.%d" % (out, rank)).read()
+        assert content == "OK", content
