@@ -104,8 +104,9 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def synth_members(workload, dims, z0, nz_total):
-    """Synthetic input for one rank as {member: dense array}; cheap enough for 1024^3."""
+def synth_members(workload, dims, z0, nz_total, alloc, share=False):
+    """Synthetic input for one rank written straight into buffers from alloc(shape, dtype) (pinned
+    host memory for the e2e leg), so that no second full-size copy ever exists on the host."""
     from libgeodecomp_b200 import models, synth
     name = WORKLOADS[workload][0]
     model = models.ALL[name]
@@ -113,16 +114,34 @@ def synth_members(workload, dims, z0, nz_total):
         nx, ny, nz = dims
         tile = min(nz, 32)   # generate a 32-plane block and repeat it along z (generation speed)
         block = synth.jacobi_grid(nx, ny, tile, seed=42 + z0)
-        reps = (nz + tile - 1) // tile
-        return model, {"temp": np.concatenate([block] * reps, axis=0)[:nz]}
+        out = alloc((nz, ny, nx), np.float64)
+        for z in range(0, nz, tile):
+            n = min(tile, nz - z)
+            out[z:z + n] = block[:n]
+        return model, {"temp": out}
     if name == "LBMCellF":
         nx, ny, nz = dims
-        raw = synth.lbm_grid(nx, ny, nz, z0=z0, nz_total=nz_total)
-        return model, {n: raw[m].view(t) for m, (n, t) in enumerate(model.members)}
+        states = synth.lbm_states(nx, ny, nz, z0, nz_total)
+        members, shared = {}, {}
+        for m, (n, t) in enumerate(model.members):
+            value = None if n == "state" else (1.0 if n in ("C", "density") else 0.0)
+            if share and value in shared:      # read-only input: equal members may share one host array
+                members[n] = shared[value]
+                continue
+            a = alloc((nz, ny, nx), t)
+            a[...] = states if n == "state" else value
+            members[n] = a
+            if value is not None:
+                shared[value] = a
+        return model, members
     nx, ny = dims
     tile = min(ny, 1024)
     block = synth.gol_grid(nx, tile)
-    return model, {"alive": np.concatenate([block] * ((ny + tile - 1) // tile), axis=0)[:ny]}
+    out = alloc((ny, nx), np.uint8)
+    for y in range(0, ny, tile):
+        n = min(tile, ny - y)
+        out[y:y + n] = block[:n]
+    return model, {"alive": out}
 
 
 def run_cpu_reference(workload, steps, warmup, threads=None):
@@ -200,31 +219,33 @@ def bench_device(workload, args, rank, world, dist, torch, with_e2e=True, with_c
     gdims = list(dims)
     gdims[last] = dims[last] * world
     z0 = dims[last] * rank
-    model, members = synth_members(workload, dims, z0, gdims[last])
+    keep = []
+
+    def alloc(shape, dtype):
+        t = torch.empty(shape, dtype=getattr(torch, np.dtype(dtype).name), pin_memory=with_e2e)
+        keep.append(t)
+        return t.numpy()
+
+    model, members = synth_members(workload, dims, z0, gdims[last], alloc, share=not with_e2e)
     cells_rank = float(np.prod(dims))
     cells_all = cells_rank * world
     K, W = args.steps, args.warmup
-
-    # pinned host copies of this rank's input (e2e uploads come from these)
-    pinned = {}
-    for n, a in members.items():
-        t = torch.from_numpy(np.ascontiguousarray(a))
-        pinned[n] = t.pin_memory() if with_e2e else t
-    members = None
-    host_out = {n: torch.empty_like(t).pin_memory() if with_e2e else None for n, t in pinned.items()}
+    # the e2e leg reads its input from these (pinned) host buffers and writes the result back into them
+    pinned = members
+    host_out = members
 
     class Init(SimpleInitializer):
         def grid(self, target):
             (o, d) = target.boundingBox()
-            for n, t in pinned.items():
-                target.loadMember(n, t.numpy(), origin=o)
+            for n, a in pinned.items():
+                target.loadMember(n, a, origin=o)
 
     class PullWriter(Writer):
         """pulls the rank's final grid into pinned host memory at WRITER_ALL_DONE"""
         def stepFinished(self, grid, step, event):
             if event == 2:
-                for n, t in host_out.items():
-                    grid.saveMember(n, out=t.numpy())
+                for n, a in host_out.items():
+                    grid.saveMember(n, out=a)
 
     def barrier():
         if world > 1:
@@ -267,7 +288,7 @@ def bench_device(workload, args, rank, world, dist, torch, with_e2e=True, with_c
             for side in (0, 1):
                 if sim.grid.modes[last][side] == capi.GHOST_PEER:
                     sim.grid.dev.halo_mark_valid(side, sim.ghost_width)
-        sim.grid.dev.step(model.kernel, n_steps=n)
+        sim.grid.dev.step(model.kernel, n_steps=n, params=model.step_params(n_roof + n == K))
         n_roof += n
     ev1.record()
     torch.cuda.synchronize()
@@ -297,7 +318,7 @@ def bench_device(workload, args, rank, world, dist, torch, with_e2e=True, with_c
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e_ms = float(t.item())
-        grid_bytes = sum(int(x.numel()) * x.element_size() for x in pinned.values())
+        grid_bytes = sum(int(x.nbytes) for x in pinned.values())
         out["e2e"] = {"value": 1e-9 * cells_all * K / (1e-3 * e_ms), "unit": "GLUPS",
                       "h2d_bytes_per_step": grid_bytes * world / K, "d2h_bytes_per_step": grid_bytes * world / K,
                       "ms_per_run": e_ms, "wall_ms_rank0": 1e3 * wall,

@@ -351,9 +351,10 @@ static int dispatch(b200geo_grid *g, int kernel, const void *params, const Box& 
     case B200GEO_KERNEL_GOL:
         return sweep_gol(g, box, s);
     case B200GEO_KERNEL_LBM_D3Q19: {
-        // params: int32 store_macroscopic_every_step (default 0 = only on the last sweep of a call)
-        bool every = params && *(const int32_t *)params != 0;
-        return sweep_lbm(g, box, every || last, s);
+        // params: int32 macroscopic store mode: 0 (default) = only on the last sweep of this call,
+        // 1 = on every sweep (what the reference cell does), 2 = never (caller is mid-run)
+        int mode = params ? *(const int32_t *)params : 0;
+        return sweep_lbm(g, box, mode == 1 || (mode == 0 && last), s);
     }
     default:
         return fail(B200GEO_ERR_LOGIC, "no kernel bound for this id");

@@ -26,7 +26,7 @@ enum { LIQUID, WEST_NOSLIP, EAST_NOSLIP, TOP, BOTTOM, NORTH_ACC, SOUTH_NOSLIP };
 #define SQR(X) ((X) * (X))
 
 template<bool MACRO>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128)
 lbm_kernel(const float *__restrict__ src, float *__restrict__ dst, int64_t pitch, int64_t plane,
            int64_t mstride, Box box)
 {
@@ -163,7 +163,7 @@ int sweep_lbm(b200geo_grid *g, const Box& box, bool store_macroscopic, cudaStrea
     int64_t mstride = g->m[1].offset / 4;
     const float *src = (const float *)g->member_ptr(0, 0) + L.origin;
     float *dst = (float *)g->member_ptr(0, 1) + L.origin;
-    int bx = g_tuning.lbm_block >= 32 && g_tuning.lbm_block <= 256 ? g_tuning.lbm_block : 128;
+    int bx = g_tuning.lbm_block >= 32 && g_tuning.lbm_block <= 128 ? g_tuning.lbm_block : 128;
     dim3 grid((box.x1 - box.x0 + bx - 1) / bx, box.y1 - box.y0, box.z1 - box.z0);
     if (grid.y > 65535 || grid.z > 65535) return fail(B200GEO_ERR_OUT_OF_RANGE, "grid dimension too large");
     if (store_macroscopic)

@@ -22,6 +22,13 @@ class CellModel:
             for k, v in edge.items():
                 self.default_cell[k] = v
 
+    def step_params(self, final):
+        """kernel parameter block for a chunk of sweeps; `final` = the grid is observed afterwards"""
+        if self.kernel == capi.KERNEL_LBM_D3Q19:
+            # density / velocity are outputs only: store them on the last sweep before an observation
+            return np.array([0 if final else 2], dtype=np.int32)
+        return None
+
     @property
     def member_bytes(self):
         return [t.itemsize for _, t in self.members]

@@ -26,22 +26,72 @@ def slab_bounds(extent, ranks):
 
 
 class HaloExchanger:
-    """Ghost-plane exchange for one slab. `dist` is torch.distributed (or None for world 1)."""
+    """Ghost-slice exchange for one slab. `dist` is torch.distributed (or None for world 1).
 
-    def __init__(self, grid, rank, world, width, periodic, members=None, dist=None):
+    Single-member grids (Jacobi, GoL): a member's `width` boundary slices are one contiguous block of
+    device memory, sent and received in place — no pack kernel, no staging copy.
+    Multi-member grids (LBM): the boundary region is serialised with ONE saveRegion launch into a
+    member-major device buffer — byte for byte the payload PatchLink::Accepter::put ships
+    (communication/patchlink.h:127-151) — sent as one message per neighbour, and loadRegion'ed into
+    the ghost slices on the other side (Provider::get, patchlink.h:218-244)."""
+
+    def __init__(self, grid, rank, world, width, periodic, dist=None):
         self.grid, self.rank, self.world, self.width, self.periodic = grid, rank, world, width, periodic
-        self.members = list(range(len(grid.model.members))) if members is None else list(members)
         self.dist = dist
         self.low = rank - 1 if rank > 0 else (world - 1 if periodic and world > 1 else None)
         self.high = rank + 1 if rank < world - 1 else (0 if periodic and world > 1 else None)
         self.bytes_per_exchange = 0
+        self.packed = len(grid.model.members) > 1
+        self._tensors = {}
+        self._staging = None
+
+    def _block(self, member, side, kind):
+        blk = self.grid.dev.halo_block(member, side, kind, self.width)
+        key = getattr(blk, "ptr", None)
+        if key is None:
+            return blk.as_tensor()
+        t = self._tensors.get(key)
+        if t is None:
+            t = self._tensors[key] = blk.as_tensor()
+        return t
+
+    def _slice_streaks(self, side, kind):
+        """whole padded slices (ghost columns included) as streaks {x, y, z, endX}"""
+        g = self.grid
+        nx, gx = g.dims[0], g.ghost[0]
+        w = self.width
+        if g.model.dim == 3:
+            ny, gy, nz = g.dims[1], g.ghost[1], g.dims[2]
+            z0 = (0 if side == 0 else nz - w) if kind == 0 else (-w if side == 0 else nz)
+            zs, ys = np.meshgrid(np.arange(z0, z0 + w), np.arange(-gy, ny + gy), indexing="ij")
+        else:
+            ny = g.dims[1]
+            y0 = (0 if side == 0 else ny - w) if kind == 0 else (-w if side == 0 else ny)
+            ys = np.arange(y0, y0 + w)
+            zs = np.zeros_like(ys)
+        n = ys.size
+        st = np.empty((n, 4), dtype=np.int32)
+        st[:, 0], st[:, 1], st[:, 2], st[:, 3] = -gx, ys.reshape(-1), zs.reshape(-1), nx + gx
+        return st
+
+    def _setup_staging(self):
+        import torch
+        self._staging = {}
+        for side in (0, 1):
+            for kind in (0, 1):
+                st = self._slice_streaks(side, kind)
+                cells = int((st[:, 3] - st[:, 0]).sum())
+                buf = torch.empty(cells * self.grid.model.cell_dtype.itemsize, dtype=torch.uint8, device="cuda")
+                self._staging[(side, kind)] = (st, buf)
 
     def exchange(self):
-        """Fill `width` ghost planes on both PEER sides of the current buffer."""
+        """Fill `width` ghost slices on both PEER sides of the current buffer."""
         dev, w = self.grid.dev, self.width
         if self.world == 1:
             return
-        ops, keep = [], []
+        if self.packed and self._staging is None:
+            self._setup_staging()
+        ops = []
         nbytes = 0
         # post receives first, then sends; one batched group = one NCCL launch. Messages between one
         # pair of ranks match in posting order, and on a periodic 2-rank ring both neighbours are the
@@ -50,25 +100,29 @@ class HaloExchanger:
         for side, peer in ((1, self.high), (0, self.low)):
             if peer is None:
                 continue
-            for m in self.members:
-                t = dev.halo_block(m, side, 1, w).as_tensor()
-                keep.append(t)
-                ops.append(self.dist.P2POp(self.dist.irecv, t, peer))
+            t = self._staging[(side, 1)][1] if self.packed else self._block(0, side, 1)
+            ops.append(self.dist.P2POp(self.dist.irecv, t, peer))
         for side, peer in ((0, self.low), (1, self.high)):
             if peer is None:
                 continue
-            for m in self.members:
-                t = dev.halo_block(m, side, 0, w).as_tensor()
-                keep.append(t)
-                nbytes += t.numel()
-                ops.append(self.dist.P2POp(self.dist.isend, t, peer))
+            if self.packed:
+                st, t = self._staging[(side, 0)]
+                dev.save_region(st, t, location=capi.CUDA_DEVICE)
+            else:
+                t = self._block(0, side, 0)
+            nbytes += t.numel()
+            ops.append(self.dist.P2POp(self.dist.isend, t, peer))
         if ops:
             for work in self.dist.batch_isend_irecv(ops):
                 work.wait()
         self.bytes_per_exchange = nbytes
         for side, peer in ((0, self.low), (1, self.high)):
-            if peer is not None:
-                dev.halo_mark_valid(side, w)
+            if peer is None:
+                continue
+            if self.packed:
+                st, t = self._staging[(side, 1)]
+                dev.load_region(st, t, location=capi.CUDA_DEVICE, both=False)
+            dev.halo_mark_valid(side, w)
 
 
 class StripedSimulator:
@@ -132,7 +186,7 @@ class StripedSimulator:
                 self.halo.exchange()
                 self._valid = self.ghost_width
             n = min(nano_steps - done, self._valid) if self.world > 1 else nano_steps - done
-            self.grid.dev.step(self.model.kernel, n_steps=n)
+            self.grid.dev.step(self.model.kernel, n_steps=n, params=self.model.step_params(done + n == nano_steps))
             if self.world > 1:
                 self._valid -= n
             done += n
