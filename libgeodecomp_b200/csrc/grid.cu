@@ -10,7 +10,7 @@
 
 namespace b200geo {
 
-static const Tuning g_tuning_default = {0, -1, 0, 128};
+static const Tuning g_tuning_default = {0, -1, 0, 128, 2, 32, 0};
 Tuning g_tuning = g_tuning_default;
 static thread_local std::string g_last_error;
 static std::atomic<uint64_t> g_launches(0);
@@ -78,6 +78,9 @@ int b200geo_set_tuning(const char *key, int value)
     else if (k == "jacobi.prefetch") g_tuning.jacobi_prefetch = value;
     else if (k == "gol.rows") g_tuning.gol_rows = value < 0 ? g_tuning_default.gol_rows : value;
     else if (k == "lbm.block") g_tuning.lbm_block = value < 0 ? g_tuning_default.lbm_block : value;
+    else if (k == "jacobi.tb") g_tuning.jacobi_tb = value < 0 ? g_tuning_default.jacobi_tb : value;
+    else if (k == "jacobi.tb_rows") g_tuning.jacobi_tb_rows = value < 0 ? g_tuning_default.jacobi_tb_rows : value;
+    else if (k == "jacobi.tb_zchunk") g_tuning.jacobi_tb_zchunk = value < 0 ? g_tuning_default.jacobi_tb_zchunk : value;
     else return fail(B200GEO_ERR_INVALID, "unknown tuning key " + k);
     return B200GEO_OK;
 }
@@ -397,25 +400,43 @@ int b200geo_step(b200geo_grid *g, int kernel, const void *params, uint32_t first
     cudaStream_t s = (cudaStream_t)stream;
     B200GEO_CUDA(cudaSetDevice(g->device));
     if (g->stats_on) cudaEventRecord(g->ev[0], s);
-    for (uint32_t t = 0; t < n_steps; ++t) {
+    const int a = g->slab_axis;
+    const bool jacobi = kernel == B200GEO_KERNEL_JACOBI6 || kernel == B200GEO_KERNEL_JACOBI7 || kernel == B200GEO_KERNEL_JACOBI27;
+    for (uint32_t t = 0; t < n_steps;) {
+        // sweeps fused into this launch: the temporal-blocked Jacobi kernel takes `depth` sweeps per
+        // HBM round trip when enough valid ghost cells are there (WRAP: ghost width, PEER: what the
+        // last exchange delivered); everything else is one sweep per launch
+        int depth = 1;
+        if (jacobi && g_tuning.jacobi_tb > 1) {
+            depth = g_tuning.jacobi_tb > 4 ? 4 : g_tuning.jacobi_tb;
+            if ((uint32_t)depth > n_steps - t) depth = (int)(n_steps - t);
+            for (int i = 0; i < 3; ++i)
+                for (int side = 0; side < 2; ++side) {
+                    int mode = g->desc.ghost_mode[i][side];
+                    if (mode == B200GEO_GHOST_WRAP && g->g[i] < depth) depth = g->g[i];
+                    if (mode == B200GEO_GHOST_PEER && g->peer_valid[side] < depth) depth = g->peer_valid[side];
+                }
+            if (depth < 1) depth = 1;
+        }
         Box box = {0, 0, 0, g->d[0], g->d[1], g->d[2]};
-        const int a = g->slab_axis;
         for (int side = 0; side < 2; ++side) {
             if (g->desc.ghost_mode[a][side] != B200GEO_GHOST_PEER) continue;
             if (g->peer_valid[side] < 1)
                 return fail(B200GEO_ERR_LOGIC, "ghost zone exhausted: exchange halos before stepping");
-            int extra = g->peer_valid[side] - 1;
+            int extra = g->peer_valid[side] - depth;
             if (a == 2) { if (side == 0) box.z0 -= extra; else box.z1 += extra; }
             else        { if (side == 0) box.y0 -= extra; else box.y1 += extra; }
         }
         rc = refresh_wrap(g, s);
         if (rc) return rc;
-        rc = dispatch(g, kernel, params, box, t + 1 == n_steps, s);
+        if (depth > 1) rc = sweep_jacobi_tb(g, kernel == B200GEO_KERNEL_JACOBI6 ? 6 : kernel == B200GEO_KERNEL_JACOBI7 ? 7 : 27, depth, box, s);
+        else rc = dispatch(g, kernel, params, box, t + 1 == n_steps, s);
         if (rc) return rc;
         g->cur ^= 1;
         for (int side = 0; side < 2; ++side)
-            if (g->desc.ghost_mode[a][side] == B200GEO_GHOST_PEER) --g->peer_valid[side];
-        ++g->sweeps;
+            if (g->desc.ghost_mode[a][side] == B200GEO_GHOST_PEER) g->peer_valid[side] -= depth;
+        g->sweeps += depth;
+        t += depth;
     }
     if (g->stats_on) {
         cudaEventRecord(g->ev[1], s);

@@ -64,6 +64,9 @@ struct Tuning {
     int jacobi_prefetch;  // L2 prefetch distance in planes (0 = off, < 0 = per-kernel default)
     int gol_rows;         // rows per CTA (0 = automatic)
     int lbm_block;        // threads per CTA
+    int jacobi_tb;        // temporal blocking depth of the Jacobi kernels (sweeps per launch; 0/1 = off)
+    int jacobi_tb_rows;   // tile shape of the temporal-blocked kernel: 32 (2 rows/thread), 64 or 33 (4 rows/thread)
+    int jacobi_tb_zchunk; // planes per CTA along z of the temporal-blocked kernel (0 = automatic)
 };
 extern Tuning g_tuning;
 
@@ -73,6 +76,7 @@ void count_launch(uint64_t n = 1);
 
 // kernel families (one translation unit each)
 int sweep_jacobi(b200geo_grid *g, int kind, const Box& box, cudaStream_t s);
+int sweep_jacobi_tb(b200geo_grid *g, int kind, int depth, const Box& box, cudaStream_t s);
 int sweep_gol(b200geo_grid *g, const Box& box, cudaStream_t s);
 int sweep_lbm(b200geo_grid *g, const Box& box, bool store_macroscopic, cudaStream_t s);
 

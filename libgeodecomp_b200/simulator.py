@@ -102,6 +102,9 @@ class Steerer:
         raise NotImplementedError
 
 
+TB_DEPTH = 4  # deepest temporal blocking the Jacobi kernels offer (b200geo_set_tuning "jacobi.tb")
+
+
 class B200Grid:
     """GridBase<CELL, DIM> as Initializers, Writers and Steerers see it (storage/gridbase.h:71-309),
     backed by the device-resident SoA grid. Coordinates are (x, y[, z]) like Coord<DIM>.
@@ -118,6 +121,10 @@ class B200Grid:
         modes = [[wrap, wrap] for _ in range(3)]
         r = model.radius
         ghost = [r, r, r if model.dim == 3 else 0]
+        if model.wraps and model.kernel in (capi.KERNEL_JACOBI6, capi.KERNEL_JACOBI7, capi.KERNEL_JACOBI27):
+            # periodic images TB_DEPTH cells wide let the temporal-blocked kernel take that many
+            # sweeps per launch on a Torus (a wrap ghost may not be wider than the grid itself)
+            ghost = [max(r, min(TB_DEPTH, d)) for d in self.dims]
         if model.dim == 2:
             modes[2] = [capi.GHOST_EDGE, capi.GHOST_EDGE]
         last = model.dim - 1

@@ -42,6 +42,43 @@ def test_jacobi_bit_exact(oracle, kind, torus, shape):
     assert np.array_equal(got, want)
 
 
+@pytest.fixture
+def tuning():
+    """set b200geo tuning keys for one test, restore the defaults afterwards"""
+    keys = []
+
+    def set_(key, value):
+        keys.append(key)
+        capi.set_tuning(key, value)
+    yield set_
+    for k in keys:
+        capi.set_tuning(k, -1)
+
+
+@pytest.mark.parametrize("kind", [6, 7, 27])
+@pytest.mark.parametrize("torus", [False, True])
+@pytest.mark.parametrize("depth", [1, 2, 3, 4])
+@pytest.mark.parametrize("rows", [32, 33, 64])
+def test_jacobi_temporal_blocking_bit_exact(oracle, tuning, kind, torus, depth, rows):
+    """T sweeps per launch (TMA-staged temporal-blocked kernel) == T single sweeps == the oracle;
+    7 steps are not a multiple of any depth, so the remainder launches are covered as well."""
+    tuning("jacobi.tb", depth)
+    tuning("jacobi.tb_rows", rows)
+    for shape in [(18, 20, 24), (7, 5, 3), (1, 1, 1), (40, 70, 130), (9, 129, 61)]:
+        data, got = run_jacobi(kind, torus, shape, 7, edge=0.25)
+        want = oracle.jacobi(kind, torus, data, 7, edge=0.25)
+        assert np.array_equal(got, want), shape
+
+
+def test_jacobi_temporal_blocking_z_chunks(oracle, tuning):
+    """several z chunks per column: every chunk warms its pipeline up on its own 2T planes"""
+    tuning("jacobi.tb", 4)
+    tuning("jacobi.tb_zchunk", 16)
+    for kind in (7, 27):
+        data, got = run_jacobi(kind, False, (70, 30, 66), 8, edge=-1.5)
+        assert np.array_equal(got, oracle.jacobi(kind, False, data, 8, edge=-1.5))
+
+
 @pytest.mark.parametrize("kind", [7, 27])
 def test_jacobi_config1_128cubed_100_steps(oracle, kind):
     """BASELINE.json config 1: 128^3 double, 100 steps, Cube and the example's Torus."""
