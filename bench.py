@@ -45,6 +45,21 @@ DESCRIPTION = {
 }
 
 
+# temporal blocking depth per workload (b200geo_set_tuning "jacobi.tb"): sweeps fused into one launch of
+# the TMA-staged Jacobi kernel; with N > 1 the ghost zone must be that wide (one exchange per launch)
+TB_DEPTH = {"jacobi27": 2, "jacobi7": 2, "jacobi7_128": 1}
+
+
+def ncu_traffic(workload):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
+    (profiles/traffic.json: dram__bytes_read.sum + dram__bytes_write.sum), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f).get(workload)
+    except (OSError, ValueError):
+        return None
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -252,7 +267,10 @@ def bench_device(workload, args, rank, world, dist, torch, with_e2e=True, with_c
             dist.barrier()
         torch.cuda.synchronize()
 
-    sim = StripedSimulator(Init(gdims, K), model, rank=rank, world=world, ghost_width=args.ghost, device=torch.cuda.current_device(), dist=dist)
+    depth = TB_DEPTH.get(workload, 1)
+    capi.set_tuning("jacobi.tb", depth)
+    ghost = args.ghost if args.ghost else depth
+    sim = StripedSimulator(Init(gdims, K), model, rank=rank, world=world, ghost_width=ghost, device=torch.cuda.current_device(), dist=dist)
     torch.cuda.synchronize()
 
     # ---- device-resident throughput
@@ -279,6 +297,7 @@ def bench_device(workload, args, rank, world, dist, torch, with_e2e=True, with_c
 
     # ---- dominant kernel alone (roofline): K sweeps without any exchange on a 1-rank-style step
     peak, peak_src = peaks()
+    launches_roof0 = capi.launch_count()
     ev0.record()
     n_roof = 0
     while n_roof < K:
@@ -292,11 +311,19 @@ def bench_device(workload, args, rank, world, dist, torch, with_e2e=True, with_c
         n_roof += n
     ev1.record()
     torch.cuda.synchronize()
-    kms = ev0.elapsed_time(ev1) / n_roof
-    achieved = alg_bytes * cells_rank / (1e-3 * kms) / 1e9
+    n_launch = capi.launch_count() - launches_roof0
+    kms = ev0.elapsed_time(ev1) / n_launch               # mean duration of one launch
+    per_launch = n_roof / n_launch                       # sweeps per launch (temporal blocking depth)
+    achieved = alg_bytes * cells_rank * per_launch / (1e-3 * kms) / 1e9
+    traffic = ncu_traffic(workload) or {}
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel_ms": kms, "algorithmic_bytes_per_update": alg_bytes,
-                "peak_source": peak_src, "kernel": model_name}
+                "traffic": traffic.get("dram_bytes_per_launch"), "traffic_source": traffic.get("source"),
+                "kernel_ms": kms, "sweeps_per_launch": per_launch, "updates_per_launch": cells_rank * per_launch,
+                "algorithmic_bytes_per_update": alg_bytes, "peak_source": peak_src, "kernel": model_name}
+    if roofline["traffic"] and abs(traffic.get("sweeps_per_launch", 1) - per_launch) < 1e-9:
+        # what the DRAM actually moved per launch / launch time: the physical HBM fraction (<= 1);
+        # with temporal blocking the ALGORITHMIC rate above may exceed the copy peak, this one cannot
+        roofline["dram_frac"] = roofline["traffic"] / (1e-3 * kms) / 1e9 / peak
 
     out = {"workload": workload, "value": value, "ms_per_step": ms / K, "roofline": roofline, "dtype": dtype,
            "gpu_launches": launches, "clocks": clocks, "model": model_name, "dims_per_gpu": list(dims),
@@ -335,7 +362,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200geo", choices=["b200geo", "reference"])
     ap.add_argument("--workload", default="jacobi27", choices=sorted(WORKLOADS))
-    ap.add_argument("--ghost", type=int, default=1, help="ghost zone width = steps between halo exchanges (N > 1)")
+    ap.add_argument("--ghost", type=int, default=0, help="ghost zone width = steps between halo exchanges (N > 1); "
+                    "0 = the workload's temporal blocking depth")
     ap.add_argument("--no-others", action="store_true", help="skip the secondary workloads (configs 0, 1, 3)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
@@ -354,7 +382,9 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the b200geo hot path has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # the halo transfer must get SMs while the interior update is running: high-priority NCCL stream
+        opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local), pg_options=opts)
     t_start = time.perf_counter()
 
     main_res = bench_device(args.workload, args, rank, world, dist if world > 1 else None, torch)

@@ -82,7 +82,9 @@ const char *b200geo_last_error(void);
 int b200geo_device_count(void);
 /* Launch / tiling parameters by name (the role misc/cudasimulationfactory.h:28-33 BlockDimX/Y/Z
  * play for the reference's CUDASimulator). Unknown keys -> B200GEO_ERR_INVALID. Keys:
- * "jacobi.zchunk", "jacobi.prefetch", "gol.rows", "lbm.block". value < 0 restores the default. */
+ * "jacobi.zchunk", "jacobi.prefetch", "gol.rows", "lbm.block", "jacobi.tb" (sweeps fused per launch
+ * by the temporal-blocked Jacobi kernels, 1..4), "jacobi.tb_rows" (tile shape), "jacobi.tb_zchunk".
+ * value < 0 restores the default. */
 int b200geo_set_tuning(const char *key, int value);
 /* number of kernels this library has launched so far in this process (bench.py: gpu_launches). */
 uint64_t b200geo_launch_count(void);
@@ -134,6 +136,13 @@ int b200geo_step(b200geo_grid *g, int kernel, const void *params, uint32_t first
  * (parallelization/stripingsimulator.h:269-286). */
 int b200geo_update_box(b200geo_grid *g, int kernel, const void *params, uint32_t nano_step,
                        const int32_t origin[3], const int32_t dim[3], void *stream);
+/* Same for n_sweeps fused sweeps of the box in ONE launch (temporal-blocked kernels: Jacobi, 2..4
+ * sweeps; n_sweeps = 1 is b200geo_update_box). Ghost / neighbour cells must be valid n_sweeps deep
+ * around the box. Reads the current buffer, writes the scratch buffer, does not swap: lets a slab
+ * update its rims first, ship them, and overlap the interior with the transfer. Kernels that cannot
+ * fuse sweeps -> B200GEO_ERR_LOGIC. */
+int b200geo_update_box_n(b200geo_grid *g, int kernel, const void *params, uint32_t nano_step,
+                         const int32_t origin[3], const int32_t dim[3], uint32_t n_sweeps, void *stream);
 int b200geo_swap(b200geo_grid *g);
 /* Re-materialise the periodic images of WRAP axes in the current buffer (done automatically by
  * b200geo_step; needed before b200geo_update_box on Torus axes). */
@@ -148,6 +157,10 @@ int b200geo_sync(void *stream);
  * zone), kind 1 = the GHOST planes on `side` (outer ghost zone). Buffer = current. */
 int b200geo_halo_block(const b200geo_grid *g, int member, int side, int kind, int width,
                        void **ptr, uint64_t *bytes);
+/* Same in the current (which = 0) or the scratch (which = 1) buffer: a rim-first schedule ships
+ * the freshly written rims of the scratch buffer before the swap. */
+int b200geo_halo_block_in(const b200geo_grid *g, int member, int side, int kind, int width, int which,
+                          void **ptr, uint64_t *bytes);
 /* CUDA-IPC plumbing for direct NVLink P2P between one-process-per-GPU ranks. */
 int b200geo_grid_ipc_export(const b200geo_grid *g, int which, void *handle64);
 int b200geo_grid_ipc_open(b200geo_grid *g, int side, int which, const void *handle64);

@@ -58,11 +58,14 @@ SYMBOLS = [
     ("b200geo_grid_save_region", ctypes.c_int, [_vp, _i32p, ctypes.c_int, _vp, ctypes.c_int, _vp]),
     ("b200geo_step", ctypes.c_int, [_vp, ctypes.c_int, _vp, ctypes.c_uint32, ctypes.c_uint32, _vp]),
     ("b200geo_update_box", ctypes.c_int, [_vp, ctypes.c_int, _vp, ctypes.c_uint32, _i32p, _i32p, _vp]),
+    ("b200geo_update_box_n", ctypes.c_int, [_vp, ctypes.c_int, _vp, ctypes.c_uint32, _i32p, _i32p, ctypes.c_uint32, _vp]),
     ("b200geo_swap", ctypes.c_int, [_vp]),
     ("b200geo_refresh_ghosts", ctypes.c_int, [_vp, _vp]),
     ("b200geo_sync", ctypes.c_int, [_vp]),
     ("b200geo_halo_block", ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                           ctypes.POINTER(_vp), ctypes.POINTER(ctypes.c_uint64)]),
+    ("b200geo_halo_block_in", ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                             ctypes.POINTER(_vp), ctypes.POINTER(ctypes.c_uint64)]),
     ("b200geo_grid_ipc_export", ctypes.c_int, [_vp, ctypes.c_int, _vp]),
     ("b200geo_grid_ipc_open", ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, _vp]),
     ("b200geo_halo_push", ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, _vp]),
@@ -225,8 +228,9 @@ class DeviceGrid:
     def step(self, kernel, n_steps=1, first_nano_step=0, params=None, stream=None):
         check(lib().b200geo_step(self._h, kernel, _ptr(params), first_nano_step, n_steps, stream))
 
-    def update_box(self, kernel, origin, dim, nano_step=0, params=None, stream=None):
-        check(lib().b200geo_update_box(self._h, kernel, _ptr(params), nano_step, _i3(origin), _i3(dim), stream))
+    def update_box(self, kernel, origin, dim, nano_step=0, params=None, stream=None, n_sweeps=1):
+        check(lib().b200geo_update_box_n(self._h, kernel, _ptr(params), nano_step, _i3(origin), _i3(dim),
+                                         int(n_sweeps), stream))
 
     def swap(self):
         check(lib().b200geo_swap(self._h))
@@ -235,9 +239,9 @@ class DeviceGrid:
         check(lib().b200geo_refresh_ghosts(self._h, stream))
 
     # -- halo
-    def halo_block(self, member, side, kind, width=1):
+    def halo_block(self, member, side, kind, width=1, which=0):
         p, n = ctypes.c_void_p(), ctypes.c_uint64()
-        check(lib().b200geo_halo_block(self._h, member, side, kind, width, ctypes.byref(p), ctypes.byref(n)))
+        check(lib().b200geo_halo_block_in(self._h, member, side, kind, width, which, ctypes.byref(p), ctypes.byref(n)))
         return DeviceBlock(p.value, n.value, self)
 
     def halo_mark_valid(self, side, width):

@@ -10,7 +10,7 @@
 
 namespace b200geo {
 
-static const Tuning g_tuning_default = {0, -1, 0, 128, 2, 32, 0};
+static const Tuning g_tuning_default = {0, -1, 0, 128, 2, 33, 0};
 Tuning g_tuning = g_tuning_default;
 static thread_local std::string g_last_error;
 static std::atomic<uint64_t> g_launches(0);
@@ -466,6 +466,34 @@ int b200geo_update_box(b200geo_grid *g, int kernel, const void *params, uint32_t
     return dispatch(g, kernel, params, box, true, (cudaStream_t)stream);
 }
 
+int b200geo_update_box_n(b200geo_grid *g, int kernel, const void *params, uint32_t nano_step,
+                         const int32_t origin[3], const int32_t dim[3], uint32_t n_sweeps, void *stream)
+{
+    if (n_sweeps == 1) return b200geo_update_box(g, kernel, params, nano_step, origin, dim, stream);
+    if (!g || !origin || !dim) return fail(B200GEO_ERR_INVALID, "null argument");
+    int rc = check_kernel_grid(g, kernel);
+    if (rc) return rc;
+    if (kernel != B200GEO_KERNEL_JACOBI6 && kernel != B200GEO_KERNEL_JACOBI7 && kernel != B200GEO_KERNEL_JACOBI27)
+        return fail(B200GEO_ERR_LOGIC, "this kernel family cannot fuse sweeps");
+    if (n_sweeps < 1 || n_sweeps > 4) return fail(B200GEO_ERR_INVALID, "n_sweeps must be 1..4");
+    const int n = (int)n_sweeps;
+    for (int i = 0; i < 3; ++i) {
+        bool slab = i == g->slab_axis && g->g[i] > 0;
+        int lo = slab ? -(g->g[i] - n) : 0, hi = g->d[i] + (slab ? g->g[i] - n : 0);
+        if (lo > 0) lo = 0;
+        if (hi < g->d[i]) hi = g->d[i];
+        if (dim[i] < 0 || origin[i] < lo || origin[i] + dim[i] > hi) return fail(B200GEO_ERR_INVALID, "box outside the updatable area");
+        for (int side = 0; side < 2; ++side)
+            if (g->desc.ghost_mode[i][side] != B200GEO_GHOST_EDGE && g->g[i] < n)
+                return fail(B200GEO_ERR_INVALID, "ghost zone narrower than n_sweeps");
+    }
+    if (dim[0] == 0 || dim[1] == 0 || dim[2] == 0) return B200GEO_OK;
+    B200GEO_CUDA(cudaSetDevice(g->device));
+    Box box = {origin[0], origin[1], origin[2], origin[0] + dim[0], origin[1] + dim[1], origin[2] + dim[2]};
+    return sweep_jacobi_tb(g, kernel == B200GEO_KERNEL_JACOBI6 ? 6 : kernel == B200GEO_KERNEL_JACOBI7 ? 7 : 27, n, box,
+                           (cudaStream_t)stream);
+}
+
 int b200geo_swap(b200geo_grid *g)
 {
     if (!g) return fail(B200GEO_ERR_INVALID, "null grid");
@@ -490,8 +518,14 @@ int b200geo_sync(void *stream)
 int b200geo_halo_block(const b200geo_grid *g, int member, int side, int kind, int width,
                        void **ptr, uint64_t *bytes)
 {
+    return b200geo_halo_block_in(g, member, side, kind, width, 0, ptr, bytes);
+}
+
+int b200geo_halo_block_in(const b200geo_grid *g, int member, int side, int kind, int width, int which,
+                          void **ptr, uint64_t *bytes)
+{
     if (!g || !ptr || !bytes) return fail(B200GEO_ERR_INVALID, "null argument");
-    if (member < 0 || member >= g->n || (side != 0 && side != 1) || (kind != 0 && kind != 1))
+    if (member < 0 || member >= g->n || (side != 0 && side != 1) || (kind != 0 && kind != 1) || (which != 0 && which != 1))
         return fail(B200GEO_ERR_INVALID, "bad member/side/kind");
     const int a = g->slab_axis, gz = g->g[a], nz = g->d[a];
     if (width < 1 || width > gz || width > nz) return fail(B200GEO_ERR_INVALID, "bad halo width");
@@ -499,7 +533,7 @@ int b200geo_halo_block(const b200geo_grid *g, int member, int side, int kind, in
     int64_t zplane;  // padded slice index of the first slice of the block
     if (kind == 0) zplane = side == 0 ? gz : gz + nz - width;
     else           zplane = side == 0 ? gz - width : gz + nz;
-    *ptr = g->member_ptr(member, 0) + zplane * g->slice_elems(member) * L.elem;
+    *ptr = g->member_ptr(member, which) + zplane * g->slice_elems(member) * L.elem;
     *bytes = (uint64_t)width * g->slice_elems(member) * L.elem;
     return B200GEO_OK;
 }

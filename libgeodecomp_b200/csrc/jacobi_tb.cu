@@ -154,8 +154,8 @@ __device__ __forceinline__ double2 with_edge(double2 v, bool o0, bool o1, double
     return v;
 }
 
-template<int KIND, int T, int R, int NW, int NS>
-__global__ void __launch_bounds__(NW * 32)
+template<int KIND, int T, int R, int NW, int NS, int MINB>
+__global__ void __launch_bounds__(NW * 32, MINB)
 jacobi_tb_kernel(const __grid_constant__ CUtensorMap tmap, double *__restrict__ dst, int64_t pitch, int64_t plane,
                  Box box, int xa, Limits lim, double edge, int zchunk, int pad_x, int pad_y, int pad_z)
 {
@@ -199,12 +199,15 @@ jacobi_tb_kernel(const __grid_constant__ CUtensorMap tmap, double *__restrict__ 
         if (yr + r < lim.lo[1] || yr + r >= lim.hi[1]) oy |= 1u << (r + 1);
     const bool sx0 = 2 * lane >= H && 2 * lane < TX - H && x >= box.x0 && x < box.x1;
     const bool sx1 = 2 * lane >= H && 2 * lane < TX - H && x + 1 >= box.x0 && x + 1 < box.x1;
+    const bool sboth = sx0 && sx1;
     unsigned sy = 0;
 #pragma unroll
     for (int r = 0; r < R; ++r) {
         int ty = warp * R + r;
         if (ty >= T && ty < TY - T && yr + r >= box.y0 && yr + r < box.y1) sy |= 1u << r;
     }
+    // CTA-uniform: does this tile touch cells outside the simulation area in x or y at all?
+    const bool edge_xy = X0 < lim.lo[0] || X0 + TX > lim.hi[0] || Y0 < lim.lo[1] || Y0 + TY > lim.hi[1];
     const int up_row = warp * R > 0 ? warp * R - 1 : 0;
     const int dn_row = warp * R + R < TY ? warp * R + R : TY - 1;
     const int up_warp = warp > 0 ? warp - 1 : 0, dn_warp = warp + 1 < NW ? warp + 1 : NW - 1;
@@ -222,6 +225,7 @@ jacobi_tb_kernel(const __grid_constant__ CUtensorMap tmap, double *__restrict__ 
 
     double *q0 = dst + (int64_t)yr * pitch + x;
 
+#pragma unroll 2
     for (int i = 0; i < niter; ++i) {
         // refill the stage consumed in the previous iteration
         if (threadIdx.x == 0 && i + NS - 1 < nload) {
@@ -241,14 +245,20 @@ jacobi_tb_kernel(const __grid_constant__ CUtensorMap tmap, double *__restrict__ 
                 const int z = zs + i;
                 const bool oz = z < lim.lo[2] || z >= lim.hi[2];
 #pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    bool o = oz || ((oy >> (r + 1)) & 1);
-                    n[r] = with_edge(*reinterpret_cast<const double2 *>(sp + (warp * R + r) * TX), o || ox0, o || ox1, edge);
+                for (int r = 0; r < R; ++r) n[r] = *reinterpret_cast<const double2 *>(sp + (warp * R + r) * TX);
+                up = *reinterpret_cast<const double2 *>(sp + up_row * TX);
+                dn = *reinterpret_cast<const double2 *>(sp + dn_row * TX);
+                if (edge_xy || oz) {  // uniform branch: interior tiles never take it
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        bool o = oz || ((oy >> (r + 1)) & 1);
+                        n[r] = with_edge(n[r], o || ox0, o || ox1, edge);
+                    }
+                    bool o = oz || (oy & 1);
+                    up = with_edge(up, o || ox0, o || ox1, edge);
+                    o = oz || ((oy >> (R + 1)) & 1);
+                    dn = with_edge(dn, o || ox0, o || ox1, edge);
                 }
-                bool o = oz || (oy & 1);
-                up = with_edge(*reinterpret_cast<const double2 *>(sp + up_row * TX), o || ox0, o || ox1, edge);
-                o = oz || ((oy >> (R + 1)) & 1);
-                dn = with_edge(*reinterpret_cast<const double2 *>(sp + dn_row * TX), o || ox0, o || ox1, edge);
             } else {
                 const double *xp = xch + (((t - 1) * 2 + (par ^ 1)) * NW) * 2 * TX + 2 * lane;
 #pragma unroll
@@ -259,20 +269,24 @@ jacobi_tb_kernel(const __grid_constant__ CUtensorMap tmap, double *__restrict__ 
             feed_plane<KIND, R>(st[t], n, up, dn, out);
             const int zo = zs + i - 2 * t - 1;  // plane index of `out`, a plane of level t + 1
             const bool oz = zo < lim.lo[2] || zo >= lim.hi[2];
+            if (edge_xy || oz) {
 #pragma unroll
-            for (int r = 0; r < R; ++r) {
-                bool o = oz || ((oy >> (r + 1)) & 1);
-                out[r] = with_edge(out[r], o || ox0, o || ox1, edge);
+                for (int r = 0; r < R; ++r) {
+                    bool o = oz || ((oy >> (r + 1)) & 1);
+                    out[r] = with_edge(out[r], o || ox0, o || ox1, edge);
+                }
             }
             if (t == T - 1) {
                 if (zo >= zb && zo < ze) {
                     double *q = q0 + (int64_t)zo * plane;
+                    if (sboth) {  // the common case: predicated 128-bit stores, no branches per row
 #pragma unroll
-                    for (int r = 0; r < R; ++r) {
-                        if (!((sy >> r) & 1)) continue;
-                        if (sx0 && sx1) *reinterpret_cast<double2 *>(q + r * pitch) = out[r];
-                        else if (sx0) q[r * pitch] = out[r].x;
-                        else if (sx1) q[r * pitch + 1] = out[r].y;
+                        for (int r = 0; r < R; ++r)
+                            if ((sy >> r) & 1) *reinterpret_cast<double2 *>(q + r * pitch) = out[r];
+                    } else if (sx0 || sx1) {  // odd box edges in x
+#pragma unroll
+                        for (int r = 0; r < R; ++r)
+                            if ((sy >> r) & 1) q[r * pitch + (sx0 ? 0 : 1)] = sx0 ? out[r].x : out[r].y;
                     }
                 }
             } else {
@@ -304,7 +318,7 @@ EncodeTiled encode_tiled()
     return fn;
 }
 
-template<int KIND, int T, int R, int NW, int NS>
+template<int KIND, int T, int R, int NW, int NS, int MINB>
 int launch_tb(b200geo_grid *g, const CUtensorMap& map, const Box& box, const Limits& lim, double edge, cudaStream_t s)
 {
     constexpr int TY = R * NW;
@@ -312,7 +326,7 @@ int launch_tb(b200geo_grid *g, const CUtensorMap& map, const Box& box, const Lim
     constexpr int NX = T > 1 ? T - 1 : 1;
     const MemberLayout& L = g->m[0];
     size_t smem = (size_t)NS * TY * TX * 8 + (size_t)NX * 2 * NW * 2 * TX * 8 + NS * 8;
-    auto kernel = jacobi_tb_kernel<KIND, T, R, NW, NS>;
+    auto kernel = jacobi_tb_kernel<KIND, T, R, NW, NS, MINB>;
     static bool attr_set = false;
     if (!attr_set) {
         B200GEO_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -336,11 +350,14 @@ int launch_tb(b200geo_grid *g, const CUtensorMap& map, const Box& box, const Lim
 template<int KIND, int T>
 int launch_tb_shape(b200geo_grid *g, const CUtensorMap& map, int rows, const Box& box, const Limits& lim, double edge, cudaStream_t s)
 {
-    // tile shapes: 64 x 32 (R = 2, 16 warps), 64 x 64 (R = 4, 16 warps), 64 x 32 (R = 4, 8 warps)
+    // tile shapes: 64 x 32 (R = 2, 16 warps), 64 x 64 (R = 4, 16 warps), 64 x 32 (R = 4, 8 warps);
+    // the register budget (state = 4 f64 per cell and level) decides how many CTAs share an SM
     switch (rows) {
-    case 64: return launch_tb<KIND, T, 4, 16, 3>(g, map, box, lim, edge, s);
-    case 33: return launch_tb<KIND, T, 4, 8, 4>(g, map, box, lim, edge, s);
-    default: return launch_tb<KIND, T, 2, 16, 4>(g, map, box, lim, edge, s);
+    case 64: return launch_tb<KIND, T, 4, 16, 3, 1>(g, map, box, lim, edge, s);
+    case 33: return launch_tb<KIND, T, 4, 8, 4, (T == 2 ? 2 : 1)>(g, map, box, lim, edge, s);
+    case 34: return launch_tb<KIND, T, 4, 8, 4, 1>(g, map, box, lim, edge, s);
+    case 31: return launch_tb<KIND, T, 2, 16, 4, 1>(g, map, box, lim, edge, s);
+    default: return launch_tb<KIND, T, 2, 16, 4, (T == 2 ? 2 : 1)>(g, map, box, lim, edge, s);
     }
 }
 

@@ -30,6 +30,23 @@ class CellModel:
         return None
 
     @property
+    def fuses_sweeps(self):
+        """the kernel family can take several sweeps per launch (b200geo_update_box_n)"""
+        return self.kernel in (capi.KERNEL_JACOBI6, capi.KERNEL_JACOBI7, capi.KERNEL_JACOBI27)
+
+    def halo_members(self, width):
+        """(members read from the low-side ghost slices, ... high-side) or None = whole cells.
+        LBM, ghost width 1: only the populations that cross the face are read from a neighbour's
+        plane (csrc/lbm.cu: T* from z-1; B* from z+1, plus SE which the EAST_NOSLIP rule of
+        src/examples/latticeboltzmann/main.cpp takes from z+1); a wider ghost zone recomputes the rim
+        and needs the neighbours' whole cells."""
+        if self.kernel == capi.KERNEL_LBM_D3Q19 and width == 1:
+            ix = self.member_index
+            return ([ix(n) for n in ("T", "TW", "TE", "TN", "TS")],
+                    [ix(n) for n in ("B", "BW", "BE", "BN", "BS", "SE")])
+        return None
+
+    @property
     def member_bytes(self):
         return [t.itemsize for _, t in self.members]
 

@@ -41,12 +41,18 @@ class HaloExchanger:
         self.low = rank - 1 if rank > 0 else (world - 1 if periodic and world > 1 else None)
         self.high = rank + 1 if rank < world - 1 else (0 if periodic and world > 1 else None)
         self.bytes_per_exchange = 0
-        self.packed = len(grid.model.members) > 1
+        n = len(grid.model.members)
+        # need[side]: the members the update reads from the ghost slices on that side. A model may
+        # name a subset (LBM with ghost width 1: the five populations that cross the face): those
+        # travel in place, member by member, without any pack kernel.
+        need = grid.model.halo_members(width)
+        self.need = need if need is not None else (list(range(n)), list(range(n)))
+        self.packed = n > 1 and need is None
         self._tensors = {}
         self._staging = None
 
-    def _block(self, member, side, kind):
-        blk = self.grid.dev.halo_block(member, side, kind, self.width)
+    def _block(self, member, side, kind, which=0):
+        blk = self.grid.dev.halo_block(member, side, kind, self.width, which=which)
         key = getattr(blk, "ptr", None)
         if key is None:
             return blk.as_tensor()
@@ -84,13 +90,19 @@ class HaloExchanger:
                 buf = torch.empty(cells * self.grid.model.cell_dtype.itemsize, dtype=torch.uint8, device="cuda")
                 self._staging[(side, kind)] = (st, buf)
 
-    def exchange(self):
-        """Fill `width` ghost slices on both PEER sides of the current buffer."""
-        dev, w = self.grid.dev, self.width
+    def post(self, which=0):
+        """Start filling `width` ghost slices on both PEER sides of the current (which = 0) or the
+        scratch (which = 1) buffer from the neighbours' outermost owned slices of the same buffer.
+        Returns the pending work handles; the transfer is ordered after everything enqueued so far
+        on the current stream and runs concurrently with whatever is enqueued next."""
+        dev = self.grid.dev
         if self.world == 1:
-            return
-        if self.packed and self._staging is None:
-            self._setup_staging()
+            return []
+        if self.packed:
+            if which != 0:
+                raise capi.LogicError("packed halo buffers are taken from the current grid buffer")
+            if self._staging is None:
+                self._setup_staging()
         ops = []
         nbytes = 0
         # post receives first, then sends; one batched group = one NCCL launch. Messages between one
@@ -100,29 +112,46 @@ class HaloExchanger:
         for side, peer in ((1, self.high), (0, self.low)):
             if peer is None:
                 continue
-            t = self._staging[(side, 1)][1] if self.packed else self._block(0, side, 1)
-            ops.append(self.dist.P2POp(self.dist.irecv, t, peer))
+            if self.packed:
+                ops.append(self.dist.P2POp(self.dist.irecv, self._staging[(side, 1)][1], peer))
+            else:
+                for m in self.need[side]:
+                    ops.append(self.dist.P2POp(self.dist.irecv, self._block(m, side, 1, which), peer))
         for side, peer in ((0, self.low), (1, self.high)):
             if peer is None:
                 continue
             if self.packed:
                 st, t = self._staging[(side, 0)]
                 dev.save_region(st, t, location=capi.CUDA_DEVICE)
+                nbytes += t.numel()
+                ops.append(self.dist.P2POp(self.dist.isend, t, peer))
             else:
-                t = self._block(0, side, 0)
-            nbytes += t.numel()
-            ops.append(self.dist.P2POp(self.dist.isend, t, peer))
-        if ops:
-            for work in self.dist.batch_isend_irecv(ops):
-                work.wait()
+                # our low-side rim lands in the neighbour's HIGH ghost: it wants need[1], and vice versa
+                for m in self.need[1 - side]:
+                    t = self._block(m, side, 0, which)
+                    nbytes += t.numel()
+                    ops.append(self.dist.P2POp(self.dist.isend, t, peer))
         self.bytes_per_exchange = nbytes
+        return self.dist.batch_isend_irecv(ops) if ops else []
+
+    def finish(self, works):
+        """Wait for post() (the current stream waits, not the host), unpack, declare the ghosts valid.
+        Call after the swap when post() addressed the scratch buffer."""
+        if self.world == 1:
+            return
+        for work in works:
+            work.wait()
         for side, peer in ((0, self.low), (1, self.high)):
             if peer is None:
                 continue
             if self.packed:
                 st, t = self._staging[(side, 1)]
-                dev.load_region(st, t, location=capi.CUDA_DEVICE, both=False)
-            dev.halo_mark_valid(side, w)
+                self.grid.dev.load_region(st, t, location=capi.CUDA_DEVICE, both=False)
+            self.grid.dev.halo_mark_valid(side, self.width)
+
+    def exchange(self):
+        """Fill `width` ghost slices on both PEER sides of the current buffer (blocking the stream)."""
+        self.finish(self.post(0))
 
 
 class StripedSimulator:
@@ -134,8 +163,10 @@ class StripedSimulator:
     own region, results are independent of the number of ranks.
     """
 
-    def __init__(self, initializer, model, rank=0, world=1, ghost_width=1, device=0, dist=None, engine=None):
+    def __init__(self, initializer, model, rank=0, world=1, ghost_width=1, device=0, dist=None, engine=None,
+                 overlap=True):
         self.initializer, self.model, self.rank, self.world = initializer, model, rank, world
+        self.overlap = overlap
         self.NANO_STEPS = model.nano_steps
         gdims = tuple(initializer.gridDimensions())
         last = model.dim - 1
@@ -179,17 +210,59 @@ class StripedSimulator:
         return self.grid
 
     def advance(self, nano_steps):
-        """nano_steps sweeps with one halo exchange per ghost_width sweeps."""
+        """nano_steps sweeps with one halo exchange per ghost_width sweeps.
+
+        Rounds of exactly ghost_width sweeps follow StripingSimulator::nanoStep's schedule
+        (parallelization/stripingsimulator.h:269-286): update the rims, start shipping them, update
+        the interior while they travel, wait. Anything else (a shorter tail, packed multi-member
+        halos) exchanges first and steps afterwards."""
         done = 0
+        w = self.ghost_width
         while done < nano_steps:
-            if self.world > 1 and self._valid == 0:
+            left = nano_steps - done
+            if self.world == 1:
+                self.grid.dev.step(self.model.kernel, n_steps=left, params=self.model.step_params(True))
+                return
+            if self._valid == 0:
                 self.halo.exchange()
-                self._valid = self.ghost_width
-            n = min(nano_steps - done, self._valid) if self.world > 1 else nano_steps - done
+                self._valid = w
+            if self.overlap and self._valid == w and left >= w and self._can_overlap():
+                self._overlapped_round(done + w == nano_steps)
+                done += w      # the ghosts are already valid again, w deep
+                continue
+            n = min(left, self._valid)
             self.grid.dev.step(self.model.kernel, n_steps=n, params=self.model.step_params(done + n == nano_steps))
-            if self.world > 1:
-                self._valid -= n
+            self._valid -= n
             done += n
+
+    def _can_overlap(self):
+        w, last = self.ghost_width, self.model.dim - 1
+        if self.halo.packed or self.grid.dims[last] < 2 * w:
+            return False
+        return w == 1 or (self.model.fuses_sweeps and w <= 4)
+
+    def _overlapped_round(self, final):
+        g, dev, w, last = self.grid, self.grid.dev, self.ghost_width, self.model.dim - 1
+        n = g.dims[last]
+        params = self.model.step_params(final)
+
+        def update(a, b):
+            if b <= a:
+                return
+            origin, dim = [0, 0, 0], list(g.dims) + [1] * (3 - len(g.dims))
+            origin[last], dim[last] = a, b - a
+            dev.update_box(self.model.kernel, origin, dim, params=params, n_sweeps=w)
+
+        if self.model.wraps:
+            dev.refresh_ghosts()
+        lo = w if self.halo.low is not None else 0
+        hi = n - w if self.halo.high is not None else n
+        update(0, lo)
+        update(hi, n)
+        works = self.halo.post(which=1)     # ships the new rims out of the scratch buffer
+        update(lo, hi)                      # overlaps with the transfer
+        dev.swap()
+        self.halo.finish(works)
 
     def step(self):
         feedback = SteererFeedback()

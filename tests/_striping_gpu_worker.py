@@ -32,7 +32,8 @@ class SlabInit(SimpleInitializer):
 def main():
     local = int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local), pg_options=opts)
     rank, world = dist.get_rank(), dist.get_world_size()
     failures = []
 
@@ -44,16 +45,19 @@ def main():
         if mine.shape != w.shape or not np.array_equal(mine.view(np.uint8), np.ascontiguousarray(w).view(np.uint8)):
             failures.append("%s rank %d" % (tag, rank))
 
-    for kind, topo, ghost, steps, shape in [(7, "Cube", 1, 6, (24, 18, 40)), (27, "Cube", 3, 8, (30, 12, 36)),
-                                            (27, "Torus", 2, 7, (16, 10, 34)), (6, "Torus", 1, 5, (12, 9, 20)),
-                                            (7, "Torus", 4, 9, (32, 8, 70))]:
+    jacobi_cases = [(7, "Cube", 1, 6, (24, 18, 40)), (27, "Cube", 3, 8, (30, 12, 36)),
+                    (27, "Torus", 2, 7, (16, 10, 34)), (6, "Torus", 1, 5, (12, 9, 20)),
+                    (7, "Torus", 4, 9, (32, 8, 70)), (27, "Cube", 2, 9, (40, 70, 130)), (7, "Torus", 2, 6, (48, 33, 65))]
+    # overlap = rim-first schedule with the interior update overlapping the transfer (fused sweeps per
+    # round through the temporal-blocked kernel); False = exchange, then step
+    for kind, topo, ghost, steps, shape, overlap in [c + (o,) for c in jacobi_cases for o in (True, False)]:
         nz, ny, nx = shape
         data = synth.jacobi_grid(nx, ny, nz, seed=kind)
         model = models.ALL["Jacobi%d%s" % (kind, topo)]
         sim = StripedSimulator(SlabInit({"temp": data}, (nx, ny, nz), steps, edge=0.75), model, rank=rank, world=world,
-                               ghost_width=ghost, device=local, dist=dist)
+                               ghost_width=ghost, device=local, dist=dist, overlap=overlap)
         sim.run()
-        check("jacobi%d%s g%d" % (kind, topo, ghost), sim, oracle_py.jacobi(kind, topo == "Torus", data, steps, edge=0.75), "temp")
+        check("jacobi%d%s g%d overlap %s" % (kind, topo, ghost, overlap), sim, oracle_py.jacobi(kind, topo == "Torus", data, steps, edge=0.75), "temp")
 
     for topo, ghost, steps, shape in [("Cube", 1, 12, (64, 100)), ("Torus", 3, 10, (48, 70))]:
         ny, nx = shape
@@ -64,16 +68,17 @@ def main():
         sim.run()
         check("gol%s g%d" % (topo, ghost), sim, oracle_py.gol(topo == "Torus", g, steps), "alive")
 
-    for ghost, steps, shape in [(1, 9, (20, 12, 16)), (2, 8, (24, 10, 18))]:
+    for ghost, steps, shape, overlap in [(1, 9, (20, 12, 16), True), (1, 9, (20, 12, 16), False), (2, 8, (24, 10, 18), True),
+                                         (1, 6, (32, 40, 70), True)]:
         nz, ny, nx = shape
         raw = synth.lbm_grid(nx, ny, nz, noise=0.01)
         members = {n: raw[m].view(t) for m, (n, t) in enumerate(models.LBMCellF.members)}
         sim = StripedSimulator(SlabInit(members, (nx, ny, nz), steps), models.LBMCellF, rank=rank, world=world,
-                               ghost_width=ghost, device=local, dist=dist)
+                               ghost_width=ghost, device=local, dist=dist, overlap=overlap)
         sim.run()
         want = oracle_py.lbm(raw, steps)
         for m, (n, t) in enumerate(models.LBMCellF.members):
-            check("lbm g%d %s" % (ghost, n), sim, want[m].view(t), n)
+            check("lbm g%d overlap %s %s" % (ghost, overlap, n), sim, want[m].view(t), n)
 
     with open("%s.%d" % (sys.argv[1], rank), "w") as f:
         f.write("FAIL " + "; ".join(failures) if failures else "OK")

@@ -34,19 +34,21 @@ def main():
     rank, world = dist.get_rank(), dist.get_world_size()
     out_path = sys.argv[1]
     failures = []
-    for kind, ghost, steps, shape in [(7, 1, 5, (12, 9, 10)), (27, 3, 7, (16, 6, 8)), (6, 2, 6, (13, 5, 4)), (27, 4, 9, (12, 4, 4))]:
+    cases = [(7, 1, 5, (12, 9, 10)), (27, 3, 7, (16, 6, 8)), (6, 2, 6, (13, 5, 4)), (27, 4, 9, (12, 4, 4))]
+    # every case with the rim-first / interior-overlapped schedule and with exchange-then-step
+    for kind, ghost, steps, shape, overlap in [c + (o,) for c in cases for o in (True, False)] + [(7, 2, 8, (24, 5, 6), True)]:
         nz, ny, nx = shape
         data = synth.jacobi_grid(nx, ny, nz, seed=kind)
         model = models.ALL["Jacobi%dCube" % kind]
         sim = StripedSimulator(SlabInit(data, steps, 0.75), model, rank=rank, world=world, ghost_width=ghost,
-                               dist=dist, engine=cpu_engine)
+                               dist=dist, engine=cpu_engine, overlap=overlap)
         sim.run()
         assert sim.getStep() == steps
         b = slab_bounds(nz, world)
         mine = sim.getGrid().saveMember("temp")
         want = oracle_py.jacobi(kind, False, data, steps, edge=0.75)[b[rank]:b[rank + 1]]
         if mine.shape != want.shape or not np.array_equal(mine, want):
-            failures.append("kind %d ghost %d rank %d" % (kind, ghost, rank))
+            failures.append("kind %d ghost %d overlap %s rank %d" % (kind, ghost, overlap, rank))
     with open("%s.%d" % (out_path, rank), "w") as f:
         f.write("FAIL " + "; ".join(failures) if failures else "OK")
     dist.barrier()
