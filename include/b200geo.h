@@ -171,6 +171,53 @@ int b200geo_halo_push(b200geo_grid *g, int side, int width, void *stream);
  * (called after an exchange done by the caller, e.g. NCCL send/recv into b200geo_halo_block). */
 int b200geo_halo_mark_valid(b200geo_grid *g, int side, int width);
 
+/* ---- BoxCell container grids: short-range n-body (B200GEO_KERNEL_NBODY) -------------------------
+ * Replaces Grid<BoxCell<FixedArray<Particle, N> > > (storage/boxcell.h:21-178, storage/fixedarray.h:21-140)
+ * and, on the step path, BoxCell::update with its re-binning (boxcell.h:112-174), the position checker
+ * (misc/apitraits.h:1074-1088) and the particle iteration order of NeighborhoodIterator
+ * (storage/neighborhooditerator.h:71-186) for the bound particle model (oracle/models/nbody.h).
+ * Interchange format of a box of containers (what GridBase::set/get(Coord, BoxCell) carry, flattened):
+ *   counts    int32 [dz][dy][dx]
+ *   particles REAL  [dz][dy][dx][capacity][6]   pos x,y,z, vel x,y,z; slots >= count are ignored on
+ *                                               load and zero on save
+ * Container (x, y, z) covers [ (c + cell_origin) * cell_edge, + cell_edge ) per axis (doubles), which
+ * is how the bound model's Initializer constructs BoxCell(origin, dimension). */
+typedef struct {
+    int32_t dim[3];           /* containers per axis */
+    int32_t ghost_mode[3][2]; /* EDGE (Cube: the empty edge container) or, on the last axis, PEER */
+    int32_t capacity;         /* N of FixedArray<Particle, N>, 1..64 */
+    int32_t real_bytes;       /* 4: float particles, 8: double */
+    int32_t cell_origin[3];   /* global index of container (0,0,0) (slab partitions) */
+    double cell_edge;
+} b200geo_boxgrid_desc;
+
+typedef struct {
+    double dt;
+    double cutoff;            /* <= cell_edge */
+    int32_t nano_steps;       /* APITraits::SelectNanoSteps of the cargo: re-bin when nanoStep % nano_steps == 0 */
+} b200geo_nbody_params;
+
+typedef struct b200geo_boxgrid b200geo_boxgrid;
+
+int b200geo_boxgrid_create(const b200geo_boxgrid_desc *desc, int device, b200geo_boxgrid **out);
+int b200geo_boxgrid_destroy(b200geo_boxgrid *g);
+/* GridBase::set / get for a box of containers (ghost containers addressable with -1 / dim). */
+int b200geo_boxgrid_load(b200geo_boxgrid *g, const int32_t origin[3], const int32_t dim[3], const int32_t *counts,
+                         const void *particles, int location, int both, void *stream);
+int b200geo_boxgrid_save(const b200geo_boxgrid *g, const int32_t origin[3], const int32_t dim[3], int32_t *counts,
+                         void *particles, int location, void *stream);
+/* n_steps x { re-bin (or copy), update every particle against the old grid; swap }. */
+int b200geo_boxgrid_step(b200geo_boxgrid *g, const b200geo_nbody_params *params, uint32_t first_nano_step,
+                         uint32_t n_steps, void *stream);
+/* Synchronises and returns B200GEO_ERR_OUT_OF_RANGE ("capacity exceeded", storage/fixedarray.h:77-83)
+ * if a container overflowed since the last check; the surplus particles were dropped. */
+int b200geo_boxgrid_check(b200geo_boxgrid *g, void *stream);
+/* One ghost (kind 1) or outermost owned (kind 0) plane of containers on `side` of the last axis, as a
+ * contiguous block: array 0 = counts, 1 = particles; which = current (0) / scratch (1) buffer. */
+int b200geo_boxgrid_halo_block(const b200geo_boxgrid *g, int array, int side, int kind, int which, void **ptr,
+                               uint64_t *bytes);
+int b200geo_boxgrid_halo_mark_valid(b200geo_boxgrid *g, int side, int width);
+
 /* ---- statistics: Simulator::gatherStatistics / Chronometer (misc/chronometer.h:142-150) ---- */
 /* out[0] = device seconds spent in update kernels (TimeComputeInner), out[1] = seconds in ghost
  * refresh / halo copies (TimeComputeGhost + TimeCommunication), out[2] = number of sweeps. Uses

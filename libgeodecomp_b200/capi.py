@@ -35,6 +35,19 @@ class GridDesc(ctypes.Structure):
                 ("member_bytes", ctypes.c_int32 * MAX_MEMBERS)]
 
 
+class BoxGridDesc(ctypes.Structure):
+    _fields_ = [("dim", ctypes.c_int32 * 3),
+                ("ghost_mode", (ctypes.c_int32 * 2) * 3),
+                ("capacity", ctypes.c_int32),
+                ("real_bytes", ctypes.c_int32),
+                ("cell_origin", ctypes.c_int32 * 3),
+                ("cell_edge", ctypes.c_double)]
+
+
+class NBodyParams(ctypes.Structure):
+    _fields_ = [("dt", ctypes.c_double), ("cutoff", ctypes.c_double), ("nano_steps", ctypes.c_int32)]
+
+
 _lib = None
 
 # every symbol include/b200geo.h declares: (name, restype, argtypes)
@@ -70,6 +83,15 @@ SYMBOLS = [
     ("b200geo_grid_ipc_open", ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, _vp]),
     ("b200geo_halo_push", ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, _vp]),
     ("b200geo_halo_mark_valid", ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int]),
+    ("b200geo_boxgrid_create", ctypes.c_int, [ctypes.POINTER(BoxGridDesc), ctypes.c_int, ctypes.POINTER(_vp)]),
+    ("b200geo_boxgrid_destroy", ctypes.c_int, [_vp]),
+    ("b200geo_boxgrid_load", ctypes.c_int, [_vp, _i32p, _i32p, _vp, _vp, ctypes.c_int, ctypes.c_int, _vp]),
+    ("b200geo_boxgrid_save", ctypes.c_int, [_vp, _i32p, _i32p, _vp, _vp, ctypes.c_int, _vp]),
+    ("b200geo_boxgrid_step", ctypes.c_int, [_vp, ctypes.POINTER(NBodyParams), ctypes.c_uint32, ctypes.c_uint32, _vp]),
+    ("b200geo_boxgrid_check", ctypes.c_int, [_vp, _vp]),
+    ("b200geo_boxgrid_halo_block", ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                                  ctypes.POINTER(_vp), ctypes.POINTER(ctypes.c_uint64)]),
+    ("b200geo_boxgrid_halo_mark_valid", ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int]),
     ("b200geo_stats_enable", ctypes.c_int, [_vp, ctypes.c_int]),
     ("b200geo_stats", ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_double)]),
 ]
@@ -266,6 +288,69 @@ class DeviceGrid:
         out = (ctypes.c_double * 3)()
         check(lib().b200geo_stats(self._h, out))
         return {"update_s": out[0], "ghost_s": out[1], "sweeps": int(out[2])}
+
+
+class DeviceBoxGrid:
+    """Thin object wrapper around a b200geo_boxgrid handle (BoxCell container grid, n-body)."""
+
+    def __init__(self, dim, capacity, real_bytes, cell_edge, cell_origin=(0, 0, 0), ghost_mode=None, device=0):
+        self._h = None
+        desc = BoxGridDesc()
+        for i in range(3):
+            desc.dim[i] = int(dim[i])
+            desc.cell_origin[i] = int(cell_origin[i])
+            for s in range(2):
+                desc.ghost_mode[i][s] = int(ghost_mode[i][s]) if ghost_mode is not None else GHOST_EDGE
+        desc.capacity, desc.real_bytes, desc.cell_edge = int(capacity), int(real_bytes), float(cell_edge)
+        h = ctypes.c_void_p()
+        check(lib().b200geo_boxgrid_create(ctypes.byref(desc), int(device), ctypes.byref(h)))
+        self._h = h
+        self.dim, self.capacity, self.real_bytes, self.device = tuple(dim), int(capacity), int(real_bytes), device
+
+    def close(self):
+        if self._h is not None and _lib is not None:
+            _lib.b200geo_boxgrid_destroy(self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def load(self, counts, particles, origin=(0, 0, 0), dim=None, location=HOST, both=True, stream=None):
+        dim = self.dim if dim is None else dim
+        check(lib().b200geo_boxgrid_load(self._h, _i3(origin), _i3(dim), _ptr(counts), _ptr(particles), location,
+                                         1 if both else 0, stream))
+
+    def save(self, counts, particles, origin=(0, 0, 0), dim=None, location=HOST, stream=None):
+        dim = self.dim if dim is None else dim
+        check(lib().b200geo_boxgrid_save(self._h, _i3(origin), _i3(dim), _ptr(counts), _ptr(particles), location, stream))
+
+    def step(self, kernel, n_steps=1, first_nano_step=0, params=None, stream=None):
+        if kernel != KERNEL_NBODY or not isinstance(params, NBodyParams):
+            raise LogicError("a BoxCell grid steps with KERNEL_NBODY and NBodyParams")
+        check(lib().b200geo_boxgrid_step(self._h, ctypes.byref(params), first_nano_step, n_steps, stream))
+
+    def check(self, stream=None):
+        """raises IndexError (std::out_of_range "capacity exceeded") if a container overflowed"""
+        check(lib().b200geo_boxgrid_check(self._h, stream))
+
+    def halo_block(self, member, side, kind, width=1, which=0):
+        if width != 1:
+            raise ValueError("BoxCell grids have a ghost zone of one container")
+        p, n = ctypes.c_void_p(), ctypes.c_uint64()
+        check(lib().b200geo_boxgrid_halo_block(self._h, member, side, kind, which, ctypes.byref(p), ctypes.byref(n)))
+        return DeviceBlock(p.value, n.value, self)
+
+    def halo_mark_valid(self, side, width):
+        check(lib().b200geo_boxgrid_halo_mark_valid(self._h, side, width))
+
+    def stats_enable(self, on=True):
+        pass
+
+    def stats(self):
+        return {}
 
 
 def sync(stream=None):

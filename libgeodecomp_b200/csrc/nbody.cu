@@ -1,0 +1,483 @@
+// Short-range n-body in BoxCell containers (B200GEO_KERNEL_NBODY): device-resident cell-list
+// grid, re-binning and particle update.
+//
+// Replaces, for the bound particle model (oracle/models/nbody.h: Lennard-Jones 12-6 truncated at the
+// cutoff, velocity += force * dt neighbour by neighbour, then pos += vel * dt), the reference's
+//   BoxCell::update / copyOver / addContainedParticles / updateCargo   storage/boxcell.h:112-174
+//   SelectPositionChecker (origin <= pos < origin + dimension, doubles) misc/apitraits.h:1074-1088
+//   NeighborhoodIterator (27 cells in CoordBox order, x fastest; particles in storage order)
+//                                                                       storage/neighborhooditerator.h:71-186
+//   FixedArray<Particle, N> (capacity N, operator<< throws std::out_of_range when full)
+//                                                                       storage/fixedarray.h:21-83
+// Same expression trees, same neighbour order, compiled -fmad=false against a -ffp-contract=off
+// oracle: positions and velocities are bit-identical to the reference's SerialSimulator.
+//
+// Layout in HBM (per buffer; two buffers, swapped per sweep like the stencil grids):
+//   counts    int32 [nz+2][ny+2][nx+2]            one ring of ghost containers: EDGE = the empty
+//   particles REAL  [nz+2][ny+2][nx+2][6][cap]     edge container of a Cube, PEER = a slab neighbour's
+// i.e. SoA inside a container (x[cap], y[cap], z[cap], vx[cap], vy[cap], vz[cap]): a warp reading
+// one component of one container touches one or two 128-byte lines, and a z-slab's ghost plane is
+// one contiguous block per array (halo exchange in place, no pack kernel).
+//
+// Roofline: FP32/FP64 pipe, not HBM (about 27 * <n> candidate pairs per particle at ~35 flop
+// versus 24 + 24 bytes per particle of traffic) and no tensor cores (no dense contraction).
+//
+// Two kernels per sweep:
+//   rebin_kernel   one warp per container: scans the 27 old containers in order, keeps the
+//                  particles whose position lies in this container's box (ordered compaction by
+//                  ballot/popc), writes the new container;
+//   force_kernel   one CTA per run of G x-adjacent containers: stages the positions of the
+//                  (G + 2) x 3 x 3 surrounding OLD containers in shared memory, packs the run's new
+//                  particles densely onto threads (so lanes are not wasted on empty slots), and
+//                  each thread walks its particle's 27 containers in reference order.
+#include "grid.h"
+
+#include <cstring>
+#include <new>
+
+struct b200geo_boxgrid {
+    b200geo_boxgrid_desc desc;
+    int device;
+    int d[3];
+    int cap, real;
+    int64_t pcells;             // padded containers per buffer
+    int32_t *counts[2];
+    char *parts[2];
+    int cur;
+    int peer_valid[2];
+    int *overflow;              // device flag: a container overflowed
+    char *staging;              // bulk I/O staging (device)
+    size_t staging_bytes;
+    uint64_t sweeps;
+
+    int64_t cell_index(int x, int y, int z) const { return ((int64_t)(z + 1) * (d[1] + 2) + (y + 1)) * (d[0] + 2) + (x + 1); }
+    size_t cell_bytes() const { return (size_t)6 * cap * real; }
+};
+
+namespace b200geo {
+
+namespace {
+
+struct BoxDims {
+    int nx, ny, nz, cap;
+    int org[3];
+    double edge;
+};
+
+__device__ __forceinline__ int64_t pcell(const BoxDims& D, int x, int y, int z)
+{
+    return ((int64_t)(z + 1) * (D.ny + 2) + (y + 1)) * (D.nx + 2) + (x + 1);
+}
+
+// addContainedParticles over the Moore hood (boxcell.h:123-138,164-174); rebin = 0 copies the
+// container (nanoStep != 0).
+template<typename REAL>
+__global__ void __launch_bounds__(128)
+rebin_kernel(const int32_t *__restrict__ cnt_old, const REAL *__restrict__ part_old, int32_t *__restrict__ cnt_new,
+             REAL *__restrict__ part_new, BoxDims D, int z0, int z1, int rebin, int *overflow)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t w = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t row_cells = (int64_t)D.nx * D.ny;
+    if (w >= row_cells * (z1 - z0)) return;
+    const int z = z0 + (int)(w / row_cells);
+    const int y = (int)((w % row_cells) / D.nx), x = (int)(w % D.nx);
+    const int64_t self = pcell(D, x, y, z);
+    const int cap = D.cap;
+    REAL *mine = part_new + self * 6 * cap;
+    if (!rebin) {
+        int n = cnt_old[self];
+        const REAL *src = part_old + self * 6 * cap;
+        for (int i = lane; i < 6 * cap; i += 32) mine[i] = src[i];
+        if (lane == 0) cnt_new[self] = n;
+        return;
+    }
+    const double ox = (double)(x + D.org[0]) * D.edge, oy = (double)(y + D.org[1]) * D.edge, oz = (double)(z + D.org[2]) * D.edge;
+    const double qx = ox + D.edge, qy = oy + D.edge, qz = oz + D.edge;
+    int n = 0;
+    for (int k = 0; k < 27; ++k) {
+        const int64_t nb = pcell(D, x + k % 3 - 1, y + (k / 3) % 3 - 1, z + k / 9 - 1);
+        const int c = cnt_old[nb];
+        const REAL *src = part_old + nb * 6 * cap;
+        for (int base = 0; base < c; base += 32) {
+            const int s = base + lane;
+            bool inside = false;
+            if (s < c) {
+                double px = src[s], py = src[cap + s], pz = src[2 * cap + s];
+                inside = ox <= px && oy <= py && oz <= pz && px < qx && py < qy && pz < qz;
+            }
+            const unsigned mask = __ballot_sync(0xffffffffu, inside);
+            if (inside) {
+                const int dst = n + __popc(mask & ((1u << lane) - 1));
+                if (dst < cap) {
+#pragma unroll
+                    for (int q = 0; q < 6; ++q) mine[q * cap + dst] = src[q * cap + s];
+                }
+            }
+            n += __popc(mask);
+        }
+    }
+    if (lane == 0) {
+        cnt_new[self] = n < cap ? n : cap;
+        if (n > cap) atomicOr(overflow, 1);  // FixedArray::operator<<: "capacity exceeded"
+    }
+}
+
+// updateCargo (boxcell.h:140-152) with LJParticle::update (oracle/models/nbody.h).
+template<typename REAL, int G>
+__global__ void __launch_bounds__(128)
+force_kernel(const int32_t *__restrict__ cnt_old, const REAL *__restrict__ part_old, const int32_t *__restrict__ cnt_new,
+             REAL *__restrict__ part_new, BoxDims D, int z0, int runs_per_row, REAL dt, REAL rc2)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int cap = D.cap;
+    REAL *spos = reinterpret_cast<REAL *>(smem_raw);            // [(G + 2) * 9][3][cap]
+    int *scnt = reinterpret_cast<int *>(spos + (G + 2) * 9 * 3 * cap);  // [(G + 2) * 9]
+    int *pre = scnt + (G + 2) * 9;                              // [G + 1]
+
+    const int run = blockIdx.x % runs_per_row;
+    const int y = (blockIdx.x / runs_per_row) % D.ny;
+    const int z = z0 + blockIdx.x / (runs_per_row * D.ny);
+    const int x0 = run * G;
+
+    // stage the old neighbourhood of the whole run: local (lx, ly, lz) = cell (x0 - 1 + lx, y - 1 + ly, z - 1 + lz)
+    for (int c = threadIdx.x; c < (G + 2) * 9; c += blockDim.x) {
+        int lx = c % (G + 2), ly = (c / (G + 2)) % 3, lz = c / ((G + 2) * 3);
+        int cx = x0 - 1 + lx;
+        scnt[c] = cx <= D.nx ? cnt_old[pcell(D, cx, y - 1 + ly, z - 1 + lz)] : 0;
+    }
+    if (threadIdx.x <= G) {
+        int acc = 0;
+        for (int j = 0; j < (int)threadIdx.x; ++j) acc += (x0 + j < D.nx) ? cnt_new[pcell(D, x0 + j, y, z)] : 0;
+        pre[threadIdx.x] = acc;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < (G + 2) * 9 * 3 * cap; i += blockDim.x) {
+        int c = i / (3 * cap), r = i % (3 * cap);
+        if (r % cap < scnt[c]) {
+            int lx = c % (G + 2), ly = (c / (G + 2)) % 3, lz = c / ((G + 2) * 3);
+            spos[i] = part_old[pcell(D, x0 - 1 + lx, y - 1 + ly, z - 1 + lz) * 6 * cap + r];
+        }
+    }
+    __syncthreads();
+
+    const int total = pre[G];
+    for (int t = threadIdx.x; t < total; t += blockDim.x) {
+        int j = 0;
+        while (pre[j + 1] <= t) ++j;
+        const int slot = t - pre[j];
+        REAL *me = part_new + pcell(D, x0 + j, y, z) * 6 * cap + slot;
+        const REAL p0 = me[0], p1 = me[cap], p2 = me[2 * cap];
+        REAL v0 = me[3 * cap], v1 = me[4 * cap], v2 = me[5 * cap];
+        for (int k = 0; k < 27; ++k) {
+            const int c = ((k / 9) * 3 + (k / 3) % 3) * (G + 2) + j + k % 3;
+            const int n = scnt[c];
+            const REAL *s = spos + c * 3 * cap;
+            for (int p = 0; p < n; ++p) {
+                const REAL d0 = p0 - s[p], d1 = p1 - s[cap + p], d2 = p2 - s[2 * cap + p];
+                const REAL r2 = (d0 * d0 + d1 * d1) + d2 * d2;
+                if (r2 == (REAL)0 || r2 >= rc2) continue;
+                const REAL inv = (REAL)1 / r2;
+                const REAL s6 = inv * inv * inv;
+                const REAL f = ((REAL)24 * inv) * s6 * ((REAL)2 * s6 - (REAL)1);
+                v0 += (d0 * f) * dt;
+                v1 += (d1 * f) * dt;
+                v2 += (d2 * f) * dt;
+            }
+        }
+        me[0] = p0 + v0 * dt;
+        me[cap] = p1 + v1 * dt;
+        me[2 * cap] = p2 + v2 * dt;
+        me[3 * cap] = v0;
+        me[4 * cap] = v1;
+        me[5 * cap] = v2;
+    }
+}
+
+// dense AoS [cells][cap][6] (host interchange format) <-> SoA containers of a box
+template<typename REAL, bool LOAD>
+__global__ void transpose_kernel(int32_t *cnt, REAL *part, BoxDims D, int ox, int oy, int oz, int dx, int dy, int dz,
+                                 int32_t *dense_cnt, REAL *dense_part)
+{
+    const int64_t cells = (int64_t)dx * dy * dz;
+    const int cap = D.cap;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < cells * cap * 6; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t c = i / (cap * 6);
+        int r = (int)(i % (cap * 6)), s = r / 6, q = r % 6;
+        int x = (int)(c % dx), y = (int)((c / dx) % dy), z = (int)(c / ((int64_t)dx * dy));
+        int64_t pc = pcell(D, ox + x, oy + y, oz + z);
+        if (LOAD) {
+            part[pc * 6 * cap + q * cap + s] = dense_part[i];
+            if (r == 0) cnt[pc] = dense_cnt[c];
+        } else {
+            dense_part[i] = s < cnt[pc] ? part[pc * 6 * cap + q * cap + s] : (REAL)0;
+            if (r == 0) dense_cnt[c] = cnt[pc];
+        }
+    }
+}
+
+BoxDims box_dims(const b200geo_boxgrid *g)
+{
+    BoxDims D;
+    D.nx = g->d[0];
+    D.ny = g->d[1];
+    D.nz = g->d[2];
+    D.cap = g->cap;
+    for (int i = 0; i < 3; ++i) D.org[i] = g->desc.cell_origin[i];
+    D.edge = g->desc.cell_edge;
+    return D;
+}
+
+constexpr int RUN = 8;  // containers per CTA of the force kernel
+
+template<typename REAL>
+int sweep(b200geo_boxgrid *g, const b200geo_nbody_params *p, int rebin, cudaStream_t s)
+{
+    BoxDims D = box_dims(g);
+    const int32_t *co = g->counts[g->cur];
+    int32_t *cn = g->counts[g->cur ^ 1];
+    const REAL *po = (const REAL *)g->parts[g->cur];
+    REAL *pn = (REAL *)g->parts[g->cur ^ 1];
+    int64_t cells = (int64_t)D.nx * D.ny * D.nz;
+    rebin_kernel<REAL><<<(unsigned)((cells + 3) / 4), 128, 0, s>>>(co, po, cn, pn, D, 0, D.nz, rebin, g->overflow);
+    count_launch();
+    int runs = (D.nx + RUN - 1) / RUN;
+    size_t smem = (size_t)(RUN + 2) * 9 * 3 * g->cap * sizeof(REAL) + ((RUN + 2) * 9 + RUN + 1) * sizeof(int);
+    static bool attr = false;
+    if (!attr) {
+        B200GEO_CUDA(cudaFuncSetAttribute(force_kernel<REAL, RUN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        attr = true;
+    }
+    REAL rc = (REAL)p->cutoff;
+    force_kernel<REAL, RUN><<<(unsigned)((int64_t)runs * D.ny * D.nz), 128, smem, s>>>(co, po, cn, pn, D, 0, runs, (REAL)p->dt, rc * rc);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "n-body sweep");
+}
+
+int ensure_staging(b200geo_boxgrid *g, size_t bytes, cudaStream_t s)
+{
+    if (g->staging_bytes >= bytes) return 0;
+    if (g->staging) {
+        cudaStreamSynchronize(s);
+        cudaFree(g->staging);
+        g->staging = 0;
+        g->staging_bytes = 0;
+    }
+    cudaError_t e = cudaMalloc((void **)&g->staging, bytes);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(B200GEO_ERR_NOMEM, std::string("cudaMalloc failed: ") + cudaGetErrorString(e));
+    }
+    g->staging_bytes = bytes;
+    return 0;
+}
+
+bool valid_cell_box(const b200geo_boxgrid *g, const int32_t o[3], const int32_t d[3])
+{
+    for (int i = 0; i < 3; ++i)
+        if (d[i] < 0 || o[i] < -1 || o[i] + d[i] > g->d[i] + 1) return false;
+    return true;
+}
+
+template<typename REAL>
+int box_io(b200geo_boxgrid *g, const int32_t o[3], const int32_t d[3], void *counts, void *parts, int location,
+           bool load, int both, cudaStream_t s)
+{
+    int64_t cells = (int64_t)d[0] * d[1] * d[2];
+    if (cells == 0) return B200GEO_OK;
+    size_t cb = (size_t)cells * sizeof(int32_t), pb = (size_t)cells * g->cap * 6 * sizeof(REAL);
+    int32_t *dc = (int32_t *)counts;
+    REAL *dp = (REAL *)parts;
+    if (location == B200GEO_HOST) {
+        size_t off = (cb + 255) / 256 * 256;
+        int rc = ensure_staging(g, off + pb, s);
+        if (rc) return rc;
+        dc = (int32_t *)g->staging;
+        dp = (REAL *)(g->staging + off);
+        if (load) {
+            B200GEO_CUDA(cudaMemcpyAsync(dc, counts, cb, cudaMemcpyHostToDevice, s));
+            B200GEO_CUDA(cudaMemcpyAsync(dp, parts, pb, cudaMemcpyHostToDevice, s));
+        }
+    }
+    BoxDims D = box_dims(g);
+    int blocks = (int)((cells * g->cap * 6 + 255) / 256 < 148 * 16 ? (cells * g->cap * 6 + 255) / 256 : 148 * 16);
+    if (load) {
+        for (int b = 0; b < (both ? 2 : 1); ++b) {
+            transpose_kernel<REAL, true><<<blocks, 256, 0, s>>>(g->counts[g->cur ^ b], (REAL *)g->parts[g->cur ^ b], D,
+                                                               o[0], o[1], o[2], d[0], d[1], d[2], dc, dp);
+            count_launch();
+        }
+    } else {
+        transpose_kernel<REAL, false><<<blocks, 256, 0, s>>>(g->counts[g->cur], (REAL *)g->parts[g->cur], D,
+                                                            o[0], o[1], o[2], d[0], d[1], d[2], dc, dp);
+        count_launch();
+        if (location == B200GEO_HOST) {
+            B200GEO_CUDA(cudaMemcpyAsync(counts, dc, cb, cudaMemcpyDeviceToHost, s));
+            B200GEO_CUDA(cudaMemcpyAsync(parts, dp, pb, cudaMemcpyDeviceToHost, s));
+        }
+    }
+    B200GEO_CUDA(cudaGetLastError());
+    if (location == B200GEO_HOST) B200GEO_CUDA(cudaStreamSynchronize(s));  // the staging buffer is reused
+    return B200GEO_OK;
+}
+
+}
+
+}
+
+using namespace b200geo;
+
+extern "C" {
+
+int b200geo_boxgrid_create(const b200geo_boxgrid_desc *desc, int device, b200geo_boxgrid **out)
+{
+    if (!desc || !out) return fail(B200GEO_ERR_INVALID, "null argument");
+    for (int i = 0; i < 3; ++i) {
+        if (desc->dim[i] < 1) return fail(B200GEO_ERR_INVALID, "grid dimension must be >= 1");
+        for (int s = 0; s < 2; ++s) {
+            int mode = desc->ghost_mode[i][s];
+            if (mode == B200GEO_GHOST_WRAP)
+                return fail(B200GEO_ERR_LOGIC, "BoxCell grids are Cube grids: the reference's BoxCell does not shift positions across a Torus seam");
+            if (mode == B200GEO_GHOST_PEER && i != 2)
+                return fail(B200GEO_ERR_LOGIC, "PEER ghost layers are supported on the last axis only (slab partition)");
+            if (mode != B200GEO_GHOST_EDGE && mode != B200GEO_GHOST_PEER) return fail(B200GEO_ERR_INVALID, "bad ghost mode");
+        }
+    }
+    if (desc->capacity < 1 || desc->capacity > 64) return fail(B200GEO_ERR_INVALID, "capacity must be 1..64");
+    if (desc->real_bytes != 4 && desc->real_bytes != 8) return fail(B200GEO_ERR_INVALID, "real_bytes must be 4 or 8");
+    if (!(desc->cell_edge > 0)) return fail(B200GEO_ERR_INVALID, "cell_edge must be positive");
+    B200GEO_CUDA(cudaSetDevice(device));
+    b200geo_boxgrid *g = new (std::nothrow) b200geo_boxgrid();
+    if (!g) return fail(B200GEO_ERR_NOMEM, "out of host memory");
+    memset(g, 0, sizeof(*g));
+    g->desc = *desc;
+    g->device = device;
+    for (int i = 0; i < 3; ++i) g->d[i] = desc->dim[i];
+    g->cap = desc->capacity;
+    g->real = desc->real_bytes;
+    g->pcells = (int64_t)(g->d[0] + 2) * (g->d[1] + 2) * (g->d[2] + 2);
+    cudaError_t e = cudaSuccess;
+    for (int b = 0; b < 2 && e == cudaSuccess; ++b) {
+        e = cudaMalloc((void **)&g->counts[b], (size_t)g->pcells * sizeof(int32_t));
+        if (e == cudaSuccess) e = cudaMalloc((void **)&g->parts[b], (size_t)g->pcells * g->cell_bytes());
+    }
+    if (e == cudaSuccess) e = cudaMalloc((void **)&g->overflow, sizeof(int));
+    if (e != cudaSuccess) {
+        b200geo_boxgrid_destroy(g);
+        cudaGetLastError();
+        return fail(B200GEO_ERR_NOMEM, std::string("cudaMalloc failed: ") + cudaGetErrorString(e));
+    }
+    // every container starts empty: the EDGE ring is the reference's default-constructed edge cell
+    for (int b = 0; b < 2; ++b) {
+        cudaMemset(g->counts[b], 0, (size_t)g->pcells * sizeof(int32_t));
+        cudaMemset(g->parts[b], 0, (size_t)g->pcells * g->cell_bytes());
+    }
+    cudaMemset(g->overflow, 0, sizeof(int));
+    *out = g;
+    return B200GEO_OK;
+}
+
+int b200geo_boxgrid_destroy(b200geo_boxgrid *g)
+{
+    if (!g) return B200GEO_OK;
+    cudaSetDevice(g->device);
+    for (int b = 0; b < 2; ++b) {
+        if (g->counts[b]) cudaFree(g->counts[b]);
+        if (g->parts[b]) cudaFree(g->parts[b]);
+    }
+    if (g->overflow) cudaFree(g->overflow);
+    if (g->staging) cudaFree(g->staging);
+    delete g;
+    return B200GEO_OK;
+}
+
+int b200geo_boxgrid_load(b200geo_boxgrid *g, const int32_t origin[3], const int32_t dim[3], const int32_t *counts,
+                         const void *particles, int location, int both, void *stream)
+{
+    if (!g || !origin || !dim || !counts || !particles) return fail(B200GEO_ERR_INVALID, "null argument");
+    if (!valid_cell_box(g, origin, dim)) return fail(B200GEO_ERR_INVALID, "box outside the grid");
+    B200GEO_CUDA(cudaSetDevice(g->device));
+    if (g->real == 4)
+        return box_io<float>(g, origin, dim, const_cast<int32_t *>(counts), const_cast<void *>(particles), location, true, both, (cudaStream_t)stream);
+    return box_io<double>(g, origin, dim, const_cast<int32_t *>(counts), const_cast<void *>(particles), location, true, both, (cudaStream_t)stream);
+}
+
+int b200geo_boxgrid_save(const b200geo_boxgrid *g, const int32_t origin[3], const int32_t dim[3], int32_t *counts,
+                         void *particles, int location, void *stream)
+{
+    if (!g || !origin || !dim || !counts || !particles) return fail(B200GEO_ERR_INVALID, "null argument");
+    if (!valid_cell_box(g, origin, dim)) return fail(B200GEO_ERR_INVALID, "box outside the grid");
+    B200GEO_CUDA(cudaSetDevice(g->device));
+    b200geo_boxgrid *m = const_cast<b200geo_boxgrid *>(g);
+    if (g->real == 4) return box_io<float>(m, origin, dim, counts, particles, location, false, 0, (cudaStream_t)stream);
+    return box_io<double>(m, origin, dim, counts, particles, location, false, 0, (cudaStream_t)stream);
+}
+
+int b200geo_boxgrid_step(b200geo_boxgrid *g, const b200geo_nbody_params *params, uint32_t first_nano_step,
+                         uint32_t n_steps, void *stream)
+{
+    if (!g || !params) return fail(B200GEO_ERR_INVALID, "null argument");
+    if (params->nano_steps < 1) return fail(B200GEO_ERR_INVALID, "nano_steps must be >= 1");
+    if (!(params->cutoff <= g->desc.cell_edge))
+        return fail(B200GEO_ERR_INVALID, "cutoff larger than the container edge: interactions would be missed");
+    B200GEO_CUDA(cudaSetDevice(g->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    for (uint32_t t = 0; t < n_steps; ++t) {
+        for (int side = 0; side < 2; ++side) {
+            if (g->desc.ghost_mode[2][side] != B200GEO_GHOST_PEER) continue;
+            if (g->peer_valid[side] < 1)
+                return fail(B200GEO_ERR_LOGIC, "ghost zone exhausted: exchange halos before stepping");
+        }
+        int rebin = ((first_nano_step + t) % (uint32_t)params->nano_steps) == 0;
+        int rc = g->real == 4 ? sweep<float>(g, params, rebin, s) : sweep<double>(g, params, rebin, s);
+        if (rc) return rc;
+        g->cur ^= 1;
+        for (int side = 0; side < 2; ++side)
+            if (g->desc.ghost_mode[2][side] == B200GEO_GHOST_PEER) --g->peer_valid[side];
+        ++g->sweeps;
+    }
+    return B200GEO_OK;
+}
+
+int b200geo_boxgrid_check(b200geo_boxgrid *g, void *stream)
+{
+    if (!g) return fail(B200GEO_ERR_INVALID, "null grid");
+    B200GEO_CUDA(cudaSetDevice(g->device));
+    int flag = 0;
+    B200GEO_CUDA(cudaMemcpyAsync(&flag, g->overflow, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    B200GEO_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    if (flag) {
+        cudaMemsetAsync(g->overflow, 0, sizeof(int), (cudaStream_t)stream);
+        return fail(B200GEO_ERR_OUT_OF_RANGE, "capacity exceeded");
+    }
+    return B200GEO_OK;
+}
+
+int b200geo_boxgrid_halo_block(const b200geo_boxgrid *g, int array, int side, int kind, int which, void **ptr,
+                               uint64_t *bytes)
+{
+    if (!g || !ptr || !bytes) return fail(B200GEO_ERR_INVALID, "null argument");
+    if ((array != 0 && array != 1) || (side != 0 && side != 1) || (kind != 0 && kind != 1) || (which != 0 && which != 1))
+        return fail(B200GEO_ERR_INVALID, "bad array/side/kind");
+    const int nz = g->d[2];
+    int64_t plane = (int64_t)(g->d[0] + 2) * (g->d[1] + 2);
+    int64_t zp = kind == 0 ? (side == 0 ? 1 : nz) : (side == 0 ? 0 : nz + 1);  // padded plane index
+    int buf = g->cur ^ which;
+    if (array == 0) {
+        *ptr = g->counts[buf] + zp * plane;
+        *bytes = (uint64_t)plane * sizeof(int32_t);
+    } else {
+        *ptr = g->parts[buf] + zp * plane * g->cell_bytes();
+        *bytes = (uint64_t)plane * g->cell_bytes();
+    }
+    return B200GEO_OK;
+}
+
+int b200geo_boxgrid_halo_mark_valid(b200geo_boxgrid *g, int side, int width)
+{
+    if (!g || (side != 0 && side != 1) || width < 0 || width > 1) return fail(B200GEO_ERR_INVALID, "bad side/width");
+    g->peer_valid[side] = width;
+    return B200GEO_OK;
+}
+
+}

@@ -30,6 +30,11 @@ class CellModel:
         return None
 
     @property
+    def grid_class(self):
+        from .simulator import B200Grid
+        return B200Grid
+
+    @property
     def fuses_sweeps(self):
         """the kernel family can take several sweeps per launch (b200geo_update_box_n)"""
         return self.kernel in (capi.KERNEL_JACOBI6, capi.KERNEL_JACOBI7, capi.KERNEL_JACOBI27)
@@ -75,6 +80,37 @@ class CellModel:
         return b"".join(np.asarray(c[n]).tobytes() for n, _ in self.members)
 
 
+class NBodyModel:
+    """Binding of BoxCell<FixedArray<LJParticle<REAL>, capacity> > (oracle/models/nbody.h) to the
+    n-body kernels: Cube<3>, Moore<3,1>, NANO_STEPS 1; containers of edge `cell_edge` >= cutoff."""
+
+    def __init__(self, name, real, capacity=32, cell_edge=2.5, cutoff=2.5, dt=0.005):
+        self.name, self.dim, self.topology, self.radius, self.nano_steps = name, 3, "cube", 1, 1
+        self.real = np.dtype(real)
+        self.capacity, self.cell_edge, self.cutoff, self.dt = capacity, cell_edge, cutoff, dt
+        self.kernel = capi.KERNEL_NBODY
+        self.members = [("counts", np.dtype("i4")), ("particles", self.real)]   # the two device arrays
+        self.ref_model = "nbody"
+        self.wraps = False
+        self.fuses_sweeps = False
+
+    def with_params(self, **kw):
+        args = dict(real=self.real, capacity=self.capacity, cell_edge=self.cell_edge, cutoff=self.cutoff, dt=self.dt)
+        args.update(kw)
+        return NBodyModel(self.name, **args)
+
+    def step_params(self, final):
+        return capi.NBodyParams(self.dt, self.cutoff, self.nano_steps)
+
+    def halo_members(self, width):
+        return ([0, 1], [0, 1])
+
+    @property
+    def grid_class(self):
+        from .boxgrid import BoxGrid
+        return BoxGrid
+
+
 _F64 = [("temp", "f8")]
 _LBM = [(n, "f4") for n in ["C", "N", "E", "W", "S", "T", "B", "NW", "SW", "NE", "SE", "TW", "BW", "TE", "BE",
                             "TN", "BN", "TS", "BS", "density", "velocityX", "velocityY", "velocityZ"]] + [("state", "i4")]
@@ -91,5 +127,8 @@ ConwayTorus = CellModel("ConwayTorus", 2, "torus", [("alive", "u1")], capi.KERNE
 LBMCellF = CellModel("LBMCellF", 3, "cube", _LBM, capi.KERNEL_LBM_D3Q19, edge={"C": 1.0, "density": 1.0},
                      ref_model="lbm")
 
-ALL = {m.name: m for m in [Jacobi6Cube, Jacobi6Torus, Jacobi7Cube, Jacobi7Torus, Jacobi27Cube, Jacobi27Torus,
+NBodyF = NBodyModel("NBodyF", "f4")
+NBodyD = NBodyModel("NBodyD", "f8")
+
+ALL = {m.name: m for m in [NBodyF, NBodyD, Jacobi6Cube, Jacobi6Torus, Jacobi7Cube, Jacobi7Torus, Jacobi27Cube, Jacobi27Torus,
                            ConwayCube, ConwayTorus, LBMCellF]}

@@ -264,7 +264,7 @@ class B200Simulator:
         self.initializer, self.model = initializer, model
         self.NANO_STEPS = model.nano_steps
         dims = initializer.gridDimensions()
-        self.grid = B200Grid(model, dims, device=device)
+        self.grid = model.grid_class(model, dims, device=device)
         # SerialSimulator initialises both grids (serialsimulator.h:54-57); loads write both buffers
         initializer.grid(self.grid)
         self.stepNum = initializer.startStep()
@@ -324,7 +324,8 @@ class B200Simulator:
         return max(1, n)
 
     def _advance(self, steps):
-        self.grid.dev.step(self.model.kernel, n_steps=steps * self.NANO_STEPS, first_nano_step=0)
+        self.grid.dev.step(self.model.kernel, n_steps=steps * self.NANO_STEPS, first_nano_step=0,
+                           params=self.model.step_params(True))
         self.stepNum += steps
 
     def _afterStep(self):

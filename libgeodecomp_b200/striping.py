@@ -187,8 +187,8 @@ class StripedSimulator:
         dims[last] = z1 - z0
         origin = [0] * model.dim
         origin[last] = z0
-        self.grid = B200Grid(model, dims, device=device, ghost_z=ghost_z, z_modes=z_modes, origin=origin,
-                             global_dims=gdims, engine=engine)
+        self.grid = model.grid_class(model, dims, device=device, ghost_z=ghost_z, z_modes=z_modes, origin=origin,
+                                     global_dims=gdims, engine=engine)
         self.ghost_width = ghost_z if world > 1 else 1
         self.halo = HaloExchanger(self.grid, rank, world, self.ghost_width, periodic, dist=dist)
         self.dist = dist
@@ -237,7 +237,7 @@ class StripedSimulator:
 
     def _can_overlap(self):
         w, last = self.ghost_width, self.model.dim - 1
-        if self.halo.packed or self.grid.dims[last] < 2 * w:
+        if self.halo.packed or self.grid.dims[last] < 2 * w or not hasattr(self.grid.dev, "update_box"):
             return False
         return w == 1 or (self.model.fuses_sweeps and w <= 4)
 

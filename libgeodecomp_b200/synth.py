@@ -87,3 +87,46 @@ def lbm_grid(nx, ny, nz, seed=11, noise=0.0, z0=0, nz_total=None):
     raw[19] = 1.0
     raw[23] = lbm_states(nx, ny, nz, z0, nz_total).view(np.float32)
     return raw
+
+
+def nbody_cells(ncx, ncy, ncz, cap=32, edge=2.5, spacing=1.058, jitter=0.1, vel=0.0, seed=1234, dtype=np.float32,
+                z0=0):
+    """Config 5: particles on a cubic lattice of `spacing` (density ~0.844) jittered by +-jitter,
+    binned into BoxCell containers of edge `edge`; optional uniform random velocities in
+    [-vel, vel] (tests use them to force particles across cell faces). z0 = first cell plane of a
+    slab (global particle ids and positions). Returns (counts int32 [ncz][ncy][ncx],
+    parts dtype [ncz][ncy][ncx][cap][6])."""
+    lx, ly = ncx * edge, ncy * edge
+    zlo, zhi = z0 * edge, (z0 + ncz) * edge
+    npx, npy = int(lx / spacing), int(ly / spacing)
+    k0, k1 = int(np.ceil(zlo / spacing - 0.5)), int(np.ceil(zhi / spacing - 0.5))
+    ix, iy, iz = np.meshgrid(np.arange(npx), np.arange(npy), np.arange(k0, k1), indexing="ij")
+    ids = ((iz.astype(np.uint64) * np.uint64(1 << 20) + iy.astype(np.uint64)) * np.uint64(1 << 20) + ix.astype(np.uint64)).reshape(-1)
+    n = ids.size
+
+    def rnd(salt):
+        bits = splitmix64(ids ^ np.uint64(seed + salt))
+        return (bits >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0)
+
+    pos = np.stack([(ix.reshape(-1) + 0.5) * spacing + jitter * (2 * rnd(1) - 1),
+                    (iy.reshape(-1) + 0.5) * spacing + jitter * (2 * rnd(2) - 1),
+                    (iz.reshape(-1) + 0.5) * spacing + jitter * (2 * rnd(3) - 1)], axis=1).astype(dtype)
+    v = np.stack([vel * (2 * rnd(4) - 1), vel * (2 * rnd(5) - 1), vel * (2 * rnd(6) - 1)], axis=1).astype(dtype)
+    # bin with the reference's position checker (origin <= pos < origin + edge, in double)
+    pd = pos.astype(np.float64)
+    c = np.floor(pd / edge).astype(np.int64)
+    c[:, 2] -= z0
+    inside = ((c >= 0) & (c < np.array([ncx, ncy, ncz]))).all(axis=1)
+    pos, v, c = pos[inside], v[inside], c[inside]
+    cell = (c[:, 2] * ncy + c[:, 1]) * ncx + c[:, 0]
+    order = np.argsort(cell, kind="stable")
+    cell, pos, v = cell[order], pos[order], v[order]
+    counts = np.bincount(cell, minlength=ncx * ncy * ncz).astype(np.int32)
+    if counts.max() > cap:
+        raise ValueError("cell capacity %d exceeded (%d)" % (cap, counts.max()))
+    start = np.concatenate([[0], np.cumsum(counts)[:-1]])
+    slot = np.arange(cell.size) - start[cell]
+    parts = np.zeros((ncx * ncy * ncz, cap, 6), dtype=dtype)
+    parts[cell, slot, 0:3] = pos
+    parts[cell, slot, 3:6] = v
+    return counts.reshape(ncz, ncy, ncx), parts.reshape(ncz, ncy, ncx, cap, 6)

@@ -369,3 +369,106 @@ int oracle_load_region(int nx, int ny, int nz, int n_members, const int *member_
 {
     return region_copy(nx, ny, nz, n_members, member_bytes, (char *)grid_raw, streaks, n_streaks, (char *)buf, 0);
 }
+
+/* ------------------------------------------------------------------------------------------
+ * Short-range n-body in BoxCell containers (oracle/models/nbody.h):
+ *   BoxCell::update / copyOver / addContainedParticles / updateCargo   storage/boxcell.h:112-174
+ *   SelectPositionChecker (origin <= pos < origin + dimension, doubles) misc/apitraits.h:1074-1088
+ *   NeighborhoodIterator: the 27 cells in CoordBox order (x fastest), each cell's particles in
+ *   storage order; cells outside the Cube are the empty edge container
+ *                                                                       storage/neighborhooditerator.h:71-186
+ *   FixedArray::operator<< throws std::out_of_range("capacity exceeded")  storage/fixedarray.h:77-83
+ * NANO_STEPS = 1, so every step re-bins (nanoStep == 0) and then updates each particle of the NEW
+ * container against the OLD grid.
+ */
+#define DEFINE_NBODY(NAME, REAL)                                                                   \
+static int NAME(int nx, int ny, int nz, int cap, int steps, double dt_, double cutoff, double edge,\
+                const int32_t *cin, const REAL *pin, int32_t *cout, REAL *pout)                    \
+{                                                                                                  \
+    size_t cells = (size_t)nx * ny * nz;                                                           \
+    int32_t *c0 = malloc(cells * sizeof(int32_t)), *c1 = malloc(cells * sizeof(int32_t));          \
+    REAL *p0 = malloc(cells * cap * 6 * sizeof(REAL)), *p1 = malloc(cells * cap * 6 * sizeof(REAL)); \
+    if (!c0 || !c1 || !p0 || !p1) { free(c0); free(c1); free(p0); free(p1); return -5; }           \
+    memcpy(c0, cin, cells * sizeof(int32_t));                                                      \
+    memcpy(p0, pin, cells * cap * 6 * sizeof(REAL));                                               \
+    const REAL dt = (REAL)dt_, rc = (REAL)cutoff, rc2 = rc * rc;                                   \
+    int overflow = 0;                                                                              \
+    for (int s = 0; s < steps; ++s) {                                                              \
+        _Pragma("omp parallel for collapse(2) reduction(|:overflow)")                              \
+        for (int z = 0; z < nz; ++z) {                                                             \
+            for (int y = 0; y < ny; ++y) {                                                         \
+                for (int x = 0; x < nx; ++x) {                                                     \
+                    size_t self = ((size_t)z * ny + y) * nx + x;                                   \
+                    double o[3] = {x * edge, y * edge, z * edge};                                  \
+                    double q[3] = {o[0] + edge, o[1] + edge, o[2] + edge};                         \
+                    REAL *mine = p1 + self * cap * 6;                                              \
+                    int n = 0;                                                                     \
+                    /* copyOver at nanoStep 0: clear, then addContainedParticles over the hood */  \
+                    for (int k = 0; k < 27; ++k) {                                                 \
+                        int ax = x + k % 3 - 1, ay = y + (k / 3) % 3 - 1, az = z + k / 9 - 1;      \
+                        if (ax < 0 || ax >= nx || ay < 0 || ay >= ny || az < 0 || az >= nz) continue; \
+                        size_t nb = ((size_t)az * ny + ay) * nx + ax;                              \
+                        for (int p = 0; p < c0[nb]; ++p) {                                         \
+                            const REAL *src = p0 + (nb * cap + p) * 6;                             \
+                            double px = src[0], py = src[1], pz = src[2];                          \
+                            if (o[0] <= px && o[1] <= py && o[2] <= pz && px < q[0] && py < q[1] && pz < q[2]) { \
+                                if (n >= cap) { overflow = 1; continue; }                          \
+                                memcpy(mine + n * 6, src, 6 * sizeof(REAL));                       \
+                                ++n;                                                               \
+                            }                                                                      \
+                        }                                                                          \
+                    }                                                                              \
+                    c1[self] = n;                                                                  \
+                    /* updateCargo: Particle::update against the OLD neighbourhood */              \
+                    for (int i = 0; i < n; ++i) {                                                  \
+                        REAL *t = mine + i * 6;                                                    \
+                        for (int k = 0; k < 27; ++k) {                                             \
+                            int ax = x + k % 3 - 1, ay = y + (k / 3) % 3 - 1, az = z + k / 9 - 1;  \
+                            if (ax < 0 || ax >= nx || ay < 0 || ay >= ny || az < 0 || az >= nz) continue; \
+                            size_t nb = ((size_t)az * ny + ay) * nx + ax;                          \
+                            for (int p = 0; p < c0[nb]; ++p) {                                     \
+                                const REAL *src = p0 + (nb * cap + p) * 6;                         \
+                                REAL d0 = t[0] - src[0], d1 = t[1] - src[1], d2 = t[2] - src[2];   \
+                                REAL r2 = (d0 * d0 + d1 * d1) + d2 * d2;                           \
+                                if (r2 == 0 || r2 >= rc2) continue;                                \
+                                REAL inv = (REAL)1 / r2;                                           \
+                                REAL s6 = inv * inv * inv;                                         \
+                                REAL f = ((REAL)24 * inv) * s6 * ((REAL)2 * s6 - (REAL)1);         \
+                                t[3] += (d0 * f) * dt;                                             \
+                                t[4] += (d1 * f) * dt;                                             \
+                                t[5] += (d2 * f) * dt;                                             \
+                            }                                                                      \
+                        }                                                                          \
+                        t[0] += t[3] * dt;                                                         \
+                        t[1] += t[4] * dt;                                                         \
+                        t[2] += t[5] * dt;                                                         \
+                    }                                                                              \
+                }                                                                                  \
+            }                                                                                      \
+        }                                                                                          \
+        if (overflow) break;                                                                       \
+        int32_t *tc = c0; c0 = c1; c1 = tc;                                                        \
+        REAL *tp = p0; p0 = p1; p1 = tp;                                                           \
+    }                                                                                              \
+    if (!overflow) {                                                                               \
+        memcpy(cout, c0, cells * sizeof(int32_t));                                                 \
+        memset(pout, 0, cells * cap * 6 * sizeof(REAL));                                           \
+        for (size_t c = 0; c < cells; ++c)                                                         \
+            memcpy(pout + c * cap * 6, p0 + c * cap * 6, (size_t)c0[c] * 6 * sizeof(REAL));        \
+    }                                                                                              \
+    free(c0); free(c1); free(p0); free(p1);                                                        \
+    return overflow ? -3 : 0;                                                                      \
+}
+
+DEFINE_NBODY(nbody_f32, float)
+DEFINE_NBODY(nbody_f64, double)
+
+int oracle_nbody(int real_bytes, int nx, int ny, int nz, int cap, int steps, double dt, double cutoff, double edge,
+                 const int32_t *counts_in, const void *parts_in, int32_t *counts_out, void *parts_out)
+{
+    if (real_bytes == 4)
+        return nbody_f32(nx, ny, nz, cap, steps, dt, cutoff, edge, counts_in, (const float *)parts_in, counts_out, (float *)parts_out);
+    if (real_bytes == 8)
+        return nbody_f64(nx, ny, nz, cap, steps, dt, cutoff, edge, counts_in, (const double *)parts_in, counts_out, (double *)parts_out);
+    return -1;
+}

@@ -43,6 +43,14 @@ int oracle_save_region(int nx, int ny, int nz, int n_members, const int *member_
 int oracle_load_region(int nx, int ny, int nz, int n_members, const int *member_bytes,
                        void *grid_raw, const int *streaks, int n_streaks, const void *buf);
 
+/* Short-range n-body in BoxCell<FixedArray<LJParticle<REAL>, cap>> containers on a Cube<3> grid of
+ * nx*ny*nz cells of edge `edge` (oracle/models/nbody.h; storage/boxcell.h:112-174). counts:
+ * int32 [nz][ny][nx]; parts: REAL [nz][ny][nx][cap][6] (pos xyz, vel xyz; unused slots zero on
+ * output). real_bytes 4 or 8. Returns -3 when a container overflows (std::out_of_range in the
+ * reference, storage/fixedarray.h:77-83). */
+int oracle_nbody(int real_bytes, int nx, int ny, int nz, int cap, int steps, double dt, double cutoff, double edge,
+                 const int32_t *counts_in, const void *parts_in, int32_t *counts_out, void *parts_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -59,6 +59,62 @@ def lbm(raw, steps):
     return out
 
 
+def nbody(counts, parts, steps, dt=0.005, cutoff=2.5, edge=2.5):
+    """counts int32 [nz][ny][nx], parts REAL [nz][ny][nx][cap][6] -> (counts, parts) after `steps`.
+    Raises IndexError when a container overflows (std::out_of_range in the reference)."""
+    c = np.ascontiguousarray(counts, dtype=np.int32)
+    p = np.ascontiguousarray(parts)
+    assert p.dtype in (np.float32, np.float64) and p.shape[:3] == c.shape and p.shape[4] == 6
+    nz, ny, nx = c.shape
+    co, po = np.empty_like(c), np.empty_like(p)
+    f = lib().oracle_nbody
+    f.argtypes = [ctypes.c_int] * 6 + [ctypes.c_double] * 3 + [ctypes.c_void_p] * 4
+    rc = f(p.dtype.itemsize, nx, ny, nz, p.shape[3], steps, dt, cutoff, edge, _p(c), _p(p), _p(co), _p(po))
+    if rc == -3:
+        raise IndexError("capacity exceeded")
+    assert rc == 0, rc
+    return co, po
+
+
+def run_ref_nbody(counts, parts, steps, dt=0.005, cutoff=2.5, edge=2.5, omp=False, threads=None, want_output=True):
+    """The reference's own SerialSimulator/OpenMPSimulator over BoxCell containers (oracle/_ref/lgd_ref_nbody,
+    capacity 32). Returns ((counts, parts) or None, stats)."""
+    c = np.ascontiguousarray(counts, dtype=np.int32)
+    p = np.ascontiguousarray(parts)
+    assert p.shape[3] == 32, "the reference binary is built for FixedArray capacity 32"
+    nz, ny, nx = c.shape
+    env = dict(os.environ)
+    if omp:
+        env["OMP_PROC_BIND"] = "true"
+        env["OMP_PLACES"] = "cores"
+        if threads:
+            env["OMP_NUM_THREADS"] = str(threads)
+    with tempfile.TemporaryDirectory() as tmp:
+        fin, fout = os.path.join(tmp, "in.raw"), os.path.join(tmp, "out.raw")
+        with open(fin, "wb") as f:
+            f.write(c.tobytes())
+            f.write(p.tobytes())
+        cmd = [ref_binary("nbody"), "nbody", str(nx), str(ny), str(nz), str(steps), fin, fout if want_output else "-",
+               "--dt", repr(float(dt)), "--cutoff", repr(float(cutoff)), "--edge", repr(float(edge))]
+        if p.dtype == np.float64:
+            cmd.append("--double")
+        if omp:
+            cmd.append("--omp")
+        res = subprocess.run(cmd, env=env, capture_output=True, text=True)
+        if res.returncode == 4 and "capacity exceeded" in res.stderr:
+            raise IndexError("capacity exceeded")
+        if res.returncode != 0:
+            raise RuntimeError(res.stderr[-2000:])
+        stats = json.loads(res.stdout.strip().splitlines()[-1])
+        out = None
+        if want_output:
+            raw = np.fromfile(fout, dtype=np.uint8)
+            co = raw[:c.nbytes].view(np.int32).reshape(c.shape)
+            po = raw[c.nbytes:].view(p.dtype).reshape(p.shape)
+            out = (co, po)
+    return out, stats
+
+
 def _region(fn, grid_raw, dims, member_bytes, streaks, buf):
     nx, ny, nz = dims
     mb = np.asarray(member_bytes, dtype=np.int32)

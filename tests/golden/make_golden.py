@@ -49,6 +49,15 @@ def main():
         cases[key + "_in"] = raw
         cases[key + "_out"] = out.view(np.float32).reshape(raw.shape)
     np.savez_compressed(os.path.join(HERE, "lbm.npz"), **cases)
+    cases = {}
+    for real, (ncx, ncy, ncz, steps, vel, dt) in [(np.float32, (6, 5, 4, 10, 8.0, 0.01)), (np.float64, (6, 5, 4, 10, 8.0, 0.01)),
+                                                  (np.float32, (9, 3, 2, 6, 20.0, 0.02)), (np.float64, (3, 3, 3, 25, 2.0, 0.005))]:
+        c, p = synth.nbody_cells(ncx, ncy, ncz, vel=vel, dtype=real)
+        (co, po), _ = oracle_py.run_ref_nbody(c, p, steps, dt=dt)
+        key = "nbody_%s_%dx%dx%d_s%d_dt%g" % (np.dtype(real).name, ncx, ncy, ncz, steps, dt)
+        cases[key + "_in_counts"], cases[key + "_in_parts"] = c, p
+        cases[key + "_out_counts"], cases[key + "_out_parts"] = co, po
+    np.savez_compressed(os.path.join(HERE, "nbody.npz"), **cases)
     print("golden fixtures written to", HERE)
 
 

@@ -143,3 +143,58 @@ def test_known_answer_vs_reference_binary(oracle):
     f = coordinate_field((0, 0, 0), (20, 10, 6))
     out, _ = oracle.run_ref("jacobi6torus", f, (20, 10, 6), 1)
     assert np.array_equal(out.view(np.float64).reshape(f.shape), expected_neighbour_sum((0, 0, 0), (20, 10, 6), True) * (1.0 / 6.0))
+
+
+# ---------------------------------------------------------------- n-body in BoxCell containers
+
+def nbody_cases():
+    z = np.load(os.path.join(GOLDEN, "nbody.npz"))
+    return sorted(k[:-len("_in_counts")] for k in z.files if k.endswith("_in_counts")), z
+
+
+@pytest.mark.parametrize("key", nbody_cases()[0])
+def test_nbody_golden(oracle, key):
+    """C restatement == the reference's SerialSimulator over BoxCell<FixedArray<LJParticle, 32>>
+    (fixture generated by tests/golden/make_golden.py): container occupancy and every bit of
+    every position / velocity, with particles crossing container faces and leaving the Cube."""
+    z = nbody_cases()[1]
+    m = re.match(r"nbody_(float32|float64)_.*_s(\d+)_dt([0-9.]+)", key)
+    co, po = oracle.nbody(z[key + "_in_counts"], z[key + "_in_parts"], int(m.group(2)), dt=float(m.group(3)))
+    assert np.array_equal(co, z[key + "_out_counts"])
+    assert np.array_equal(po.view(np.uint8), z[key + "_out_parts"].view(np.uint8))
+    assert not np.array_equal(co, z[key + "_in_counts"])   # the case does re-bin
+
+
+@pytest.mark.parametrize("real", [np.float32, np.float64])
+def test_nbody_live_reference(oracle, real):
+    if not oracle.have_ref("nbody"):
+        pytest.skip("oracle/_ref not built (no /root/reference on this machine)")
+    c, p = synth.nbody_cells(5, 4, 6, vel=12.0, seed=99, dtype=real)
+    (cr, pr), _ = oracle.run_ref_nbody(c, p, 8, dt=0.01)
+    co, po = oracle.nbody(c, p, 8, dt=0.01)
+    assert np.array_equal(co, cr) and np.array_equal(po.view(np.uint8), pr.view(np.uint8))
+
+
+def test_nbody_capacity_exceeded_is_out_of_range(oracle):
+    """FixedArray::operator<< throws std::out_of_range("capacity exceeded") (storage/fixedarray.h:77-83)"""
+    c = np.zeros((1, 1, 2), dtype=np.int32)
+    p = np.zeros((1, 1, 2, 32, 6), dtype=np.float32)
+    c[0, 0, 0] = c[0, 0, 1] = 20
+    p[0, 0, 0, :20, 0] = 2.4          # all in container 0 ...
+    p[0, 0, 1, :20, 0] = 2.6
+    p[0, 0, 1, :20, 3] = -100.0       # ... and container 1's particles fly into container 0
+    p[0, 0, :, :20, 1] = np.linspace(0.1, 2.4, 20)
+    p[0, 0, :, :20, 2] = 1.0
+    with pytest.raises(IndexError):
+        oracle.nbody(c, p, 2, dt=0.01, cutoff=0.01)
+    if oracle.have_ref("nbody"):
+        with pytest.raises(IndexError):
+            oracle.run_ref_nbody(c, p, 2, dt=0.01, cutoff=0.01)
+
+
+def test_nbody_neighbour_counts_like_boxcelltest(oracle):
+    """storage/test/unit/boxcelltest.h counts neighbours within a distance; here: with a huge dt-free
+    probe (dt = 0) nothing moves, so occupancy is a fixed point and positions stay bit-identical."""
+    c, p = synth.nbody_cells(4, 4, 4, vel=0.0, dtype=np.float64)
+    co, po = oracle.nbody(c, p, 3, dt=0.0)
+    assert np.array_equal(co, c) and np.array_equal(po[..., :3], p[..., :3])
