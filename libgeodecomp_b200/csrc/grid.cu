@@ -10,7 +10,7 @@
 
 namespace b200geo {
 
-static const Tuning g_tuning_default = {0, -1, 0, 128, 2, 33, 0};
+static const Tuning g_tuning_default = {0, -1, 0, 128, 2, 33, 0, 3};
 Tuning g_tuning = g_tuning_default;
 static thread_local std::string g_last_error;
 static std::atomic<uint64_t> g_launches(0);
@@ -81,6 +81,7 @@ int b200geo_set_tuning(const char *key, int value)
     else if (k == "jacobi.tb") g_tuning.jacobi_tb = value < 0 ? g_tuning_default.jacobi_tb : value;
     else if (k == "jacobi.tb_rows") g_tuning.jacobi_tb_rows = value < 0 ? g_tuning_default.jacobi_tb_rows : value;
     else if (k == "jacobi.tb_zchunk") g_tuning.jacobi_tb_zchunk = value < 0 ? g_tuning_default.jacobi_tb_zchunk : value;
+    else if (k == "nbody.kernel") g_tuning.nbody_kernel = value < 0 ? g_tuning_default.nbody_kernel : value;
     else return fail(B200GEO_ERR_INVALID, "unknown tuning key " + k);
     return B200GEO_OK;
 }

@@ -194,6 +194,319 @@ force_kernel(const int32_t *__restrict__ cnt_old, const REAL *__restrict__ part_
     }
 }
 
+// Same update, two passes per particle so that the expensive part runs with full lanes:
+//   pass 1 walks the 27 containers in reference order and records, in a per-thread list in shared
+//          memory, the candidates inside a slightly ENLARGED cutoff (cheap FMA distance, 1 + 2^-16 margin:
+//          conservative, it only decides what pass 2 looks at);
+//   pass 2 walks that list in the same order and does the reference arithmetic, including the exact
+//          `r2 == 0 || r2 >= rc2` test, so the result is bit-identical to the one-pass kernel.
+// Only ~15 % of the candidates (4/3 pi rc^3 of the 27 rc^3 searched) interact; in the one-pass
+// kernel nearly every warp iteration has some lane inside the cutoff, so all lanes pay for the
+// force evaluation of every candidate.
+template<typename REAL> struct alignas(2 * sizeof(REAL)) Pos2 { REAL x, y; };
+
+__device__ __forceinline__ float fma_any(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+__device__ __forceinline__ double fma_any(double a, double b, double c) { return __fma_rn(a, b, c); }
+
+// four consecutive slots (16-byte aligned: capacity and slot index are multiples of four)
+__device__ __forceinline__ void load4(const float *p, float (&v)[4])
+{
+    float4 t = *reinterpret_cast<const float4 *>(p);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+
+__device__ __forceinline__ void load4(const double *p, double (&v)[4])
+{
+    double2 a = *reinterpret_cast<const double2 *>(p), b = *reinterpret_cast<const double2 *>(p + 2);
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
+
+template<typename REAL, int G, int NT, int LMAX>
+__global__ void __launch_bounds__(NT)
+force_list_kernel(const int32_t *__restrict__ cnt_old, const REAL *__restrict__ part_old, const int32_t *__restrict__ cnt_new,
+                  REAL *__restrict__ part_new, BoxDims D, int z0, int runs_per_row, REAL dt, REAL rc2, REAL rc2_loose)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int cap = D.cap;
+    constexpr int NC = (G + 2) * 9;
+    Pos2<REAL> *sxy = reinterpret_cast<Pos2<REAL> *>(smem_raw);       // [NC][cap]
+    REAL *sz = reinterpret_cast<REAL *>(sxy + NC * cap);             // [NC][cap]
+    int *scnt = reinterpret_cast<int *>(sz + NC * cap);              // [NC]
+    int *pre = scnt + NC;                                            // [G + 1]
+    unsigned short *list = reinterpret_cast<unsigned short *>(pre + G + 1 + ((G + 1) & 1));  // [LMAX + 1][NT]
+
+    const int run = blockIdx.x % runs_per_row;
+    const int y = (blockIdx.x / runs_per_row) % D.ny;
+    const int z = z0 + blockIdx.x / (runs_per_row * D.ny);
+    const int x0 = run * G;
+
+    for (int c = threadIdx.x; c < NC; c += NT) {
+        int lx = c % (G + 2), ly = (c / (G + 2)) % 3, lz = c / ((G + 2) * 3);
+        int cx = x0 - 1 + lx;
+        scnt[c] = cx <= D.nx ? cnt_old[pcell(D, cx, y - 1 + ly, z - 1 + lz)] : 0;
+    }
+    if (threadIdx.x <= G) {
+        int acc = 0;
+        for (int j = 0; j < (int)threadIdx.x; ++j) acc += (x0 + j < D.nx) ? cnt_new[pcell(D, x0 + j, y, z)] : 0;
+        pre[threadIdx.x] = acc;
+    }
+    __syncthreads();
+    // four slots per work item: three 128-bit loads, interleaved (x, y) pairs and z to shared memory
+    const int quads = cap / 4;
+    for (int i = threadIdx.x; i < NC * quads; i += NT) {
+        int c = i / quads, sl = (i % quads) * 4;
+        if (sl < scnt[c]) {
+            int lx = c % (G + 2), ly = (c / (G + 2)) % 3, lz = c / ((G + 2) * 3);
+            const REAL *src = part_old + pcell(D, x0 - 1 + lx, y - 1 + ly, z - 1 + lz) * 6 * cap + sl;
+            REAL xs[4], ys[4], zs[4];
+            load4(src, xs);
+            load4(src + cap, ys);
+            load4(src + 2 * cap, zs);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                Pos2<REAL> xy;
+                xy.x = xs[q];
+                xy.y = ys[q];
+                sxy[c * cap + sl + q] = xy;
+                sz[c * cap + sl + q] = zs[q];
+            }
+        }
+    }
+    __syncthreads();
+
+    const int total = pre[G];
+    unsigned short *mylist = list + threadIdx.x;
+    for (int t = threadIdx.x; t < total; t += NT) {
+        int j = 0;
+        while (pre[j + 1] <= t) ++j;
+        const int slot = t - pre[j];
+        REAL *me = part_new + pcell(D, x0 + j, y, z) * 6 * cap + slot;
+        const REAL p0 = me[0], p1 = me[cap], p2 = me[2 * cap];
+        REAL v0 = me[3 * cap], v1 = me[4 * cap], v2 = me[5 * cap];
+        // pass 1: branch-free candidate filter. Every candidate is stored at the list's current end
+        // and the end only advances for the ones inside the enlarged cutoff.
+        int n = 0;
+        for (int k = 0; k < 27; ++k) {
+            const int cell = ((k / 9) * 3 + (k / 3) % 3) * (G + 2) + j + k % 3;
+            const int base = cell * cap, cn = scnt[cell];
+#pragma unroll 4
+            for (int p = 0; p < cn; ++p) {
+                const Pos2<REAL> xy = sxy[base + p];
+                const REAL d0 = p0 - xy.x, d1 = p1 - xy.y, d2 = p2 - sz[base + p];
+                const REAL r2 = fma_any(d2, d2, fma_any(d1, d1, d0 * d0));
+                mylist[n * NT] = (unsigned short)(base + p);
+                n = min(n + (r2 < rc2_loose ? 1 : 0), LMAX);
+            }
+        }
+        if (n < LMAX) {
+            // pass 2: the reference arithmetic on the short list, in the same order
+            for (int i = 0; i < n; ++i) {
+                const int idx = mylist[i * NT];
+                const Pos2<REAL> xy = sxy[idx];
+                const REAL d0 = p0 - xy.x, d1 = p1 - xy.y, d2 = p2 - sz[idx];
+                const REAL r2 = (d0 * d0 + d1 * d1) + d2 * d2;
+                if (r2 == (REAL)0 || r2 >= rc2) continue;
+                const REAL inv = (REAL)1 / r2;
+                const REAL s6 = inv * inv * inv;
+                const REAL f = ((REAL)24 * inv) * s6 * ((REAL)2 * s6 - (REAL)1);
+                v0 += (d0 * f) * dt;
+                v1 += (d1 * f) * dt;
+                v2 += (d2 * f) * dt;
+            }
+        } else {
+            // list full (a very dense neighbourhood): one pass over everything, like force_kernel
+            for (int k = 0; k < 27; ++k) {
+                const int cell = ((k / 9) * 3 + (k / 3) % 3) * (G + 2) + j + k % 3;
+                const int base = cell * cap, cn = scnt[cell];
+                for (int p = 0; p < cn; ++p) {
+                    const Pos2<REAL> xy = sxy[base + p];
+                    const REAL d0 = p0 - xy.x, d1 = p1 - xy.y, d2 = p2 - sz[base + p];
+                    const REAL r2 = (d0 * d0 + d1 * d1) + d2 * d2;
+                    if (r2 == (REAL)0 || r2 >= rc2) continue;
+                    const REAL inv = (REAL)1 / r2;
+                    const REAL s6 = inv * inv * inv;
+                    const REAL f = ((REAL)24 * inv) * s6 * ((REAL)2 * s6 - (REAL)1);
+                    v0 += (d0 * f) * dt;
+                    v1 += (d1 * f) * dt;
+                    v2 += (d2 * f) * dt;
+                }
+            }
+        }
+        me[0] = p0 + v0 * dt;
+        me[cap] = p1 + v1 * dt;
+        me[2 * cap] = p2 + v2 * dt;
+        me[3 * cap] = v0;
+        me[4 * cap] = v1;
+        me[5 * cap] = v2;
+    }
+}
+
+// Re-bin and update in ONE kernel: the staged neighbourhood serves both, the new containers are
+// written once (no separate pass over the grid for addContainedParticles).
+template<typename REAL, int G, int NT, int LMAX>
+__global__ void __launch_bounds__(NT)
+fused_kernel(const int32_t *__restrict__ cnt_old, const REAL *__restrict__ part_old, int32_t *__restrict__ cnt_new,
+             REAL *__restrict__ part_new, BoxDims D, int z0, int runs_per_row, REAL dt, REAL rc2, REAL rc2_loose,
+             int rebin, int *overflow)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int cap = D.cap;
+    constexpr int NC = (G + 2) * 9;
+    Pos2<REAL> *sxy = reinterpret_cast<Pos2<REAL> *>(smem_raw);       // [NC][cap]
+    REAL *sz = reinterpret_cast<REAL *>(sxy + NC * cap);             // [NC][cap]
+    int *scnt = reinterpret_cast<int *>(sz + NC * cap);              // [NC]
+    int *pre = scnt + NC;                                            // [G + 1]
+    unsigned short *newidx = reinterpret_cast<unsigned short *>(pre + G + 1 + ((G + 1) & 1));  // [G][cap]: staged index of every new particle
+    unsigned short *list = newidx + G * cap + ((G * cap) & 1);                                  // [LMAX + 1][NT]
+
+    const int run = blockIdx.x % runs_per_row;
+    const int y = (blockIdx.x / runs_per_row) % D.ny;
+    const int z = z0 + blockIdx.x / (runs_per_row * D.ny);
+    const int x0 = run * G;
+
+    for (int c = threadIdx.x; c < NC; c += NT) {
+        int lx = c % (G + 2), ly = (c / (G + 2)) % 3, lz = c / ((G + 2) * 3);
+        int cx = x0 - 1 + lx;
+        scnt[c] = cx <= D.nx ? cnt_old[pcell(D, cx, y - 1 + ly, z - 1 + lz)] : 0;
+    }
+    __syncthreads();
+    // four slots per work item: three 128-bit loads, interleaved (x, y) pairs and z to shared memory
+    const int quads = cap / 4;
+    for (int i = threadIdx.x; i < NC * quads; i += NT) {
+        int c = i / quads, sl = (i % quads) * 4;
+        if (sl < scnt[c]) {
+            int lx = c % (G + 2), ly = (c / (G + 2)) % 3, lz = c / ((G + 2) * 3);
+            const REAL *src = part_old + pcell(D, x0 - 1 + lx, y - 1 + ly, z - 1 + lz) * 6 * cap + sl;
+            REAL xs[4], ys[4], zs[4];
+            load4(src, xs);
+            load4(src + cap, ys);
+            load4(src + 2 * cap, zs);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                Pos2<REAL> xy;
+                xy.x = xs[q];
+                xy.y = ys[q];
+                sxy[c * cap + sl + q] = xy;
+                sz[c * cap + sl + q] = zs[q];
+            }
+        }
+    }
+    __syncthreads();
+
+    // re-bin (boxcell.h:123-138,164-174): one warp per container of the run scans the 27 staged OLD
+    // containers in order and keeps, by ordered ballot/popc compaction, the particles inside its box
+    {
+        const int lane = threadIdx.x & 31;
+        for (int j = threadIdx.x >> 5; j < G; j += NT / 32) {
+            int n = 0;
+            if (x0 + j < D.nx) {
+                const double ox = (double)(x0 + j + D.org[0]) * D.edge, oy = (double)(y + D.org[1]) * D.edge,
+                             oz = (double)(z + D.org[2]) * D.edge;
+                const double qx = ox + D.edge, qy = oy + D.edge, qz = oz + D.edge;
+                for (int k = rebin ? 0 : 13; k < (rebin ? 27 : 14); ++k) {
+                    const int cell = ((k / 9) * 3 + (k / 3) % 3) * (G + 2) + j + k % 3;
+                    const int cn = scnt[cell];
+                    for (int b = 0; b < cn; b += 32) {
+                        const int sl = b + lane;
+                        bool inside = false;
+                        if (sl < cn) {
+                            const Pos2<REAL> xy = sxy[cell * cap + sl];
+                            const double px = xy.x, py = xy.y, pz = sz[cell * cap + sl];
+                            inside = !rebin || (ox <= px && oy <= py && oz <= pz && px < qx && py < qy && pz < qz);
+                        }
+                        const unsigned mask = __ballot_sync(0xffffffffu, inside);
+                        if (inside) {
+                            const int dst = n + __popc(mask & ((1u << lane) - 1));
+                            if (dst < cap) newidx[j * cap + dst] = (unsigned short)(cell * cap + sl);
+                        }
+                        n += __popc(mask);
+                    }
+                }
+                if (lane == 0) {
+                    cnt_new[pcell(D, x0 + j, y, z)] = n < cap ? n : cap;
+                    if (n > cap) atomicOr(overflow, 1);  // FixedArray::operator<<: "capacity exceeded"
+                }
+            }
+            if (lane == 0) pre[j + 1] = n < cap ? n : cap;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        pre[0] = 0;
+        for (int j = 0; j < G; ++j) pre[j + 1] += pre[j];
+    }
+    __syncthreads();
+
+    const int total = pre[G];
+    unsigned short *mylist = list + threadIdx.x;
+    for (int t = threadIdx.x; t < total; t += NT) {
+        int j = 0;
+        while (pre[j + 1] <= t) ++j;
+        const int slot = t - pre[j];
+        REAL *me = part_new + pcell(D, x0 + j, y, z) * 6 * cap + slot;
+        // the particle's old state: position from the staged copy, velocity from its old container
+        const int from = newidx[j * cap + slot], fc = from / cap, fs = from % cap;
+        const REAL *old = part_old + pcell(D, x0 - 1 + fc % (G + 2), y - 1 + (fc / (G + 2)) % 3, z - 1 + fc / ((G + 2) * 3)) * 6 * cap + fs;
+        const REAL p0 = sxy[from].x, p1 = sxy[from].y, p2 = sz[from];
+        REAL v0 = old[3 * cap], v1 = old[4 * cap], v2 = old[5 * cap];
+        // pass 1: branch-free candidate filter. Every candidate is stored at the list's current end
+        // and the end only advances for the ones inside the enlarged cutoff.
+        int n = 0;
+        for (int k = 0; k < 27; ++k) {
+            const int cell = ((k / 9) * 3 + (k / 3) % 3) * (G + 2) + j + k % 3;
+            const int base = cell * cap, cn = scnt[cell];
+#pragma unroll 4
+            for (int p = 0; p < cn; ++p) {
+                const Pos2<REAL> xy = sxy[base + p];
+                const REAL d0 = p0 - xy.x, d1 = p1 - xy.y, d2 = p2 - sz[base + p];
+                const REAL r2 = fma_any(d2, d2, fma_any(d1, d1, d0 * d0));
+                mylist[n * NT] = (unsigned short)(base + p);
+                n = min(n + (r2 < rc2_loose ? 1 : 0), LMAX);
+            }
+        }
+        if (n < LMAX) {
+            // pass 2: the reference arithmetic on the short list, in the same order
+            for (int i = 0; i < n; ++i) {
+                const int idx = mylist[i * NT];
+                const Pos2<REAL> xy = sxy[idx];
+                const REAL d0 = p0 - xy.x, d1 = p1 - xy.y, d2 = p2 - sz[idx];
+                const REAL r2 = (d0 * d0 + d1 * d1) + d2 * d2;
+                if (r2 == (REAL)0 || r2 >= rc2) continue;
+                const REAL inv = (REAL)1 / r2;
+                const REAL s6 = inv * inv * inv;
+                const REAL f = ((REAL)24 * inv) * s6 * ((REAL)2 * s6 - (REAL)1);
+                v0 += (d0 * f) * dt;
+                v1 += (d1 * f) * dt;
+                v2 += (d2 * f) * dt;
+            }
+        } else {
+            // list full (a very dense neighbourhood): one pass over everything, like force_kernel
+            for (int k = 0; k < 27; ++k) {
+                const int cell = ((k / 9) * 3 + (k / 3) % 3) * (G + 2) + j + k % 3;
+                const int base = cell * cap, cn = scnt[cell];
+                for (int p = 0; p < cn; ++p) {
+                    const Pos2<REAL> xy = sxy[base + p];
+                    const REAL d0 = p0 - xy.x, d1 = p1 - xy.y, d2 = p2 - sz[base + p];
+                    const REAL r2 = (d0 * d0 + d1 * d1) + d2 * d2;
+                    if (r2 == (REAL)0 || r2 >= rc2) continue;
+                    const REAL inv = (REAL)1 / r2;
+                    const REAL s6 = inv * inv * inv;
+                    const REAL f = ((REAL)24 * inv) * s6 * ((REAL)2 * s6 - (REAL)1);
+                    v0 += (d0 * f) * dt;
+                    v1 += (d1 * f) * dt;
+                    v2 += (d2 * f) * dt;
+                }
+            }
+        }
+        me[0] = p0 + v0 * dt;
+        me[cap] = p1 + v1 * dt;
+        me[2 * cap] = p2 + v2 * dt;
+        me[3 * cap] = v0;
+        me[4 * cap] = v1;
+        me[5 * cap] = v2;
+    }
+}
+
 // dense AoS [cells][cap][6] (host interchange format) <-> SoA containers of a box
 template<typename REAL, bool LOAD>
 __global__ void transpose_kernel(int32_t *cnt, REAL *part, BoxDims D, int ox, int oy, int oz, int dx, int dy, int dz,
@@ -239,17 +552,49 @@ int sweep(b200geo_boxgrid *g, const b200geo_nbody_params *p, int rebin, cudaStre
     const REAL *po = (const REAL *)g->parts[g->cur];
     REAL *pn = (REAL *)g->parts[g->cur ^ 1];
     int64_t cells = (int64_t)D.nx * D.ny * D.nz;
-    rebin_kernel<REAL><<<(unsigned)((cells + 3) / 4), 128, 0, s>>>(co, po, cn, pn, D, 0, D.nz, rebin, g->overflow);
-    count_launch();
-    int runs = (D.nx + RUN - 1) / RUN;
-    size_t smem = (size_t)(RUN + 2) * 9 * 3 * g->cap * sizeof(REAL) + ((RUN + 2) * 9 + RUN + 1) * sizeof(int);
-    static bool attr = false;
-    if (!attr) {
-        B200GEO_CUDA(cudaFuncSetAttribute(force_kernel<REAL, RUN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-        attr = true;
+    const bool fused = g_tuning.nbody_kernel >= 3 && g->cap % 4 == 0;
+    if (!fused) {
+        rebin_kernel<REAL><<<(unsigned)((cells + 3) / 4), 128, 0, s>>>(co, po, cn, pn, D, 0, D.nz, rebin, g->overflow);
+        count_launch();
     }
     REAL rc = (REAL)p->cutoff;
-    force_kernel<REAL, RUN><<<(unsigned)((int64_t)runs * D.ny * D.nz), 128, smem, s>>>(co, po, cn, pn, D, 0, runs, (REAL)p->dt, rc * rc);
+    if (g_tuning.nbody_kernel == 1 || g->cap % 4 != 0) {
+        int runs = (D.nx + RUN - 1) / RUN;
+        size_t smem = (size_t)(RUN + 2) * 9 * 3 * g->cap * sizeof(REAL) + ((RUN + 2) * 9 + RUN + 1) * sizeof(int);
+        static bool attr = false;
+        if (!attr) {
+            B200GEO_CUDA(cudaFuncSetAttribute(force_kernel<REAL, RUN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+            attr = true;
+        }
+        force_kernel<REAL, RUN><<<(unsigned)((int64_t)runs * D.ny * D.nz), 128, smem, s>>>(co, po, cn, pn, D, 0, runs, (REAL)p->dt, rc * rc);
+    } else {
+        // run length / CTA size: two CTAs per SM must fit their staged neighbourhoods and lists in 227 KB
+        constexpr int G = sizeof(REAL) == 4 ? 16 : 8, NT = 16 * G, LMAX = 88, NC = (G + 2) * 9;
+        int runs = (D.nx + G - 1) / G;
+        size_t smem = (size_t)NC * g->cap * 3 * sizeof(REAL) + (NC + G + 2) * sizeof(int) + (size_t)(LMAX + 1) * NT * sizeof(unsigned short);
+        if (smem > 227 * 1024) return fail(B200GEO_ERR_LOGIC, "container capacity too large for the list kernel's shared memory");
+        static bool attr = false;
+        if (!attr) {
+            B200GEO_CUDA(cudaFuncSetAttribute(force_list_kernel<REAL, G, NT, LMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            attr = true;
+        }
+        // enlarged cutoff of the candidate filter: covers the rounding difference between the fused and
+        // the reference evaluation of r2 (a few ulp) many times over
+        REAL loose = rc * rc * (REAL)(1.0 + 1.0 / 65536.0);
+        if (fused) {
+            smem += (size_t)(G * g->cap + 2) * sizeof(unsigned short);
+            static bool attr3 = false;
+            if (!attr3) {
+                B200GEO_CUDA(cudaFuncSetAttribute(fused_kernel<REAL, G, NT, LMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+                attr3 = true;
+            }
+            fused_kernel<REAL, G, NT, LMAX><<<(unsigned)((int64_t)runs * D.ny * D.nz), NT, smem, s>>>(
+                co, po, cn, pn, D, 0, runs, (REAL)p->dt, rc * rc, loose, rebin, g->overflow);
+        } else {
+            force_list_kernel<REAL, G, NT, LMAX><<<(unsigned)((int64_t)runs * D.ny * D.nz), NT, smem, s>>>(
+                co, po, cn, pn, D, 0, runs, (REAL)p->dt, rc * rc, loose);
+        }
+    }
     count_launch();
     return check_cuda(cudaGetLastError(), "n-body sweep");
 }

@@ -1,0 +1,7 @@
+#!/bin/bash
+mkdir -p gpurun_out
+python -m pytest tests/test_nbody_gpu.py -x -q -m gpu 2>&1 | tail -2
+NBODY_KERNEL=3 python tools/nbody_bench.py 108 20 f4 | tail -1
+NBODY_KERNEL=2 python tools/nbody_bench.py 108 20 f4 | tail -1
+NBODY_KERNEL=3 python tools/nbody_bench.py 64 20 f8 | tail -1
+NBODY_KERNEL=3 timeout 600 ncu --set full --clock-control none --import-source on -k regex:fused_kernel -s 3 -c 1 -o gpurun_out/prof_r1j_nbody_fused python tools/nbody_bench.py 64 3 f4 > gpurun_out/r1j_ncu.log 2>&1
