@@ -355,6 +355,102 @@ def bench_device(workload, args, rank, world, dist, torch, with_e2e=True, with_c
     return out
 
 
+def bench_nbody(args, rank, world, dist, torch, containers=108, with_e2e=True):
+    """BASELINE.json configs[4]: short-range n-body in BoxCell containers, ~16.6 M particles per GPU
+    (255^3 lattice sites in 108^3 containers of edge 2.5 = cutoff), slabs of containers along z.
+    Metric: particle updates/s and candidate pair evaluations/s; bound = FP32 pipe."""
+    from libgeodecomp_b200 import capi, models, synth
+    from libgeodecomp_b200.simulator import SimpleInitializer, Writer
+    from libgeodecomp_b200.striping import StripedSimulator
+
+    n = containers
+    model = models.NBodyF
+    K, W = max(4, args.steps // 5), 2
+    cap = model.capacity
+    c, p = synth.nbody_cells(n, n, n, cap=cap, z0=rank * n, dtype=np.float32)
+    pc = torch.empty(c.shape, dtype=torch.int32, pin_memory=True)
+    pp = torch.empty(p.shape, dtype=torch.float32, pin_memory=True)
+    pc.numpy()[...] = c
+    pp.numpy()[...] = p
+    hc, hp = pc.numpy(), pp.numpy()
+    particles = int(c.sum())
+    # candidate pairs of one sweep: every particle meets every particle of its 27 containers
+    cc = np.pad(c.astype(np.int64), 1)
+    hood = sum(cc[dz:dz + n, dy:dy + n, dx:dx + n] for dz in range(3) for dy in range(3) for dx in range(3))
+    pairs = int((c.astype(np.int64) * hood).sum())
+    del c, p
+
+    class Init(SimpleInitializer):
+        def grid(self, target):
+            o, d = target.boundingBox()
+            target.loadCells(hc, hp, origin=o)
+
+    class Pull(Writer):
+        def stepFinished(self, grid, step, event):
+            if event == 2:
+                grid.saveCells(out=(hc, hp))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sim = StripedSimulator(Init((n, n, n * world), K), model, rank=rank, world=world, ghost_width=1,
+                           device=torch.cuda.current_device(), dist=dist)
+    sim.advance(W)
+    barrier()
+    launches0 = capi.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    sim.advance(K)
+    ev1.record()
+    barrier()
+    t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / K
+    launches = capi.launch_count() - launches0
+    sim.grid.dev.check()
+    # FP32 pipe: 8 flop per candidate (3 sub, 3 mul, 2 add; the reference arithmetic has no FMA) and
+    # ~20 more for the ~15 % inside the cutoff; peak = 148 SMs x 128 lanes x 2 flop x max SM clock
+    flop = pairs * (8 + 0.155 * 20)
+    peak = 148 * 128 * 2 * 1.965e9 / 1e12
+    out = {"workload": "nbody", "metric": "G particle updates/s", "value": 1e-9 * particles * world / (1e-3 * ms), "unit": "Gparticles/s",
+           "ms_per_step": ms, "particles_per_gpu": particles, "containers_per_gpu": [n, n, n], "capacity": cap,
+           "candidate_pairs_per_s": pairs * world / (1e-3 * ms), "dtype": "f32", "gpu_launches": launches, "steps": K,
+           "roofline": {"bound": "fp32-pipe", "achieved": flop / (1e-3 * ms) / 1e12, "peak": peak, "unit": "TFLOP/s",
+                        "frac": flop / (1e-3 * ms) / 1e12 / peak, "traffic": (ncu_traffic("nbody") or {}).get("dram_bytes_per_launch"),
+                        "note": "algorithmic flop (8 per candidate pair + 20 per interacting pair, no FMA by the parity rule) "
+                                "against the nominal FMA peak; pipe utilisation from ncu in profiles/"}}
+    if with_e2e:
+        sim.writers = [Pull("", 1 << 30)]
+        barrier()
+        ev0.record()
+        sim.run()
+        ev1.record()
+        barrier()
+        t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e_ms = float(t.item())
+        nbytes = hc.nbytes + hp.nbytes
+        out["e2e"] = {"value": 1e-9 * particles * world * K / (1e-3 * e_ms), "unit": "Gparticles/s",
+                      "h2d_bytes_per_step": nbytes * world / K, "d2h_bytes_per_step": nbytes * world / K, "ms_per_run": e_ms,
+                      "what": "StripedSimulator.run(): containers from pinned host memory -> %d steps -> pulled back" % K}
+    if rank == 0 and world == 1 and not args.no_cpu:
+        try:   # the reference's own OpenMPSimulator over BoxCell containers on a bounded sample
+            from oracle import oracle_py
+            sc, sp = synth.nbody_cells(24, 24, 24, dtype=np.float32)
+            _, st = oracle_py.run_ref_nbody(sc, sp, 3, omp=True, threads=os.cpu_count(), want_output=False)
+            out["cpu_baseline"] = {"value": st["gpups_compute"], "unit": "Gparticles/s", "cores": os.cpu_count(), "kind": "reference",
+                                   "sample": "24^3 containers (%d particles) x 3 steps, reference OpenMPSimulator over "
+                                             "BoxCell<FixedArray<LJParticle<float>, 32>>, TimeCompute interval" % int(sc.sum())}
+        except Exception as e:
+            out["cpu_baseline"] = {"value": None, "sample": "failed: %r" % (e,)}
+    del sim
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -400,6 +496,12 @@ def main():
                              with_e2e=(w in ("gol", "jacobi7_128")), with_clocks=False)
             others.append({k: r[k] for k in ("workload", "value", "ms_per_step", "roofline", "dtype", "dims_per_gpu",
                                              "global_dims", "gpu_launches") if k in r} | ({"e2e": r["e2e"]} if "e2e" in r else {}))
+
+    if not args.no_others and world in (1, 8):
+        try:
+            others.append(bench_nbody(args, rank, world, dist if world > 1 else None, torch))
+        except Exception as e:  # secondary workload: never take the headline line down with it
+            others.append({"workload": "nbody", "error": repr(e)})
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:

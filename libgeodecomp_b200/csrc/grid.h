@@ -67,7 +67,7 @@ struct Tuning {
     int jacobi_tb;        // temporal blocking depth of the Jacobi kernels (sweeps per launch; 0/1 = off)
     int jacobi_tb_rows;   // tile shape of the temporal-blocked kernel: 32 (2 rows/thread), 64 or 33 (4 rows/thread)
     int jacobi_tb_zchunk; // planes per CTA along z of the temporal-blocked kernel (0 = automatic)
-    int nbody_kernel;     // 1 = re-bin + one-pass force kernel, 2 = re-bin + candidate-list kernel, 3 = fused
+    int nbody_kernel;     // 1 = re-bin kernel + one-pass force kernel, otherwise the fused re-bin / candidate-list kernel
 };
 extern Tuning g_tuning;
 

@@ -194,15 +194,49 @@ force_kernel(const int32_t *__restrict__ cnt_old, const REAL *__restrict__ part_
     }
 }
 
-// Same update, two passes per particle so that the expensive part runs with full lanes:
-//   pass 1 walks the 27 containers in reference order and records, in a per-thread list in shared
-//          memory, the candidates inside a slightly ENLARGED cutoff (cheap FMA distance, 1 + 2^-16 margin:
-//          conservative, it only decides what pass 2 looks at);
-//   pass 2 walks that list in the same order and does the reference arithmetic, including the exact
-//          `r2 == 0 || r2 >= rc2` test, so the result is bit-identical to the one-pass kernel.
-// Only ~15 % of the candidates (4/3 pi rc^3 of the 27 rc^3 searched) interact; in the one-pass
-// kernel nearly every warp iteration has some lane inside the cutoff, so all lanes pay for the
-// force evaluation of every candidate.
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+
+// one contiguous block global -> shared through the TMA engine, completion counted on an mbarrier
+__device__ __forceinline__ void bulk_load(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
 template<typename REAL> struct alignas(2 * sizeof(REAL)) Pos2 { REAL x, y; };
 
 __device__ __forceinline__ float fma_any(float a, float b, float c) { return __fmaf_rn(a, b, c); }
@@ -221,203 +255,100 @@ __device__ __forceinline__ void load4(const double *p, double (&v)[4])
     v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
 }
 
-template<typename REAL, int G, int NT, int LMAX>
-__global__ void __launch_bounds__(NT)
-force_list_kernel(const int32_t *__restrict__ cnt_old, const REAL *__restrict__ part_old, const int32_t *__restrict__ cnt_new,
-                  REAL *__restrict__ part_new, BoxDims D, int z0, int runs_per_row, REAL dt, REAL rc2, REAL rc2_loose)
-{
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int cap = D.cap;
-    constexpr int NC = (G + 2) * 9;
-    Pos2<REAL> *sxy = reinterpret_cast<Pos2<REAL> *>(smem_raw);       // [NC][cap]
-    REAL *sz = reinterpret_cast<REAL *>(sxy + NC * cap);             // [NC][cap]
-    int *scnt = reinterpret_cast<int *>(sz + NC * cap);              // [NC]
-    int *pre = scnt + NC;                                            // [G + 1]
-    unsigned short *list = reinterpret_cast<unsigned short *>(pre + G + 1 + ((G + 1) & 1));  // [LMAX + 1][NT]
+// smallest REAL >= v: for a REAL-valued p, (double)p >= v <=> p >= round_up(v) and (double)p < v <=> p < round_up(v),
+// so the reference's double-precision position check can be done on the particles' own type
+__device__ __forceinline__ void round_up(double v, float& r) { r = __double2float_ru(v); }
+__device__ __forceinline__ void round_up(double v, double& r) { r = v; }
 
-    const int run = blockIdx.x % runs_per_row;
-    const int y = (blockIdx.x / runs_per_row) % D.ny;
-    const int z = z0 + blockIdx.x / (runs_per_row * D.ny);
-    const int x0 = run * G;
-
-    for (int c = threadIdx.x; c < NC; c += NT) {
-        int lx = c % (G + 2), ly = (c / (G + 2)) % 3, lz = c / ((G + 2) * 3);
-        int cx = x0 - 1 + lx;
-        scnt[c] = cx <= D.nx ? cnt_old[pcell(D, cx, y - 1 + ly, z - 1 + lz)] : 0;
-    }
-    if (threadIdx.x <= G) {
-        int acc = 0;
-        for (int j = 0; j < (int)threadIdx.x; ++j) acc += (x0 + j < D.nx) ? cnt_new[pcell(D, x0 + j, y, z)] : 0;
-        pre[threadIdx.x] = acc;
-    }
-    __syncthreads();
-    // four slots per work item: three 128-bit loads, interleaved (x, y) pairs and z to shared memory
-    const int quads = cap / 4;
-    for (int i = threadIdx.x; i < NC * quads; i += NT) {
-        int c = i / quads, sl = (i % quads) * 4;
-        if (sl < scnt[c]) {
-            int lx = c % (G + 2), ly = (c / (G + 2)) % 3, lz = c / ((G + 2) * 3);
-            const REAL *src = part_old + pcell(D, x0 - 1 + lx, y - 1 + ly, z - 1 + lz) * 6 * cap + sl;
-            REAL xs[4], ys[4], zs[4];
-            load4(src, xs);
-            load4(src + cap, ys);
-            load4(src + 2 * cap, zs);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                Pos2<REAL> xy;
-                xy.x = xs[q];
-                xy.y = ys[q];
-                sxy[c * cap + sl + q] = xy;
-                sz[c * cap + sl + q] = zs[q];
-            }
-        }
-    }
-    __syncthreads();
-
-    const int total = pre[G];
-    unsigned short *mylist = list + threadIdx.x;
-    for (int t = threadIdx.x; t < total; t += NT) {
-        int j = 0;
-        while (pre[j + 1] <= t) ++j;
-        const int slot = t - pre[j];
-        REAL *me = part_new + pcell(D, x0 + j, y, z) * 6 * cap + slot;
-        const REAL p0 = me[0], p1 = me[cap], p2 = me[2 * cap];
-        REAL v0 = me[3 * cap], v1 = me[4 * cap], v2 = me[5 * cap];
-        // pass 1: branch-free candidate filter. Every candidate is stored at the list's current end
-        // and the end only advances for the ones inside the enlarged cutoff.
-        int n = 0;
-        for (int k = 0; k < 27; ++k) {
-            const int cell = ((k / 9) * 3 + (k / 3) % 3) * (G + 2) + j + k % 3;
-            const int base = cell * cap, cn = scnt[cell];
-#pragma unroll 4
-            for (int p = 0; p < cn; ++p) {
-                const Pos2<REAL> xy = sxy[base + p];
-                const REAL d0 = p0 - xy.x, d1 = p1 - xy.y, d2 = p2 - sz[base + p];
-                const REAL r2 = fma_any(d2, d2, fma_any(d1, d1, d0 * d0));
-                mylist[n * NT] = (unsigned short)(base + p);
-                n = min(n + (r2 < rc2_loose ? 1 : 0), LMAX);
-            }
-        }
-        if (n < LMAX) {
-            // pass 2: the reference arithmetic on the short list, in the same order
-            for (int i = 0; i < n; ++i) {
-                const int idx = mylist[i * NT];
-                const Pos2<REAL> xy = sxy[idx];
-                const REAL d0 = p0 - xy.x, d1 = p1 - xy.y, d2 = p2 - sz[idx];
-                const REAL r2 = (d0 * d0 + d1 * d1) + d2 * d2;
-                if (r2 == (REAL)0 || r2 >= rc2) continue;
-                const REAL inv = (REAL)1 / r2;
-                const REAL s6 = inv * inv * inv;
-                const REAL f = ((REAL)24 * inv) * s6 * ((REAL)2 * s6 - (REAL)1);
-                v0 += (d0 * f) * dt;
-                v1 += (d1 * f) * dt;
-                v2 += (d2 * f) * dt;
-            }
-        } else {
-            // list full (a very dense neighbourhood): one pass over everything, like force_kernel
-            for (int k = 0; k < 27; ++k) {
-                const int cell = ((k / 9) * 3 + (k / 3) % 3) * (G + 2) + j + k % 3;
-                const int base = cell * cap, cn = scnt[cell];
-                for (int p = 0; p < cn; ++p) {
-                    const Pos2<REAL> xy = sxy[base + p];
-                    const REAL d0 = p0 - xy.x, d1 = p1 - xy.y, d2 = p2 - sz[base + p];
-                    const REAL r2 = (d0 * d0 + d1 * d1) + d2 * d2;
-                    if (r2 == (REAL)0 || r2 >= rc2) continue;
-                    const REAL inv = (REAL)1 / r2;
-                    const REAL s6 = inv * inv * inv;
-                    const REAL f = ((REAL)24 * inv) * s6 * ((REAL)2 * s6 - (REAL)1);
-                    v0 += (d0 * f) * dt;
-                    v1 += (d1 * f) * dt;
-                    v2 += (d2 * f) * dt;
-                }
-            }
-        }
-        me[0] = p0 + v0 * dt;
-        me[cap] = p1 + v1 * dt;
-        me[2 * cap] = p2 + v2 * dt;
-        me[3 * cap] = v0;
-        me[4 * cap] = v1;
-        me[5 * cap] = v2;
-    }
-}
-
-// Re-bin and update in ONE kernel: the staged neighbourhood serves both, the new containers are
-// written once (no separate pass over the grid for addContainedParticles).
+// Re-bin and update in ONE kernel: the staged neighbourhood serves both, and the new containers
+// are written once.
 template<typename REAL, int G, int NT, int LMAX>
 __global__ void __launch_bounds__(NT)
 fused_kernel(const int32_t *__restrict__ cnt_old, const REAL *__restrict__ part_old, int32_t *__restrict__ cnt_new,
              REAL *__restrict__ part_new, BoxDims D, int z0, int runs_per_row, REAL dt, REAL rc2, REAL rc2_loose,
              int rebin, int *overflow)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     const int cap = D.cap;
+    // a staged container = the position block of the old container as it lies in HBM, x[cap] y[cap]
+    // z[cap] (one bulk copy), `SP` elements apart: the 4 extra elements shift consecutive containers
+    // by 4 banks, so lanes working on neighbouring containers do not collide in shared memory
+    const int SP = 3 * cap + 4;
     constexpr int NC = (G + 2) * 9;
-    Pos2<REAL> *sxy = reinterpret_cast<Pos2<REAL> *>(smem_raw);       // [NC][cap]
-    REAL *sz = reinterpret_cast<REAL *>(sxy + NC * cap);             // [NC][cap]
-    int *scnt = reinterpret_cast<int *>(sz + NC * cap);              // [NC]
+    REAL *spos = reinterpret_cast<REAL *>(smem_raw);                 // [NC][SP]
+    int *scnt = reinterpret_cast<int *>(spos + NC * SP);             // [NC]
     int *pre = scnt + NC;                                            // [G + 1]
-    unsigned short *newidx = reinterpret_cast<unsigned short *>(pre + G + 1 + ((G + 1) & 1));  // [G][cap]: staged index of every new particle
-    unsigned short *list = newidx + G * cap + ((G * cap) & 1);                                  // [LMAX + 1][NT]
+    uint64_t *bar = reinterpret_cast<uint64_t *>(pre + G + 1 + ((G + 1) & 1));
+    unsigned short *newidx = reinterpret_cast<unsigned short *>(bar + 1);   // [G][cap]: staged index of every new particle
+    unsigned short *list = newidx + G * cap + ((G * cap) & 1);              // [LMAX][NT]
 
     const int run = blockIdx.x % runs_per_row;
     const int y = (blockIdx.x / runs_per_row) % D.ny;
     const int z = z0 + blockIdx.x / (runs_per_row * D.ny);
     const int x0 = run * G;
 
+    // stage the old neighbourhood of the whole run: local (lx, ly, lz) = container (x0 - 1 + lx, y - 1 + ly,
+    // z - 1 + lz). One thread per container reads its count and, if it holds particles, issues ONE
+    // bulk asynchronous copy (cp.async.bulk, the TMA engine) of its 3 * cap positions; all copies are in
+    // flight at once and complete on one mbarrier.
+    if (threadIdx.x == 0) {
+        mbar_init(bar, NC);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
     for (int c = threadIdx.x; c < NC; c += NT) {
         int lx = c % (G + 2), ly = (c / (G + 2)) % 3, lz = c / ((G + 2) * 3);
         int cx = x0 - 1 + lx;
-        scnt[c] = cx <= D.nx ? cnt_old[pcell(D, cx, y - 1 + ly, z - 1 + lz)] : 0;
-    }
-    __syncthreads();
-    // four slots per work item: three 128-bit loads, interleaved (x, y) pairs and z to shared memory
-    const int quads = cap / 4;
-    for (int i = threadIdx.x; i < NC * quads; i += NT) {
-        int c = i / quads, sl = (i % quads) * 4;
-        if (sl < scnt[c]) {
-            int lx = c % (G + 2), ly = (c / (G + 2)) % 3, lz = c / ((G + 2) * 3);
-            const REAL *src = part_old + pcell(D, x0 - 1 + lx, y - 1 + ly, z - 1 + lz) * 6 * cap + sl;
-            REAL xs[4], ys[4], zs[4];
-            load4(src, xs);
-            load4(src + cap, ys);
-            load4(src + 2 * cap, zs);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                Pos2<REAL> xy;
-                xy.x = xs[q];
-                xy.y = ys[q];
-                sxy[c * cap + sl + q] = xy;
-                sz[c * cap + sl + q] = zs[q];
+        int n = 0;
+        if (cx <= D.nx) {
+            const int64_t pc = pcell(D, cx, y - 1 + ly, z - 1 + lz);
+            n = cnt_old[pc];
+            if (n > 0) {
+                const uint32_t bytes = 3 * cap * sizeof(REAL);
+                mbar_expect_tx(bar, bytes);
+                bulk_load(spos + c * SP, part_old + pc * 6 * cap, bytes, bar);
             }
         }
+        if (n <= 0) mbar_arrive(bar);
+        scnt[c] = n;
     }
     __syncthreads();
+    while (!mbar_try_wait(bar, 0)) {}
 
     // re-bin (boxcell.h:123-138,164-174): one warp per container of the run scans the 27 staged OLD
-    // containers in order and keeps, by ordered ballot/popc compaction, the particles inside its box
+    // containers in reference order and keeps, by ordered ballot/popc compaction, the particles inside
+    // its box; nanoStep != 0 keeps the container as it is
     {
         const int lane = threadIdx.x & 31;
         for (int j = threadIdx.x >> 5; j < G; j += NT / 32) {
             int n = 0;
             if (x0 + j < D.nx) {
-                const double ox = (double)(x0 + j + D.org[0]) * D.edge, oy = (double)(y + D.org[1]) * D.edge,
-                             oz = (double)(z + D.org[2]) * D.edge;
-                const double qx = ox + D.edge, qy = oy + D.edge, qz = oz + D.edge;
-                for (int k = rebin ? 0 : 13; k < (rebin ? 27 : 14); ++k) {
+                const double ex = (double)(x0 + j + D.org[0]) * D.edge, ey = (double)(y + D.org[1]) * D.edge,
+                             ez = (double)(z + D.org[2]) * D.edge;
+                REAL ox, oy, oz, qx, qy, qz;
+                round_up(ex, ox);
+                round_up(ey, oy);
+                round_up(ez, oz);
+                round_up(ex + D.edge, qx);
+                round_up(ey + D.edge, qy);
+                round_up(ez + D.edge, qz);
+#pragma unroll
+                for (int k = 0; k < 27; ++k) {
+                    if (!rebin && k != 13) continue;
                     const int cell = ((k / 9) * 3 + (k / 3) % 3) * (G + 2) + j + k % 3;
                     const int cn = scnt[cell];
                     for (int b = 0; b < cn; b += 32) {
                         const int sl = b + lane;
                         bool inside = false;
                         if (sl < cn) {
-                            const Pos2<REAL> xy = sxy[cell * cap + sl];
-                            const double px = xy.x, py = xy.y, pz = sz[cell * cap + sl];
+                            const REAL *q = spos + cell * SP + sl;
+                            const REAL px = q[0], py = q[cap], pz = q[2 * cap];
                             inside = !rebin || (ox <= px && oy <= py && oz <= pz && px < qx && py < qy && pz < qz);
                         }
                         const unsigned mask = __ballot_sync(0xffffffffu, inside);
                         if (inside) {
                             const int dst = n + __popc(mask & ((1u << lane) - 1));
-                            if (dst < cap) newidx[j * cap + dst] = (unsigned short)(cell * cap + sl);
+                            if (dst < cap) newidx[j * cap + dst] = (unsigned short)(cell * SP + sl);
                         }
                         n += __popc(mask);
                     }
@@ -437,39 +368,33 @@ fused_kernel(const int32_t *__restrict__ cnt_old, const REAL *__restrict__ part_
     }
     __syncthreads();
 
+    // updateCargo (boxcell.h:140-152) with LJParticle::update, two passes per particle so that the
+    // expensive part runs with full lanes:
+    //   pass 1 walks the 27 containers in reference order and appends to a per-thread list in shared
+    //          memory the candidates inside a slightly ENLARGED cutoff (cheap fused distance; the margin
+    //          of 2^-16 covers its rounding difference to the reference expression many times over: it
+    //          only decides what pass 2 looks at). Branch-free: every candidate is stored at the list's
+    //          end, the end only advances for the accepted ones.
+    //   pass 2 walks the list in the same order with the reference arithmetic, including the exact
+    //          `r2 == 0 || r2 >= rc2` test, so the result is bit-identical to the one-pass kernel.
+    // Only ~15 % of the candidates interact (4/3 pi rc^3 of the 27 rc^3 searched); in a one-pass loop
+    // nearly every warp iteration has SOME lane inside the cutoff and all lanes pay for the force.
     const int total = pre[G];
     unsigned short *mylist = list + threadIdx.x;
     for (int t = threadIdx.x; t < total; t += NT) {
         int j = 0;
         while (pre[j + 1] <= t) ++j;
         const int slot = t - pre[j];
-        REAL *me = part_new + pcell(D, x0 + j, y, z) * 6 * cap + slot;
         // the particle's old state: position from the staged copy, velocity from its old container
-        const int from = newidx[j * cap + slot], fc = from / cap, fs = from % cap;
+        const int from = newidx[j * cap + slot], fc = from / SP, fs = from % SP;
         const REAL *old = part_old + pcell(D, x0 - 1 + fc % (G + 2), y - 1 + (fc / (G + 2)) % 3, z - 1 + fc / ((G + 2) * 3)) * 6 * cap + fs;
-        const REAL p0 = sxy[from].x, p1 = sxy[from].y, p2 = sz[from];
+        const REAL p0 = spos[from], p1 = spos[from + cap], p2 = spos[from + 2 * cap];
         REAL v0 = old[3 * cap], v1 = old[4 * cap], v2 = old[5 * cap];
-        // pass 1: branch-free candidate filter. Every candidate is stored at the list's current end
-        // and the end only advances for the ones inside the enlarged cutoff.
-        int n = 0;
-        for (int k = 0; k < 27; ++k) {
-            const int cell = ((k / 9) * 3 + (k / 3) % 3) * (G + 2) + j + k % 3;
-            const int base = cell * cap, cn = scnt[cell];
-#pragma unroll 4
-            for (int p = 0; p < cn; ++p) {
-                const Pos2<REAL> xy = sxy[base + p];
-                const REAL d0 = p0 - xy.x, d1 = p1 - xy.y, d2 = p2 - sz[base + p];
-                const REAL r2 = fma_any(d2, d2, fma_any(d1, d1, d0 * d0));
-                mylist[n * NT] = (unsigned short)(base + p);
-                n = min(n + (r2 < rc2_loose ? 1 : 0), LMAX);
-            }
-        }
-        if (n < LMAX) {
-            // pass 2: the reference arithmetic on the short list, in the same order
+
+        auto drain = [&](int n) {
             for (int i = 0; i < n; ++i) {
-                const int idx = mylist[i * NT];
-                const Pos2<REAL> xy = sxy[idx];
-                const REAL d0 = p0 - xy.x, d1 = p1 - xy.y, d2 = p2 - sz[idx];
+                const REAL *q = spos + mylist[i * NT];
+                const REAL d0 = p0 - q[0], d1 = p1 - q[cap], d2 = p2 - q[2 * cap];
                 const REAL r2 = (d0 * d0 + d1 * d1) + d2 * d2;
                 if (r2 == (REAL)0 || r2 >= rc2) continue;
                 const REAL inv = (REAL)1 / r2;
@@ -479,25 +404,31 @@ fused_kernel(const int32_t *__restrict__ cnt_old, const REAL *__restrict__ part_
                 v1 += (d1 * f) * dt;
                 v2 += (d2 * f) * dt;
             }
-        } else {
-            // list full (a very dense neighbourhood): one pass over everything, like force_kernel
-            for (int k = 0; k < 27; ++k) {
-                const int cell = ((k / 9) * 3 + (k / 3) % 3) * (G + 2) + j + k % 3;
-                const int base = cell * cap, cn = scnt[cell];
+        };
+
+        unsigned short *lp = mylist;
+        for (int kk = 0; kk < 9; ++kk) {
+            for (int kx = 0; kx < 3; ++kx) {
+                const int cell = kk * (G + 2) + j + kx;
+                const int cn = scnt[cell];
+                if ((int)(lp - mylist) + cn * NT > LMAX * NT) {  // the list could overflow: evaluate what is there
+                    drain((int)(lp - mylist) / NT);
+                    lp = mylist;
+                }
+                const REAL *q = spos + cell * SP;
+                const int idx0 = cell * SP;
+#pragma unroll 4
                 for (int p = 0; p < cn; ++p) {
-                    const Pos2<REAL> xy = sxy[base + p];
-                    const REAL d0 = p0 - xy.x, d1 = p1 - xy.y, d2 = p2 - sz[base + p];
-                    const REAL r2 = (d0 * d0 + d1 * d1) + d2 * d2;
-                    if (r2 == (REAL)0 || r2 >= rc2) continue;
-                    const REAL inv = (REAL)1 / r2;
-                    const REAL s6 = inv * inv * inv;
-                    const REAL f = ((REAL)24 * inv) * s6 * ((REAL)2 * s6 - (REAL)1);
-                    v0 += (d0 * f) * dt;
-                    v1 += (d1 * f) * dt;
-                    v2 += (d2 * f) * dt;
+                    const REAL d0 = p0 - q[p], d1 = p1 - q[cap + p], d2 = p2 - q[2 * cap + p];
+                    const REAL r2 = fma_any(d2, d2, fma_any(d1, d1, d0 * d0));
+                    *lp = (unsigned short)(idx0 + p);
+                    lp += r2 < rc2_loose ? NT : 0;
                 }
             }
         }
+        drain((int)(lp - mylist) / NT);
+
+        REAL *me = part_new + pcell(D, x0 + j, y, z) * 6 * cap + slot;
         me[0] = p0 + v0 * dt;
         me[cap] = p1 + v1 * dt;
         me[2 * cap] = p2 + v2 * dt;
@@ -552,13 +483,11 @@ int sweep(b200geo_boxgrid *g, const b200geo_nbody_params *p, int rebin, cudaStre
     const REAL *po = (const REAL *)g->parts[g->cur];
     REAL *pn = (REAL *)g->parts[g->cur ^ 1];
     int64_t cells = (int64_t)D.nx * D.ny * D.nz;
-    const bool fused = g_tuning.nbody_kernel >= 3 && g->cap % 4 == 0;
-    if (!fused) {
-        rebin_kernel<REAL><<<(unsigned)((cells + 3) / 4), 128, 0, s>>>(co, po, cn, pn, D, 0, D.nz, rebin, g->overflow);
-        count_launch();
-    }
     REAL rc = (REAL)p->cutoff;
     if (g_tuning.nbody_kernel == 1 || g->cap % 4 != 0) {
+        // two kernels: re-bin, then the one-pass force kernel (any capacity)
+        rebin_kernel<REAL><<<(unsigned)((cells + 3) / 4), 128, 0, s>>>(co, po, cn, pn, D, 0, D.nz, rebin, g->overflow);
+        count_launch();
         int runs = (D.nx + RUN - 1) / RUN;
         size_t smem = (size_t)(RUN + 2) * 9 * 3 * g->cap * sizeof(REAL) + ((RUN + 2) * 9 + RUN + 1) * sizeof(int);
         static bool attr = false;
@@ -571,29 +500,18 @@ int sweep(b200geo_boxgrid *g, const b200geo_nbody_params *p, int rebin, cudaStre
         // run length / CTA size: two CTAs per SM must fit their staged neighbourhoods and lists in 227 KB
         constexpr int G = sizeof(REAL) == 4 ? 16 : 8, NT = 16 * G, LMAX = 88, NC = (G + 2) * 9;
         int runs = (D.nx + G - 1) / G;
-        size_t smem = (size_t)NC * g->cap * 3 * sizeof(REAL) + (NC + G + 2) * sizeof(int) + (size_t)(LMAX + 1) * NT * sizeof(unsigned short);
-        if (smem > 227 * 1024) return fail(B200GEO_ERR_LOGIC, "container capacity too large for the list kernel's shared memory");
-        static bool attr = false;
-        if (!attr) {
-            B200GEO_CUDA(cudaFuncSetAttribute(force_list_kernel<REAL, G, NT, LMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-            attr = true;
+        size_t smem = (size_t)NC * (3 * g->cap + 4) * sizeof(REAL) + (NC + G + 2) * sizeof(int) + 8 +
+                      (size_t)(G * g->cap + 2) * sizeof(unsigned short) + (size_t)LMAX * NT * sizeof(unsigned short);
+        if (smem > 227 * 1024) return fail(B200GEO_ERR_LOGIC, "container capacity too large for the fused kernel's shared memory");
+        static bool attr3 = false;
+        if (!attr3) {
+            B200GEO_CUDA(cudaFuncSetAttribute(fused_kernel<REAL, G, NT, LMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            attr3 = true;
         }
-        // enlarged cutoff of the candidate filter: covers the rounding difference between the fused and
-        // the reference evaluation of r2 (a few ulp) many times over
+        // enlarged cutoff of the candidate filter
         REAL loose = rc * rc * (REAL)(1.0 + 1.0 / 65536.0);
-        if (fused) {
-            smem += (size_t)(G * g->cap + 2) * sizeof(unsigned short);
-            static bool attr3 = false;
-            if (!attr3) {
-                B200GEO_CUDA(cudaFuncSetAttribute(fused_kernel<REAL, G, NT, LMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-                attr3 = true;
-            }
-            fused_kernel<REAL, G, NT, LMAX><<<(unsigned)((int64_t)runs * D.ny * D.nz), NT, smem, s>>>(
-                co, po, cn, pn, D, 0, runs, (REAL)p->dt, rc * rc, loose, rebin, g->overflow);
-        } else {
-            force_list_kernel<REAL, G, NT, LMAX><<<(unsigned)((int64_t)runs * D.ny * D.nz), NT, smem, s>>>(
-                co, po, cn, pn, D, 0, runs, (REAL)p->dt, rc * rc, loose);
-        }
+        fused_kernel<REAL, G, NT, LMAX><<<(unsigned)((int64_t)runs * D.ny * D.nz), NT, smem, s>>>(
+            co, po, cn, pn, D, 0, runs, (REAL)p->dt, rc * rc, loose, rebin, g->overflow);
     }
     count_launch();
     return check_cuda(cudaGetLastError(), "n-body sweep");

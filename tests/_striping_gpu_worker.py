@@ -80,6 +80,29 @@ def main():
         for m, (n, t) in enumerate(models.LBMCellF.members):
             check("lbm g%d overlap %s %s" % (ghost, overlap, n), sim, want[m].view(t), n)
 
+    # n-body: slabs of containers, one ghost plane of containers (counts + particles) per side
+    class CellInit(SimpleInitializer):
+        def __init__(self, counts, parts, steps):
+            SimpleInitializer.__init__(self, counts.shape[::-1], steps)
+            self.counts, self.parts = counts, parts
+
+        def grid(self, target):
+            o, d = target.boundingBox()
+            sl = tuple(slice(o[i], o[i] + d[i]) for i in reversed(range(3)))
+            target.loadCells(self.counts[sl], self.parts[sl], origin=o)
+
+    for real, dims, steps, vel in [(np.float32, (6, 5, 8), 8, 10.0), (np.float64, (4, 4, 12), 6, 12.0)]:
+        c, p = synth.nbody_cells(*dims, vel=vel, dtype=real)
+        model = (models.NBodyF if real == np.float32 else models.NBodyD).with_params(dt=0.01)
+        sim = StripedSimulator(CellInit(c, p, steps), model, rank=rank, world=world, ghost_width=1, device=local, dist=dist)
+        sim.run()
+        gc, gp = sim.getGrid().saveCells()
+        wc, wp = oracle_py.nbody(c, p, steps, dt=0.01)
+        b = slab_bounds(dims[2], world)
+        if not (np.array_equal(gc, wc[b[rank]:b[rank + 1]]) and
+                np.array_equal(gp.view(np.uint8), np.ascontiguousarray(wp[b[rank]:b[rank + 1]]).view(np.uint8))):
+            failures.append("nbody %s rank %d" % (np.dtype(real).name, rank))
+
     with open("%s.%d" % (sys.argv[1], rank), "w") as f:
         f.write("FAIL " + "; ".join(failures) if failures else "OK")
     dist.barrier()
