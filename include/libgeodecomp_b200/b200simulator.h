@@ -28,6 +28,7 @@
 #include <libgeodecomp/storage/gridbase.h>
 
 #include <cstddef>
+#include <algorithm>
 #include <cstring>
 #include <new>
 #include <stdexcept>
@@ -95,6 +96,26 @@ inline void toStreak4(const Streak<DIM>& s, const Coord<DIM>& origin, int32_t *o
 }
 
 }
+
+}
+
+#include "b200boxgrid.h"
+
+namespace LibGeoDecomp {
+
+template<typename CELL>
+class B200Grid;
+
+/* which device grid backs a cell type: the SoA grid, or the container grid for BoxCell<FixedArray<P, N> > */
+template<typename CELL>
+struct B200GridSelector {
+    typedef B200Grid<CELL> Type;
+};
+
+template<typename PARTICLE, int N>
+struct B200GridSelector<BoxCell<FixedArray<PARTICLE, N> > > {
+    typedef B200BoxGrid<PARTICLE, N> Type;
+};
 
 template<typename CELL>
 class B200Grid : public GridBase<CELL, APITraits::SelectTopology<CELL>::Value::DIM>
@@ -323,6 +344,13 @@ private:
             desc.ghost[i] = used ? Stencil::RADIUS : 0;
             int mode = (used && Topology::wrapsAxis(i)) ? B200GEO_GHOST_WRAP : B200GEO_GHOST_EDGE;
             desc.ghost_mode[i][0] = desc.ghost_mode[i][1] = mode;
+            // periodic images 4 cells wide let the temporal-blocked Jacobi kernels fuse up to 4 sweeps
+            // per launch on a Torus (a wrap ghost may not be wider than the grid itself)
+            int k = B200KernelBinding<CELL>::kernel();
+            bool jacobi = k == B200GEO_KERNEL_JACOBI6 || k == B200GEO_KERNEL_JACOBI7 || k == B200GEO_KERNEL_JACOBI27;
+            if (jacobi && mode == B200GEO_GHOST_WRAP) {
+                desc.ghost[i] = std::max(desc.ghost[i], std::min(4, desc.dim[i]));
+            }
         }
         if (members.size() > B200GEO_MAX_MEMBERS) {
             throw std::out_of_range("too many SoA members");
@@ -385,7 +413,7 @@ public:
     typedef typename MonolithicSimulator<CELL>::Topology Topology;
     typedef typename MonolithicSimulator<CELL>::WriterVector WriterVector;
     typedef typename Steerer<CELL>::SteererFeedback SteererFeedback;
-    typedef B200Grid<CELL> GridType;
+    typedef typename B200GridSelector<CELL>::Type GridType;
     typedef GridBase<CELL, Topology::DIM> GridBaseType;
     static const int DIM = Topology::DIM;
     static const unsigned NANO_STEPS = APITraits::SelectNanoSteps<CELL>::VALUE;

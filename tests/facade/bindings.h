@@ -8,6 +8,7 @@
 #include "models/conway.h"
 #include "models/jacobi.h"
 #include "models/lbm.h"
+#include "models/nbody.h"
 
 #define B200_BIND_JACOBI(NAME, KERNEL) \
     B200GEO_BIND_CELL(b200models::NAME, KERNEL, B200GEO_MEMBER_ENTRY(b200models::NAME, temp))
@@ -29,5 +30,11 @@ B200GEO_BIND_CELL(b200models::LBMCellF, B200GEO_KERNEL_LBM_D3Q19,
     B200_LBM_M(TW) B200_LBM_M(BW) B200_LBM_M(TE) B200_LBM_M(BE)
     B200_LBM_M(TN) B200_LBM_M(BN) B200_LBM_M(TS) B200_LBM_M(BS)
     B200_LBM_M(density) B200_LBM_M(velocityX) B200_LBM_M(velocityY) B200_LBM_M(velocityZ) B200_LBM_M(state))
+
+/* n-body: where position and velocity live inside the particle, and the model constants */
+B200GEO_BIND_PARTICLE(b200models::LJParticle<float>, float, pos, vel,
+                      b200models::NBodyParams::dt(), b200models::NBodyParams::cutoff(), b200models::NBodyParams::cellEdge())
+B200GEO_BIND_PARTICLE(b200models::LJParticle<double>, double, pos, vel,
+                      b200models::NBodyParams::dt(), b200models::NBodyParams::cutoff(), b200models::NBodyParams::cellEdge())
 
 #endif

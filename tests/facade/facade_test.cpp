@@ -12,6 +12,7 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <iostream>
 
 #include "bindings.h"
@@ -247,6 +248,74 @@ void testRegionBytesMatchSoAGrid()
     std::printf("saveRegion/loadRegion/saveMember/loadMember vs SoAGrid: %s\n", (a == b && c == d) ? "byte-identical" : "DIFFERENT");
 }
 
+/* n-body: BoxCell<FixedArray<LJParticle<REAL>, 32> > through the reference's SerialSimulator and through
+ * B200Simulator (container grid on the device): same occupancy, bit-identical particles */
+template<typename REAL>
+class ParticleInitializer : public SimpleInitializer<BoxCell<FixedArray<LJParticle<REAL>, NBODY_CAPACITY> > >
+{
+public:
+    typedef BoxCell<FixedArray<LJParticle<REAL>, NBODY_CAPACITY> > Cell;
+
+    ParticleInitializer(const Coord<3>& dim, unsigned steps) : SimpleInitializer<Cell>(dim, steps) {}
+
+    virtual void grid(GridBase<Cell, 3> *ret)
+    {
+        CoordBox<3> box = ret->boundingBox();
+        Coord<3> dim = this->gridDimensions();
+        double e = NBodyParams::cellEdge();
+        for (CoordBox<3>::Iterator i = box.begin(); i != box.end(); ++i) {
+            Cell cell(FloatCoord<3>(i->x() * e, i->y() * e, i->z() * e), FloatCoord<3>(e, e, e));
+            uint64_t id = i->toIndex(dim);
+            int n = 8 + (int)(splitmix(id) % 9);
+            for (int p = 0; p < n; ++p) {
+                LJParticle<REAL> particle;
+                for (int k = 0; k < 3; ++k) {
+                    // well separated sites inside the container, fast enough to cross faces within a few steps
+                    double site = ((p >> k) & 1) * 0.5 + (p / 8) * 0.25 + 0.125 + 0.05 * uniform(id * 1000 + p * 8 + k);
+                    particle.pos[k] = (REAL)(((*i)[k] + site) * e);
+                    particle.vel[k] = (REAL)(16.0 * (uniform(id * 1000 + p * 8 + k + 4) - 0.5));
+                }
+                cell << particle;
+            }
+            ret->set(*i, cell);
+        }
+    }
+};
+
+template<typename REAL>
+static void compareNBody(const char *name, const Coord<3>& dim, unsigned steps)
+{
+    typedef BoxCell<FixedArray<LJParticle<REAL>, NBODY_CAPACITY> > Cell;
+    NBodyParams::dt() = 0.01;
+    SerialSimulator<Cell> ref(new ParticleInitializer<REAL>(dim, steps));
+    B200Simulator<Cell> dev(new ParticleInitializer<REAL>(dim, steps));
+    ref.run();
+    dev.run();
+    const GridBase<Cell, 3> *a = ref.getGrid();
+    const GridBase<Cell, 3> *b = dev.getGrid();
+    std::size_t particles = 0, moved = 0, bad = 0;
+    CoordBox<3> box(Coord<3>(), dim);
+    for (CoordBox<3>::Iterator i = box.begin(); i != box.end(); ++i) {
+        Cell ca = a->get(*i), cb = b->get(*i);
+        if (ca.size() != cb.size()) {
+            ++bad;
+            continue;
+        }
+        particles += ca.size();
+        for (std::size_t p = 0; p < ca.size(); ++p) {
+            if (std::memcmp(ca[p].pos, cb[p].pos, sizeof(ca[p].pos)) || std::memcmp(ca[p].vel, cb[p].vel, sizeof(ca[p].vel))) {
+                ++bad;
+            }
+            moved += ca[p].vel[0] != 0;
+        }
+    }
+    CHECK(bad == 0);
+    CHECK(particles > 0 && moved > 0);
+    CHECK(ref.getStep() == dev.getStep());
+    std::printf("%-14s %3dx%3dx%3d x %2u steps: %zu particles, %s\n", name, dim.x(), dim.y(), dim.z(), steps, particles,
+                bad == 0 ? "bit-identical to SerialSimulator" : "DIFFERENT");
+}
+
 int main()
 {
     try {
@@ -259,6 +328,8 @@ int main()
         compareWithSerialSimulator<ConwayCube, SeededInitializer<ConwayCube>, 2>("ConwayCube", Coord<2>(70, 33), 25);
         compareWithSerialSimulator<ConwayTorus, SeededInitializer<ConwayTorus>, 2>("ConwayTorus", Coord<2>(48, 20), 25);
         compareWithSerialSimulator<LBMCellF, LBMInitializer, 3>("LBMCellF", Coord<3>(18, 12, 10), 15);
+        compareNBody<float>("NBody<float>", Coord<3>(7, 5, 4), 8);
+        compareNBody<double>("NBody<double>", Coord<3>(4, 6, 3), 6);
         testEventProtocol();
         testRegionBytesMatchSoAGrid();
     } catch (const std::exception& e) {
