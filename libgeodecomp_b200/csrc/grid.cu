@@ -10,7 +10,7 @@
 
 namespace b200geo {
 
-static const Tuning g_tuning_default = {0, -1, 0, 128, 2, 33, 0, 3};
+static const Tuning g_tuning_default = {0, -1, 0, 128, 2, 33, 0, 4, 0, 3};
 Tuning g_tuning = g_tuning_default;
 static thread_local std::string g_last_error;
 static std::atomic<uint64_t> g_launches(0);
@@ -81,6 +81,8 @@ int b200geo_set_tuning(const char *key, int value)
     else if (k == "jacobi.tb") g_tuning.jacobi_tb = value < 0 ? g_tuning_default.jacobi_tb : value;
     else if (k == "jacobi.tb_rows") g_tuning.jacobi_tb_rows = value < 0 ? g_tuning_default.jacobi_tb_rows : value;
     else if (k == "jacobi.tb_zchunk") g_tuning.jacobi_tb_zchunk = value < 0 ? g_tuning_default.jacobi_tb_zchunk : value;
+    else if (k == "gol.bits") g_tuning.gol_bits = value < 0 ? g_tuning_default.gol_bits : value;
+    else if (k == "gol.bits_rows") g_tuning.gol_bits_rows = value < 0 ? g_tuning_default.gol_bits_rows : value;
     else if (k == "nbody.kernel") g_tuning.nbody_kernel = value < 0 ? g_tuning_default.nbody_kernel : value;
     else return fail(B200GEO_ERR_INVALID, "unknown tuning key " + k);
     return B200GEO_OK;
@@ -186,6 +188,7 @@ int b200geo_grid_destroy(b200geo_grid *g)
     cudaFree(g->buf[0]);
     cudaFree(g->buf[1]);
     if (g->scratch) cudaFree(g->scratch);
+    if (g->bits) cudaFree(g->bits);
     for (int i = 0; i < 4; ++i) cudaEventDestroy(g->ev[i]);
     delete g;
     return B200GEO_OK;
@@ -402,6 +405,14 @@ int b200geo_step(b200geo_grid *g, int kernel, const void *params, uint32_t first
     B200GEO_CUDA(cudaSetDevice(g->device));
     if (g->stats_on) cudaEventRecord(g->ev[0], s);
     const int a = g->slab_axis;
+    // Game of Life, several sweeps in one call: pack to one bit per cell, sweep the packed copy (it
+    // stays in L2), unpack. The byte grid, its ghost ring and `cur` are as after n_steps byte sweeps.
+    if (kernel == B200GEO_KERNEL_GOL && g_tuning.gol_bits > 0 && n_steps >= (uint32_t)g_tuning.gol_bits && gol_bits_applicable(g)) {
+        rc = sweep_gol_bits(g, n_steps, s);
+        if (rc) return rc;
+        g->sweeps += n_steps;
+        n_steps = 0;
+    }
     const bool jacobi = kernel == B200GEO_KERNEL_JACOBI6 || kernel == B200GEO_KERNEL_JACOBI7 || kernel == B200GEO_KERNEL_JACOBI27;
     for (uint32_t t = 0; t < n_steps;) {
         // sweeps fused into this launch: the temporal-blocked Jacobi kernel takes `depth` sweeps per

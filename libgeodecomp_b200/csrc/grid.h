@@ -49,6 +49,8 @@ struct b200geo_grid {
     cudaEvent_t ev[4];
     double t_update, t_ghost;
     uint64_t sweeps;
+    void *bits;          // bit-packed copy of a Game of Life grid (two buffers), allocated on first use
+    size_t bits_bytes;
     void *scratch;       // small device scratch (streak lists etc.)
     size_t scratch_bytes;
 
@@ -67,6 +69,8 @@ struct Tuning {
     int jacobi_tb;        // temporal blocking depth of the Jacobi kernels (sweeps per launch; 0/1 = off)
     int jacobi_tb_rows;   // tile shape of the temporal-blocked kernel: 32 (2 rows/thread), 64 or 33 (4 rows/thread)
     int jacobi_tb_zchunk; // planes per CTA along z of the temporal-blocked kernel (0 = automatic)
+    int gol_bits;         // fewest sweeps per b200geo_step call for which Game of Life runs bit-packed (0 = never)
+    int gol_bits_rows;    // rows per CTA of the bit-packed kernel (0 = automatic)
     int nbody_kernel;     // 1 = re-bin kernel + one-pass force kernel, otherwise the fused re-bin / candidate-list kernel
 };
 extern Tuning g_tuning;
@@ -79,6 +83,8 @@ void count_launch(uint64_t n = 1);
 int sweep_jacobi(b200geo_grid *g, int kind, const Box& box, cudaStream_t s);
 int sweep_jacobi_tb(b200geo_grid *g, int kind, int depth, const Box& box, cudaStream_t s);
 int sweep_gol(b200geo_grid *g, const Box& box, cudaStream_t s);
+bool gol_bits_applicable(const b200geo_grid *g);
+int sweep_gol_bits(b200geo_grid *g, uint32_t sweeps, cudaStream_t s);
 int sweep_lbm(b200geo_grid *g, const Box& box, bool store_macroscopic, cudaStream_t s);
 
 // ghost maintenance and (de)serialisation kernels (region.cu)

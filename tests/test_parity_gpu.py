@@ -91,9 +91,13 @@ def test_jacobi6_example_torus_128(oracle):
     assert np.array_equal(got, oracle.jacobi(6, True, data, 30))
 
 
+@pytest.mark.parametrize("bits", [0, 4])
 @pytest.mark.parametrize("torus", [False, True])
-@pytest.mark.parametrize("shape", [(130, 150), (1, 1), (3, 17), (64, 2048), (100, 16), (37, 4099)])
-def test_gol_bit_exact(oracle, torus, shape):
+@pytest.mark.parametrize("shape", [(130, 150), (1, 1), (3, 17), (64, 2048), (100, 16), (37, 4099), (33, 4096), (200, 96), (5, 31)])
+def test_gol_bit_exact(oracle, tuning, bits, torus, shape):
+    """bits = 0: one byte-grid sweep per launch; 4: the bit-packed path (pack, 20 packed sweeps, unpack)
+    wherever it applies (a Torus narrower or wider than whole 32-cell words stays on the byte kernel)"""
+    tuning("gol.bits", bits)
     ny, nx = shape
     g = synth.gol_grid(nx, ny)
     model = models.ConwayTorus if torus else models.ConwayCube
@@ -109,11 +113,29 @@ def test_gol_2048_64_steps(oracle):
     assert np.array_equal(sim.getGrid().saveMember("alive"), oracle.gol(False, g, 64))
 
 
-def test_gol_alive_edge(oracle):
-    g = synth.gol_grid(70, 50)
-    sim = B200Simulator(MemberInit((70, 50), 9, {"alive": g}, edge=1), models.ConwayCube)
+@pytest.mark.parametrize("bits", [0, 4])
+@pytest.mark.parametrize("shape", [(50, 70), (40, 64), (9, 33)])
+def test_gol_alive_edge(oracle, tuning, bits, shape):
+    tuning("gol.bits", bits)
+    ny, nx = shape
+    g = synth.gol_grid(nx, ny)
+    sim = B200Simulator(MemberInit((nx, ny), 9, {"alive": g}, edge=1), models.ConwayCube)
     sim.run()
     assert np.array_equal(sim.getGrid().saveMember("alive"), oracle.gol(False, g, 9, edge_alive=1))
+
+
+def test_gol_packed_and_byte_sweeps_interleave(oracle):
+    """a packed multi-sweep call leaves the byte grid (and its ghost ring) exactly as byte sweeps would:
+    3 byte sweeps, 10 packed, 2 byte, 5 packed == 20 sweeps"""
+    g = synth.gol_grid(300, 77)
+    for model, torus in ((models.ConwayCube, False), (models.ConwayTorus, True)):
+        nx = 288 if torus else 300
+        gg = np.ascontiguousarray(g[:, :nx])
+        grid = B200Grid(model, (nx, 77))
+        grid.loadMember("alive", gg)
+        for n in (3, 10, 2, 5):
+            grid.dev.step(capi.KERNEL_GOL, n)
+        assert np.array_equal(grid.saveMember("alive"), oracle.gol(torus, gg, 20))
 
 
 def lbm_members(raw):
