@@ -3,6 +3,8 @@
  *   B200KernelBinding<CELL>  states which hand-written kernel family implements CELL::update /
  *                            CELL::updateLineX and where CELL's members live (the SoA member table
  *                            LIBFLATARRAY_REGISTER_SOA would generate, in registration order).
+ *                            Unbound cells in an nvcc translation unit fall back to the generic
+ *                            device path of b200generic.h (their own update() as a kernel).
  *   B200Grid<CELL>           a GridBase<CELL, DIM> (storage/gridbase.h:71-309) backed by the
  *                            device-resident SoA grid of libb200geo.so — what Initializers, Writers
  *                            and Steerers are handed; plays the role of CUDASoAGrid
@@ -56,6 +58,10 @@ struct B200KernelBinding;      /* specialise with B200GEO_BIND_CELL */
     namespace LibGeoDecomp {                                                            \
     template<> struct B200KernelBinding<CELL> {                                         \
         static int kernel() { return KERNEL_ID; }                                       \
+        static void step(b200geo_grid *g, const int32_t *, unsigned first, unsigned n)  \
+        {                                                                               \
+            B200Helpers::check(b200geo_step(g, KERNEL_ID, 0, first, n, 0));             \
+        }                                                                               \
         static std::vector<B200Member> members()                                        \
         {                                                                               \
             B200Member tab[] = { __VA_ARGS__ };                                         \
@@ -98,6 +104,12 @@ inline void toStreak4(const Streak<DIM>& s, const Coord<DIM>& origin, int32_t *o
 }
 
 }
+
+/* nvcc translation units: cells without a B200GEO_BIND_CELL line take the generic device path
+ * (the user's own update() compiled into a kernel); with a host compiler unbound cells do not compile */
+#ifdef __CUDACC__
+#include "b200generic.h"
+#endif
 
 #include "b200boxgrid.h"
 
@@ -258,7 +270,11 @@ public:
     /* the hot path: n sweeps + swaps on the device (SerialSimulator::nanoStep, serialsimulator.h:132-139) */
     void update(unsigned firstNanoStep, unsigned sweeps)
     {
-        B200Helpers::check(b200geo_step(handle, B200KernelBinding<CELL>::kernel(), 0, firstNanoStep, sweeps, 0));
+        int32_t dim[3] = {1, 1, 1};
+        for (int i = 0; i < DIM; ++i) {
+            dim[i] = box.dimensions[i];
+        }
+        B200KernelBinding<CELL>::step(handle, dim, firstNanoStep, sweeps);
     }
 
     void sync() const

@@ -2,4 +2,7 @@
 #ifndef LIBFLATARRAY_CONFIG_H
 #define LIBFLATARRAY_CONFIG_H
 #define LIBFLATARRAY_WITH_CPP14 true
+#ifdef __CUDACC__
+#define LIBFLATARRAY_WITH_CUDA true
+#endif
 #endif

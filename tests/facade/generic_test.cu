@@ -1,0 +1,384 @@
+/* Drop-in test of the GENERIC device path (include/libgeodecomp_b200/b200generic.h): user cells WITHOUT
+ * a B200GEO_BIND_CELL line, their own update() / updateLineX() compiled by nvcc into sm_100a kernels.
+ *
+ *  1. the reference's own CUDA-simulator suite (parallelization/test/unit/cudasimulatortest.h:13-26,
+ *     60-140): TestCell in 1-D/2-D/3-D on Cube and Torus topologies, initialised by the reference's
+ *     TestInitializer, checked after EVERY step with the logic of TestWriter / TS_ASSERT_TEST_GRID
+ *     (io/testwriter.h:39-62, misc/testhelper.h:99-141) and cell by cell against SerialSimulator;
+ *  2. a Game-of-Life cell written like src/examples/gameoflife/main.cpp:25-62 (run-time Coord<2>
+ *     neighbour access — not supported by the reference's CUDA path);
+ *  3. a two-member heat cell that leaves one member unassigned (sees the new grid's stale value, like
+ *     VanillaUpdateFunctor's `gridNew[c].update(...)`);
+ *  4. an AoS-signature updateLineX model with NANO_STEPS = 2 on a Torus<3>.
+ * Every case runs the reference's SerialSimulator beside B200Simulator in this process and requires
+ * bit-identical grids. Compiled HERE (tests/facade/Makefile), run on the GPU box by tests/test_facade_gpu.py. */
+#include <cuda.h>
+
+#include <libgeodecomp/io/simpleinitializer.h>
+#include <libgeodecomp/io/testinitializer.h>
+#include <libgeodecomp/misc/clonable.h>
+#include <libgeodecomp/misc/testcell.h>
+#include <libgeodecomp/parallelization/serialsimulator.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <iostream>
+
+#include <libgeodecomp_b200/b200simulator.h>
+
+using namespace LibGeoDecomp;
+
+static int failures = 0;
+#define CHECK(COND)                                                                     \
+    do {                                                                                \
+        if (!(COND)) {                                                                  \
+            ++failures;                                                                 \
+            std::printf("FAILED %s:%d: %s\n", __FILE__, __LINE__, #COND);              \
+        }                                                                               \
+    } while (0)
+
+typedef TestCell<1, Stencils::VonNeumann<1, 1>, Topologies::Cube<1>::Topology,
+                 TestCellHelpers::EmptyAPI, TestCellHelpers::NoOutput> TestCell1dCube;
+typedef TestCell<1, Stencils::Moore<1, 1>, Topologies::Torus<1>::Topology,
+                 TestCellHelpers::EmptyAPI, TestCellHelpers::NoOutput> TestCell1dTorus;
+typedef TestCell<2, Stencils::VonNeumann<2, 1>, Topologies::Cube<2>::Topology,
+                 TestCellHelpers::EmptyAPI, TestCellHelpers::NoOutput> TestCell2dCube;
+typedef TestCell<2, Stencils::Moore<2, 1>, Topologies::Torus<2>::Topology,
+                 TestCellHelpers::EmptyAPI, TestCellHelpers::NoOutput> TestCell2dTorus;
+typedef TestCell<3, Stencils::VonNeumann<3, 1>, Topologies::Cube<3>::Topology,
+                 TestCellHelpers::EmptyAPI, TestCellHelpers::NoOutput> TestCell3dCube;
+typedef TestCell<3, Stencils::Moore<3, 1>, Topologies::Torus<3>::Topology,
+                 TestCellHelpers::EmptyAPI, TestCellHelpers::NoOutput> TestCell3dTorus;
+typedef TestCell<3, Stencils::Moore<3, 1>, Topologies::Cube<3>::Topology,
+                 TestCellHelpers::EmptyAPI, TestCellHelpers::NoOutput> TestCell3dMooreCube;
+
+/* TestWriter's checks (io/testwriter.h:39-62) without the cxxtest runner: the expected (step, event)
+ * sequence, and TS_ASSERT_TEST_GRID on every call */
+template<typename CELL>
+class CheckingWriter : public Clonable<Writer<CELL>, CheckingWriter<CELL> >
+{
+public:
+    typedef typename Writer<CELL>::GridType GridType;
+    static const int DIM = GridType::DIM;
+    using Writer<CELL>::NANO_STEPS;
+
+    CheckingWriter(int period, int firstStep, int lastStep, long *badCells, long *badEvents) :
+        Clonable<Writer<CELL>, CheckingWriter<CELL> >("", period),
+        badCells(badCells),
+        badEvents(badEvents)
+    {
+        expectedSteps.push_back(firstStep);
+        expectedEvents.push_back(WRITER_INITIALIZED);
+        for (int i = firstStep + period - firstStep % period; i < lastStep; i += period) {
+            expectedSteps.push_back(i);
+            expectedEvents.push_back(WRITER_STEP_FINISHED);
+        }
+        expectedSteps.push_back(lastStep);
+        expectedEvents.push_back(WRITER_ALL_DONE);
+    }
+
+    virtual void stepFinished(const GridType& grid, unsigned step, WriterEvent event)
+    {
+        if (expectedSteps.empty() || expectedSteps.front() != (int)step || expectedEvents.front() != event) {
+            ++*badEvents;
+        }
+        if (!expectedSteps.empty()) {
+            expectedSteps.erase(expectedSteps.begin());
+            expectedEvents.erase(expectedEvents.begin());
+        }
+        unsigned expectedCycle = NANO_STEPS * step;
+        if (!grid.getEdge().edgeCell() || !grid.getEdge().valid()) {
+            ++*badCells;
+        }
+        CoordBox<DIM> box = grid.boundingBox();
+        std::vector<CELL> row(box.dimensions.x());
+        for (typename CoordBox<DIM>::StreakIterator i = box.beginStreak(); i != box.endStreak(); ++i) {
+            grid.get(*i, row.data());
+            for (std::size_t x = 0; x < row.size(); ++x) {
+                if (!row[x].valid() || row[x].edgeCell() || row[x].cycleCounter != expectedCycle) {
+                    ++*badCells;
+                }
+            }
+        }
+    }
+
+    bool allEventsDone() const
+    {
+        return expectedSteps.empty() && expectedEvents.empty();
+    }
+
+private:
+    std::vector<int> expectedSteps;
+    std::vector<WriterEvent> expectedEvents;
+    long *badCells;
+    long *badEvents;
+};
+
+template<typename CELL, int DIM>
+static long differingCells(const GridBase<CELL, DIM> *a, const GridBase<CELL, DIM> *b)
+{
+    long bad = 0;
+    CoordBox<DIM> box = a->boundingBox();
+    if (!(box == b->boundingBox())) {
+        return -1;
+    }
+    std::vector<CELL> ra(box.dimensions.x()), rb(box.dimensions.x());
+    for (typename CoordBox<DIM>::StreakIterator i = box.beginStreak(); i != box.endStreak(); ++i) {
+        a->get(*i, ra.data());
+        b->get(*i, rb.data());
+        for (std::size_t x = 0; x < ra.size(); ++x) {
+            if (!(ra[x] == rb[x])) {
+                ++bad;
+            }
+        }
+    }
+    return bad;
+}
+
+/* the cases of CUDASimulatorTest::test{1,2,3}d{Cube,Torus} */
+template<typename CELL, int DIM>
+static void testCellSuite(const char *name, const Coord<DIM>& dim, int steps)
+{
+    long badCells = 0, badEvents = 0;
+    B200Simulator<CELL> sim(new TestInitializer<CELL>(dim, steps));
+    CheckingWriter<CELL> *writer = new CheckingWriter<CELL>(1, 0, steps, &badCells, &badEvents);
+    sim.addWriter(writer);
+    sim.run();
+    CHECK(writer->allEventsDone());
+    CHECK(badCells == 0);
+    CHECK(badEvents == 0);
+    CHECK((int)sim.getStep() == steps);
+
+    SerialSimulator<CELL> ref(new TestInitializer<CELL>(dim, steps));
+    ref.run();
+    long bad = differingCells<CELL, DIM>(ref.getGrid(), sim.getGrid());
+    CHECK(bad == 0);
+    std::printf("%-22s %d steps x %u nano steps: %ld invalid cells, %ld cells differing from SerialSimulator, events %s\n",
+                name, steps, (unsigned)CELL::NANO_STEPS, badCells, bad, badEvents == 0 && writer->allEventsDone() ? "ok" : "WRONG");
+}
+
+static uint64_t splitmix(uint64_t x)
+{
+    uint64_t z = x + 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+static double uniform(uint64_t i)
+{
+    return (double)(splitmix(i) >> 11) * (1.0 / 9007199254740992.0);
+}
+
+/* Game of Life as a user would write it (src/examples/gameoflife/main.cpp:25-62): default API
+ * (Cube<2>, Moore<2,1>), neighbours through run-time Coord<2> */
+class LifeCell
+{
+public:
+    class API : public APITraits::HasStencil<Stencils::Moore<2, 1> >
+    {};
+
+    __host__ __device__
+    explicit LifeCell(bool alive = false) : alive(alive)
+    {}
+
+    __host__ __device__
+    int countLivingNeighbors(const LifeCell& c) const
+    {
+        return c.alive ? 1 : 0;
+    }
+
+    template<typename COORD_MAP>
+    __host__ __device__
+    void update(const COORD_MAP& neighborhood, unsigned)
+    {
+        int livingNeighbors = 0;
+        for (int y = -1; y <= 1; ++y) {
+            for (int x = -1; x <= 1; ++x) {
+                livingNeighbors += countLivingNeighbors(neighborhood[Coord<2>(x, y)]);
+            }
+        }
+        const LifeCell old = neighborhood[Coord<2>(0, 0)];
+        livingNeighbors -= old.alive ? 1 : 0;
+        alive = old.alive ? (livingNeighbors >= 2 && livingNeighbors <= 3) : (livingNeighbors == 3);
+    }
+
+    bool operator==(const LifeCell& o) const
+    {
+        return alive == o.alive;
+    }
+
+    bool alive;
+};
+
+/* two members of different type; `hits` is assigned only where the cell is hot, otherwise the new
+ * grid's stale value stays (deliberately order dependent: must match the CPU's double buffering) */
+class HeatCell
+{
+public:
+    class API :
+        public APITraits::HasStencil<Stencils::VonNeumann<2, 1> >,
+        public APITraits::HasTorusTopology<2>
+    {};
+
+    __host__ __device__
+    explicit HeatCell(double temp = 0, long long hits = 0) : temp(temp), hits(hits)
+    {}
+
+    template<typename HOOD>
+    __host__ __device__
+    void update(const HOOD& hood, unsigned nanoStep)
+    {
+        double sum = hood[FixedCoord< 0, -1>()].temp + hood[FixedCoord<-1, 0>()].temp + hood[FixedCoord<0, 0>()].temp +
+            hood[FixedCoord< 1, 0>()].temp + hood[FixedCoord< 0, 1>()].temp;
+        temp = sum * 0.2;
+        if (temp > 0.55) {
+            hits = hood[FixedCoord<0, 0>()].hits + 1 + nanoStep;
+        }
+    }
+
+    bool operator==(const HeatCell& o) const
+    {
+        return std::memcmp(&temp, &o.temp, sizeof(temp)) == 0 && hits == o.hits;
+    }
+
+    double temp;
+    long long hits;
+};
+
+/* AoS line signature (src/examples/jacobi3dupdateline/main.cpp:32-42 style), two nano steps that use
+ * different formulas, Torus<3>, float members */
+class WaveCell
+{
+public:
+    class API :
+        public APITraits::HasFixedCoordsOnlyUpdate,
+        public APITraits::HasUpdateLineX,
+        public APITraits::HasStencil<Stencils::VonNeumann<3, 1> >,
+        public APITraits::HasTorusTopology<3>,
+        public APITraits::HasNanoSteps<2>
+    {};
+
+    __host__ __device__
+    explicit WaveCell(float u = 0, float v = 0) : u(u), v(v)
+    {}
+
+    template<typename HOOD>
+    __host__ __device__
+    static void updateLineX(WaveCell *target, long *x, long endX, const HOOD& hood, unsigned nanoStep)
+    {
+        for (; *x < endX; ++*x) {
+            const WaveCell c = hood[FixedCoord<0, 0, 0>()];
+            if (nanoStep == 0) {
+                float lap = hood[FixedCoord<0, 0, -1>()].u + hood[FixedCoord<0, -1, 0>()].u + hood[FixedCoord<-1, 0, 0>()].u +
+                    hood[FixedCoord<1, 0, 0>()].u + hood[FixedCoord<0, 1, 0>()].u + hood[FixedCoord<0, 0, 1>()].u;
+                target[*x].v = c.v + 0.1f * (lap - 6.0f * c.u);
+                target[*x].u = c.u;
+            } else {
+                target[*x].u = c.u + 0.5f * c.v;
+                target[*x].v = c.v;
+            }
+        }
+    }
+
+    bool operator==(const WaveCell& o) const
+    {
+        return std::memcmp(this, &o, sizeof(*this)) == 0;
+    }
+
+    float u, v;
+};
+
+template<typename CELL> struct Seed;
+template<> struct Seed<LifeCell> {
+    static LifeCell make(uint64_t i) { return LifeCell(uniform(i) < 0.35); }
+    static LifeCell edge() { return LifeCell(false); }
+};
+template<> struct Seed<HeatCell> {
+    static HeatCell make(uint64_t i) { return HeatCell(uniform(i), (long long)(i % 7)); }
+    static HeatCell edge() { return HeatCell(0.5, -1); }
+};
+template<> struct Seed<WaveCell> {
+    static WaveCell make(uint64_t i) { return WaveCell((float)uniform(2 * i), (float)(uniform(2 * i + 1) - 0.5)); }
+    static WaveCell edge() { return WaveCell(0, 0); }
+};
+
+template<typename CELL>
+class SeededInitializer : public SimpleInitializer<CELL>
+{
+public:
+    typedef typename SimpleInitializer<CELL>::Topology Topology;
+    static const int DIM = Topology::DIM;
+    using SimpleInitializer<CELL>::gridDimensions;
+
+    SeededInitializer(const Coord<DIM>& dim, unsigned steps) : SimpleInitializer<CELL>(dim, steps) {}
+
+    virtual void grid(GridBase<CELL, DIM> *ret)
+    {
+        CoordBox<DIM> box = ret->boundingBox();
+        ret->setEdge(Seed<CELL>::edge());
+        std::vector<CELL> row(box.dimensions.x());
+        for (typename CoordBox<DIM>::StreakIterator i = box.beginStreak(); i != box.endStreak(); ++i) {
+            Coord<DIM> c = i->origin;
+            for (std::size_t x = 0; x < row.size(); ++x, ++c.x()) {
+                row[x] = Seed<CELL>::make(c.toIndex(gridDimensions()));
+            }
+            ret->set(*i, row.data());
+        }
+    }
+};
+
+template<typename CELL, int DIM>
+static void compareWithSerialSimulator(const char *name, const Coord<DIM>& dim, unsigned steps)
+{
+    SerialSimulator<CELL> ref(new SeededInitializer<CELL>(dim, steps));
+    B200Simulator<CELL> sim(new SeededInitializer<CELL>(dim, steps));
+    ref.run();
+    sim.run();
+    CHECK(ref.getStep() == steps);
+    CHECK(sim.getStep() == steps);
+    CHECK(ref.getGrid()->getEdge() == sim.getGrid()->getEdge());
+    long bad = differingCells<CELL, DIM>(ref.getGrid(), sim.getGrid());
+    CHECK(bad == 0);
+    std::printf("%-22s %s: %ld differing cells after %u steps\n", name, bad ? "MISMATCH" : "bit-exact", bad, steps);
+
+    // one step() at a time gives the same grid as run()
+    B200Simulator<CELL> single(new SeededInitializer<CELL>(dim, steps));
+    for (unsigned i = 0; i < steps; ++i) {
+        single.step();
+    }
+    CHECK(single.getStep() == steps);
+    CHECK((differingCells<CELL, DIM>(ref.getGrid(), single.getGrid()) == 0));
+}
+
+int main()
+{
+    try {
+        CHECK(B200KernelBinding<LifeCell>::kernel() == B200GEO_KERNEL_GENERIC);
+        CHECK(B200Generic::Words<LifeCell>::N == 1 && B200Generic::Words<LifeCell>::W == 1);
+        CHECK(B200Generic::Words<HeatCell>::N == 2 && B200Generic::Words<HeatCell>::W == 8);
+        CHECK(B200Generic::Words<TestCell3dCube>::W == 4);
+
+        testCellSuite<TestCell1dCube, 1>("TestCell 1d Cube", Coord<1>(777), 33);
+        testCellSuite<TestCell1dTorus, 1>("TestCell 1d Torus", Coord<1>(666), 33);
+        testCellSuite<TestCell2dCube, 2>("TestCell 2d Cube", Coord<2>(64, 32), 33);
+        testCellSuite<TestCell2dTorus, 2>("TestCell 2d Torus", Coord<2>(123, 77), 15);
+        testCellSuite<TestCell3dCube, 3>("TestCell 3d Cube", Coord<3>(50, 20, 10), 5);
+        testCellSuite<TestCell3dTorus, 3>("TestCell 3d Torus", Coord<3>(30, 20, 10), 5);
+        testCellSuite<TestCell3dMooreCube, 3>("TestCell 3d Moore Cube", Coord<3>(13, 12, 11), 4);
+
+        compareWithSerialSimulator<LifeCell, 2>("LifeCell (Coord<2>)", Coord<2>(150, 67), 30);
+        compareWithSerialSimulator<HeatCell, 2>("HeatCell (stale member)", Coord<2>(97, 41), 23);
+        compareWithSerialSimulator<WaveCell, 3>("WaveCell (updateLineX)", Coord<3>(40, 9, 7), 12);
+    } catch (const std::exception& e) {
+        std::printf("FAILED with exception: %s\n", e.what());
+        return 2;
+    }
+    if (failures) {
+        std::printf("%d check(s) FAILED\n", failures);
+        return 1;
+    }
+    std::printf("generic_test: all checks passed\n");
+    return 0;
+}
