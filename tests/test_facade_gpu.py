@@ -21,6 +21,23 @@ def test_cpp_facade_drop_in():
     assert "all checks passed" in res.stdout
 
 
+GENERIC_BIN = os.path.join(HERE, "facade", "_bin", "generic_test")
+
+
+@pytest.mark.gpu
+def test_generic_device_path_for_unbound_cells():
+    """tests/facade/generic_test.cu: user cells without a kernel binding (the reference's TestCell suite of
+    cudasimulatortest.h, a Coord<2>-addressed Game of Life, a partially assigned cell, an AoS updateLineX
+    model), their own update() compiled by nvcc, bit-identical to SerialSimulator."""
+    if not os.access(GENERIC_BIN, os.X_OK):
+        pytest.skip("tests/facade/_bin/generic_test not built (needs /root/reference at build time)")
+    res = subprocess.run([GENERIC_BIN], capture_output=True, text=True, timeout=600)
+    print(res.stdout[-4000:], res.stderr[-2000:])
+    assert res.returncode == 0, res.stdout[-4000:] + res.stderr[-2000:]
+    assert "all checks passed" in res.stdout
+
+
 def test_facade_header_has_no_oracle_dependency():
-    text = open(os.path.join(HERE, "..", "include", "libgeodecomp_b200", "b200simulator.h")).read()
-    assert "oracle" not in text
+    for name in ("b200simulator.h", "b200generic.h", "b200boxgrid.h"):
+        text = open(os.path.join(HERE, "..", "include", "libgeodecomp_b200", name)).read()
+        assert "oracle" not in text
