@@ -9,7 +9,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import torch
 
-from libgeodecomp_b200 import capi, models
+from libgeodecomp_b200 import capi, models, synth
 from libgeodecomp_b200.simulator import B200Grid
 
 SPEC = {"jacobi27": (models.Jacobi27Cube, (1024, 1024, 1024), 16), "jacobi7": (models.Jacobi7Cube, (1024, 1024, 1024), 16),
@@ -26,7 +26,10 @@ def main():
         a = (np.random.default_rng(0).random((dims[1], dims[0])) < 0.35).astype(np.uint8)
         grid.loadMember("alive", a)
     elif wl == "lbm":
+        # lid-driven cavity: fluid at rest inside the six walls of the reference example
         grid.loadMember("C", np.ones(dims[::-1], dtype=np.float32))
+        grid.loadMember("density", np.ones(dims[::-1], dtype=np.float32))
+        grid.loadMember("state", synth.lbm_states(dims[0], dims[1], dims[2], 0, dims[2]))
     else:
         grid.loadMember("temp", np.random.default_rng(0).random(dims[::-1]))
     cells = float(np.prod(dims))
