@@ -173,6 +173,30 @@ int b200geo_halo_push(b200geo_grid *g, int side, int width, void *stream);
  * (called after an exchange done by the caller, e.g. NCCL send/recv into b200geo_halo_block). */
 int b200geo_halo_mark_valid(b200geo_grid *g, int side, int width);
 
+/* ---- slab groups: one host thread, several GPUs of one box -------------------------------------
+ * The slabs of ONE simulation space (b200geo_grid handles on different devices, in slab order along
+ * the last axis; faces towards a neighbour are PEER ghost layers of equal width w) stepped together.
+ * Replaces StripingSimulator::nanoStep (parallelization/stripingsimulator.h:269-286: rims first, ship
+ * them, interior while they travel) and the PatchLink pair (communication/patchlink.h:127-151,218-244:
+ * MPI_Isend/Irecv of packed regions) by direct NVLink copies of the contiguous rim planes into the
+ * neighbours' ghost planes; one exchange per w sweeps (ghost zone width of
+ * parallelization/nesting/vanillastepper.h:157-225), the w sweeps of a round fused into one launch
+ * where the kernel family can (Jacobi). Called by B200StripingSimulator<CELL>
+ * (include/libgeodecomp_b200/b200stripingsimulator.h). Does not own the grids. */
+typedef struct b200geo_group b200geo_group;
+int b200geo_group_create(b200geo_grid *const *grids, int n, int periodic, b200geo_group **out);
+int b200geo_group_destroy(b200geo_group *grp);
+/* the caller wrote cells (Initializer / Steerer): ghost planes are stale, exchange before stepping */
+int b200geo_group_invalidate(b200geo_group *grp);
+/* fill the w ghost planes of every PEER side of the current buffers now (whole cells) */
+int b200geo_group_exchange(b200geo_group *grp);
+/* n_steps x { UpdateFunctor over every slab; swap } with the exchanges they need; results are
+ * bit-identical to b200geo_step on one grid holding the whole space */
+int b200geo_group_step(b200geo_group *grp, int kernel, const void *params, uint32_t first_nano_step, uint32_t n_steps);
+int b200geo_group_sync(b200geo_group *grp);
+/* out[0] = exchanges so far, out[1] = bytes shipped between devices */
+int b200geo_group_stats(const b200geo_group *grp, uint64_t out[2]);
+
 /* ---- BoxCell container grids: short-range n-body (B200GEO_KERNEL_NBODY) -------------------------
  * Replaces Grid<BoxCell<FixedArray<Particle, N> > > (storage/boxcell.h:21-178, storage/fixedarray.h:21-140)
  * and, on the step path, BoxCell::update with its re-binning (boxcell.h:112-174), the position checker

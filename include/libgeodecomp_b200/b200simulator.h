@@ -144,13 +144,28 @@ public:
         edgeCell(edgeCell),
         device(device),
         handle(0),
-        members(B200KernelBinding<CELL>::members())
+        members(B200KernelBinding<CELL>::members()),
+        slabGhost(0),
+        lowPeer(false),
+        highPeer(false)
     {
-        cellBytes = 0;
-        for (std::size_t m = 0; m < members.size(); ++m) {
-            cellBytes += members[m].bytes;
-        }
-        create();
+        init();
+    }
+
+    /* one slab of a larger simulation space (B200StripingSimulator): `slabGhost` ghost layers along the
+     * last axis; a face towards a neighbouring slab holds that neighbour's cells (PEER) */
+    B200Grid(const CoordBox<DIM>& box, const CELL& edgeCell, int device, int slabGhost, bool lowPeer, bool highPeer) :
+        Base(box.dimensions),
+        box(box),
+        edgeCell(edgeCell),
+        device(device),
+        handle(0),
+        members(B200KernelBinding<CELL>::members()),
+        slabGhost(slabGhost),
+        lowPeer(lowPeer),
+        highPeer(highPeer)
+    {
+        init();
     }
 
     virtual ~B200Grid()
@@ -282,6 +297,32 @@ public:
         B200Helpers::check(b200geo_sync(0));
     }
 
+    int bytesPerCell() const
+    {
+        return cellBytes;
+    }
+
+    /* Selector I/O for a streak list (what GridBase::saveMember / loadMember end up calling) */
+    void saveMemberStreaks(
+        char *target,
+        MemoryLocation::Location targetLocation,
+        const Selector<CELL>& selector,
+        const typename Region<DIM>::StreakIterator& begin,
+        const typename Region<DIM>::StreakIterator& end) const
+    {
+        saveMemberImplementation(target, targetLocation, selector, begin, end);
+    }
+
+    void loadMemberStreaks(
+        const char *source,
+        MemoryLocation::Location sourceLocation,
+        const Selector<CELL>& selector,
+        const typename Region<DIM>::StreakIterator& begin,
+        const typename Region<DIM>::StreakIterator& end)
+    {
+        loadMemberImplementation(source, sourceLocation, selector, begin, end);
+    }
+
 protected:
     virtual void saveMemberImplementation(
         char *target,
@@ -349,6 +390,18 @@ private:
     b200geo_grid *handle;
     std::vector<B200Member> members;
     int cellBytes;
+    int slabGhost;
+    bool lowPeer;
+    bool highPeer;
+
+    void init()
+    {
+        cellBytes = 0;
+        for (std::size_t m = 0; m < members.size(); ++m) {
+            cellBytes += members[m].bytes;
+        }
+        create();
+    }
 
     void create()
     {
@@ -366,6 +419,13 @@ private:
             bool jacobi = k == B200GEO_KERNEL_JACOBI6 || k == B200GEO_KERNEL_JACOBI7 || k == B200GEO_KERNEL_JACOBI27;
             if (jacobi && mode == B200GEO_GHOST_WRAP) {
                 desc.ghost[i] = std::max(desc.ghost[i], std::min(4, desc.dim[i]));
+            }
+            if (i == DIM - 1 && slabGhost > 0) {
+                // a slab: the faces towards its neighbours are filled by the halo exchange; an outer face
+                // of a Torus slab is PEER as well (ring closure), so only Cube slabs keep EDGE here
+                desc.ghost[i] = slabGhost;
+                desc.ghost_mode[i][0] = lowPeer ? B200GEO_GHOST_PEER : B200GEO_GHOST_EDGE;
+                desc.ghost_mode[i][1] = highPeer ? B200GEO_GHOST_PEER : B200GEO_GHOST_EDGE;
             }
         }
         if (members.size() > B200GEO_MAX_MEMBERS) {

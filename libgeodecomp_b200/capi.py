@@ -83,6 +83,13 @@ SYMBOLS = [
     ("b200geo_grid_ipc_open", ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, _vp]),
     ("b200geo_halo_push", ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, _vp]),
     ("b200geo_halo_mark_valid", ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int]),
+    ("b200geo_group_create", ctypes.c_int, [ctypes.POINTER(_vp), ctypes.c_int, ctypes.c_int, ctypes.POINTER(_vp)]),
+    ("b200geo_group_destroy", ctypes.c_int, [_vp]),
+    ("b200geo_group_invalidate", ctypes.c_int, [_vp]),
+    ("b200geo_group_exchange", ctypes.c_int, [_vp]),
+    ("b200geo_group_step", ctypes.c_int, [_vp, ctypes.c_int, _vp, ctypes.c_uint32, ctypes.c_uint32]),
+    ("b200geo_group_sync", ctypes.c_int, [_vp]),
+    ("b200geo_group_stats", ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_uint64)]),
     ("b200geo_boxgrid_create", ctypes.c_int, [ctypes.POINTER(BoxGridDesc), ctypes.c_int, ctypes.POINTER(_vp)]),
     ("b200geo_boxgrid_destroy", ctypes.c_int, [_vp]),
     ("b200geo_boxgrid_load", ctypes.c_int, [_vp, _i32p, _i32p, _vp, _vp, ctypes.c_int, ctypes.c_int, _vp]),
@@ -288,6 +295,47 @@ class DeviceGrid:
         out = (ctypes.c_double * 3)()
         check(lib().b200geo_stats(self._h, out))
         return {"update_s": out[0], "ghost_s": out[1], "sweeps": int(out[2])}
+
+
+class SlabGroup:
+    """b200geo_group: the slabs of one simulation space on several GPUs of this box, driven by one
+    host thread (rim-first schedule, direct NVLink copies between neighbouring slabs)."""
+
+    def __init__(self, grids, periodic=False):
+        self._h = None
+        self.grids = list(grids)
+        arr = (ctypes.c_void_p * len(self.grids))(*[g._h for g in self.grids])
+        h = ctypes.c_void_p()
+        check(lib().b200geo_group_create(arr, len(self.grids), 1 if periodic else 0, ctypes.byref(h)))
+        self._h = h
+
+    def close(self):
+        if self._h is not None and _lib is not None:
+            _lib.b200geo_group_destroy(self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def invalidate(self):
+        check(lib().b200geo_group_invalidate(self._h))
+
+    def exchange(self):
+        check(lib().b200geo_group_exchange(self._h))
+
+    def step(self, kernel, n_steps=1, first_nano_step=0, params=None):
+        check(lib().b200geo_group_step(self._h, kernel, _ptr(params), first_nano_step, n_steps))
+
+    def sync(self):
+        check(lib().b200geo_group_sync(self._h))
+
+    def stats(self):
+        out = (ctypes.c_uint64 * 2)()
+        check(lib().b200geo_group_stats(self._h, out))
+        return {"exchanges": int(out[0]), "bytes": int(out[1])}
 
 
 class DeviceBoxGrid:

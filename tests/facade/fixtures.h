@@ -1,0 +1,122 @@
+/* Shared fixtures of the façade drop-in tests (facade_test.cpp, striping_test.cpp): the user models of
+ * oracle/models/*.h with their kernel bindings, seeded Initializers written against the reference's
+ * SimpleInitializer, and the CHECK macro. */
+#ifndef B200GEO_TESTS_FACADE_FIXTURES_H
+#define B200GEO_TESTS_FACADE_FIXTURES_H
+
+#include <libgeodecomp/misc/testcell.h>
+#include <libgeodecomp/io/mocksteerer.h>
+#include <libgeodecomp/io/mockwriter.h>
+#include <libgeodecomp/io/simpleinitializer.h>
+#include <libgeodecomp/parallelization/serialsimulator.h>
+#include <libgeodecomp/storage/soagrid.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <iostream>
+
+#include "bindings.h"
+
+using namespace LibGeoDecomp;
+using namespace b200models;
+
+static int failures = 0;
+#define CHECK(COND)                                                                     \
+    do {                                                                                \
+        if (!(COND)) {                                                                  \
+            ++failures;                                                                 \
+            std::printf("FAILED %s:%d: %s\n", __FILE__, __LINE__, #COND);              \
+        }                                                                               \
+    } while (0)
+
+static uint64_t splitmix(uint64_t x)
+{
+    uint64_t z = x + 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+static double uniform(uint64_t i)
+{
+    return (double)(splitmix(i) >> 11) * (1.0 / 9007199254740992.0);
+}
+
+template<typename CELL> struct Seed;
+template<typename CELL> struct SeedJacobi {
+    static CELL make(uint64_t i) { return CELL(uniform(i)); }
+    static CELL edge() { return CELL(0.25); }
+};
+template<> struct Seed<Jacobi6Cube> : SeedJacobi<Jacobi6Cube> {};
+template<> struct Seed<Jacobi6Torus> : SeedJacobi<Jacobi6Torus> {};
+template<> struct Seed<Jacobi7Cube> : SeedJacobi<Jacobi7Cube> {};
+template<> struct Seed<Jacobi7Torus> : SeedJacobi<Jacobi7Torus> {};
+template<> struct Seed<Jacobi27Cube> : SeedJacobi<Jacobi27Cube> {};
+template<> struct Seed<Jacobi27Torus> : SeedJacobi<Jacobi27Torus> {};
+template<> struct Seed<ConwayCube> {
+    static ConwayCube make(uint64_t i) { return ConwayCube(uniform(i) < 0.35); }
+    static ConwayCube edge() { return ConwayCube(false); }
+};
+template<> struct Seed<ConwayTorus> {
+    static ConwayTorus make(uint64_t i) { return ConwayTorus(uniform(i) < 0.35); }
+    static ConwayTorus edge() { return ConwayTorus(false); }
+};
+
+template<typename CELL>
+class SeededInitializer : public SimpleInitializer<CELL>
+{
+public:
+    typedef typename SimpleInitializer<CELL>::Topology Topology;
+    static const int DIM = Topology::DIM;
+    using SimpleInitializer<CELL>::gridDimensions;
+
+    SeededInitializer(const Coord<DIM>& dim, unsigned steps) : SimpleInitializer<CELL>(dim, steps) {}
+
+    virtual void grid(GridBase<CELL, DIM> *ret)
+    {
+        CoordBox<DIM> box = ret->boundingBox();
+        ret->setEdge(Seed<CELL>::edge());
+        for (typename CoordBox<DIM>::Iterator i = box.begin(); i != box.end(); ++i) {
+            ret->set(*i, Seed<CELL>::make(i->toIndex(gridDimensions())));
+        }
+    }
+};
+
+class LBMInitializer : public SimpleInitializer<LBMCellF>
+{
+public:
+    LBMInitializer(const Coord<3>& dim, unsigned steps) : SimpleInitializer<LBMCellF>(dim, steps) {}
+
+    /* walls as src/examples/latticeboltzmann/main.cpp:249-287, rows written with set(Streak, cells) */
+    virtual void grid(GridBase<LBMCellF, 3> *ret)
+    {
+        CoordBox<3> box = ret->boundingBox();
+        Coord<3> size = gridDimensions();
+        std::vector<LBMCellF> row(box.dimensions.x());
+        for (int z = box.origin.z(); z < box.origin.z() + box.dimensions.z(); ++z) {
+            for (int y = box.origin.y(); y < box.origin.y() + box.dimensions.y(); ++y) {
+                for (int x = 0; x < box.dimensions.x(); ++x) {
+                    int gx = box.origin.x() + x;
+                    int s = LBMCellF::LIQUID;
+                    if (gx == 0) s = LBMCellF::WEST_NOSLIP;
+                    if (gx == size.x() - 1) s = LBMCellF::EAST_NOSLIP;
+                    if (y == 0) s = LBMCellF::SOUTH_NOSLIP;
+                    if (y == size.y() - 1) s = LBMCellF::NORTH_ACC;
+                    if (z == 0) s = LBMCellF::BOTTOM;
+                    if (z == size.z() - 1) s = LBMCellF::TOP;
+                    LBMCellF c(1.0f, s);
+                    uint64_t i = Coord<3>(gx, y, z).toIndex(size);
+                    c.N = 0.01f * (float)uniform(3 * i);
+                    c.TE = 0.01f * (float)uniform(3 * i + 1);
+                    c.BS = 0.01f * (float)uniform(3 * i + 2);
+                    row[x] = c;
+                }
+                ret->set(Streak<3>(Coord<3>(box.origin.x(), y, z), box.origin.x() + box.dimensions.x()), row.data());
+            }
+        }
+    }
+};
+
+
+#endif

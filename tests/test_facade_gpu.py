@@ -37,7 +37,22 @@ def test_generic_device_path_for_unbound_cells():
     assert "all checks passed" in res.stdout
 
 
+STRIPING_BIN = os.path.join(HERE, "facade", "_bin", "striping_test")
+
+
+@pytest.mark.gpu
+def test_cpp_striping_simulator_drop_in():
+    """tests/facade/striping_test.cpp: B200StripingSimulator (one process, slabs round-robin over the GPUs
+    present, direct device-to-device halos) bit-identical to SerialSimulator for 1-4 slabs."""
+    if not os.access(STRIPING_BIN, os.X_OK):
+        pytest.skip("tests/facade/_bin/striping_test not built (needs /root/reference at build time)")
+    res = subprocess.run([STRIPING_BIN], capture_output=True, text=True, timeout=600)
+    print(res.stdout[-4000:], res.stderr[-2000:])
+    assert res.returncode == 0, res.stdout[-4000:] + res.stderr[-2000:]
+    assert "all checks passed" in res.stdout
+
+
 def test_facade_header_has_no_oracle_dependency():
-    for name in ("b200simulator.h", "b200generic.h", "b200boxgrid.h"):
+    for name in ("b200simulator.h", "b200generic.h", "b200boxgrid.h", "b200stripingsimulator.h"):
         text = open(os.path.join(HERE, "..", "include", "libgeodecomp_b200", name)).read()
         assert "oracle" not in text
