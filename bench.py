@@ -47,7 +47,7 @@ DESCRIPTION = {
 
 # temporal blocking depth per workload (b200geo_set_tuning "jacobi.tb"): sweeps fused into one launch of
 # the TMA-staged Jacobi kernel; with N > 1 the ghost zone must be that wide (one exchange per launch)
-TB_DEPTH = {"jacobi27": 2, "jacobi7": 2, "jacobi7_128": 1}
+TB_DEPTH = {"jacobi27": 2, "jacobi7": 4, "jacobi7_128": 1}
 
 
 def ncu_traffic(workload):

@@ -83,7 +83,7 @@ int b200geo_device_count(void);
 /* Launch / tiling parameters by name (the role misc/cudasimulationfactory.h:28-33 BlockDimX/Y/Z
  * play for the reference's CUDASimulator). Unknown keys -> B200GEO_ERR_INVALID. Keys:
  * "jacobi.zchunk", "jacobi.prefetch", "gol.rows", "lbm.block", "jacobi.tb" (sweeps fused per launch
- * by the temporal-blocked Jacobi kernels, 1..4), "jacobi.tb_rows" (tile shape), "jacobi.tb_zchunk", "gol.bits" (fewest sweeps per call that run
+ * by the temporal-blocked Jacobi kernels, 1..4; 0 = automatic: 2 for the 27-point kernel, 4 for 6/7-point), "jacobi.tb_rows" (tile shape), "jacobi.tb_zchunk", "gol.bits" (fewest sweeps per call that run
  * bit-packed; 0 = never), "gol.bits_rows", "nbody.kernel", "lbm.variant" (0 = wall test before the pulls, 1 = pulls hoisted
  * above the test, 2 = same with two rows per thread).
  * value < 0 restores the default. */

@@ -10,7 +10,7 @@
 
 namespace b200geo {
 
-static const Tuning g_tuning_default = {0, -1, 0, 128, 2, 33, 0, 4, 0, 3, 1};
+static const Tuning g_tuning_default = {0, -1, 0, 128, 0, 33, 0, 4, 0, 3, 1};
 Tuning g_tuning = g_tuning_default;
 static thread_local std::string g_last_error;
 static std::atomic<uint64_t> g_launches(0);
@@ -420,8 +420,11 @@ int b200geo_step(b200geo_grid *g, int kernel, const void *params, uint32_t first
         // HBM round trip when enough valid ghost cells are there (WRAP: ghost width, PEER: what the
         // last exchange delivered); everything else is one sweep per launch
         int depth = 1;
-        if (jacobi && g_tuning.jacobi_tb > 1) {
-            depth = g_tuning.jacobi_tb > 4 ? 4 : g_tuning.jacobi_tb;
+        // 0 = automatic (measured on B200, profiles/r1s_tuning.md): the 27-point kernel is fastest with two
+        // fused sweeps (deeper blocking runs out of registers), the 6/7-point kernels with four
+        const int tb = g_tuning.jacobi_tb != 0 ? g_tuning.jacobi_tb : (kernel == B200GEO_KERNEL_JACOBI27 ? 2 : 4);
+        if (jacobi && tb > 1) {
+            depth = tb > 4 ? 4 : tb;
             if ((uint32_t)depth > n_steps - t) depth = (int)(n_steps - t);
             for (int i = 0; i < 3; ++i)
                 for (int side = 0; side < 2; ++side) {

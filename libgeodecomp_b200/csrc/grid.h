@@ -66,7 +66,7 @@ struct Tuning {
     int jacobi_prefetch;  // L2 prefetch distance in planes (0 = off, < 0 = per-kernel default)
     int gol_rows;         // rows per CTA (0 = automatic)
     int lbm_block;        // threads per CTA
-    int jacobi_tb;        // temporal blocking depth of the Jacobi kernels (sweeps per launch; 0/1 = off)
+    int jacobi_tb;        // temporal blocking depth of the Jacobi kernels (sweeps per launch; 0 = automatic, 1 = off)
     int jacobi_tb_rows;   // tile shape of the temporal-blocked kernel: 32 (2 rows/thread), 64 or 33 (4 rows/thread)
     int jacobi_tb_zchunk; // planes per CTA along z of the temporal-blocked kernel (0 = automatic)
     int gol_bits;         // fewest sweeps per b200geo_step call for which Game of Life runs bit-packed (0 = never)

@@ -327,10 +327,11 @@ int launch_tb(b200geo_grid *g, const CUtensorMap& map, const Box& box, const Lim
     const MemberLayout& L = g->m[0];
     size_t smem = (size_t)NS * TY * TX * 8 + (size_t)NX * 2 * NW * 2 * TX * 8 + NS * 8;
     auto kernel = jacobi_tb_kernel<KIND, T, R, NW, NS, MINB>;
-    static bool attr_set = false;
-    if (!attr_set) {
+    // function attributes are per device: one process may drive several GPUs (slab groups)
+    static bool attr_set[64] = {false};
+    if (g->device < 0 || g->device >= 64 || !attr_set[g->device]) {
         B200GEO_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
+        if (g->device >= 0 && g->device < 64) attr_set[g->device] = true;
     }
     int xa = box.x0 & ~1;
     int gx = (box.x1 - xa + (TX - 2 * H) - 1) / (TX - 2 * H);

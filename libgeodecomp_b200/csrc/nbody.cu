@@ -490,10 +490,10 @@ int sweep(b200geo_boxgrid *g, const b200geo_nbody_params *p, int rebin, cudaStre
         count_launch();
         int runs = (D.nx + RUN - 1) / RUN;
         size_t smem = (size_t)(RUN + 2) * 9 * 3 * g->cap * sizeof(REAL) + ((RUN + 2) * 9 + RUN + 1) * sizeof(int);
-        static bool attr = false;
-        if (!attr) {
+        static bool attr[64] = {false};   // per device
+        if (!attr[g->device & 63]) {
             B200GEO_CUDA(cudaFuncSetAttribute(force_kernel<REAL, RUN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-            attr = true;
+            attr[g->device & 63] = true;
         }
         force_kernel<REAL, RUN><<<(unsigned)((int64_t)runs * D.ny * D.nz), 128, smem, s>>>(co, po, cn, pn, D, 0, runs, (REAL)p->dt, rc * rc);
     } else {
@@ -503,10 +503,10 @@ int sweep(b200geo_boxgrid *g, const b200geo_nbody_params *p, int rebin, cudaStre
         size_t smem = (size_t)NC * (3 * g->cap + 4) * sizeof(REAL) + (NC + G + 2) * sizeof(int) + 8 +
                       (size_t)(G * g->cap + 2) * sizeof(unsigned short) + (size_t)LMAX * NT * sizeof(unsigned short);
         if (smem > 227 * 1024) return fail(B200GEO_ERR_LOGIC, "container capacity too large for the fused kernel's shared memory");
-        static bool attr3 = false;
-        if (!attr3) {
+        static bool attr3[64] = {false};  // per device
+        if (!attr3[g->device & 63]) {
             B200GEO_CUDA(cudaFuncSetAttribute(fused_kernel<REAL, G, NT, LMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-            attr3 = true;
+            attr3[g->device & 63] = true;
         }
         // enlarged cutoff of the candidate filter
         REAL loose = rc * rc * (REAL)(1.0 + 1.0 / 65536.0);
