@@ -320,7 +320,7 @@ def bench_device(workload, args, rank, world, dist, torch, with_e2e=True, with_c
                 "traffic": traffic.get("dram_bytes_per_launch"), "traffic_source": traffic.get("source"),
                 "kernel_ms": kms, "sweeps_per_launch": per_launch, "updates_per_launch": cells_rank * per_launch,
                 "algorithmic_bytes_per_update": alg_bytes, "peak_source": peak_src, "kernel": model_name}
-    if roofline["traffic"] and abs(traffic.get("sweeps_per_launch", 1) - per_launch) < 1e-9:
+    if roofline["traffic"] and traffic.get("sweeps_per_launch") and abs(traffic["sweeps_per_launch"] - per_launch) < 1e-9:
         # what the DRAM actually moved per launch / launch time: the physical HBM fraction (<= 1);
         # with temporal blocking the ALGORITHMIC rate above may exceed the copy peak, this one cannot
         roofline["dram_frac"] = roofline["traffic"] / (1e-3 * kms) / 1e9 / peak
