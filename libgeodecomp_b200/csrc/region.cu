@@ -14,42 +14,50 @@
 
 namespace b200geo {
 
+// fill a box of one member array (padded coordinates) with a constant
 template<typename T>
-__global__ void fill_edge_kernel(T *base, int64_t pitch, int64_t plane, int lead,
-                                 int nx, int ny, int nz, int gx, int gy, int gz,
-                                 int ex0, int ex1, int ey0, int ey1, int ez0, int ez1, T value)
+__global__ void fill_box_kernel(T *base, int64_t pitch, int64_t plane, int x0, int y0, int z0, int w, int h, int d, T value)
 {
-    int x = blockIdx.x * blockDim.x + threadIdx.x - gx;
-    int y = blockIdx.y - gy;
-    int z = blockIdx.z - gz;
-    if (x >= nx + gx) return;
-    bool edge = (x < 0 && ex0) || (x >= nx && ex1) || (y < 0 && ey0) || (y >= ny && ey1) ||
-                (z < 0 && ez0) || (z >= nz && ez1);
-    if (edge) base[(int64_t)(z + gz) * plane + (int64_t)(y + gy) * pitch + lead + x] = value;
+    int64_t n = (int64_t)w * h * d;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        int x = (int)(i % w);
+        int64_t r = i / w;
+        int y = (int)(r % h), z = (int)(r / h);
+        base[(int64_t)(z0 + z) * plane + (int64_t)(y0 + y) * pitch + x0 + x] = value;
+    }
 }
 
+// Only the EDGE ghost layers are touched (work ~ surface, not volume): whole padded planes below / above
+// the grid, whole padded rows in front of / behind it in the remaining planes, the x ghost columns of the
+// interior rows.
 template<typename T>
 static void launch_fill_edge(b200geo_grid *g, int m, int which, cudaStream_t s)
 {
     const MemberLayout& L = g->m[m];
     T value;
     memcpy(&value, g->edge + L.edge_offset, sizeof(T));
-    int px = g->d[0] + 2 * g->g[0];
-    dim3 block(128), grid((px + 127) / 128, g->d[1] + 2 * g->g[1], g->d[2] + 2 * g->g[2]);
+    const int nx = g->d[0], ny = g->d[1], nz = g->d[2], gx = g->g[0], gy = g->g[1], gz = g->g[2];
+    const int px = nx + 2 * gx, py = ny + 2 * gy;
     const int (*mode)[2] = g->desc.ghost_mode;
-    // planes go to gridDim.z (<= 65535) and rows to gridDim.y (<= 65535)
-    fill_edge_kernel<T><<<grid, block, 0, s>>>(
-        (T *)g->member_ptr(m, which), L.pitch, L.plane, L.lead, g->d[0], g->d[1], g->d[2], g->g[0], g->g[1], g->g[2],
-        mode[0][0] == B200GEO_GHOST_EDGE, mode[0][1] == B200GEO_GHOST_EDGE,
-        mode[1][0] == B200GEO_GHOST_EDGE, mode[1][1] == B200GEO_GHOST_EDGE,
-        mode[2][0] == B200GEO_GHOST_EDGE, mode[2][1] == B200GEO_GHOST_EDGE, value);
-    count_launch();
+    T *base = (T *)g->member_ptr(m, which);
+    auto fill = [&](int x0, int y0, int z0, int w, int h, int d) {
+        int64_t n = (int64_t)w * h * d;
+        if (n <= 0) return;
+        int blocks = (int)((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16);
+        fill_box_kernel<T><<<blocks, 256, 0, s>>>(base, L.pitch, L.plane, x0, y0, z0, w, h, d, value);
+        count_launch();
+    };
+    const int x_lo = L.lead - gx;  // padded x of the first ghost column
+    if (mode[2][0] == B200GEO_GHOST_EDGE) fill(x_lo, 0, 0, px, py, gz);
+    if (mode[2][1] == B200GEO_GHOST_EDGE) fill(x_lo, 0, gz + nz, px, py, gz);
+    if (mode[1][0] == B200GEO_GHOST_EDGE) fill(x_lo, 0, 0, px, gy, nz + 2 * gz);
+    if (mode[1][1] == B200GEO_GHOST_EDGE) fill(x_lo, gy + ny, 0, px, gy, nz + 2 * gz);
+    if (mode[0][0] == B200GEO_GHOST_EDGE) fill(x_lo, 0, 0, gx, py, nz + 2 * gz);
+    if (mode[0][1] == B200GEO_GHOST_EDGE) fill(L.lead + nx, 0, 0, gx, py, nz + 2 * gz);
 }
 
 int fill_edge(b200geo_grid *g, int which, cudaStream_t s)
 {
-    if (g->d[1] + 2 * g->g[1] > 65535 || g->d[2] + 2 * g->g[2] > 65535)
-        return fail(B200GEO_ERR_OUT_OF_RANGE, "grid dimension too large");
     for (int m = 0; m < g->n; ++m) {
         switch (g->m[m].elem) {
         case 1: launch_fill_edge<uint8_t>(g, m, which, s); break;

@@ -220,6 +220,10 @@ int main()
         compareNBody<double>("NBody<double>", Coord<3>(4, 6, 3), 6);
         testEventProtocol();
         testRegionBytesMatchSoAGrid();
+        {
+            B200Simulator<Jacobi7Cube> sim(new SeededInitializer<Jacobi7Cube>(Coord<3>(20, 7, 12), 6));
+            testSerialBOVWriter(sim, "single");
+        }
     } catch (const std::exception& e) {
         std::printf("FAILED with exception: %s\n", e.what());
         return 2;

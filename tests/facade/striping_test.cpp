@@ -194,6 +194,10 @@ int main()
         testEventProtocol();
         testSteererWritesAcrossSlabs();
         testRegionAndMemberStreamsAcrossSlabs();
+        {
+            B200StripingSimulator<Jacobi7Cube> sim(new SeededInitializer<Jacobi7Cube>(Coord<3>(20, 7, 12), 6), devicesFor(3), 2);
+            testSerialBOVWriter(sim, "striped");
+        }
         bool thrown = false;
         try {
             B200StripingSimulator<Jacobi7Cube> tooThin(new SeededInitializer<Jacobi7Cube>(Coord<3>(8, 8, 4), 1), devicesFor(4), 2);
