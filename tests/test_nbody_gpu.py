@@ -30,10 +30,22 @@ def run(model, counts, parts, steps):
     return sim.getGrid().saveCells()
 
 
+@pytest.fixture
+def nbody_kernel():
+    """select the kernel variant ("nbody.kernel") for one test: 1 = re-bin + one-pass force kernels,
+    3 = fused re-bin / candidate-list kernel (default)"""
+    def set_(value):
+        capi.set_tuning("nbody.kernel", value)
+    yield set_
+    capi.set_tuning("nbody.kernel", -1)
+
+
+@pytest.mark.parametrize("kernel", [1, 3])
 @pytest.mark.parametrize("real", [np.float32, np.float64])
 @pytest.mark.parametrize("dims,steps,vel,dt", [((6, 5, 4), 10, 8.0, 0.01), ((9, 3, 2), 6, 20.0, 0.02), ((1, 1, 1), 5, 1.0, 0.01),
                                                ((17, 4, 3), 8, 10.0, 0.01), ((8, 8, 8), 10, 0.0, 0.005), ((2, 1, 7), 9, 15.0, 0.01)])
-def test_nbody_bit_exact(oracle, real, dims, steps, vel, dt):
+def test_nbody_bit_exact(oracle, nbody_kernel, kernel, real, dims, steps, vel, dt):
+    nbody_kernel(kernel)
     c, p = synth.nbody_cells(*dims, vel=vel, dtype=real)
     model = (models.NBodyF if real == np.float32 else models.NBodyD).with_params(dt=dt)
     co, po = run(model, c, p, steps)
@@ -64,6 +76,21 @@ def test_nbody_golden_from_the_reference(key):
     co, po = run(model, z[key + "_in_counts"], z[key + "_in_parts"], int(m.group(2)))
     assert np.array_equal(co, z[key + "_out_counts"])
     assert np.array_equal(po.view(np.uint8), z[key + "_out_parts"].view(np.uint8))
+
+
+@pytest.mark.parametrize("kernel", [1, 3])
+@pytest.mark.parametrize("real", [np.float32, np.float64])
+def test_nbody_dense_containers_overflow_the_candidate_lists(oracle, nbody_kernel, kernel, real):
+    """~27 (capacity 32) and ~33 (capacity 48) particles per container: more than 88 candidates pass the
+    filter of the fused kernel, so its candidate lists are flushed mid-way"""
+    nbody_kernel(kernel)
+    for cap, spacing in ((32, 0.84), (48, 0.80)):
+        c, p = synth.nbody_cells(5, 4, 3, cap=cap, spacing=spacing, jitter=0.05, vel=3.0, dtype=real)
+        assert c.max() > (24 if cap == 32 else 32)
+        model = (models.NBodyF if real == np.float32 else models.NBodyD).with_params(capacity=cap, dt=0.002)
+        co, po = run(model, c, p, 4)
+        wc, wp = oracle.nbody(c, p, 4, dt=0.002)
+        assert np.array_equal(co, wc) and np.array_equal(po.view(np.uint8), wp.view(np.uint8))
 
 
 def test_nbody_other_capacity_and_edge(oracle):
