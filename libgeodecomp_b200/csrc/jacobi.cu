@@ -13,6 +13,8 @@
 // are re-read through L1/L2, never from HBM (three planes of a 1024^2 slab are 25 MB << 126 MB L2).
 #include "grid.h"
 
+#include <cstring>
+
 namespace b200geo {
 
 namespace {
@@ -51,8 +53,14 @@ __device__ __forceinline__ double2 plane_sum(const double *p, int64_t pitch)
 template<int KIND>
 __global__ void __launch_bounds__(256)
 jacobi_kernel(const double *__restrict__ src, double *__restrict__ dst, int64_t pitch, int64_t plane,
-              Box box, int xa, int zchunk, int pf, int zlast)
+              Box box, int xa, int zchunk, int pf, int zlast, int pdl)
 {
+    // programmatic dependent launch (small, L2-resident grids): let the NEXT sweep's CTAs be scheduled while
+    // this one drains, and do not touch memory before the previous sweep has completed and flushed
+    if (pdl) {
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+    }
     const int x = xa + 2 * (blockIdx.x * blockDim.x + threadIdx.x);
     const int y = box.y0 + blockIdx.y * blockDim.y + threadIdx.y;
     const int zb = box.z0 + blockIdx.z * zchunk;
@@ -114,21 +122,40 @@ int sweep_jacobi(b200geo_grid *g, int kind, const Box& box, cudaStream_t s)
     dim3 block(64, 4);
     if (pairs <= 32) block = dim3(32, 8);
     int gx = (pairs + block.x - 1) / block.x, gy = (ny + block.y - 1) / block.y;
-    // enough z chunks for >= 8 CTAs per SM, but long enough to amortise the two-plane prologue
+    // enough z chunks for >= 8 CTAs per SM, but long enough to amortise the two-plane prologue (measured on
+    // 64^3 .. 256^3 grids, profiles/r1s_tuning.md: 2 planes for the 6/7-point kernels, 4 for the 27-point one)
     int zchunk = 32;
-    while (zchunk > 4 && (int64_t)gx * gy * ((nz + zchunk - 1) / zchunk) < 148 * 8) zchunk /= 2;
+    const int zmin = kind == 27 ? 4 : 2;
+    while (zchunk > zmin && (int64_t)gx * gy * ((nz + zchunk - 1) / zchunk) < 148 * 8) zchunk /= 2;
     if (g_tuning.jacobi_zchunk > 0) zchunk = g_tuning.jacobi_zchunk;
     // measured on B200 (profiles/r1b_tuning.md): +14% for the 7-point kernel, nothing for the 27-point one
     int pf = g_tuning.jacobi_prefetch >= 0 ? g_tuning.jacobi_prefetch : (kind == 27 ? 0 : 2), zlast = g->d[2] + g->g[2] - 1;
     dim3 grid(gx, gy, (nz + zchunk - 1) / zchunk);
     if (grid.y > 65535 || grid.z > 65535) return fail(B200GEO_ERR_OUT_OF_RANGE, "grid dimension too large");
+    // A sweep over a small grid (both buffers L2 resident) costs about as much as the gap between two
+    // dependent launches: overlap the launch of sweep n + 1 with the tail of sweep n (programmatic stream
+    // serialization). Large grids gain nothing and keep the plain launch.
+    const int64_t cells = (int64_t)(box.x1 - box.x0) * ny * nz;
+    const int pdl = g_tuning.jacobi_pdl >= 0 ? g_tuning.jacobi_pdl : (cells <= (1 << 24) ? 1 : 0);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    const int64_t pitch = L.pitch, plane = L.plane;
+    cudaError_t e;
     switch (kind) {
-    case 6: jacobi_kernel<6><<<grid, block, 0, s>>>(src, dst, L.pitch, L.plane, box, xa, zchunk, pf, zlast); break;
-    case 7: jacobi_kernel<7><<<grid, block, 0, s>>>(src, dst, L.pitch, L.plane, box, xa, zchunk, pf, zlast); break;
-    default: jacobi_kernel<27><<<grid, block, 0, s>>>(src, dst, L.pitch, L.plane, box, xa, zchunk, pf, zlast); break;
+    case 6: e = cudaLaunchKernelEx(&cfg, jacobi_kernel<6>, src, dst, pitch, plane, box, xa, zchunk, pf, zlast, pdl); break;
+    case 7: e = cudaLaunchKernelEx(&cfg, jacobi_kernel<7>, src, dst, pitch, plane, box, xa, zchunk, pf, zlast, pdl); break;
+    default: e = cudaLaunchKernelEx(&cfg, jacobi_kernel<27>, src, dst, pitch, plane, box, xa, zchunk, pf, zlast, pdl); break;
     }
     count_launch();
-    return check_cuda(cudaGetLastError(), "jacobi sweep");
+    return check_cuda(e != cudaSuccess ? e : cudaGetLastError(), "jacobi sweep");
 }
 
 }
