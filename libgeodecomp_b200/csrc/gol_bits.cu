@@ -19,6 +19,8 @@
 // last word are kept equal to the edge value.
 #include "grid.h"
 
+#include <cstring>
+
 namespace b200geo {
 
 namespace {
@@ -146,6 +148,10 @@ __device__ __forceinline__ void march(const uint32_t *__restrict__ src, uint32_t
 __global__ void __launch_bounds__(128)
 gol_bits_kernel(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst, BitGrid B, int rows_per_block)
 {
+    // programmatic dependent launch: a packed sweep (~20 us) is short next to the gap between two dependent
+    // launches, so sweep n + 1 is scheduled while sweep n drains; no memory access before the wait
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     const int lane = threadIdx.x & 31;
     Column col;
     col.w = blockIdx.x * blockDim.x + threadIdx.x;
@@ -256,8 +262,20 @@ int sweep_gol_bits(b200geo_grid *g, uint32_t sweeps, cudaStream_t s)
     while (rows > 4 && (int64_t)gx * ((B.ny + rows - 1) / rows) < 148 * 16) rows /= 2;
     if (g_tuning.gol_bits_rows > 0) rows = g_tuning.gol_bits_rows;
     dim3 sgrid(gx, (B.ny + rows - 1) / rows);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = sgrid;
+    cfg.blockDim = dim3(128);
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
     for (uint32_t t = 0; t < sweeps; ++t) {
-        gol_bits_kernel<<<sgrid, 128, 0, s>>>(buf[t & 1], buf[(t + 1) & 1], B, rows);
+        const uint32_t *src = buf[t & 1];
+        uint32_t *dst = buf[(t + 1) & 1];
+        B200GEO_CUDA(cudaLaunchKernelEx(&cfg, gol_bits_kernel, src, dst, B, rows));
         count_launch();
     }
     gol_unpack_kernel<<<pgrid, 128, 0, s>>>(buf[sweeps & 1], B, cur, L.pitch, g->d[0]);

@@ -352,8 +352,83 @@ static void compareWithSerialSimulator(const char *name, const Coord<DIM>& dim, 
     CHECK((differingCells<CELL, DIM>(ref.getGrid(), single.getGrid()) == 0));
 }
 
-int main()
+/* 7-point Jacobi as a plain user cell (no binding, no hand kernel): what the generic path costs */
+class PlainJacobi
 {
+public:
+    class API :
+        public APITraits::HasStencil<Stencils::VonNeumann<3, 1> >,
+        public APITraits::HasCubeTopology<3>
+    {};
+
+    __host__ __device__
+    explicit PlainJacobi(double temp = 0) : temp(temp)
+    {}
+
+    template<typename HOOD>
+    __host__ __device__
+    void update(const HOOD& hood, unsigned)
+    {
+        temp = (hood[FixedCoord<0, 0, -1>()].temp + hood[FixedCoord<0, -1, 0>()].temp + hood[FixedCoord<-1, 0, 0>()].temp +
+                hood[FixedCoord<0, 0, 0>()].temp + hood[FixedCoord<1, 0, 0>()].temp + hood[FixedCoord<0, 1, 0>()].temp +
+                hood[FixedCoord<0, 0, 1>()].temp) * (1.0 / 7.0);
+    }
+
+    bool operator==(const PlainJacobi& o) const
+    {
+        return std::memcmp(&temp, &o.temp, sizeof(temp)) == 0;
+    }
+
+    double temp;
+};
+
+template<> struct Seed<PlainJacobi> {
+    static PlainJacobi make(uint64_t i) { return PlainJacobi(uniform(i)); }
+    static PlainJacobi edge() { return PlainJacobi(0.5); }
+};
+
+/* throughput of the generic path (`generic_test --bench`): wall clock around step() calls, grid resident */
+template<typename CELL, int DIM>
+static void benchGeneric(const char *name, const Coord<DIM>& dim, unsigned steps, int bytesPerUpdate)
+{
+    B200Simulator<CELL> sim(new SeededInitializer<CELL>(dim, steps + 3));
+    for (int i = 0; i < 3; ++i) {
+        sim.step();
+    }
+    sim.getGrid();
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    cudaEventRecord(e0, 0);
+    for (unsigned i = 0; i < steps; ++i) {
+        sim.step();
+    }
+    cudaEventRecord(e1, 0);
+    cudaEventSynchronize(e1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    double cells = 1;
+    for (int d = 0; d < DIM; ++d) {
+        cells *= dim[d];
+    }
+    double glups = 1e-9 * cells * steps * APITraits::SelectNanoSteps<CELL>::VALUE / (1e-3 * ms);
+    std::printf("{\"generic\": \"%s\", \"cells\": %.0f, \"steps\": %u, \"ms_per_sweep\": %.4f, \"glups\": %.2f, \"algorithmic_gbs\": %.0f}\n",
+                name, cells, steps, ms / (steps * APITraits::SelectNanoSteps<CELL>::VALUE), glups, glups * bytesPerUpdate);
+}
+
+int main(int argc, char **argv)
+{
+    if (argc > 1 && std::string(argv[1]) == "--bench") {
+        try {
+            benchGeneric<PlainJacobi, 3>("PlainJacobi 7-point f64 384^3 (user update(), FixedCoord)", Coord<3>(384, 384, 384), 30, 16);
+            benchGeneric<LifeCell, 2>("LifeCell 8192^2 (user update(), run-time Coord<2>)", Coord<2>(8192, 8192), 50, 2);
+            benchGeneric<WaveCell, 3>("WaveCell 2 x f32 256^3 Torus (user updateLineX, 2 nano steps)", Coord<3>(256, 256, 256), 30, 16);
+        } catch (const std::exception& e) {
+            std::printf("FAILED with exception: %s\n", e.what());
+            return 2;
+        }
+        return 0;
+    }
     try {
         CHECK(B200KernelBinding<LifeCell>::kernel() == B200GEO_KERNEL_GENERIC);
         CHECK(B200Generic::Words<LifeCell>::N == 1 && B200Generic::Words<LifeCell>::W == 1);
@@ -371,6 +446,7 @@ int main()
         compareWithSerialSimulator<LifeCell, 2>("LifeCell (Coord<2>)", Coord<2>(150, 67), 30);
         compareWithSerialSimulator<HeatCell, 2>("HeatCell (stale member)", Coord<2>(97, 41), 23);
         compareWithSerialSimulator<WaveCell, 3>("WaveCell (updateLineX)", Coord<3>(40, 9, 7), 12);
+        compareWithSerialSimulator<PlainJacobi, 3>("PlainJacobi (7-point)", Coord<3>(33, 10, 9), 9);
     } catch (const std::exception& e) {
         std::printf("FAILED with exception: %s\n", e.what());
         return 2;
