@@ -175,11 +175,15 @@ public:
 
     b200geo_grid *raw()
     {
+        flush();
         return handle;
     }
 
     virtual void resize(const CoordBox<DIM>& newBox)
     {
+        pendingCells.clear();
+        pendingStreaks.clear();
+        rowCacheValid = false;
         b200geo_grid_destroy(handle);
         handle = 0;
         box = newBox;
@@ -192,32 +196,90 @@ public:
         set(Streak<DIM>(coord, coord.x() + 1), &cell);
     }
 
+    /* Writes are combined on the host and shipped as ONE streak list (b200geo_grid_load_region) before the
+     * next read, sweep or explicit flush: an Initializer that calls set(Coord, cell) for every cell of its box
+     * (src/examples/jacobi3d/main.cpp:54-72, src/examples/gameoflife/main.cpp:69-108) costs one transfer per
+     * 64 Ki cells instead of one per cell. Later writes win, as they would one by one. */
     virtual void set(const Streak<DIM>& streak, const CELL *cells)
     {
         int n = streak.length();
         if (n <= 0) {
             return;
         }
-        std::vector<char> buf((std::size_t)n * cellBytes);
-        std::size_t off = 0;
-        for (std::size_t m = 0; m < members.size(); ++m) {
-            for (int i = 0; i < n; ++i) {
-                std::memcpy(&buf[off + (std::size_t)i * members[m].bytes],
-                            reinterpret_cast<const char*>(cells + i) + members[m].offsetInCell, members[m].bytes);
-            }
-            off += (std::size_t)n * members[m].bytes;
-        }
         int32_t s[4];
         B200Helpers::toStreak4(streak, box.origin, s);
-        // both buffers: SerialSimulator initialises curGrid and newGrid alike (serialsimulator.h:54-57)
-        B200Helpers::check(b200geo_grid_load_region(handle, s, 1, buf.data(), B200GEO_HOST, 1, 0));
+        pendingStreaks.insert(pendingStreaks.end(), s, s + 4);
+        pendingCells.insert(pendingCells.end(), cells, cells + n);
+        rowCacheValid = false;
+        if (pendingCells.size() >= MAX_PENDING_CELLS) {
+            flush();
+        }
     }
 
+    /* ship the combined writes (both buffers: serialsimulator.h:54-57 initialises curGrid and newGrid alike) */
+    void flush() const
+    {
+        if (pendingCells.empty()) {
+            return;
+        }
+        std::size_t n = pendingCells.size();
+        std::vector<char> buf(n * cellBytes);
+        std::size_t off = 0;
+        for (std::size_t m = 0; m < members.size(); ++m) {
+            const std::size_t bytes = members[m].bytes, at = members[m].offsetInCell;
+            for (std::size_t i = 0; i < n; ++i) {
+                std::memcpy(&buf[off + i * bytes], reinterpret_cast<const char*>(&pendingCells[i]) + at, bytes);
+            }
+            off += n * bytes;
+        }
+        // overlapping streaks are applied in list order by separate calls only if they overlap; the common
+        // case (disjoint cells) is one call
+        std::vector<int32_t> streaks;
+        streaks.swap(pendingStreaks);
+        pendingCells.clear();
+        if (disjoint(streaks)) {
+            B200Helpers::check(b200geo_grid_load_region(handle, streaks.data(), (int)(streaks.size() / 4), buf.data(), B200GEO_HOST, 1, 0));
+            return;
+        }
+        // rewritten cells: one call per streak keeps the order of the writes
+        std::size_t done = 0;
+        for (std::size_t k = 0; k < streaks.size(); k += 4) {
+            std::size_t len = streaks[k + 3] - streaks[k];
+            std::vector<char> one(len * cellBytes);
+            std::size_t moff = 0, ooff = 0;
+            for (std::size_t m = 0; m < members.size(); ++m) {
+                std::memcpy(&one[ooff], &buf[moff + done * members[m].bytes], len * members[m].bytes);
+                ooff += len * members[m].bytes;
+                moff += n * members[m].bytes;
+            }
+            B200Helpers::check(b200geo_grid_load_region(handle, &streaks[k], 1, one.data(), B200GEO_HOST, 1, 0));
+            done += len;
+        }
+    }
+
+    /* single-cell reads are served from a cache of the row they lie in (Writers that walk the grid cell by
+     * cell, e.g. TS_ASSERT_TEST_GRID, misc/testhelper.h:115-136): one transfer per row, not per cell */
     virtual CELL get(const Coord<DIM>& coord) const
     {
-        CELL cell;
-        get(Streak<DIM>(coord, coord.x() + 1), &cell);
-        return cell;
+        Coord<DIM> rowOrigin = coord;
+        rowOrigin.x() = box.origin.x();
+        if (!rowCacheValid || !(rowCacheOrigin == rowOrigin)) {
+            bool inside = true;
+            for (int d = 0; d < DIM; ++d) {
+                inside &= coord[d] >= box.origin[d] && coord[d] < box.origin[d] + box.dimensions[d];
+            }
+            if (!inside) {
+                // edge ring / ghost cells: straight from the device
+                CELL cell;
+                get(Streak<DIM>(coord, coord.x() + 1), &cell);
+                return cell;
+            }
+            rowCache.resize(box.dimensions.x());
+            get(Streak<DIM>(rowOrigin, rowOrigin.x() + box.dimensions.x()), rowCache.data());
+            rowCacheOrigin = rowOrigin;
+            rowCacheValid = true;
+        }
+        return rowCache[coord.x() - box.origin.x()];
     }
 
     virtual void get(const Streak<DIM>& streak, CELL *cells) const
@@ -226,6 +288,7 @@ public:
         if (n <= 0) {
             return;
         }
+        flush();
         std::vector<char> buf((std::size_t)n * cellBytes);
         int32_t s[4];
         B200Helpers::toStreak4(streak, box.origin, s);
@@ -266,6 +329,7 @@ public:
     /* member-major byte stream, byte-compatible with SoAGrid::saveRegion (storage/soagrid.h:523-547) */
     virtual void saveRegion(std::vector<char> *buffer, const Region<DIM>& region, const Coord<DIM>& offset = Coord<DIM>()) const
     {
+        flush();
         std::vector<int32_t> streaks = flatten(region, offset);
         buffer->resize(region.size() * cellBytes);
         B200Helpers::check(b200geo_grid_save_region(handle, streaks.data(), (int)(streaks.size() / 4), buffer->data(), B200GEO_HOST, 0));
@@ -277,6 +341,8 @@ public:
         if (buffer.size() != region.size() * cellBytes) {
             throw std::invalid_argument("buffer size does not match region");
         }
+        flush();
+        rowCacheValid = false;
         std::vector<int32_t> streaks = flatten(region, offset);
         B200Helpers::check(b200geo_grid_load_region(handle, streaks.data(), (int)(streaks.size() / 4), buffer.data(), B200GEO_HOST, 1, 0));
         B200Helpers::check(b200geo_sync(0));
@@ -285,6 +351,8 @@ public:
     /* the hot path: n sweeps + swaps on the device (SerialSimulator::nanoStep, serialsimulator.h:132-139) */
     void update(unsigned firstNanoStep, unsigned sweeps)
     {
+        flush();
+        rowCacheValid = false;
         int32_t dim[3] = {1, 1, 1};
         for (int i = 0; i < DIM; ++i) {
             dim[i] = box.dimensions[i];
@@ -294,7 +362,14 @@ public:
 
     void sync() const
     {
+        flush();
         B200Helpers::check(b200geo_sync(0));
+    }
+
+    /* the device grid was changed behind this object's back (slab group stepping): drop cached rows */
+    void invalidateCache() const
+    {
+        rowCacheValid = false;
     }
 
     int bytesPerCell() const
@@ -331,6 +406,7 @@ protected:
         const typename Region<DIM>::StreakIterator& begin,
         const typename Region<DIM>::StreakIterator& end) const
     {
+        flush();
         int m = findMember(selector);
         for (typename Region<DIM>::StreakIterator i = begin; i != end; ++i) {
             int n = i->length();
@@ -360,6 +436,8 @@ protected:
         const typename Region<DIM>::StreakIterator& begin,
         const typename Region<DIM>::StreakIterator& end)
     {
+        flush();
+        rowCacheValid = false;
         int m = findMember(selector);
         for (typename Region<DIM>::StreakIterator i = begin; i != end; ++i) {
             int n = i->length();
@@ -393,6 +471,29 @@ private:
     int slabGhost;
     bool lowPeer;
     bool highPeer;
+    static const std::size_t MAX_PENDING_CELLS = 1 << 16;
+    mutable std::vector<CELL> pendingCells;        /* combined writes: cells ...                  */
+    mutable std::vector<int32_t> pendingStreaks;   /* ... and where they go, {x, y, z, endX} each */
+    mutable std::vector<CELL> rowCache;
+    mutable Coord<DIM> rowCacheOrigin;
+    mutable bool rowCacheValid = false;
+
+    /* no two streaks of the list share a cell (then their order does not matter) */
+    static bool disjoint(const std::vector<int32_t>& streaks)
+    {
+        std::vector<std::pair<std::pair<int32_t, int32_t>, std::pair<int32_t, int32_t> > > v;
+        v.reserve(streaks.size() / 4);
+        for (std::size_t k = 0; k < streaks.size(); k += 4) {
+            v.push_back(std::make_pair(std::make_pair(streaks[k + 2], streaks[k + 1]), std::make_pair(streaks[k], streaks[k + 3])));
+        }
+        std::sort(v.begin(), v.end());
+        for (std::size_t i = 1; i < v.size(); ++i) {
+            if (v[i].first == v[i - 1].first && v[i].second.first < v[i - 1].second.second) {
+                return false;
+            }
+        }
+        return true;
+    }
 
     void init()
     {

@@ -192,6 +192,10 @@ public:
     /* sweeps x { update every slab; swap } with the halo exchanges they need */
     void update(unsigned firstNanoStep, unsigned sweeps)
     {
+        for (std::size_t s = 0; s < slabs.size(); ++s) {
+            slabs[s]->flush();            // combined host writes reach the device before the sweep
+            slabs[s]->invalidateCache();  // and cached rows are stale after it
+        }
         if (dirty) {
             // cells were written from the host: the neighbours' ghost copies are stale
             B200Helpers::check(b200geo_group_invalidate(group));
@@ -202,6 +206,9 @@ public:
 
     void sync() const
     {
+        for (std::size_t s = 0; s < slabs.size(); ++s) {
+            slabs[s]->flush();
+        }
         B200Helpers::check(b200geo_group_sync(group));
     }
 

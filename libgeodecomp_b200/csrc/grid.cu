@@ -190,6 +190,7 @@ int b200geo_grid_destroy(b200geo_grid *g)
     cudaFree(g->buf[0]);
     cudaFree(g->buf[1]);
     if (g->scratch) cudaFree(g->scratch);
+    if (g->io_staging) cudaFree(g->io_staging);
     if (g->bits) cudaFree(g->bits);
     for (int i = 0; i < 4; ++i) cudaEventDestroy(g->ev[i]);
     delete g;
@@ -315,22 +316,35 @@ static int region_io(b200geo_grid *g, const int32_t *streaks, int n_streaks, voi
     B200GEO_CUDA(cudaSetDevice(g->device));
     char *dev = (char *)buf;
     size_t bytes = (size_t)count * g->cell_bytes;
-    char *staging = 0;
-    if (location == B200GEO_HOST) {
-        B200GEO_CUDA(cudaMalloc((void **)&staging, bytes ? bytes : 1));
-        dev = staging;
-        if (!save) {
-            cudaError_t e = cudaMemcpyAsync(dev, buf, bytes, cudaMemcpyHostToDevice, s);
-            if (e != cudaSuccess) { cudaFree(staging); return check_cuda(e, "cudaMemcpyAsync"); }
+    const bool staged = location == B200GEO_HOST;
+    if (staged) {
+        // Initializers and Writers that go cell by cell (GridBase::set / get in a loop) come through here once
+        // per call: the staging buffer is kept, so such a call is two small copies and one launch
+        if (g->io_staging_bytes < bytes) {
+            if (g->io_staging) {
+                cudaStreamSynchronize(s);
+                cudaFree(g->io_staging);
+                g->io_staging = 0;
+                g->io_staging_bytes = 0;
+            }
+            size_t want = bytes < 4096 ? 4096 : bytes;
+            cudaError_t e = cudaMalloc((void **)&g->io_staging, want);
+            if (e != cudaSuccess) {
+                cudaGetLastError();
+                return fail(B200GEO_ERR_NOMEM, std::string("cudaMalloc failed: ") + cudaGetErrorString(e));
+            }
+            g->io_staging_bytes = want;
         }
+        dev = g->io_staging;
+        // pageable host memory: the copy has left the caller's buffer when cudaMemcpyAsync returns
+        if (!save) B200GEO_CUDA(cudaMemcpyAsync(dev, buf, bytes, cudaMemcpyHostToDevice, s));
     }
     int rc = copy_region(g, streaks, n_streaks, dev, count, save, 0, s);
     if (rc == 0 && !save && both) rc = copy_region(g, streaks, n_streaks, dev, count, false, 1, s);
-    if (rc == 0 && location == B200GEO_HOST && save)
+    if (rc == 0 && staged && save) {
+        // the caller reads its buffer right after the call (and the next call reuses the staging buffer)
         rc = check_cuda(cudaMemcpyAsync(buf, dev, bytes, cudaMemcpyDeviceToHost, s), "cudaMemcpyAsync");
-    if (staging) {
-        cudaStreamSynchronize(s);
-        cudaFree(staging);
+        if (rc == 0) rc = check_cuda(cudaStreamSynchronize(s), "cudaStreamSynchronize");
     }
     return rc;
 }

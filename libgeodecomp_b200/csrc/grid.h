@@ -53,6 +53,8 @@ struct b200geo_grid {
     size_t bits_bytes;
     void *scratch;       // small device scratch (streak lists etc.)
     size_t scratch_bytes;
+    char *io_staging;    // device staging of host-side region I/O (grow-only: no cudaMalloc per set/get call)
+    size_t io_staging_bytes;
 
     char *member_ptr(int member, int which) const { return buf[cur ^ which] + m[member].offset; }
     // elements per slice (plane, or row for 2-D grids) along the slab axis

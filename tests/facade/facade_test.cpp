@@ -5,6 +5,8 @@
  * tests/test_facade_gpu.py. Exit code 0 = all checks passed. */
 #include "fixtures.h"
 
+#include <ctime>
+
 template<typename CELL, typename INIT, int DIM>
 void compareWithSerialSimulator(const char *name, const Coord<DIM>& dim, unsigned steps)
 {
@@ -204,6 +206,45 @@ static void compareNBody(const char *name, const Coord<3>& dim, unsigned steps)
                 bad == 0 ? "bit-identical to SerialSimulator" : "DIFFERENT");
 }
 
+/* Initializers / Writers that go cell by cell (GridBase::set(Coord) / get(Coord) in a loop, as the reference's
+ * examples do): writes are combined and rows cached, later writes win, a read after a write sees the write */
+static void testCellByCellAccess()
+{
+    typedef Jacobi7Cube CELL;
+    Coord<3> dim(96, 64, 48);
+    CoordBox<3> box(Coord<3>(), dim);
+    B200Grid<CELL> dev(box);
+    std::clock_t t0 = std::clock();
+    for (CoordBox<3>::Iterator i = box.begin(); i != box.end(); ++i) {
+        dev.set(*i, CELL(uniform(i->toIndex(dim))));
+    }
+    // overwrite a few cells twice in a row, then read them back at once (write, write, read)
+    dev.set(Coord<3>(5, 6, 7), CELL(1.25));
+    dev.set(Coord<3>(5, 6, 7), CELL(2.5));
+    dev.set(Streak<3>(Coord<3>(4, 6, 7), 7), std::vector<CELL>(3, CELL(7.0)).data());
+    dev.set(Coord<3>(6, 6, 7), CELL(9.0));
+    CHECK(dev.get(Coord<3>(4, 6, 7)) == CELL(7.0));
+    CHECK(dev.get(Coord<3>(5, 6, 7)) == CELL(7.0));
+    CHECK(dev.get(Coord<3>(6, 6, 7)) == CELL(9.0));
+    dev.set(Coord<3>(6, 6, 7), CELL(uniform(Coord<3>(6, 6, 7).toIndex(dim))));
+    dev.set(Coord<3>(5, 6, 7), CELL(uniform(Coord<3>(5, 6, 7).toIndex(dim))));
+    dev.set(Coord<3>(4, 6, 7), CELL(uniform(Coord<3>(4, 6, 7).toIndex(dim))));
+    long bad = 0;
+    for (CoordBox<3>::Iterator i = box.begin(); i != box.end(); ++i) {
+        if (!(dev.get(*i) == CELL(uniform(i->toIndex(dim))))) ++bad;
+    }
+    double seconds = (double)(std::clock() - t0) / CLOCKS_PER_SEC;
+    CHECK(bad == 0);
+    // the edge ring is read straight from the device
+    dev.setEdge(CELL(0.125));
+    CHECK(dev.get(Coord<3>(-1, 0, 0)) == CELL(0.125));
+    // a sweep invalidates cached rows
+    CELL before = dev.get(Coord<3>(10, 10, 10));
+    dev.update(0, 1);
+    CHECK(!(dev.get(Coord<3>(10, 10, 10)) == before));
+    std::printf("cell-by-cell set + get of %d cells: %ld wrong, %.2f s CPU\n", dim.prod(), bad, seconds);
+}
+
 int main()
 {
     try {
@@ -220,6 +261,7 @@ int main()
         compareNBody<double>("NBody<double>", Coord<3>(4, 6, 3), 6);
         testEventProtocol();
         testRegionBytesMatchSoAGrid();
+        testCellByCellAccess();
         {
             B200Simulator<Jacobi7Cube> sim(new SeededInitializer<Jacobi7Cube>(Coord<3>(20, 7, 12), 6));
             testSerialBOVWriter(sim, "single");
