@@ -97,6 +97,8 @@ int b200geo_grid_create(const b200geo_grid_desc *desc, int device, b200geo_grid 
 int b200geo_grid_destroy(b200geo_grid *g);
 /* bytes of one of the two buffers (padded layout) */
 int b200geo_grid_buffer_bytes(const b200geo_grid *g, uint64_t *bytes);
+/* the CUDA device the grid lives on */
+int b200geo_grid_device(const b200geo_grid *g, int *device);
 /* layout query for one member: row pitch and plane pitch in elements, and the element offset of
  * interior cell (0,0,0) from the member's base pointer */
 int b200geo_grid_layout(const b200geo_grid *g, int member, int64_t *pitch_x, int64_t *pitch_plane,
@@ -194,6 +196,16 @@ int b200geo_group_exchange(b200geo_group *grp);
 /* n_steps x { UpdateFunctor over every slab; swap } with the exchanges they need; results are
  * bit-identical to b200geo_step on one grid holding the whole space */
 int b200geo_group_step(b200geo_group *grp, int kernel, const void *params, uint32_t first_nano_step, uint32_t n_steps);
+/* Same for cells whose update kernel lives OUTSIDE this library (the generic device path of
+ * include/libgeodecomp_b200/b200generic.h: the user's own Cell::update compiled by nvcc): `update` is called with
+ * the slab's device current and must enqueue, on `stream`, one sweep over the `dim` cells at `origin` (interior
+ * coordinates of that slab), reading the grid's current buffer and writing its scratch buffer
+ * (b200geo_grid_member_ptr which = 0 / 1); it returns 0 or a negative b200geo_status. One exchange of
+ * ghost-width planes per sweep; rims first, interior overlapped with the transfer. */
+typedef int (*b200geo_update_fn)(void *ctx, b200geo_grid *g, uint32_t nano_step, const int32_t origin[3],
+                                 const int32_t dim[3], void *stream);
+int b200geo_group_step_with(b200geo_group *grp, b200geo_update_fn update, void *ctx, uint32_t first_nano_step,
+                            uint32_t n_steps);
 int b200geo_group_sync(b200geo_group *grp);
 /* out[0] = exchanges so far, out[1] = bytes shipped between devices */
 int b200geo_group_stats(const b200geo_group *grp, uint64_t out[2]);

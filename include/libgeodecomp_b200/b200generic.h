@@ -188,7 +188,8 @@ struct Invoke<CELL, HOOD, false> {
     }
 };
 
-/* One sweep: thread = cell, x fastest (coalesced per word array), y and z from the block index. */
+/* One sweep over a box: thread = cell, x fastest (coalesced per word array), y and z from the block index.
+ * `origin` = element index of the box's first cell. */
 template<typename CELL, int DIM>
 __global__ void __launch_bounds__(256)
 updateKernel(View oldView, View newView, long long origin, int nx, int ny, unsigned nanoStep)
@@ -264,29 +265,62 @@ struct B200KernelBinding {
         return ret;
     }
 
-    /* sweeps x { refresh periodic images; UpdateFunctor over the whole grid; swap }
-     * = SerialSimulator::nanoStep (parallelization/serialsimulator.h:132-139) */
-    static void step(b200geo_grid *g, const int32_t dim[3], unsigned firstNanoStep, unsigned sweeps)
+    /* enqueue one sweep over the box (origin, dim) of grid g on `stream`: current buffer -> scratch buffer */
+    static void launchBox(b200geo_grid *g, unsigned nanoStep, const int32_t origin[3], const int32_t dim[3], cudaStream_t stream)
     {
-        int64_t origin = 0;
-        B200Generic::check(b200geo_grid_layout(g, 0, 0, 0, &origin));
+        if (dim[0] <= 0 || dim[1] <= 0 || dim[2] <= 0) {
+            return;
+        }
+        int64_t first = 0;
+        B200Generic::check(b200geo_grid_layout(g, 0, 0, 0, &first));
+        B200Generic::View oldView = B200Generic::view<CELL>(g, 0);
+        B200Generic::View newView = B200Generic::view<CELL>(g, 1);
+        first += origin[0] + origin[1] * oldView.pitch + origin[2] * oldView.plane;
         dim3 block(128, DIM > 1 ? 2 : 1, 1);
         dim3 grid((dim[0] + block.x - 1) / block.x, (dim[1] + block.y - 1) / block.y, dim[2]);
         if (grid.y > 65535u || grid.z > 65535u) {
             throw std::out_of_range("grid dimension too large");
         }
+        B200Generic::updateKernel<CELL, DIM><<<grid, block, 0, stream>>>(
+            oldView, newView, (long long)first, dim[0], dim[1], nanoStep % NANO_STEPS);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) {
+            throw std::runtime_error(std::string("CUDA error: ") + cudaGetErrorString(e) + " in generic update kernel");
+        }
+    }
+
+    /* sweeps x { refresh periodic images; UpdateFunctor over the whole grid; swap }
+     * = SerialSimulator::nanoStep (parallelization/serialsimulator.h:132-139) */
+    static void step(b200geo_grid *g, const int32_t dim[3], unsigned firstNanoStep, unsigned sweeps)
+    {
+        const int32_t origin[3] = {0, 0, 0};
         for (unsigned t = 0; t < sweeps; ++t) {
             B200Generic::check(b200geo_refresh_ghosts(g, 0));
-            B200Generic::View oldView = B200Generic::view<CELL>(g, 0);
-            B200Generic::View newView = B200Generic::view<CELL>(g, 1);
-            B200Generic::updateKernel<CELL, DIM><<<grid, block>>>(
-                oldView, newView, (long long)origin, dim[0], dim[1], (firstNanoStep + t) % NANO_STEPS);
-            cudaError_t e = cudaGetLastError();
-            if (e != cudaSuccess) {
-                throw std::runtime_error(std::string("CUDA error: ") + cudaGetErrorString(e) + " in generic update kernel");
-            }
+            launchBox(g, firstNanoStep + t, origin, dim, 0);
             B200Generic::check(b200geo_swap(g));
         }
+    }
+
+    /* the same on a slab group (B200StripingSimulator): the group drives the schedule — rims, halo copies,
+     * interiors — and calls back for every box it wants updated */
+    static int updateCallback(void *, b200geo_grid *g, uint32_t nanoStep, const int32_t origin[3], const int32_t dim[3], void *stream)
+    {
+        try {
+            int device = 0;
+            B200Generic::check(b200geo_grid_device(g, &device));
+            if (cudaSetDevice(device) != cudaSuccess) {
+                return B200GEO_ERR_CUDA;
+            }
+            launchBox(g, nanoStep, origin, dim, static_cast<cudaStream_t>(stream));
+        } catch (const std::exception&) {
+            return B200GEO_ERR_CUDA;
+        }
+        return B200GEO_OK;
+    }
+
+    static void groupStep(b200geo_group *group, unsigned firstNanoStep, unsigned sweeps)
+    {
+        B200Generic::check(b200geo_group_step_with(group, &updateCallback, 0, firstNanoStep, sweeps));
     }
 };
 

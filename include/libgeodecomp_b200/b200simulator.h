@@ -62,6 +62,10 @@ struct B200KernelBinding;      /* specialise with B200GEO_BIND_CELL */
         {                                                                               \
             B200Helpers::check(b200geo_step(g, KERNEL_ID, 0, first, n, 0));             \
         }                                                                               \
+        static void groupStep(b200geo_group *group, unsigned first, unsigned n)         \
+        {                                                                               \
+            B200Helpers::check(b200geo_group_step(group, KERNEL_ID, 0, first, n));      \
+        }                                                                               \
         static std::vector<B200Member> members()                                        \
         {                                                                               \
             B200Member tab[] = { __VA_ARGS__ };                                         \

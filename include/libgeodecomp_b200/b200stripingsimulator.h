@@ -1,4 +1,4 @@
-/* Multi-GPU drop-in for bound cells: ONE process and host thread, the simulation space cut into equal
+/* Multi-GPU drop-in: ONE process and host thread, the simulation space cut into equal
  * slabs along the last axis (geometry/partitions/stripingpartition.h:57-62), one slab per GPU of the box.
  *
  *   B200StripedGrid<CELL>        the GridBase<CELL, DIM> that Initializers, Writers and Steerers see: the
@@ -201,7 +201,8 @@ public:
             B200Helpers::check(b200geo_group_invalidate(group));
             dirty = false;
         }
-        B200Helpers::check(b200geo_group_step(group, B200KernelBinding<CELL>::kernel(), 0, firstNanoStep, sweeps));
+        // bound cells: the library's kernels; unbound cells (nvcc translation units): their own update()
+        B200KernelBinding<CELL>::groupStep(group, firstNanoStep, sweeps);
     }
 
     void sync() const

@@ -61,6 +61,7 @@ SYMBOLS = [
     ("b200geo_grid_create", ctypes.c_int, [ctypes.POINTER(GridDesc), ctypes.c_int, ctypes.POINTER(_vp)]),
     ("b200geo_grid_destroy", ctypes.c_int, [_vp]),
     ("b200geo_grid_buffer_bytes", ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_uint64)]),
+    ("b200geo_grid_device", ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_int)]),
     ("b200geo_grid_layout", ctypes.c_int, [_vp, ctypes.c_int, _i64p, _i64p, _i64p]),
     ("b200geo_grid_member_ptr", ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(_vp)]),
     ("b200geo_grid_set_edge", ctypes.c_int, [_vp, _vp, _vp]),
@@ -88,6 +89,7 @@ SYMBOLS = [
     ("b200geo_group_invalidate", ctypes.c_int, [_vp]),
     ("b200geo_group_exchange", ctypes.c_int, [_vp]),
     ("b200geo_group_step", ctypes.c_int, [_vp, ctypes.c_int, _vp, ctypes.c_uint32, ctypes.c_uint32]),
+    ("b200geo_group_step_with", ctypes.c_int, [_vp, _vp, _vp, ctypes.c_uint32, ctypes.c_uint32]),
     ("b200geo_group_sync", ctypes.c_int, [_vp]),
     ("b200geo_group_stats", ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_uint64)]),
     ("b200geo_boxgrid_create", ctypes.c_int, [ctypes.POINTER(BoxGridDesc), ctypes.c_int, ctypes.POINTER(_vp)]),

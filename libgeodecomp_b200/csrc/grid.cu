@@ -204,6 +204,13 @@ int b200geo_grid_buffer_bytes(const b200geo_grid *g, uint64_t *bytes)
     return B200GEO_OK;
 }
 
+int b200geo_grid_device(const b200geo_grid *g, int *device)
+{
+    if (!g || !device) return fail(B200GEO_ERR_INVALID, "null argument");
+    *device = g->device;
+    return B200GEO_OK;
+}
+
 int b200geo_grid_layout(const b200geo_grid *g, int member, int64_t *pitch_x, int64_t *pitch_plane,
                         int64_t *origin_offset)
 {

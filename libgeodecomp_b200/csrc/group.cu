@@ -33,6 +33,24 @@ namespace b200geo {
 
 namespace {
 
+// What updates a box of one slab: a kernel family of this library (possibly several fused sweeps per
+// launch), or a callback for cells whose kernel lives in the caller's translation unit (one sweep).
+struct Updater {
+    int kernel;
+    const void *params;
+    b200geo_update_fn fn;
+    void *ctx;
+
+    int box(b200geo_grid *g, uint32_t nano_step, const int32_t origin[3], const int32_t dim[3], int sweeps, cudaStream_t s) const
+    {
+        if (!fn) return b200geo_update_box_n(g, kernel, params, nano_step, origin, dim, (uint32_t)sweeps, s);
+        if (sweeps != 1) return fail(B200GEO_ERR_LOGIC, "update callbacks take one sweep per call");
+        int rc = fn(ctx, g, nano_step, origin, dim, s);
+        if (rc < 0) return fail(rc, "update callback failed");
+        return B200GEO_OK;
+    }
+};
+
 // neighbour of slab i on `side` (0 = low, 1 = high), or -1
 int neighbour(const b200geo_group *grp, int i, int side)
 {
@@ -151,9 +169,10 @@ int exchange_current(b200geo_group *grp, int kernel, int width)
     return mark_valid(grp, width);
 }
 
-// One round of `w` sweeps, rim first: [0, w) and [n - w, n) of every slab, ship them out of the scratch
-// buffers while the interiors [w, n - w) are updated, swap.
-int overlapped_round(b200geo_group *grp, int kernel, const void *params, uint32_t nano_step, int w)
+// One round of `sweeps` sweeps, rim first: the `w` outermost planes on both sides of every slab, ship them out
+// of the scratch buffers while the interiors are updated, swap. Bound kernels fuse sweeps = w sweeps per launch;
+// callbacks take one sweep per round (w = their stencil radius).
+int overlapped_round(b200geo_group *grp, const Updater& up, uint32_t nano_step, int w, int sweeps)
 {
     int a = grp->g[0]->slab_axis;
     for (int i = 0; i < grp->n; ++i) {
@@ -167,13 +186,13 @@ int overlapped_round(b200geo_group *grp, int kernel, const void *params, uint32_
         if (lo > 0) {
             origin[a] = 0;
             dim[a] = lo;
-            rc = b200geo_update_box_n(g, kernel, params, nano_step, origin, dim, w, grp->compute[i]);
+            rc = up.box(g, nano_step, origin, dim, sweeps, grp->compute[i]);
             if (rc) return rc;
         }
         if (hi < n) {
             origin[a] = hi;
             dim[a] = n - hi;
-            rc = b200geo_update_box_n(g, kernel, params, nano_step, origin, dim, w, grp->compute[i]);
+            rc = up.box(g, nano_step, origin, dim, sweeps, grp->compute[i]);
             if (rc) return rc;
         }
         B200GEO_CUDA(cudaEventRecord(grp->rim[i], grp->compute[i]));
@@ -188,7 +207,7 @@ int overlapped_round(b200geo_group *grp, int kernel, const void *params, uint32_
             if (j >= 0) B200GEO_CUDA(cudaStreamWaitEvent(grp->copy[i], grp->rim[j], 0));
         }
     }
-    int rc = ship_rims(grp, kernel, w, 1);
+    int rc = ship_rims(grp, up.kernel, w, 1);
     if (rc) return rc;
     for (int i = 0; i < grp->n; ++i) {
         b200geo_grid *g = grp->g[i];
@@ -199,15 +218,36 @@ int overlapped_round(b200geo_group *grp, int kernel, const void *params, uint32_
             int32_t origin[3] = {0, 0, 0}, dim[3] = {g->d[0], g->d[1], g->d[2]};
             origin[a] = lo;
             dim[a] = hi - lo;
-            rc = b200geo_update_box_n(g, kernel, params, nano_step, origin, dim, w, grp->compute[i]);
+            rc = up.box(g, nano_step, origin, dim, sweeps, grp->compute[i]);
             if (rc) return rc;
         }
         g->cur ^= 1;
-        g->sweeps += w;
+        g->sweeps += sweeps;
     }
     rc = wait_for_copies(grp);
     if (rc) return rc;
     return mark_valid(grp, w);
+}
+
+// callbacks on slabs too thin for a rim / interior split: exchange, one sweep over every slab, swap
+int plain_round(b200geo_group *grp, const Updater& up, uint32_t nano_step, int w)
+{
+    int rc = exchange_current(grp, 0, w);
+    if (rc) return rc;
+    for (int i = 0; i < grp->n; ++i) {
+        b200geo_grid *g = grp->g[i];
+        B200GEO_CUDA(cudaSetDevice(g->device));
+        rc = refresh_wrap(g, grp->compute[i]);
+        if (rc) return rc;
+        int32_t origin[3] = {0, 0, 0}, dim[3] = {g->d[0], g->d[1], g->d[2]};
+        rc = up.box(g, nano_step, origin, dim, 1, grp->compute[i]);
+        if (rc) return rc;
+        g->cur ^= 1;
+        g->sweeps += 1;
+    }
+    for (int i = 0; i < grp->n; ++i) grp->g[i]->peer_valid[0] = grp->g[i]->peer_valid[1] = 0;
+    grp->valid = 0;
+    return B200GEO_OK;
 }
 
 }
@@ -325,7 +365,8 @@ int b200geo_group_step(b200geo_group *grp, int kernel, const void *params, uint3
         }
         if (overlap && grp->valid == w && left >= (uint32_t)w) {
             const void *p = lbm_lazy ? (const void *)(done + w == n_steps ? &lbm_store : &lbm_skip) : params;
-            int rc = overlapped_round(grp, kernel, p, first_nano_step + done, w);
+            Updater up = {kernel, p, 0, 0};
+            int rc = overlapped_round(grp, up, first_nano_step + done, w, w);
             if (rc) return rc;
             done += w;
             continue;
@@ -339,6 +380,43 @@ int b200geo_group_step(b200geo_group *grp, int kernel, const void *params, uint3
         }
         grp->valid -= (int)k;
         done += k;
+    }
+    return B200GEO_OK;
+}
+
+int b200geo_group_step_with(b200geo_group *grp, b200geo_update_fn update, void *ctx, uint32_t first_nano_step, uint32_t n_steps)
+{
+    if (!grp || !update) return fail(B200GEO_ERR_INVALID, "null argument");
+    const int w = ghost_width(grp), a = grp->g[0]->slab_axis;
+    Updater up = {0, 0, update, ctx};
+    bool overlap = grp->n > 1;
+    for (int i = 0; i < grp->n; ++i)
+        if (grp->g[i]->d[a] < 2 * w) overlap = false;
+    for (uint32_t done = 0; done < n_steps; ++done) {
+        const uint32_t nano = first_nano_step + done;
+        if (grp->n == 1) {
+            b200geo_grid *g = grp->g[0];
+            B200GEO_CUDA(cudaSetDevice(g->device));
+            int rc = refresh_wrap(g, grp->compute[0]);
+            if (rc) return rc;
+            int32_t origin[3] = {0, 0, 0}, dim[3] = {g->d[0], g->d[1], g->d[2]};
+            rc = up.box(g, nano, origin, dim, 1, grp->compute[0]);
+            if (rc) return rc;
+            g->cur ^= 1;
+            g->sweeps += 1;
+            continue;
+        }
+        if (!overlap) {
+            int rc = plain_round(grp, up, nano, w);
+            if (rc) return rc;
+            continue;
+        }
+        if (grp->valid < w) {
+            int rc = exchange_current(grp, 0, w);
+            if (rc) return rc;
+        }
+        int rc = overlapped_round(grp, up, nano, w, 1);
+        if (rc) return rc;
     }
     return B200GEO_OK;
 }

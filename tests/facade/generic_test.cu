@@ -25,7 +25,7 @@
 #include <cstring>
 #include <iostream>
 
-#include <libgeodecomp_b200/b200simulator.h>
+#include <libgeodecomp_b200/b200stripingsimulator.h>
 
 using namespace LibGeoDecomp;
 
@@ -352,6 +352,34 @@ static void compareWithSerialSimulator(const char *name, const Coord<DIM>& dim, 
     CHECK((differingCells<CELL, DIM>(ref.getGrid(), single.getGrid()) == 0));
 }
 
+/* unbound cells on a slab group: the group drives rims / halo copies / interiors and calls the user's update()
+ * back for every box (b200geo_group_step_with); slabs round-robin over the GPUs present */
+static std::vector<int> devicesFor(int slabs)
+{
+    int n = b200geo_device_count();
+    std::vector<int> ret;
+    for (int s = 0; s < slabs; ++s) {
+        ret.push_back(n > 0 ? s % n : 0);
+    }
+    return ret;
+}
+
+template<typename CELL, typename INIT, int DIM>
+static void compareStriped(const char *name, const Coord<DIM>& dim, unsigned steps, int slabs)
+{
+    SerialSimulator<CELL> ref(new INIT(dim, steps));
+    B200StripingSimulator<CELL> sim(new INIT(dim, steps), devicesFor(slabs));
+    ref.run();
+    sim.run();
+    CHECK(sim.getStep() == steps);
+    long bad = differingCells<CELL, DIM>(ref.getGrid(), sim.getGrid());
+    CHECK(bad == 0);
+    std::pair<unsigned long long, unsigned long long> st = sim.stripedGrid().exchangeStatistics();
+    CHECK(slabs == 1 || st.first >= steps);
+    std::printf("%-22s on %d slabs: %s (%ld differing cells after %u steps, %llu exchanges)\n", name, slabs,
+                bad ? "MISMATCH" : "bit-exact", bad, steps, st.first);
+}
+
 /* 7-point Jacobi as a plain user cell (no binding, no hand kernel): what the generic path costs */
 class PlainJacobi
 {
@@ -447,6 +475,16 @@ int main(int argc, char **argv)
         compareWithSerialSimulator<HeatCell, 2>("HeatCell (stale member)", Coord<2>(97, 41), 23);
         compareWithSerialSimulator<WaveCell, 3>("WaveCell (updateLineX)", Coord<3>(40, 9, 7), 12);
         compareWithSerialSimulator<PlainJacobi, 3>("PlainJacobi (7-point)", Coord<3>(33, 10, 9), 9);
+
+        compareStriped<TestCell2dCube, TestInitializer<TestCell2dCube>, 2>("TestCell 2d Cube", Coord<2>(64, 32), 9, 3);
+        compareStriped<TestCell2dTorus, TestInitializer<TestCell2dTorus>, 2>("TestCell 2d Torus", Coord<2>(50, 21), 7, 2);
+        compareStriped<TestCell3dCube, TestInitializer<TestCell3dCube>, 3>("TestCell 3d Cube", Coord<3>(20, 10, 12), 4, 4);
+        compareStriped<TestCell3dTorus, TestInitializer<TestCell3dTorus>, 3>("TestCell 3d Torus", Coord<3>(13, 12, 11), 4, 3);
+        compareStriped<TestCell3dMooreCube, TestInitializer<TestCell3dMooreCube>, 3>("TestCell 3d Moore Cube", Coord<3>(13, 12, 3), 3, 3);
+        compareStriped<LifeCell, SeededInitializer<LifeCell>, 2>("LifeCell (Coord<2>)", Coord<2>(150, 67), 30, 4);
+        compareStriped<HeatCell, SeededInitializer<HeatCell>, 2>("HeatCell (stale member)", Coord<2>(97, 41), 23, 2);
+        compareStriped<WaveCell, SeededInitializer<WaveCell>, 3>("WaveCell (updateLineX)", Coord<3>(40, 9, 14), 12, 3);
+        compareStriped<PlainJacobi, SeededInitializer<PlainJacobi>, 3>("PlainJacobi (7-point)", Coord<3>(33, 10, 9), 9, 1);
     } catch (const std::exception& e) {
         std::printf("FAILED with exception: %s\n", e.what());
         return 2;
