@@ -85,8 +85,7 @@ int b200geo_device_count(void);
  * "jacobi.zchunk", "jacobi.prefetch", "gol.rows", "lbm.block", "jacobi.tb" (sweeps fused per launch
  * by the temporal-blocked Jacobi kernels, 1..4; 0 = automatic: 2 for the 27-point kernel, 4 for 6/7-point), "jacobi.tb_rows" (tile shape), "jacobi.tb_zchunk", "gol.bits" (fewest sweeps per call that run
  * bit-packed; 0 = never), "gol.bits_rows", "nbody.kernel", "jacobi.pdl" (programmatic dependent launch of the one-sweep Jacobi
- * kernel: 0, 1, < 0 = small grids only), "lbm.variant" (0 = wall test before the pulls, 1 = pulls hoisted
- * above the test, 2 = same with two rows per thread).
+ * kernel: 0, 1, < 0 = small grids only), "lbm.variant" (rows per thread of the LBM kernel: 1 or 2).
  * value < 0 restores the default. */
 int b200geo_set_tuning(const char *key, int value);
 /* number of kernels this library has launched so far in this process (bench.py: gpu_launches). */

@@ -75,7 +75,7 @@ struct Tuning {
     int gol_bits_rows;    // rows per CTA of the bit-packed kernel (0 = automatic)
     int nbody_kernel;     // 1 = re-bin kernel + one-pass force kernel, otherwise the fused re-bin / candidate-list kernel
     int jacobi_pdl;       // programmatic dependent launch of the one-sweep Jacobi kernel: 0 / 1, < 0 = small grids only
-    int lbm_variant;      // 0 = state test before the pulls, 1 = pulls hoisted above the test, 2 = same, two rows per thread
+    int lbm_variant;      // rows per thread of the LBM kernel: 1 (default) or 2
 };
 extern Tuning g_tuning;
 

@@ -25,138 +25,12 @@ enum { LIQUID, WEST_NOSLIP, EAST_NOSLIP, TOP, BOTTOM, NORTH_ACC, SOUTH_NOSLIP };
 #define PUT(COMP) dst[(int64_t)(COMP) * mstride + i]
 #define SQR(X) ((X) * (X))
 
-template<bool MACRO>
-__global__ void __launch_bounds__(128)
-lbm_kernel(const float *__restrict__ src, float *__restrict__ dst, int64_t pitch, int64_t plane,
-           int64_t mstride, Box box)
-{
-    const int x = box.x0 + blockIdx.x * blockDim.x + threadIdx.x;
-    if (x >= box.x1) return;
-    const int y = box.y0 + blockIdx.y, z = box.z0 + blockIdx.z;
-    const int64_t i = (int64_t)z * plane + (int64_t)y * pitch + x;
-
-    const int s = __float_as_int(GET_COMP(0, 0, 0, STATE));
-    if (s != LIQUID) {
-#pragma unroll
-        for (int m = 0; m < 19; ++m) PUT(m) = GET_COMP(0, 0, 0, m);
-        switch (s) {
-        case WEST_NOSLIP:
-            PUT(E)  = GET_COMP(1, 0,  0, W);
-            PUT(NE) = GET_COMP(1, 1,  0, SW);
-            PUT(SE) = GET_COMP(1,-1,  0, NW);
-            PUT(TE) = GET_COMP(1, 0,  1, BW);
-            PUT(BE) = GET_COMP(1, 0, -1, TW);
-            break;
-        case EAST_NOSLIP:
-            PUT(W)  = GET_COMP(-1, 0, 0, E);
-            PUT(NW) = GET_COMP(-1, 0, 1, SE);
-            PUT(SW) = GET_COMP(-1,-1, 0, NE);
-            PUT(TW) = GET_COMP(-1, 0, 1, BE);
-            PUT(BW) = GET_COMP(-1, 0,-1, TE);
-            break;
-        case TOP:
-            PUT(B)  = GET_COMP(0, 0,-1, T);
-            PUT(BE) = GET_COMP(1, 0,-1, TW);
-            PUT(BW) = GET_COMP(-1,0,-1, TE);
-            PUT(BN) = GET_COMP(0, 1,-1, TS);
-            PUT(BS) = GET_COMP(0,-1,-1, TN);
-            break;
-        case BOTTOM:
-            PUT(T)  = GET_COMP(0, 0, 1, B);
-            PUT(TE) = GET_COMP(1, 0, 1, BW);
-            PUT(TW) = GET_COMP(-1,0, 1, BE);
-            PUT(TN) = GET_COMP(0, 1, 1, BS);
-            PUT(TS) = GET_COMP(0,-1, 1, BN);
-            break;
-        case NORTH_ACC: {
-            const float w_1 = 0.01f;
-            PUT(S)  = GET_COMP(0,-1, 0, N);
-            PUT(SE) = GET_COMP(1,-1, 0, NW) + 6.0f * w_1 * 0.1f;
-            PUT(SW) = GET_COMP(-1,-1,0, NE) - 6.0f * w_1 * 0.1f;
-            PUT(TS) = GET_COMP(0,-1, 1, BN);
-            PUT(BS) = GET_COMP(0,-1,-1, TN);
-            break;
-        }
-        case SOUTH_NOSLIP:
-            PUT(N)  = GET_COMP(0, 1, 0, S);
-            PUT(NE) = GET_COMP(1, 1, 0, SW);
-            PUT(NW) = GET_COMP(-1,1, 0, SE);
-            PUT(TN) = GET_COMP(0, 1, 1, BS);
-            PUT(BN) = GET_COMP(0, 1,-1, TS);
-            break;
-        }
-        return;
-    }
-
-    const float omega     = (float)(1.0 / 1.7);
-    const float omega_trm = 1.0f - omega;
-    const float omega_w0  = (float)(3.0 * 1.0 / 3.0)  * omega;
-    const float omega_w1  = (float)(3.0 * 1.0 / 18.0) * omega;
-    const float omega_w2  = (float)(3.0 * 1.0 / 36.0) * omega;
-    const float one_third = (float)(1.0 / 3.0);
-
-    // every population is read exactly once (pull scheme)
-    const float fC  = GET_COMP( 0, 0, 0, C);
-    const float fN  = GET_COMP( 0,-1, 0, N),  fS  = GET_COMP( 0, 1, 0, S);
-    const float fE  = GET_COMP(-1, 0, 0, E),  fW  = GET_COMP( 1, 0, 0, W);
-    const float fT  = GET_COMP( 0, 0,-1, T),  fB  = GET_COMP( 0, 0, 1, B);
-    const float fNW = GET_COMP( 1,-1, 0, NW), fSW = GET_COMP( 1, 1, 0, SW);
-    const float fNE = GET_COMP(-1,-1, 0, NE), fSE = GET_COMP(-1, 1, 0, SE);
-    const float fTW = GET_COMP( 1, 0,-1, TW), fBW = GET_COMP( 1, 0, 1, BW);
-    const float fTE = GET_COMP(-1, 0,-1, TE), fBE = GET_COMP(-1, 0, 1, BE);
-    const float fTN = GET_COMP( 0,-1,-1, TN), fBN = GET_COMP( 0,-1, 1, BN);
-    const float fTS = GET_COMP( 0, 1,-1, TS), fBS = GET_COMP( 0, 1, 1, BS);
-
-    float velX, velY, velZ;
-    velX = fE + fNE + fSE + fTE + fBE;
-    velY = fN + fNW + fTN + fBN;
-    velZ = fT + fTS + fTW;
-
-    const float rho = fC + fS + fW + fB + fSW + fBS + fBW + velX + velY + velZ;
-    velX = velX - fW - fNW - fSW - fTW - fBW;
-    velY = velY + fNE - fS - fSW - fSE - fTS - fBS;
-    velZ = velZ + fTN + fTE - fB - fBN - fBS - fBW - fBE;
-
-    if (MACRO) {
-        PUT(DENSITY) = rho;
-        PUT(VELX) = velX;
-        PUT(VELY) = velY;
-        PUT(VELZ) = velZ;
-    }
-
-    const float dir_indep_trm = one_third * rho - 0.5f * (velX * velX + velY * velY + velZ * velZ);
-
-    PUT(C)  = omega_trm * fC + omega_w0 * (dir_indep_trm);
-
-    PUT(NW) = omega_trm * fNW + omega_w2 * (dir_indep_trm - (velX - velY) + 1.5f * SQR(velX - velY));
-    PUT(SE) = omega_trm * fSE + omega_w2 * (dir_indep_trm + (velX - velY) + 1.5f * SQR(velX - velY));
-    PUT(NE) = omega_trm * fNE + omega_w2 * (dir_indep_trm + (velX + velY) + 1.5f * SQR(velX + velY));
-    PUT(SW) = omega_trm * fSW + omega_w2 * (dir_indep_trm - (velX + velY) + 1.5f * SQR(velX + velY));
-
-    PUT(TW) = omega_trm * fTW + omega_w2 * (dir_indep_trm - (velX - velZ) + 1.5f * SQR(velX - velZ));
-    PUT(BE) = omega_trm * fBE + omega_w2 * (dir_indep_trm + (velX - velZ) + 1.5f * SQR(velX - velZ));
-    PUT(TE) = omega_trm * fTE + omega_w2 * (dir_indep_trm + (velX + velZ) + 1.5f * SQR(velX + velZ));
-    PUT(BW) = omega_trm * fBW + omega_w2 * (dir_indep_trm - (velX + velZ) + 1.5f * SQR(velX + velZ));
-
-    PUT(TS) = omega_trm * fTS + omega_w2 * (dir_indep_trm - (velY - velZ) + 1.5f * SQR(velY - velZ));
-    PUT(BN) = omega_trm * fBN + omega_w2 * (dir_indep_trm + (velY - velZ) + 1.5f * SQR(velY - velZ));
-    PUT(TN) = omega_trm * fTN + omega_w2 * (dir_indep_trm + (velY + velZ) + 1.5f * SQR(velY + velZ));
-    PUT(BS) = omega_trm * fBS + omega_w2 * (dir_indep_trm - (velY + velZ) + 1.5f * SQR(velY + velZ));
-
-    PUT(N) = omega_trm * fN + omega_w1 * (dir_indep_trm + velY + 1.5f * SQR(velY));
-    PUT(S) = omega_trm * fS + omega_w1 * (dir_indep_trm - velY + 1.5f * SQR(velY));
-    PUT(E) = omega_trm * fE + omega_w1 * (dir_indep_trm + velX + 1.5f * SQR(velX));
-    PUT(W) = omega_trm * fW + omega_w1 * (dir_indep_trm - velX + 1.5f * SQR(velX));
-    PUT(T) = omega_trm * fT + omega_w1 * (dir_indep_trm + velZ + 1.5f * SQR(velZ));
-    PUT(B) = omega_trm * fB + omega_w1 * (dir_indep_trm - velZ + 1.5f * SQR(velZ));
-}
-
-// Variant with the loads hoisted: the 19 pulled populations are requested together with the state,
-// BEFORE the wall test, so a warp waits for one DRAM round trip per cell instead of two (state,
-// then populations). The loads are volatile asm so that neither nvcc nor ptxas sinks them back
-// below the branch. Wall cells (faces only) pull values they do not use — every address is valid,
+// The 19 pulled populations are requested together with the state, BEFORE the wall test, so a warp
+// waits for one DRAM round trip per cell instead of two (state, then populations: the first version of
+// this kernel did that and reached 80 % instead of 91 % of the copy bandwidth, profiles/r1s_tuning.md).
+// The loads are volatile asm so that neither nvcc nor ptxas sinks them back below the branch. Wall cells (faces only) pull values they do not use — every address is valid,
 // the ghost ring is part of the array. R cells per thread along y: all 19 * R loads are in flight
-// at once. Same expression trees as lbm_kernel, term by term.
+// at once.
 __device__ __forceinline__ float ldg_stream(const float *p)
 {
     float v;
@@ -355,14 +229,7 @@ int sweep_lbm(b200geo_grid *g, const Box& box, bool store_macroscopic, cudaStrea
         if (store_macroscopic) lbm_kernel_early<true, R, BX><<<grid, BX, 0, s>>>(src, dst, L.pitch, L.plane, mstride, box); \
         else lbm_kernel_early<false, R, BX><<<grid, BX, 0, s>>>(src, dst, L.pitch, L.plane, mstride, box); \
     } while (0)
-    if (variant == 0) {
-        int bx = g_tuning.lbm_block >= 32 && g_tuning.lbm_block <= 128 ? g_tuning.lbm_block : 128;
-        dim3 grid((nx + bx - 1) / bx, ny, nz);
-        if (store_macroscopic)
-            lbm_kernel<true><<<grid, bx, 0, s>>>(src, dst, L.pitch, L.plane, mstride, box);
-        else
-            lbm_kernel<false><<<grid, bx, 0, s>>>(src, dst, L.pitch, L.plane, mstride, box);
-    } else if (variant == 2) {
+    if (variant == 2) {
         if (g_tuning.lbm_block == 256) LBM_LAUNCH_EARLY(2, 256); else LBM_LAUNCH_EARLY(2, 128);
     } else {
         if (g_tuning.lbm_block == 256) LBM_LAUNCH_EARLY(1, 256); else LBM_LAUNCH_EARLY(1, 128);

@@ -242,19 +242,6 @@ template<typename REAL> struct alignas(2 * sizeof(REAL)) Pos2 { REAL x, y; };
 __device__ __forceinline__ float fma_any(float a, float b, float c) { return __fmaf_rn(a, b, c); }
 __device__ __forceinline__ double fma_any(double a, double b, double c) { return __fma_rn(a, b, c); }
 
-// four consecutive slots (16-byte aligned: capacity and slot index are multiples of four)
-__device__ __forceinline__ void load4(const float *p, float (&v)[4])
-{
-    float4 t = *reinterpret_cast<const float4 *>(p);
-    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
-}
-
-__device__ __forceinline__ void load4(const double *p, double (&v)[4])
-{
-    double2 a = *reinterpret_cast<const double2 *>(p), b = *reinterpret_cast<const double2 *>(p + 2);
-    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
-}
-
 // smallest REAL >= v: for a REAL-valued p, (double)p >= v <=> p >= round_up(v) and (double)p < v <=> p < round_up(v),
 // so the reference's double-precision position check can be done on the particles' own type
 __device__ __forceinline__ void round_up(double v, float& r) { r = __double2float_ru(v); }

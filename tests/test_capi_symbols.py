@@ -26,6 +26,20 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), name
 
 
+@pytest.mark.parametrize("compiler,flags", [("gcc", ["-std=c99", "-x", "c"]), ("g++", ["-std=c++11", "-x", "c++"])])
+def test_header_is_plain_c_and_cpp(tmp_path, compiler, flags):
+    """the C ABI header has no C++ or torch types in it: it compiles as C99 and as C++11 on its own"""
+    import shutil
+    import subprocess
+    if not shutil.which(compiler):
+        pytest.skip(compiler + " not installed")
+    src = tmp_path / "probe.c"
+    src.write_text('#include "b200geo.h"\nint probe(void) { b200geo_grid_desc d; d.n_members = 1; return (int)sizeof(d) + B200GEO_OK; }\n')
+    res = subprocess.run([compiler] + flags + ["-Wall", "-Werror", "-pedantic", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), str(src)],
+                         capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+
+
 def test_version_and_error_text():
     lib = capi.lib()
     assert b"b200geo" in lib.b200geo_version()
