@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(128)
 force_kernel(const int32_t *__restrict__ cnt_old, const REAL *__restrict__ part_old, const int32_t *__restrict__ cnt_new,
              REAL *__restrict__ part_new, BoxDims D, int z0, int runs_per_row, REAL dt, REAL rc2)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     const int cap = D.cap;
     REAL *spos = reinterpret_cast<REAL *>(smem_raw);            // [(G + 2) * 9][3][cap]
     int *scnt = reinterpret_cast<int *>(spos + (G + 2) * 9 * 3 * cap);  // [(G + 2) * 9]
