@@ -256,6 +256,19 @@ int b200geo_boxgrid_halo_block(const b200geo_boxgrid *g, int array, int side, in
                                uint64_t *bytes);
 int b200geo_boxgrid_halo_mark_valid(b200geo_boxgrid *g, int side, int width);
 
+/* Slab group of container grids (slabs of containers along z, in order; faces towards a neighbour PEER): one
+ * host thread, one slab per GPU. Per sweep every slab pulls its neighbours' boundary container planes (counts
+ * and particles: one contiguous block each) straight into its ghost planes over NVLink, then re-bins / updates.
+ * Replaces the MPI PatchLink pair for BoxCell grids; called by B200StripingSimulator<BoxCell<...> >. */
+typedef struct b200geo_boxgroup b200geo_boxgroup;
+int b200geo_boxgroup_create(b200geo_boxgrid *const *grids, int n, b200geo_boxgroup **out);
+int b200geo_boxgroup_destroy(b200geo_boxgroup *grp);
+int b200geo_boxgroup_step(b200geo_boxgroup *grp, const b200geo_nbody_params *params, uint32_t first_nano_step,
+                          uint32_t n_steps);
+int b200geo_boxgroup_sync(b200geo_boxgroup *grp);
+/* out[0] = exchanges so far, out[1] = bytes shipped between devices */
+int b200geo_boxgroup_stats(const b200geo_boxgroup *grp, uint64_t out[2]);
+
 /* ---- statistics: Simulator::gatherStatistics / Chronometer (misc/chronometer.h:142-150) ---- */
 /* out[0] = device seconds spent in update kernels (TimeComputeInner), out[1] = seconds in ghost
  * refresh / halo copies (TimeComputeGhost + TimeCommunication), out[2] = number of sweeps. Uses

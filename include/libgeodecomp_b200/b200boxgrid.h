@@ -61,9 +61,39 @@ public:
         box(box),
         edgeCell(edgeCell),
         device(device),
-        handle(0)
+        handle(0),
+        lowPeer(false),
+        highPeer(false)
     {
         create();
+    }
+
+    /* one slab (along z) of a larger container grid: a face towards a neighbouring slab is a ghost plane of
+     * that neighbour's containers (B200StripingSimulator) */
+    B200BoxGrid(const CoordBox<3>& box, const CELL& edgeCell, int device, bool lowPeer, bool highPeer) :
+        Base(box.dimensions),
+        box(box),
+        edgeCell(edgeCell),
+        device(device),
+        handle(0),
+        lowPeer(lowPeer),
+        highPeer(highPeer)
+    {
+        create();
+    }
+
+    b200geo_boxgrid *raw()
+    {
+        return handle;
+    }
+
+    static b200geo_nbody_params parameters()
+    {
+        b200geo_nbody_params p;
+        p.dt = Binding::dt();
+        p.cutoff = Binding::cutoff();
+        p.nano_steps = APITraits::SelectNanoSteps<PARTICLE>::VALUE;
+        return p;
     }
 
     virtual ~B200BoxGrid()
@@ -160,10 +190,7 @@ public:
     /* n sweeps: re-bin (nanoStep % NANO_STEPS == 0) or copy, update every particle; swap */
     void update(unsigned firstNanoStep, unsigned sweeps)
     {
-        b200geo_nbody_params p;
-        p.dt = Binding::dt();
-        p.cutoff = Binding::cutoff();
-        p.nano_steps = APITraits::SelectNanoSteps<PARTICLE>::VALUE;
+        b200geo_nbody_params p = parameters();
         B200Helpers::check(b200geo_boxgrid_step(handle, &p, firstNanoStep, sweeps, 0));
     }
 
@@ -192,6 +219,8 @@ private:
     CELL edgeCell;
     int device;
     b200geo_boxgrid *handle;
+    bool lowPeer;
+    bool highPeer;
 
     void local(const Coord<3>& c, int32_t *o) const
     {
@@ -208,6 +237,12 @@ private:
             desc.dim[i] = box.dimensions[i];
             desc.ghost_mode[i][0] = desc.ghost_mode[i][1] = B200GEO_GHOST_EDGE;
             desc.cell_origin[i] = box.origin[i];
+        }
+        if (lowPeer) {
+            desc.ghost_mode[2][0] = B200GEO_GHOST_PEER;
+        }
+        if (highPeer) {
+            desc.ghost_mode[2][1] = B200GEO_GHOST_PEER;
         }
         desc.capacity = N;
         desc.real_bytes = (int)sizeof(Real);

@@ -79,6 +79,16 @@ public:
         b200geo_group_destroy(group);
     }
 
+    /* ghost zone width = sweeps between two halo exchanges; the temporal-blocked Jacobi kernels fuse the
+     * sweeps of one round into a single launch, so 2 is their default */
+    static int defaultGhostWidth()
+    {
+        int k = B200KernelBinding<CELL>::kernel();
+        bool jacobi = k == B200GEO_KERNEL_JACOBI6 || k == B200GEO_KERNEL_JACOBI7 || k == B200GEO_KERNEL_JACOBI27;
+        int radius = APITraits::SelectStencil<CELL>::Value::RADIUS;
+        return std::max(radius, jacobi ? 2 : 1);
+    }
+
     std::size_t numSlabs() const
     {
         return slabs.size();
@@ -301,13 +311,177 @@ private:
     }
 };
 
+/* The same for grids of BoxCell containers (short-range n-body): slabs of containers along z, each a
+ * B200BoxGrid on its own GPU; per sweep a slab pulls its neighbours' boundary container planes into its ghost
+ * planes (b200geo_boxgroup_*) — the ghost plane is the particle migration message, BoxCell pulls from its
+ * neighbourhood (storage/boxcell.h:123-138). */
+template<typename PARTICLE, int N>
+class B200StripedBoxGrid : public GridBase<BoxCell<FixedArray<PARTICLE, N> >, 3>
+{
+public:
+    typedef BoxCell<FixedArray<PARTICLE, N> > CELL;
+    typedef GridBase<CELL, 3> Base;
+    typedef B200BoxGrid<PARTICLE, N> SlabType;
+    static const int DIM = 3;
+
+    B200StripedBoxGrid(const CoordBox<3>& box, const std::vector<int>& devices, int /* ghost width: one container */,
+                       const CELL& edgeCell = CELL()) :
+        Base(box.dimensions),
+        box(box),
+        edgeCell(edgeCell),
+        group(0)
+    {
+        int n = (int)devices.size();
+        if (n < 1) {
+            throw std::invalid_argument("B200StripedBoxGrid needs at least one device");
+        }
+        int extent = box.dimensions[2];
+        if (extent / n < 1) {
+            throw std::invalid_argument("slab thinner than the ghost zone");
+        }
+        std::vector<b200geo_boxgrid*> handles;
+        for (int s = 0; s <= n; ++s) {
+            bounds.push_back(box.origin[2] + (int)(((long)extent * s) / n));
+        }
+        for (int s = 0; s < n; ++s) {
+            CoordBox<3> slabBox = box;
+            slabBox.origin[2] = bounds[s];
+            slabBox.dimensions[2] = bounds[s + 1] - bounds[s];
+            slabs.push_back(std::unique_ptr<SlabType>(new SlabType(slabBox, edgeCell, devices[s], n > 1 && s > 0, n > 1 && s < n - 1)));
+            handles.push_back(slabs.back()->raw());
+        }
+        B200Helpers::check(b200geo_boxgroup_create(handles.data(), n, &group));
+    }
+
+    virtual ~B200StripedBoxGrid()
+    {
+        b200geo_boxgroup_destroy(group);
+    }
+
+    static int defaultGhostWidth()
+    {
+        return 1;
+    }
+
+    std::size_t numSlabs() const
+    {
+        return slabs.size();
+    }
+
+    virtual void resize(const CoordBox<3>&)
+    {
+        throw std::logic_error("B200StripedBoxGrid cannot be resized");
+    }
+
+    virtual void set(const Coord<3>& coord, const CELL& cell)
+    {
+        slabs[owner(coord.z())]->set(coord, cell);
+    }
+
+    virtual void set(const Streak<3>& streak, const CELL *cells)
+    {
+        slabs[owner(streak.origin.z())]->set(streak, cells);
+    }
+
+    virtual CELL get(const Coord<3>& coord) const
+    {
+        return slabs[owner(coord.z())]->get(coord);
+    }
+
+    virtual void get(const Streak<3>& streak, CELL *cells) const
+    {
+        slabs[owner(streak.origin.z())]->get(streak, cells);
+    }
+
+    virtual void setEdge(const CELL& cell)
+    {
+        for (std::size_t s = 0; s < slabs.size(); ++s) {
+            slabs[s]->setEdge(cell);
+        }
+        edgeCell = cell;
+    }
+
+    virtual const CELL& getEdge() const
+    {
+        return edgeCell;
+    }
+
+    virtual CoordBox<3> boundingBox() const
+    {
+        return box;
+    }
+
+    void update(unsigned firstNanoStep, unsigned sweeps)
+    {
+        b200geo_nbody_params p = SlabType::parameters();
+        B200Helpers::check(b200geo_boxgroup_step(group, &p, firstNanoStep, sweeps));
+    }
+
+    void sync() const
+    {
+        B200Helpers::check(b200geo_boxgroup_sync(group));
+    }
+
+    std::pair<unsigned long long, unsigned long long> exchangeStatistics() const
+    {
+        uint64_t out[2] = {0, 0};
+        B200Helpers::check(b200geo_boxgroup_stats(group, out));
+        return std::make_pair((unsigned long long)out[0], (unsigned long long)out[1]);
+    }
+
+protected:
+    virtual void saveMemberImplementation(char *, MemoryLocation::Location, const Selector<CELL>&,
+                                          const typename Region<3>::StreakIterator&,
+                                          const typename Region<3>::StreakIterator&) const
+    {
+        throw std::logic_error("B200StripedBoxGrid: containers have no selectable members");
+    }
+
+    virtual void loadMemberImplementation(const char *, MemoryLocation::Location, const Selector<CELL>&,
+                                          const typename Region<3>::StreakIterator&,
+                                          const typename Region<3>::StreakIterator&)
+    {
+        throw std::logic_error("B200StripedBoxGrid: containers have no selectable members");
+    }
+
+private:
+    CoordBox<3> box;
+    CELL edgeCell;
+    b200geo_boxgroup *group;
+    std::vector<std::unique_ptr<SlabType> > slabs;
+    std::vector<int> bounds;
+
+    std::size_t owner(int z) const
+    {
+        if (z < bounds.front() || z >= bounds.back()) {
+            throw std::out_of_range("coordinate outside the grid");
+        }
+        std::size_t s = 0;
+        while (z >= bounds[s + 1]) {
+            ++s;
+        }
+        return s;
+    }
+};
+
+/* which striped grid backs a cell type */
+template<typename CELL>
+struct B200StripedGridSelector {
+    typedef B200StripedGrid<CELL> Type;
+};
+
+template<typename PARTICLE, int N>
+struct B200StripedGridSelector<BoxCell<FixedArray<PARTICLE, N> > > {
+    typedef B200StripedBoxGrid<PARTICLE, N> Type;
+};
+
 template<typename CELL>
 class B200StripingSimulator : public MonolithicSimulator<CELL>
 {
 public:
     typedef typename MonolithicSimulator<CELL>::Topology Topology;
     typedef typename Steerer<CELL>::SteererFeedback SteererFeedback;
-    typedef B200StripedGrid<CELL> GridType;
+    typedef typename B200StripedGridSelector<CELL>::Type GridType;
     typedef GridBase<CELL, Topology::DIM> GridBaseType;
     static const int DIM = Topology::DIM;
     static const unsigned NANO_STEPS = APITraits::SelectNanoSteps<CELL>::VALUE;
@@ -335,14 +509,9 @@ public:
         return ret;
     }
 
-    /* ghost zone width = sweeps between two halo exchanges; the temporal-blocked Jacobi kernels fuse the
-     * sweeps of one round into a single launch, so 2 is their default */
     static int defaultGhostWidth()
     {
-        int k = B200KernelBinding<CELL>::kernel();
-        bool jacobi = k == B200GEO_KERNEL_JACOBI6 || k == B200GEO_KERNEL_JACOBI7 || k == B200GEO_KERNEL_JACOBI27;
-        int radius = APITraits::SelectStencil<CELL>::Value::RADIUS;
-        return std::max(radius, jacobi ? 2 : 1);
+        return GridType::defaultGhostWidth();
     }
 
     explicit B200StripingSimulator(

@@ -101,6 +101,11 @@ SYMBOLS = [
     ("b200geo_boxgrid_halo_block", ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                                   ctypes.POINTER(_vp), ctypes.POINTER(ctypes.c_uint64)]),
     ("b200geo_boxgrid_halo_mark_valid", ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int]),
+    ("b200geo_boxgroup_create", ctypes.c_int, [ctypes.POINTER(_vp), ctypes.c_int, ctypes.POINTER(_vp)]),
+    ("b200geo_boxgroup_destroy", ctypes.c_int, [_vp]),
+    ("b200geo_boxgroup_step", ctypes.c_int, [_vp, ctypes.POINTER(NBodyParams), ctypes.c_uint32, ctypes.c_uint32]),
+    ("b200geo_boxgroup_sync", ctypes.c_int, [_vp]),
+    ("b200geo_boxgroup_stats", ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_uint64)]),
     ("b200geo_stats_enable", ctypes.c_int, [_vp, ctypes.c_int]),
     ("b200geo_stats", ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_double)]),
 ]
@@ -337,6 +342,40 @@ class SlabGroup:
     def stats(self):
         out = (ctypes.c_uint64 * 2)()
         check(lib().b200geo_group_stats(self._h, out))
+        return {"exchanges": int(out[0]), "bytes": int(out[1])}
+
+
+class BoxSlabGroup:
+    """b200geo_boxgroup: slabs of BoxCell containers on several GPUs of this box, one host thread"""
+
+    def __init__(self, grids):
+        self._h = None
+        self.grids = list(grids)
+        arr = (ctypes.c_void_p * len(self.grids))(*[g._h for g in self.grids])
+        h = ctypes.c_void_p()
+        check(lib().b200geo_boxgroup_create(arr, len(self.grids), ctypes.byref(h)))
+        self._h = h
+
+    def close(self):
+        if self._h is not None and _lib is not None:
+            _lib.b200geo_boxgroup_destroy(self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def step(self, params, n_steps=1, first_nano_step=0):
+        check(lib().b200geo_boxgroup_step(self._h, ctypes.byref(params), first_nano_step, n_steps))
+
+    def sync(self):
+        check(lib().b200geo_boxgroup_sync(self._h))
+
+    def stats(self):
+        out = (ctypes.c_uint64 * 2)()
+        check(lib().b200geo_boxgroup_stats(self._h, out))
         return {"exchanges": int(out[0]), "bytes": int(out[1])}
 
 

@@ -730,4 +730,135 @@ int b200geo_boxgrid_halo_mark_valid(b200geo_boxgrid *g, int side, int width)
     return B200GEO_OK;
 }
 
+/* ---- slab groups of container grids: one host thread, several GPUs (twin of csrc/group.cu) ------------- */
+
+}
+
+#define B200GEO_BOXGROUP_MAX 16
+
+struct b200geo_boxgroup {
+    int n;
+    b200geo_boxgrid *g[B200GEO_BOXGROUP_MAX];
+    cudaStream_t stream[B200GEO_BOXGROUP_MAX];
+    cudaEvent_t done[B200GEO_BOXGROUP_MAX];
+    uint64_t exchanges, bytes_moved;
+};
+
+extern "C" {
+
+int b200geo_boxgroup_create(b200geo_boxgrid *const *grids, int n, b200geo_boxgroup **out)
+{
+    if (!grids || !out || n < 1 || n > B200GEO_BOXGROUP_MAX) return fail(B200GEO_ERR_INVALID, "bad slab group");
+    for (int i = 0; i < n; ++i) {
+        const b200geo_boxgrid *g = grids[i];
+        if (!g) return fail(B200GEO_ERR_INVALID, "null grid in slab group");
+        if (g->d[0] != grids[0]->d[0] || g->d[1] != grids[0]->d[1] || g->cap != grids[0]->cap || g->real != grids[0]->real)
+            return fail(B200GEO_ERR_INVALID, "slabs of one group must have the same cross-section, capacity and particle type");
+        bool low = n > 1 && i > 0, high = n > 1 && i < n - 1;
+        if ((g->desc.ghost_mode[2][0] == B200GEO_GHOST_PEER) != low || (g->desc.ghost_mode[2][1] == B200GEO_GHOST_PEER) != high)
+            return fail(B200GEO_ERR_INVALID, "slab faces towards a neighbour must be PEER ghost layers, outer faces must not");
+    }
+    b200geo_boxgroup *grp = new (std::nothrow) b200geo_boxgroup();
+    if (!grp) return fail(B200GEO_ERR_NOMEM, "out of host memory");
+    memset(grp, 0, sizeof(*grp));
+    grp->n = n;
+    for (int i = 0; i < n; ++i) grp->g[i] = grids[i];
+    for (int i = 0; i < n; ++i) {
+        int dev = grids[i]->device;
+        cudaError_t e = cudaSetDevice(dev);
+        for (int j = i - 1; j <= i + 1 && e == cudaSuccess; j += 2) {
+            if (j < 0 || j >= n || grids[j]->device == dev) continue;
+            int can = 0;
+            if (cudaDeviceCanAccessPeer(&can, dev, grids[j]->device) == cudaSuccess && can) {
+                cudaError_t p = cudaDeviceEnablePeerAccess(grids[j]->device, 0);
+                if (p != cudaSuccess && p != cudaErrorPeerAccessAlreadyEnabled) e = p;
+                cudaGetLastError();
+            }
+        }
+        if (e == cudaSuccess) e = cudaStreamCreate(&grp->stream[i]);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&grp->done[i], cudaEventDisableTiming);
+        if (e != cudaSuccess) {
+            b200geo_boxgroup_destroy(grp);
+            return check_cuda(e, "slab group setup");
+        }
+    }
+    *out = grp;
+    return B200GEO_OK;
+}
+
+int b200geo_boxgroup_destroy(b200geo_boxgroup *grp)
+{
+    if (!grp) return B200GEO_OK;
+    for (int i = 0; i < grp->n; ++i) {
+        cudaSetDevice(grp->g[i]->device);
+        if (grp->stream[i]) { cudaStreamSynchronize(grp->stream[i]); cudaStreamDestroy(grp->stream[i]); }
+        if (grp->done[i]) cudaEventDestroy(grp->done[i]);
+    }
+    delete grp;
+    return B200GEO_OK;
+}
+
+/* n_steps x { pull the neighbours' boundary container planes (counts and particles, one contiguous block
+ * each) into the ghost planes over NVLink; re-bin / update every slab; swap }. BoxCell pulls its particles
+ * from the neighbourhood, so the ghost plane IS the migration message (storage/boxcell.h:123-138). */
+int b200geo_boxgroup_step(b200geo_boxgroup *grp, const b200geo_nbody_params *params, uint32_t first_nano_step, uint32_t n_steps)
+{
+    if (!grp || !params) return fail(B200GEO_ERR_INVALID, "null argument");
+    for (uint32_t t = 0; t < n_steps; ++t) {
+        if (grp->n > 1) {
+            for (int i = 0; i < grp->n; ++i) {
+                B200GEO_CUDA(cudaSetDevice(grp->g[i]->device));
+                B200GEO_CUDA(cudaEventRecord(grp->done[i], grp->stream[i]));
+            }
+            for (int i = 0; i < grp->n; ++i) {
+                b200geo_boxgrid *g = grp->g[i];
+                B200GEO_CUDA(cudaSetDevice(g->device));
+                for (int side = 0; side < 2; ++side) {
+                    int j = side == 0 ? i - 1 : i + 1;
+                    if (j < 0 || j >= grp->n) continue;
+                    b200geo_boxgrid *peer = grp->g[j];
+                    B200GEO_CUDA(cudaStreamWaitEvent(grp->stream[i], grp->done[j], 0));
+                    for (int array = 0; array < 2; ++array) {
+                        void *src = 0, *dst = 0;
+                        uint64_t bytes = 0, dst_bytes = 0;
+                        // our low-side ghost plane = the low neighbour's HIGH boundary plane, and vice versa
+                        int rc = b200geo_boxgrid_halo_block(peer, array, 1 - side, 0, 0, &src, &bytes);
+                        if (rc) return rc;
+                        rc = b200geo_boxgrid_halo_block(g, array, side, 1, 0, &dst, &dst_bytes);
+                        if (rc) return rc;
+                        if (bytes != dst_bytes) return fail(B200GEO_ERR_INVALID, "slabs of one group must have the same cross-section");
+                        B200GEO_CUDA(cudaMemcpyPeerAsync(dst, g->device, src, peer->device, bytes, grp->stream[i]));
+                        grp->bytes_moved += bytes;
+                    }
+                    g->peer_valid[side] = 1;
+                }
+            }
+            ++grp->exchanges;
+        }
+        for (int i = 0; i < grp->n; ++i) {
+            int rc = b200geo_boxgrid_step(grp->g[i], params, first_nano_step + t, 1, grp->stream[i]);
+            if (rc) return rc;
+        }
+    }
+    return B200GEO_OK;
+}
+
+int b200geo_boxgroup_sync(b200geo_boxgroup *grp)
+{
+    if (!grp) return fail(B200GEO_ERR_INVALID, "null group");
+    for (int i = 0; i < grp->n; ++i) {
+        B200GEO_CUDA(cudaSetDevice(grp->g[i]->device));
+        B200GEO_CUDA(cudaStreamSynchronize(grp->stream[i]));
+    }
+    return B200GEO_OK;
+}
+
+int b200geo_boxgroup_stats(const b200geo_boxgroup *grp, uint64_t out[2])
+{
+    if (!grp || !out) return fail(B200GEO_ERR_INVALID, "null argument");
+    out[0] = grp->exchanges;
+    out[1] = grp->bytes_moved;
+    return B200GEO_OK;
+}
+
 }

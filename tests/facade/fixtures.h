@@ -122,6 +122,40 @@ public:
 };
 
 
+/* n-body: BoxCell<FixedArray<LJParticle<REAL>, 32> > through the reference's SerialSimulator and through
+ * B200Simulator (container grid on the device): same occupancy, bit-identical particles */
+template<typename REAL>
+class ParticleInitializer : public SimpleInitializer<BoxCell<FixedArray<LJParticle<REAL>, NBODY_CAPACITY> > >
+{
+public:
+    typedef BoxCell<FixedArray<LJParticle<REAL>, NBODY_CAPACITY> > Cell;
+
+    ParticleInitializer(const Coord<3>& dim, unsigned steps) : SimpleInitializer<Cell>(dim, steps) {}
+
+    virtual void grid(GridBase<Cell, 3> *ret)
+    {
+        CoordBox<3> box = ret->boundingBox();
+        Coord<3> dim = this->gridDimensions();
+        double e = NBodyParams::cellEdge();
+        for (CoordBox<3>::Iterator i = box.begin(); i != box.end(); ++i) {
+            Cell cell(FloatCoord<3>(i->x() * e, i->y() * e, i->z() * e), FloatCoord<3>(e, e, e));
+            uint64_t id = i->toIndex(dim);
+            int n = 8 + (int)(splitmix(id) % 9);
+            for (int p = 0; p < n; ++p) {
+                LJParticle<REAL> particle;
+                for (int k = 0; k < 3; ++k) {
+                    // well separated sites inside the container, fast enough to cross faces within a few steps
+                    double site = ((p >> k) & 1) * 0.5 + (p / 8) * 0.25 + 0.125 + 0.05 * uniform(id * 1000 + p * 8 + k);
+                    particle.pos[k] = (REAL)(((*i)[k] + site) * e);
+                    particle.vel[k] = (REAL)(16.0 * (uniform(id * 1000 + p * 8 + k + 4) - 0.5));
+                }
+                cell << particle;
+            }
+            ret->set(*i, cell);
+        }
+    }
+};
+
 /* The reference's own concrete Writer (io/serialbovwriter.h:20-84 -> BOVOutput::writeGrid, io/bovoutput.h:65-98, which
  * pulls one member row by row through GridBase::saveMemberUnchecked) on the reference's simulator and on SIM: the
  * .bov headers and the .data bricks must be the same bytes. */

@@ -175,6 +175,41 @@ static void testRegionAndMemberStreamsAcrossSlabs()
                 (a == b && c == d && da.size() == db.size()) ? "byte-identical" : "DIFFERENT");
 }
 
+template<typename REAL>
+static void compareNBodyStriped(const char *name, const Coord<3>& dim, unsigned steps, int slabs)
+{
+    typedef BoxCell<FixedArray<LJParticle<REAL>, NBODY_CAPACITY> > Cell;
+    NBodyParams::dt() = 0.01;
+    SerialSimulator<Cell> ref(new ParticleInitializer<REAL>(dim, steps));
+    B200StripingSimulator<Cell> dev(new ParticleInitializer<REAL>(dim, steps), devicesFor(slabs));
+    ref.run();
+    dev.run();
+    const GridBase<Cell, 3> *a = ref.getGrid();
+    const GridBase<Cell, 3> *b = dev.getGrid();
+    std::size_t particles = 0, bad = 0;
+    CoordBox<3> box(Coord<3>(), dim);
+    for (CoordBox<3>::Iterator i = box.begin(); i != box.end(); ++i) {
+        Cell ca = a->get(*i), cb = b->get(*i);
+        if (ca.size() != cb.size()) {
+            ++bad;
+            continue;
+        }
+        particles += ca.size();
+        for (std::size_t p = 0; p < ca.size(); ++p) {
+            if (std::memcmp(ca[p].pos, cb[p].pos, sizeof(ca[p].pos)) || std::memcmp(ca[p].vel, cb[p].vel, sizeof(ca[p].vel))) {
+                ++bad;
+            }
+        }
+    }
+    CHECK(bad == 0);
+    CHECK(particles > 0);
+    CHECK(ref.getStep() == dev.getStep());
+    std::pair<unsigned long long, unsigned long long> st = dev.stripedGrid().exchangeStatistics();
+    CHECK(slabs == 1 || st.first >= steps);
+    std::printf("%-14s %d slab(s) of containers: %zu particles after %u steps, %s (%llu exchanges)\n", name, slabs, particles, steps,
+                bad == 0 ? "bit-identical to SerialSimulator" : "DIFFERENT", st.first);
+}
+
 int main()
 {
     try {
@@ -191,6 +226,10 @@ int main()
         compareStriped<ConwayTorus, SeededInitializer<ConwayTorus>, 2>("ConwayTorus", Coord<2>(64, 20), 25, 2, 2);
         compareStriped<LBMCellF, LBMInitializer, 3>("LBMCellF", Coord<3>(18, 12, 10), 15, 2, 1);
         compareStriped<LBMCellF, LBMInitializer, 3>("LBMCellF", Coord<3>(18, 12, 13), 9, 3, 2);
+        compareNBodyStriped<float>("NBody<float>", Coord<3>(7, 5, 8), 8, 3);
+        compareNBodyStriped<float>("NBody<float>", Coord<3>(5, 4, 4), 6, 4);
+        compareNBodyStriped<double>("NBody<double>", Coord<3>(4, 6, 5), 6, 2);
+        compareNBodyStriped<double>("NBody<double>", Coord<3>(4, 3, 3), 4, 1);
         testEventProtocol();
         testSteererWritesAcrossSlabs();
         testRegionAndMemberStreamsAcrossSlabs();
