@@ -31,6 +31,7 @@ def main():
     iS, iE, iN, iT = h.index("Source"), h.index("Instructions Executed"), h.index("# Samples"), h.index("Thread Instructions Executed")
     stall_cols = [i for i, k in enumerate(h) if k.startswith("stall_") and "Not Issued" not in k]
     op, thr, stalls, tot = Counter(), Counter(), Counter(), 0
+    full = Counter()   # full mnemonic (with modifiers) of the integer / move instructions
     for r in data:
         try:
             e = int(r[iE])
@@ -40,12 +41,17 @@ def main():
         o = (s[1] if s[0].startswith("@") else s[0]).split(".")[0]
         op[o] += e
         thr[o] += int(r[iT] or 0)
+        if o in ("IMAD", "ISETP", "LEA", "VIADD", "IADD3", "MOV", "LOP3", "PLOP3", "SEL", "FSEL", "LDC", "UISETP"):
+            full[s[1] if s[0].startswith("@") else s[0]] += e
         tot += e
         for i in stall_cols:
             stalls[h[i]] += int(r[i] or 0)
     print("warp instructions executed: %d" % tot)
     for k, n in op.most_common(18):
         print("  %-10s %6.2f %%   avg active threads %.1f" % (k, 100.0 * n / tot, thr[k] / max(n, 1)))
+    print("integer / move instructions by full mnemonic:")
+    for k, n in full.most_common(14):
+        print("  %-22s %6.2f %%" % (k, 100.0 * n / tot))
     ssum = sum(stalls.values())
     print("stall samples:", ", ".join("%s %.0f%%" % (k[6:], 100.0 * n / ssum) for k, n in stalls.most_common(8)))
     print("hottest lines (samples, executed, sass):")
