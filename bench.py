@@ -214,7 +214,7 @@ def reference_arm(args):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * info["seconds"] / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": dtype, "data": "synthetic",
-        "config": {"workload": DESCRIPTION[args.workload], "model": model_name,
+        "config": {"workload": DESCRIPTION[args.workload], "cell": model_name,
                    "note": "CPU reference on the host cores of this box; bounded sample, see cpu_baseline.sample"},
         "cpu_baseline": info,
         "e2e": {"value": glups, "unit": "GLUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -516,7 +516,7 @@ def main():
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": main_res["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": main_res["dtype"],
             "data": "synthetic",
-            "config": {"workload": DESCRIPTION[args.workload], "model": main_res["model"],
+            "config": {"workload": DESCRIPTION[args.workload], "cell": main_res["model"],
                        "dims_per_gpu": main_res["dims_per_gpu"], "global_dims": main_res["global_dims"],
                        "partition": "z-slabs x%d" % world, "ghost_width": main_res["ghost_width"],
                        "halo_bytes_per_exchange_per_rank": main_res["halo_bytes_per_exchange"],

@@ -67,6 +67,19 @@ def test_no_cpu_fallback():
         capi.DeviceGrid((8, 8, 8), [8])
 
 
+def test_cpp_facade_fails_loudly_without_a_gpu():
+    """tests/facade/nogpu_test.cpp (built where /root/reference exists): B200Grid / B200Simulator /
+    B200StripingSimulator throw std::runtime_error("CUDA error ...") when there is no device; argument
+    validation maps to std::invalid_argument / std::logic_error before any CUDA call"""
+    import subprocess
+    binary = os.path.join(ROOT, "tests", "facade", "_bin", "nogpu_test")
+    if not os.access(binary, os.X_OK):
+        pytest.skip("tests/facade/_bin/nogpu_test not built (needs /root/reference at build time)")
+    res = subprocess.run([binary], capture_output=True, text=True, timeout=120)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    assert "all checks passed" in res.stdout
+
+
 def test_product_does_not_import_the_oracle():
     pkg = os.path.join(ROOT, "libgeodecomp_b200")
     for dirpath, _, files in os.walk(pkg):
