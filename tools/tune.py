@@ -15,7 +15,8 @@ from libgeodecomp_b200.simulator import B200Grid
 SPEC = {"jacobi27": (models.Jacobi27Cube, (1024, 1024, 1024), 16), "jacobi7": (models.Jacobi7Cube, (1024, 1024, 1024), 16),
         "lbm": (models.LBMCellF, (512, 512, 512), 152), "gol": (models.ConwayCube, (16384, 16384), 2),
         "jacobi7_128": (models.Jacobi7Cube, (128, 128, 128), 16), "jacobi7_64": (models.Jacobi7Cube, (64, 64, 64), 16),
-        "jacobi7_256": (models.Jacobi7Cube, (256, 256, 256), 16), "jacobi27_128": (models.Jacobi27Cube, (128, 128, 128), 16)}
+        "jacobi7_256": (models.Jacobi7Cube, (256, 256, 256), 16), "jacobi27_128": (models.Jacobi27Cube, (128, 128, 128), 16),
+        "jacobi7_512": (models.Jacobi7Cube, (512, 512, 512), 16), "jacobi27_512": (models.Jacobi27Cube, (512, 512, 512), 16)}
 
 
 def main():
