@@ -32,6 +32,7 @@
 #include <cstddef>
 #include <algorithm>
 #include <cstring>
+#include <map>
 #include <new>
 #include <stdexcept>
 #include <string>
@@ -220,45 +221,41 @@ public:
         }
     }
 
-    /* ship the combined writes (both buffers: serialsimulator.h:54-57 initialises curGrid and newGrid alike) */
+    /* ship the combined writes (both buffers: serialsimulator.h:54-57 initialises curGrid and newGrid alike).
+     * The list is cut into runs of mutually disjoint streaks — one b200geo_grid_load_region call per run, in
+     * order — so a cell that was written twice ends up with its last value (an Initializer that runs twice,
+     * as in SerialSimulator's constructor + run(), gives two runs). */
     void flush() const
     {
         if (pendingCells.empty()) {
             return;
         }
-        std::size_t n = pendingCells.size();
-        std::vector<char> buf(n * cellBytes);
-        std::size_t off = 0;
-        for (std::size_t m = 0; m < members.size(); ++m) {
-            const std::size_t bytes = members[m].bytes, at = members[m].offsetInCell;
-            for (std::size_t i = 0; i < n; ++i) {
-                std::memcpy(&buf[off + i * bytes], reinterpret_cast<const char*>(&pendingCells[i]) + at, bytes);
-            }
-            off += n * bytes;
-        }
-        // overlapping streaks are applied in list order by separate calls only if they overlap; the common
-        // case (disjoint cells) is one call
+        std::vector<CELL> cells;
         std::vector<int32_t> streaks;
+        cells.swap(pendingCells);
         streaks.swap(pendingStreaks);
-        pendingCells.clear();
-        if (disjoint(streaks)) {
-            B200Helpers::check(b200geo_grid_load_region(handle, streaks.data(), (int)(streaks.size() / 4), buf.data(), B200GEO_HOST, 1, 0));
-            return;
-        }
-        // rewritten cells: one call per streak keeps the order of the writes
-        std::size_t done = 0;
+        std::map<std::pair<int32_t, int32_t>, std::vector<std::pair<int32_t, int32_t> > > rows;
+        std::size_t runStreak = 0, runCell = 0, cell = 0;
         for (std::size_t k = 0; k < streaks.size(); k += 4) {
-            std::size_t len = streaks[k + 3] - streaks[k];
-            std::vector<char> one(len * cellBytes);
-            std::size_t moff = 0, ooff = 0;
-            for (std::size_t m = 0; m < members.size(); ++m) {
-                std::memcpy(&one[ooff], &buf[moff + done * members[m].bytes], len * members[m].bytes);
-                ooff += len * members[m].bytes;
-                moff += n * members[m].bytes;
+            std::vector<std::pair<int32_t, int32_t> >& taken = rows[std::make_pair(streaks[k + 2], streaks[k + 1])];
+            bool overlaps = false;
+            for (std::size_t i = 0; i < taken.size(); ++i) {
+                overlaps |= streaks[k] < taken[i].second && taken[i].first < streaks[k + 3];
             }
-            B200Helpers::check(b200geo_grid_load_region(handle, &streaks[k], 1, one.data(), B200GEO_HOST, 1, 0));
-            done += len;
+            if (overlaps) {
+                ship(streaks, runStreak, k, cells, runCell, cell);
+                rows.clear();
+                runStreak = k;
+                runCell = cell;
+                rows[std::make_pair(streaks[k + 2], streaks[k + 1])].push_back(std::make_pair(streaks[k], streaks[k + 3]));
+            } else if (!taken.empty() && taken.back().second == streaks[k]) {
+                taken.back().second = streaks[k + 3];   // cell after cell along x: one growing interval
+            } else {
+                taken.push_back(std::make_pair(streaks[k], streaks[k + 3]));
+            }
+            cell += streaks[k + 3] - streaks[k];
         }
+        ship(streaks, runStreak, streaks.size(), cells, runCell, cell);
     }
 
     /* single-cell reads are served from a cache of the row they lie in (Writers that walk the grid cell by
@@ -482,21 +479,24 @@ private:
     mutable Coord<DIM> rowCacheOrigin;
     mutable bool rowCacheValid = false;
 
-    /* no two streaks of the list share a cell (then their order does not matter) */
-    static bool disjoint(const std::vector<int32_t>& streaks)
+    /* streaks [s0, s1) of the list with their cells [c0, c1), member-major, in one call */
+    void ship(const std::vector<int32_t>& streaks, std::size_t s0, std::size_t s1,
+              const std::vector<CELL>& cells, std::size_t c0, std::size_t c1) const
     {
-        std::vector<std::pair<std::pair<int32_t, int32_t>, std::pair<int32_t, int32_t> > > v;
-        v.reserve(streaks.size() / 4);
-        for (std::size_t k = 0; k < streaks.size(); k += 4) {
-            v.push_back(std::make_pair(std::make_pair(streaks[k + 2], streaks[k + 1]), std::make_pair(streaks[k], streaks[k + 3])));
+        if (c1 <= c0) {
+            return;
         }
-        std::sort(v.begin(), v.end());
-        for (std::size_t i = 1; i < v.size(); ++i) {
-            if (v[i].first == v[i - 1].first && v[i].second.first < v[i - 1].second.second) {
-                return false;
+        std::size_t n = c1 - c0;
+        std::vector<char> buf(n * cellBytes);
+        std::size_t off = 0;
+        for (std::size_t m = 0; m < members.size(); ++m) {
+            const std::size_t bytes = members[m].bytes, at = members[m].offsetInCell;
+            for (std::size_t i = 0; i < n; ++i) {
+                std::memcpy(&buf[off + i * bytes], reinterpret_cast<const char*>(&cells[c0 + i]) + at, bytes);
             }
+            off += n * bytes;
         }
-        return true;
+        B200Helpers::check(b200geo_grid_load_region(handle, &streaks[s0], (int)((s1 - s0) / 4), buf.data(), B200GEO_HOST, 1, 0));
     }
 
     void init()
