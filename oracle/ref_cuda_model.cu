@@ -5,7 +5,7 @@
  * secondary comparator): what a user gets today by recompiling LibGeoDecomp, and what the hand-written kernels
  * of libb200geo.so are measured against. Nothing in the product links or calls this.
  *
- * usage: lgd_ref_cuda_jacobi [n = 512] [steps = 50]     prints one JSON line per cell type */
+ * usage: lgd_ref_cuda_jacobi [n = 512] [steps = 50]     prints one JSON line per cell type (LBM: at most 256^3) */
 #include <cuda.h>
 
 #include <libgeodecomp/io/simpleinitializer.h>
@@ -14,7 +14,10 @@
 #include <cstdio>
 #include <cstdlib>
 
+#include "models/lbm_aos.h"
+
 using namespace LibGeoDecomp;
+using b200models::LBMCellAoS;
 
 class RefJacobi7
 {
@@ -87,8 +90,38 @@ public:
     }
 };
 
+/* lid-driven cavity of src/examples/latticeboltzmann/main.cpp:249-287, fluid at rest */
+template<>
+class Init<LBMCellAoS> : public SimpleInitializer<LBMCellAoS>
+{
+public:
+    Init(const Coord<3>& dim, unsigned steps) : SimpleInitializer<LBMCellAoS>(dim, steps) {}
+
+    virtual void grid(GridBase<LBMCellAoS, 3> *ret)
+    {
+        CoordBox<3> box = ret->boundingBox();
+        Coord<3> size = gridDimensions();
+        std::vector<LBMCellAoS> row(box.dimensions.x());
+        for (CoordBox<3>::StreakIterator i = box.beginStreak(); i != box.endStreak(); ++i) {
+            int y = i->origin.y(), z = i->origin.z();
+            for (std::size_t x = 0; x < row.size(); ++x) {
+                int gx = i->origin.x() + (int)x;
+                int s = LBMCellAoS::LIQUID;
+                if (gx == 0) s = LBMCellAoS::WEST_NOSLIP;
+                if (gx == size.x() - 1) s = LBMCellAoS::EAST_NOSLIP;
+                if (y == 0) s = LBMCellAoS::SOUTH_NOSLIP;
+                if (y == size.y() - 1) s = LBMCellAoS::NORTH_ACC;
+                if (z == 0) s = LBMCellAoS::BOTTOM;
+                if (z == size.z() - 1) s = LBMCellAoS::TOP;
+                row[x] = LBMCellAoS(1.0f, s);
+            }
+            ret->set(*i, row.data());
+        }
+    }
+};
+
 template<typename CELL>
-static void bench(const char *name, int n, int steps)
+static void bench(const char *name, int n, int steps, int bytesPerUpdate = 16)
 {
     Coord<3> dim(n, n, n);
     CUDASimulator<CELL> sim(new Init<CELL>(dim, 3));
@@ -109,7 +142,7 @@ static void bench(const char *name, int n, int steps)
     double cells = (double)n * n * n;
     std::printf("{\"impl\": \"reference CUDASimulator (cudasimulator.h, recompiled for sm_100a)\", \"cell\": \"%s\", \"dims\": [%d, %d, %d], "
                 "\"steps\": %d, \"ms_per_step\": %.4f, \"glups\": %.2f, \"algorithmic_gbs\": %.0f, \"cuda\": \"%s\"}\n",
-                name, n, n, n, steps, ms / steps, 1e-9 * cells * steps / (1e-3 * ms), 16e-9 * cells * steps / (1e-3 * ms),
+                name, n, n, n, steps, ms / steps, 1e-9 * cells * steps / (1e-3 * ms), bytesPerUpdate * 1e-9 * cells * steps / (1e-3 * ms),
                 cudaGetErrorString(e));
 }
 
@@ -119,5 +152,6 @@ int main(int argc, char **argv)
     int steps = argc > 2 ? std::atoi(argv[2]) : 50;
     bench<RefJacobi7>("Jacobi 7-point f64 (AoS, FixedCoord)", n, steps);
     bench<RefJacobi27>("Jacobi 27-point f64 (AoS, FixedCoord)", n, steps);
+    bench<LBMCellAoS>("LBM D3Q19 f32 cavity (AoS cell of 96 bytes, FixedCoord)", n > 256 ? 256 : n, steps < 20 ? steps : 20, 152);
     return 0;
 }

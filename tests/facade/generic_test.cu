@@ -27,7 +27,10 @@
 
 #include <libgeodecomp_b200/b200stripingsimulator.h>
 
+#include "models/lbm_aos.h"
+
 using namespace LibGeoDecomp;
+using b200models::LBMCellAoS;
 
 static int failures = 0;
 #define CHECK(COND)                                                                     \
@@ -352,6 +355,40 @@ static void compareWithSerialSimulator(const char *name, const Coord<DIM>& dim, 
     CHECK((differingCells<CELL, DIM>(ref.getGrid(), single.getGrid()) == 0));
 }
 
+/* the D3Q19 cavity as a plain 96-byte AoS user cell (oracle/models/lbm_aos.h): 24 words per cell on the device grid */
+class CavityInitializer : public SimpleInitializer<LBMCellAoS>
+{
+public:
+    CavityInitializer(const Coord<3>& dim, unsigned steps) : SimpleInitializer<LBMCellAoS>(dim, steps) {}
+
+    virtual void grid(GridBase<LBMCellAoS, 3> *ret)
+    {
+        CoordBox<3> box = ret->boundingBox();
+        Coord<3> size = gridDimensions();
+        std::vector<LBMCellAoS> row(box.dimensions.x());
+        for (CoordBox<3>::StreakIterator i = box.beginStreak(); i != box.endStreak(); ++i) {
+            int y = i->origin.y(), z = i->origin.z();
+            for (std::size_t x = 0; x < row.size(); ++x) {
+                int gx = i->origin.x() + (int)x;
+                int s = LBMCellAoS::LIQUID;
+                if (gx == 0) s = LBMCellAoS::WEST_NOSLIP;
+                if (gx == size.x() - 1) s = LBMCellAoS::EAST_NOSLIP;
+                if (y == 0) s = LBMCellAoS::SOUTH_NOSLIP;
+                if (y == size.y() - 1) s = LBMCellAoS::NORTH_ACC;
+                if (z == 0) s = LBMCellAoS::BOTTOM;
+                if (z == size.z() - 1) s = LBMCellAoS::TOP;
+                LBMCellAoS c(1.0f, s);
+                uint64_t id = Coord<3>(gx, y, z).toIndex(size);
+                c.N = 0.01f * (float)uniform(3 * id);
+                c.TE = 0.01f * (float)uniform(3 * id + 1);
+                c.BS = 0.01f * (float)uniform(3 * id + 2);
+                row[x] = c;
+            }
+            ret->set(*i, row.data());
+        }
+    }
+};
+
 /* unbound cells on a slab group: the group drives rims / halo copies / interiors and calls the user's update()
  * back for every box (b200geo_group_step_with); slabs round-robin over the GPUs present */
 static std::vector<int> devicesFor(int slabs)
@@ -416,10 +453,10 @@ template<> struct Seed<PlainJacobi> {
 };
 
 /* throughput of the generic path (`generic_test --bench`): wall clock around step() calls, grid resident */
-template<typename CELL, int DIM>
+template<typename CELL, int DIM, typename INIT = SeededInitializer<CELL> >
 static void benchGeneric(const char *name, const Coord<DIM>& dim, unsigned steps, int bytesPerUpdate)
 {
-    B200Simulator<CELL> sim(new SeededInitializer<CELL>(dim, steps + 3));
+    B200Simulator<CELL> sim(new INIT(dim, steps + 3));
     for (int i = 0; i < 3; ++i) {
         sim.step();
     }
@@ -451,6 +488,7 @@ int main(int argc, char **argv)
             benchGeneric<PlainJacobi, 3>("PlainJacobi 7-point f64 384^3 (user update(), FixedCoord)", Coord<3>(384, 384, 384), 30, 16);
             benchGeneric<LifeCell, 2>("LifeCell 8192^2 (user update(), run-time Coord<2>)", Coord<2>(8192, 8192), 50, 2);
             benchGeneric<WaveCell, 3>("WaveCell 2 x f32 256^3 Torus (user updateLineX, 2 nano steps)", Coord<3>(256, 256, 256), 30, 16);
+            benchGeneric<LBMCellAoS, 3, CavityInitializer>("LBM D3Q19 f32 cavity 256^3 (96-byte AoS user cell, update())", Coord<3>(256, 256, 256), 20, 152);
         } catch (const std::exception& e) {
             std::printf("FAILED with exception: %s\n", e.what());
             return 2;
@@ -485,6 +523,8 @@ int main(int argc, char **argv)
         compareStriped<HeatCell, SeededInitializer<HeatCell>, 2>("HeatCell (stale member)", Coord<2>(97, 41), 23, 2);
         compareStriped<WaveCell, SeededInitializer<WaveCell>, 3>("WaveCell (updateLineX)", Coord<3>(40, 9, 14), 12, 3);
         compareStriped<PlainJacobi, SeededInitializer<PlainJacobi>, 3>("PlainJacobi (7-point)", Coord<3>(33, 10, 9), 9, 1);
+        compareStriped<LBMCellAoS, CavityInitializer, 3>("LBMCellAoS (96-byte cell)", Coord<3>(18, 12, 10), 15, 1);
+        compareStriped<LBMCellAoS, CavityInitializer, 3>("LBMCellAoS (96-byte cell)", Coord<3>(18, 12, 10), 15, 3);
     } catch (const std::exception& e) {
         std::printf("FAILED with exception: %s\n", e.what());
         return 2;
