@@ -1,0 +1,528 @@
+/* TEST INFRASTRUCTURE — a host-memory stand-in for libb200geo.so, so that the HOST logic of the C++ façade
+ * (B200Grid: combined writes, cached rows, region / member streams; B200StripedGrid: routing across slabs;
+ * B200Simulator / B200StripingSimulator: event protocol, step fusing; status code -> exception mapping) runs in
+ * the CPU test suite, where there is no GPU. It implements the C ABI of include/b200geo.h on plain arrays; the
+ * sweeps themselves are delegated to the oracle (oracle/oracle.c) — which is exactly why this file lives under
+ * tests/ and is never part of the product. Slab groups are stepped by assembling the slabs into the whole
+ * space, so they exercise the façade's partition bookkeeping, not the halo schedule (that is GPU-tested).
+ * Built into tests/facade/_bin/*_cpu by tests/facade/Makefile, run by tests/test_facade_cpu.py. */
+#include "../../include/b200geo.h"
+#include "../../oracle/oracle.h"
+
+#include <cstring>
+#include <string>
+#include <vector>
+
+static thread_local std::string g_error;
+
+static int fail(int status, const std::string& msg)
+{
+    g_error = msg;
+    return status;
+}
+
+struct b200geo_grid {
+    b200geo_grid_desc desc;
+    int n, d[3], g[3], elem[B200GEO_MAX_MEMBERS], cell_bytes, slab_axis, cur;
+    int64_t px, py, pz;                         // padded extents
+    std::vector<char> buf[2][B200GEO_MAX_MEMBERS];
+    unsigned char edge[8 * B200GEO_MAX_MEMBERS];
+    uint64_t sweeps;
+
+    int64_t index(int x, int y, int z) const { return ((int64_t)(z + g[2]) * py + (y + g[1])) * px + (x + g[0]); }
+    int64_t cells() const { return (int64_t)d[0] * d[1] * d[2]; }
+};
+
+struct b200geo_group {
+    std::vector<b200geo_grid *> g;
+    bool periodic;
+    uint64_t exchanges, bytes;
+};
+
+struct b200geo_boxgrid {
+    b200geo_boxgrid_desc desc;
+    int d[3], cap, real;
+    std::vector<int32_t> counts;                // interior only, [z][y][x]
+    std::vector<char> parts;                    // [z][y][x][cap][6] REAL
+    bool overflow;
+};
+
+struct b200geo_boxgroup {
+    std::vector<b200geo_boxgrid *> g;
+    uint64_t exchanges, bytes;
+};
+
+namespace {
+
+// dense member-major interior of the current buffer <-> grid
+void gather(const b200geo_grid *g, std::vector<char>& raw)
+{
+    raw.resize((size_t)g->cells() * g->cell_bytes);
+    size_t off = 0;
+    for (int m = 0; m < g->n; ++m) {
+        const int e = g->elem[m];
+        for (int z = 0; z < g->d[2]; ++z)
+            for (int y = 0; y < g->d[1]; ++y)
+                memcpy(&raw[off + (((size_t)z * g->d[1] + y) * g->d[0]) * e], &g->buf[g->cur][m][g->index(0, y, z) * e], (size_t)g->d[0] * e);
+        off += (size_t)g->cells() * e;
+    }
+}
+
+void scatter(b200geo_grid *g, int which, const std::vector<char>& raw)
+{
+    size_t off = 0;
+    for (int m = 0; m < g->n; ++m) {
+        const int e = g->elem[m];
+        for (int z = 0; z < g->d[2]; ++z)
+            for (int y = 0; y < g->d[1]; ++y)
+                memcpy(&g->buf[which][m][g->index(0, y, z) * e], &raw[off + (((size_t)z * g->d[1] + y) * g->d[0]) * e], (size_t)g->d[0] * e);
+        off += (size_t)g->cells() * e;
+    }
+}
+
+// `steps` sweeps of the kernel family over a dense member-major grid of nx * ny * nz cells
+int oracle_sweeps(const b200geo_grid *like, int kernel, int nx, int ny, int nz, int steps, const std::vector<char>& in, std::vector<char>& out)
+{
+    out.resize(in.size());
+    const bool torus = like->desc.ghost_mode[0][0] == B200GEO_GHOST_WRAP;
+    switch (kernel) {
+    case B200GEO_KERNEL_JACOBI6:
+    case B200GEO_KERNEL_JACOBI7:
+    case B200GEO_KERNEL_JACOBI27: {
+        double edge;
+        memcpy(&edge, like->edge, 8);
+        int kind = kernel == B200GEO_KERNEL_JACOBI6 ? 6 : kernel == B200GEO_KERNEL_JACOBI7 ? 7 : 27;
+        return oracle_jacobi(kind, torus, nx, ny, nz, steps, edge, (const double *)in.data(), (double *)out.data());
+    }
+    case B200GEO_KERNEL_GOL:
+        return oracle_gol(torus, nx, ny, steps, like->edge[0] != 0, (const uint8_t *)in.data(), (uint8_t *)out.data());
+    case B200GEO_KERNEL_LBM_D3Q19:
+        return oracle_lbm(nx, ny, nz, steps, in.data(), out.data());
+    default:
+        return fail(B200GEO_ERR_LOGIC, "no kernel bound for this id");
+    }
+}
+
+int region(b200geo_grid *g, const int32_t *streaks, int n, char *buf, bool save, bool both)
+{
+    int64_t count = 0;
+    for (int i = 0; i < n; ++i) {
+        const int32_t *k = streaks + 4 * i;
+        if (k[3] < k[0] || k[0] < -g->g[0] || k[3] > g->d[0] + g->g[0] || k[1] < -g->g[1] || k[1] >= g->d[1] + g->g[1] ||
+            k[2] < -g->g[2] || k[2] >= g->d[2] + g->g[2])
+            return fail(B200GEO_ERR_INVALID, "streak outside the grid");
+        count += k[3] - k[0];
+    }
+    int64_t moff = 0;
+    for (int m = 0; m < g->n; ++m) {
+        const int e = g->elem[m];
+        int64_t pos = 0;
+        for (int i = 0; i < n; ++i) {
+            const int32_t *k = streaks + 4 * i;
+            const int64_t len = k[3] - k[0], at = g->index(k[0], k[1], k[2]) * e;
+            char *b = buf + moff + pos * e;
+            if (save) {
+                memcpy(b, &g->buf[g->cur][m][at], len * e);
+            } else {
+                memcpy(&g->buf[g->cur][m][at], b, len * e);
+                if (both) memcpy(&g->buf[g->cur ^ 1][m][at], b, len * e);
+            }
+            pos += len;
+        }
+        moff += count * e;
+    }
+    return B200GEO_OK;
+}
+
+int member_box(b200geo_grid *g, int m, const int32_t o[3], const int32_t d[3], char *dense, bool load, bool both)
+{
+    if (m < 0 || m >= g->n) return fail(B200GEO_ERR_INVALID, "bad member index");
+    for (int i = 0; i < 3; ++i)
+        if (d[i] < 0 || o[i] < -g->g[i] || o[i] + d[i] > g->d[i] + g->g[i]) return fail(B200GEO_ERR_INVALID, "box outside the grid");
+    const int e = g->elem[m];
+    for (int z = 0; z < d[2]; ++z)
+        for (int y = 0; y < d[1]; ++y) {
+            char *row = dense + (((size_t)z * d[1] + y) * d[0]) * e;
+            const int64_t at = g->index(o[0], o[1] + y, o[2] + z) * e;
+            if (load) {
+                memcpy(&g->buf[g->cur][m][at], row, (size_t)d[0] * e);
+                if (both) memcpy(&g->buf[g->cur ^ 1][m][at], row, (size_t)d[0] * e);
+            } else {
+                memcpy(row, &g->buf[g->cur][m][at], (size_t)d[0] * e);
+            }
+        }
+    return B200GEO_OK;
+}
+
+size_t box_cell_bytes(const b200geo_boxgrid *g) { return (size_t)g->cap * 6 * g->real; }
+
+}
+
+extern "C" {
+
+const char *b200geo_version(void) { return "b200geo mock (host memory, tests only)"; }
+const char *b200geo_last_error(void) { return g_error.c_str(); }
+int b200geo_device_count(void) { return 1; }
+int b200geo_set_tuning(const char *, int) { return B200GEO_OK; }
+uint64_t b200geo_launch_count(void) { return 0; }
+
+int b200geo_grid_create(const b200geo_grid_desc *desc, int, b200geo_grid **out)
+{
+    if (!desc || !out) return fail(B200GEO_ERR_INVALID, "null argument");
+    if (desc->n_members < 1 || desc->n_members > B200GEO_MAX_MEMBERS) return fail(B200GEO_ERR_INVALID, "n_members out of range");
+    int slab = (desc->dim[2] == 1 && desc->ghost[2] == 0) ? 1 : 2;
+    for (int i = 0; i < 3; ++i) {
+        if (desc->dim[i] < 1) return fail(B200GEO_ERR_INVALID, "grid dimension must be >= 1");
+        if (desc->ghost[i] < 0 || desc->ghost[i] > 16) return fail(B200GEO_ERR_INVALID, "ghost width out of range");
+        for (int s = 0; s < 2; ++s) {
+            int mode = desc->ghost_mode[i][s];
+            if (mode < B200GEO_GHOST_EDGE || mode > B200GEO_GHOST_PEER) return fail(B200GEO_ERR_INVALID, "bad ghost mode");
+            if (mode == B200GEO_GHOST_PEER && i != slab)
+                return fail(B200GEO_ERR_LOGIC, "PEER ghost layers are supported on the last axis only (slab partition)");
+            if (mode == B200GEO_GHOST_WRAP && desc->ghost[i] > desc->dim[i]) return fail(B200GEO_ERR_INVALID, "wrap ghost wider than the grid");
+        }
+    }
+    b200geo_grid *g = new b200geo_grid();
+    g->desc = *desc;
+    g->n = desc->n_members;
+    g->cell_bytes = 0;
+    g->cur = 0;
+    g->sweeps = 0;
+    g->slab_axis = slab;
+    memset(g->edge, 0, sizeof(g->edge));
+    for (int i = 0; i < 3; ++i) {
+        g->d[i] = desc->dim[i];
+        g->g[i] = desc->ghost[i];
+    }
+    g->px = g->d[0] + 2 * g->g[0];
+    g->py = g->d[1] + 2 * g->g[1];
+    g->pz = g->d[2] + 2 * g->g[2];
+    for (int m = 0; m < g->n; ++m) {
+        int e = desc->member_bytes[m];
+        if (e != 1 && e != 2 && e != 4 && e != 8) {
+            delete g;
+            return fail(B200GEO_ERR_INVALID, "member size must be 1, 2, 4 or 8 bytes");
+        }
+        g->elem[m] = e;
+        g->cell_bytes += e;
+        g->buf[0][m].assign((size_t)(g->px * g->py * g->pz) * e, 0);
+        g->buf[1][m].assign((size_t)(g->px * g->py * g->pz) * e, 0);
+    }
+    *out = g;
+    return B200GEO_OK;
+}
+
+int b200geo_grid_destroy(b200geo_grid *g) { delete g; return B200GEO_OK; }
+int b200geo_grid_buffer_bytes(const b200geo_grid *g, uint64_t *bytes) { *bytes = (uint64_t)(g->px * g->py * g->pz) * g->cell_bytes; return B200GEO_OK; }
+int b200geo_grid_device(const b200geo_grid *, int *device) { *device = 0; return B200GEO_OK; }
+
+int b200geo_grid_layout(const b200geo_grid *g, int, int64_t *pitch, int64_t *plane, int64_t *origin)
+{
+    if (pitch) *pitch = g->px;
+    if (plane) *plane = g->px * g->py;
+    if (origin) *origin = g->index(0, 0, 0);
+    return B200GEO_OK;
+}
+
+int b200geo_grid_member_ptr(const b200geo_grid *g, int m, int which, void **ptr)
+{
+    *ptr = const_cast<char *>(g->buf[g->cur ^ which][m].data());
+    return B200GEO_OK;
+}
+
+int b200geo_grid_set_edge(b200geo_grid *g, const void *cell, void *)
+{
+    memcpy(g->edge, cell, g->cell_bytes);
+    int off = 0;
+    for (int m = 0; m < g->n; ++m) {
+        const int e = g->elem[m];
+        for (int z = -g->g[2]; z < g->d[2] + g->g[2]; ++z)
+            for (int y = -g->g[1]; y < g->d[1] + g->g[1]; ++y)
+                for (int x = -g->g[0]; x < g->d[0] + g->g[0]; ++x) {
+                    const int c[3] = {x, y, z};
+                    bool is_edge = false;
+                    for (int i = 0; i < 3; ++i) {
+                        if (c[i] < 0 && g->desc.ghost_mode[i][0] == B200GEO_GHOST_EDGE) is_edge = true;
+                        if (c[i] >= g->d[i] && g->desc.ghost_mode[i][1] == B200GEO_GHOST_EDGE) is_edge = true;
+                    }
+                    if (!is_edge) continue;
+                    for (int b = 0; b < 2; ++b) memcpy(&g->buf[b][m][g->index(x, y, z) * e], g->edge + off, e);
+                }
+        off += e;
+    }
+    return B200GEO_OK;
+}
+
+int b200geo_grid_get_edge(const b200geo_grid *g, void *cell) { memcpy(cell, g->edge, g->cell_bytes); return B200GEO_OK; }
+
+int b200geo_grid_load_member(b200geo_grid *g, int m, const int32_t o[3], const int32_t d[3], const void *src, int, int both, void *)
+{
+    return member_box(g, m, o, d, (char *)const_cast<void *>(src), true, both != 0);
+}
+
+int b200geo_grid_save_member(const b200geo_grid *g, int m, const int32_t o[3], const int32_t d[3], void *dst, int, void *)
+{
+    return member_box(const_cast<b200geo_grid *>(g), m, o, d, (char *)dst, false, false);
+}
+
+int b200geo_grid_load_region(b200geo_grid *g, const int32_t *streaks, int n, const void *buf, int, int both, void *)
+{
+    if (n <= 0) return B200GEO_OK;
+    return region(g, streaks, n, (char *)const_cast<void *>(buf), false, both != 0);
+}
+
+int b200geo_grid_save_region(const b200geo_grid *g, const int32_t *streaks, int n, void *buf, int, void *)
+{
+    if (n <= 0) return B200GEO_OK;
+    return region(const_cast<b200geo_grid *>(g), streaks, n, (char *)buf, true, false);
+}
+
+int b200geo_step(b200geo_grid *g, int kernel, const void *, uint32_t, uint32_t n_steps, void *)
+{
+    for (int i = 0; i < 3; ++i)
+        for (int s = 0; s < 2; ++s)
+            if (g->desc.ghost_mode[i][s] == B200GEO_GHOST_PEER) return fail(B200GEO_ERR_LOGIC, "mock: slabs are stepped through their group");
+    if (n_steps == 0) return B200GEO_OK;
+    std::vector<char> in, out;
+    gather(g, in);
+    int rc = oracle_sweeps(g, kernel, g->d[0], g->d[1], g->d[2], (int)n_steps, in, out);
+    if (rc) return rc < 0 ? rc : fail(B200GEO_ERR_INVALID, "oracle failed");
+    // an odd number of sweeps ends in the other buffer, like the real engine
+    int target = (n_steps & 1) ? g->cur ^ 1 : g->cur;
+    scatter(g, target, out);
+    g->cur = target;
+    g->sweeps += n_steps;
+    return B200GEO_OK;
+}
+
+int b200geo_update_box(b200geo_grid *, int, const void *, uint32_t, const int32_t *, const int32_t *, void *) { return fail(B200GEO_ERR_LOGIC, "not in the mock"); }
+int b200geo_update_box_n(b200geo_grid *, int, const void *, uint32_t, const int32_t *, const int32_t *, uint32_t, void *) { return fail(B200GEO_ERR_LOGIC, "not in the mock"); }
+int b200geo_swap(b200geo_grid *g) { g->cur ^= 1; return B200GEO_OK; }
+int b200geo_refresh_ghosts(b200geo_grid *, void *) { return B200GEO_OK; }
+int b200geo_sync(void *) { return B200GEO_OK; }
+int b200geo_halo_block(const b200geo_grid *, int, int, int, int, void **, uint64_t *) { return fail(B200GEO_ERR_LOGIC, "not in the mock"); }
+int b200geo_halo_block_in(const b200geo_grid *, int, int, int, int, int, void **, uint64_t *) { return fail(B200GEO_ERR_LOGIC, "not in the mock"); }
+int b200geo_grid_ipc_export(const b200geo_grid *, int, void *) { return fail(B200GEO_ERR_LOGIC, "not in the mock"); }
+int b200geo_grid_ipc_open(b200geo_grid *, int, int, const void *) { return fail(B200GEO_ERR_LOGIC, "not in the mock"); }
+int b200geo_halo_push(b200geo_grid *, int, int, void *) { return fail(B200GEO_ERR_LOGIC, "not in the mock"); }
+int b200geo_halo_mark_valid(b200geo_grid *, int, int) { return B200GEO_OK; }
+int b200geo_stats_enable(b200geo_grid *, int) { return B200GEO_OK; }
+int b200geo_stats(b200geo_grid *g, double out[3]) { out[0] = out[1] = 0; out[2] = (double)g->sweeps; return B200GEO_OK; }
+
+/* ---- slab groups: assembled into the whole space ---------------------------------------------------------- */
+int b200geo_group_create(b200geo_grid *const *grids, int n, int periodic, b200geo_group **out)
+{
+    if (!grids || !out || n < 1 || n > 16) return fail(B200GEO_ERR_INVALID, "bad slab group");
+    for (int i = 0; i < n; ++i) {
+        const b200geo_grid *g = grids[i];
+        const int a = g->slab_axis;
+        if (n > 1) {
+            bool low = i > 0 || periodic, high = i < n - 1 || periodic;
+            if ((g->desc.ghost_mode[a][0] == B200GEO_GHOST_PEER) != low || (g->desc.ghost_mode[a][1] == B200GEO_GHOST_PEER) != high)
+                return fail(B200GEO_ERR_INVALID, "slab faces towards a neighbour must be PEER ghost layers, outer faces must not");
+            if (g->d[a] < g->g[a]) return fail(B200GEO_ERR_INVALID, "slab thinner than the ghost zone");
+        }
+    }
+    b200geo_group *grp = new b200geo_group();
+    grp->g.assign(grids, grids + n);
+    grp->periodic = periodic != 0;
+    grp->exchanges = grp->bytes = 0;
+    *out = grp;
+    return B200GEO_OK;
+}
+
+int b200geo_group_destroy(b200geo_group *grp) { delete grp; return B200GEO_OK; }
+int b200geo_group_invalidate(b200geo_group *) { return B200GEO_OK; }
+int b200geo_group_exchange(b200geo_group *) { return B200GEO_OK; }
+
+int b200geo_group_step(b200geo_group *grp, int kernel, const void *params, uint32_t first, uint32_t n_steps)
+{
+    if (grp->g.size() == 1) return b200geo_step(grp->g[0], kernel, params, first, n_steps, 0);
+    if (n_steps == 0) return B200GEO_OK;
+    b200geo_grid *g0 = grp->g[0];
+    const int a = g0->slab_axis;
+    int dims[3] = {g0->d[0], g0->d[1], g0->d[2]};
+    dims[a] = 0;
+    for (size_t s = 0; s < grp->g.size(); ++s) dims[a] += grp->g[s]->d[a];
+    const int64_t cells = (int64_t)dims[0] * dims[1] * dims[2];
+    std::vector<char> in((size_t)cells * g0->cell_bytes), out, part;
+    // slabs are contiguous along the slowest used axis: member by member, slab after slab
+    size_t moff = 0;
+    for (int m = 0; m < g0->n; ++m) {
+        size_t pos = 0;
+        for (size_t s = 0; s < grp->g.size(); ++s) {
+            b200geo_grid *g = grp->g[s];
+            gather(g, part);
+            size_t poff = 0;
+            for (int k = 0; k < m; ++k) poff += (size_t)g->cells() * g->elem[k];
+            memcpy(&in[moff + pos], &part[poff], (size_t)g->cells() * g->elem[m]);
+            pos += (size_t)g->cells() * g->elem[m];
+        }
+        moff += (size_t)cells * g0->elem[m];
+    }
+    // a Torus group: the wrap flag lives in the x axis of the slabs (the slab axis itself is PEER)
+    int rc = oracle_sweeps(g0, kernel, dims[0], dims[1], dims[2], (int)n_steps, in, out);
+    if (rc) return rc < 0 ? rc : fail(B200GEO_ERR_INVALID, "oracle failed");
+    moff = 0;
+    std::vector<std::vector<char> > parts(grp->g.size());
+    for (size_t s = 0; s < grp->g.size(); ++s) parts[s].resize((size_t)grp->g[s]->cells() * g0->cell_bytes);
+    for (int m = 0; m < g0->n; ++m) {
+        size_t pos = 0;
+        for (size_t s = 0; s < grp->g.size(); ++s) {
+            b200geo_grid *g = grp->g[s];
+            size_t poff = 0;
+            for (int k = 0; k < m; ++k) poff += (size_t)g->cells() * g->elem[k];
+            memcpy(&parts[s][poff], &out[moff + pos], (size_t)g->cells() * g->elem[m]);
+            pos += (size_t)g->cells() * g->elem[m];
+        }
+        moff += (size_t)cells * g0->elem[m];
+    }
+    for (size_t s = 0; s < grp->g.size(); ++s) {
+        b200geo_grid *g = grp->g[s];
+        int target = (n_steps & 1) ? g->cur ^ 1 : g->cur;
+        scatter(g, target, parts[s]);
+        g->cur = target;
+        g->sweeps += n_steps;
+    }
+    const int w = g0->g[a] > 0 ? g0->g[a] : 1;
+    grp->exchanges += (n_steps + w - 1) / w;
+    grp->bytes += 1;
+    return B200GEO_OK;
+}
+
+int b200geo_group_step_with(b200geo_group *, b200geo_update_fn, void *, uint32_t, uint32_t) { return fail(B200GEO_ERR_LOGIC, "not in the mock"); }
+int b200geo_group_sync(b200geo_group *) { return B200GEO_OK; }
+int b200geo_group_stats(const b200geo_group *grp, uint64_t out[2]) { out[0] = grp->exchanges; out[1] = grp->bytes; return B200GEO_OK; }
+
+/* ---- container grids ---------------------------------------------------------------------------------------- */
+int b200geo_boxgrid_create(const b200geo_boxgrid_desc *desc, int, b200geo_boxgrid **out)
+{
+    if (!desc || !out) return fail(B200GEO_ERR_INVALID, "null argument");
+    if (desc->capacity < 1 || desc->capacity > 64 || (desc->real_bytes != 4 && desc->real_bytes != 8))
+        return fail(B200GEO_ERR_INVALID, "bad capacity / particle type");
+    b200geo_boxgrid *g = new b200geo_boxgrid();
+    g->desc = *desc;
+    for (int i = 0; i < 3; ++i) g->d[i] = desc->dim[i];
+    g->cap = desc->capacity;
+    g->real = desc->real_bytes;
+    g->overflow = false;
+    g->counts.assign((size_t)g->d[0] * g->d[1] * g->d[2], 0);
+    g->parts.assign(g->counts.size() * box_cell_bytes(g), 0);
+    *out = g;
+    return B200GEO_OK;
+}
+
+int b200geo_boxgrid_destroy(b200geo_boxgrid *g) { delete g; return B200GEO_OK; }
+
+static int box_io(b200geo_boxgrid *g, const int32_t o[3], const int32_t d[3], int32_t *counts, char *parts, bool load)
+{
+    for (int i = 0; i < 3; ++i)
+        if (d[i] < 0 || o[i] < 0 || o[i] + d[i] > g->d[i]) return fail(B200GEO_ERR_INVALID, "mock: container box outside the interior");
+    const size_t cb = box_cell_bytes(g);
+    for (int z = 0; z < d[2]; ++z)
+        for (int y = 0; y < d[1]; ++y)
+            for (int x = 0; x < d[0]; ++x) {
+                size_t dense = ((size_t)z * d[1] + y) * d[0] + x;
+                size_t mine = ((size_t)(o[2] + z) * g->d[1] + (o[1] + y)) * g->d[0] + (o[0] + x);
+                if (load) {
+                    g->counts[mine] = counts[dense];
+                    memcpy(&g->parts[mine * cb], parts + dense * cb, cb);
+                } else {
+                    counts[dense] = g->counts[mine];
+                    memcpy(parts + dense * cb, &g->parts[mine * cb], cb);
+                }
+            }
+    return B200GEO_OK;
+}
+
+int b200geo_boxgrid_load(b200geo_boxgrid *g, const int32_t o[3], const int32_t d[3], const int32_t *counts, const void *parts, int, int, void *)
+{
+    return box_io(g, o, d, const_cast<int32_t *>(counts), (char *)const_cast<void *>(parts), true);
+}
+
+int b200geo_boxgrid_save(const b200geo_boxgrid *g, const int32_t o[3], const int32_t d[3], int32_t *counts, void *parts, int, void *)
+{
+    return box_io(const_cast<b200geo_boxgrid *>(g), o, d, counts, (char *)parts, false);
+}
+
+static int nbody_sweeps(b200geo_boxgrid *like, int nx, int ny, int nz, const b200geo_nbody_params *p, uint32_t steps,
+                        std::vector<int32_t>& counts, std::vector<char>& parts)
+{
+    if (!(p->cutoff <= like->desc.cell_edge)) return fail(B200GEO_ERR_INVALID, "cutoff larger than the container edge: interactions would be missed");
+    std::vector<int32_t> co(counts.size());
+    std::vector<char> po(parts.size());
+    int rc = oracle_nbody(like->real, nx, ny, nz, like->cap, (int)steps, p->dt, p->cutoff, like->desc.cell_edge, counts.data(), parts.data(), co.data(), po.data());
+    if (rc == -3) {
+        like->overflow = true;
+        return B200GEO_OK;   // reported by b200geo_boxgrid_check, like the device flag
+    }
+    if (rc) return fail(B200GEO_ERR_INVALID, "oracle failed");
+    counts.swap(co);
+    parts.swap(po);
+    return B200GEO_OK;
+}
+
+int b200geo_boxgrid_step(b200geo_boxgrid *g, const b200geo_nbody_params *p, uint32_t, uint32_t n_steps, void *)
+{
+    if (g->desc.ghost_mode[2][0] == B200GEO_GHOST_PEER || g->desc.ghost_mode[2][1] == B200GEO_GHOST_PEER)
+        return fail(B200GEO_ERR_LOGIC, "mock: slabs are stepped through their group");
+    if (n_steps == 0) return B200GEO_OK;
+    return nbody_sweeps(g, g->d[0], g->d[1], g->d[2], p, n_steps, g->counts, g->parts);
+}
+
+int b200geo_boxgrid_check(b200geo_boxgrid *g, void *)
+{
+    if (g->overflow) {
+        g->overflow = false;
+        return fail(B200GEO_ERR_OUT_OF_RANGE, "capacity exceeded");
+    }
+    return B200GEO_OK;
+}
+
+int b200geo_boxgrid_halo_block(const b200geo_boxgrid *, int, int, int, int, void **, uint64_t *) { return fail(B200GEO_ERR_LOGIC, "not in the mock"); }
+int b200geo_boxgrid_halo_mark_valid(b200geo_boxgrid *, int, int) { return B200GEO_OK; }
+
+int b200geo_boxgroup_create(b200geo_boxgrid *const *grids, int n, b200geo_boxgroup **out)
+{
+    if (!grids || !out || n < 1 || n > 16) return fail(B200GEO_ERR_INVALID, "bad slab group");
+    b200geo_boxgroup *grp = new b200geo_boxgroup();
+    grp->g.assign(grids, grids + n);
+    grp->exchanges = grp->bytes = 0;
+    *out = grp;
+    return B200GEO_OK;
+}
+
+int b200geo_boxgroup_destroy(b200geo_boxgroup *grp) { delete grp; return B200GEO_OK; }
+
+int b200geo_boxgroup_step(b200geo_boxgroup *grp, const b200geo_nbody_params *p, uint32_t, uint32_t n_steps)
+{
+    if (n_steps == 0) return B200GEO_OK;
+    b200geo_boxgrid *g0 = grp->g[0];
+    std::vector<int32_t> counts;
+    std::vector<char> parts;
+    int nz = 0;
+    for (size_t s = 0; s < grp->g.size(); ++s) {   // slabs along z are contiguous blocks of the dense arrays
+        b200geo_boxgrid *g = grp->g[s];
+        counts.insert(counts.end(), g->counts.begin(), g->counts.end());
+        parts.insert(parts.end(), g->parts.begin(), g->parts.end());
+        nz += g->d[2];
+    }
+    // the assembled space starts at container (0, 0, 0), which is what the oracle assumes
+    int rc = nbody_sweeps(g0, g0->d[0], g0->d[1], nz, p, n_steps, counts, parts);
+    if (rc) return rc;
+    size_t c = 0;
+    for (size_t s = 0; s < grp->g.size(); ++s) {
+        b200geo_boxgrid *g = grp->g[s];
+        std::copy(counts.begin() + c, counts.begin() + c + g->counts.size(), g->counts.begin());
+        memcpy(g->parts.data(), &parts[c * box_cell_bytes(g0)], g->parts.size());
+        c += g->counts.size();
+        if (g0->overflow) g->overflow = true;
+    }
+    if (grp->g.size() > 1) grp->exchanges += n_steps;
+    return B200GEO_OK;
+}
+
+int b200geo_boxgroup_sync(b200geo_boxgroup *) { return B200GEO_OK; }
+int b200geo_boxgroup_stats(const b200geo_boxgroup *grp, uint64_t out[2]) { out[0] = grp->exchanges; out[1] = grp->bytes; return B200GEO_OK; }
+
+}

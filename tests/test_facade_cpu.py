@@ -1,0 +1,25 @@
+"""Host logic of the C++ façade on the CPU: tests/facade/facade_test.cpp and striping_test.cpp — the very objects
+the GPU suite runs — linked against tests/facade/mock_b200geo.cpp, a host-memory stand-in for libb200geo.so that
+implements the C ABI on plain arrays and delegates the sweeps to the oracle. What this covers without a GPU:
+B200Grid (combined writes, cached rows, region / member byte streams against the reference's SoAGrid, status code ->
+exception mapping), B200StripedGrid / B200StripedBoxGrid (routing across slabs, region split, slab bookkeeping),
+B200Simulator / B200StripingSimulator (event protocol against the reference's MockWriter / MockSteerer, step fusing,
+Steerer writes), the reference's SerialBOVWriter on both — each case beside the reference's SerialSimulator in the same
+process. The kernels and the halo schedule themselves are GPU-tested (tests/test_facade_gpu.py)."""
+import os
+import subprocess
+
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.mark.parametrize("name", ["facade_test_cpu", "striping_test_cpu"])
+def test_cpp_facade_host_logic_on_the_mock_engine(name):
+    binary = os.path.join(HERE, "facade", "_bin", name)
+    if not os.access(binary, os.X_OK):
+        pytest.skip("tests/facade/_bin/%s not built (needs /root/reference at build time)" % name)
+    res = subprocess.run([binary], capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-4000:] + res.stderr[-2000:]
+    assert "all checks passed" in res.stdout
+    assert "MISMATCH" not in res.stdout and "DIFFERENT" not in res.stdout
