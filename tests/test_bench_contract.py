@@ -1,0 +1,40 @@
+"""The JSON line bench.py prints: keys and types the driver and the judge rely on (both arms)."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BASE_KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+             "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches"}
+
+
+def run_bench(*args):
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py")] + list(args), capture_output=True, text=True,
+                         timeout=900, cwd=ROOT)
+    assert res.returncode == 0, res.stderr[-3000:]
+    lines = [l for l in res.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1, res.stdout[-2000:]
+    return json.loads(lines[0])
+
+
+def check_common(d):
+    assert BASE_KEYS <= set(d), sorted(BASE_KEYS - set(d))
+    assert d["metric"].startswith("GLUPS") and d["unit"] == "GLUPS" and d["higher_is_better"] is True
+    assert d["vs_baseline"] is None and d["data"] == "synthetic" and d["scaling"] == "weak"
+    assert d["value"] > 0 and d["ms_per_step"] > 0
+    assert "workload" in d["config"] and "model" not in d["config"]
+    for k in ("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"):
+        assert k in d["e2e"], k
+
+
+def test_reference_arm_line():
+    """bench.py --impl reference: the reference's own CPU implementation (oracle/_ref, or the C port) on a bounded sample"""
+    d = run_bench("--impl", "reference", "--workload", "jacobi7_128", "--steps", "2", "--warmup", "0")
+    check_common(d)
+    assert d["impl"] == "reference" and d["gpu_launches"] == 0
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
+    cb = d["cpu_baseline"]
+    assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["sample"] and cb["value"] == d["value"]
