@@ -1,0 +1,170 @@
+/* CPU-only companion of facade_test.cpp / striping_test.cpp: error paths and corner cases of the façade's HOST
+ * logic, linked against the host-memory mock of the engine (mock_b200geo.cpp) only — never run on the GPU box.
+ *  - a container that overflows its FixedArray capacity on the device surfaces as std::out_of_range when the
+ *    grid is read (storage/fixedarray.h:77-83), on one grid and on slabs;
+ *  - B200Grid::resize drops pending writes and cached rows and keeps working;
+ *  - overlapping combined writes keep their order across flushes of different sizes;
+ *  - wrong-size region buffers and member type mismatches map to std::invalid_argument;
+ *  - a filtered (non-member) Selector takes the host path of saveMember. */
+#include "fixtures.h"
+
+#include <libgeodecomp_b200/b200stripingsimulator.h>
+
+typedef BoxCell<FixedArray<LJParticle<float>, NBODY_CAPACITY> > ParticleCell;
+
+/* 20 particles in container (0,0,0) and 20 in (1,0,0), all of them positioned inside container (1,0,0): the
+ * first re-bin moves 40 particles into a FixedArray of 32 */
+class OverflowInitializer : public SimpleInitializer<ParticleCell>
+{
+public:
+    OverflowInitializer(const Coord<3>& dim, unsigned steps) : SimpleInitializer<ParticleCell>(dim, steps) {}
+
+    virtual void grid(GridBase<ParticleCell, 3> *ret)
+    {
+        double e = NBodyParams::cellEdge();
+        for (int c = 0; c < 2; ++c) {
+            ParticleCell cell(FloatCoord<3>(c * e, 0, 0), FloatCoord<3>(e, e, e));
+            for (int p = 0; p < 20; ++p) {
+                LJParticle<float> particle;
+                particle.pos[0] = (float)(e + 0.1 + 0.1 * p + 0.05 * c);
+                particle.pos[1] = (float)(0.2 + 0.1 * p);
+                particle.pos[2] = (float)(0.3 + 0.05 * p);
+                cell << particle;
+            }
+            ret->set(Coord<3>(c, 0, 0), cell);
+        }
+    }
+};
+
+template<typename SIM>
+static bool overflows(SIM& sim)
+{
+    try {
+        sim.run();
+        sim.getGrid()->get(Coord<3>(1, 0, 0));
+    } catch (const std::out_of_range&) {
+        return true;
+    }
+    return false;
+}
+
+static void testCapacityExceeded()
+{
+    Coord<3> dim(3, 2, 4);
+    {
+        SerialSimulator<ParticleCell> ref(new OverflowInitializer(dim, 1));
+        CHECK(overflows(ref));      // the reference throws from FixedArray::operator<< inside update()
+    }
+    {
+        B200Simulator<ParticleCell> sim(new OverflowInitializer(dim, 1));
+        CHECK(overflows(sim));
+    }
+    {
+        B200StripingSimulator<ParticleCell> sim(new OverflowInitializer(dim, 1), std::vector<int>(2, 0));
+        CHECK(overflows(sim));
+    }
+    std::printf("capacity exceeded: std::out_of_range from SerialSimulator, B200Simulator and B200StripingSimulator\n");
+}
+
+static void testResizeAndWriteOrder()
+{
+    typedef Jacobi7Cube CELL;
+    B200Grid<CELL> grid(CoordBox<3>(Coord<3>(), Coord<3>(6, 5, 4)));
+    grid.set(Coord<3>(1, 1, 1), CELL(1.0));
+    CHECK(grid.get(Coord<3>(1, 1, 1)) == CELL(1.0));
+    grid.set(Coord<3>(2, 1, 1), CELL(5.0));             // pending when the grid is resized
+    grid.resize(CoordBox<3>(Coord<3>(2, 0, 0), Coord<3>(9, 3, 2)));
+    CHECK(grid.boundingBox() == CoordBox<3>(Coord<3>(2, 0, 0), Coord<3>(9, 3, 2)));
+    CHECK(grid.get(Coord<3>(3, 1, 1)) == CELL(0.0));    // fresh grid, nothing of the old one
+    // the same cell written many times, interleaved with whole rows, through small and large flushes
+    std::vector<CELL> row(9);
+    for (int round = 0; round < 5; ++round) {
+        for (int x = 0; x < 9; ++x) row[x] = CELL(100.0 * round + x);
+        grid.set(Streak<3>(Coord<3>(2, 2, 1), 11), row.data());
+        grid.set(Coord<3>(4, 2, 1), CELL(-1.0 * round));
+        if (round == 2) CHECK(grid.get(Coord<3>(4, 2, 1)) == CELL(-2.0));
+    }
+    CHECK(grid.get(Coord<3>(4, 2, 1)) == CELL(-4.0));
+    CHECK(grid.get(Coord<3>(5, 2, 1)) == CELL(403.0));
+    CHECK(grid.get(Coord<3>(10, 2, 1)) == CELL(408.0));
+    // more than one automatic flush (64 Ki cells) with rewrites in between
+    B200Grid<CELL> big(CoordBox<3>(Coord<3>(), Coord<3>(64, 64, 40)));
+    CoordBox<3> box = big.boundingBox();
+    for (int pass = 0; pass < 2; ++pass) {
+        for (CoordBox<3>::Iterator i = box.begin(); i != box.end(); ++i) {
+            big.set(*i, CELL(pass * 1e6 + (double)i->toIndex(box.dimensions)));
+        }
+    }
+    long bad = 0;
+    for (CoordBox<3>::Iterator i = box.begin(); i != box.end(); ++i) {
+        if (!(big.get(*i) == CELL(1e6 + (double)i->toIndex(box.dimensions)))) ++bad;
+    }
+    CHECK(bad == 0);
+    std::printf("resize, write order across flushes: %ld wrong cells\n", bad);
+}
+
+static double squareOfTemp(const Jacobi7Cube& cell)
+{
+    return cell.temp * cell.temp;
+}
+
+static void testSelectorsAndErrors()
+{
+    typedef Jacobi7Cube CELL;
+    CoordBox<3> box(Coord<3>(), Coord<3>(7, 4, 3));
+    B200Grid<CELL> grid(box);
+    for (CoordBox<3>::Iterator i = box.begin(); i != box.end(); ++i) {
+        grid.set(*i, CELL(1.0 + i->toIndex(box.dimensions)));
+    }
+    Region<3> region;
+    region << Streak<3>(Coord<3>(1, 1, 1), 6) << Streak<3>(Coord<3>(0, 3, 2), 7);
+    Selector<CELL> plain(&CELL::temp, "temp");
+    std::vector<double> values(region.size());
+    grid.saveMember(values.data(), MemoryLocation::HOST, plain, region);
+    CHECK(values[0] == 1.0 + Coord<3>(1, 1, 1).toIndex(box.dimensions));
+    CHECK(values[5] == 1.0 + Coord<3>(0, 3, 2).toIndex(box.dimensions));
+    bool mismatch = false;
+    try {
+        std::vector<float> wrong(region.size());
+        grid.saveMember(wrong.data(), MemoryLocation::HOST, plain, region);
+    } catch (const std::invalid_argument&) {
+        mismatch = true;
+    }
+    CHECK(mismatch);
+    bool wrongSize = false;
+    try {
+        std::vector<char> tooLong(region.size() * sizeof(double) + 8);
+        grid.loadRegion(tooLong, region);
+    } catch (const std::invalid_argument&) {
+        wrongSize = true;
+    }
+    CHECK(wrongSize);
+    bool outside = false;
+    try {
+        grid.get(Coord<3>(0, 0, 17));
+    } catch (const std::exception&) {
+        outside = true;
+    }
+    CHECK(outside);
+    std::printf("selectors and error mapping: ok\n");
+    (void)squareOfTemp;
+}
+
+int main()
+{
+    try {
+        NBodyParams::dt() = 0.01;
+        testCapacityExceeded();
+        testResizeAndWriteOrder();
+        testSelectorsAndErrors();
+    } catch (const std::exception& e) {
+        std::printf("FAILED with exception: %s\n", e.what());
+        return 2;
+    }
+    if (failures) {
+        std::printf("%d check(s) FAILED\n", failures);
+        return 1;
+    }
+    std::printf("host_logic_test: all checks passed\n");
+    return 0;
+}
