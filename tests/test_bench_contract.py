@@ -38,3 +38,18 @@ def test_reference_arm_line():
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
     cb = d["cpu_baseline"]
     assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["sample"] and cb["value"] == d["value"]
+@pytest.mark.gpu
+def test_device_arm_line():
+    """the device arm on the small workload (configs[0]); the secondary workloads are switched off to keep it short"""
+    d = run_bench("--workload", "jacobi7_128", "--steps", "20", "--warmup", "3", "--no-others")
+    check_common(d)
+    assert "impl" not in d and d["n_gpus"] == 1 and d["gpu_launches"] >= 20 and d["dtype"] == "f64"
+    r = d["roofline"]
+    for k in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
+        assert k in r, k
+    assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0 and d["e2e"]["value"] > 0
+    assert d["e2e"]["value"] < d["value"]          # the copies are inside the timed region
+    assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(d["clocks"])
+    cb = d["cpu_baseline"]
+    assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["unit"] == "GLUPS"
