@@ -10,6 +10,8 @@
 
 #include <libgeodecomp_b200/b200stripingsimulator.h>
 
+#include "models/lbm_aos.h"
+
 typedef BoxCell<FixedArray<LJParticle<float>, NBODY_CAPACITY> > ParticleCell;
 
 /* 20 particles in container (0,0,0) and 20 in (1,0,0), all of them positioned inside container (1,0,0): the
@@ -150,10 +152,59 @@ static void testSelectorsAndErrors()
     (void)squareOfTemp;
 }
 
+/* The AoS form of the D3Q19 cell (oracle/models/lbm_aos.h, used by the GPU comparator and the generic-path test) is the
+ * same model as the SoA / updateLineX cell the hand-written kernel is bound to: both through the reference's
+ * SerialSimulator (VanillaUpdateFunctor-free FixedCoord path vs FixedNeighborhoodUpdateFunctor), member by member. */
+class CavityAoSInitializer : public SimpleInitializer<LBMCellAoS>
+{
+public:
+    CavityAoSInitializer(const Coord<3>& dim, unsigned steps) : SimpleInitializer<LBMCellAoS>(dim, steps) {}
+
+    virtual void grid(GridBase<LBMCellAoS, 3> *ret)
+    {
+        // the very cells LBMInitializer produces, converted member by member
+        CoordBox<3> box = ret->boundingBox();
+        SoAGrid<LBMCellF, Topologies::Cube<3>::Topology> tmp(box);
+        LBMInitializer(gridDimensions(), 1).grid(&tmp);
+        for (CoordBox<3>::Iterator i = box.begin(); i != box.end(); ++i) {
+            ret->set(*i, convert(tmp.get(*i)));
+        }
+    }
+
+    static LBMCellAoS convert(const LBMCellF& c)
+    {
+        LBMCellAoS a(c.C, c.state);
+        a.N = c.N; a.E = c.E; a.W = c.W; a.S = c.S; a.T = c.T; a.B = c.B;
+        a.NW = c.NW; a.SW = c.SW; a.NE = c.NE; a.SE = c.SE;
+        a.TW = c.TW; a.BW = c.BW; a.TE = c.TE; a.BE = c.BE;
+        a.TN = c.TN; a.BN = c.BN; a.TS = c.TS; a.BS = c.BS;
+        a.density = c.density; a.velocityX = c.velocityX; a.velocityY = c.velocityY; a.velocityZ = c.velocityZ;
+        return a;
+    }
+};
+
+static void testAoSAndSoALBMModelsAgree()
+{
+    Coord<3> dim(14, 9, 8);
+    unsigned steps = 12;
+    SerialSimulator<LBMCellF> soa(new LBMInitializer(dim, steps));
+    SerialSimulator<LBMCellAoS> aos(new CavityAoSInitializer(dim, steps));
+    soa.run();
+    aos.run();
+    long bad = 0;
+    CoordBox<3> box(Coord<3>(), dim);
+    for (CoordBox<3>::Iterator i = box.begin(); i != box.end(); ++i) {
+        if (!(CavityAoSInitializer::convert(soa.getGrid()->get(*i)) == aos.getGrid()->get(*i))) ++bad;
+    }
+    CHECK(bad == 0);
+    std::printf("LBM: AoS update() model vs SoA updateLineX model through SerialSimulator: %ld differing cells after %u steps\n", bad, steps);
+}
+
 int main()
 {
     try {
         NBodyParams::dt() = 0.01;
+        testAoSAndSoALBMModelsAgree();
         testCapacityExceeded();
         testResizeAndWriteOrder();
         testSelectorsAndErrors();
