@@ -87,7 +87,9 @@ class HaloExchanger:
             for kind in (0, 1):
                 st = self._slice_streaks(side, kind)
                 cells = int((st[:, 3] - st[:, 0]).sum())
-                buf = torch.empty(cells * self.grid.model.cell_dtype.itemsize, dtype=torch.uint8, device="cuda")
+                # device memory for the real engine; the CPU test engine (tests/cpu_engine.py) names its own
+                where = getattr(self.grid.engine, "staging_device", "cuda")
+                buf = torch.empty(cells * self.grid.model.cell_dtype.itemsize, dtype=torch.uint8, device=where)
                 self._staging[(side, kind)] = (st, buf)
 
     def post(self, which=0):

@@ -2,12 +2,17 @@
 reference's stepper tests, storage/mockpatchaccepter.h): the same DeviceGrid interface as
 libgeodecomp_b200.capi, backed by numpy arrays and the oracle, so that the host-side slab / ghost-zone /
 halo-exchange logic of libgeodecomp_b200.striping can be exercised with gloo on a machine without a GPU.
-Never imported by the product. Cube topologies only."""
+Never imported by the product. Cube topologies only; Jacobi (one f64 member) and LBM D3Q19 (24 members)."""
 import numpy as np
 import torch
 
 from libgeodecomp_b200 import capi
 from oracle import oracle_py
+
+
+staging_device = "cpu"   # where striping.HaloExchanger allocates its packed halo buffers for this engine
+
+_JACOBI = {capi.KERNEL_JACOBI6: 6, capi.KERNEL_JACOBI7: 7, capi.KERNEL_JACOBI27: 27}
 
 
 class _Block:
@@ -52,6 +57,8 @@ class DeviceGrid:
         ox, oy, oz = origin
         gz = self.ghost[2]
         a = np.asarray(src).reshape(dim[2], dim[1], dim[0])
+        if a.dtype != self.arr[member].dtype:      # e.g. the int32 state member of the LBM cell: keep the bits
+            a = np.ascontiguousarray(a).view(self.arr[member].dtype)
         for buf in (self.bufs if both else [self.arr]):
             buf[member][oz + gz:oz + gz + dim[2], oy:oy + dim[1], ox:ox + dim[0]] = a
 
@@ -59,7 +66,56 @@ class DeviceGrid:
         dim = self.dim if dim is None else dim
         ox, oy, oz = origin
         gz = self.ghost[2]
-        dst.reshape(dim[2], dim[1], dim[0])[...] = self.arr[member][oz + gz:oz + gz + dim[2], oy:oy + dim[1], ox:ox + dim[0]]
+        out = dst.reshape(dim[2], dim[1], dim[0])
+        if out.dtype != self.arr[member].dtype:
+            out = out.view(self.arr[member].dtype)
+        out[...] = self.arr[member][oz + gz:oz + gz + dim[2], oy:oy + dim[1], ox:ox + dim[0]]
+
+    def _sweeps(self, kernel, planes, n):
+        """n sweeps of the kernel family over the padded planes [planes) of the current buffer, all sides treated
+        as domain boundaries by the oracle; returns one dense array per member"""
+        if kernel in _JACOBI:
+            dense = np.ascontiguousarray(self.arr[0][planes])
+            return [oracle_py.jacobi(_JACOBI[kernel], False, dense, n, edge=float(self.edge[0]))]
+        if kernel == capi.KERNEL_LBM_D3Q19:
+            raw = np.stack([np.ascontiguousarray(self.arr[m][planes]).view(np.float32) for m in range(24)])
+            out = oracle_py.lbm(raw, n)
+            return [out[m].view(self.arr[m].dtype) for m in range(24)]
+        raise capi.LogicError("no kernel bound for this id in the CPU mock")
+
+    def _region(self, streaks, buf, save, both=False):
+        """member-major (de)serialisation of streaks {x, y, z, endX}; this mock keeps no x / y ghost cells, so the
+        parts of a streak outside the interior read as zero and are skipped on load"""
+        st = np.asarray(streaks, dtype=np.int64).reshape(-1, 4)
+        count = int((st[:, 3] - st[:, 0]).sum())
+        raw = buf.numpy() if hasattr(buf, "numpy") else np.asarray(buf)
+        raw = raw.reshape(-1).view(np.uint8)
+        nx, ny, nz = self.dim
+        gz = self.ghost[2]
+        moff = 0
+        for m, b in enumerate(self.member_bytes):
+            block = raw[moff:moff + count * b].view(self.arr[m].dtype)
+            pos = 0
+            for x0, y, z, x1 in st:
+                n = int(x1 - x0)
+                a, e = max(int(x0), 0), min(int(x1), nx)
+                if 0 <= y < ny and a < e:
+                    seg = slice(pos + a - int(x0), pos + e - int(x0))
+                    if save:
+                        block[seg] = self.arr[m][z + gz, y, a:e]
+                    else:
+                        for bufs in (self.bufs if both else [self.arr]):
+                            bufs[m][z + gz, y, a:e] = block[seg]
+                elif save:
+                    block[pos:pos + n] = 0
+                pos += n
+            moff += count * b
+
+    def save_region(self, streaks, buf, location=0, stream=None):
+        self._region(streaks, buf, True)
+
+    def load_region(self, streaks, buf, location=0, both=True, stream=None):
+        self._region(streaks, buf, False, both)
 
     def step(self, kernel, n_steps=1, first_nano_step=0, params=None, stream=None):
         gz, nz = self.ghost[2], self.dim[2]
@@ -73,13 +129,11 @@ class DeviceGrid:
                         lo = self.valid[0]
                     else:
                         hi = self.valid[1]
-            sl = slice(gz - lo, gz + nz + hi)
-            dense = np.ascontiguousarray(self.arr[0][sl])
-            kind = {capi.KERNEL_JACOBI6: 6, capi.KERNEL_JACOBI7: 7, capi.KERNEL_JACOBI27: 27}[kernel]
-            out = oracle_py.jacobi(kind, False, dense, 1, edge=float(self.edge[0]))
+            outs = self._sweeps(kernel, slice(gz - lo, gz + nz + hi), 1)
             # the outermost plane on a PEER side had no valid neighbour: drop it
-            a, b = (1 if lo else 0), (out.shape[0] - (1 if hi else 0))
-            self.bufs[self.cur ^ 1][0][gz - lo + a:gz - lo + b] = out[a:b]
+            for m, out in enumerate(outs):
+                a, b = (1 if lo else 0), (out.shape[0] - (1 if hi else 0))
+                self.bufs[self.cur ^ 1][m][gz - lo + a:gz - lo + b] = out[a:b]
             self.cur ^= 1
             for side in (0, 1):
                 if self.mode[2][side] == capi.GHOST_PEER:
@@ -94,10 +148,8 @@ class DeviceGrid:
         a = z0 - n_sweeps if (z0 - n_sweeps >= 0 or self.mode[2][0] == capi.GHOST_PEER) else 0
         b = z1 + n_sweeps if (z1 + n_sweeps <= nz or self.mode[2][1] == capi.GHOST_PEER) else nz
         assert a >= -self.valid[0] and b <= nz + self.valid[1], "ghost zone exhausted"
-        dense = np.ascontiguousarray(self.arr[0][gz + a:gz + b])
-        kind = {capi.KERNEL_JACOBI6: 6, capi.KERNEL_JACOBI7: 7, capi.KERNEL_JACOBI27: 27}[kernel]
-        out = oracle_py.jacobi(kind, False, dense, n_sweeps, edge=float(self.edge[0]))
-        self.bufs[self.cur ^ 1][0][gz + z0:gz + z1] = out[z0 - a:z1 - a]
+        for m, out in enumerate(self._sweeps(kernel, slice(gz + a, gz + b), n_sweeps)):
+            self.bufs[self.cur ^ 1][m][gz + z0:gz + z1] = out[z0 - a:z1 - a]
 
     def swap(self):
         self.cur ^= 1
