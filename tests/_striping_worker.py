@@ -49,6 +49,22 @@ def main():
         want = oracle_py.jacobi(kind, False, data, steps, edge=0.75)[b[rank]:b[rank + 1]]
         if mine.shape != want.shape or not np.array_equal(mine, want):
             failures.append("kind %d ghost %d overlap %s rank %d" % (kind, ghost, overlap, rank))
+    # Torus: the slab ring is closed (rank 0's low neighbour is the last rank; with two ranks both neighbours are the
+    # same rank and the messages are told apart by posting order)
+    for kind, ghost, steps, shape, overlap in [(27, 2, 7, (12, 5, 6), True), (6, 1, 5, (9, 4, 7), True), (7, 3, 8, (18, 4, 5), False),
+                                               (27, 1, 4, (6, 6, 6), False)]:
+        nz, ny, nx = shape
+        data = synth.jacobi_grid(nx, ny, nz, seed=kind + 100)
+        model = models.ALL["Jacobi%dTorus" % kind]
+        sim = StripedSimulator(SlabInit(data, steps, 0.0), model, rank=rank, world=world, ghost_width=ghost,
+                               dist=dist, engine=cpu_engine, overlap=overlap)
+        sim.run()
+        b = slab_bounds(nz, world)
+        mine = sim.getGrid().saveMember("temp")
+        want = oracle_py.jacobi(kind, True, data, steps)[b[rank]:b[rank + 1]]
+        if mine.shape != want.shape or not np.array_equal(mine, want):
+            failures.append("torus kind %d ghost %d overlap %s rank %d" % (kind, ghost, overlap, rank))
+
     # LBM D3Q19 (24 members): ghost width 1 ships only the populations that cross the face, member by member and in
     # place, with the rim-first schedule; ghost width 2 packs whole cells with saveRegion / loadRegion
     class LBMInit(SimpleInitializer):

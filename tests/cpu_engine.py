@@ -2,7 +2,7 @@
 reference's stepper tests, storage/mockpatchaccepter.h): the same DeviceGrid interface as
 libgeodecomp_b200.capi, backed by numpy arrays and the oracle, so that the host-side slab / ghost-zone /
 halo-exchange logic of libgeodecomp_b200.striping can be exercised with gloo on a machine without a GPU.
-Never imported by the product. Cube topologies only; Jacobi (one f64 member) and LBM D3Q19 (24 members)."""
+Never imported by the product. Jacobi (one f64 member; Cube and Torus) and LBM D3Q19 (24 members, Cube)."""
 import numpy as np
 import torch
 
@@ -76,7 +76,10 @@ class DeviceGrid:
         as domain boundaries by the oracle; returns one dense array per member"""
         if kernel in _JACOBI:
             dense = np.ascontiguousarray(self.arr[0][planes])
-            return [oracle_py.jacobi(_JACOBI[kernel], False, dense, n, edge=float(self.edge[0]))]
+            # Torus: x and y wrap inside the oracle; its z wrap only reaches the n outermost planes of the range,
+            # which are ghost planes of a slab (dropped by the callers) or, on a single rank, the true images
+            torus = self.mode[0][0] == capi.GHOST_WRAP
+            return [oracle_py.jacobi(_JACOBI[kernel], torus, dense, n, edge=float(self.edge[0]))]
         if kernel == capi.KERNEL_LBM_D3Q19:
             raw = np.stack([np.ascontiguousarray(self.arr[m][planes]).view(np.float32) for m in range(24)])
             out = oracle_py.lbm(raw, n)
