@@ -383,7 +383,7 @@ int oracle_load_region(int nx, int ny, int nz, int n_members, const int *member_
  */
 #define DEFINE_NBODY(NAME, REAL)                                                                   \
 static int NAME(int nx, int ny, int nz, int cap, int steps, double dt_, double cutoff, double edge,\
-                const int32_t *cin, const REAL *pin, int32_t *cout, REAL *pout)                    \
+                const int *org, const int32_t *cin, const REAL *pin, int32_t *cout, REAL *pout)    \
 {                                                                                                  \
     size_t cells = (size_t)nx * ny * nz;                                                           \
     int32_t *c0 = malloc(cells * sizeof(int32_t)), *c1 = malloc(cells * sizeof(int32_t));          \
@@ -399,7 +399,7 @@ static int NAME(int nx, int ny, int nz, int cap, int steps, double dt_, double c
             for (int y = 0; y < ny; ++y) {                                                         \
                 for (int x = 0; x < nx; ++x) {                                                     \
                     size_t self = ((size_t)z * ny + y) * nx + x;                                   \
-                    double o[3] = {x * edge, y * edge, z * edge};                                  \
+                    double o[3] = {(x + org[0]) * edge, (y + org[1]) * edge, (z + org[2]) * edge}; \
                     double q[3] = {o[0] + edge, o[1] + edge, o[2] + edge};                         \
                     REAL *mine = p1 + self * cap * 6;                                              \
                     int n = 0;                                                                     \
@@ -463,12 +463,19 @@ static int NAME(int nx, int ny, int nz, int cap, int steps, double dt_, double c
 DEFINE_NBODY(nbody_f32, float)
 DEFINE_NBODY(nbody_f64, double)
 
+int oracle_nbody_at(int real_bytes, int nx, int ny, int nz, int cap, int steps, double dt, double cutoff, double edge,
+                    const int origin[3], const int32_t *counts_in, const void *parts_in, int32_t *counts_out, void *parts_out)
+{
+    if (real_bytes == 4)
+        return nbody_f32(nx, ny, nz, cap, steps, dt, cutoff, edge, origin, counts_in, (const float *)parts_in, counts_out, (float *)parts_out);
+    if (real_bytes == 8)
+        return nbody_f64(nx, ny, nz, cap, steps, dt, cutoff, edge, origin, counts_in, (const double *)parts_in, counts_out, (double *)parts_out);
+    return -1;
+}
+
 int oracle_nbody(int real_bytes, int nx, int ny, int nz, int cap, int steps, double dt, double cutoff, double edge,
                  const int32_t *counts_in, const void *parts_in, int32_t *counts_out, void *parts_out)
 {
-    if (real_bytes == 4)
-        return nbody_f32(nx, ny, nz, cap, steps, dt, cutoff, edge, counts_in, (const float *)parts_in, counts_out, (float *)parts_out);
-    if (real_bytes == 8)
-        return nbody_f64(nx, ny, nz, cap, steps, dt, cutoff, edge, counts_in, (const double *)parts_in, counts_out, (double *)parts_out);
-    return -1;
+    const int origin[3] = {0, 0, 0};
+    return oracle_nbody_at(real_bytes, nx, ny, nz, cap, steps, dt, cutoff, edge, origin, counts_in, parts_in, counts_out, parts_out);
 }

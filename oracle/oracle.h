@@ -50,6 +50,10 @@ int oracle_load_region(int nx, int ny, int nz, int n_members, const int *member_
  * reference, storage/fixedarray.h:77-83). */
 int oracle_nbody(int real_bytes, int nx, int ny, int nz, int cap, int steps, double dt, double cutoff, double edge,
                  const int32_t *counts_in, const void *parts_in, int32_t *counts_out, void *parts_out);
+/* the same for a block of containers whose container (0,0,0) is container `origin` of a larger grid (container
+ * (x, y, z) covers [(c + origin) * edge, + edge) per axis); everything outside the block is empty */
+int oracle_nbody_at(int real_bytes, int nx, int ny, int nz, int cap, int steps, double dt, double cutoff, double edge,
+                    const int origin[3], const int32_t *counts_in, const void *parts_in, int32_t *counts_out, void *parts_out);
 
 #ifdef __cplusplus
 }

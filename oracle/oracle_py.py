@@ -59,7 +59,7 @@ def lbm(raw, steps):
     return out
 
 
-def nbody(counts, parts, steps, dt=0.005, cutoff=2.5, edge=2.5):
+def nbody(counts, parts, steps, dt=0.005, cutoff=2.5, edge=2.5, origin=(0, 0, 0)):
     """counts int32 [nz][ny][nx], parts REAL [nz][ny][nx][cap][6] -> (counts, parts) after `steps`.
     Raises IndexError when a container overflows (std::out_of_range in the reference)."""
     c = np.ascontiguousarray(counts, dtype=np.int32)
@@ -67,9 +67,10 @@ def nbody(counts, parts, steps, dt=0.005, cutoff=2.5, edge=2.5):
     assert p.dtype in (np.float32, np.float64) and p.shape[:3] == c.shape and p.shape[4] == 6
     nz, ny, nx = c.shape
     co, po = np.empty_like(c), np.empty_like(p)
-    f = lib().oracle_nbody
-    f.argtypes = [ctypes.c_int] * 6 + [ctypes.c_double] * 3 + [ctypes.c_void_p] * 4
-    rc = f(p.dtype.itemsize, nx, ny, nz, p.shape[3], steps, dt, cutoff, edge, _p(c), _p(p), _p(co), _p(po))
+    f = lib().oracle_nbody_at
+    f.argtypes = [ctypes.c_int] * 6 + [ctypes.c_double] * 3 + [ctypes.c_void_p] * 5
+    org = (ctypes.c_int * 3)(*[int(v) for v in origin])
+    rc = f(p.dtype.itemsize, nx, ny, nz, p.shape[3], steps, dt, cutoff, edge, org, _p(c), _p(p), _p(co), _p(po))
     if rc == -3:
         raise IndexError("capacity exceeded")
     assert rc == 0, rc

@@ -90,6 +90,31 @@ def main():
             if not np.array_equal(mine.view(np.int32), want[m, b[rank]:b[rank + 1]].view(np.int32)):
                 failures.append("lbm ghost %d overlap %s member %s rank %d" % (ghost, overlap, name, rank))
                 break
+    # n-body: slabs of BoxCell containers, one ghost plane of containers (counts + particles) per side and sweep;
+    # velocities large enough that particles change containers and slabs
+    class CellInit(SimpleInitializer):
+        def __init__(self, counts, parts, steps):
+            SimpleInitializer.__init__(self, counts.shape[::-1], steps)
+            self.counts, self.parts = counts, parts
+
+        def grid(self, target):
+            o, d = target.boundingBox()
+            sl = tuple(slice(o[i], o[i] + d[i]) for i in reversed(range(3)))
+            target.loadCells(self.counts[sl], self.parts[sl], origin=o)
+
+    for real, dims, steps, vel in [(np.float32, (4, 3, 7), 6, 10.0), (np.float64, (3, 4, 6), 5, 12.0)]:
+        c, p = synth.nbody_cells(*dims, vel=vel, dtype=real)
+        model = (models.NBodyF if real == np.float32 else models.NBodyD).with_params(dt=0.01)
+        sim = StripedSimulator(CellInit(c, p, steps), model, rank=rank, world=world, ghost_width=1, dist=dist, engine=cpu_engine)
+        sim.run()
+        gc, gp = sim.getGrid().saveCells()
+        wc, wp = oracle_py.nbody(c, p, steps, dt=0.01)
+        b = slab_bounds(dims[2], world)
+        moved = not np.array_equal(wc, c)
+        if not (moved and np.array_equal(gc, wc[b[rank]:b[rank + 1]]) and
+                np.array_equal(gp.view(np.uint8), np.ascontiguousarray(wp[b[rank]:b[rank + 1]]).view(np.uint8))):
+            failures.append("nbody %s rank %d" % (np.dtype(real).name, rank))
+
     with open("%s.%d" % (out_path, rank), "w") as f:
         f.write("FAIL " + "; ".join(failures) if failures else "OK")
     dist.barrier()

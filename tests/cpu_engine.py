@@ -2,7 +2,8 @@
 reference's stepper tests, storage/mockpatchaccepter.h): the same DeviceGrid interface as
 libgeodecomp_b200.capi, backed by numpy arrays and the oracle, so that the host-side slab / ghost-zone /
 halo-exchange logic of libgeodecomp_b200.striping can be exercised with gloo on a machine without a GPU.
-Never imported by the product. Jacobi (one f64 member; Cube and Torus) and LBM D3Q19 (24 members, Cube)."""
+Never imported by the product. Jacobi (one f64 member; Cube and Torus), LBM D3Q19 (24 members, Cube) and
+slabs of BoxCell containers (n-body; counts + particles, one ghost plane of containers per side)."""
 import numpy as np
 import torch
 
@@ -167,6 +168,82 @@ class DeviceGrid:
         else:
             z = gz - width if side == 0 else gz + nz
         return _Block(self.bufs[self.cur ^ which][member][z:z + width])
+
+    def halo_mark_valid(self, side, width):
+        self.valid[side] = width
+
+    def stats_enable(self, on=True):
+        pass
+
+
+class DeviceBoxGrid:
+    """capi.DeviceBoxGrid on host arrays: containers in the interchange format (counts [z][y][x], particles
+    [z][y][x][capacity][6]) with one ghost plane of containers per z side; the sweep is the oracle's, run on the slab
+    plus its valid ghost planes at the slab's place in the global container lattice (container origins enter the
+    position check of the re-bin, storage/boxcell.h:150-174)"""
+
+    def __init__(self, dim, capacity, real_bytes, cell_edge, cell_origin=(0, 0, 0), ghost_mode=None, device=0):
+        self.dim, self.capacity, self.cell_edge = tuple(dim), int(capacity), float(cell_edge)
+        self.cell_origin, self.mode = tuple(cell_origin), ghost_mode
+        nx, ny, nz = self.dim
+        real = {4: np.float32, 8: np.float64}[real_bytes]
+        self.bufs = [[np.zeros((nz + 2, ny, nx), dtype=np.int32), np.zeros((nz + 2, ny, nx, capacity, 6), dtype=real)]
+                     for _ in range(2)]
+        self.cur = 0
+        self.valid = [0, 0]
+        self.overflow = False
+
+    def load(self, counts, particles, origin=(0, 0, 0), dim=None, location=0, both=True, stream=None):
+        dim = self.dim if dim is None else dim
+        (ox, oy, oz), (dx, dy, dz) = origin, dim
+        for buf in (self.bufs if both else [self.bufs[self.cur]]):
+            buf[0][oz + 1:oz + 1 + dz, oy:oy + dy, ox:ox + dx] = np.asarray(counts).reshape(dz, dy, dx)
+            buf[1][oz + 1:oz + 1 + dz, oy:oy + dy, ox:ox + dx] = np.asarray(particles).reshape(dz, dy, dx, self.capacity, 6)
+
+    def save(self, counts, particles, origin=(0, 0, 0), dim=None, location=0, stream=None):
+        dim = self.dim if dim is None else dim
+        (ox, oy, oz), (dx, dy, dz) = origin, dim
+        c, p = self.bufs[self.cur]
+        counts.reshape(dz, dy, dx)[...] = c[oz + 1:oz + 1 + dz, oy:oy + dy, ox:ox + dx]
+        particles.reshape(dz, dy, dx, self.capacity, 6)[...] = p[oz + 1:oz + 1 + dz, oy:oy + dy, ox:ox + dx]
+
+    def step(self, kernel, n_steps=1, first_nano_step=0, params=None, stream=None):
+        if kernel != capi.KERNEL_NBODY or not isinstance(params, capi.NBodyParams):
+            raise capi.LogicError("a BoxCell grid steps with KERNEL_NBODY and NBodyParams")
+        nz = self.dim[2]
+        for _ in range(n_steps):
+            lo = hi = 0
+            for side in (0, 1):
+                if self.mode[2][side] == capi.GHOST_PEER:
+                    if self.valid[side] < 1:
+                        raise capi.LogicError("ghost zone exhausted")
+                    lo, hi = (1, hi) if side == 0 else (lo, 1)
+            c, p = self.bufs[self.cur]
+            planes = slice(1 - lo, 1 + nz + hi)
+            org = (self.cell_origin[0], self.cell_origin[1], self.cell_origin[2] - lo)
+            try:
+                oc, op = oracle_py.nbody(c[planes], p[planes], 1, dt=params.dt, cutoff=params.cutoff, edge=self.cell_edge,
+                                         origin=org)
+            except IndexError:      # reported by check(), like the device's sticky overflow flag
+                self.overflow = True
+                return
+            nc, npart = self.bufs[self.cur ^ 1]
+            nc[1:1 + nz], npart[1:1 + nz] = oc[lo:lo + nz], op[lo:lo + nz]
+            self.cur ^= 1
+            for side in (0, 1):
+                if self.mode[2][side] == capi.GHOST_PEER:
+                    self.valid[side] -= 1
+
+    def check(self, stream=None):
+        if self.overflow:
+            raise IndexError("capacity exceeded")
+
+    def halo_block(self, member, side, kind, width=1, which=0):
+        if width != 1:
+            raise ValueError("BoxCell grids have a ghost zone of one container")
+        nz = self.dim[2]
+        z = (1 if side == 0 else nz) if kind == 0 else (0 if side == 0 else nz + 1)
+        return _Block(self.bufs[self.cur ^ which][member][z:z + 1])
 
     def halo_mark_valid(self, side, width):
         self.valid[side] = width
