@@ -93,6 +93,18 @@ uint64_t b200geo_launch_count(void);
 
 /* ---- grid life cycle: replaces SoAGrid::SoAGrid/resize (storage/soagrid.h:380-427) -------- */
 int b200geo_grid_create(const b200geo_grid_desc *desc, int device, b200geo_grid **out);
+/* Same grid in the UNIFORM ELEMENT LAYOUT: all members share one lead-in and one row / plane pitch counted in
+ * elements, and every member array holds exactly `member_stride` elements, so member m starts
+ * member_stride x (bytes of the members before it) into a buffer. That is the addressing contract of
+ * LibFlatArray's soa_accessor (lib/libflatarray/include/libflatarray/macros.hpp:327-349: data + DIM_PROD x
+ * offset<CELL, m> + index x sizeof(member)) with DIM_PROD = member_stride — what lets the generic device path run a
+ * model's SoA-signature updateLineX() with the accessors LIBFLATARRAY_REGISTER_SOA generated
+ * (include/libgeodecomp_b200/b200genericsoa.h). member_stride: a multiple of 256, at least
+ * b200geo_grid_uniform_min_stride(desc). b200geo_grid_member_ptr(g, 0, which) is the accessors' data pointer. */
+int b200geo_grid_create_uniform(const b200geo_grid_desc *desc, int device, int64_t member_stride, b200geo_grid **out);
+int b200geo_grid_uniform_min_stride(const b200geo_grid_desc *desc, int64_t *min_stride);
+/* elements per member array of a uniform-layout grid; 0 for a grid in the default layout */
+int b200geo_grid_member_stride(const b200geo_grid *g, int64_t *member_stride);
 int b200geo_grid_destroy(b200geo_grid *g);
 /* bytes of one of the two buffers (padded layout) */
 int b200geo_grid_buffer_bytes(const b200geo_grid *g, uint64_t *bytes);

@@ -19,9 +19,10 @@
  *  - `*this` inside update() is the cell of the NEW grid, exactly as in VanillaUpdateFunctor
  *    (storage/vanillaupdatefunctor.h:28-32): a model that does not assign every member sees the
  *    value from two sweeps ago, like on the CPU.
- * Not covered here: SoA-signature updateLineX(hoodOld, indexEnd, hoodNew, nanoStep) (its accessors
- * are generated for LibFlatArray's compile-time layouts; such cells need a bound kernel), static data
- * (APITraits::HasStaticData), cells larger than 32 words.
+ * Struct-of-Arrays cells (APITraits::HasSoA + HasUpdateLineX) take the sibling path of b200genericsoa.h:
+ * their SoA-signature updateLineX(hoodOld, indexEnd, hoodNew, nanoStep) runs with the accessors
+ * LIBFLATARRAY_REGISTER_SOA generated for them. Not covered: static data (APITraits::HasStaticData),
+ * word-sliced cells larger than 32 words.
  */
 #ifndef LIBGEODECOMP_B200_B200GENERIC_H
 #define LIBGEODECOMP_B200_B200GENERIC_H
@@ -237,11 +238,9 @@ inline View view(b200geo_grid *g, int which)
     return v;
 }
 
-}
-
-/* Primary template = the generic path. B200GEO_BIND_CELL specialises it for bound cells. */
+/* the word-sliced binding: any cell with a __host__ __device__ update() or AoS-signature updateLineX() */
 template<typename CELL>
-struct B200KernelBinding {
+struct WordSlicedBinding {
     typedef typename APITraits::SelectTopology<CELL>::Value Topology;
     static const int DIM = Topology::DIM;
     static const unsigned NANO_STEPS = APITraits::SelectNanoSteps<CELL>::VALUE;
@@ -323,6 +322,27 @@ struct B200KernelBinding {
         B200Generic::check(b200geo_group_step_with(group, &updateCallback, 0, firstNanoStep, sweeps));
     }
 };
+
+/* which generic binding a cell gets: Struct-of-Arrays cells with an updateLineX() are handed the accessors
+ * LibFlatArray generated for them (b200genericsoa.h) — the route UpdateFunctor takes for them on the CPU
+ * (storage/updatefunctor.h:403-428 -> FixedNeighborhoodUpdateFunctor); every other cell is word-sliced */
+template<typename CELL, typename SOA = typename APITraits::SelectSoA<CELL>::Value,
+         typename LINE = typename APITraits::SelectUpdateLineX<CELL>::Value>
+struct SelectBinding {
+    typedef WordSlicedBinding<CELL> Type;
+};
+
+template<typename CELL>
+struct SelectBinding<CELL, APITraits::TrueType, APITraits::TrueType> {
+    typedef SoA::Binding<CELL, SoA::DeviceSweep> Type;
+};
+
+}
+
+/* Primary template = the generic path. B200GEO_BIND_CELL specialises it for bound cells. */
+template<typename CELL>
+struct B200KernelBinding : public B200Generic::SelectBinding<CELL>::Type
+{};
 
 }
 

@@ -97,6 +97,21 @@ inline void check(int rc)
     }
 }
 
+/* a binding may create the device grid itself (the generic SoA path asks for the uniform element layout,
+ * b200genericsoa.h); bound cells and word-sliced generic cells take the default layout */
+template<typename BINDING>
+inline auto createGrid(const b200geo_grid_desc *desc, int device, b200geo_grid **out, int) ->
+    decltype(BINDING::createGrid(desc, device, out))
+{
+    return BINDING::createGrid(desc, device, out);
+}
+
+template<typename BINDING>
+inline int createGrid(const b200geo_grid_desc *desc, int device, b200geo_grid **out, long)
+{
+    return b200geo_grid_create(desc, device, out);
+}
+
 template<int DIM>
 inline void toStreak4(const Streak<DIM>& s, const Coord<DIM>& origin, int32_t *out)
 {
@@ -112,6 +127,7 @@ inline void toStreak4(const Streak<DIM>& s, const Coord<DIM>& origin, int32_t *o
 
 /* nvcc translation units: cells without a B200GEO_BIND_CELL line take the generic device path
  * (the user's own update() compiled into a kernel); with a host compiler unbound cells do not compile */
+#include "b200genericsoa.h"
 #ifdef __CUDACC__
 #include "b200generic.h"
 #endif
@@ -540,7 +556,7 @@ private:
         for (std::size_t m = 0; m < members.size(); ++m) {
             desc.member_bytes[m] = members[m].bytes;
         }
-        B200Helpers::check(b200geo_grid_create(&desc, device, &handle));
+        B200Helpers::check(B200Helpers::createGrid<B200KernelBinding<CELL> >(&desc, device, &handle, 0));
         setEdge(edgeCell);
     }
 

@@ -59,6 +59,9 @@ SYMBOLS = [
     ("b200geo_launch_count", ctypes.c_uint64, []),
     ("b200geo_set_tuning", ctypes.c_int, [ctypes.c_char_p, ctypes.c_int]),
     ("b200geo_grid_create", ctypes.c_int, [ctypes.POINTER(GridDesc), ctypes.c_int, ctypes.POINTER(_vp)]),
+    ("b200geo_grid_create_uniform", ctypes.c_int, [ctypes.POINTER(GridDesc), ctypes.c_int, ctypes.c_int64, ctypes.POINTER(_vp)]),
+    ("b200geo_grid_uniform_min_stride", ctypes.c_int, [ctypes.POINTER(GridDesc), _i64p]),
+    ("b200geo_grid_member_stride", ctypes.c_int, [_vp, _i64p]),
     ("b200geo_grid_destroy", ctypes.c_int, [_vp]),
     ("b200geo_grid_buffer_bytes", ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_uint64)]),
     ("b200geo_grid_device", ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_int)]),
@@ -181,7 +184,9 @@ class DeviceBlock:
 class DeviceGrid:
     """Thin object wrapper around a b200geo_grid handle."""
 
-    def __init__(self, dim, member_bytes, ghost=(1, 1, 1), ghost_mode=None, device=0):
+    def __init__(self, dim, member_bytes, ghost=(1, 1, 1), ghost_mode=None, device=0, member_stride=None):
+        """member_stride: None = the default padded layout; an element count (or 0 = the smallest valid one) = the
+        uniform element layout of b200geo_grid_create_uniform."""
         self._h = None
         desc = GridDesc()
         dim = list(dim) + [1] * (3 - len(dim))
@@ -197,7 +202,13 @@ class DeviceGrid:
         for m, b in enumerate(member_bytes):
             desc.member_bytes[m] = int(b)
         h = ctypes.c_void_p()
-        check(lib().b200geo_grid_create(ctypes.byref(desc), int(device), ctypes.byref(h)))
+        if member_stride is None:
+            check(lib().b200geo_grid_create(ctypes.byref(desc), int(device), ctypes.byref(h)))
+        else:
+            least = ctypes.c_int64()
+            check(lib().b200geo_grid_uniform_min_stride(ctypes.byref(desc), ctypes.byref(least)))
+            self.member_stride = int(member_stride) if member_stride else least.value
+            check(lib().b200geo_grid_create_uniform(ctypes.byref(desc), int(device), self.member_stride, ctypes.byref(h)))
         self._h = h
         self.dim, self.ghost, self.member_bytes, self.device = tuple(dim), tuple(ghost), list(member_bytes), device
         self.cell_bytes = int(sum(member_bytes))

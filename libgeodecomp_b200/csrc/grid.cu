@@ -95,7 +95,54 @@ uint64_t b200geo_launch_count(void)
     return g_launches.load();
 }
 
+// Geometry of the uniform element layout (b200geo_grid_create_uniform): ONE lead-in and ONE pitch, counted in
+// elements, for all members, so that one element index addresses every member of a cell. The lead-in is 128 bytes
+// of the narrowest member (rows of wider members then start on multiples of 128 bytes as well).
+static void uniform_geometry(const b200geo_grid_desc *desc, int *lead, int64_t *pitch, int64_t *min_stride)
+{
+    int min_e = 8;
+    for (int m = 0; m < desc->n_members; ++m) min_e = desc->member_bytes[m] < min_e ? desc->member_bytes[m] : min_e;
+    if (min_e < 1) min_e = 1;
+    *lead = 128 / min_e;
+    *pitch = round_up((int64_t)*lead + desc->dim[0] + desc->ghost[0], *lead);
+    int64_t elems = *pitch * (desc->dim[1] + 2 * desc->ghost[1]) * (desc->dim[2] + 2 * desc->ghost[2]);
+    *min_stride = round_up(elems + *lead, 256);   // same slack behind the last row as the default layout
+}
+
+static int create_grid(const b200geo_grid_desc *desc, int device, int64_t uniform_stride, b200geo_grid **out);
+
 int b200geo_grid_create(const b200geo_grid_desc *desc, int device, b200geo_grid **out)
+{
+    return create_grid(desc, device, 0, out);
+}
+
+int b200geo_grid_create_uniform(const b200geo_grid_desc *desc, int device, int64_t member_stride, b200geo_grid **out)
+{
+    if (member_stride <= 0 || member_stride % 256 != 0)
+        return fail(B200GEO_ERR_INVALID, "member stride must be a positive multiple of 256 elements");
+    return create_grid(desc, device, member_stride, out);
+}
+
+int b200geo_grid_uniform_min_stride(const b200geo_grid_desc *desc, int64_t *min_stride)
+{
+    if (!desc || !min_stride) return fail(B200GEO_ERR_INVALID, "null argument");
+    if (desc->n_members < 1 || desc->n_members > B200GEO_MAX_MEMBERS)
+        return fail(B200GEO_ERR_INVALID, "n_members out of range");
+    for (int m = 0; m < desc->n_members; ++m) {
+        int e = desc->member_bytes[m];
+        if (e != 1 && e != 2 && e != 4 && e != 8)
+            return fail(B200GEO_ERR_INVALID, "member size must be 1, 2, 4 or 8 bytes");
+    }
+    for (int i = 0; i < 3; ++i)
+        if (desc->dim[i] < 1 || desc->ghost[i] < 0 || desc->ghost[i] > 16)
+            return fail(B200GEO_ERR_INVALID, "grid dimension or ghost width out of range");
+    int lead;
+    int64_t pitch;
+    uniform_geometry(desc, &lead, &pitch, min_stride);
+    return B200GEO_OK;
+}
+
+static int create_grid(const b200geo_grid_desc *desc, int device, int64_t uniform_stride, b200geo_grid **out)
 {
     if (!desc || !out) return fail(B200GEO_ERR_INVALID, "null argument");
     if (desc->n_members < 1 || desc->n_members > B200GEO_MAX_MEMBERS)
@@ -122,6 +169,12 @@ int b200geo_grid_create(const b200geo_grid_desc *desc, int device, b200geo_grid 
             return fail(B200GEO_ERR_INVALID, "member size must be 1, 2, 4 or 8 bytes");
         if (desc->ghost[0] > 128 / e) return fail(B200GEO_ERR_INVALID, "x ghost wider than the 128-byte lead-in");
     }
+    int ulead = 0;
+    int64_t upitch = 0, umin = 0;
+    if (uniform_stride > 0) {
+        uniform_geometry(desc, &ulead, &upitch, &umin);
+        if (uniform_stride < umin) return fail(B200GEO_ERR_INVALID, "member stride smaller than the padded grid");
+    }
     B200GEO_CUDA(cudaSetDevice(device));
 
     b200geo_grid *g = new (std::nothrow) b200geo_grid();
@@ -135,6 +188,7 @@ int b200geo_grid_create(const b200geo_grid_desc *desc, int device, b200geo_grid 
         g->g[i] = desc->ghost[i];
     }
     g->slab_axis = (g->d[2] == 1 && g->g[2] == 0) ? 1 : 2;
+    g->uniform_stride = uniform_stride;
     int64_t off = 0;
     int cell = 0;
     for (int m = 0; m < g->n; ++m) {
@@ -145,17 +199,20 @@ int b200geo_grid_create(const b200geo_grid_desc *desc, int device, b200geo_grid 
         }
         MemberLayout& L = g->m[m];
         L.elem = e;
-        L.lead = 128 / e;
+        L.lead = uniform_stride > 0 ? ulead : 128 / e;
         if (g->g[0] > L.lead) {
             delete g;
             return fail(B200GEO_ERR_INVALID, "x ghost wider than the 128-byte lead-in");
         }
-        L.pitch = round_up((int64_t)(L.lead + g->d[0] + g->g[0]) * e, 128) / e;
+        L.pitch = uniform_stride > 0 ? upitch : round_up((int64_t)(L.lead + g->d[0] + g->g[0]) * e, 128) / e;
         L.plane = L.pitch * (g->d[1] + 2 * g->g[1]);
         L.origin = (int64_t)g->g[2] * L.plane + (int64_t)g->g[1] * L.pitch + L.lead;
         // 128 B of slack: vector accesses of partially valid groups may touch the bytes just past
         // the last row (never stored to, values never used)
         L.bytes = round_up(L.plane * (g->d[2] + 2 * g->g[2]) * e + 128, 256);
+        // uniform layout: every member array has member_stride elements, so member m starts member_stride x
+        // (bytes of the members before it) into the buffer — LibFlatArray's DIM_PROD x offset<CELL, m>
+        if (uniform_stride > 0) L.bytes = uniform_stride * e;
         L.offset = off;
         L.edge_offset = cell;
         off += L.bytes;
@@ -177,6 +234,13 @@ int b200geo_grid_create(const b200geo_grid_desc *desc, int device, b200geo_grid 
     cudaMemset(g->buf[1], 0, (size_t)off);
     for (int i = 0; i < 4; ++i) cudaEventCreate(&g->ev[i]);
     *out = g;
+    return B200GEO_OK;
+}
+
+int b200geo_grid_member_stride(const b200geo_grid *g, int64_t *member_stride)
+{
+    if (!g || !member_stride) return fail(B200GEO_ERR_INVALID, "null argument");
+    *member_stride = g->uniform_stride;
     return B200GEO_OK;
 }
 

@@ -37,6 +37,7 @@ struct b200geo_grid {
     int device;
     int n, g[3], d[3];
     int slab_axis;       // axis slabs are cut along: the last used axis (2, or 1 for 2-D grids)
+    int64_t uniform_stride; // elements per member array in the uniform element layout (0 = default layout)
     b200geo::MemberLayout m[B200GEO_MAX_MEMBERS];
     int64_t buffer_bytes;
     char *buf[2];        // buf[cur] = current, buf[cur ^ 1] = scratch

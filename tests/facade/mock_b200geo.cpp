@@ -25,7 +25,10 @@ struct b200geo_grid {
     b200geo_grid_desc desc;
     int n, d[3], g[3], elem[B200GEO_MAX_MEMBERS], cell_bytes, slab_axis, cur;
     int64_t px, py, pz;                         // padded extents
-    std::vector<char> buf[2][B200GEO_MAX_MEMBERS];
+    std::vector<char> buf[2][B200GEO_MAX_MEMBERS];  // default layout: one array per member
+    std::vector<char> flat[2];                      // uniform element layout: member m at stride * (bytes before m)
+    char *ptr[2][B200GEO_MAX_MEMBERS];
+    int64_t stride;
     unsigned char edge[8 * B200GEO_MAX_MEMBERS];
     uint64_t sweeps;
 
@@ -63,7 +66,7 @@ void gather(const b200geo_grid *g, std::vector<char>& raw)
         const int e = g->elem[m];
         for (int z = 0; z < g->d[2]; ++z)
             for (int y = 0; y < g->d[1]; ++y)
-                memcpy(&raw[off + (((size_t)z * g->d[1] + y) * g->d[0]) * e], &g->buf[g->cur][m][g->index(0, y, z) * e], (size_t)g->d[0] * e);
+                memcpy(&raw[off + (((size_t)z * g->d[1] + y) * g->d[0]) * e], &g->ptr[g->cur][m][g->index(0, y, z) * e], (size_t)g->d[0] * e);
         off += (size_t)g->cells() * e;
     }
 }
@@ -75,7 +78,7 @@ void scatter(b200geo_grid *g, int which, const std::vector<char>& raw)
         const int e = g->elem[m];
         for (int z = 0; z < g->d[2]; ++z)
             for (int y = 0; y < g->d[1]; ++y)
-                memcpy(&g->buf[which][m][g->index(0, y, z) * e], &raw[off + (((size_t)z * g->d[1] + y) * g->d[0]) * e], (size_t)g->d[0] * e);
+                memcpy(&g->ptr[which][m][g->index(0, y, z) * e], &raw[off + (((size_t)z * g->d[1] + y) * g->d[0]) * e], (size_t)g->d[0] * e);
         off += (size_t)g->cells() * e;
     }
 }
@@ -122,10 +125,10 @@ int region(b200geo_grid *g, const int32_t *streaks, int n, char *buf, bool save,
             const int64_t len = k[3] - k[0], at = g->index(k[0], k[1], k[2]) * e;
             char *b = buf + moff + pos * e;
             if (save) {
-                memcpy(b, &g->buf[g->cur][m][at], len * e);
+                memcpy(b, &g->ptr[g->cur][m][at], len * e);
             } else {
-                memcpy(&g->buf[g->cur][m][at], b, len * e);
-                if (both) memcpy(&g->buf[g->cur ^ 1][m][at], b, len * e);
+                memcpy(&g->ptr[g->cur][m][at], b, len * e);
+                if (both) memcpy(&g->ptr[g->cur ^ 1][m][at], b, len * e);
             }
             pos += len;
         }
@@ -145,10 +148,10 @@ int member_box(b200geo_grid *g, int m, const int32_t o[3], const int32_t d[3], c
             char *row = dense + (((size_t)z * d[1] + y) * d[0]) * e;
             const int64_t at = g->index(o[0], o[1] + y, o[2] + z) * e;
             if (load) {
-                memcpy(&g->buf[g->cur][m][at], row, (size_t)d[0] * e);
-                if (both) memcpy(&g->buf[g->cur ^ 1][m][at], row, (size_t)d[0] * e);
+                memcpy(&g->ptr[g->cur][m][at], row, (size_t)d[0] * e);
+                if (both) memcpy(&g->ptr[g->cur ^ 1][m][at], row, (size_t)d[0] * e);
             } else {
-                memcpy(row, &g->buf[g->cur][m][at], (size_t)d[0] * e);
+                memcpy(row, &g->ptr[g->cur][m][at], (size_t)d[0] * e);
             }
         }
     return B200GEO_OK;
@@ -166,7 +169,37 @@ int b200geo_device_count(void) { return 1; }
 int b200geo_set_tuning(const char *, int) { return B200GEO_OK; }
 uint64_t b200geo_launch_count(void) { return 0; }
 
+static int create_grid(const b200geo_grid_desc *desc, int64_t stride, b200geo_grid **out);
+
 int b200geo_grid_create(const b200geo_grid_desc *desc, int, b200geo_grid **out)
+{
+    return create_grid(desc, 0, out);
+}
+
+int b200geo_grid_uniform_min_stride(const b200geo_grid_desc *desc, int64_t *min_stride)
+{
+    int64_t elems = 1;
+    for (int i = 0; i < 3; ++i) elems *= desc->dim[i] + 2 * desc->ghost[i];
+    *min_stride = (elems + 255) / 256 * 256;
+    return B200GEO_OK;
+}
+
+int b200geo_grid_create_uniform(const b200geo_grid_desc *desc, int, int64_t member_stride, b200geo_grid **out)
+{
+    int64_t least = 0;
+    b200geo_grid_uniform_min_stride(desc, &least);
+    if (member_stride <= 0 || member_stride % 256 != 0) return fail(B200GEO_ERR_INVALID, "member stride must be a positive multiple of 256 elements");
+    if (member_stride < least) return fail(B200GEO_ERR_INVALID, "member stride smaller than the padded grid");
+    return create_grid(desc, member_stride, out);
+}
+
+int b200geo_grid_member_stride(const b200geo_grid *g, int64_t *member_stride)
+{
+    *member_stride = g->stride;
+    return B200GEO_OK;
+}
+
+static int create_grid(const b200geo_grid_desc *desc, int64_t stride, b200geo_grid **out)
 {
     if (!desc || !out) return fail(B200GEO_ERR_INVALID, "null argument");
     if (desc->n_members < 1 || desc->n_members > B200GEO_MAX_MEMBERS) return fail(B200GEO_ERR_INVALID, "n_members out of range");
@@ -205,8 +238,23 @@ int b200geo_grid_create(const b200geo_grid_desc *desc, int, b200geo_grid **out)
         }
         g->elem[m] = e;
         g->cell_bytes += e;
-        g->buf[0][m].assign((size_t)(g->px * g->py * g->pz) * e, 0);
-        g->buf[1][m].assign((size_t)(g->px * g->py * g->pz) * e, 0);
+        if (stride == 0) {
+            for (int b = 0; b < 2; ++b) {
+                g->buf[b][m].assign((size_t)(g->px * g->py * g->pz) * e, 0);
+                g->ptr[b][m] = g->buf[b][m].data();
+            }
+        }
+    }
+    g->stride = stride;
+    if (stride > 0) {
+        for (int b = 0; b < 2; ++b) {
+            g->flat[b].assign((size_t)stride * g->cell_bytes, 0);
+            size_t before = 0;
+            for (int m = 0; m < g->n; ++m) {
+                g->ptr[b][m] = g->flat[b].data() + (size_t)stride * before;
+                before += g->elem[m];
+            }
+        }
     }
     *out = g;
     return B200GEO_OK;
@@ -226,7 +274,7 @@ int b200geo_grid_layout(const b200geo_grid *g, int, int64_t *pitch, int64_t *pla
 
 int b200geo_grid_member_ptr(const b200geo_grid *g, int m, int which, void **ptr)
 {
-    *ptr = const_cast<char *>(g->buf[g->cur ^ which][m].data());
+    *ptr = g->ptr[g->cur ^ which][m];
     return B200GEO_OK;
 }
 
@@ -246,7 +294,7 @@ int b200geo_grid_set_edge(b200geo_grid *g, const void *cell, void *)
                         if (c[i] >= g->d[i] && g->desc.ghost_mode[i][1] == B200GEO_GHOST_EDGE) is_edge = true;
                     }
                     if (!is_edge) continue;
-                    for (int b = 0; b < 2; ++b) memcpy(&g->buf[b][m][g->index(x, y, z) * e], g->edge + off, e);
+                    for (int b = 0; b < 2; ++b) memcpy(&g->ptr[b][m][g->index(x, y, z) * e], g->edge + off, e);
                 }
         off += e;
     }
@@ -298,7 +346,27 @@ int b200geo_step(b200geo_grid *g, int kernel, const void *, uint32_t, uint32_t n
 int b200geo_update_box(b200geo_grid *, int, const void *, uint32_t, const int32_t *, const int32_t *, void *) { return fail(B200GEO_ERR_LOGIC, "not in the mock"); }
 int b200geo_update_box_n(b200geo_grid *, int, const void *, uint32_t, const int32_t *, const int32_t *, uint32_t, void *) { return fail(B200GEO_ERR_LOGIC, "not in the mock"); }
 int b200geo_swap(b200geo_grid *g) { g->cur ^= 1; return B200GEO_OK; }
-int b200geo_refresh_ghosts(b200geo_grid *, void *) { return B200GEO_OK; }
+// periodic images of WRAP axes in the current buffer, axis by axis (x first, so that corners end up right)
+int b200geo_refresh_ghosts(b200geo_grid *g, void *)
+{
+    for (int axis = 0; axis < 3; ++axis) {
+        if (g->desc.ghost_mode[axis][0] != B200GEO_GHOST_WRAP || g->g[axis] == 0) continue;
+        for (int m = 0; m < g->n; ++m) {
+            const int e = g->elem[m];
+            char *base = g->ptr[g->cur][m];
+            for (int z = -g->g[2]; z < g->d[2] + g->g[2]; ++z)
+                for (int y = -g->g[1]; y < g->d[1] + g->g[1]; ++y)
+                    for (int x = -g->g[0]; x < g->d[0] + g->g[0]; ++x) {
+                        int c[3] = {x, y, z};
+                        if (c[axis] >= 0 && c[axis] < g->d[axis]) continue;
+                        int s[3] = {x, y, z};
+                        s[axis] = (c[axis] + g->d[axis]) % g->d[axis];
+                        memcpy(base + g->index(x, y, z) * e, base + g->index(s[0], s[1], s[2]) * e, e);
+                    }
+        }
+    }
+    return B200GEO_OK;
+}
 int b200geo_sync(void *) { return B200GEO_OK; }
 int b200geo_halo_block(const b200geo_grid *, int, int, int, int, void **, uint64_t *) { return fail(B200GEO_ERR_LOGIC, "not in the mock"); }
 int b200geo_halo_block_in(const b200geo_grid *, int, int, int, int, int, void **, uint64_t *) { return fail(B200GEO_ERR_LOGIC, "not in the mock"); }
