@@ -14,6 +14,10 @@ value  = lattice updates of ALL ranks / max-over-ranks device time, inputs resid
 e2e    = the same metric through the public API (StripedSimulator.run(): Initializer::grid from
          PINNED HOST memory -> K steps -> Writer pulling the final grid back to host memory), all
          host<->device copies inside the timed region; h2d/d2h bytes are per step (total / K).
+         On one GPU the large Jacobi workloads are timed a second time with stream_io (the same call; upload,
+         sweeps and download pipelined chunk by chunk along z, striping.py::_run_streamed); that number is
+         reported only if its result is bit-identical to the plain schedule's at full size (e2e.verified),
+         with the plain number kept beside it (e2e.plain_schedule); otherwise the plain number stands.
 """
 import argparse
 import json
@@ -226,7 +230,6 @@ def reference_arm(args):
 def bench_device(workload, args, rank, world, dist, torch, with_e2e=True, with_clocks=True):
     """Returns a dict with value / roofline / e2e for one workload."""
     from libgeodecomp_b200 import capi
-    from libgeodecomp_b200.simulator import SimpleInitializer, Writer
     from libgeodecomp_b200.striping import StripedSimulator
 
     model_name, dims, alg_bytes, dtype, _ = WORKLOADS[workload]
@@ -249,18 +252,7 @@ def bench_device(workload, args, rank, world, dist, torch, with_e2e=True, with_c
     pinned = members
     host_out = members
 
-    class Init(SimpleInitializer):
-        def grid(self, target):
-            (o, d) = target.boundingBox()
-            for n, a in pinned.items():
-                target.loadMember(n, a, origin=o)
-
-    class PullWriter(Writer):
-        """pulls the rank's final grid into pinned host memory at WRITER_ALL_DONE"""
-        def stepFinished(self, grid, step, event):
-            if event == 2:
-                for n, a in host_out.items():
-                    grid.saveMember(n, out=a)
+    Init, PullWriter = make_plugins(pinned, host_out, last, z0)
 
     def barrier():
         if world > 1:
@@ -351,8 +343,94 @@ def bench_device(workload, args, rank, world, dist, torch, with_e2e=True, with_c
                       "ms_per_run": e_ms, "wall_ms_rank0": 1e3 * wall,
                       "what": "StripedSimulator.run(): Initializer::grid from pinned host memory -> %d steps -> "
                               "Writer pulls the final grid to pinned host memory" % K}
+        # The same call with stream_io: upload, sweeps and download pipelined chunk by chunk along z (time-skewed
+        # schedule, striping.py::_run_streamed). Taken as the e2e number only if the result is bit-identical to the
+        # plain schedule on the same input AT THIS SIZE (checksums of the device grid and of the pulled host copy).
+        if world == 1 and model.fuses_sweeps and grid_bytes >= (1 << 30):
+            out["e2e"]["schedule"] = "plain: upload, sweep, download one after the other"
+            try:
+                streamed = streamed_e2e(sim, model, pinned, K, depth, torch, capi)
+            except Exception as e:   # noqa: BLE001 - whatever goes wrong, the plain number stands
+                torch.cuda.synchronize()
+                streamed = {"verified": False, "error": "%s: %s" % (type(e).__name__, e)}
+            if streamed.get("verified"):
+                plain = out["e2e"]
+                out["e2e"] = dict(plain, value=1e-9 * cells_all * K / (1e-3 * streamed["ms_per_run"]),
+                                  ms_per_run=streamed["ms_per_run"], wall_ms_rank0=streamed["wall_ms"],
+                                  schedule=streamed["schedule"], verified=streamed["how"],
+                                  plain_schedule={"value": plain["value"], "ms_per_run": plain["ms_per_run"]})
+                out["gpu_launches_e2e"] = streamed["launches"]
+            else:
+                out["e2e"]["streamed_schedule"] = streamed
     del sim
     return out
+
+
+def make_plugins(pinned, host_out, last, z0):
+    """The Initializer and the Writer of the e2e leg: host arrays (pinned) in, host arrays out, through the plugin API."""
+    from libgeodecomp_b200.simulator import ParallelWriter, SimpleInitializer
+
+    class Init(SimpleInitializer):
+        """initialises the cells inside target.boundingBox() — the rank's slab, or one window of it when run() streams"""
+        def grid(self, target):
+            (o, d) = target.boundingBox()
+            a0 = o[last] - z0
+            for n, a in pinned.items():
+                target.loadMember(n, a[a0:a0 + d[last]], origin=o)
+
+    class PullWriter(ParallelWriter):
+        """pulls the rank's final grid into pinned host memory at WRITER_ALL_DONE, region by region"""
+        def stepFinishedRegion(self, grid, validRegion, globalDimensions, step, event, rank_, lastCall):
+            if event == 2:
+                (o, d) = validRegion
+                a0 = o[last] - z0
+                for n, a in host_out.items():
+                    grid.saveMember(n, origin=o, dims=d, out=a[a0:a0 + d[last]])
+
+    return Init, PullWriter
+
+
+def streamed_e2e(sim, model, pinned, K, depth, torch, capi):
+    """Times sim.run() with stream_io and checks it against the plain schedule. On entry the host arrays and the
+    device grid hold the same state R1 (a plain run() has just finished). (1) K more sweeps on the device with the
+    plain schedule -> checksum of R2; (2) streamed run() from the host arrays (R1) -> device and host hold R2';
+    (3) R2' must equal R2 bit for bit, on the device and in the pulled host copy."""
+    name = model.members[0][0]
+    host = pinned[name]
+    dense = torch.empty(host.shape, dtype=torch.float64, device="cuda")
+
+    def device_checksum():
+        sim.grid.saveMember(name, out=dense, location=capi.CUDA_DEVICE)
+        torch.cuda.synchronize()
+        return int(dense.view(torch.int64).sum().item())
+
+    sim.advance(K)
+    want = device_checksum()
+    sim.stream_io, sim.stream_depth = True, depth
+    plan = sim._stream_plan()
+    if plan is None:
+        return {"verified": False, "error": "run() cannot be streamed for this configuration"}
+    torch.cuda.synchronize()
+    launches0 = capi.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    ev0.record()
+    sim.run()
+    ev1.record()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    ms = ev0.elapsed_time(ev1)
+    launches = capi.launch_count() - launches0
+    got_device = device_checksum()
+    got_host = int(host.reshape(-1).view(np.int64).sum(dtype=np.int64))
+    del dense
+    levels, chunk = plan
+    return {"verified": sim.streamed_runs >= 1 and got_device == want and got_host == want, "ms_per_run": ms,
+            "wall_ms": 1e3 * wall, "launches": launches,
+            "schedule": "streamed: z-chunks of %d planes, %d levels of <= %d fused sweeps, time-skewed; upload / sweeps / "
+                        "download on three streams" % (chunk, len(levels), max(levels)),
+            "how": "int64 checksum of the final grid equals the plain schedule's on the same input (device %s, host %s)"
+                   % (got_device == want, got_host == want)}
 
 
 def bench_nbody(args, rank, world, dist, torch, containers=108, with_e2e=True):

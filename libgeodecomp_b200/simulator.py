@@ -72,6 +72,22 @@ class Writer:
         raise NotImplementedError
 
 
+class ParallelWriter(Writer):
+    """io/parallelwriter.h:29-107: a writer that is handed the grid piece by piece —
+    stepFinished(grid, validRegion, globalDimensions, step, event, rank, lastCall) may be called several times per
+    step, each time with another part of the simulation space, `lastCall` on the final one. `grid` is then a
+    GridWindow whose boundingBox() is `validRegion` (origin, dims). Reads through a GridWindow are ASYNCHRONOUS
+    (stream ordered): the host buffers are complete when the simulator's run() returns."""
+
+    def stepFinishedRegion(self, grid, validRegion, globalDimensions, step, event, rank, lastCall):
+        raise NotImplementedError
+
+    def stepFinished(self, grid, step, event):
+        # handed the whole grid at once (B200Simulator, StripedSimulator without streaming)
+        self.stepFinishedRegion(grid, grid.boundingBox(), getattr(grid, "global_dims", grid.dimensions()), step,
+                                event, 0, True)
+
+
 class SteererFeedback:
     """io/steerer.h:45-62"""
 
@@ -254,6 +270,66 @@ class B200Grid:
     def to_raw(self):
         """whole interior as the member-major byte stream (one dense array per member)."""
         return [self.saveMember(n) for n, _ in self.model.members]
+
+
+class GridWindow:
+    """The planes [z0, z1) (rows in 2-D) of a B200Grid along its last axis, as the GridBase an Initializer or a
+    ParallelWriter is handed for a sub-box: Initializer::grid 'may be called for sub-boxes and must only touch cells
+    inside boundingBox()' (io/initializer.h:38-71), ParallelWriter::stepFinished gets a validRegion
+    (io/parallelwriter.h:92-99). Transfers are enqueued on `stream` and touch ONE buffer (the grid's current one at
+    the time of the call) — the building block of StripedSimulator's streamed run, where host<->device copies of
+    one part of the space overlap the sweeps over another."""
+
+    def __init__(self, grid, z0, z1, stream=None):
+        self.grid, self.model, self.stream = grid, grid.model, stream
+        last = grid.model.dim - 1
+        self.origin = tuple(o + (z0 if i == last else 0) for i, o in enumerate(grid.origin))
+        self.dims = tuple((z1 - z0) if i == last else d for i, d in enumerate(grid.dims))
+        self.global_dims = grid.global_dims
+
+    def boundingBox(self):
+        return (self.origin, self.dims)
+
+    def dimensions(self):
+        return self.dims
+
+    def setEdge(self, cell):
+        # the edge cell belongs to the whole grid; re-stating it per window is a no-op
+        if self.model.cell_to_bytes(cell) != self.grid._edge:
+            self.grid.engine.sync()
+            self.grid.setEdge(cell)
+            self.grid.engine.sync()
+
+    def getEdge(self):
+        return self.grid.getEdge()
+
+    def _inside(self, origin, dims):
+        if origin is None:
+            origin = self.origin
+        if dims is None:
+            dims = [self.dims[i] - (origin[i] - self.origin[i]) for i in range(self.model.dim)]
+        for i in range(self.model.dim):
+            if origin[i] < self.origin[i] or origin[i] + dims[i] > self.origin[i] + self.dims[i]:
+                raise ValueError("box outside the window's boundingBox()")
+        return origin, dims
+
+    def loadMember(self, name, array, origin=None, location=capi.HOST):
+        m = self.model.member_index(name)
+        t = self.model.members[m][1]
+        if location == capi.HOST:
+            array = np.ascontiguousarray(array, dtype=t)
+        origin, dims = self._inside(origin, tuple(array.shape)[::-1])
+        o, d = self.grid._box(origin, dims)
+        self.grid.dev.load_member(m, array, o, d, location=location, both=False, stream=self.stream)
+
+    def saveMember(self, name, origin=None, dims=None, out=None, location=capi.HOST):
+        m = self.model.member_index(name)
+        origin, dims = self._inside(origin, dims)
+        o, d = self.grid._box(origin, dims)
+        if out is None:
+            raise ValueError("GridWindow.saveMember is asynchronous: pass the (pinned) array to fill as out=")
+        self.grid.dev.save_member(m, out, o, d, location=location, stream=self.stream)
+        return out
 
 
 class B200Simulator:

@@ -16,8 +16,8 @@ Mirrors, for the regular-grid path:
 import numpy as np
 
 from . import capi
-from .simulator import (B200Grid, SteererFeedback, STEERER_ALL_DONE, STEERER_INITIALIZED, STEERER_NEXT_STEP,
-                        WRITER_ALL_DONE, WRITER_INITIALIZED, WRITER_STEP_FINISHED)
+from .simulator import (B200Grid, GridWindow, ParallelWriter, SteererFeedback, STEERER_ALL_DONE, STEERER_INITIALIZED,
+                        STEERER_NEXT_STEP, WRITER_ALL_DONE, WRITER_INITIALIZED, WRITER_STEP_FINISHED)
 
 
 def slab_bounds(extent, ranks):
@@ -156,6 +156,57 @@ class HaloExchanger:
         self.finish(self.post(0))
 
 
+class _CudaStreams:
+    """three CUDA streams (host->device, sweeps, device->host) and the events between them; torch is the plumbing"""
+
+    def __init__(self):
+        import torch
+        self.torch = torch
+        self.up, self.run, self.down = (torch.cuda.Stream() for _ in range(3))
+        start = torch.cuda.Event()
+        start.record()                      # everything here starts after what the caller enqueued so far
+        for st in (self.up, self.run, self.down):
+            st.wait_event(start)
+
+    @staticmethod
+    def handle(stream):
+        return stream.cuda_stream
+
+    def record(self, stream):
+        ev = self.torch.cuda.Event()
+        ev.record(stream)
+        return ev
+
+    @staticmethod
+    def wait(stream, event):
+        stream.wait_event(event)
+
+    def join(self):
+        """the caller's current stream continues after all three"""
+        cur = self.torch.cuda.current_stream()
+        for st in (self.up, self.run, self.down):
+            cur.wait_event(self.record(st))
+
+
+class _NoStreams:
+    """engines that execute synchronously (tests/cpu_engine.py)"""
+    up = run = down = None
+
+    @staticmethod
+    def handle(stream):
+        return None
+
+    def record(self, stream):
+        return None
+
+    @staticmethod
+    def wait(stream, event):
+        pass
+
+    def join(self):
+        pass
+
+
 class StripedSimulator:
     """DistributedSimulator over equal slabs along the last axis, one rank per GPU.
 
@@ -166,9 +217,14 @@ class StripedSimulator:
     """
 
     def __init__(self, initializer, model, rank=0, world=1, ghost_width=1, device=0, dist=None, engine=None,
-                 overlap=True):
+                 overlap=True, stream_io=False, stream_depth=None, stream_chunks=16):
+        """stream_io: let run() pipeline Initializer -> sweeps -> ParallelWriters chunk by chunk along the last axis
+        (see _run_streamed) where that is possible; stream_depth = sweeps per launch there (default: what the
+        kernel family fuses), stream_chunks = number of chunks the axis is cut into."""
         self.initializer, self.model, self.rank, self.world = initializer, model, rank, world
         self.overlap = overlap
+        self.stream_io, self.stream_depth, self.stream_chunks = stream_io, stream_depth, stream_chunks
+        self.streamed_runs = 0
         self.NANO_STEPS = model.nano_steps
         gdims = tuple(initializer.gridDimensions())
         last = model.dim - 1
@@ -273,7 +329,117 @@ class StripedSimulator:
         self.stepNum += 1
         self._afterStep()
 
+    # ---- streamed run: host -> device -> host as a pipeline along the last axis -------------------------------
+    def _stream_plan(self):
+        """(sweeps per level, ...) or None when run() cannot be streamed: one rank, a Cube topology (periodic images
+        would tie the first planes to the last), no Steerers, only ParallelWriters that fire at the very end."""
+        if not self.stream_io or self.world != 1 or self.model.wraps or self.steerers:
+            return None
+        if not hasattr(self.grid.dev, "update_box") or not hasattr(self.model, "member_index"):
+            return None
+        steps = self.initializer.maxSteps() - self.initializer.startStep()
+        sweeps = steps * self.NANO_STEPS
+        if sweeps < 1:
+            return None
+        for w in self.writers:
+            if not isinstance(w, ParallelWriter) or w.getPeriod() < steps:
+                return None
+        depth = self.stream_depth
+        if depth is None:
+            depth = {capi.KERNEL_JACOBI27: 2, capi.KERNEL_JACOBI6: 4, capi.KERNEL_JACOBI7: 4}.get(self.model.kernel, 1)
+        if not self.model.fuses_sweeps:
+            depth = 1
+        depth = max(1, min(int(depth), 4, sweeps))
+        # the shorter remainder level goes FIRST: a level may not be deeper than the one after it (see below)
+        levels = ([sweeps % depth] if sweeps % depth else []) + [depth] * (sweeps // depth)
+        n = self.grid.dims[self.model.dim - 1]
+        chunk = max(2 * depth, -(-n // max(1, int(self.stream_chunks))))
+        chunk = -(-chunk // depth) * depth     # boxes that are cut off at plane 0 stay whole multiples of the depth
+        if n < 2 * chunk:
+            return None
+        return levels, chunk
+
+    def _run_streamed(self, levels, chunk):
+        """Time-skewed sweep over chunks of `chunk` planes (rows in 2-D) of the last axis, so that the upload of one
+        chunk, the sweeps over the chunks before it and the download of finished planes run at the same time on three
+        streams — instead of upload everything, sweep, download everything. The reference's parallel simulators hand
+        Initializers and ParallelWriters sub-boxes in the same way (io/initializer.h:38-71, io/parallelwriter.h:92-99);
+        results are bit-identical to the plain run (same kernels, same order of arithmetic per cell).
+
+        Level l = levels[l] fused sweeps (one b200geo_update_box_n launch) taking planes from time t_l = sum(levels[:l])
+        to t_l + levels[l]; off[l] = sum(levels[:l + 1]). In round c, level l updates planes
+        [c * chunk - off[l], (c + 1) * chunk - off[l]): its input reaches up to (c + 1) * chunk - off[l - 1], which
+        level l - 1 of the same round has just produced (level 0: up to (c + 1) * chunk, the chunk just uploaded).
+        Plane z at time t lives in buffer (number of levels up to t) % 2. Level l + 1 overwrites the buffer level l
+        read from, up to plane (c + 1) * chunk - off[l + 1]; round c + 1 will read that buffer from plane
+        (c + 1) * chunk - off[l] - levels[l] on — no overlap as long as levels[l + 1] >= levels[l]. All sweeps are on
+        one stream in this order, uploads touch only planes no level has reached, downloads only planes that are
+        final."""
+        g, dev, model = self.grid, self.grid.dev, self.model
+        last = model.dim - 1
+        n = g.dims[last]
+        L = len(levels)
+        off = [sum(levels[:l + 1]) for l in range(L)]
+        first_nano = [(sum(levels[:l])) % self.NANO_STEPS for l in range(L)]
+        streams = _NoStreams() if getattr(g.engine, "synchronous", False) else _CudaStreams()
+        start, last_step = self.initializer.startStep(), self.initializer.maxSteps()
+        parity = [0]
+
+        def want(p):
+            # which buffer the C ABI calls "current" is a host-side flag; device work already enqueued keeps its pointers
+            if parity[0] != p:
+                dev.swap()
+                parity[0] = p
+
+        def box(a, b):
+            origin, dim = [0, 0, 0], list(g.dims) + [1] * (3 - len(g.dims))
+            origin[last], dim[last] = a, b - a
+            return origin, dim
+
+        def region(a, b):
+            o, d = list(g.origin), list(g.dims)
+            o[last], d[last] = g.origin[last] + a, b - a
+            return (tuple(o), tuple(d))
+
+        uploads = -(-n // chunk)
+        rounds = -(-(n + off[-1]) // chunk)
+        for c in range(rounds):
+            if c < uploads:
+                a, b = c * chunk, min((c + 1) * chunk, n)
+                want(0)
+                window = GridWindow(g, a, b, stream=streams.handle(streams.up))
+                self.initializer.grid(window)
+                for w in self.writers:
+                    w.stepFinishedRegion(window, region(a, b), g.global_dims, start, WRITER_INITIALIZED, self.rank,
+                                         b == n)
+                streams.wait(streams.run, streams.record(streams.up))
+            for l in range(L):
+                a, b = max(c * chunk - off[l], 0), min((c + 1) * chunk - off[l], n)
+                if b <= a:
+                    continue
+                want(l % 2)
+                origin, dim = box(a, b)
+                dev.update_box(model.kernel, origin, dim, nano_step=first_nano[l], params=model.step_params(l == L - 1),
+                               n_sweeps=levels[l], stream=streams.handle(streams.run))
+            a, b = max(c * chunk - off[-1], 0), min((c + 1) * chunk - off[-1], n)
+            if b > a and self.writers:
+                streams.wait(streams.down, streams.record(streams.run))
+                want(L % 2)
+                window = GridWindow(g, a, b, stream=streams.handle(streams.down))
+                for w in self.writers:
+                    w.stepFinishedRegion(window, region(a, b), g.global_dims, last_step, WRITER_ALL_DONE, self.rank,
+                                         b == n)
+        want(L % 2)   # the final state is the current buffer from here on
+        streams.join()
+        self.stepNum = last_step
+        self.streamed_runs += 1
+
     def run(self):
+        plan = self._stream_plan()
+        if plan is not None:
+            self._valid = 0
+            self._run_streamed(*plan)
+            return
         self.initializer.grid(self.grid)
         self._valid = 0
         self.stepNum = self.initializer.startStep()

@@ -11,6 +11,7 @@ from libgeodecomp_b200 import capi
 from oracle import oracle_py
 
 
+synchronous = True        # no streams: striping.StripedSimulator._run_streamed issues everything in order
 staging_device = "cpu"   # where striping.HaloExchanger allocates its packed halo buffers for this engine
 
 _JACOBI = {capi.KERNEL_JACOBI6: 6, capi.KERNEL_JACOBI7: 7, capi.KERNEL_JACOBI27: 27}

@@ -67,3 +67,38 @@ def test_uniform_element_layout_round_trip():
         for g in grids[1:]:
             assert np.array_equal(pull(g, m, w), want), "member %d differs in the uniform layout" % m
         assert np.array_equal(want[1:-1, 1:-1, 1:-1], data[m])
+
+
+@pytest.mark.gpu
+@unverified
+@pytest.mark.parametrize("kind,depth,steps,shape,chunks", [
+    (27, 2, 8, (160, 96, 128), 5), (27, 2, 7, (96, 40, 70), 4), (7, 4, 12, (128, 64, 96), 4), (7, 1, 5, (64, 33, 50), 8),
+    (6, 3, 10, (90, 32, 64), 6)])
+def test_streamed_run_on_the_device(kind, depth, steps, shape, chunks):
+    """StripedSimulator(stream_io=True).run() on the real engine: pinned host arrays in and out (in place), three
+    streams, time-skewed update_box_n launches — bit-identical to the oracle and to the plain run. CPU twin:
+    tests/test_streamed_run_cpu.py."""
+    import sys
+    import torch
+    sys.path.insert(0, os.path.dirname(HERE))
+    import bench
+    from libgeodecomp_b200 import capi, models, synth
+    from libgeodecomp_b200.striping import StripedSimulator
+    from oracle import oracle_py
+    nz, ny, nx = shape
+    data = synth.jacobi_grid(nx, ny, nz, seed=kind)
+    want = oracle_py.jacobi(kind, False, data, steps)
+    pinned = torch.empty(shape, dtype=torch.float64, pin_memory=True)
+    host = {"temp": pinned.numpy()}
+    for stream_io in (True, False, True):
+        host["temp"][...] = data
+        Init, PullWriter = bench.make_plugins(host, host, 2, 0)
+        sim = StripedSimulator(Init((nx, ny, nz), steps), models.ALL["Jacobi%dCube" % kind], stream_io=stream_io,
+                               stream_depth=depth, stream_chunks=chunks)
+        sim.writers = [PullWriter("", 1 << 30)]
+        sim.run()
+        capi.sync()
+        torch.cuda.synchronize()
+        assert sim.streamed_runs == (1 if stream_io else 0)
+        assert np.array_equal(host["temp"], want), "stream_io=%s" % stream_io
+        assert np.array_equal(sim.getGrid().saveMember("temp"), want)
