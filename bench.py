@@ -348,22 +348,43 @@ def bench_device(workload, args, rank, world, dist, torch, with_e2e=True, with_c
         # plain schedule on the same input AT THIS SIZE (checksums of the device grid and of the pulled host copy).
         if world == 1 and model.fuses_sweeps and grid_bytes >= (1 << 30):
             out["e2e"]["schedule"] = "plain: upload, sweep, download one after the other"
-            try:
-                streamed = streamed_e2e(sim, model, pinned, K, depth, torch, capi)
-            except Exception as e:   # noqa: BLE001 - whatever goes wrong, the plain number stands
-                torch.cuda.synchronize()
-                streamed = {"verified": False, "error": "%s: %s" % (type(e).__name__, e)}
-            if streamed.get("verified"):
-                plain = out["e2e"]
-                out["e2e"] = dict(plain, value=1e-9 * cells_all * K / (1e-3 * streamed["ms_per_run"]),
-                                  ms_per_run=streamed["ms_per_run"], wall_ms_rank0=streamed["wall_ms"],
-                                  schedule=streamed["schedule"], verified=streamed["how"],
-                                  plain_schedule={"value": plain["value"], "ms_per_run": plain["ms_per_run"]})
-                out["gpu_launches_e2e"] = streamed["launches"]
-            else:
-                out["e2e"]["streamed_schedule"] = streamed
+
+            def streamed(sim=sim):
+                capi.set_tuning("jacobi.tb", depth)
+                return streamed_e2e(sim, model, pinned, K, depth, torch, capi), 1e-9 * cells_all * K
+            # run by main() as the LAST thing on the device, under a watchdog: whatever happens in there, every other
+            # number of the line has been measured by then
+            out["_streamed"] = streamed
     del sim
     return out
+
+
+def try_streamed_e2e(line, streamed, t_start, limit_s=240.0):
+    """The streamed e2e attempt (see bench_device): replaces line["e2e"] only when it ran and was verified; an
+    exception, a wrong result or a hang leave the plain e2e number in place. A hang prints the line and exits."""
+    def bail():
+        line["e2e"]["streamed_schedule"] = {"verified": False, "error": "no result after %.0f s" % limit_s}
+        line["wall_s"] = time.perf_counter() - t_start
+        print(json.dumps(line), flush=True)
+        os._exit(0)
+
+    timer = threading.Timer(limit_s, bail)
+    timer.daemon = True
+    timer.start()
+    try:
+        res, updates = streamed()
+    except BaseException as e:   # noqa: BLE001 - whatever goes wrong, the plain number stands
+        res, updates = {"verified": False, "error": "%s: %s" % (type(e).__name__, e)}, 0.0
+    timer.cancel()
+    if res.get("verified"):
+        plain = line["e2e"]
+        line["e2e"] = dict(plain, value=updates / (1e-3 * res["ms_per_run"]), ms_per_run=res["ms_per_run"],
+                           wall_ms_rank0=res["wall_ms"], schedule=res["schedule"], verified=res["how"],
+                           gpu_launches=res["launches"],
+                           plain_schedule={"value": plain["value"], "ms_per_run": plain["ms_per_run"]})
+    else:
+        line["e2e"]["streamed_schedule"] = res
+    line["wall_s"] = time.perf_counter() - t_start
 
 
 def make_plugins(pinned, host_out, last, z0):
@@ -608,7 +629,12 @@ def main():
         if others:
             line["others"] = others
         line["wall_s"] = time.perf_counter() - t_start
-        print(json.dumps(line))
+        streamed = main_res.get("_streamed")
+        if streamed is not None:
+            try_streamed_e2e(line, streamed, t_start)
+        print(json.dumps(line), flush=True)
+        if (line.get("e2e") or {}).get("streamed_schedule", {}).get("error"):
+            os._exit(0)   # the CUDA context may be unusable after a failed attempt: skip the teardown
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -189,3 +189,25 @@ def test_bench_plugins_work_on_whole_grids_and_on_windows():
             assert origin == (0, 0, 14) and np.array_equal(array, data[14:22])
 
     Init((nx, ny, nz), steps).grid(Target())
+
+
+def test_bench_takes_the_streamed_number_only_when_verified():
+    sys.path.insert(0, os.path.dirname(HERE))
+    import time
+    import bench
+    plain = {"value": 200.0, "unit": "GLUPS", "ms_per_run": 500.0, "h2d_bytes_per_step": 1, "d2h_bytes_per_step": 1}
+    good = {"verified": True, "ms_per_run": 250.0, "wall_ms": 251.0, "launches": 900, "schedule": "streamed", "how": "checksums"}
+    line = {"e2e": dict(plain)}
+    bench.try_streamed_e2e(line, lambda: (good, 1e-9 * 1e11), time.perf_counter())
+    assert line["e2e"]["value"] == pytest.approx(1e2 / 0.25) and line["e2e"]["plain_schedule"]["value"] == 200.0
+    assert line["e2e"]["h2d_bytes_per_step"] == 1 and line["e2e"]["verified"] == "checksums"
+    line = {"e2e": dict(plain)}
+    bench.try_streamed_e2e(line, lambda: (dict(good, verified=False), 100.0), time.perf_counter())
+    assert line["e2e"]["value"] == 200.0 and line["e2e"]["streamed_schedule"]["verified"] is False
+
+    def boom():
+        raise RuntimeError("CUDA error: an illegal memory access was encountered")
+
+    line = {"e2e": dict(plain)}
+    bench.try_streamed_e2e(line, boom, time.perf_counter())
+    assert line["e2e"]["value"] == 200.0 and "illegal memory access" in line["e2e"]["streamed_schedule"]["error"]
