@@ -159,12 +159,13 @@ class HaloExchanger:
 class _CudaStreams:
     """three CUDA streams (host->device, sweeps, device->host) and the events between them; torch is the plumbing"""
 
-    def __init__(self):
+    def __init__(self, device):
         import torch
         self.torch = torch
-        self.up, self.run, self.down = (torch.cuda.Stream() for _ in range(3))
+        self.device = torch.device("cuda", device)
+        self.up, self.run, self.down = (torch.cuda.Stream(device=self.device) for _ in range(3))
         start = torch.cuda.Event()
-        start.record()                      # everything here starts after what the caller enqueued so far
+        start.record(torch.cuda.current_stream(self.device))   # everything here starts after what the caller enqueued so far
         for st in (self.up, self.run, self.down):
             st.wait_event(start)
 
@@ -183,7 +184,7 @@ class _CudaStreams:
 
     def join(self):
         """the caller's current stream continues after all three"""
-        cur = self.torch.cuda.current_stream()
+        cur = self.torch.cuda.current_stream(self.device)
         for st in (self.up, self.run, self.down):
             cur.wait_event(self.record(st))
 
@@ -224,6 +225,7 @@ class StripedSimulator:
         self.initializer, self.model, self.rank, self.world = initializer, model, rank, world
         self.overlap = overlap
         self.stream_io, self.stream_depth, self.stream_chunks = stream_io, stream_depth, stream_chunks
+        self.device = device
         self.streamed_runs = 0
         self.NANO_STEPS = model.nano_steps
         gdims = tuple(initializer.gridDimensions())
@@ -381,7 +383,7 @@ class StripedSimulator:
         L = len(levels)
         off = [sum(levels[:l + 1]) for l in range(L)]
         first_nano = [(sum(levels[:l])) % self.NANO_STEPS for l in range(L)]
-        streams = _NoStreams() if getattr(g.engine, "synchronous", False) else _CudaStreams()
+        streams = _NoStreams() if getattr(g.engine, "synchronous", False) else _CudaStreams(self.device)
         start, last_step = self.initializer.startStep(), self.initializer.maxSteps()
         parity = [0]
 
