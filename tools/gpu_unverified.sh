@@ -12,3 +12,4 @@ import json
 d = json.load(open("gpurun_out/bench_streamed.json"))
 print("value %.1f GLUPS; e2e %s" % (d["value"], json.dumps(d["e2e"])[:900]))
 PY
+timeout 600 python tools/stream_bench.py --chunks 8,16,32 | tee gpurun_out/stream_bench.jsonl
