@@ -103,6 +103,11 @@ int b200geo_grid_create(const b200geo_grid_desc *desc, int device, b200geo_grid 
  * b200geo_grid_uniform_min_stride(desc). b200geo_grid_member_ptr(g, 0, which) is the accessors' data pointer. */
 int b200geo_grid_create_uniform(const b200geo_grid_desc *desc, int device, int64_t member_stride, b200geo_grid **out);
 int b200geo_grid_uniform_min_stride(const b200geo_grid_desc *desc, int64_t *min_stride);
+/* How b200geo_grid_create (member_stride = 0) / b200geo_grid_create_uniform would lay the member arrays out, without
+ * allocating anything — needs no device. layout: int64 [n_members][7] = element bytes, lead-in (elements before
+ * interior x = 0 in a row), row pitch, plane pitch, element offset of interior cell (0,0,0), bytes of the member array,
+ * byte offset of the member array inside a buffer. Fails like the create calls for a bad description. */
+int b200geo_grid_plan(const b200geo_grid_desc *desc, int64_t member_stride, int64_t *layout, int64_t *buffer_bytes);
 /* elements per member array of a uniform-layout grid; 0 for a grid in the default layout */
 int b200geo_grid_member_stride(const b200geo_grid *g, int64_t *member_stride);
 int b200geo_grid_destroy(b200geo_grid *g);

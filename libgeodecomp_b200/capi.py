@@ -61,6 +61,7 @@ SYMBOLS = [
     ("b200geo_grid_create", ctypes.c_int, [ctypes.POINTER(GridDesc), ctypes.c_int, ctypes.POINTER(_vp)]),
     ("b200geo_grid_create_uniform", ctypes.c_int, [ctypes.POINTER(GridDesc), ctypes.c_int, ctypes.c_int64, ctypes.POINTER(_vp)]),
     ("b200geo_grid_uniform_min_stride", ctypes.c_int, [ctypes.POINTER(GridDesc), _i64p]),
+    ("b200geo_grid_plan", ctypes.c_int, [ctypes.POINTER(GridDesc), ctypes.c_int64, _i64p, _i64p]),
     ("b200geo_grid_member_stride", ctypes.c_int, [_vp, _i64p]),
     ("b200geo_grid_destroy", ctypes.c_int, [_vp]),
     ("b200geo_grid_buffer_bytes", ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_uint64)]),

@@ -142,9 +142,11 @@ int b200geo_grid_uniform_min_stride(const b200geo_grid_desc *desc, int64_t *min_
     return B200GEO_OK;
 }
 
-static int create_grid(const b200geo_grid_desc *desc, int device, int64_t uniform_stride, b200geo_grid **out)
+// Checks a grid description and lays out its member arrays (default layout: uniform_stride = 0). No device needed.
+static int plan_layout(const b200geo_grid_desc *desc, int64_t uniform_stride, MemberLayout *layout, int64_t *buffer_bytes,
+                       int *cell_bytes)
 {
-    if (!desc || !out) return fail(B200GEO_ERR_INVALID, "null argument");
+    if (!desc) return fail(B200GEO_ERR_INVALID, "null argument");
     if (desc->n_members < 1 || desc->n_members > B200GEO_MAX_MEMBERS)
         return fail(B200GEO_ERR_INVALID, "n_members out of range");
     for (int i = 0; i < 3; ++i) {
@@ -175,6 +177,59 @@ static int create_grid(const b200geo_grid_desc *desc, int device, int64_t unifor
         uniform_geometry(desc, &ulead, &upitch, &umin);
         if (uniform_stride < umin) return fail(B200GEO_ERR_INVALID, "member stride smaller than the padded grid");
     }
+    const int *d = desc->dim, *gh = desc->ghost;
+    int64_t off = 0;
+    int cell = 0;
+    for (int m = 0; m < desc->n_members; ++m) {
+        int e = desc->member_bytes[m];
+        MemberLayout& L = layout[m];
+        L.elem = e;
+        L.lead = uniform_stride > 0 ? ulead : 128 / e;
+        if (gh[0] > L.lead) return fail(B200GEO_ERR_INVALID, "x ghost wider than the 128-byte lead-in");
+        L.pitch = uniform_stride > 0 ? upitch : round_up((int64_t)(L.lead + d[0] + gh[0]) * e, 128) / e;
+        L.plane = L.pitch * (d[1] + 2 * gh[1]);
+        L.origin = (int64_t)gh[2] * L.plane + (int64_t)gh[1] * L.pitch + L.lead;
+        // 128 B of slack: vector accesses of partially valid groups may touch the bytes just past
+        // the last row (never stored to, values never used)
+        L.bytes = round_up(L.plane * (d[2] + 2 * gh[2]) * e + 128, 256);
+        // uniform layout: every member array has member_stride elements, so member m starts member_stride x
+        // (bytes of the members before it) into the buffer — LibFlatArray's DIM_PROD x offset<CELL, m>
+        if (uniform_stride > 0) L.bytes = uniform_stride * e;
+        L.offset = off;
+        L.edge_offset = cell;
+        off += L.bytes;
+        cell += e;
+    }
+    *buffer_bytes = off;
+    *cell_bytes = cell;
+    return B200GEO_OK;
+}
+
+int b200geo_grid_plan(const b200geo_grid_desc *desc, int64_t member_stride, int64_t *layout, int64_t *buffer_bytes)
+{
+    if (!layout || !buffer_bytes) return fail(B200GEO_ERR_INVALID, "null argument");
+    if (member_stride < 0 || member_stride % 256 != 0)
+        return fail(B200GEO_ERR_INVALID, "member stride must be a multiple of 256 elements (0 = default layout)");
+    MemberLayout m[B200GEO_MAX_MEMBERS];
+    int cell = 0;
+    int rc = plan_layout(desc, member_stride, m, buffer_bytes, &cell);
+    if (rc) return rc;
+    for (int i = 0; i < desc->n_members; ++i) {
+        int64_t *row = layout + 7 * i;
+        row[0] = m[i].elem; row[1] = m[i].lead; row[2] = m[i].pitch; row[3] = m[i].plane;
+        row[4] = m[i].origin; row[5] = m[i].bytes; row[6] = m[i].offset;
+    }
+    return B200GEO_OK;
+}
+
+static int create_grid(const b200geo_grid_desc *desc, int device, int64_t uniform_stride, b200geo_grid **out)
+{
+    if (!out) return fail(B200GEO_ERR_INVALID, "null argument");
+    MemberLayout layout[B200GEO_MAX_MEMBERS];
+    int64_t off = 0;
+    int cell = 0;
+    int rc = plan_layout(desc, uniform_stride, layout, &off, &cell);
+    if (rc) return rc;
     B200GEO_CUDA(cudaSetDevice(device));
 
     b200geo_grid *g = new (std::nothrow) b200geo_grid();
@@ -189,35 +244,7 @@ static int create_grid(const b200geo_grid_desc *desc, int device, int64_t unifor
     }
     g->slab_axis = (g->d[2] == 1 && g->g[2] == 0) ? 1 : 2;
     g->uniform_stride = uniform_stride;
-    int64_t off = 0;
-    int cell = 0;
-    for (int m = 0; m < g->n; ++m) {
-        int e = desc->member_bytes[m];
-        if (e != 1 && e != 2 && e != 4 && e != 8) {
-            delete g;
-            return fail(B200GEO_ERR_INVALID, "member size must be 1, 2, 4 or 8 bytes");
-        }
-        MemberLayout& L = g->m[m];
-        L.elem = e;
-        L.lead = uniform_stride > 0 ? ulead : 128 / e;
-        if (g->g[0] > L.lead) {
-            delete g;
-            return fail(B200GEO_ERR_INVALID, "x ghost wider than the 128-byte lead-in");
-        }
-        L.pitch = uniform_stride > 0 ? upitch : round_up((int64_t)(L.lead + g->d[0] + g->g[0]) * e, 128) / e;
-        L.plane = L.pitch * (g->d[1] + 2 * g->g[1]);
-        L.origin = (int64_t)g->g[2] * L.plane + (int64_t)g->g[1] * L.pitch + L.lead;
-        // 128 B of slack: vector accesses of partially valid groups may touch the bytes just past
-        // the last row (never stored to, values never used)
-        L.bytes = round_up(L.plane * (g->d[2] + 2 * g->g[2]) * e + 128, 256);
-        // uniform layout: every member array has member_stride elements, so member m starts member_stride x
-        // (bytes of the members before it) into the buffer — LibFlatArray's DIM_PROD x offset<CELL, m>
-        if (uniform_stride > 0) L.bytes = uniform_stride * e;
-        L.offset = off;
-        L.edge_offset = cell;
-        off += L.bytes;
-        cell += e;
-    }
+    for (int m = 0; m < g->n; ++m) g->m[m] = layout[m];
     g->buffer_bytes = off;
     g->cell_bytes = cell;
     for (int b = 0; b < 2; ++b) {
