@@ -21,9 +21,12 @@
 
 #include "b200simulator.h"
 
+#include <libgeodecomp/io/parallelwriter.h>
+#include <libgeodecomp/misc/sharedptr.h>
 #include <libgeodecomp/storage/selector.h>
 
 #include <memory>
+#include <type_traits>
 
 namespace LibGeoDecomp {
 
@@ -526,6 +529,22 @@ public:
         initializer->grid(&grid);
     }
 
+    using MonolithicSimulator<CELL>::addWriter;
+
+    /* Programs written for the reference's StripingSimulator / HiParSimulator (DistributedSimulator,
+     * parallelization/distributedsimulator.h:43-46) register ParallelWriters. This simulator holds the whole
+     * simulation space in one process, so each of them is called once per event with the whole area as validRegion,
+     * rank 0 and lastCall = true — what StripingSimulator::handleOutput does on a single rank
+     * (parallelization/stripingsimulator.h:337-352). The simulator takes ownership, like the reference. Writers that
+     * are BOTH a Writer and a ParallelWriter (TracingWriter, MockWriter) keep going through addWriter(Writer *). */
+    template<typename WRITER>
+    typename std::enable_if<std::is_base_of<ParallelWriter<CELL>, WRITER>::value &&
+                            !std::is_base_of<Writer<CELL>, WRITER>::value>::type
+    addWriter(WRITER *writer)
+    {
+        parallelWriters.push_back(typename SharedPtr<ParallelWriter<CELL> >::Type(writer));
+    }
+
     virtual void step()
     {
         SteererFeedback feedback;
@@ -538,6 +557,9 @@ public:
         stepNum = initializer->startStep();
         for (unsigned i = 0; i < steerers.size(); i++) {
             steerers[i]->setRegion(simArea);
+        }
+        for (std::size_t i = 0; i < parallelWriters.size(); ++i) {
+            parallelWriters[i]->setRegion(simArea);
         }
 
         SteererFeedback feedback;
@@ -572,6 +594,7 @@ public:
 protected:
     GridType grid;
     Region<DIM> simArea;
+    std::vector<typename SharedPtr<ParallelWriter<CELL> >::Type> parallelWriters;
 
     void step(SteererFeedback *feedback, bool fuse)
     {
@@ -582,7 +605,7 @@ protected:
         {
             TimeCompute t(&chronometer);
             grid.update(0, steps * NANO_STEPS);
-            if (steps > 1 || !writers.empty()) {
+            if (steps > 1 || !writers.empty() || !parallelWriters.empty()) {
                 grid.sync();
             }
         }
@@ -607,6 +630,10 @@ protected:
             unsigned p = steerers[i]->getPeriod();
             n = (std::min)(n, p - stepNum % p);
         }
+        for (std::size_t i = 0; i < parallelWriters.size(); ++i) {
+            unsigned p = parallelWriters[i]->getPeriod();
+            n = (std::min)(n, p - stepNum % p);
+        }
         return n > 0 ? n : 1;
     }
 
@@ -617,6 +644,12 @@ protected:
             if ((event != WRITER_STEP_FINISHED) || ((getStep() % writers[i]->getPeriod()) == 0)) {
                 grid.sync();
                 writers[i]->stepFinished(grid, getStep(), event);
+            }
+        }
+        for (std::size_t i = 0; i < parallelWriters.size(); ++i) {
+            if ((event != WRITER_STEP_FINISHED) || ((getStep() % parallelWriters[i]->getPeriod()) == 0)) {
+                grid.sync();
+                parallelWriters[i]->stepFinished(grid, simArea, gridDim, getStep(), event, 0, true);
             }
         }
     }

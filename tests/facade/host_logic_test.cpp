@@ -5,8 +5,12 @@
  *  - B200Grid::resize drops pending writes and cached rows and keeps working;
  *  - overlapping combined writes keep their order across flushes of different sizes;
  *  - wrong-size region buffers and member type mismatches map to std::invalid_argument;
- *  - a filtered (non-member) Selector takes the host path of saveMember. */
+ *  - a filtered (non-member) Selector takes the host path of saveMember;
+ *  - ParallelWriters on B200StripingSimulator. */
 #include "fixtures.h"
+
+#include <libgeodecomp/io/tracingwriter.h>
+#include <libgeodecomp/misc/clonable.h>
 
 #include <libgeodecomp_b200/b200stripingsimulator.h>
 
@@ -200,10 +204,97 @@ static void testAoSAndSoALBMModelsAgree()
     std::printf("LBM: AoS update() model vs SoA updateLineX model through SerialSimulator: %ld differing cells after %u steps\n", bad, steps);
 }
 
+/* A writer that is ONLY a ParallelWriter (what programs written for the reference's StripingSimulator / HiParSimulator
+ * register, parallelization/distributedsimulator.h:43-46): B200StripingSimulator calls it once per event with the whole
+ * simulation area, rank 0, lastCall = true, at the steps a serial Writer of the same period sees on SerialSimulator, and
+ * the grid it is handed holds the reference's state of that step. */
+struct WriterCall {
+    unsigned step;
+    int event;
+    double sum;
+    bool operator==(const WriterCall& o) const { return step == o.step && event == o.event && sum == o.sum; }
+};
+
+template<typename GRID>
+static double gridSum(const GRID& grid)
+{
+    double sum = 0;
+    CoordBox<3> box = grid.boundingBox();
+    for (CoordBox<3>::Iterator i = box.begin(); i != box.end(); ++i) {
+        sum += grid.get(*i).temp;
+    }
+    return sum;
+}
+
+class SerialProbe : public Clonable<Writer<Jacobi7Cube>, SerialProbe>
+{
+public:
+    SerialProbe(unsigned period, std::vector<WriterCall> *log) : Clonable<Writer<Jacobi7Cube>, SerialProbe>("", period), log(log) {}
+
+    virtual void stepFinished(const GridType& grid, unsigned step, WriterEvent event)
+    {
+        WriterCall c = {step, (int)event, gridSum(grid)};
+        log->push_back(c);
+    }
+
+private:
+    std::vector<WriterCall> *log;
+};
+
+class ParallelProbe : public Clonable<ParallelWriter<Jacobi7Cube>, ParallelProbe>
+{
+public:
+    ParallelProbe(unsigned period, std::vector<WriterCall> *log, int *bad, int *regionSet) :
+        Clonable<ParallelWriter<Jacobi7Cube>, ParallelProbe>("", period), log(log), bad(bad), regionSet(regionSet) {}
+
+    virtual void setRegion(const Region<3>& newRegion)
+    {
+        ParallelWriter<Jacobi7Cube>::setRegion(newRegion);
+        ++*regionSet;
+    }
+
+    virtual void stepFinished(const GridType& grid, const RegionType& validRegion, const CoordType& globalDimensions,
+                              unsigned step, WriterEvent event, std::size_t rank, bool lastCall)
+    {
+        *bad += !(validRegion == region) || validRegion.size() != (std::size_t)globalDimensions.prod() || rank != 0 || !lastCall ||
+            !(grid.boundingBox().dimensions == globalDimensions);
+        WriterCall c = {step, (int)event, gridSum(grid)};
+        log->push_back(c);
+    }
+
+private:
+    std::vector<WriterCall> *log;
+    int *bad;
+    int *regionSet;
+};
+
+static void testParallelWritersOnTheStripingSimulator()
+{
+    typedef Jacobi7Cube CELL;
+    Coord<3> dim(9, 6, 12);
+    for (int fuse = 0; fuse < 2; ++fuse) {
+        std::vector<WriterCall> a, b;
+        int bad = 0, regionSet = 0;
+        SerialSimulator<CELL> ref(new SeededInitializer<CELL>(dim, 10));
+        ref.addWriter(new SerialProbe(4, &a));
+        ref.run();
+        B200StripingSimulator<CELL> sim(new SeededInitializer<CELL>(dim, 10), std::vector<int>(3, 0), 2);
+        sim.fuseSteps = fuse != 0;
+        sim.addWriter(new ParallelProbe(4, &b, &bad, &regionSet));
+        sim.addWriter(new TracingWriter<CELL>(100, 10, 0, std::cout));   // both a Writer and a ParallelWriter: the serial overload, no ambiguity
+        sim.run();
+        CHECK(a.size() == 4 && a == b);   // INITIALIZED @0, STEP_FINISHED @4 and @8, ALL_DONE @10
+        CHECK(bad == 0 && regionSet == 1);
+        std::printf("ParallelWriter on B200StripingSimulator (fuseSteps %d): %zu calls, %s the serial Writer's on SerialSimulator\n",
+                    fuse, b.size(), a == b ? "same steps, events and grids as" : "DIFFERENT from");
+    }
+}
+
 int main()
 {
     try {
         NBodyParams::dt() = 0.01;
+        testParallelWritersOnTheStripingSimulator();
         testAoSAndSoALBMModelsAgree();
         testCapacityExceeded();
         testResizeAndWriteOrder();
