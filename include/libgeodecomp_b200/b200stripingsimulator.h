@@ -22,6 +22,7 @@
 #include "b200simulator.h"
 
 #include <libgeodecomp/io/parallelwriter.h>
+#include <libgeodecomp/loadbalancer/loadbalancer.h>
 #include <libgeodecomp/misc/sharedptr.h>
 #include <libgeodecomp/storage/selector.h>
 
@@ -529,6 +530,26 @@ public:
         initializer->grid(&grid);
     }
 
+    /* The reference's parallel simulators are constructed with a LoadBalancer:
+     * StripingSimulator(initializer, balancer, loadBalancingPeriod), parallelization/stripingsimulator.h:58-75, and
+     * HiParSimulator(initializer, balancer, loadBalancingPeriod, ghostZoneWidth), parallelization/hiparsimulator.h:60-66.
+     * These overloads keep such call sites compiling. The slabs here are equal and the GPUs of a box identical, so the
+     * balancer has nothing to decide: it is owned (deleted with the simulator, as the reference does) and never asked. */
+    B200StripingSimulator(
+        Initializer<CELL> *init,
+        LoadBalancer *balancer,
+        unsigned /* loadBalancingPeriod */ = 1,
+        unsigned ghostZoneWidth = 0) :
+        MonolithicSimulator<CELL>(init),
+        grid(CoordBox<DIM>(Coord<DIM>(), init->gridBox().dimensions), allDevices(),
+             ghostZoneWidth > 0 ? (int)ghostZoneWidth : defaultGhostWidth()),
+        balancer(balancer)
+    {
+        stepNum = init->startStep();
+        simArea << CoordBox<DIM>(Coord<DIM>(), init->gridBox().dimensions);
+        initializer->grid(&grid);
+    }
+
     using MonolithicSimulator<CELL>::addWriter;
 
     /* Programs written for the reference's StripingSimulator / HiParSimulator (DistributedSimulator,
@@ -595,6 +616,7 @@ protected:
     GridType grid;
     Region<DIM> simArea;
     std::vector<typename SharedPtr<ParallelWriter<CELL> >::Type> parallelWriters;
+    typename SharedPtr<LoadBalancer>::Type balancer;
 
     void step(SteererFeedback *feedback, bool fuse)
     {

@@ -290,10 +290,52 @@ static void testParallelWritersOnTheStripingSimulator()
     }
 }
 
+/* call sites written for StripingSimulator(init, balancer, period) / HiParSimulator(init, balancer, period, ghostZoneWidth) */
+class CountingBalancer : public LoadBalancer
+{
+public:
+    explicit CountingBalancer(int *alive) : alive(alive) { ++*alive; }
+    virtual ~CountingBalancer() { --*alive; }
+    virtual WeightVec balance(const WeightVec& weights, const LoadVec&) { ++asked; return weights; }
+    static int asked;
+
+private:
+    int *alive;
+};
+int CountingBalancer::asked = 0;
+
+static void testReferenceConstructorSignatures()
+{
+    typedef Jacobi7Cube CELL;
+    Coord<3> dim(9, 6, 12);
+    int alive = 0;
+    SerialSimulator<CELL> ref(new SeededInitializer<CELL>(dim, 5));
+    ref.run();
+    {
+        B200StripingSimulator<CELL> striping(new SeededInitializer<CELL>(dim, 5), new CountingBalancer(&alive), 2);
+        B200StripingSimulator<CELL> hipar(new SeededInitializer<CELL>(dim, 5), new CountingBalancer(&alive), 1, 2);
+        B200StripingSimulator<CELL> none(new SeededInitializer<CELL>(dim, 5), 0);
+        CHECK(alive == 2);
+        striping.run();
+        hipar.run();
+        none.run();
+        long bad = 0;
+        CoordBox<3> box(Coord<3>(), dim);
+        for (CoordBox<3>::Iterator i = box.begin(); i != box.end(); ++i) {
+            double want = ref.getGrid()->get(*i).temp;
+            bad += striping.getGrid()->get(*i).temp != want || hipar.getGrid()->get(*i).temp != want || none.getGrid()->get(*i).temp != want;
+        }
+        CHECK(bad == 0);
+    }
+    CHECK(alive == 0 && CountingBalancer::asked == 0);
+    std::printf("reference constructor signatures (initializer, balancer, period[, ghostZoneWidth]): balancers owned and released, results identical\n");
+}
+
 int main()
 {
     try {
         NBodyParams::dt() = 0.01;
+        testReferenceConstructorSignatures();
         testParallelWritersOnTheStripingSimulator();
         testAoSAndSoALBMModelsAgree();
         testCapacityExceeded();
