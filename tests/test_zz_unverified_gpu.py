@@ -102,3 +102,66 @@ def test_streamed_run_on_the_device(kind, depth, steps, shape, chunks):
         assert sim.streamed_runs == (1 if stream_io else 0)
         assert np.array_equal(host["temp"], want), "stream_io=%s" % stream_io
         assert np.array_equal(sim.getGrid().saveMember("temp"), want)
+
+
+@pytest.mark.gpu
+@unverified
+def test_streamed_lbm_and_gol_on_the_device():
+    """kernel families that take one sweep per launch (b200geo_update_box): LBM D3Q19 (24 members, macroscopics stored
+    on the last level only) and the byte Game of Life kernel (2-D: chunks of rows), streamed vs the oracle."""
+    import torch
+    from libgeodecomp_b200 import capi, models, synth
+    from libgeodecomp_b200.simulator import ParallelWriter, SimpleInitializer
+    from libgeodecomp_b200.striping import StripedSimulator
+    from oracle import oracle_py
+    nx, ny, nz, steps = 40, 24, 64, 6
+    raw = synth.lbm_grid(nx, ny, nz, noise=0.01)
+    pinned = torch.empty(raw.shape, dtype=torch.float32, pin_memory=True)
+    host = pinned.numpy()
+    host[...] = raw
+
+    class LBMInit(SimpleInitializer):
+        def grid(self, target):
+            (ox, oy, oz), (dx, dy, dz) = target.boundingBox()
+            for m, (name, t) in enumerate(models.LBMCellF.members):
+                target.loadMember(name, host[m, oz:oz + dz].view(t), origin=(ox, oy, oz))
+
+    class LBMPull(ParallelWriter):
+        def stepFinishedRegion(self, grid, validRegion, globalDimensions, step, event, rank, lastCall):
+            (ox, oy, oz), (dx, dy, dz) = validRegion
+            if event == 2:
+                for m, (name, t) in enumerate(models.LBMCellF.members):
+                    grid.saveMember(name, origin=(ox, oy, oz), dims=(dx, dy, dz), out=host[m, oz:oz + dz].view(t))
+
+    sim = StripedSimulator(LBMInit((nx, ny, nz), steps), models.LBMCellF, stream_io=True, stream_chunks=4)
+    sim.addWriter(LBMPull("", steps))
+    sim.run()
+    capi.sync()
+    torch.cuda.synchronize()
+    assert sim.streamed_runs == 1
+    assert np.array_equal(host.view(np.uint32), oracle_py.lbm(raw, steps).view(np.uint32))
+
+    gx, gy, gsteps = 300, 256, 9
+    gol = synth.gol_grid(gx, gy)
+    gpinned = torch.empty(gol.shape, dtype=torch.uint8, pin_memory=True)
+    ghost = gpinned.numpy()
+    ghost[...] = gol
+
+    class GolInit(SimpleInitializer):
+        def grid(self, target):
+            (ox, oy), (dx, dy) = target.boundingBox()
+            target.loadMember("alive", ghost[oy:oy + dy], origin=(ox, oy))
+
+    class GolPull(ParallelWriter):
+        def stepFinishedRegion(self, grid, validRegion, globalDimensions, step, event, rank, lastCall):
+            (ox, oy), (dx, dy) = validRegion
+            if event == 2:
+                grid.saveMember("alive", origin=(ox, oy), dims=(dx, dy), out=ghost[oy:oy + dy])
+
+    sim = StripedSimulator(GolInit((gx, gy), gsteps), models.ALL["ConwayCube"], stream_io=True, stream_chunks=8)
+    sim.addWriter(GolPull("", gsteps))
+    sim.run()
+    capi.sync()
+    torch.cuda.synchronize()
+    assert sim.streamed_runs == 1
+    assert np.array_equal(ghost, oracle_py.gol(False, gol, gsteps))
