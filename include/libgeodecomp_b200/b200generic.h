@@ -323,17 +323,20 @@ struct WordSlicedBinding {
     }
 };
 
-/* which generic binding a cell gets: Struct-of-Arrays cells with an updateLineX() are handed the accessors
- * LibFlatArray generated for them (b200genericsoa.h) — the route UpdateFunctor takes for them on the CPU
- * (storage/updatefunctor.h:403-428 -> FixedNeighborhoodUpdateFunctor); every other cell is word-sliced */
+/* which generic binding a cell gets: Struct-of-Arrays cells whose only update is a SoA-signature updateLineX() are
+ * handed the accessors LibFlatArray generated for them (b200genericsoa.h) — the route UpdateFunctor takes for them on
+ * the CPU (storage/updatefunctor.h:403-428 -> FixedNeighborhoodUpdateFunctor). Every other cell is word-sliced; that
+ * includes SoA cells that ALSO have a per-cell update(), which wins as it does for AoS cells (the reference's
+ * TestCellSoA is such a cell, and only its update() is __host__ __device__, misc/testcell.h:213-281). */
 template<typename CELL, typename SOA = typename APITraits::SelectSoA<CELL>::Value,
-         typename LINE = typename APITraits::SelectUpdateLineX<CELL>::Value>
+         typename LINE = typename APITraits::SelectUpdateLineX<CELL>::Value,
+         bool HAS_UPDATE = HasUpdate<CELL, Hood<CELL, APITraits::SelectTopology<CELL>::Value::DIM> >::VALUE>
 struct SelectBinding {
     typedef WordSlicedBinding<CELL> Type;
 };
 
 template<typename CELL>
-struct SelectBinding<CELL, APITraits::TrueType, APITraits::TrueType> {
+struct SelectBinding<CELL, APITraits::TrueType, APITraits::TrueType, false> {
     typedef SoA::Binding<CELL, SoA::DeviceSweep> Type;
 };
 

@@ -28,7 +28,8 @@
  * the generated accessors themselves (probeMembers below) — the user adds nothing. Requirements: updateLineX must
  * be `__host__ __device__` (as the reference's CUDA path requires of update()), members must be 1, 2, 4 or 8 bytes
  * wide (arrays of those are fine), the cell trivially copyable. Cells with a B200GEO_BIND_CELL line keep their
- * hand-written kernels.
+ * hand-written kernels; SoA cells that also have a per-cell update() take the word-sliced path of b200generic.h
+ * (B200Generic::SelectBinding).
  *
  * This header also compiles with a host compiler: everything but the kernel launch is host code, which is how the
  * CPU test suite runs the address arithmetic against the reference (tests/facade/generic_soa_host_test.cpp supplies

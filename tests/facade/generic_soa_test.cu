@@ -24,6 +24,18 @@
 using namespace LibGeoDecomp;
 using namespace soacells;
 
+/* which generic path a cell takes is decided at compile time */
+#include <libgeodecomp/misc/testcell.h>
+#include <type_traits>
+static_assert(std::is_base_of<B200Generic::SoA::Binding<HeatSoACube, B200Generic::SoA::DeviceSweep>, B200KernelBinding<HeatSoACube> >::value,
+              "a SoA cell whose only update is a SoA-signature updateLineX() takes the SoA path");
+static_assert(std::is_base_of<B200Generic::SoA::Binding<MixSoATorus, B200Generic::SoA::DeviceSweep>, B200KernelBinding<MixSoATorus> >::value,
+              "a SoA cell whose only update is a SoA-signature updateLineX() takes the SoA path");
+static_assert(std::is_base_of<B200Generic::WordSlicedBinding<TestCellSoA>, B200KernelBinding<TestCellSoA> >::value,
+              "a SoA cell with a per-cell update() stays word-sliced: the reference's TestCellSoA");
+static_assert(std::is_base_of<B200Generic::WordSlicedBinding<TestCell<3> >, B200KernelBinding<TestCell<3> > >::value,
+              "AoS cells are word-sliced");
+
 static int failures = 0;
 #define CHECK(COND)                                                                     \
     do {                                                                                \
