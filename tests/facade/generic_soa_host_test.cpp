@@ -15,7 +15,7 @@
 
 #include "soa_cells.h"
 
-#include <libgeodecomp_b200/b200simulator.h>
+#include <libgeodecomp_b200/b200stripingsimulator.h>
 
 using namespace LibGeoDecomp;
 using namespace soacells;
@@ -158,7 +158,18 @@ static void compare(const char *name, const Coord<DIM>& dim, unsigned steps, int
         std::printf("%-14s %-16s %u steps, member stride %ld: %ld cells differ from SerialSimulator\n",
                     name, dim.toString().c_str(), steps, HostSweep::lastStride, bad);
     }
-    (void)slabs;
+    if (slabs > 0) {
+        /* slabs along z on a slab group: PEER ghost planes of the uniform-layout grids, the group calling the binding's
+         * updateCallback for every slab (b200geo_group_step_with) */
+        B200StripingSimulator<CELL> sim(new SeededInitializer<CELL>(dim, steps), std::vector<int>(slabs, 0), 1);
+        sim.run();
+        long bad = mismatches<CELL, DIM>(*ref.getGrid(), *sim.getGrid());
+        CHECK(bad == 0);
+        std::pair<unsigned long long, unsigned long long> st = sim.stripedGrid().exchangeStatistics();
+        CHECK(slabs == 1 || st.first >= steps);
+        std::printf("%-14s %-16s on %d slabs: %ld cells differ from SerialSimulator (%llu exchanges)\n",
+                    name, dim.toString().c_str(), slabs, bad, st.first);
+    }
 }
 
 template<typename CELL>
@@ -207,10 +218,10 @@ int main()
     CHECK(thrown);
 
     compare<HeatSoACube, 3>("HeatSoACube", Coord<3>(20, 11, 7), 9, 1);
-    compare<HeatSoATorus, 3>("HeatSoATorus", Coord<3>(20, 11, 7), 9, 1);
-    compare<HeatSoACube, 3>("HeatSoACube", Coord<3>(70, 40, 33), 3, 1);      /* second stride of the list */
-    compare<MixSoACube, 3>("MixSoACube", Coord<3>(13, 9, 6), 7, 1);
-    compare<MixSoATorus, 3>("MixSoATorus", Coord<3>(13, 9, 6), 7, 1);
+    compare<HeatSoATorus, 3>("HeatSoATorus", Coord<3>(20, 11, 7), 9, 2);
+    compare<HeatSoACube, 3>("HeatSoACube", Coord<3>(70, 40, 33), 3, 0);      /* second stride of the list */
+    compare<MixSoACube, 3>("MixSoACube", Coord<3>(13, 9, 6), 7, 3);
+    compare<MixSoATorus, 3>("MixSoATorus", Coord<3>(13, 9, 6), 7, 2);
 
     std::printf(failures == 0 ? "generic SoA host test: all checks passed\n" : "generic SoA host test: %d FAILED\n", failures);
     return failures == 0 ? 0 : 1;

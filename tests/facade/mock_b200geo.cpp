@@ -458,7 +458,51 @@ int b200geo_group_step(b200geo_group *grp, int kernel, const void *params, uint3
     return B200GEO_OK;
 }
 
-int b200geo_group_step_with(b200geo_group *, b200geo_update_fn, void *, uint32_t, uint32_t) { return fail(B200GEO_ERR_LOGIC, "not in the mock"); }
+// Callback-driven stepping (generic device paths): per sweep every PEER ghost slice is filled from the neighbour's
+// outermost owned slices (whole padded slices, x / y ghosts included — what the real group copies over NVLink), the
+// periodic images of the other axes are refreshed, the callback updates each slab's whole box, the buffers swap. One
+// exchange per sweep, no rim / interior split: this checks the callback plumbing and the ghost geometry, not the schedule.
+int b200geo_group_step_with(b200geo_group *grp, b200geo_update_fn update, void *ctx, uint32_t first, uint32_t n_steps)
+{
+    const int n = (int)grp->g.size();
+    for (uint32_t t = 0; t < n_steps; ++t) {
+        for (int s = 0; s < n && n > 1; ++s) {
+            b200geo_grid *g = grp->g[s];
+            const int a = g->slab_axis, w = g->g[a];
+            for (int side = 0; side < 2; ++side) {
+                if (g->desc.ghost_mode[a][side] != B200GEO_GHOST_PEER) continue;
+                b200geo_grid *nb = grp->g[(s + (side ? 1 : n - 1)) % n];
+                for (int m = 0; m < g->n; ++m) {
+                    const int e = g->elem[m];
+                    for (int k = 0; k < w; ++k) {
+                        // ghost slice k below / above this slab <- the neighbour's k-th slice from its far / near face
+                        const int dst = side ? g->d[a] + k : -w + k;
+                        const int src = side ? k : nb->d[a] - w + k;
+                        for (int y = (a == 1 ? 0 : -g->g[1]); y < (a == 1 ? 1 : g->d[1] + g->g[1]); ++y) {
+                            const int64_t to = a == 2 ? g->index(-g->g[0], y, dst) : g->index(-g->g[0], dst, 0);
+                            const int64_t from = a == 2 ? nb->index(-nb->g[0], y, src) : nb->index(-nb->g[0], src, 0);
+                            memcpy(g->ptr[g->cur][m] + to * e, nb->ptr[nb->cur][m] + from * e, (size_t)g->px * e);
+                        }
+                    }
+                }
+            }
+            grp->bytes += 1;
+        }
+        if (n > 1) ++grp->exchanges;
+        for (int s = 0; s < n; ++s) {
+            b200geo_grid *g = grp->g[s];
+            b200geo_refresh_ghosts(g, 0);
+            const int32_t origin[3] = {0, 0, 0}, dim[3] = {g->d[0], g->d[1], g->d[2]};
+            int rc = update(ctx, g, first + t, origin, dim, 0);
+            if (rc < 0) return rc;
+        }
+        for (int s = 0; s < n; ++s) {
+            grp->g[s]->cur ^= 1;
+            ++grp->g[s]->sweeps;
+        }
+    }
+    return B200GEO_OK;
+}
 int b200geo_group_sync(b200geo_group *) { return B200GEO_OK; }
 int b200geo_group_stats(const b200geo_group *grp, uint64_t out[2]) { out[0] = grp->exchanges; out[1] = grp->bytes; return B200GEO_OK; }
 
