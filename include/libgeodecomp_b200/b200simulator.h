@@ -229,8 +229,17 @@ public:
         }
         int32_t s[4];
         B200Helpers::toStreak4(streak, box.origin, s);
-        pendingStreaks.insert(pendingStreaks.end(), s, s + 4);
-        pendingCells.insert(pendingCells.end(), cells, cells + n);
+        const std::size_t k = pendingStreaks.size();
+        if (k >= 4 && pendingStreaks[k - 3] == s[1] && pendingStreaks[k - 2] == s[2] && pendingStreaks[k - 1] == s[0]) {
+            pendingStreaks[k - 1] = s[3];   // continues the previous streak (cell after cell along x): one longer streak
+        } else {
+            pendingStreaks.insert(pendingStreaks.end(), s, s + 4);
+        }
+        if (n == 1) {
+            pendingCells.push_back(*cells);
+        } else {
+            pendingCells.insert(pendingCells.end(), cells, cells + n);
+        }
         rowCacheValid = false;
         if (pendingCells.size() >= MAX_PENDING_CELLS) {
             flush();
@@ -250,10 +259,20 @@ public:
         std::vector<int32_t> streaks;
         cells.swap(pendingCells);
         streaks.swap(pendingStreaks);
-        std::map<std::pair<int32_t, int32_t>, std::vector<std::pair<int32_t, int32_t> > > rows;
+        pendingCells.reserve(cells.size());   // the next batch is likely as long: no regrowth from zero
+        typedef std::vector<std::pair<int32_t, int32_t> > Intervals;
+        std::map<std::pair<int32_t, int32_t>, Intervals> rows;
         std::size_t runStreak = 0, runCell = 0, cell = 0;
+        // cell-by-cell Initializers stay in one row for a long time: look the row up once, not once per cell
+        std::pair<int32_t, int32_t> lastRow(0, 0);
+        Intervals *lastTaken = 0;
         for (std::size_t k = 0; k < streaks.size(); k += 4) {
-            std::vector<std::pair<int32_t, int32_t> >& taken = rows[std::make_pair(streaks[k + 2], streaks[k + 1])];
+            std::pair<int32_t, int32_t> row(streaks[k + 2], streaks[k + 1]);
+            if (lastTaken == 0 || !(row == lastRow)) {
+                lastTaken = &rows[row];
+                lastRow = row;
+            }
+            Intervals& taken = *lastTaken;
             bool overlaps = false;
             for (std::size_t i = 0; i < taken.size(); ++i) {
                 overlaps |= streaks[k] < taken[i].second && taken[i].first < streaks[k + 3];
@@ -263,7 +282,8 @@ public:
                 rows.clear();
                 runStreak = k;
                 runCell = cell;
-                rows[std::make_pair(streaks[k + 2], streaks[k + 1])].push_back(std::make_pair(streaks[k], streaks[k + 3]));
+                lastTaken = &rows[row];
+                lastTaken->push_back(std::make_pair(streaks[k], streaks[k + 3]));
             } else if (!taken.empty() && taken.back().second == streaks[k]) {
                 taken.back().second = streaks[k + 3];   // cell after cell along x: one growing interval
             } else {
@@ -306,9 +326,14 @@ public:
             return;
         }
         flush();
-        std::vector<char> buf((std::size_t)n * cellBytes);
         int32_t s[4];
         B200Helpers::toStreak4(streak, box.origin, s);
+        if (cellIsItsOnlyMember()) {
+            B200Helpers::check(b200geo_grid_save_region(handle, s, 1, cells, B200GEO_HOST, 0));
+            B200Helpers::check(b200geo_sync(0));
+            return;
+        }
+        std::vector<char> buf((std::size_t)n * cellBytes);
         B200Helpers::check(b200geo_grid_save_region(handle, s, 1, buf.data(), B200GEO_HOST, 0));
         B200Helpers::check(b200geo_sync(0));
         std::size_t off = 0;
@@ -503,6 +528,11 @@ private:
             return;
         }
         std::size_t n = c1 - c0;
+        if (cellIsItsOnlyMember()) {
+            // an array of such cells IS the member-major stream (Jacobi, Game of Life): no packing pass
+            B200Helpers::check(b200geo_grid_load_region(handle, &streaks[s0], (int)((s1 - s0) / 4), &cells[c0], B200GEO_HOST, 1, 0));
+            return;
+        }
         std::vector<char> buf(n * cellBytes);
         std::size_t off = 0;
         for (std::size_t m = 0; m < members.size(); ++m) {
@@ -513,6 +543,11 @@ private:
             off += n * bytes;
         }
         B200Helpers::check(b200geo_grid_load_region(handle, &streaks[s0], (int)((s1 - s0) / 4), buf.data(), B200GEO_HOST, 1, 0));
+    }
+
+    bool cellIsItsOnlyMember() const
+    {
+        return members.size() == 1 && members[0].offsetInCell == 0 && (std::size_t)members[0].bytes == sizeof(CELL);
     }
 
     void init()
