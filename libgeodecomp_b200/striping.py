@@ -467,8 +467,12 @@ class StripedSimulator:
     def _handleOutput(self, event):
         for w in self.writers:
             if event != WRITER_STEP_FINISHED or self.stepNum % w.getPeriod() == 0:
-                # ParallelWriter::stepFinished(grid, validRegion, globalDims, step, event, rank, lastCall)
-                w.stepFinished(self.grid, self.stepNum, event)
+                if isinstance(w, ParallelWriter):
+                    # ParallelWriter::stepFinished(grid, validRegion, globalDims, step, event, rank, lastCall): the rank's slab
+                    w.stepFinishedRegion(self.grid, self.grid.boundingBox(), self.grid.global_dims, self.stepNum, event,
+                                         self.rank, True)
+                else:
+                    w.stepFinished(self.grid, self.stepNum, event)
 
     def _handleInput(self, event, feedback):
         for s in self.steerers:

@@ -90,6 +90,34 @@ def main():
             if not np.array_equal(mine.view(np.int32), want[m, b[rank]:b[rank + 1]].view(np.int32)):
                 failures.append("lbm ghost %d overlap %s member %s rank %d" % (ghost, overlap, name, rank))
                 break
+    # ParallelWriters are handed the rank's slab as validRegion, the global dimensions and the rank (io/parallelwriter.h:92-99);
+    # the same writer pulls its slab — this is what bench.py's e2e leg does on every rank
+    from libgeodecomp_b200.simulator import ParallelWriter
+
+    class SlabPull(ParallelWriter):
+        def __init__(self, period):
+            ParallelWriter.__init__(self, "", period)
+            self.calls, self.out = [], None
+
+        def stepFinishedRegion(self, grid, validRegion, globalDimensions, step, event, rank_, lastCall):
+            self.calls.append((event, step, validRegion, tuple(globalDimensions), rank_, lastCall))
+            (o, d) = validRegion
+            self.out = grid.saveMember("temp", origin=o, dims=d)
+
+    nz, ny, nx, steps = 12, 5, 6, 4
+    data = synth.jacobi_grid(nx, ny, nz, seed=3)
+    sim = StripedSimulator(SlabInit(data, steps, 0.75), models.ALL["Jacobi7Cube"], rank=rank, world=world, ghost_width=2,
+                           dist=dist, engine=cpu_engine)
+    pull = SlabPull(2)
+    sim.addWriter(pull)
+    sim.run()
+    b = slab_bounds(nz, world)
+    region = ((0, 0, b[rank]), (nx, ny, b[rank + 1] - b[rank]))
+    want_calls = [(0, 0, region, (nx, ny, nz), rank, True), (1, 2, region, (nx, ny, nz), rank, True),
+                  (2, 4, region, (nx, ny, nz), rank, True)]
+    if pull.calls != want_calls or not np.array_equal(pull.out, oracle_py.jacobi(7, False, data, steps, edge=0.75)[b[rank]:b[rank + 1]]):
+        failures.append("parallel writer rank %d: %r" % (rank, pull.calls))
+
     # n-body: slabs of BoxCell containers, one ghost plane of containers (counts + particles) per side and sweep;
     # velocities large enough that particles change containers and slabs
     class CellInit(SimpleInitializer):
