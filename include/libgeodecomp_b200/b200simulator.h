@@ -294,13 +294,18 @@ public:
         ship(streaks, runStreak, streaks.size(), cells, runCell, cell);
     }
 
-    /* single-cell reads are served from a cache of the row they lie in (Writers that walk the grid cell by
-     * cell, e.g. TS_ASSERT_TEST_GRID, misc/testhelper.h:115-136): one transfer per row, not per cell */
+    /* single-cell reads are served from a cache of the rows around them (Writers that walk the grid cell by
+     * cell, e.g. TS_ASSERT_TEST_GRID, misc/testhelper.h:115-136): one transfer per block of up to 64 rows of a plane
+     * (about 256 KiB), not one per cell */
     virtual CELL get(const Coord<DIM>& coord) const
     {
-        Coord<DIM> rowOrigin = coord;
-        rowOrigin.x() = box.origin.x();
-        if (!rowCacheValid || !(rowCacheOrigin == rowOrigin)) {
+        bool hit = rowCacheValid;
+        for (int d = 2; d < DIM && hit; ++d) {
+            hit = coord[d] == rowCacheOrigin[d];
+        }
+        const int y = DIM > 1 ? coord[DIM > 1 ? 1 : 0] : 0, y0 = DIM > 1 ? rowCacheOrigin[DIM > 1 ? 1 : 0] : 0;
+        hit = hit && y >= y0 && y < y0 + rowCacheRows && coord.x() >= box.origin.x() && coord.x() < box.origin.x() + box.dimensions.x();
+        if (!hit) {
             bool inside = true;
             for (int d = 0; d < DIM; ++d) {
                 inside &= coord[d] >= box.origin[d] && coord[d] < box.origin[d] + box.dimensions[d];
@@ -311,12 +316,21 @@ public:
                 get(Streak<DIM>(coord, coord.x() + 1), &cell);
                 return cell;
             }
-            rowCache.resize(box.dimensions.x());
-            get(Streak<DIM>(rowOrigin, rowOrigin.x() + box.dimensions.x()), rowCache.data());
-            rowCacheOrigin = rowOrigin;
+            const int nx = box.dimensions.x();
+            int rows = 1;
+            if (DIM > 1) {
+                int want = (int)((std::size_t)(1 << 18) / ((std::size_t)nx * sizeof(CELL)));
+                rows = (std::max)(1, (std::min)((std::min)(want, 64), box.origin[DIM > 1 ? 1 : 0] + box.dimensions[DIM > 1 ? 1 : 0] - y));
+            }
+            Coord<DIM> origin = coord;
+            origin.x() = box.origin.x();
+            rowCache.resize((std::size_t)rows * nx);
+            fetchRows(origin, rows, rowCache.data());
+            rowCacheOrigin = origin;
+            rowCacheRows = rows;
             rowCacheValid = true;
         }
-        return rowCache[coord.x() - box.origin.x()];
+        return rowCache[(std::size_t)(y - (DIM > 1 ? rowCacheOrigin[DIM > 1 ? 1 : 0] : 0)) * box.dimensions.x() + (coord.x() - box.origin.x())];
     }
 
     virtual void get(const Streak<DIM>& streak, CELL *cells) const
@@ -516,9 +530,42 @@ private:
     static const std::size_t MAX_PENDING_CELLS = 1 << 16;
     mutable std::vector<CELL> pendingCells;        /* combined writes: cells ...                  */
     mutable std::vector<int32_t> pendingStreaks;   /* ... and where they go, {x, y, z, endX} each */
-    mutable std::vector<CELL> rowCache;
+    mutable std::vector<CELL> rowCache;            /* rowCacheRows whole rows of one plane, starting at rowCacheOrigin */
     mutable Coord<DIM> rowCacheOrigin;
+    mutable int rowCacheRows = 0;
     mutable bool rowCacheValid = false;
+
+    /* `rows` whole rows (same plane, consecutive y) starting at `origin` in ONE transfer */
+    void fetchRows(const Coord<DIM>& origin, int rows, CELL *cells) const
+    {
+        flush();
+        const int nx = box.dimensions.x();
+        std::vector<int32_t> streaks((std::size_t)rows * 4);
+        for (int r = 0; r < rows; ++r) {
+            Coord<DIM> c = origin;
+            if (DIM > 1) {
+                c[DIM > 1 ? 1 : 0] += r;
+            }
+            B200Helpers::toStreak4(Streak<DIM>(c, c.x() + nx), box.origin, &streaks[(std::size_t)r * 4]);
+        }
+        const std::size_t n = (std::size_t)rows * nx;
+        if (cellIsItsOnlyMember()) {
+            B200Helpers::check(b200geo_grid_save_region(handle, streaks.data(), rows, cells, B200GEO_HOST, 0));
+            B200Helpers::check(b200geo_sync(0));
+            return;
+        }
+        std::vector<char> buf(n * cellBytes);
+        B200Helpers::check(b200geo_grid_save_region(handle, streaks.data(), rows, buf.data(), B200GEO_HOST, 0));
+        B200Helpers::check(b200geo_sync(0));
+        std::size_t off = 0;
+        for (std::size_t m = 0; m < members.size(); ++m) {
+            const std::size_t bytes = members[m].bytes, at = members[m].offsetInCell;
+            for (std::size_t i = 0; i < n; ++i) {
+                std::memcpy(reinterpret_cast<char*>(cells + i) + at, &buf[off + i * bytes], bytes);
+            }
+            off += n * bytes;
+        }
+    }
 
     /* streaks [s0, s1) of the list with their cells [c0, c1), member-major, in one call */
     void ship(const std::vector<int32_t>& streaks, std::size_t s0, std::size_t s1,
