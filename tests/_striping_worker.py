@@ -107,7 +107,7 @@ def main():
     nz, ny, nx, steps = 12, 5, 6, 4
     data = synth.jacobi_grid(nx, ny, nz, seed=3)
     sim = StripedSimulator(SlabInit(data, steps, 0.75), models.ALL["Jacobi7Cube"], rank=rank, world=world, ghost_width=2,
-                           dist=dist, engine=cpu_engine)
+                           dist=dist, engine=cpu_engine, stream_io=True)   # more than one rank: run() must not stream
     pull = SlabPull(2)
     sim.addWriter(pull)
     sim.run()
@@ -115,6 +115,8 @@ def main():
     region = ((0, 0, b[rank]), (nx, ny, b[rank + 1] - b[rank]))
     want_calls = [(0, 0, region, (nx, ny, nz), rank, True), (1, 2, region, (nx, ny, nz), rank, True),
                   (2, 4, region, (nx, ny, nz), rank, True)]
+    if sim.streamed_runs != 0:
+        failures.append("streamed on %d ranks" % world)
     if pull.calls != want_calls or not np.array_equal(pull.out, oracle_py.jacobi(7, False, data, steps, edge=0.75)[b[rank]:b[rank + 1]]):
         failures.append("parallel writer rank %d: %r" % (rank, pull.calls))
 
