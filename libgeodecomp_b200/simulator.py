@@ -322,6 +322,19 @@ class GridWindow:
         o, d = self.grid._box(origin, dims)
         self.grid.dev.load_member(m, array, o, d, location=location, both=False, stream=self.stream)
 
+    def set_streak(self, origin, cells):
+        """set(Streak, const CELL*): cells is a structured array of the model's cell dtype"""
+        cells = np.asarray(cells, dtype=self.model.cell_dtype)
+        origin, _ = self._inside(tuple(origin), (len(cells),) + (1,) * (self.model.dim - 1))
+        for m, (n, _) in enumerate(self.model.members):
+            self.grid.dev.load_member(m, np.ascontiguousarray(cells[n]), self.grid._local3(origin), (len(cells), 1, 1),
+                                      both=False, stream=self.stream)
+
+    def set(self, coord, cell):
+        one = np.zeros(1, dtype=self.model.cell_dtype)
+        one[0] = np.frombuffer(self.model.cell_to_bytes(cell), dtype=self.model.cell_dtype)[0]
+        self.set_streak(coord, one)
+
     def saveMember(self, name, origin=None, dims=None, out=None, location=capi.HOST):
         m = self.model.member_index(name)
         origin, dims = self._inside(origin, dims)

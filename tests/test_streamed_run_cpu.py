@@ -211,3 +211,26 @@ def test_bench_takes_the_streamed_number_only_when_verified():
     line = {"e2e": dict(plain)}
     bench.try_streamed_e2e(line, boom, time.perf_counter())
     assert line["e2e"]["value"] == 200.0 and "illegal memory access" in line["e2e"]["streamed_schedule"]["error"]
+
+
+def test_initializers_that_write_rows_and_single_cells_into_a_window():
+    nz, ny, nx, steps = 24, 4, 5, 3
+    data = synth.jacobi_grid(nx, ny, nz)
+    model = models.ALL["Jacobi7Cube"]
+
+    class RowInit(SimpleInitializer):
+        def grid(self, target):
+            (ox, oy, oz), (dx, dy, dz) = target.boundingBox()
+            for z in range(oz, oz + dz):
+                for y in range(oy, oy + dy):
+                    row = np.zeros(dx, dtype=model.cell_dtype)
+                    row["temp"] = data[z, y, ox:ox + dx]
+                    target.set_streak((ox, y, z), row[:-1])
+                    target.set((ox + dx - 1, y, z), float(data[z, y, ox + dx - 1]))
+
+    sim = StripedSimulator(RowInit((nx, ny, nz), steps), model, engine=cpu_engine, stream_io=True, stream_chunks=4)
+    pull = Pull((nz, ny, nx), steps)
+    sim.addWriter(pull)
+    sim.run()
+    assert sim.streamed_runs == 1
+    assert np.array_equal(pull.out, oracle_py.jacobi(7, False, data, steps))
