@@ -715,6 +715,27 @@ public:
         initializer->grid(&grid);
     }
 
+    /* Call sites written for CUDASimulator(initializer, blockSize) (parallelization/cudasimulator.h:314-316) and for
+     * OpenMPSimulator(initializer, enableFineGrainedParallelism) (openmpsimulator.h:48-50) keep compiling and keep their
+     * meaning: the launch geometry is the kernels' own business here (b200geo_set_tuning), and a bool is NOT a device id. */
+    B200Simulator(Initializer<CELL> *init, const Coord<3>& /* blockSize */, int device = 0) :
+        MonolithicSimulator<CELL>(init),
+        grid(CoordBox<DIM>(Coord<DIM>(), init->gridBox().dimensions), CELL(), device)
+    {
+        stepNum = init->startStep();
+        simArea << CoordBox<DIM>(Coord<DIM>(), init->gridBox().dimensions);
+        initializer->grid(&grid);
+    }
+
+    B200Simulator(Initializer<CELL> *init, bool /* enableFineGrainedParallelism */) :
+        MonolithicSimulator<CELL>(init),
+        grid(CoordBox<DIM>(Coord<DIM>(), init->gridBox().dimensions), CELL(), 0)
+    {
+        stepNum = init->startStep();
+        simArea << CoordBox<DIM>(Coord<DIM>(), init->gridBox().dimensions);
+        initializer->grid(&grid);
+    }
+
     /* one step, exactly like the reference (serialsimulator.h:70-93) */
     virtual void step()
     {

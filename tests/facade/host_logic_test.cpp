@@ -328,6 +328,31 @@ static void testReferenceConstructorSignatures()
         CHECK(bad == 0);
     }
     CHECK(alive == 0 && CountingBalancer::asked == 0);
+    {
+        // CUDASimulator(initializer, blockSize) and OpenMPSimulator(initializer, enableFineGrainedParallelism) call sites
+        B200Simulator<CELL> cuda(new SeededInitializer<CELL>(dim, 5), Coord<3>(128, 4, 1));
+        B200Simulator<CELL> omp(new SeededInitializer<CELL>(dim, 5), true);     // a bool is not a device id
+        B200Simulator<CELL> plain(new SeededInitializer<CELL>(dim, 5), 0);      // an int is
+        B200Simulator<CELL> second(new SeededInitializer<CELL>(dim, 5), 1);
+        int devices[4] = {-1, -1, -1, -1};
+        B200Simulator<CELL> *sims[4] = {&cuda, &omp, &plain, &second};
+        for (int i = 0; i < 4; ++i) {
+            const B200Grid<CELL> *g = dynamic_cast<const B200Grid<CELL>*>(sims[i]->getGrid());
+            CHECK(g != 0);
+            b200geo_grid_device(const_cast<B200Grid<CELL>*>(g)->raw(), &devices[i]);
+        }
+        CHECK(devices[0] == 0 && devices[1] == 0 && devices[2] == 0 && devices[3] == 1);
+        cuda.run();
+        omp.run();
+        plain.run();
+        long bad = 0;
+        CoordBox<3> box(Coord<3>(), dim);
+        for (CoordBox<3>::Iterator i = box.begin(); i != box.end(); ++i) {
+            double want = ref.getGrid()->get(*i).temp;
+            bad += cuda.getGrid()->get(*i).temp != want || omp.getGrid()->get(*i).temp != want || plain.getGrid()->get(*i).temp != want;
+        }
+        CHECK(bad == 0);
+    }
     std::printf("reference constructor signatures (initializer, balancer, period[, ghostZoneWidth]): balancers owned and released, results identical\n");
 }
 

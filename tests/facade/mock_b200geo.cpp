@@ -29,6 +29,7 @@ struct b200geo_grid {
     std::vector<char> flat[2];                      // uniform element layout: member m at stride * (bytes before m)
     char *ptr[2][B200GEO_MAX_MEMBERS];
     int64_t stride;
+    int device;                                     // what the caller asked for (there is one host "device")
     unsigned char edge[8 * B200GEO_MAX_MEMBERS];
     uint64_t sweeps;
 
@@ -171,9 +172,11 @@ uint64_t b200geo_launch_count(void) { return 0; }
 
 static int create_grid(const b200geo_grid_desc *desc, int64_t stride, b200geo_grid **out);
 
-int b200geo_grid_create(const b200geo_grid_desc *desc, int, b200geo_grid **out)
+int b200geo_grid_create(const b200geo_grid_desc *desc, int device, b200geo_grid **out)
 {
-    return create_grid(desc, 0, out);
+    int rc = create_grid(desc, 0, out);
+    if (rc == B200GEO_OK) (*out)->device = device;
+    return rc;
 }
 
 int b200geo_grid_uniform_min_stride(const b200geo_grid_desc *desc, int64_t *min_stride)
@@ -184,13 +187,15 @@ int b200geo_grid_uniform_min_stride(const b200geo_grid_desc *desc, int64_t *min_
     return B200GEO_OK;
 }
 
-int b200geo_grid_create_uniform(const b200geo_grid_desc *desc, int, int64_t member_stride, b200geo_grid **out)
+int b200geo_grid_create_uniform(const b200geo_grid_desc *desc, int device, int64_t member_stride, b200geo_grid **out)
 {
     int64_t least = 0;
     b200geo_grid_uniform_min_stride(desc, &least);
     if (member_stride <= 0 || member_stride % 256 != 0) return fail(B200GEO_ERR_INVALID, "member stride must be a positive multiple of 256 elements");
     if (member_stride < least) return fail(B200GEO_ERR_INVALID, "member stride smaller than the padded grid");
-    return create_grid(desc, member_stride, out);
+    int rc = create_grid(desc, member_stride, out);
+    if (rc == B200GEO_OK) (*out)->device = device;
+    return rc;
 }
 
 int b200geo_grid_member_stride(const b200geo_grid *g, int64_t *member_stride)
@@ -262,7 +267,7 @@ static int create_grid(const b200geo_grid_desc *desc, int64_t stride, b200geo_gr
 
 int b200geo_grid_destroy(b200geo_grid *g) { delete g; return B200GEO_OK; }
 int b200geo_grid_buffer_bytes(const b200geo_grid *g, uint64_t *bytes) { *bytes = (uint64_t)(g->px * g->py * g->pz) * g->cell_bytes; return B200GEO_OK; }
-int b200geo_grid_device(const b200geo_grid *, int *device) { *device = 0; return B200GEO_OK; }
+int b200geo_grid_device(const b200geo_grid *g, int *device) { *device = g->device; return B200GEO_OK; }
 
 int b200geo_grid_layout(const b200geo_grid *g, int, int64_t *pitch, int64_t *plane, int64_t *origin)
 {
