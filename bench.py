@@ -352,11 +352,26 @@ def bench_device(workload, args, rank, world, dist, torch, with_e2e=True, with_c
             def streamed(sim=sim):
                 capi.set_tuning("jacobi.tb", depth)
                 return streamed_e2e(sim, model, pinned, K, depth, torch, capi), 1e-9 * cells_all * K
-            # run by main() as the LAST thing on the device, under a watchdog: whatever happens in there, every other
-            # number of the line has been measured by then
+            # run by `bench.py --streamed-child`, a process of its own that main() starts once every other number of
+            # the line has been measured
             out["_streamed"] = streamed
     del sim
     return out
+
+
+def streamed_child(args, limit_s=200.0):
+    """Runs `bench.py --streamed-child` for the same workload and step count and returns (result dict, updates per run)."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--streamed-child", "--workload", args.workload,
+           "--steps", str(args.steps), "--warmup", str(min(args.warmup, 3)), "--no-others", "--no-cpu"]
+    env = dict(os.environ)
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT"):
+        env.pop(k, None)
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=limit_s, env=env, cwd=ROOT)
+    lines = [ln for ln in res.stdout.splitlines() if ln.startswith("{")]
+    if res.returncode != 0 or not lines:
+        raise RuntimeError("child exited with %d: %s" % (res.returncode, (res.stderr or res.stdout)[-300:].replace("\n", " | ")))
+    d = json.loads(lines[-1])
+    return d["streamed"], d["updates"]
 
 
 def try_streamed_e2e(line, streamed, t_start, limit_s=240.0):
@@ -561,11 +576,26 @@ def main():
                     "0 = the workload's temporal blocking depth")
     ap.add_argument("--no-others", action="store_true", help="skip the secondary workloads (configs 0, 1, 3)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--streamed-child", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
 
     if args.impl == "reference":
         reference_arm(args)
+        return
+
+    if args.streamed_child:
+        # child of try_streamed_e2e: the main workload's legs again (they bring host arrays and device grid into the same
+        # state), then the streamed attempt; prints {"streamed": ..., "updates": ...}
+        import torch
+        torch.cuda.set_device(0)
+        res = bench_device(args.workload, args, 0, 1, None, torch, with_e2e=True, with_clocks=False)
+        attempt = res.get("_streamed")
+        if attempt is None:
+            print(json.dumps({"streamed": {"verified": False, "error": "run() cannot be streamed for this workload"}, "updates": 0.0}))
+            return
+        streamed, updates = attempt()
+        print(json.dumps({"streamed": streamed, "updates": updates}), flush=True)
         return
 
     import torch
@@ -583,6 +613,8 @@ def main():
     t_start = time.perf_counter()
 
     main_res = bench_device(args.workload, args, rank, world, dist if world > 1 else None, torch)
+    if main_res.get("_streamed") is not None:
+        main_res["_streamed"] = True     # only the fact is kept; the closure would pin the grids and the host arrays
 
     others = []
     if not args.no_others:
@@ -629,12 +661,10 @@ def main():
         if others:
             line["others"] = others
         line["wall_s"] = time.perf_counter() - t_start
-        streamed = main_res.get("_streamed")
-        if streamed is not None:
-            try_streamed_e2e(line, streamed, t_start)
+        if main_res.get("_streamed") is not None:
+            # in a process of its own: a crash, a hang or a poisoned CUDA context in there cannot take this line down
+            try_streamed_e2e(line, lambda: streamed_child(args), t_start)
         print(json.dumps(line), flush=True)
-        if (line.get("e2e") or {}).get("streamed_schedule", {}).get("error"):
-            os._exit(0)   # the CUDA context may be unusable after a failed attempt: skip the teardown
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

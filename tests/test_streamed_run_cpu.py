@@ -234,3 +234,17 @@ def test_initializers_that_write_rows_and_single_cells_into_a_window():
     sim.run()
     assert sim.streamed_runs == 1
     assert np.array_equal(pull.out, oracle_py.jacobi(7, False, data, steps))
+
+
+def test_a_failing_child_process_leaves_the_plain_number_in_place():
+    """bench.py runs the streamed attempt in a process of its own; here there is no GPU, so the child fails — the line
+    keeps its plain e2e number and says why"""
+    sys.path.insert(0, os.path.dirname(HERE))
+    import argparse
+    import time
+    import bench
+    args = argparse.Namespace(workload="jacobi7_128", steps=2, warmup=0)
+    line = {"e2e": {"value": 200.0, "unit": "GLUPS", "ms_per_run": 500.0}}
+    bench.try_streamed_e2e(line, lambda: bench.streamed_child(args, limit_s=120.0), time.perf_counter())
+    assert line["e2e"]["value"] == 200.0
+    assert line["e2e"]["streamed_schedule"]["verified"] is False and "child exited" in line["e2e"]["streamed_schedule"]["error"]
