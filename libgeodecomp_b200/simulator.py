@@ -335,6 +335,20 @@ class GridWindow:
         one[0] = np.frombuffer(self.model.cell_to_bytes(cell), dtype=self.model.cell_dtype)[0]
         self.set_streak(coord, one)
 
+    def get_streak(self, origin, length):
+        """get(Streak, CELL*): synchronous — waits for the window's stream"""
+        origin, _ = self._inside(tuple(origin), (length,) + (1,) * (self.model.dim - 1))
+        out = np.zeros(length, dtype=self.model.cell_dtype)
+        for m, (n, t) in enumerate(self.model.members):
+            v = np.zeros(length, dtype=t)
+            self.grid.dev.save_member(m, v, self.grid._local3(origin), (length, 1, 1), stream=self.stream)
+            self.grid.engine.sync(self.stream)
+            out[n] = v
+        return out
+
+    def get(self, coord):
+        return self.get_streak(coord, 1)[0]
+
     def saveMember(self, name, origin=None, dims=None, out=None, location=capi.HOST):
         m = self.model.member_index(name)
         origin, dims = self._inside(origin, dims)

@@ -231,9 +231,29 @@ def test_initializers_that_write_rows_and_single_cells_into_a_window():
     sim = StripedSimulator(RowInit((nx, ny, nz), steps), model, engine=cpu_engine, stream_io=True, stream_chunks=4)
     pull = Pull((nz, ny, nx), steps)
     sim.addWriter(pull)
+
+    class CellReader(ParallelWriter):
+        """reads single cells and rows of the windows it is handed"""
+        def __init__(self):
+            ParallelWriter.__init__(self, "", steps)
+            self.seen = np.full((nz, ny, nx), np.nan)
+
+        def stepFinishedRegion(self, grid, validRegion, globalDimensions, step, event, rank, lastCall):
+            (ox, oy, oz), (dx, dy, dz) = validRegion
+            if event == 2:
+                for z in range(oz, oz + dz):
+                    self.seen[z, 0, :] = grid.get_streak((ox, oy, z), dx)["temp"]
+                    self.seen[z, 1, 2] = grid.get((ox + 2, oy + 1, z))["temp"]
+                with pytest.raises(ValueError):
+                    grid.get((ox, oy, oz + dz))     # outside the window
+
+    reader = CellReader()
+    sim.addWriter(reader)
     sim.run()
     assert sim.streamed_runs == 1
-    assert np.array_equal(pull.out, oracle_py.jacobi(7, False, data, steps))
+    want = oracle_py.jacobi(7, False, data, steps)
+    assert np.array_equal(pull.out, want)
+    assert np.array_equal(reader.seen[:, 0, :], want[:, 0, :]) and np.array_equal(reader.seen[:, 1, 2], want[:, 1, 2])
 
 
 def test_a_failing_child_process_leaves_the_plain_number_in_place():
