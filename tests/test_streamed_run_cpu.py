@@ -268,3 +268,26 @@ def test_a_failing_child_process_leaves_the_plain_number_in_place():
     bench.try_streamed_e2e(line, lambda: bench.streamed_child(args, limit_s=120.0), time.perf_counter())
     assert line["e2e"]["value"] == 200.0
     assert line["e2e"]["streamed_schedule"]["verified"] is False and "child exited" in line["e2e"]["streamed_schedule"]["error"]
+
+
+def test_streamed_schedule_random_configurations():
+    """40 seeded random combinations of kernel, fusing depth, step count, grid height and chunk count"""
+    rng = np.random.default_rng(20260117)
+    streamed = 0
+    for _ in range(40):
+        kind = int(rng.choice([6, 7, 27]))
+        depth = int(rng.integers(1, 5))
+        steps = int(rng.integers(1, 14))
+        nz, ny, nx = int(rng.integers(8, 60)), int(rng.integers(3, 7)), int(rng.integers(3, 8))
+        chunks = int(rng.integers(2, 12))
+        data = synth.jacobi_grid(nx, ny, nz, seed=int(rng.integers(1, 1000)))
+        sim = StripedSimulator(BoxInit(data, steps, 0.75), models.ALL["Jacobi%dCube" % kind], engine=cpu_engine,
+                               stream_io=True, stream_depth=depth, stream_chunks=chunks)
+        pull = Pull((nz, ny, nx), steps)
+        sim.addWriter(pull)
+        sim.run()
+        want = oracle_py.jacobi(kind, False, data, steps, edge=0.75)
+        got = pull.out if sim.streamed_runs else sim.getGrid().saveMember("temp")
+        assert np.array_equal(got, want), (kind, depth, steps, (nz, ny, nx), chunks, sim.streamed_runs)
+        streamed += sim.streamed_runs
+    assert streamed >= 25     # most of them can be streamed; the rest are too short for two chunks and fall back
