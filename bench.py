@@ -163,18 +163,119 @@ def synth_members(workload, dims, z0, nz_total, alloc, share=False):
     return model, {"alive": out}
 
 
-def run_cpu_reference(workload, steps, warmup, threads=None):
-    """Time the reference's own SerialSimulator/OpenMPSimulator (oracle/_ref) on a bounded sample of
-    the workload. Returns (glups, dict)."""
+def initial_window(workload, dims, world, lo, hi):
+    """The synthetic input of synth_members on the global box [lo, hi) (array order: slowest axis first, global
+    coordinates), regenerated without the full grid: {member: array}."""
+    from libgeodecomp_b200 import models, synth
+    name = WORKLOADS[workload][0]
+    model = models.ALL[name]
+    if name.startswith("Jacobi"):
+        nx, ny, nz = dims
+        tile = min(nz, 32)
+        out = np.empty(tuple(h - l for l, h in zip(lo, hi)), dtype=np.float64)
+        gz = np.arange(lo[0], hi[0])
+        for r in sorted(set(gz // nz)):          # every rank repeats its own 32-plane block (seed 42 + z0)
+            sel = np.nonzero(gz // nz == r)[0]
+            out[sel] = synth.jacobi_box(nx, ny, tile, (0, lo[1], lo[2]), (0, hi[1], hi[2]), seed=42 + int(r) * nz,
+                                        zmap=(gz[sel] % nz) % tile)
+        return {"temp": out}
+    if name == "LBMCellF":
+        nx, ny, nz = dims
+        shape = tuple(h - l for l, h in zip(lo, hi))
+        out = {}
+        for n, t in model.members:
+            if n == "state":
+                out[n] = synth.lbm_states_box(nx, ny, nz * world, lo, hi)
+            else:
+                out[n] = np.full(shape, 1.0 if n in ("C", "density") else 0.0, dtype=t)
+        return out
+    nx, ny = dims
+    tile = min(ny, 1024)
+    block = synth.gol_grid(nx, tile)
+    gy = np.arange(lo[0], hi[0])
+    return {"alive": np.ascontiguousarray(block[(gy % ny) % tile][:, lo[1]:hi[1]])}
+
+
+def verify_windows(workload, dims, world, rank, host_out, steps):
+    """The checker of the e2e leg: this rank's pulled result (host arrays, the rank's slab) against the oracle on
+    WINDOWS of the global grid — at both slab faces (cells that depend on the neighbours' planes through `steps` halo
+    exchanges) and inside. The update is local, so the oracle runs on the window plus a halo of `steps` cells wherever the
+    window side is not a true domain boundary (tests/test_fullsize_gpu.py uses the same method). Bit-exact or False."""
+    from oracle import oracle_py
+    from libgeodecomp_b200 import models
+    name = WORKLOADS[workload][0]
+    model = models.ALL[name]
+    nd = len(dims)
+    ext = list(dims[::-1])                       # per-rank extents, slowest axis first
+    gext = [ext[0] * world] + ext[1:]
+    z0 = ext[0] * rank
+    nz = ext[0]
+    dz = min(4, nz)
+
+    def clip(a, n, size):
+        a = max(0, min(a, n - size))
+        return a, min(n, a + size)
+
+    inner = [clip(n // 2 - 7, n, 14) for n in ext[1:-1]] + [clip(ext[-1] // 3, ext[-1], 24)]
+    corner = [clip(n, n, 12) for n in ext[1:-1]] + [clip(ext[-1], ext[-1], 20)]
+    windows = [[(0, dz)] + inner, [(nz - dz, nz)] + corner, [clip(nz // 2 - 2, nz, 4)] + inner]
+    checked = 0
+    for win in windows:
+        glo = [z0 + win[0][0]] + [a for a, _ in win[1:]]
+        ghi = [z0 + win[0][1]] + [b for _, b in win[1:]]
+        lo = [max(0, a - steps) for a in glo]
+        hi = [min(n, b + steps) for b, n in zip(ghi, gext)]
+        members = initial_window(workload, dims, world, lo, hi)
+        inner_sl = tuple(slice(a - l, b - l) for a, b, l in zip(glo, ghi, lo))
+        mine_sl = (slice(win[0][0], win[0][1]),) + tuple(slice(a, b) for a, b in win[1:])
+        if name.startswith("Jacobi"):
+            want = {"temp": oracle_py.jacobi(int(name[6:-4]), False, members["temp"], steps)}
+        elif name == "LBMCellF":
+            raw = np.stack([members[n].view(np.float32) for n, _ in model.members])
+            res = oracle_py.lbm(raw, steps)
+            want = {n: res[m].view(t) for m, (n, t) in enumerate(model.members)}
+        else:
+            want = {"alive": oracle_py.gol(False, members["alive"], steps)}
+        for n, w in want.items():
+            got = host_out[n][mine_sl]
+            if not np.array_equal(got.view(np.uint8), np.ascontiguousarray(w[inner_sl]).view(np.uint8)):
+                return {"ok": False, "rank": rank, "window": [glo, ghi], "member": n}
+        checked += int(np.prod([b - a for a, b in zip(glo, ghi)]))
+    return {"ok": True, "rank": rank, "windows": len(windows), "cells": checked}
+
+
+def mem_available_gb():
+    try:
+        with open("/proc/meminfo") as f:
+            for line in f:
+                if line.startswith("MemAvailable:"):
+                    return int(line.split()[1]) / 1048576.0
+    except OSError:
+        pass
+    return 0.0
+
+
+def run_cpu_reference(workload, steps, warmup, threads=None, full=True, full_steps=20):
+    """Time the reference's own OpenMPSimulator (oracle/_ref) on the workload. The Jacobi 1024^3 configurations run at
+    FULL size when the host has the memory (two 1032^3 f64 grids = 17.6 GB; the synthetic input repeats every 32 planes,
+    so only that block is handed over) — SURVEY.md 8(d) C3 — with the step count capped so that the run ends within a
+    few minutes; otherwise, and for the other workloads, on a bounded sample. Returns (glups, dict)."""
     from oracle import oracle_py
     from libgeodecomp_b200 import synth
     model_name, dims, _, _, ref_model = WORKLOADS[workload]
     cores = threads or os.cpu_count()
+    tile, same_config = 0, False
     if workload in ("jacobi27", "jacobi7"):
-        sdims, sample = (1024, 1024, 32), "1024x1024x32 slab of the 1024^3 grid"
-        raw = synth.jacobi_grid(*sdims)
+        if full and oracle_py.have_ref(ref_model) and mem_available_gb() >= 30.0:
+            sdims, tile, same_config = dims, 32, True
+            steps, warmup = min(steps, full_steps), 0
+            sample = "the full 1024^3 grid (same config as the device arm)"
+            raw = synth.jacobi_grid(dims[0], dims[1], tile)
+        else:
+            sdims, sample = (1024, 1024, 32), "1024x1024x32 slab of the 1024^3 grid"
+            raw = synth.jacobi_grid(*sdims)
     elif workload == "jacobi7_128":
-        sdims, sample = (128, 128, 128), "full 128^3 grid"
+        sdims, sample, same_config = (128, 128, 128), "full 128^3 grid", True
         raw = synth.jacobi_grid(*sdims)
     elif workload == "lbm":
         sdims, sample = (512, 512, 8), "512x512x8 slab of the 512^3 grid"
@@ -184,12 +285,12 @@ def run_cpu_reference(workload, steps, warmup, threads=None):
         raw = synth.gol_grid(sdims[0], sdims[1])
     if oracle_py.have_ref(ref_model):
         if warmup:
-            oracle_py.run_ref(ref_model, raw, sdims, warmup, omp=True, threads=cores, want_output=False)
-        _, st = oracle_py.run_ref(ref_model, raw, sdims, steps, omp=True, threads=cores, want_output=False)
+            oracle_py.run_ref(ref_model, raw, sdims, warmup, omp=True, threads=cores, want_output=False, tile=tile)
+        _, st = oracle_py.run_ref(ref_model, raw, sdims, steps, omp=True, threads=cores, want_output=False, tile=tile)
         glups = st["glups_compute"]
         info = {"kind": "reference", "cores": cores, "simulator": st["simulator"],
                 "sample": "%s x %d steps, reference OpenMPSimulator built from /root/reference, TimeCompute interval" % (sample, steps),
-                "seconds": st["time_compute_s"]}
+                "seconds": st["time_compute_s"], "steps": steps, "same_config": same_config}
     else:
         fn = {"jacobi27": lambda: oracle_py.jacobi(27, False, raw, steps),
               "jacobi7": lambda: oracle_py.jacobi(7, False, raw, steps),
@@ -201,7 +302,7 @@ def run_cpu_reference(workload, steps, warmup, threads=None):
         dt = time.perf_counter() - t0
         glups = 1e-9 * steps * float(np.prod(sdims)) / dt
         info = {"kind": "port", "cores": cores, "sample": "%s x %d steps, C restatement (oracle/oracle.c, OpenMP)" % (sample, steps),
-                "seconds": dt}
+                "seconds": dt, "steps": steps, "same_config": same_config}
     info.update({"value": glups, "unit": "GLUPS"})
     return glups, info
 
@@ -216,10 +317,12 @@ def reference_arm(args):
     line = {
         "impl": "reference", "metric": "GLUPS (giga lattice updates/s)", "value": glups, "unit": "GLUPS",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * info["seconds"] / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
+        "ms_per_step": 1e3 * info["seconds"] / max(1, info["steps"]), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": dtype, "data": "synthetic",
         "config": {"workload": DESCRIPTION[args.workload], "cell": model_name,
-                   "note": "CPU reference on the host cores of this box; bounded sample, see cpu_baseline.sample"},
+                   "dims_per_gpu": list(dims), "same_config": info["same_config"],
+                   "note": "CPU reference on the host cores of this box; see cpu_baseline.sample for what was timed "
+                           "(%d of the %d steps asked for)" % (info["steps"], args.steps)},
         "cpu_baseline": info,
         "e2e": {"value": glups, "unit": "GLUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "wall_s": time.perf_counter() - t0,
@@ -343,6 +446,33 @@ def bench_device(workload, args, rank, world, dist, torch, with_e2e=True, with_c
                       "ms_per_run": e_ms, "wall_ms_rank0": 1e3 * wall,
                       "what": "StripedSimulator.run(): Initializer::grid from pinned host memory -> %d steps -> "
                               "Writer pulls the final grid to pinned host memory" % K}
+        # ---- the checker: every rank's pulled slab against the oracle on windows at both slab faces and inside
+        if not args.no_verify:
+            vsteps = K
+            if K > 40:
+                # the oracle's halo grows with the step count: beyond 40 steps the same call is repeated (untimed) with
+                # 16 steps on the regenerated input and THAT result is checked
+                vsteps = 16
+                spare = iter(list(members.values()))
+                synth_members(workload, dims, z0, gdims[last], lambda shape, dtype: next(spare), share=False)
+                sim.initializer = Init(gdims, vsteps)
+                sim.run()
+                barrier()
+            ver = verify_windows(workload, dims, world, rank, host_out, vsteps)
+            flags = torch.tensor([1 if ver["ok"] else 0, ver.get("cells", 0)], dtype=torch.int64, device="cuda")
+            if world > 1:
+                all_flags = [torch.zeros_like(flags) for _ in range(world)]
+                dist.all_gather(all_flags, flags)
+            else:
+                all_flags = [flags]
+            per_rank = [bool(int(f[0].item())) for f in all_flags]
+            out["verified"] = {"ok": all(per_rank), "per_rank": per_rank, "steps": vsteps,
+                               "cells_per_rank": int(all_flags[0][1].item()),
+                               "what": ("the timed e2e run's pulled result" if vsteps == K else
+                                        "an untimed repeat of the e2e call with %d steps" % vsteps) +
+                                       ", bit for bit against the oracle on 3 windows per rank (both slab faces, interior)"}
+            if not ver["ok"]:
+                out["verified"]["first_mismatch"] = ver
         # The same call with stream_io: upload, sweeps and download pipelined chunk by chunk along z (time-skewed
         # schedule, striping.py::_run_streamed). Taken as the e2e number only if the result is bit-identical to the
         # plain schedule on the same input AT THIS SIZE (checksums of the device grid and of the pulled host copy).
@@ -351,7 +481,7 @@ def bench_device(workload, args, rank, world, dist, torch, with_e2e=True, with_c
 
             def streamed(sim=sim):
                 capi.set_tuning("jacobi.tb", depth)
-                return streamed_e2e(sim, model, pinned, K, depth, torch, capi), 1e-9 * cells_all * K
+                return streamed_e2e(sim, model, pinned, K, depth, torch, capi, workload, dims, Init), 1e-9 * cells_all * K
             # run by `bench.py --streamed-child`, a process of its own that main() starts once every other number of
             # the line has been measured
             out["_streamed"] = streamed
@@ -426,22 +556,23 @@ def make_plugins(pinned, host_out, last, z0):
     return Init, PullWriter
 
 
-def streamed_e2e(sim, model, pinned, K, depth, torch, capi):
-    """Times sim.run() with stream_io and checks it against the plain schedule. On entry the host arrays and the
-    device grid hold the same state R1 (a plain run() has just finished). (1) K more sweeps on the device with the
-    plain schedule -> checksum of R2; (2) streamed run() from the host arrays (R1) -> device and host hold R2';
-    (3) R2' must equal R2 bit for bit, on the device and in the pulled host copy."""
+def streamed_e2e(sim, model, pinned, K, depth, torch, capi, workload, dims, Init):
+    """Times sim.run() with stream_io and checks it. On entry the host arrays and the device grid hold the same state
+    R1 (a plain run() has just finished). (1) K more sweeps on the device with the plain schedule -> R2, kept as a dense
+    device array; (2) streamed run() from the host arrays (R1) -> device and host hold R2'; (3) R2' must equal R2
+    ELEMENT BY ELEMENT, on the device and in the pulled host copy (read right after run() returns, with no
+    synchronisation in between: the ParallelWriter contract). (4) a streamed run of <= 16 steps from the regenerated
+    synthetic input, its pulled result bit for bit against the oracle on windows (verify_windows)."""
     name = model.members[0][0]
     host = pinned[name]
-    dense = torch.empty(host.shape, dtype=torch.float64, device="cuda")
-
-    def device_checksum():
-        sim.grid.saveMember(name, out=dense, location=capi.CUDA_DEVICE)
-        torch.cuda.synchronize()
-        return int(dense.view(torch.int64).sum().item())
+    want = torch.empty(host.shape, dtype=torch.float64, device="cuda")
+    got = torch.empty(host.shape, dtype=torch.float64, device="cuda")
 
     sim.advance(K)
-    want = device_checksum()
+    sim.grid.saveMember(name, out=want, location=capi.CUDA_DEVICE)
+    torch.cuda.synchronize()
+    sample = sorted(set(list(range(0, host.shape[0], 64)) + [host.shape[0] - 2, host.shape[0] - 1]))
+    want_sample = want[sample].cpu().numpy()
     sim.stream_io, sim.stream_depth = True, depth
     plan = sim._stream_plan()
     if plan is None:
@@ -453,20 +584,72 @@ def streamed_e2e(sim, model, pinned, K, depth, torch, capi):
     ev0.record()
     sim.run()
     ev1.record()
-    torch.cuda.synchronize()
+    # read by the CPU right after run() returned, with no synchronisation of our own (the last planes pulled are the
+    # ones that would still be in flight): the ParallelWriter contract
+    got_now = bool(np.array_equal(host[sample].view(np.int64), want_sample.view(np.int64)))
     wall = time.perf_counter() - t0
+    got_host = got_now
+    step = max(1, host.shape[0] // 16)
+    for a in range(0, host.shape[0], step):
+        got[a:a + step].copy_(torch.from_numpy(host[a:a + step]))
+        got_host = got_host and bool(torch.equal(got[a:a + step].view(torch.int64), want[a:a + step].view(torch.int64)))
+    torch.cuda.synchronize()
     ms = ev0.elapsed_time(ev1)
     launches = capi.launch_count() - launches0
-    got_device = device_checksum()
-    got_host = int(host.reshape(-1).view(np.int64).sum(dtype=np.int64))
-    del dense
+    sim.grid.saveMember(name, out=got, location=capi.CUDA_DEVICE)
+    torch.cuda.synchronize()
+    got_device = bool(torch.equal(got.view(torch.int64), want.view(torch.int64)))
+    del got, want
     levels, chunk = plan
-    return {"verified": sim.streamed_runs >= 1 and got_device == want and got_host == want, "ms_per_run": ms,
+    # (4) against the oracle
+    vsteps = min(K, 16)
+    spare = iter(list(pinned.values()))
+    synth_members(workload, dims, 0, dims[-1], lambda shape, dtype: next(spare), share=False)
+    sim.initializer = Init(list(dims), vsteps)
+    runs = sim.streamed_runs
+    sim.run()
+    oracle = verify_windows(workload, dims, 1, 0, pinned, vsteps) if sim.streamed_runs == runs + 1 else {"ok": False}
+    return {"verified": sim.streamed_runs >= 2 and got_device and got_host and oracle["ok"], "ms_per_run": ms,
             "wall_ms": 1e3 * wall, "launches": launches,
             "schedule": "streamed: z-chunks of %d planes, %d levels of <= %d fused sweeps, time-skewed; upload / sweeps / "
                         "download on three streams" % (chunk, len(levels), max(levels)),
-            "how": "int64 checksum of the final grid equals the plain schedule's on the same input (device %s, host %s)"
-                   % (got_device == want, got_host == want)}
+            "how": "final grid equal ELEMENT BY ELEMENT to the plain schedule's on the same input (device %s; host copy read "
+                   "right after run() returned %s); a streamed run of %d steps bit-exact vs the oracle on 3 windows (%s)"
+                   % (got_device, got_host, vsteps, oracle["ok"])}
+
+
+def gpu_reference(workload, args, torch):
+    """The reference's OWN GPU path on this B200 beside ours: LibGeoDecomp's CUDASimulator<CELL> (cudasimulator.h, AoS
+    Jacobi cell with FixedCoord access) recompiled for sm_100a (oracle/_ref/lgd_ref_cuda_jacobi, built by oracle/Makefile
+    from /root/reference) at 512^3 — its host-side DisplacedGrid initialisation makes 1024^3 impractical — and
+    libb200geo.so on a grid of the same size, both timed with CUDA events around K steps of resident data."""
+    from libgeodecomp_b200 import capi, models
+    from libgeodecomp_b200.simulator import B200Grid
+    kind = {"jacobi27": "27", "jacobi7": "7"}.get(workload)
+    exe = os.path.join(ROOT, "oracle", "_ref", "lgd_ref_cuda_jacobi")
+    if kind is None or not os.access(exe, os.X_OK):
+        return None
+    n, K = 512, max(10, min(args.steps, 50))
+    res = subprocess.run([exe, str(n), str(K), kind], capture_output=True, text=True, timeout=300)
+    lines = [ln for ln in res.stdout.splitlines() if ln.startswith("{")]
+    if res.returncode != 0 or not lines:
+        return {"error": "lgd_ref_cuda_jacobi exited with %d" % res.returncode}
+    ref = json.loads(lines[-1])
+    model = models.ALL[WORKLOADS[workload][0]]
+    grid = B200Grid(model, (n, n, n))
+    grid.loadMember("temp", torch.rand((n, n, n), dtype=torch.float64, device="cuda"), location=capi.CUDA_DEVICE)
+    grid.dev.step(model.kernel, n_steps=4)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    ev0.record()
+    grid.dev.step(model.kernel, n_steps=K)
+    ev1.record()
+    torch.cuda.synchronize()
+    ours = 1e-9 * n ** 3 * K / (1e-3 * ev0.elapsed_time(ev1))
+    del grid
+    return {"impl": ref["impl"], "cell": ref["cell"], "dims": ref["dims"], "steps": K, "value": ref["glups"], "unit": "GLUPS",
+            "ms_per_step": ref["ms_per_step"], "b200geo_same_dims": ours, "ratio": ours / ref["glups"] if ref["glups"] else None,
+            "cuda_status": ref.get("cuda")}
 
 
 def bench_nbody(args, rank, world, dist, torch, containers=108, with_e2e=True):
@@ -576,6 +759,7 @@ def main():
                     "0 = the workload's temporal blocking depth")
     ap.add_argument("--no-others", action="store_true", help="skip the secondary workloads (configs 0, 1, 3)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-verify", action="store_true", help="skip the oracle check of the e2e result")
     ap.add_argument("--streamed-child", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
@@ -637,9 +821,16 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         try:
-            _, cpu = run_cpu_reference(args.workload, 10, 1)
+            _, cpu = run_cpu_reference(args.workload, 10, 1, full_steps=4)
         except Exception as e:  # the baseline is reported, never required for the GPU number
             cpu = {"value": None, "unit": "GLUPS", "cores": os.cpu_count(), "kind": "reference", "sample": "failed: %r" % (e,)}
+
+    gpu_ref = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        try:
+            gpu_ref = gpu_reference(args.workload, args, torch)
+        except Exception as e:  # a comparator, never required for the line
+            gpu_ref = {"error": repr(e)}
 
     if rank == 0:
         line = {
@@ -656,8 +847,21 @@ def main():
             "roofline": main_res["roofline"], "e2e": main_res.get("e2e"), "gpu_launches": main_res["gpu_launches"],
             "clocks": main_res["clocks"],
         }
+        if main_res.get("verified") is not None:
+            line["verified"] = main_res["verified"]
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if gpu_ref is not None:
+            line["gpu_reference"] = gpu_ref
+        # the secondary workloads' headline numbers as flat top-level scalars (the full records follow in "others")
+        for r in others:
+            w = r.get("workload")
+            if w and "value" in r:
+                line["%s_%s" % (w, "gparticles_per_s" if w == "nbody" else "glups")] = r["value"]
+                if "roofline" in r:
+                    line["%s_roofline_frac" % w] = r["roofline"].get("frac")
+                if "e2e" in r:
+                    line["%s_e2e" % w] = r["e2e"].get("value")
         if others:
             line["others"] = others
         line["wall_s"] = time.perf_counter() - t_start

@@ -178,8 +178,14 @@ class DeviceBlock:
             "shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2, "strides": None}
 
     def as_tensor(self):
+        """zero-copy view on the device the block lives on (NOT torch's current device: torch would copy the block
+        there and NCCL would send and receive on the copy)"""
         import torch
-        return torch.as_tensor(self, device="cuda")
+        dev = getattr(self.owner, "device", None)
+        t = torch.as_tensor(self, device=torch.device("cuda", int(dev)) if dev is not None else "cuda")
+        if t.data_ptr() != self.ptr:
+            raise LogicError("torch copied the halo block instead of viewing it (device mismatch)")
+        return t
 
 
 class DeviceGrid:

@@ -357,18 +357,23 @@ int b200geo_group_step(b200geo_group *grp, int kernel, const void *params, uint3
             B200GEO_CUDA(cudaSetDevice(grp->g[0]->device));
             return b200geo_step(grp->g[0], kernel, params, first_nano_step + done, left, grp->compute[0]);
         }
-        if (grp->valid == 0) {
+        if (grp->valid == 0 || (overlap && grp->valid < w)) {
             // first exchange (or after an invalidate): whole cells, so that members the update never
-            // re-reads from a neighbour (wall states, ...) are in place as well
+            // re-reads from a neighbour (wall states, ...) are in place as well. Leftover validity from an
+            // earlier call (0 < valid < w) is topped up the same way, so that every round below is a fused,
+            // overlapped one (StripingSimulator::nanoStep, parallelization/stripingsimulator.h:269-286)
             int rc = exchange_current(grp, 0, w);
             if (rc) return rc;
         }
-        if (overlap && grp->valid == w && left >= (uint32_t)w) {
-            const void *p = lbm_lazy ? (const void *)(done + w == n_steps ? &lbm_store : &lbm_skip) : params;
+        if (overlap) {
+            // a round of fewer than w sweeps (the tail of this call) still ships w planes: the ghost zones are
+            // w deep again afterwards and the next call starts with an overlapped round, not with an exchange
+            const uint32_t k = left < (uint32_t)w ? left : (uint32_t)w;
+            const void *p = lbm_lazy ? (const void *)(done + k == n_steps ? &lbm_store : &lbm_skip) : params;
             Updater up = {kernel, p, 0, 0};
-            int rc = overlapped_round(grp, up, first_nano_step + done, w, w);
+            int rc = overlapped_round(grp, up, first_nano_step + done, w, (int)k);
             if (rc) return rc;
-            done += w;
+            done += k;
             continue;
         }
         uint32_t k = left < (uint32_t)grp->valid ? left : (uint32_t)grp->valid;

@@ -52,6 +52,16 @@ class CellModel:
         return None
 
     @property
+    def invariant_members(self):
+        """members (indices) the kernel family never rewrites: every sweep reads them from whichever buffer is
+        current, so an upload has to put them into BOTH buffers (SerialSimulator initialises both grids,
+        parallelization/serialsimulator.h:54-57). LBM: csrc/lbm.cu leaves `state` and the wall cells' density /
+        velocity alone."""
+        if self.kernel == capi.KERNEL_LBM_D3Q19:
+            return [self.member_index(n) for n in ("density", "velocityX", "velocityY", "velocityZ", "state")]
+        return []
+
+    @property
     def member_bytes(self):
         return [t.itemsize for _, t in self.members]
 

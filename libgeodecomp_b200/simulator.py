@@ -278,7 +278,8 @@ class GridWindow:
     inside boundingBox()' (io/initializer.h:38-71), ParallelWriter::stepFinished gets a validRegion
     (io/parallelwriter.h:92-99). Transfers are enqueued on `stream` and touch ONE buffer (the grid's current one at
     the time of the call) — the building block of StripedSimulator's streamed run, where host<->device copies of
-    one part of the space overlap the sweeps over another."""
+    one part of the space overlap the sweeps over another. Members the kernel never rewrites
+    (model.invariant_members, e.g. the LBM cell's `state`) go into BOTH buffers, device to device."""
 
     def __init__(self, grid, z0, z1, stream=None):
         self.grid, self.model, self.stream = grid, grid.model, stream
@@ -320,7 +321,8 @@ class GridWindow:
             array = np.ascontiguousarray(array, dtype=t)
         origin, dims = self._inside(origin, tuple(array.shape)[::-1])
         o, d = self.grid._box(origin, dims)
-        self.grid.dev.load_member(m, array, o, d, location=location, both=False, stream=self.stream)
+        self.grid.dev.load_member(m, array, o, d, location=location, both=m in self.model.invariant_members,
+                                  stream=self.stream)
 
     def set_streak(self, origin, cells):
         """set(Streak, const CELL*): cells is a structured array of the model's cell dtype"""
@@ -328,7 +330,7 @@ class GridWindow:
         origin, _ = self._inside(tuple(origin), (len(cells),) + (1,) * (self.model.dim - 1))
         for m, (n, _) in enumerate(self.model.members):
             self.grid.dev.load_member(m, np.ascontiguousarray(cells[n]), self.grid._local3(origin), (len(cells), 1, 1),
-                                      both=False, stream=self.stream)
+                                      both=m in self.model.invariant_members, stream=self.stream)
 
     def set(self, coord, cell):
         one = np.zeros(1, dtype=self.model.cell_dtype)

@@ -183,10 +183,13 @@ class _CudaStreams:
         stream.wait_event(event)
 
     def join(self):
-        """the caller's current stream continues after all three"""
+        """the caller's current stream continues after all three, and the HOST waits for them: the ParallelWriter
+        contract says the host buffers are complete when run() returns"""
         cur = self.torch.cuda.current_stream(self.device)
         for st in (self.up, self.run, self.down):
             cur.wait_event(self.record(st))
+        for st in (self.up, self.run, self.down):
+            st.synchronize()
 
 
 class _NoStreams:
@@ -232,6 +235,9 @@ class StripedSimulator:
         last = model.dim - 1
         bounds = slab_bounds(gdims[last], world)
         z0, z1 = bounds[rank], bounds[rank + 1]
+        # every rank must take the same schedule (the exchanges pair up): decisions that depend on the slab thickness
+        # use the thinnest slab of the partition
+        self._thinnest = min(bounds[r + 1] - bounds[r] for r in range(world))
         if z1 - z0 < ghost_width and world > 1:
             raise ValueError("slab thinner than the ghost zone")
         periodic = model.wraps
@@ -272,10 +278,10 @@ class StripedSimulator:
     def advance(self, nano_steps):
         """nano_steps sweeps with one halo exchange per ghost_width sweeps.
 
-        Rounds of exactly ghost_width sweeps follow StripingSimulator::nanoStep's schedule
+        Rounds of up to ghost_width sweeps follow StripingSimulator::nanoStep's schedule
         (parallelization/stripingsimulator.h:269-286): update the rims, start shipping them, update
-        the interior while they travel, wait. Anything else (a shorter tail, packed multi-member
-        halos) exchanges first and steps afterwards."""
+        the interior while they travel, wait. Configurations that cannot overlap (packed multi-member
+        halos, slabs thinner than two ghost zones) exchange first and step afterwards."""
         done = 0
         w = self.ghost_width
         while done < nano_steps:
@@ -283,12 +289,18 @@ class StripedSimulator:
             if self.world == 1:
                 self.grid.dev.step(self.model.kernel, n_steps=left, params=self.model.step_params(True))
                 return
-            if self._valid == 0:
+            fused = self.overlap and self._can_overlap()
+            if self._valid == 0 or (fused and self._valid < w):
+                # the first exchange; leftover validity (0 < _valid < w) is topped up the same way, so that every
+                # round below is a fused, overlapped one
                 self.halo.exchange()
                 self._valid = w
-            if self.overlap and self._valid == w and left >= w and self._can_overlap():
-                self._overlapped_round(done + w == nano_steps)
-                done += w      # the ghosts are already valid again, w deep
+            if fused:
+                # a round of fewer than w sweeps (the tail of this call) still ships w planes: the ghost zones are
+                # w deep again afterwards and the next call starts with an overlapped round, not with an exchange
+                n = min(left, w)
+                self._overlapped_round(done + n == nano_steps, n)
+                done += n
                 continue
             n = min(left, self._valid)
             self.grid.dev.step(self.model.kernel, n_steps=n, params=self.model.step_params(done + n == nano_steps))
@@ -297,11 +309,12 @@ class StripedSimulator:
 
     def _can_overlap(self):
         w, last = self.ghost_width, self.model.dim - 1
-        if self.halo.packed or self.grid.dims[last] < 2 * w or not hasattr(self.grid.dev, "update_box"):
+        if self.halo.packed or self._thinnest < 2 * w or not hasattr(self.grid.dev, "update_box"):
             return False
         return w == 1 or (self.model.fuses_sweeps and w <= 4)
 
-    def _overlapped_round(self, final):
+    def _overlapped_round(self, final, sweeps):
+        """`sweeps` <= ghost_width sweeps fused per launch; the ghost zones are ghost_width deep again afterwards"""
         g, dev, w, last = self.grid, self.grid.dev, self.ghost_width, self.model.dim - 1
         n = g.dims[last]
         params = self.model.step_params(final)
@@ -311,7 +324,7 @@ class StripedSimulator:
                 return
             origin, dim = [0, 0, 0], list(g.dims) + [1] * (3 - len(g.dims))
             origin[last], dim[last] = a, b - a
-            dev.update_box(self.model.kernel, origin, dim, params=params, n_sweeps=w)
+            dev.update_box(self.model.kernel, origin, dim, params=params, n_sweeps=sweeps)
 
         if self.model.wraps:
             dev.refresh_ghosts()
@@ -343,8 +356,10 @@ class StripedSimulator:
         sweeps = steps * self.NANO_STEPS
         if sweeps < 1:
             return None
+        first, end = self.initializer.startStep(), self.initializer.maxSteps()
         for w in self.writers:
-            if not isinstance(w, ParallelWriter) or w.getPeriod() < steps:
+            # no WRITER_STEP_FINISHED may fall due inside the run: no step s in (first, end) with s % period == 0
+            if not isinstance(w, ParallelWriter) or first // w.getPeriod() != (end - 1) // w.getPeriod():
                 return None
         depth = self.stream_depth
         if depth is None:

@@ -44,6 +44,22 @@ def jacobi_grid(nx, ny, nz, seed=42, z0=0, nz_total=None):
     return v
 
 
+def jacobi_box(nx, ny, nz, lo, hi, seed=42, zmap=None):
+    """jacobi_grid(nx, ny, nz, seed)[lo[0]:hi[0], lo[1]:hi[1], lo[2]:hi[2]] (z, y, x) without building the whole grid —
+    the input of a windowed oracle at full size. zmap: plane indices to take instead of range(lo[0], hi[0])."""
+    zs = np.arange(lo[0], hi[0]) if zmap is None else np.asarray(zmap)
+    ys, xs = np.arange(lo[1], hi[1]), np.arange(lo[2], hi[2])
+    idx = ((zs[:, None, None].astype(np.uint64) * np.uint64(ny) + ys[None, :, None].astype(np.uint64)) * np.uint64(nx)
+           + xs[None, None, :].astype(np.uint64))
+    bits = splitmix64(idx ^ np.uint64(seed))
+    v = (bits >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0)
+    off, size = nx * 5 // 128, nx * 50 // 128
+    hot = ((zs >= off) & (zs < off + size))[:, None, None] & ((ys >= off) & (ys < off + size))[None, :, None] \
+        & ((xs >= off) & (xs < off + size))[None, None, :]
+    v[hot] = 0.99999999999
+    return v
+
+
 def gol_grid(nx, ny, seed=7, density=0.35):
     """Config 2: Bernoulli(density) soup plus the glider / Diehard / Acorn of
     src/examples/gameoflife/main.cpp:69-108."""
@@ -67,6 +83,19 @@ def lbm_states(nx, ny, nz, z0=0, nz_total=None):
     s[:, 0, :] = LBM_STATES["SOUTH_NOSLIP"]
     s[:, ny - 1, :] = LBM_STATES["NORTH_ACC"]
     zs = np.arange(z0, z0 + nz)
+    s[zs == 0] = LBM_STATES["BOTTOM"]
+    s[zs == nz_total - 1] = LBM_STATES["TOP"]
+    return s
+
+
+def lbm_states_box(nx, ny, nz_total, lo, hi):
+    """lbm_states of the global nx x ny x nz_total cavity on the box [lo, hi) (z, y, x)"""
+    zs, ys, xs = (np.arange(lo[i], hi[i]) for i in range(3))
+    s = np.zeros((len(zs), len(ys), len(xs)), dtype=np.int32)
+    s[:, :, xs == 0] = LBM_STATES["WEST_NOSLIP"]
+    s[:, :, xs == nx - 1] = LBM_STATES["EAST_NOSLIP"]
+    s[:, ys == 0, :] = LBM_STATES["SOUTH_NOSLIP"]
+    s[:, ys == ny - 1, :] = LBM_STATES["NORTH_ACC"]
     s[zs == 0] = LBM_STATES["BOTTOM"]
     s[zs == nz_total - 1] = LBM_STATES["TOP"]
     return s

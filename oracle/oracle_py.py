@@ -146,9 +146,10 @@ def have_ref(model):
     return os.access(ref_binary(model), os.X_OK)
 
 
-def run_ref(model, raw_in, dims, steps, omp=False, edge=None, threads=None, want_output=True):
+def run_ref(model, raw_in, dims, steps, omp=False, edge=None, threads=None, want_output=True, tile=0):
     """Run the reference's own SerialSimulator/OpenMPSimulator on raw_in (any numpy array whose
-    bytes are the member-major grid); returns (raw_out_bytes as uint8 array, stats dict)."""
+    bytes are the member-major grid); returns (raw_out_bytes as uint8 array, stats dict).
+    tile > 0: raw_in holds only `tile` planes (nx x ny x tile) and is repeated along z."""
     nx, ny, nz = dims
     env = dict(os.environ)
     if omp:
@@ -165,6 +166,8 @@ def run_ref(model, raw_in, dims, steps, omp=False, edge=None, threads=None, want
             cmd.append("--omp")
         if edge is not None:
             cmd += ["--edge", repr(float(edge))]
+        if tile:
+            cmd += ["--tile", str(int(tile))]
         res = subprocess.run(cmd, env=env, check=True, capture_output=True, text=True)
         stats = json.loads(res.stdout.strip().splitlines()[-1])
         out = np.fromfile(fout, dtype=np.uint8) if want_output else None

@@ -5,7 +5,8 @@
  * secondary comparator): what a user gets today by recompiling LibGeoDecomp, and what the hand-written kernels
  * of libb200geo.so are measured against. Nothing in the product links or calls this.
  *
- * usage: lgd_ref_cuda_jacobi [n = 512] [steps = 50]     prints one JSON line per cell type (LBM: at most 256^3) */
+ * usage: lgd_ref_cuda_jacobi [n = 512] [steps = 50] [which = all | 7 | 27 | lbm]
+ *        prints one JSON line per cell type (LBM: at most 256^3) */
 #include <cuda.h>
 
 #include <libgeodecomp/io/simpleinitializer.h>
@@ -13,6 +14,7 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <string>
 
 #include "models/lbm_aos.h"
 
@@ -150,8 +152,10 @@ int main(int argc, char **argv)
 {
     int n = argc > 1 ? std::atoi(argv[1]) : 512;
     int steps = argc > 2 ? std::atoi(argv[2]) : 50;
-    bench<RefJacobi7>("Jacobi 7-point f64 (AoS, FixedCoord)", n, steps);
-    bench<RefJacobi27>("Jacobi 27-point f64 (AoS, FixedCoord)", n, steps);
-    bench<LBMCellAoS>("LBM D3Q19 f32 cavity (AoS cell of 96 bytes, FixedCoord)", n > 256 ? 256 : n, steps < 20 ? steps : 20, 152);
+    std::string which = argc > 3 ? argv[3] : "all";
+    if (which == "all" || which == "7") bench<RefJacobi7>("Jacobi 7-point f64 (AoS, FixedCoord)", n, steps);
+    if (which == "all" || which == "27") bench<RefJacobi27>("Jacobi 27-point f64 (AoS, FixedCoord)", n, steps);
+    if (which == "all" || which == "lbm")
+        bench<LBMCellAoS>("LBM D3Q19 f32 cavity (AoS cell of 96 bytes, FixedCoord)", n > 256 ? 256 : n, steps < 20 ? steps : 20, 152);
     return 0;
 }

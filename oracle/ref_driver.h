@@ -8,7 +8,9 @@
  * storage/soagrid.h:523-576): for every member in registration order one dense array
  * [nz][ny][nx] (x fastest) of that member's type, little endian, no padding.
  *
- * usage: lgd_ref_<family> <model> <nx> <ny> <nz> <steps> <in.raw> <out.raw> [--omp] [--edge <v>]
+ * usage: lgd_ref_<family> <model> <nx> <ny> <nz> <steps> <in.raw> <out.raw> [--omp] [--edge <v>] [--tile <t>]
+ * --tile t: in.raw holds only t planes (nx x ny x t, member-major) and is repeated along z — how bench.py's synthetic
+ * Jacobi input is built — so that a full-size run (1024^3) needs no full-size file; out.raw "-" = no output pass.
  * prints one JSON line with the reference's own TimeCompute interval (misc/chronometer.h).
  */
 #ifndef B200GEO_ORACLE_REF_DRIVER_H
@@ -57,8 +59,8 @@ public:
     typedef typename SimpleInitializer<CELL>::Topology Topology;
     static const int DIM = Topology::DIM;
 
-    RawInitializer(const Coord<DIM>& dim, unsigned steps, const std::vector<char> *raw, bool haveEdge, double edge) :
-        SimpleInitializer<CELL>(dim, steps), raw(raw), haveEdge(haveEdge), edge(edge)
+    RawInitializer(const Coord<DIM>& dim, unsigned steps, const std::vector<char> *raw, bool haveEdge, double edge, int tile = 0) :
+        SimpleInitializer<CELL>(dim, steps), raw(raw), haveEdge(haveEdge), edge(edge), tile(tile)
     {}
 
     virtual void grid(GridBase<CELL, DIM> *ret)
@@ -70,6 +72,10 @@ public:
         }
         std::size_t cells = (std::size_t)dim.prod();
         int nx = dim.x();
+        if (tile > 0) {
+            // the file holds `tile` planes, repeated along z
+            cells = (std::size_t)nx * Dims<DIM>::ny(dim) * tile;
+        }
         std::vector<CELL> row(nx);
         for (int z = 0; z < Dims<DIM>::nz(dim); ++z) {
             for (int y = 0; y < Dims<DIM>::ny(dim); ++y) {
@@ -77,7 +83,7 @@ public:
                 if (!box.inBounds(origin)) {
                     continue;
                 }
-                std::size_t base = ((std::size_t)z * Dims<DIM>::ny(dim) + y) * nx;
+                std::size_t base = ((std::size_t)(tile > 0 ? z % tile : z) * Dims<DIM>::ny(dim) + y) * nx;
                 for (int x = 0; x < nx; ++x) {
                     Codec<CELL>::fromRaw(&row[x], raw->data(), cells, base + x);
                 }
@@ -90,6 +96,7 @@ private:
     const std::vector<char> *raw;
     bool haveEdge;
     double edge;
+    int tile;
 };
 
 inline std::vector<char> readFile(const char *name)
@@ -107,7 +114,7 @@ inline std::vector<char> readFile(const char *name)
 
 template<typename CELL, typename SIM>
 int runSim(const char *model, int nx, int ny, int nz, unsigned steps, const char *in, const char *out,
-           bool haveEdge, double edge, const char *simName, int threads)
+           bool haveEdge, double edge, const char *simName, int threads, int tile = 0)
 {
     typedef typename APITraits::SelectTopology<CELL>::Value Topology;
     const int DIM = Topology::DIM;
@@ -115,12 +122,13 @@ int runSim(const char *model, int nx, int ny, int nz, unsigned steps, const char
     std::size_t cells = (std::size_t)dim.prod();
 
     std::vector<char> raw = readFile(in);
-    if (raw.size() != cells * Codec<CELL>::BYTES) {
-        fprintf(stderr, "input size %zu != %zu cells x %d bytes\n", raw.size(), cells, (int)Codec<CELL>::BYTES);
+    std::size_t fileCells = tile > 0 ? (std::size_t)nx * ny * tile : cells;
+    if (raw.size() != fileCells * Codec<CELL>::BYTES) {
+        fprintf(stderr, "input size %zu != %zu cells x %d bytes\n", raw.size(), fileCells, (int)Codec<CELL>::BYTES);
         return 2;
     }
 
-    SIM sim(new RawInitializer<CELL>(dim, steps, &raw, haveEdge, edge));
+    SIM sim(new RawInitializer<CELL>(dim, steps, &raw, haveEdge, edge, tile));
     auto t0 = std::chrono::steady_clock::now();
     sim.run();
     auto t1 = std::chrono::steady_clock::now();
@@ -128,9 +136,10 @@ int runSim(const char *model, int nx, int ny, int nz, unsigned steps, const char
     double compute = sim.gatherStatistics()[0].template interval<TimeCompute>();
 
     const GridBase<CELL, DIM> *grid = sim.getGrid();
-    std::vector<char> res(raw.size());
+    const bool wantOutput = strcmp(out, "-") != 0;
+    std::vector<char> res(wantOutput ? cells * Codec<CELL>::BYTES : 0);
     std::vector<CELL> row(nx);
-    for (int z = 0; z < Dims<DIM>::nz(dim); ++z) {
+    for (int z = 0; wantOutput && z < Dims<DIM>::nz(dim); ++z) {
         for (int y = 0; y < Dims<DIM>::ny(dim); ++y) {
             grid->get(Streak<DIM>(Dims<DIM>::rowOrigin(y, z), nx), row.data());
             std::size_t base = ((std::size_t)z * Dims<DIM>::ny(dim) + y) * nx;
@@ -139,7 +148,7 @@ int runSim(const char *model, int nx, int ny, int nz, unsigned steps, const char
             }
         }
     }
-    if (strcmp(out, "-") != 0) {
+    if (wantOutput) {
         FILE *f = fopen(out, "wb");
         if (!f || fwrite(res.data(), 1, res.size(), f) != res.size()) {
             fprintf(stderr, "cannot write %s\n", out);
@@ -168,14 +177,16 @@ int runModel(const char *model, int argc, char **argv)
     unsigned steps = (unsigned)atoi(argv[5]);
     bool omp = false, haveEdge = false;
     double edge = 0;
+    int tile = 0;
     for (int i = 8; i < argc; ++i) {
         if (!strcmp(argv[i], "--omp")) omp = true;
+        if (!strcmp(argv[i], "--tile") && i + 1 < argc) tile = atoi(argv[++i]);
         if (!strcmp(argv[i], "--edge") && i + 1 < argc) { haveEdge = true; edge = atof(argv[++i]); }
     }
 #ifdef _OPENMP
     if (omp) {
         return runSim<CELL, OpenMPSimulator<CELL> >(model, nx, ny, nz, steps, argv[6], argv[7], haveEdge, edge,
-                                                    "OpenMPSimulator", omp_get_max_threads());
+                                                    "OpenMPSimulator", omp_get_max_threads(), tile);
     }
 #else
     if (omp) {
@@ -184,7 +195,7 @@ int runModel(const char *model, int argc, char **argv)
     }
 #endif
     return runSim<CELL, SerialSimulator<CELL> >(model, nx, ny, nz, steps, argv[6], argv[7], haveEdge, edge,
-                                                "SerialSimulator", 1);
+                                                "SerialSimulator", 1, tile);
 }
 
 template<typename T>

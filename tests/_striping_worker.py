@@ -120,6 +120,31 @@ def main():
     if pull.calls != want_calls or not np.array_equal(pull.out, oracle_py.jacobi(7, False, data, steps, edge=0.75)[b[rank]:b[rank + 1]]):
         failures.append("parallel writer rank %d: %r" % (rank, pull.calls))
 
+    # advance() calls that are not multiples of the ghost width (a writer period of 5 with ghost width 2; bench.py's
+    # --warmup 5): every round stays a fused, overlapped one — no blocking exchange after the very first, no
+    # single-sweep launches except the one-sweep tail of a call (round 1's SCALE run lost 10 points to this)
+    nz, ny, nx = 24, 5, 6
+    data = synth.jacobi_grid(nx, ny, nz, seed=11)
+    sim = StripedSimulator(SlabInit(data, 25, 0.75), models.ALL["Jacobi27Cube"], rank=rank, world=world, ghost_width=2,
+                           dist=dist, engine=cpu_engine)
+    log = []
+    dev = sim.grid.dev
+    real_box, real_step, real_exchange = dev.update_box, dev.step, sim.halo.exchange
+    dev.update_box = lambda *a, **kw: (log.append(("box", kw.get("n_sweeps", 1))), real_box(*a, **kw))[1]
+    dev.step = lambda *a, **kw: (log.append(("step", kw.get("n_steps", 1))), real_step(*a, **kw))[1]
+    sim.halo.exchange = lambda: (log.append(("exchange", 0)), real_exchange())[1]
+    sim.advance(5)
+    warm = list(log)
+    del log[:]
+    sim.advance(20)
+    if [e for e in warm if e[0] != "box"] != [("exchange", 0)] or sorted(set(n for _, n in warm if _ == "box")) != [1, 2]:
+        failures.append("misaligned advance, warm-up schedule: %r" % (warm,))
+    if any(e != ("box", 2) for e in log) or len(log) != 10 * (3 if 0 < rank < world - 1 else 2):
+        failures.append("misaligned advance, timed schedule: %r" % (log,))
+    b = slab_bounds(nz, world)
+    if not np.array_equal(sim.getGrid().saveMember("temp"), oracle_py.jacobi(27, False, data, 25, edge=0.75)[b[rank]:b[rank + 1]]):
+        failures.append("misaligned advance: result rank %d" % rank)
+
     # n-body: slabs of BoxCell containers, one ghost plane of containers (counts + particles) per side and sweep;
     # velocities large enough that particles change containers and slabs
     class CellInit(SimpleInitializer):

@@ -5,6 +5,7 @@ that has /root/reference (tests/facade/Makefile, also run by __graft_entry__.bui
 import os
 import subprocess
 
+import numpy as np
 import pytest
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -52,7 +53,61 @@ def test_cpp_striping_simulator_drop_in():
     assert "all checks passed" in res.stdout
 
 
+GENERIC_SOA_BIN = os.path.join(HERE, "facade", "_bin", "generic_soa_test")
+
+
+@pytest.mark.gpu
+def test_generic_device_path_for_unbound_soa_cells():
+    """tests/facade/generic_soa_test.cu: Struct-of-Arrays user cells without a kernel binding, their SoA-signature
+    updateLineX() compiled by nvcc with LibFlatArray's generated accessors, bit-identical to SerialSimulator on one
+    device and on slab groups."""
+    if not os.access(GENERIC_SOA_BIN, os.X_OK):
+        pytest.skip("tests/facade/_bin/generic_soa_test not built (needs /root/reference at build time)")
+    res = subprocess.run([GENERIC_SOA_BIN], capture_output=True, text=True, timeout=600)
+    print(res.stdout[-4000:], res.stderr[-2000:])
+    assert res.returncode == 0, res.stdout[-4000:] + res.stderr[-2000:]
+    assert "all checks passed" in res.stdout
+
+
+@pytest.mark.gpu
+def test_uniform_element_layout_round_trip():
+    """b200geo_grid_create_uniform: members of different widths share one element index; member I/O, region I/O,
+    the edge ring and the periodic images behave as in the default layout."""
+    from libgeodecomp_b200 import capi
+    dim, widths = (37, 9, 5), [8, 4, 4, 1, 2]
+    wrap = [[capi.GHOST_WRAP] * 2, [capi.GHOST_EDGE] * 2, [capi.GHOST_WRAP] * 2]
+    grids = [capi.DeviceGrid(dim, widths, ghost=(1, 1, 1), ghost_mode=wrap, member_stride=s) for s in (None, 0, 65536)]
+    assert grids[1].member_stride % 256 == 0 and grids[2].member_stride == 65536
+    rng = np.random.default_rng(5)
+    dtypes = {8: np.float64, 4: np.uint32, 2: np.uint16, 1: np.uint8}
+    edge = bytes(rng.integers(0, 255, sum(widths), dtype=np.uint8))
+    for g in grids:
+        g.set_edge(edge)
+    data = []
+    for m, w in enumerate(widths):
+        a = rng.integers(0, 200, dim[::-1]).astype(dtypes[w])
+        data.append(a)
+        for g in grids:
+            g.load_member(m, a)
+    for g in grids:
+        g.refresh_ghosts()
+    # the whole padded box (ghost ring included) must agree with the default layout, member by member
+    padded = tuple(d + 2 for d in dim)
+
+    def pull(g, m, w):
+        out = np.zeros(padded[::-1], dtype=dtypes[w])
+        g.save_member(m, out, origin=(-1, -1, -1), dim=padded)
+        capi.sync()
+        return out
+
+    for m, w in enumerate(widths):
+        want = pull(grids[0], m, w)
+        for g in grids[1:]:
+            assert np.array_equal(pull(g, m, w), want), "member %d differs in the uniform layout" % m
+        assert np.array_equal(want[1:-1, 1:-1, 1:-1], data[m])
+
+
 def test_facade_header_has_no_oracle_dependency():
-    for name in ("b200simulator.h", "b200generic.h", "b200boxgrid.h", "b200stripingsimulator.h"):
+    for name in ("b200simulator.h", "b200generic.h", "b200genericsoa.h", "b200boxgrid.h", "b200stripingsimulator.h"):
         text = open(os.path.join(HERE, "..", "include", "libgeodecomp_b200", name)).read()
         assert "oracle" not in text

@@ -1,76 +1,17 @@
-"""GPU tests of code that was written AFTER the round's GPU budget was spent: compiled for sm_100a and covered on the
-CPU as far as that goes (tests/test_facade_cpu.py runs the generic SoA path's host side and address arithmetic against
-the reference on the mock engine), but not yet run on a B200. They are skipped unless B200GEO_RUN_UNVERIFIED=1, so the
-driver's round-end GPU suite reports what has been measured; the first GPU job of the next round runs them
-(tools/gpu_unverified.sh) and moves them next to their siblings in tests/test_facade_gpu.py / test_parity_gpu.py."""
+"""The streamed run of StripedSimulator (striping.py::_run_streamed) on the real engine: pinned host arrays in and out,
+three CUDA streams, time-skewed b200geo_update_box_n launches, bit-identical to the oracle. The CPU twin (same schedule on
+the numpy engine) is tests/test_streamed_run_cpu.py. The tests read the host buffers right after run() returns, with no
+synchronisation of their own: ParallelWriter reads through a GridWindow are stream ordered and the contract
+(simulator.py::ParallelWriter) says they are complete when run() returns."""
 import os
-import subprocess
 
 import numpy as np
 import pytest
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-unverified = pytest.mark.skipif(os.environ.get("B200GEO_RUN_UNVERIFIED") != "1",
-                                reason="not yet run on a GPU (round-1 GPU budget exhausted); set B200GEO_RUN_UNVERIFIED=1")
-
-GENERIC_SOA_BIN = os.path.join(HERE, "facade", "_bin", "generic_soa_test")
 
 
 @pytest.mark.gpu
-@unverified
-def test_generic_device_path_for_unbound_soa_cells():
-    """tests/facade/generic_soa_test.cu: Struct-of-Arrays user cells without a kernel binding, their SoA-signature
-    updateLineX() compiled by nvcc with LibFlatArray's generated accessors, bit-identical to SerialSimulator on one
-    device and on slab groups."""
-    if not os.access(GENERIC_SOA_BIN, os.X_OK):
-        pytest.skip("tests/facade/_bin/generic_soa_test not built (needs /root/reference at build time)")
-    res = subprocess.run([GENERIC_SOA_BIN], capture_output=True, text=True, timeout=600)
-    print(res.stdout[-4000:], res.stderr[-2000:])
-    assert res.returncode == 0, res.stdout[-4000:] + res.stderr[-2000:]
-    assert "all checks passed" in res.stdout
-
-
-@pytest.mark.gpu
-@unverified
-def test_uniform_element_layout_round_trip():
-    """b200geo_grid_create_uniform: members of different widths share one element index; member I/O, region I/O,
-    the edge ring and the periodic images behave as in the default layout."""
-    from libgeodecomp_b200 import capi
-    dim, widths = (37, 9, 5), [8, 4, 4, 1, 2]
-    wrap = [[capi.GHOST_WRAP] * 2, [capi.GHOST_EDGE] * 2, [capi.GHOST_WRAP] * 2]
-    grids = [capi.DeviceGrid(dim, widths, ghost=(1, 1, 1), ghost_mode=wrap, member_stride=s) for s in (None, 0, 65536)]
-    assert grids[1].member_stride % 256 == 0 and grids[2].member_stride == 65536
-    rng = np.random.default_rng(5)
-    dtypes = {8: np.float64, 4: np.uint32, 2: np.uint16, 1: np.uint8}
-    edge = bytes(rng.integers(0, 255, sum(widths), dtype=np.uint8))
-    for g in grids:
-        g.set_edge(edge)
-    data = []
-    for m, w in enumerate(widths):
-        a = rng.integers(0, 200, dim[::-1]).astype(dtypes[w])
-        data.append(a)
-        for g in grids:
-            g.load_member(m, a)
-    for g in grids:
-        g.refresh_ghosts()
-    # the whole padded box (ghost ring included) must agree with the default layout, member by member
-    padded = tuple(d + 2 for d in dim)
-
-    def pull(g, m, w):
-        out = np.zeros(padded[::-1], dtype=dtypes[w])
-        g.save_member(m, out, origin=(-1, -1, -1), dim=padded)
-        capi.sync()
-        return out
-
-    for m, w in enumerate(widths):
-        want = pull(grids[0], m, w)
-        for g in grids[1:]:
-            assert np.array_equal(pull(g, m, w), want), "member %d differs in the uniform layout" % m
-        assert np.array_equal(want[1:-1, 1:-1, 1:-1], data[m])
-
-
-@pytest.mark.gpu
-@unverified
 @pytest.mark.parametrize("kind,depth,steps,shape,chunks", [
     (27, 2, 8, (160, 96, 128), 5), (27, 2, 7, (96, 40, 70), 4), (7, 4, 12, (128, 64, 96), 4), (7, 1, 5, (64, 33, 50), 8),
     (6, 3, 10, (90, 32, 64), 6)])
@@ -96,16 +37,13 @@ def test_streamed_run_on_the_device(kind, depth, steps, shape, chunks):
         sim = StripedSimulator(Init((nx, ny, nz), steps), models.ALL["Jacobi%dCube" % kind], stream_io=stream_io,
                                stream_depth=depth, stream_chunks=chunks)
         sim.writers = [PullWriter("", 1 << 30)]
-        sim.run()
-        capi.sync()
-        torch.cuda.synchronize()
+        sim.run()     # no synchronisation here: the host buffers must be complete when run() returns
         assert sim.streamed_runs == (1 if stream_io else 0)
         assert np.array_equal(host["temp"], want), "stream_io=%s" % stream_io
         assert np.array_equal(sim.getGrid().saveMember("temp"), want)
 
 
 @pytest.mark.gpu
-@unverified
 def test_streamed_lbm_and_gol_on_the_device():
     """kernel families that take one sweep per launch (b200geo_update_box): LBM D3Q19 (24 members, macroscopics stored
     on the last level only) and the byte Game of Life kernel (2-D: chunks of rows), streamed vs the oracle."""
@@ -135,9 +73,7 @@ def test_streamed_lbm_and_gol_on_the_device():
 
     sim = StripedSimulator(LBMInit((nx, ny, nz), steps), models.LBMCellF, stream_io=True, stream_chunks=4)
     sim.addWriter(LBMPull("", steps))
-    sim.run()
-    capi.sync()
-    torch.cuda.synchronize()
+    sim.run()     # no synchronisation here: the host buffers must be complete when run() returns
     assert sim.streamed_runs == 1
     assert np.array_equal(host.view(np.uint32), oracle_py.lbm(raw, steps).view(np.uint32))
 
@@ -160,8 +96,6 @@ def test_streamed_lbm_and_gol_on_the_device():
 
     sim = StripedSimulator(GolInit((gx, gy), gsteps), models.ALL["ConwayCube"], stream_io=True, stream_chunks=8)
     sim.addWriter(GolPull("", gsteps))
-    sim.run()
-    capi.sync()
-    torch.cuda.synchronize()
+    sim.run()     # no synchronisation here: the host buffers must be complete when run() returns
     assert sim.streamed_runs == 1
     assert np.array_equal(ghost, oracle_py.gol(False, gol, gsteps))

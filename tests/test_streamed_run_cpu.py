@@ -114,6 +114,59 @@ def test_streamed_lbm_equals_the_oracle():
     assert np.array_equal(out.view(np.uint32), want.view(np.uint32))
 
 
+def test_streamed_lbm_with_walls_that_changed_after_construction():
+    """The LBM kernel never rewrites `state` (nor the walls' density / velocity): a streamed upload has to put them into
+    BOTH buffers, or odd levels read what the constructor-time Initializer::grid call left there."""
+    nx, ny, nz, steps = 8, 7, 24, 5
+    raw = synth.lbm_grid(nx, ny, nz, noise=0.01)
+    src = raw.copy()
+    state = models.LBMCellF.member_index("state")
+    src[state] = 0                       # at construction: no walls at all
+
+    class LBMInit(SimpleInitializer):
+        def grid(self, target):
+            (ox, oy, oz), (dx, dy, dz) = target.boundingBox()
+            for m, (name, t) in enumerate(models.LBMCellF.members):
+                target.loadMember(name, src[m, oz:oz + dz, oy:oy + dy, ox:ox + dx].view(t), origin=(ox, oy, oz))
+
+    out = np.zeros_like(raw)
+
+    class LBMPull(ParallelWriter):
+        def stepFinishedRegion(self, grid, validRegion, globalDimensions, step, event, rank, lastCall):
+            (ox, oy, oz), (dx, dy, dz) = validRegion
+            if event == 2:
+                for m, (name, t) in enumerate(models.LBMCellF.members):
+                    grid.saveMember(name, origin=(ox, oy, oz), dims=(dx, dy, dz), out=out[m, oz:oz + dz].view(t))
+
+    sim = StripedSimulator(LBMInit((nx, ny, nz), steps), models.LBMCellF, engine=cpu_engine, stream_io=True, stream_chunks=4)
+    sim.addWriter(LBMPull("", steps))
+    src[...] = raw                       # the cavity's walls appear before run()
+    sim.run()
+    assert sim.streamed_runs == 1
+    assert np.array_equal(out.view(np.uint32), oracle_py.lbm(raw, steps).view(np.uint32))
+
+
+def test_a_writer_period_that_falls_due_inside_the_run_is_not_streamed():
+    """startStep 5, maxSteps 12, period 10: step 10 is due mid-run (the plain schedule fires WRITER_STEP_FINISHED there)"""
+    nz, ny, nx = 24, 5, 6
+    data = synth.jacobi_grid(nx, ny, nz)
+
+    class Late(BoxInit):
+        def startStep(self):
+            return 5
+
+        def maxSteps(self):
+            return 12
+
+    for period, streams in ((10, False), (12, True), (13, True), (7, False), (6, False)):
+        sim = StripedSimulator(Late(data, 12, 0.75), models.ALL["Jacobi7Cube"], engine=cpu_engine, stream_io=True, stream_chunks=4)
+        pull = Pull((nz, ny, nx), period)
+        sim.addWriter(pull)
+        sim.run()
+        assert sim.streamed_runs == (1 if streams else 0), period
+        assert np.array_equal(pull.out, oracle_py.jacobi(7, False, data, 7, edge=0.75)), period
+
+
 def test_run_falls_back_to_the_plain_schedule_when_it_cannot_stream():
     nz, ny, nx, steps = 24, 5, 6, 4
     data = synth.jacobi_grid(nx, ny, nz)
