@@ -636,6 +636,7 @@ def gpu_reference(workload, args, torch):
         return {"error": "lgd_ref_cuda_jacobi exited with %d" % res.returncode}
     ref = json.loads(lines[-1])
     model = models.ALL[WORKLOADS[workload][0]]
+    capi.set_tuning("jacobi.tb", TB_DEPTH.get(workload, 0))   # the secondary workloads set their own depth
     grid = B200Grid(model, (n, n, n))
     grid.loadMember("temp", torch.rand((n, n, n), dtype=torch.float64, device="cuda"), location=capi.CUDA_DEVICE)
     grid.dev.step(model.kernel, n_steps=4)

@@ -121,6 +121,56 @@ inline void toStreak4(const Streak<DIM>& s, const Coord<DIM>& origin, int32_t *o
     out[3] = s.endX - origin[0];
 }
 
+
+/* A run of streaks that tile a box: rows of equal extent in x at consecutive y, planes of equal extent in
+ * (x, y) at consecutive z. A dense [z][y][x] array of the box IS the concatenation of its streaks, so Selector
+ * I/O and region I/O over such a run is ONE strided copy (b200geo_grid_save_member / _load_member) instead of
+ * one call per streak. Box-shaped regions — a Writer's whole grid, a slab, a ghost zone face — collapse to a
+ * single box (geometry/region.h:582 keeps them as run-length streaks; SURVEY App. B asks for this fast path). */
+struct StreakBox {
+    int32_t origin[3];   /* relative to the grid's origin */
+    int32_t dim[3];
+    std::size_t cells() const { return (std::size_t)dim[0] * dim[1] * dim[2]; }
+};
+
+template<int DIM, typename ITERATOR>
+inline std::vector<StreakBox> mergeStreaks(ITERATOR begin, const ITERATOR& end, const Coord<DIM>& gridOrigin)
+{
+    std::vector<StreakBox> boxes;
+    /* rows -> slabs of rows (same x extent, consecutive y, one plane) */
+    for (ITERATOR i = begin; i != end; ++i) {
+        int32_t s[4];
+        toStreak4(*i, gridOrigin, s);
+        if (s[3] <= s[0]) {
+            continue;
+        }
+        if (!boxes.empty()) {
+            StreakBox& b = boxes.back();
+            if (b.dim[2] == 1 && b.origin[0] == s[0] && b.dim[0] == s[3] - s[0] && b.origin[2] == s[2] && b.origin[1] + b.dim[1] == s[1]) {
+                ++b.dim[1];
+                continue;
+            }
+        }
+        StreakBox b = {{s[0], s[1], s[2]}, {s[3] - s[0], 1, 1}};
+        boxes.push_back(b);
+    }
+    /* slabs of rows -> boxes (same x and y extent, consecutive z) */
+    std::size_t out = 0;
+    for (std::size_t k = 0; k < boxes.size(); ++k) {
+        if (out > 0) {
+            StreakBox& b = boxes[out - 1];
+            const StreakBox& n = boxes[k];
+            if (b.origin[0] == n.origin[0] && b.dim[0] == n.dim[0] && b.origin[1] == n.origin[1] && b.dim[1] == n.dim[1] &&
+                b.origin[2] + b.dim[2] == n.origin[2] && n.dim[2] == 1) {
+                ++b.dim[2];
+                continue;
+            }
+        }
+        boxes[out++] = boxes[k];
+    }
+    boxes.resize(out);
+    return boxes;
+}
 }
 
 }
@@ -433,6 +483,12 @@ public:
         return cellBytes;
     }
 
+    /* strided member copies issued by saveMember / loadMember so far (one per box of the region) */
+    std::size_t memberCopyCalls() const
+    {
+        return memberCalls;
+    }
+
     /* Selector I/O for a streak list (what GridBase::saveMember / loadMember end up calling) */
     void saveMemberStreaks(
         char *target,
@@ -464,22 +520,27 @@ protected:
     {
         flush();
         int m = findMember(selector);
+        if (m >= 0) {
+            /* a plain member selector: one strided copy per BOX of the streak list, device to device for
+             * MemoryLocation::CUDA_DEVICE (storage/gridbase.h:217-261) */
+            const int loc = targetLocation == MemoryLocation::HOST ? B200GEO_HOST : B200GEO_CUDA_DEVICE;
+            std::vector<B200Helpers::StreakBox> boxes = B200Helpers::mergeStreaks<DIM>(begin, end, box.origin);
+            for (std::size_t k = 0; k < boxes.size(); ++k) {
+                B200Helpers::check(b200geo_grid_save_member(handle, m, boxes[k].origin, boxes[k].dim, target, loc, 0));
+                target += selector.sizeOfExternal() * boxes[k].cells();
+            }
+            memberCalls += boxes.size();
+            sync();
+            return;
+        }
         for (typename Region<DIM>::StreakIterator i = begin; i != end; ++i) {
             int n = i->length();
-            if (m >= 0) {
-                int32_t s[4], o[3], d[3] = {n, 1, 1};
-                B200Helpers::toStreak4(*i, box.origin, s);
-                o[0] = s[0]; o[1] = s[1]; o[2] = s[2];
-                int loc = targetLocation == MemoryLocation::HOST ? B200GEO_HOST : B200GEO_CUDA_DEVICE;
-                B200Helpers::check(b200geo_grid_save_member(handle, m, o, d, target, loc, 0));
-            } else {
-                if (targetLocation != MemoryLocation::HOST) {
-                    throw std::logic_error("B200Grid: filtered selectors are only supported for host targets");
-                }
-                std::vector<CELL> cells(n);
-                get(*i, cells.data());
-                selector.copyMemberOut(cells.data(), MemoryLocation::HOST, target, MemoryLocation::HOST, n);
+            if (targetLocation != MemoryLocation::HOST) {
+                throw std::logic_error("B200Grid: filtered selectors are only supported for host targets");
             }
+            std::vector<CELL> cells(n);
+            get(*i, cells.data());
+            selector.copyMemberOut(cells.data(), MemoryLocation::HOST, target, MemoryLocation::HOST, n);
             target += selector.sizeOfExternal() * n;
         }
         sync();
@@ -495,23 +556,26 @@ protected:
         flush();
         rowCacheValid = false;
         int m = findMember(selector);
+        if (m >= 0) {
+            const int loc = sourceLocation == MemoryLocation::HOST ? B200GEO_HOST : B200GEO_CUDA_DEVICE;
+            std::vector<B200Helpers::StreakBox> boxes = B200Helpers::mergeStreaks<DIM>(begin, end, box.origin);
+            for (std::size_t k = 0; k < boxes.size(); ++k) {
+                B200Helpers::check(b200geo_grid_load_member(handle, m, boxes[k].origin, boxes[k].dim, source, loc, 1, 0));
+                source += selector.sizeOfExternal() * boxes[k].cells();
+            }
+            memberCalls += boxes.size();
+            sync();
+            return;
+        }
         for (typename Region<DIM>::StreakIterator i = begin; i != end; ++i) {
             int n = i->length();
-            if (m >= 0) {
-                int32_t s[4], o[3], d[3] = {n, 1, 1};
-                B200Helpers::toStreak4(*i, box.origin, s);
-                o[0] = s[0]; o[1] = s[1]; o[2] = s[2];
-                int loc = sourceLocation == MemoryLocation::HOST ? B200GEO_HOST : B200GEO_CUDA_DEVICE;
-                B200Helpers::check(b200geo_grid_load_member(handle, m, o, d, source, loc, 1, 0));
-            } else {
-                if (sourceLocation != MemoryLocation::HOST) {
-                    throw std::logic_error("B200Grid: filtered selectors are only supported for host sources");
-                }
-                std::vector<CELL> cells(n);
-                get(*i, cells.data());
-                selector.copyMemberIn(source, MemoryLocation::HOST, cells.data(), MemoryLocation::HOST, n);
-                set(*i, cells.data());
+            if (sourceLocation != MemoryLocation::HOST) {
+                throw std::logic_error("B200Grid: filtered selectors are only supported for host sources");
             }
+            std::vector<CELL> cells(n);
+            get(*i, cells.data());
+            selector.copyMemberIn(source, MemoryLocation::HOST, cells.data(), MemoryLocation::HOST, n);
+            set(*i, cells.data());
             source += selector.sizeOfExternal() * n;
         }
         sync();
@@ -534,6 +598,7 @@ private:
     mutable Coord<DIM> rowCacheOrigin;
     mutable int rowCacheRows = 0;
     mutable bool rowCacheValid = false;
+    mutable std::size_t memberCalls = 0;
 
     /* `rows` whole rows (same plane, consecutive y) starting at `origin` in ONE transfer */
     void fetchRows(const Coord<DIM>& origin, int rows, CELL *cells) const

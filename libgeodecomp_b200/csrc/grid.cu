@@ -10,7 +10,7 @@
 
 namespace b200geo {
 
-static const Tuning g_tuning_default = {0, -1, 0, 128, 0, 33, 0, 4, 0, 3, -1, 1};
+static const Tuning g_tuning_default = {0, -1, 0, 128, 0, 33, 0, 4, 0, 0, -1, 1, 3, 0, 0};
 Tuning g_tuning = g_tuning_default;
 static thread_local std::string g_last_error;
 static std::atomic<uint64_t> g_launches(0);
@@ -85,6 +85,9 @@ int b200geo_set_tuning(const char *key, int value)
     else if (k == "gol.bits_rows") g_tuning.gol_bits_rows = value < 0 ? g_tuning_default.gol_bits_rows : value;
     else if (k == "nbody.kernel") g_tuning.nbody_kernel = value < 0 ? g_tuning_default.nbody_kernel : value;
     else if (k == "jacobi.pdl") g_tuning.jacobi_pdl = value;
+    else if (k == "jacobi.tb_promo") g_tuning.jacobi_tb_promo = value < 0 ? g_tuning_default.jacobi_tb_promo : value;
+    else if (k == "nbody.run") g_tuning.nbody_run = value < 0 ? g_tuning_default.nbody_run : value;
+    else if (k == "jacobi.tb_raster") g_tuning.jacobi_tb_raster = value < 0 ? g_tuning_default.jacobi_tb_raster : value;
     else if (k == "lbm.variant") g_tuning.lbm_variant = value < 0 ? g_tuning_default.lbm_variant : value;
     else return fail(B200GEO_ERR_INVALID, "unknown tuning key " + k);
     return B200GEO_OK;

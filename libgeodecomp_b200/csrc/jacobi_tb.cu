@@ -29,9 +29,9 @@
 
 namespace b200geo {
 
-namespace {
+int tensor_map(b200geo_grid *g, int which, int tile_cols, int tile_rows, CUtensorMap *out);
 
-constexpr int TX = 64;
+namespace {
 
 struct Limits {
     int lo[3], hi[3];  // cells outside [lo, hi) on an axis hold the edge cell (Cube sides only)
@@ -85,82 +85,132 @@ __device__ __forceinline__ double shfl_down1(double v)
     return __shfl_down_sync(0xffffffffu, v, 1);
 }
 
-// (W + C) + E for the two cells of a lane (27-point row sums, same association as jacobi.cu)
-__device__ __forceinline__ double2 row_sum(double2 c)
+// CX x-adjacent cells of one row, owned by one lane (CX = 2 or 4; 16-byte aligned in memory)
+template<int CX>
+struct Cells {
+    double v[CX];
+};
+
+template<int CX>
+__device__ __forceinline__ Cells<CX> zero_cells()
 {
-    double w = shfl_up1(c.y), e = shfl_down1(c.x);
-    double2 r;
-    r.x = (w + c.x) + c.y;
-    r.y = (c.x + c.y) + e;
+    Cells<CX> c;
+#pragma unroll
+    for (int k = 0; k < CX; ++k) c.v[k] = 0.0;
+    return c;
+}
+
+template<int CX>
+__device__ __forceinline__ Cells<CX> load_cells(const double *p)
+{
+    Cells<CX> c;
+#pragma unroll
+    for (int k = 0; k < CX; k += 2) {
+        double2 d = *reinterpret_cast<const double2 *>(p + k);
+        c.v[k] = d.x;
+        c.v[k + 1] = d.y;
+    }
+    return c;
+}
+
+template<int CX>
+__device__ __forceinline__ void store_cells(double *p, const Cells<CX>& c)
+{
+#pragma unroll
+    for (int k = 0; k < CX; k += 2) *reinterpret_cast<double2 *>(p + k) = make_double2(c.v[k], c.v[k + 1]);
+}
+
+// (W + C) + E for the cells of a lane (27-point row sums, same association as jacobi.cu): the lane's outer
+// neighbours come from the adjacent lanes by shuffle — two shuffles per CX cells
+template<int CX>
+__device__ __forceinline__ Cells<CX> row_sum(const Cells<CX>& c)
+{
+    const double w = shfl_up1(c.v[CX - 1]), e = shfl_down1(c.v[0]);
+    Cells<CX> r;
+#pragma unroll
+    for (int k = 0; k < CX; ++k) {
+        const double l = k == 0 ? w : c.v[k == 0 ? 0 : k - 1];
+        const double h = k == CX - 1 ? e : c.v[k == CX - 1 ? k : k + 1];
+        r.v[k] = (l + c.v[k]) + h;
+    }
     return r;
 }
 
-// Per-level pipeline state of one thread: R rows x 2 cells.
+// Per-level pipeline state of one thread: R rows x CX cells.
 //  6/7-point: zm = plane p-1, acc = partial sum of plane p-1's update still waiting for plane p
 //  27-point : zm = plane sum S(p-2), acc = plane sum S(p-1)
-template<int R>
+template<int CX, int R>
 struct LevelState {
-    double2 zm[R], acc[R];
+    Cells<CX> zm[R], acc[R];
 };
 
 // Feed plane p of one level (own rows n[], the row above and the row below) and get the next
 // level's plane p-1.
-template<int KIND, int R>
-__device__ __forceinline__ void feed_plane(LevelState<R>& st, const double2 (&n)[R], double2 up, double2 dn, double2 (&out)[R])
+template<int KIND, int CX, int R>
+__device__ __forceinline__ void feed_plane(LevelState<CX, R>& st, const Cells<CX> (&n)[R], const Cells<CX>& up, const Cells<CX>& dn,
+                                           Cells<CX> (&out)[R])
 {
     if (KIND == 27) {
-        double2 rs[R + 2];
-        rs[0] = row_sum(up);
+        Cells<CX> rs[R + 2];
+        rs[0] = row_sum<CX>(up);
 #pragma unroll
-        for (int r = 0; r < R; ++r) rs[r + 1] = row_sum(n[r]);
-        rs[R + 1] = row_sum(dn);
+        for (int r = 0; r < R; ++r) rs[r + 1] = row_sum<CX>(n[r]);
+        rs[R + 1] = row_sum<CX>(dn);
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            double2 s;
-            s.x = (rs[r].x + rs[r + 1].x) + rs[r + 2].x;
-            s.y = (rs[r].y + rs[r + 1].y) + rs[r + 2].y;
-            out[r].x = ((st.zm[r].x + st.acc[r].x) + s.x) * (1.0 / 27.0);
-            out[r].y = ((st.zm[r].y + st.acc[r].y) + s.y) * (1.0 / 27.0);
-            st.zm[r] = st.acc[r];
-            st.acc[r] = s;
+#pragma unroll
+            for (int k = 0; k < CX; ++k) {
+                const double s = (rs[r].v[k] + rs[r + 1].v[k]) + rs[r + 2].v[k];
+                out[r].v[k] = ((st.zm[r].v[k] + st.acc[r].v[k]) + s) * (1.0 / 27.0);
+                st.zm[r].v[k] = st.acc[r].v[k];
+                st.acc[r].v[k] = s;
+            }
         }
     } else {
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            double2 c = n[r];
-            double2 ym = r == 0 ? up : n[r == 0 ? 0 : r - 1];
-            double2 yp = r == R - 1 ? dn : n[r == R - 1 ? r : r + 1];
-            double w = shfl_up1(c.y), e = shfl_down1(c.x);
-            if (KIND == 6) {
-                out[r].x = (st.acc[r].x + c.x) * (1.0 / 6.0);
-                out[r].y = (st.acc[r].y + c.y) * (1.0 / 6.0);
-                st.acc[r].x = st.zm[r].x + ym.x + w + c.y + yp.x;
-                st.acc[r].y = st.zm[r].y + ym.y + c.x + e + yp.y;
-            } else {
-                out[r].x = (st.acc[r].x + c.x) * (1.0 / 7.0);
-                out[r].y = (st.acc[r].y + c.y) * (1.0 / 7.0);
-                st.acc[r].x = st.zm[r].x + ym.x + w + c.x + c.y + yp.x;
-                st.acc[r].y = st.zm[r].y + ym.y + c.x + c.y + e + yp.y;
+            const Cells<CX> c = n[r];
+            const Cells<CX>& ym = r == 0 ? up : n[r == 0 ? 0 : r - 1];
+            const Cells<CX>& yp = r == R - 1 ? dn : n[r == R - 1 ? r : r + 1];
+            const double w = shfl_up1(c.v[CX - 1]), e = shfl_down1(c.v[0]);
+#pragma unroll
+            for (int k = 0; k < CX; ++k) {
+                const double l = k == 0 ? w : c.v[k == 0 ? 0 : k - 1];
+                const double h = k == CX - 1 ? e : c.v[k == CX - 1 ? k : k + 1];
+                if (KIND == 6) {
+                    out[r].v[k] = (st.acc[r].v[k] + c.v[k]) * (1.0 / 6.0);
+                    st.acc[r].v[k] = st.zm[r].v[k] + ym.v[k] + l + h + yp.v[k];
+                } else {
+                    out[r].v[k] = (st.acc[r].v[k] + c.v[k]) * (1.0 / 7.0);
+                    st.acc[r].v[k] = st.zm[r].v[k] + ym.v[k] + l + c.v[k] + h + yp.v[k];
+                }
             }
             st.zm[r] = c;
         }
     }
 }
 
-__device__ __forceinline__ double2 with_edge(double2 v, bool o0, bool o1, double edge)
+// cells [first, first + CX) of a lane: those outside [lo, hi) take the edge value (o = the whole row is outside)
+template<int CX>
+__device__ __forceinline__ void with_edge(Cells<CX>& c, bool o, unsigned ox, double edge)
 {
-    if (o0) v.x = edge;
-    if (o1) v.y = edge;
-    return v;
+#pragma unroll
+    for (int k = 0; k < CX; ++k)
+        if (o || ((ox >> k) & 1)) c.v[k] = edge;
 }
 
-template<int KIND, int T, int R, int NW, int NS, int MINB>
+// KIND: 6 / 7 / 27 points; T sweeps per launch; a lane owns CX x-adjacent cells of R rows, a warp R rows of
+// TX = 32 * CX cells, a CTA NW warps = a TX x (R * NW) tile; NS shared-memory stages; H = halo in x (>= T, even:
+// 128-bit stores stay aligned; a multiple of 4 keeps the stored core a whole number of 64-byte blocks)
+template<int KIND, int T, int CX, int R, int NW, int NS, int MINB, int H>
 __global__ void __launch_bounds__(NW * 32, MINB)
 jacobi_tb_kernel(const __grid_constant__ CUtensorMap tmap, double *__restrict__ dst, int64_t pitch, int64_t plane,
-                 Box box, int xa, Limits lim, double edge, int zchunk, int pad_x, int pad_y, int pad_z)
+                 Box box, int xa, Limits lim, double edge, int zchunk, int pad_x, int pad_y, int pad_z, int gx, int gy, int panel)
 {
+    static_assert(CX == 2 || CX == 4, "a lane owns 2 or 4 cells of a row");
+    static_assert(H >= T && H % 2 == 0, "x halo");
+    constexpr int TX = 32 * CX;
     constexpr int TY = R * NW;
-    constexpr int H = (T + 1) & ~1;
     constexpr int NX = T > 1 ? T - 1 : 1;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double *stage = reinterpret_cast<double *>(smem_raw);  // [NS][TY][TX]
@@ -168,8 +218,20 @@ jacobi_tb_kernel(const __grid_constant__ CUtensorMap tmap, double *__restrict__ 
     uint64_t *bars = reinterpret_cast<uint64_t *>(xch + NX * 2 * NW * 2 * TX);
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int X0 = xa + blockIdx.x * (TX - 2 * H) - H;
-    const int Y0 = box.y0 + blockIdx.y * (TY - 2 * T) - T;
+    // CTA order: tiles are numbered along x first (panel = 0), or in panels of `panel` tile rows with y fastest
+    // inside a panel — neighbouring CTAs then share their longer (x) halos as well as the y ones
+    int bx, by;
+    if (panel <= 0) {
+        bx = blockIdx.x % gx;
+        by = blockIdx.x / gx;
+    } else {
+        const int per_panel = panel * gx, p = blockIdx.x / per_panel, rest = blockIdx.x % per_panel;
+        const int rows = min(panel, gy - p * panel);
+        bx = rest / rows;
+        by = p * panel + rest % rows;
+    }
+    const int X0 = xa + bx * (TX - 2 * H) - H;
+    const int Y0 = box.y0 + by * (TY - 2 * T) - T;
     const int zb = box.z0 + blockIdx.z * zchunk;
     const int ze = min(zb + zchunk, box.z1);
     const int zs = zb - T;
@@ -188,18 +250,22 @@ jacobi_tb_kernel(const __grid_constant__ CUtensorMap tmap, double *__restrict__ 
         }
     }
 
-    // this thread's cells: x, x + 1 in rows Y0 + warp * R + r
-    const int x = X0 + 2 * lane;
+    // this thread's cells: x .. x + CX - 1 in rows Y0 + warp * R + r
+    const int x = X0 + CX * lane;
     const int yr = Y0 + warp * R;
-    const bool ox0 = x < lim.lo[0] || x >= lim.hi[0], ox1 = x + 1 < lim.lo[0] || x + 1 >= lim.hi[0];
+    // bit k of ox: cell x + k lies outside the simulation area; bit k of sx: cell x + k is stored
+    unsigned ox = 0, sx = 0;
+#pragma unroll
+    for (int k = 0; k < CX; ++k) {
+        if (x + k < lim.lo[0] || x + k >= lim.hi[0]) ox |= 1u << k;
+        if (CX * lane + k >= H && CX * lane + k < TX - H && x + k >= box.x0 && x + k < box.x1) sx |= 1u << k;
+    }
     // bit r + 1 of oy: row yr + r lies outside the simulation area (r = -1 .. R)
     unsigned oy = 0;
 #pragma unroll
     for (int r = -1; r <= R; ++r)
         if (yr + r < lim.lo[1] || yr + r >= lim.hi[1]) oy |= 1u << (r + 1);
-    const bool sx0 = 2 * lane >= H && 2 * lane < TX - H && x >= box.x0 && x < box.x1;
-    const bool sx1 = 2 * lane >= H && 2 * lane < TX - H && x + 1 >= box.x0 && x + 1 < box.x1;
-    const bool sboth = sx0 && sx1;
+    const bool sall = sx == (1u << CX) - 1;
     unsigned sy = 0;
 #pragma unroll
     for (int r = 0; r < R; ++r) {
@@ -212,15 +278,15 @@ jacobi_tb_kernel(const __grid_constant__ CUtensorMap tmap, double *__restrict__ 
     const int dn_row = warp * R + R < TY ? warp * R + R : TY - 1;
     const int up_warp = warp > 0 ? warp - 1 : 0, dn_warp = warp + 1 < NW ? warp + 1 : NW - 1;
 
-    LevelState<R> st[T];
-    double2 carry[T][R];  // carry[t]: level t plane produced in the previous iteration (t >= 1)
+    LevelState<CX, R> st[T];
+    Cells<CX> carry[T][R];  // carry[t]: level t plane produced in the previous iteration (t >= 1)
 #pragma unroll
     for (int t = 0; t < T; ++t)
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            st[t].zm[r] = make_double2(0.0, 0.0);
-            st[t].acc[r] = make_double2(0.0, 0.0);
-            carry[t][r] = make_double2(0.0, 0.0);
+            st[t].zm[r] = zero_cells<CX>();
+            st[t].acc[r] = zero_cells<CX>();
+            carry[t][r] = zero_cells<CX>();
         }
 
     double *q0 = dst + (int64_t)yr * pitch + x;
@@ -236,63 +302,59 @@ jacobi_tb_kernel(const __grid_constant__ CUtensorMap tmap, double *__restrict__ 
         const int par = i & 1;
 #pragma unroll
         for (int t = T - 1; t >= 0; --t) {
-            double2 n[R], up, dn, out[R];
+            Cells<CX> n[R], up, dn, out[R];
             if (t == 0) {
                 if (i >= nload) continue;
                 const int s = i % NS;
                 while (!mbar_try_wait(&bars[s], (i / NS) & 1)) {}
-                const double *sp = stage + s * TY * TX + 2 * lane;
+                const double *sp = stage + s * TY * TX + CX * lane;
                 const int z = zs + i;
                 const bool oz = z < lim.lo[2] || z >= lim.hi[2];
 #pragma unroll
-                for (int r = 0; r < R; ++r) n[r] = *reinterpret_cast<const double2 *>(sp + (warp * R + r) * TX);
-                up = *reinterpret_cast<const double2 *>(sp + up_row * TX);
-                dn = *reinterpret_cast<const double2 *>(sp + dn_row * TX);
+                for (int r = 0; r < R; ++r) n[r] = load_cells<CX>(sp + (warp * R + r) * TX);
+                up = load_cells<CX>(sp + up_row * TX);
+                dn = load_cells<CX>(sp + dn_row * TX);
                 if (edge_xy || oz) {  // uniform branch: interior tiles never take it
 #pragma unroll
-                    for (int r = 0; r < R; ++r) {
-                        bool o = oz || ((oy >> (r + 1)) & 1);
-                        n[r] = with_edge(n[r], o || ox0, o || ox1, edge);
-                    }
-                    bool o = oz || (oy & 1);
-                    up = with_edge(up, o || ox0, o || ox1, edge);
-                    o = oz || ((oy >> (R + 1)) & 1);
-                    dn = with_edge(dn, o || ox0, o || ox1, edge);
+                    for (int r = 0; r < R; ++r) with_edge<CX>(n[r], oz || ((oy >> (r + 1)) & 1), ox, edge);
+                    with_edge<CX>(up, oz || (oy & 1), ox, edge);
+                    with_edge<CX>(dn, oz || ((oy >> (R + 1)) & 1), ox, edge);
                 }
             } else {
-                const double *xp = xch + (((t - 1) * 2 + (par ^ 1)) * NW) * 2 * TX + 2 * lane;
+                const double *xp = xch + (((t - 1) * 2 + (par ^ 1)) * NW) * 2 * TX + CX * lane;
 #pragma unroll
                 for (int r = 0; r < R; ++r) n[r] = carry[t][r];
-                up = *reinterpret_cast<const double2 *>(xp + (up_warp * 2 + 1) * TX);
-                dn = *reinterpret_cast<const double2 *>(xp + (dn_warp * 2 + 0) * TX);
+                up = load_cells<CX>(xp + (up_warp * 2 + 1) * TX);
+                dn = load_cells<CX>(xp + (dn_warp * 2 + 0) * TX);
             }
-            feed_plane<KIND, R>(st[t], n, up, dn, out);
+            feed_plane<KIND, CX, R>(st[t], n, up, dn, out);
             const int zo = zs + i - 2 * t - 1;  // plane index of `out`, a plane of level t + 1
             const bool oz = zo < lim.lo[2] || zo >= lim.hi[2];
             if (edge_xy || oz) {
 #pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    bool o = oz || ((oy >> (r + 1)) & 1);
-                    out[r] = with_edge(out[r], o || ox0, o || ox1, edge);
-                }
+                for (int r = 0; r < R; ++r) with_edge<CX>(out[r], oz || ((oy >> (r + 1)) & 1), ox, edge);
             }
             if (t == T - 1) {
                 if (zo >= zb && zo < ze) {
                     double *q = q0 + (int64_t)zo * plane;
-                    if (sboth) {  // the common case: predicated 128-bit stores, no branches per row
+                    if (sall) {  // the common case: predicated 128-bit stores, no branches per row
 #pragma unroll
                         for (int r = 0; r < R; ++r)
-                            if ((sy >> r) & 1) *reinterpret_cast<double2 *>(q + r * pitch) = out[r];
-                    } else if (sx0 || sx1) {  // odd box edges in x
+                            if ((sy >> r) & 1) store_cells<CX>(q + r * pitch, out[r]);
+                    } else if (sx) {  // tile halo, odd box edges in x
 #pragma unroll
                         for (int r = 0; r < R; ++r)
-                            if ((sy >> r) & 1) q[r * pitch + (sx0 ? 0 : 1)] = sx0 ? out[r].x : out[r].y;
+                            if ((sy >> r) & 1) {
+#pragma unroll
+                                for (int k = 0; k < CX; ++k)
+                                    if ((sx >> k) & 1) q[r * pitch + k] = out[r].v[k];
+                            }
                     }
                 }
             } else {
-                double *xp = xch + ((t * 2 + par) * NW + warp) * 2 * TX + 2 * lane;
-                *reinterpret_cast<double2 *>(xp) = out[0];
-                *reinterpret_cast<double2 *>(xp + TX) = out[R - 1];
+                double *xp = xch + ((t * 2 + par) * NW + warp) * 2 * TX + CX * lane;
+                store_cells<CX>(xp, out[0]);
+                store_cells<CX>(xp + TX, out[R - 1]);
 #pragma unroll
                 for (int r = 0; r < R; ++r) carry[t + 1][r] = out[r];
             }
@@ -318,57 +380,65 @@ EncodeTiled encode_tiled()
     return fn;
 }
 
-template<int KIND, int T, int R, int NW, int NS, int MINB>
-int launch_tb(b200geo_grid *g, const CUtensorMap& map, const Box& box, const Limits& lim, double edge, cudaStream_t s)
+template<int KIND, int T, int CX, int R, int NW, int NS, int MINB, int H>
+int launch_tb(b200geo_grid *g, const Box& box, const Limits& lim, double edge, cudaStream_t s)
 {
+    constexpr int TX = 32 * CX;
     constexpr int TY = R * NW;
-    constexpr int H = (T + 1) & ~1;
     constexpr int NX = T > 1 ? T - 1 : 1;
     const MemberLayout& L = g->m[0];
+    CUtensorMap map;
+    int rc = tensor_map(g, g->cur, TX, TY, &map);
+    if (rc) return rc;
     size_t smem = (size_t)NS * TY * TX * 8 + (size_t)NX * 2 * NW * 2 * TX * 8 + NS * 8;
-    auto kernel = jacobi_tb_kernel<KIND, T, R, NW, NS, MINB>;
+    auto kernel = jacobi_tb_kernel<KIND, T, CX, R, NW, NS, MINB, H>;
     // function attributes are per device: one process may drive several GPUs (slab groups)
     static bool attr_set[64] = {false};
     if (g->device < 0 || g->device >= 64 || !attr_set[g->device]) {
         B200GEO_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         if (g->device >= 0 && g->device < 64) attr_set[g->device] = true;
     }
-    int xa = box.x0 & ~1;
+    int xa = box.x0 & ~(CX - 1);
     int gx = (box.x1 - xa + (TX - 2 * H) - 1) / (TX - 2 * H);
     int gy = (box.y1 - box.y0 + (TY - 2 * T) - 1) / (TY - 2 * T);
     int nz = box.z1 - box.z0;
     // long z chunks amortise the 2T warm-up planes; enough chunks to fill the machine several times over
     int zchunk = g_tuning.jacobi_tb_zchunk > 0 ? g_tuning.jacobi_tb_zchunk : 128;
     while (zchunk > 16 && (int64_t)gx * gy * ((nz + zchunk - 1) / zchunk) < 148 * 6) zchunk /= 2;
-    dim3 grid(gx, gy, (nz + zchunk - 1) / zchunk);
-    if (grid.y > 65535 || grid.z > 65535) return fail(B200GEO_ERR_OUT_OF_RANGE, "grid dimension too large");
+    dim3 grid((unsigned)(gx * gy), 1, (nz + zchunk - 1) / zchunk);
+    if ((int64_t)gx * gy > 0x7fffffff || grid.z > 65535) return fail(B200GEO_ERR_OUT_OF_RANGE, "grid dimension too large");
     double *dst = (double *)g->member_ptr(0, 1) + L.origin;
-    kernel<<<grid, NW * 32, smem, s>>>(map, dst, L.pitch, L.plane, box, xa, lim, edge, zchunk, L.lead, g->g[1], g->g[2]);
+    kernel<<<grid, NW * 32, smem, s>>>(map, dst, L.pitch, L.plane, box, xa, lim, edge, zchunk, L.lead, g->g[1], g->g[2], gx, gy,
+                                       g_tuning.jacobi_tb_raster);
     count_launch();
     return check_cuda(cudaGetLastError(), "temporal-blocked jacobi sweep");
 }
 
 template<int KIND, int T>
-int launch_tb_shape(b200geo_grid *g, const CUtensorMap& map, int rows, const Box& box, const Limits& lim, double edge, cudaStream_t s)
+int launch_tb_shape(b200geo_grid *g, int rows, const Box& box, const Limits& lim, double edge, cudaStream_t s)
 {
-    // tile shapes: 64 x 32 (R = 2, 16 warps), 64 x 64 (R = 4, 16 warps), 64 x 32 (R = 4, 8 warps);
-    // the register budget (state = 4 f64 per cell and level) decides how many CTAs share an SM
+    // tile shapes ("jacobi.tb_rows"): the register budget (state = 6 f64 per cell and level) decides how many CTAs
+    // share an SM, the halo (2H of TX columns, 2T of TY rows) how much of a tile is redundant
+    constexpr int HD = (T + 1) & ~1;        // narrowest even x halo
+    constexpr int H4 = (T + 3) & ~3;        // x halo that keeps stored cores whole multiples of 64 bytes
+    constexpr int M2 = T == 2 ? 2 : 1;
     switch (rows) {
-    case 64: return launch_tb<KIND, T, 4, 16, 3, 1>(g, map, box, lim, edge, s);
-    case 33: return launch_tb<KIND, T, 4, 8, 4, (T == 2 ? 2 : 1)>(g, map, box, lim, edge, s);
-    case 34: return launch_tb<KIND, T, 4, 8, 4, 1>(g, map, box, lim, edge, s);
-    case 31: return launch_tb<KIND, T, 2, 16, 4, 1>(g, map, box, lim, edge, s);
-    default: return launch_tb<KIND, T, 2, 16, 4, (T == 2 ? 2 : 1)>(g, map, box, lim, edge, s);
+    case 64: return launch_tb<KIND, T, 2, 4, 16, 3, 1, HD>(g, box, lim, edge, s);    // 64 x 64, 4 rows / thread
+    case 34: return launch_tb<KIND, T, 2, 4, 8, 4, 1, HD>(g, box, lim, edge, s);     // 64 x 32, one CTA / SM
+    case 31: return launch_tb<KIND, T, 2, 2, 16, 4, 1, HD>(g, box, lim, edge, s);
+    case 32: return launch_tb<KIND, T, 2, 2, 16, 4, M2, HD>(g, box, lim, edge, s);   // 64 x 32, 2 rows / thread
+    case 40: return launch_tb<KIND, T, 2, 4, 8, 4, M2, H4>(g, box, lim, edge, s);    // as 33 with 64-byte-aligned cores
+    default: return launch_tb<KIND, T, 2, 4, 8, 4, M2, HD>(g, box, lim, edge, s);    // 33: 64 x 32, 4 rows / thread
     }
 }
 
 template<int KIND>
-int launch_tb_depth(b200geo_grid *g, const CUtensorMap& map, int depth, int rows, const Box& box, const Limits& lim, double edge, cudaStream_t s)
+int launch_tb_depth(b200geo_grid *g, int depth, int rows, const Box& box, const Limits& lim, double edge, cudaStream_t s)
 {
     switch (depth) {
-    case 2: return launch_tb_shape<KIND, 2>(g, map, rows, box, lim, edge, s);
-    case 3: return launch_tb_shape<KIND, 3>(g, map, rows, box, lim, edge, s);
-    case 4: return launch_tb_shape<KIND, 4>(g, map, rows, box, lim, edge, s);
+    case 2: return launch_tb_shape<KIND, 2>(g, rows, box, lim, edge, s);
+    case 3: return launch_tb_shape<KIND, 3>(g, rows, box, lim, edge, s);
+    case 4: return launch_tb_shape<KIND, 4>(g, rows, box, lim, edge, s);
     default: return fail(B200GEO_ERR_INVALID, "temporal blocking depth must be 2, 3 or 4");
     }
 }
@@ -376,18 +446,21 @@ int launch_tb_depth(b200geo_grid *g, const CUtensorMap& map, int depth, int rows
 }
 
 // TMA descriptor of member 0 of buffer `which` (absolute index): the whole padded array as a
-// rank-3 tensor of f64, box = one 64 x TY x 1 tile.
-static int tensor_map(b200geo_grid *g, int which, int tile_rows, CUtensorMap *out)
+// rank-3 tensor of f64, box = one TX x TY x 1 tile.
+int tensor_map(b200geo_grid *g, int which, int tile_cols, int tile_rows, CUtensorMap *out)
 {
     EncodeTiled enc = encode_tiled();
     if (!enc) return fail(B200GEO_ERR_CUDA, "CUDA error: cuTensorMapEncodeTiled is not available in this driver");
     const MemberLayout& L = g->m[0];
     cuuint64_t dims[3] = {(cuuint64_t)L.pitch, (cuuint64_t)(g->d[1] + 2 * g->g[1]), (cuuint64_t)(g->d[2] + 2 * g->g[2])};
     cuuint64_t strides[2] = {(cuuint64_t)L.pitch * 8, (cuuint64_t)L.plane * 8};
-    cuuint32_t boxdim[3] = {(cuuint32_t)TX, (cuuint32_t)tile_rows, 1};
+    cuuint32_t boxdim[3] = {(cuuint32_t)tile_cols, (cuuint32_t)tile_rows, 1};
     cuuint32_t estr[3] = {1, 1, 1};
+    const CUtensorMapL2promotion promo = g_tuning.jacobi_tb_promo == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE :
+        g_tuning.jacobi_tb_promo == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B :
+        g_tuning.jacobi_tb_promo == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
     CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, g->buf[which] + L.offset, dims, strides, boxdim, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, promo,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(B200GEO_ERR_CUDA, "CUDA error: cuTensorMapEncodeTiled failed");
     return B200GEO_OK;
@@ -396,10 +469,6 @@ static int tensor_map(b200geo_grid *g, int which, int tile_rows, CUtensorMap *ou
 int sweep_jacobi_tb(b200geo_grid *g, int kind, int depth, const Box& box, cudaStream_t s)
 {
     int rows = g_tuning.jacobi_tb_rows;
-    int tile_rows = rows == 64 ? 64 : 32;
-    CUtensorMap map;
-    int rc = tensor_map(g, g->cur, tile_rows, &map);
-    if (rc) return rc;
     Limits lim;
     for (int i = 0; i < 3; ++i) {
         lim.lo[i] = g->desc.ghost_mode[i][0] == B200GEO_GHOST_EDGE ? 0 : INT_MIN;
@@ -408,9 +477,9 @@ int sweep_jacobi_tb(b200geo_grid *g, int kind, int depth, const Box& box, cudaSt
     double edge;
     memcpy(&edge, g->edge + g->m[0].edge_offset, 8);
     switch (kind) {
-    case 6: return launch_tb_depth<6>(g, map, depth, rows, box, lim, edge, s);
-    case 7: return launch_tb_depth<7>(g, map, depth, rows, box, lim, edge, s);
-    default: return launch_tb_depth<27>(g, map, depth, rows, box, lim, edge, s);
+    case 6: return launch_tb_depth<6>(g, depth, rows, box, lim, edge, s);
+    case 7: return launch_tb_depth<7>(g, depth, rows, box, lim, edge, s);
+    default: return launch_tb_depth<27>(g, depth, rows, box, lim, edge, s);
     }
 }
 

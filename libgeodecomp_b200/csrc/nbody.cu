@@ -425,6 +425,203 @@ fused_kernel(const int32_t *__restrict__ cnt_old, const REAL *__restrict__ part_
     }
 }
 
+// 128-bit shared-memory load of V = 16 / sizeof(REAL) consecutive coordinates
+__device__ __forceinline__ void lds_vec(const float *p, float (&v)[4])
+{
+    const float4 t = *reinterpret_cast<const float4 *>(p);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+__device__ __forceinline__ void lds_vec(const double *p, double (&v)[2])
+{
+    const double2 t = *reinterpret_cast<const double2 *>(p);
+    v[0] = t.x; v[1] = t.y;
+}
+
+// The fused re-bin / update kernel, second generation (capacity <= 32). Same staging and re-bin as fused_kernel;
+// the particle update differs:
+//   pass 1 (filter): per neighbour container ONE 32-bit mask of the slots inside the enlarged cutoff, built from
+//          128-bit shared-memory loads (4 floats / 2 doubles of x, of y, of z per load: 0.75 loads per candidate
+//          instead of 3) and a fused distance; the 27 masks go to shared memory ([27][NT] words: 27 stores per
+//          particle where the candidate lists took one store per CANDIDATE, and 27.6 KB per CTA instead of 45 KB);
+//   pass 2 (exact): walks the set bits of the 27 masks in order — container by container, slot by slot: the
+//          reference's order — as ONE flat loop per lane (a lane refills its mask word when it runs dry, lanes do
+//          not wait for each other per container), with the reference arithmetic incl. the exact cutoff test.
+template<typename REAL, int G, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB)
+fused2_kernel(const int32_t *__restrict__ cnt_old, const REAL *__restrict__ part_old, int32_t *__restrict__ cnt_new,
+              REAL *__restrict__ part_new, BoxDims D, int z0, int runs_per_row, REAL dt, REAL rc2, REAL rc2_loose,
+              int rebin, int *overflow)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int V = 16 / (int)sizeof(REAL);
+    const int cap = D.cap;
+    const int SP = 3 * cap + 4;      // see fused_kernel
+    constexpr int NC = (G + 2) * 9;
+    REAL *spos = reinterpret_cast<REAL *>(smem_raw);                 // [NC][SP]
+    uint32_t *smask = reinterpret_cast<uint32_t *>(spos + NC * SP);  // [27][NT]
+    int *scnt = reinterpret_cast<int *>(smask + 27 * NT);            // [NC]
+    int *pre = scnt + NC;                                            // [G + 1]
+    uint64_t *bar = reinterpret_cast<uint64_t *>(pre + G + 1 + ((G + 1) & 1));
+    unsigned short *newidx = reinterpret_cast<unsigned short *>(bar + 1);   // [G][cap]: staged index of every new particle
+
+    const int run = blockIdx.x % runs_per_row;
+    const int y = (blockIdx.x / runs_per_row) % D.ny;
+    const int z = z0 + blockIdx.x / (runs_per_row * D.ny);
+    const int x0 = run * G;
+
+    if (threadIdx.x == 0) {
+        mbar_init(bar, NC);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < NC; c += NT) {
+        int lx = c % (G + 2), ly = (c / (G + 2)) % 3, lz = c / ((G + 2) * 3);
+        int cx = x0 - 1 + lx;
+        int n = 0;
+        if (cx <= D.nx) {
+            const int64_t pc = pcell(D, cx, y - 1 + ly, z - 1 + lz);
+            n = cnt_old[pc];
+            if (n > 0) {
+                const uint32_t bytes = 3 * cap * sizeof(REAL);
+                mbar_expect_tx(bar, bytes);
+                bulk_load(spos + c * SP, part_old + pc * 6 * cap, bytes, bar);
+            }
+        }
+        if (n <= 0) mbar_arrive(bar);
+        scnt[c] = n;
+    }
+    __syncthreads();
+    while (!mbar_try_wait(bar, 0)) {}
+
+    // re-bin: as in fused_kernel (boxcell.h:123-138,164-174)
+    {
+        const int lane = threadIdx.x & 31;
+        for (int j = threadIdx.x >> 5; j < G; j += NT / 32) {
+            int n = 0;
+            if (x0 + j < D.nx) {
+                const double ex = (double)(x0 + j + D.org[0]) * D.edge, ey = (double)(y + D.org[1]) * D.edge,
+                             ez = (double)(z + D.org[2]) * D.edge;
+                REAL ox, oy, oz, qx, qy, qz;
+                round_up(ex, ox);
+                round_up(ey, oy);
+                round_up(ez, oz);
+                round_up(ex + D.edge, qx);
+                round_up(ey + D.edge, qy);
+                round_up(ez + D.edge, qz);
+#pragma unroll
+                for (int k = 0; k < 27; ++k) {
+                    if (!rebin && k != 13) continue;
+                    const int cell = ((k / 9) * 3 + (k / 3) % 3) * (G + 2) + j + k % 3;
+                    const int cn = scnt[cell];
+                    for (int b = 0; b < cn; b += 32) {
+                        const int sl = b + lane;
+                        bool inside = false;
+                        if (sl < cn) {
+                            const REAL *q = spos + cell * SP + sl;
+                            const REAL px = q[0], py = q[cap], pz = q[2 * cap];
+                            inside = !rebin || (ox <= px && oy <= py && oz <= pz && px < qx && py < qy && pz < qz);
+                        }
+                        const unsigned mask = __ballot_sync(0xffffffffu, inside);
+                        if (inside) {
+                            const int dst = n + __popc(mask & ((1u << lane) - 1));
+                            if (dst < cap) newidx[j * cap + dst] = (unsigned short)(cell * SP + sl);
+                        }
+                        n += __popc(mask);
+                    }
+                }
+                if (lane == 0) {
+                    cnt_new[pcell(D, x0 + j, y, z)] = n < cap ? n : cap;
+                    if (n > cap) atomicOr(overflow, 1);  // FixedArray::operator<<: "capacity exceeded"
+                }
+            }
+            if (lane == 0) pre[j + 1] = n < cap ? n : cap;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        pre[0] = 0;
+        for (int j = 0; j < G; ++j) pre[j + 1] += pre[j];
+    }
+    __syncthreads();
+
+    const int total = pre[G];
+    uint32_t *mymask = smask + threadIdx.x;
+    for (int t = threadIdx.x; t < total; t += NT) {
+        int j = 0;
+        while (pre[j + 1] <= t) ++j;
+        const int slot = t - pre[j];
+        const int from = newidx[j * cap + slot], fc = from / SP, fs = from % SP;
+        const REAL *old = part_old + pcell(D, x0 - 1 + fc % (G + 2), y - 1 + (fc / (G + 2)) % 3, z - 1 + fc / ((G + 2) * 3)) * 6 * cap + fs;
+        const REAL p0 = spos[from], p1 = spos[from + cap], p2 = spos[from + 2 * cap];
+        REAL v0 = old[3 * cap], v1 = old[4 * cap], v2 = old[5 * cap];
+
+        // pass 1: one mask per neighbour container (the row loop is NOT unrolled: 27 copies of the candidate loop
+        // thrash the instruction cache — 24 % of the stall samples were no_inst, profiles/r3d)
+#pragma unroll 1
+        for (int kk = 0; kk < 9; ++kk) {
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const int cell = kk * (G + 2) + j + kx;
+                const int cn = scnt[cell];
+                const REAL *q = spos + cell * SP;
+                uint32_t m = 0;
+#pragma unroll 2
+                for (int p = 0; p < cn; p += V) {
+                    REAL xs[V], ys[V], zs[V];
+                    lds_vec(q + p, xs);
+                    lds_vec(q + cap + p, ys);
+                    lds_vec(q + 2 * cap + p, zs);
+                    uint32_t nib = 0;
+#pragma unroll
+                    for (int u = 0; u < V; ++u) {
+                        const REAL d0 = p0 - xs[u], d1 = p1 - ys[u], d2 = p2 - zs[u];
+                        const REAL r2 = fma_any(d2, d2, fma_any(d1, d1, d0 * d0));
+                        if (r2 < rc2_loose) nib |= 1u << u;
+                    }
+                    m |= nib << p;
+                }
+                // slots at and beyond cn of the last group hold stale shared memory
+                m &= cn >= 32 ? 0xffffffffu : (1u << cn) - 1u;
+                mymask[(kk * 3 + kx) * NT] = m;
+            }
+        }
+
+        // pass 2: the accepted candidates in reference order, reference arithmetic
+        {
+            int k = -1;
+            uint32_t m = 0;
+            const REAL *q = spos;
+            for (;;) {
+                while (m == 0 && k < 26) {
+                    ++k;
+                    m = mymask[k * NT];
+                    q = spos + ((k / 3) * (G + 2) + j + k % 3) * SP;
+                }
+                if (m == 0) break;
+                const int p = __ffs(m) - 1;
+                m &= m - 1;
+                const REAL d0 = p0 - q[p], d1 = p1 - q[cap + p], d2 = p2 - q[2 * cap + p];
+                const REAL r2 = (d0 * d0 + d1 * d1) + d2 * d2;
+                if (r2 == (REAL)0 || r2 >= rc2) continue;
+                const REAL inv = (REAL)1 / r2;
+                const REAL s6 = inv * inv * inv;
+                const REAL f = ((REAL)24 * inv) * s6 * ((REAL)2 * s6 - (REAL)1);
+                v0 += (d0 * f) * dt;
+                v1 += (d1 * f) * dt;
+                v2 += (d2 * f) * dt;
+            }
+        }
+
+        REAL *me = part_new + pcell(D, x0 + j, y, z) * 6 * cap + slot;
+        me[0] = p0 + v0 * dt;
+        me[cap] = p1 + v1 * dt;
+        me[2 * cap] = p2 + v2 * dt;
+        me[3 * cap] = v0;
+        me[4 * cap] = v1;
+        me[5 * cap] = v2;
+    }
+}
+
 // dense AoS [cells][cap][6] (host interchange format) <-> SoA containers of a box
 template<typename REAL, bool LOAD>
 __global__ void transpose_kernel(int32_t *cnt, REAL *part, BoxDims D, int ox, int oy, int oz, int dx, int dy, int dz,
@@ -483,8 +680,8 @@ int sweep(b200geo_boxgrid *g, const b200geo_nbody_params *p, int rebin, cudaStre
             attr[g->device & 63] = true;
         }
         force_kernel<REAL, RUN><<<(unsigned)((int64_t)runs * D.ny * D.nz), 128, smem, s>>>(co, po, cn, pn, D, 0, runs, (REAL)p->dt, rc * rc);
-    } else {
-        // run length / CTA size: two CTAs per SM must fit their staged neighbourhoods and lists in 227 KB
+    } else if (g_tuning.nbody_kernel == 3 || g->cap > 32) {
+        // first-generation fused kernel (per-thread candidate lists): any capacity up to 64
         constexpr int G = sizeof(REAL) == 4 ? 16 : 8, NT = 16 * G, LMAX = 88, NC = (G + 2) * 9;
         int runs = (D.nx + G - 1) / G;
         size_t smem = (size_t)NC * (3 * g->cap + 4) * sizeof(REAL) + (NC + G + 2) * sizeof(int) + 8 +
@@ -499,6 +696,29 @@ int sweep(b200geo_boxgrid *g, const b200geo_nbody_params *p, int rebin, cudaStre
         REAL loose = rc * rc * (REAL)(1.0 + 1.0 / 65536.0);
         fused_kernel<REAL, G, NT, LMAX><<<(unsigned)((int64_t)runs * D.ny * D.nz), NT, smem, s>>>(
             co, po, cn, pn, D, 0, runs, (REAL)p->dt, rc * rc, loose, rebin, g->overflow);
+    } else {
+        // second-generation fused kernel (per-container masks); run length / CTA size: "nbody.run" = 8 or 16
+        REAL loose = rc * rc * (REAL)(1.0 + 1.0 / 65536.0);
+#define NBODY_LAUNCH2(G, NT, MINB)                                                                                          \
+        do {                                                                                                                \
+            constexpr int NC = (G + 2) * 9;                                                                                 \
+            int runs = (D.nx + G - 1) / G;                                                                                  \
+            size_t smem = (size_t)NC * (3 * g->cap + 4) * sizeof(REAL) + (size_t)27 * NT * 4 + (NC + G + 2) * sizeof(int) + 8 +  \
+                          (size_t)(G * g->cap + 2) * sizeof(unsigned short);                                                \
+            static bool attr4[64] = {false};                                                                                \
+            if (!attr4[g->device & 63]) {                                                                                   \
+                B200GEO_CUDA(cudaFuncSetAttribute(fused2_kernel<REAL, G, NT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
+                attr4[g->device & 63] = true;                                                                               \
+            }                                                                                                               \
+            fused2_kernel<REAL, G, NT, MINB><<<(unsigned)((int64_t)runs * D.ny * D.nz), NT, smem, s>>>(                      \
+                co, po, cn, pn, D, 0, runs, (REAL)p->dt, rc * rc, loose, rebin, g->overflow);                               \
+        } while (0)
+        // 0 = automatic: runs of 16 for float, of 8 for double (its staged neighbourhood is twice as large)
+        const int run = g_tuning.nbody_run > 0 ? g_tuning.nbody_run : (sizeof(REAL) == 4 ? 16 : 8);
+        if (run == 8) NBODY_LAUNCH2(8, 128, 4);
+        else if (run == 12) NBODY_LAUNCH2(12, 192, 3);
+        else NBODY_LAUNCH2(16, 256, 2);
+#undef NBODY_LAUNCH2
     }
     count_launch();
     return check_cuda(cudaGetLastError(), "n-body sweep");

@@ -156,6 +156,59 @@ static void testSelectorsAndErrors()
     (void)squareOfTemp;
 }
 
+/* saveMember / loadMember over box-shaped and ragged regions: one strided copy per BOX of the streak list
+ * (B200Helpers::mergeStreaks), same bytes as streak by streak */
+static void testMemberBoxFastPath()
+{
+    typedef Jacobi7Cube CELL;
+    CoordBox<3> box(Coord<3>(2, 3, 4), Coord<3>(9, 6, 5));      // a grid that does not start at the origin
+    B200Grid<CELL> grid(box);
+    for (CoordBox<3>::Iterator i = box.begin(); i != box.end(); ++i) {
+        grid.set(*i, CELL(0.5 + (*i - box.origin).toIndex(box.dimensions)));
+    }
+    Selector<CELL> sel(&CELL::temp, "temp");
+    struct Case { Region<3> region; std::size_t boxes; } cases[4];
+    cases[0].region << box;                                                          // the whole grid: ONE copy
+    cases[0].boxes = 1;
+    cases[1].region << CoordBox<3>(Coord<3>(3, 4, 5), Coord<3>(4, 3, 2));            // an inner box
+    cases[1].boxes = 1;
+    cases[2].region << CoordBox<3>(Coord<3>(2, 3, 4), Coord<3>(9, 6, 1))             // a plane ...
+                    << CoordBox<3>(Coord<3>(4, 5, 6), Coord<3>(3, 2, 2))             // ... a box two planes up ...
+                    << Streak<3>(Coord<3>(2, 8, 8), 7);                              // ... and a lone streak
+    cases[2].boxes = 3;
+    cases[3].region << Streak<3>(Coord<3>(2, 3, 4), 6) << Streak<3>(Coord<3>(2, 4, 4), 7) << Streak<3>(Coord<3>(3, 5, 4), 7);
+    cases[3].boxes = 3;                                                              // ragged rows: nothing to merge
+    for (int c = 0; c < 4; ++c) {
+        const Region<3>& region = cases[c].region;
+        std::vector<double> got(region.size(), -1.0), want;
+        for (Region<3>::StreakIterator i = region.beginStreak(); i != region.endStreak(); ++i) {
+            for (int x = i->origin.x(); x < i->endX; ++x) {
+                Coord<3> at(x, i->origin.y(), i->origin.z());
+                want.push_back(0.5 + (at - box.origin).toIndex(box.dimensions));
+            }
+        }
+        std::size_t before = grid.memberCopyCalls();
+        grid.saveMember(got.data(), MemoryLocation::HOST, sel, region);
+        CHECK(grid.memberCopyCalls() - before == cases[c].boxes);
+        CHECK(got == want);
+        // and back in, negated
+        for (std::size_t k = 0; k < got.size(); ++k) {
+            got[k] = -got[k];
+        }
+        before = grid.memberCopyCalls();
+        grid.loadMember(got.data(), MemoryLocation::HOST, sel, region);
+        CHECK(grid.memberCopyCalls() - before == cases[c].boxes);
+        long bad = 0;
+        for (CoordBox<3>::Iterator i = box.begin(); i != box.end(); ++i) {
+            double v = 0.5 + (*i - box.origin).toIndex(box.dimensions);
+            bad += grid.get(*i).temp != (region.count(*i) ? -v : v);
+        }
+        CHECK(bad == 0);
+        grid.loadMember(want.data(), MemoryLocation::HOST, sel, region);
+    }
+    std::printf("member I/O by boxes: 1 / 1 / 3 / 3 copies for a grid / a box / plane + box + streak / ragged rows\n");
+}
+
 /* The AoS form of the D3Q19 cell (oracle/models/lbm_aos.h, used by the GPU comparator and the generic-path test) is the
  * same model as the SoA / updateLineX cell the hand-written kernel is bound to: both through the reference's
  * SerialSimulator (VanillaUpdateFunctor-free FixedCoord path vs FixedNeighborhoodUpdateFunctor), member by member. */
@@ -366,6 +419,7 @@ int main()
         testCapacityExceeded();
         testResizeAndWriteOrder();
         testSelectorsAndErrors();
+        testMemberBoxFastPath();
     } catch (const std::exception& e) {
         std::printf("FAILED with exception: %s\n", e.what());
         return 2;

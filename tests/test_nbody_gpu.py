@@ -33,14 +33,17 @@ def run(model, counts, parts, steps):
 @pytest.fixture
 def nbody_kernel():
     """select the kernel variant ("nbody.kernel") for one test: 1 = re-bin + one-pass force kernels,
-    3 = fused re-bin / candidate-list kernel (default)"""
+    3 = fused re-bin / candidate-list kernel, 0 = fused kernel with per-container masks (default), 8 / 12 = the
+    default kernel with runs of 8 / 12 containers per CTA ("nbody.run")"""
     def set_(value):
-        capi.set_tuning("nbody.kernel", value)
+        capi.set_tuning("nbody.kernel", value if value in (1, 3) else 0)
+        capi.set_tuning("nbody.run", value if value in (8, 12) else -1)
     yield set_
     capi.set_tuning("nbody.kernel", -1)
+    capi.set_tuning("nbody.run", -1)
 
 
-@pytest.mark.parametrize("kernel", [1, 3])
+@pytest.mark.parametrize("kernel", [0, 1, 3, 8, 12])
 @pytest.mark.parametrize("real", [np.float32, np.float64])
 @pytest.mark.parametrize("dims,steps,vel,dt", [((6, 5, 4), 10, 8.0, 0.01), ((9, 3, 2), 6, 20.0, 0.02), ((1, 1, 1), 5, 1.0, 0.01),
                                                ((17, 4, 3), 8, 10.0, 0.01), ((8, 8, 8), 10, 0.0, 0.005), ((2, 1, 7), 9, 15.0, 0.01)])
@@ -78,7 +81,7 @@ def test_nbody_golden_from_the_reference(key):
     assert np.array_equal(po.view(np.uint8), z[key + "_out_parts"].view(np.uint8))
 
 
-@pytest.mark.parametrize("kernel", [1, 3])
+@pytest.mark.parametrize("kernel", [0, 1, 3, 8])
 @pytest.mark.parametrize("real", [np.float32, np.float64])
 def test_nbody_dense_containers_overflow_the_candidate_lists(oracle, nbody_kernel, kernel, real):
     """~27 (capacity 32) and ~33 (capacity 48) particles per container: more than 88 candidates pass the

@@ -58,13 +58,13 @@ def tuning():
 @pytest.mark.parametrize("kind", [6, 7, 27])
 @pytest.mark.parametrize("torus", [False, True])
 @pytest.mark.parametrize("depth", [1, 2, 3, 4])
-@pytest.mark.parametrize("rows", [32, 33, 64])
+@pytest.mark.parametrize("rows", [32, 33, 64, 40])
 def test_jacobi_temporal_blocking_bit_exact(oracle, tuning, kind, torus, depth, rows):
     """T sweeps per launch (TMA-staged temporal-blocked kernel) == T single sweeps == the oracle;
     7 steps are not a multiple of any depth, so the remainder launches are covered as well."""
     tuning("jacobi.tb", depth)
     tuning("jacobi.tb_rows", rows)
-    for shape in [(18, 20, 24), (7, 5, 3), (1, 1, 1), (40, 70, 130), (9, 129, 61)]:
+    for shape in [(18, 20, 24), (7, 5, 3), (1, 1, 1), (40, 70, 130), (9, 129, 61), (5, 30, 259)]:
         data, got = run_jacobi(kind, torus, shape, 7, edge=0.25)
         want = oracle.jacobi(kind, torus, data, 7, edge=0.25)
         assert np.array_equal(got, want), shape
