@@ -85,7 +85,8 @@ int b200geo_device_count(void);
  * "jacobi.zchunk", "jacobi.prefetch", "gol.rows", "lbm.block", "jacobi.tb" (sweeps fused per launch
  * by the temporal-blocked Jacobi kernels, 1..4; 0 = automatic: 2 for the 27-point kernel, 4 for 6/7-point), "jacobi.tb_rows" (tile shape), "jacobi.tb_zchunk", "gol.bits" (fewest sweeps per call that run
  * bit-packed; 0 = never), "gol.bits_rows", "nbody.kernel", "jacobi.pdl" (programmatic dependent launch of the one-sweep Jacobi
- * kernel: 0, 1, < 0 = small grids only), "lbm.variant" (rows per thread of the LBM kernel: 1 or 2).
+ * kernel: 0, 1, < 0 = small grids only), "lbm.variant" (rows per thread of the LBM kernel: 1 or 2), "jacobi.tb_promo" (L2 promotion of the
+ * temporal-blocked kernel's TMA loads), "jacobi.tb_raster" (its CTA order), "nbody.run" (containers per CTA).
  * value < 0 restores the default. */
 int b200geo_set_tuning(const char *key, int value);
 /* number of kernels this library has launched so far in this process (bench.py: gpu_launches). */
@@ -169,6 +170,12 @@ int b200geo_swap(b200geo_grid *g);
  * b200geo_step; needed before b200geo_update_box on Torus axes). */
 int b200geo_refresh_ghosts(b200geo_grid *g, void *stream);
 int b200geo_sync(void *stream);
+/* Plain device memory on `device` for region buffers that stay on the GPU: the device twins of the host-side
+ * PatchBufferFixed a Stepper keeps for its rim and its volatile kernel (parallelization/nesting/commonstepper.h:
+ * 29-30, 236-283; storage/patchbufferfixed.h) — filled and drained by b200geo_grid_save_region /
+ * _load_region with location = B200GEO_CUDA_DEVICE. */
+int b200geo_device_alloc(int device, uint64_t bytes, void **ptr);
+int b200geo_device_free(int device, void *ptr);
 
 /* ---- halo exchange (replaces PatchLink::Accepter::put / Provider::get,
  *      communication/patchlink.h:127-151,218-244, for slab partitions along the last axis,

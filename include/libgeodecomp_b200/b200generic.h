@@ -288,6 +288,12 @@ struct WordSlicedBinding {
         }
     }
 
+    /* one sweep over a box: current buffer -> scratch buffer, no swap (B200Grid::updateRegion, B200Stepper) */
+    static void updateBox(b200geo_grid *g, unsigned nanoStep, const int32_t origin[3], const int32_t dim[3])
+    {
+        launchBox(g, nanoStep, origin, dim, 0);
+    }
+
     /* sweeps x { refresh periodic images; UpdateFunctor over the whole grid; swap }
      * = SerialSimulator::nanoStep (parallelization/serialsimulator.h:132-139) */
     static void step(b200geo_grid *g, const int32_t dim[3], unsigned firstNanoStep, unsigned sweeps)

@@ -67,6 +67,11 @@ struct B200KernelBinding;      /* specialise with B200GEO_BIND_CELL */
         {                                                                               \
             B200Helpers::check(b200geo_group_step(group, KERNEL_ID, 0, first, n));      \
         }                                                                               \
+        /* one sweep over a box: current buffer -> scratch buffer, no swap */           \
+        static void updateBox(b200geo_grid *g, unsigned nanoStep, const int32_t origin[3], const int32_t dim[3]) \
+        {                                                                               \
+            B200Helpers::check(b200geo_update_box(g, KERNEL_ID, 0, nanoStep, origin, dim, 0)); \
+        }                                                                               \
         static std::vector<B200Member> members()                                        \
         {                                                                               \
             B200Member tab[] = { __VA_ARGS__ };                                         \
@@ -470,6 +475,130 @@ public:
     {
         flush();
         B200Helpers::check(b200geo_sync(0));
+    }
+
+    /* UpdateFunctor over an arbitrary Region (storage/updatefunctor.h:403-428 takes a Region, too): one sweep of
+     * the region's cells, current buffer -> scratch buffer, NO swap — one launch per box of the region
+     * (B200Helpers::mergeStreaks). What a Stepper's update1() / updateGhost() do to inner sets and rims
+     * (parallelization/nesting/vanillastepper.h:93-225). Returns the number of launches. */
+    std::size_t updateRegion(const Region<DIM>& region, unsigned nanoStep)
+    {
+        flush();
+        rowCacheValid = false;
+        B200Helpers::check(b200geo_refresh_ghosts(handle, 0));
+        std::vector<B200Helpers::StreakBox> boxes = B200Helpers::mergeStreaks<DIM>(region.beginStreak(), region.endStreak(), box.origin);
+        for (std::size_t k = 0; k < boxes.size(); ++k) {
+            B200KernelBinding<CELL>::updateBox(handle, nanoStep, boxes[k].origin, boxes[k].dim);
+        }
+        return boxes.size();
+    }
+
+    /* the scratch buffer becomes the current one (swap(oldGrid, newGrid)) */
+    void swapBuffers()
+    {
+        flush();
+        rowCacheValid = false;
+        B200Helpers::check(b200geo_swap(handle));
+    }
+
+    /* region <-> a member-major buffer in DEVICE memory (b200geo_device_alloc): patch buffers that never leave the GPU */
+    void saveRegionToDevice(void *deviceBuffer, const Region<DIM>& region) const
+    {
+        flush();
+        std::vector<int32_t> streaks = flatten(region, Coord<DIM>());
+        B200Helpers::check(b200geo_grid_save_region(handle, streaks.data(), (int)(streaks.size() / 4), deviceBuffer, B200GEO_CUDA_DEVICE, 0));
+    }
+
+    void loadRegionFromDevice(const void *deviceBuffer, const Region<DIM>& region)
+    {
+        flush();
+        rowCacheValid = false;
+        std::vector<int32_t> streaks = flatten(region, Coord<DIM>());
+        /* the current buffer only: a Stepper's two grids differ on purpose */
+        B200Helpers::check(b200geo_grid_load_region(handle, streaks.data(), (int)(streaks.size() / 4), deviceBuffer, B200GEO_CUDA_DEVICE, 0, 0));
+    }
+
+    /* GridBase::saveRegion / loadRegion for AoS buffers (std::vector<CELL>, storage/gridbase.h:157-180): what
+     * SerializationBuffer selects for cells without an SoA registration (storage/serializationbuffer.h:20-57) */
+    virtual void saveRegion(std::vector<CELL> *buffer, const Region<DIM>& region, const Coord<DIM>& offset = Coord<DIM>()) const
+    {
+        flush();
+        std::vector<int32_t> streaks = flatten(region, offset);
+        const std::size_t n = region.size();
+        buffer->resize(n);
+        if (n == 0) {
+            return;
+        }
+        if (cellIsItsOnlyMember()) {
+            B200Helpers::check(b200geo_grid_save_region(handle, streaks.data(), (int)(streaks.size() / 4), buffer->data(), B200GEO_HOST, 0));
+            B200Helpers::check(b200geo_sync(0));
+            return;
+        }
+        std::vector<char> raw(n * cellBytes);
+        B200Helpers::check(b200geo_grid_save_region(handle, streaks.data(), (int)(streaks.size() / 4), raw.data(), B200GEO_HOST, 0));
+        B200Helpers::check(b200geo_sync(0));
+        std::size_t off = 0;
+        for (std::size_t m = 0; m < members.size(); ++m) {
+            const std::size_t bytes = members[m].bytes, at = members[m].offsetInCell;
+            for (std::size_t i = 0; i < n; ++i) {
+                std::memcpy(reinterpret_cast<char*>(&(*buffer)[i]) + at, &raw[off + i * bytes], bytes);
+            }
+            off += n * bytes;
+        }
+    }
+
+    virtual void loadRegion(const std::vector<CELL>& buffer, const Region<DIM>& region, const Coord<DIM>& offset = Coord<DIM>())
+    {
+        loadRegionCells(buffer, region, offset, 1);
+    }
+
+    /* both = 0: the current buffer only */
+    void loadRegionCells(const std::vector<CELL>& buffer, const Region<DIM>& region, const Coord<DIM>& offset, int both)
+    {
+        if (buffer.size() != region.size()) {
+            throw std::invalid_argument("buffer size does not match region");
+        }
+        flush();
+        rowCacheValid = false;
+        const std::size_t n = region.size();
+        if (n == 0) {
+            return;
+        }
+        std::vector<int32_t> streaks = flatten(region, offset);
+        if (cellIsItsOnlyMember()) {
+            B200Helpers::check(b200geo_grid_load_region(handle, streaks.data(), (int)(streaks.size() / 4), buffer.data(), B200GEO_HOST, both, 0));
+            B200Helpers::check(b200geo_sync(0));
+            return;
+        }
+        std::vector<char> raw(n * cellBytes);
+        std::size_t off = 0;
+        for (std::size_t m = 0; m < members.size(); ++m) {
+            const std::size_t bytes = members[m].bytes, at = members[m].offsetInCell;
+            for (std::size_t i = 0; i < n; ++i) {
+                std::memcpy(&raw[off + i * bytes], reinterpret_cast<const char*>(&buffer[i]) + at, bytes);
+            }
+            off += n * bytes;
+        }
+        B200Helpers::check(b200geo_grid_load_region(handle, streaks.data(), (int)(streaks.size() / 4), raw.data(), B200GEO_HOST, both, 0));
+        B200Helpers::check(b200geo_sync(0));
+    }
+
+    /* the char-buffer twin of loadRegionCells */
+    void loadRegionBytes(const std::vector<char>& buffer, const Region<DIM>& region, const Coord<DIM>& offset, int both)
+    {
+        if (buffer.size() != region.size() * cellBytes) {
+            throw std::invalid_argument("buffer size does not match region");
+        }
+        flush();
+        rowCacheValid = false;
+        std::vector<int32_t> streaks = flatten(region, offset);
+        B200Helpers::check(b200geo_grid_load_region(handle, streaks.data(), (int)(streaks.size() / 4), buffer.data(), B200GEO_HOST, both, 0));
+        B200Helpers::check(b200geo_sync(0));
+    }
+
+    int deviceIndex() const
+    {
+        return device;
     }
 
     /* the device grid was changed behind this object's back (slab group stepping): drop cached rows */

@@ -10,7 +10,7 @@
 
 namespace b200geo {
 
-static const Tuning g_tuning_default = {0, -1, 0, 128, 0, 33, 0, 4, 0, 0, -1, 1, 3, 0, 0};
+static const Tuning g_tuning_default = {0, -1, 0, 128, 0, 33, 0, 4, 0, 3, -1, 1, 0, 0, 0};
 Tuning g_tuning = g_tuning_default;
 static thread_local std::string g_last_error;
 static std::atomic<uint64_t> g_launches(0);
@@ -644,6 +644,27 @@ int b200geo_refresh_ghosts(b200geo_grid *g, void *stream)
 int b200geo_sync(void *stream)
 {
     B200GEO_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    return B200GEO_OK;
+}
+
+int b200geo_device_alloc(int device, uint64_t bytes, void **ptr)
+{
+    if (!ptr) return fail(B200GEO_ERR_INVALID, "null argument");
+    *ptr = 0;
+    B200GEO_CUDA(cudaSetDevice(device));
+    cudaError_t e = cudaMalloc(ptr, bytes ? (size_t)bytes : 1);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(B200GEO_ERR_NOMEM, std::string("cudaMalloc failed: ") + cudaGetErrorString(e));
+    }
+    return B200GEO_OK;
+}
+
+int b200geo_device_free(int device, void *ptr)
+{
+    if (!ptr) return B200GEO_OK;
+    B200GEO_CUDA(cudaSetDevice(device));
+    B200GEO_CUDA(cudaFree(ptr));
     return B200GEO_OK;
 }
 

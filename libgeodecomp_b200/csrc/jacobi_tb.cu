@@ -403,7 +403,8 @@ int launch_tb(b200geo_grid *g, const Box& box, const Limits& lim, double edge, c
     int gy = (box.y1 - box.y0 + (TY - 2 * T) - 1) / (TY - 2 * T);
     int nz = box.z1 - box.z0;
     // long z chunks amortise the 2T warm-up planes; enough chunks to fill the machine several times over
-    int zchunk = g_tuning.jacobi_tb_zchunk > 0 ? g_tuning.jacobi_tb_zchunk : 128;
+    // (deeper blocking warms up on more planes per chunk: 256 planes measured 1.3 % faster than 128 for T = 4, profiles/r3d)
+    int zchunk = g_tuning.jacobi_tb_zchunk > 0 ? g_tuning.jacobi_tb_zchunk : (T >= 3 ? 256 : 128);
     while (zchunk > 16 && (int64_t)gx * gy * ((nz + zchunk - 1) / zchunk) < 148 * 6) zchunk /= 2;
     dim3 grid((unsigned)(gx * gy), 1, (nz + zchunk - 1) / zchunk);
     if ((int64_t)gx * gy > 0x7fffffff || grid.z > 65535) return fail(B200GEO_ERR_OUT_OF_RANGE, "grid dimension too large");

@@ -26,6 +26,8 @@
 #include <iostream>
 
 #include <libgeodecomp_b200/b200stripingsimulator.h>
+#include <libgeodecomp_b200/b200stepper.h>
+#include <libgeodecomp/geometry/partitions/stripingpartition.h>
 
 #include "models/lbm_aos.h"
 
@@ -481,6 +483,51 @@ static void benchGeneric(const char *name, const Coord<DIM>& dim, unsigned steps
                 name, cells, steps, ms / (steps * APITraits::SelectNanoSteps<CELL>::VALUE), glups, glups * bytesPerUpdate);
 }
 
+/* The reference's stepper test on B200Stepper, with its own TestCell (unbound: the generic device path) —
+ * parallelization/nesting/test/parallel_mpi_1/vanillastepperregiontest.h:48-124: a 17 x 12 space, a StripingPartition
+ * with ragged weights, this process as rank 1 of 3, ghost zone width 3; after n calls of update1() the cells of
+ * innerSet(n) must be valid TestCells of cycle n (TS_ASSERT_TEST_GRID_REGION, misc/testhelper.h:146-180). 3-D likewise. */
+template<typename CELL, int DIM>
+static void stepperRegionTest(const char *name, const Coord<DIM>& dim, const std::vector<std::size_t>& weights, unsigned ghostZoneWidth)
+{
+    typedef typename APITraits::SelectTopology<CELL>::Value Topology;
+    typedef B200Stepper<CELL> StepperType;
+    typedef typename StepperType::GridType GridType;
+    typename SharedPtr<TestInitializer<CELL> >::Type init(new TestInitializer<CELL>(dim));
+    CoordBox<DIM> rect = init->gridBox();
+    typename SharedPtr<Partition<DIM> >::Type partition(new StripingPartition<DIM>(Coord<DIM>(), rect.dimensions, 0, weights));
+    typename SharedPtr<AdjacencyManufacturer<DIM> >::Type adjacency(new DummyAdjacencyManufacturer<DIM>);
+    typename SharedPtr<PartitionManager<Topology> >::Type manager(new PartitionManager<Topology>());
+    manager->resetRegions(adjacency, rect, partition, 1, ghostZoneWidth);
+    std::vector<CoordBox<DIM> > boundingBoxes, expandedBoundingBoxes;
+    for (int i = 0; i < 3; ++i) {
+        Region<DIM> region = partition->getRegion(i);
+        boundingBoxes.push_back(region.boundingBox());
+        expandedBoundingBoxes.push_back(region.expandWithTopology(ghostZoneWidth, rect.dimensions, Topology()).boundingBox());
+    }
+    manager->resetGhostZones(boundingBoxes, expandedBoundingBoxes);
+    StepperType stepper(manager, init);
+    long bad = 0, checked = 0;
+    for (unsigned n = 0; n < ghostZoneWidth; ++n) {
+        if (n > 0) {
+            stepper.update1();
+        }
+        const GridType& grid = stepper.grid();
+        CHECK(grid.getEdge().edgeCell() && grid.getEdge().valid());
+        unsigned expectedCycle = n * APITraits::SelectNanoSteps<CELL>::VALUE / APITraits::SelectNanoSteps<CELL>::VALUE;
+        const Region<DIM>& region = manager->innerSet(n);
+        for (typename Region<DIM>::Iterator i = region.begin(); i != region.end(); ++i) {
+            CELL cell = grid.get(*i);
+            bad += !(cell.valid() && !cell.edgeCell() && cell.cycleCounter == n);
+            ++checked;
+        }
+        (void)expectedCycle;
+    }
+    CHECK(bad == 0 && checked > 0);
+    std::printf("B200Stepper<%s> as rank 1 of 3, ghost zone width %u: %ld of %ld inner set cells wrong after update1() x 0..%u, %zu launches\n",
+                name, ghostZoneWidth, bad, checked, ghostZoneWidth - 1, stepper.launchCount());
+}
+
 int main(int argc, char **argv)
 {
     if (argc > 1 && std::string(argv[1]) == "--bench") {
@@ -508,6 +555,15 @@ int main(int argc, char **argv)
         testCellSuite<TestCell3dCube, 3>("TestCell 3d Cube", Coord<3>(50, 20, 10), 5);
         testCellSuite<TestCell3dTorus, 3>("TestCell 3d Torus", Coord<3>(30, 20, 10), 5);
         testCellSuite<TestCell3dMooreCube, 3>("TestCell 3d Moore Cube", Coord<3>(13, 12, 11), 4);
+
+        {
+            std::vector<std::size_t> w2(3), w3(3);
+            w2[0] = 4 * 17 + 7; w2[1] = 2 * 17 - 1; w2[2] = 12 * 17 - w2[0] - w2[1];        // the reference test's weights
+            stepperRegionTest<TestCell2dCube, 2>("TestCell 2d Cube", Coord<2>(17, 12), w2, 3);
+            w3[0] = 3 * 66 + 2 * 11 + 5; w3[1] = 3 * 66 + 3 * 11 - 2; w3[2] = 11 * 6 * 10 - w3[0] - w3[1];
+            stepperRegionTest<TestCell3dCube, 3>("TestCell 3d Cube", Coord<3>(11, 6, 10), w3, 2);
+            stepperRegionTest<TestCell3dMooreCube, 3>("TestCell 3d Moore Cube", Coord<3>(11, 6, 10), w3, 3);
+        }
 
         compareWithSerialSimulator<LifeCell, 2>("LifeCell (Coord<2>)", Coord<2>(150, 67), 30);
         compareWithSerialSimulator<HeatCell, 2>("HeatCell (stale member)", Coord<2>(97, 41), 23);

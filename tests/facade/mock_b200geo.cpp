@@ -9,6 +9,7 @@
 #include "../../include/b200geo.h"
 #include "../../oracle/oracle.h"
 
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -348,8 +349,75 @@ int b200geo_step(b200geo_grid *g, int kernel, const void *, uint32_t, uint32_t n
     return B200GEO_OK;
 }
 
-int b200geo_update_box(b200geo_grid *, int, const void *, uint32_t, const int32_t *, const int32_t *, void *) { return fail(B200GEO_ERR_LOGIC, "not in the mock"); }
-int b200geo_update_box_n(b200geo_grid *, int, const void *, uint32_t, const int32_t *, const int32_t *, uint32_t, void *) { return fail(B200GEO_ERR_LOGIC, "not in the mock"); }
+// n sweeps over the box [o, o + d): current buffer -> scratch buffer, no swap. The oracle runs on the box plus a ring of
+// n cells (ghost cells included: they are real cells of the padded arrays), only the box is written back.
+int b200geo_update_box_n(b200geo_grid *g, int kernel, const void *, uint32_t, const int32_t *o, const int32_t *d, uint32_t n_sweeps, void *)
+{
+    const int n = (int)n_sweeps;
+    if (n < 1) return fail(B200GEO_ERR_INVALID, "n_sweeps must be >= 1");
+    if (d[0] <= 0 || d[1] <= 0 || d[2] <= 0) return B200GEO_OK;
+    int lo[3], hi[3];
+    for (int i = 0; i < 3; ++i) {
+        const bool used = g->d[i] > 1 || g->g[i] > 0;
+        lo[i] = o[i] - (used ? n : 0);
+        hi[i] = o[i] + d[i] + (used ? n : 0);
+        if (lo[i] < -g->g[i] || hi[i] > g->d[i] + g->g[i]) return fail(B200GEO_ERR_INVALID, "box outside the updatable area");
+    }
+    const int ex = hi[0] - lo[0], ey = hi[1] - lo[1], ez = hi[2] - lo[2];
+    const size_t cells = (size_t)ex * ey * ez;
+    std::vector<char> in(cells * g->cell_bytes), out;
+    size_t off = 0;
+    for (int m = 0; m < g->n; ++m) {
+        const int e = g->elem[m];
+        for (int z = 0; z < ez; ++z)
+            for (int y = 0; y < ey; ++y)
+                memcpy(&in[off + (((size_t)z * ey + y) * ex) * e], &g->ptr[g->cur][m][g->index(lo[0], lo[1] + y, lo[2] + z) * e], (size_t)ex * e);
+        off += cells * e;
+    }
+    // the window's own boundary is never a topological one here: periodic images are cells of the ghost ring
+    b200geo_grid cube = *g;
+    for (int i = 0; i < 3; ++i) cube.desc.ghost_mode[i][0] = cube.desc.ghost_mode[i][1] = B200GEO_GHOST_EDGE;
+    for (int sweep = 0; sweep < n; ++sweep) {
+        int rc = oracle_sweeps(&cube, kernel, ex, ey, ez, 1, in, out);
+        if (rc) return rc < 0 ? rc : fail(B200GEO_ERR_INVALID, "oracle failed");
+        // cells of the constant edge ring (EDGE sides) inside the window never change
+        off = 0;
+        for (int m = 0; m < g->n; ++m) {
+            const int e = g->elem[m];
+            for (int z = 0; z < ez; ++z)
+                for (int y = 0; y < ey; ++y)
+                    for (int x = 0; x < ex; ++x) {
+                        const int c[3] = {lo[0] + x, lo[1] + y, lo[2] + z};
+                        bool is_edge = false;
+                        for (int i = 0; i < 3; ++i) {
+                            if (c[i] < 0 && g->desc.ghost_mode[i][0] == B200GEO_GHOST_EDGE) is_edge = true;
+                            if (c[i] >= g->d[i] && g->desc.ghost_mode[i][1] == B200GEO_GHOST_EDGE) is_edge = true;
+                        }
+                        if (is_edge) {
+                            const size_t at = off + (((size_t)z * ey + y) * ex + x) * e;
+                            memcpy(&out[at], &in[at], e);
+                        }
+                    }
+            off += cells * e;
+        }
+        if (sweep + 1 < n) in.swap(out);
+    }
+    off = 0;
+    for (int m = 0; m < g->n; ++m) {
+        const int e = g->elem[m];
+        for (int z = 0; z < d[2]; ++z)
+            for (int y = 0; y < d[1]; ++y)
+                memcpy(&g->ptr[g->cur ^ 1][m][g->index(o[0], o[1] + y, o[2] + z) * e],
+                       &out[off + (((size_t)(z + o[2] - lo[2]) * ey + (y + o[1] - lo[1])) * ex + (o[0] - lo[0])) * e], (size_t)d[0] * e);
+        off += cells * e;
+    }
+    return B200GEO_OK;
+}
+
+int b200geo_update_box(b200geo_grid *g, int kernel, const void *params, uint32_t nano, const int32_t *o, const int32_t *d, void *stream)
+{
+    return b200geo_update_box_n(g, kernel, params, nano, o, d, 1, stream);
+}
 int b200geo_swap(b200geo_grid *g) { g->cur ^= 1; return B200GEO_OK; }
 // periodic images of WRAP axes in the current buffer, axis by axis (x first, so that corners end up right)
 int b200geo_refresh_ghosts(b200geo_grid *g, void *)
@@ -373,6 +441,8 @@ int b200geo_refresh_ghosts(b200geo_grid *g, void *)
     return B200GEO_OK;
 }
 int b200geo_sync(void *) { return B200GEO_OK; }
+int b200geo_device_alloc(int, uint64_t bytes, void **ptr) { *ptr = malloc(bytes ? (size_t)bytes : 1); return *ptr ? B200GEO_OK : fail(B200GEO_ERR_NOMEM, "out of memory"); }
+int b200geo_device_free(int, void *ptr) { free(ptr); return B200GEO_OK; }
 int b200geo_halo_block(const b200geo_grid *, int, int, int, int, void **, uint64_t *) { return fail(B200GEO_ERR_LOGIC, "not in the mock"); }
 int b200geo_halo_block_in(const b200geo_grid *, int, int, int, int, int, void **, uint64_t *) { return fail(B200GEO_ERR_LOGIC, "not in the mock"); }
 int b200geo_grid_ipc_export(const b200geo_grid *, int, void *) { return fail(B200GEO_ERR_LOGIC, "not in the mock"); }

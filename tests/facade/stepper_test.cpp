@@ -1,0 +1,271 @@
+/* B200Stepper (include/libgeodecomp_b200/b200stepper.h) beside the reference's VanillaStepper, set up the way the
+ * reference tests its steppers (parallelization/nesting/test/parallel_mpi_1/vanillastepperregiontest.h:48-88): a
+ * hand-built PartitionManager that makes this process "rank 1 of 3" of a StripingPartition with ragged weights
+ * (region borders in the middle of rows), no MPI anywhere. Both steppers get
+ *   - a ghost zone PatchProvider that hands them the neighbours' cells of the outer ghost zone at every
+ *     synchronisation point — taken from a SerialSimulator run of the WHOLE simulation space, i.e. what real
+ *     neighbours would send;
+ *   - a ghost zone PatchAccepter and an inner set PatchAccepter that record what the stepper hands out.
+ * After every update1() the stepper's grid must equal the whole-space run on the inner set that is valid at that
+ * nano step (vanillastepperregiontest.h:114-124 checks exactly those sets), the records of the two steppers must be
+ * identical, and B200Stepper must have moved regions between host and device only when a patch was due.
+ * Ghost zone widths 1-4, 2-D (Game of Life) and 3-D (Jacobi 7- and 27-point).
+ * Linked against libb200geo.so (GPU box) or tests/facade/mock_b200geo.cpp (CPU suite). */
+#include <libgeodecomp/geometry/partitionmanager.h>
+#include <libgeodecomp/geometry/partitions/stripingpartition.h>
+#include <libgeodecomp/parallelization/nesting/vanillastepper.h>
+#include <libgeodecomp/storage/patchaccepter.h>
+#include <libgeodecomp/storage/patchprovider.h>
+
+#include <libgeodecomp_b200/b200stepper.h>
+
+#include "fixtures.h"
+
+/* one patch a stepper handed to an accepter */
+template<typename CELL>
+struct Record {
+    std::size_t nanoStep;
+    std::size_t cells;
+    std::vector<CELL> data;
+};
+
+template<typename GRID>
+class RecordingAccepter : public PatchAccepter<GRID>
+{
+public:
+    typedef typename GRID::CellType CELL;
+    static const int DIM = GRID::DIM;
+    using PatchAccepter<GRID>::requestedNanoSteps;
+    using PatchAccepter<GRID>::pushRequest;
+
+    RecordingAccepter(std::size_t first, std::size_t stride, std::size_t last)
+    {
+        for (std::size_t s = first; s <= last; s += stride) {
+            pushRequest(s);
+        }
+    }
+
+    virtual void put(const GRID& grid, const Region<DIM>& validRegion, const Coord<DIM>&, const std::size_t nanoStep, const std::size_t)
+    {
+        if (!this->checkNanoStepPut(nanoStep)) {
+            return;
+        }
+        Record<CELL> r;
+        r.nanoStep = nanoStep;
+        r.cells = validRegion.size();
+        for (typename Region<DIM>::Iterator i = validRegion.begin(); i != validRegion.end(); ++i) {
+            r.data.push_back(grid.get(*i));
+        }
+        records.push_back(r);
+        requestedNanoSteps.erase(requestedNanoSteps.begin());
+    }
+
+    std::vector<Record<CELL> > records;
+};
+
+/* the neighbours: cells of the outer ghost zone out of the whole-space run */
+template<typename GRID, typename CELL>
+class NeighbourProvider : public PatchProvider<GRID>
+{
+public:
+    static const int DIM = GRID::DIM;
+    using PatchProvider<GRID>::storedNanoSteps;
+
+    NeighbourProvider(const std::vector<std::vector<CELL> > *history, const CoordBox<DIM>& box, const Region<DIM>& outerGhost,
+                      std::size_t first, std::size_t stride, std::size_t last) :
+        history(history), box(box), outerGhost(outerGhost)
+    {
+        for (std::size_t s = first; s <= last; s += stride) {
+            storedNanoSteps.insert(s);
+        }
+    }
+
+    virtual void get(GRID *grid, const Region<DIM>& patchableRegion, const Coord<DIM>&, const std::size_t nanoStep, const std::size_t, const bool remove = true)
+    {
+        this->checkNanoStepGet(nanoStep);
+        Region<DIM> region = outerGhost & patchableRegion;
+        for (typename Region<DIM>::Iterator i = region.begin(); i != region.end(); ++i) {
+            grid->set(*i, (*history)[nanoStep][(*i - box.origin).toIndex(box.dimensions)]);
+        }
+        if (remove) {
+            storedNanoSteps.erase(storedNanoSteps.begin());
+        }
+    }
+
+private:
+    const std::vector<std::vector<CELL> > *history;
+    CoordBox<DIM> box;
+    Region<DIM> outerGhost;
+};
+
+template<int DIM> struct Weights;
+template<> struct Weights<2> {
+    /* vanillastepperregiontest.h:57-61: 4 rows + 7 cells | 2 rows - 1 cell | the rest */
+    static std::vector<std::size_t> make(const Coord<2>& dim)
+    {
+        std::vector<std::size_t> w(3);
+        w[0] = 4 * dim.x() + 7;
+        w[1] = 2 * dim.x() - 1 + (dim.y() > 12 ? (dim.y() - 12) / 2 * dim.x() : 0);
+        w[2] = dim.prod() - w[0] - w[1];
+        return w;
+    }
+};
+template<> struct Weights<3> {
+    static std::vector<std::size_t> make(const Coord<3>& dim)
+    {
+        std::vector<std::size_t> w(3);
+        std::size_t plane = (std::size_t)dim.x() * dim.y();
+        w[0] = (dim.z() / 3) * plane + 2 * dim.x() + 5;       /* ends in the middle of a row */
+        w[1] = (dim.z() / 3) * plane + 3 * dim.x() - 2;
+        w[2] = dim.prod() - w[0] - w[1];
+        return w;
+    }
+};
+
+template<typename CELL>
+static void runCase(const char *name, const Coord<APITraits::SelectTopology<CELL>::Value::DIM>& dim, unsigned ghostZoneWidth, unsigned steps)
+{
+    typedef typename APITraits::SelectTopology<CELL>::Value Topology;
+    const int DIM = Topology::DIM;
+    typedef VanillaStepper<CELL, UpdateFunctorHelpers::ConcurrencyNoP> Reference;
+    typedef B200Stepper<CELL> Device;
+    typedef typename Reference::GridType GridType;
+
+    /* the whole-space run: history[t] = every cell at nano step t */
+    CoordBox<DIM> box(Coord<DIM>(), dim);
+    std::vector<std::vector<CELL> > history;
+    {
+        SerialSimulator<CELL> whole(new SeededInitializer<CELL>(dim, steps + 2 * ghostZoneWidth));
+        for (unsigned t = 0; t <= steps + 2 * ghostZoneWidth; ++t) {
+            std::vector<CELL> now;
+            for (typename CoordBox<DIM>::Iterator i = box.begin(); i != box.end(); ++i) {
+                now.push_back(whole.getGrid()->get(*i));
+            }
+            history.push_back(now);
+            whole.step();
+        }
+    }
+
+    struct Setup {
+        typename SharedPtr<PartitionManager<Topology> >::Type manager;
+        typename SharedPtr<SeededInitializer<CELL> >::Type init;
+        typename SharedPtr<RecordingAccepter<GridType> >::Type ghostAccepter, innerAccepter;
+        typename SharedPtr<NeighbourProvider<GridType, CELL> >::Type provider;
+    };
+    Setup setups[2];
+    const std::size_t last = steps + 2 * ghostZoneWidth;
+    for (int s = 0; s < 2; ++s) {
+        Setup& u = setups[s];
+        u.init.reset(new SeededInitializer<CELL>(dim, last));
+        typename SharedPtr<Partition<DIM> >::Type partition(new StripingPartition<DIM>(Coord<DIM>(), dim, 0, Weights<DIM>::make(dim)));
+        typename SharedPtr<AdjacencyManufacturer<DIM> >::Type adjacency(new DummyAdjacencyManufacturer<DIM>);
+        u.manager.reset(new PartitionManager<Topology>());
+        u.manager->resetRegions(adjacency, box, partition, 1, ghostZoneWidth);
+        std::vector<CoordBox<DIM> > boundingBoxes, expandedBoundingBoxes;
+        for (int i = 0; i < 3; ++i) {
+            Region<DIM> region = partition->getRegion(i);
+            boundingBoxes.push_back(region.boundingBox());
+            expandedBoundingBoxes.push_back(region.expandWithTopology(ghostZoneWidth, dim, Topology()).boundingBox());
+        }
+        u.manager->resetGhostZones(boundingBoxes, expandedBoundingBoxes);
+        /* synchronisation points as UpdateGroup charges its PatchLinks: ghostZoneWidth, 2 * ghostZoneWidth, ... */
+        u.ghostAccepter.reset(new RecordingAccepter<GridType>(ghostZoneWidth, ghostZoneWidth, last));
+        u.innerAccepter.reset(new RecordingAccepter<GridType>(3, 3, last));     /* a writer with period 3 */
+        u.provider.reset(new NeighbourProvider<GridType, CELL>(&history, box, u.manager->getOuterRim(), ghostZoneWidth, ghostZoneWidth, last));
+    }
+
+    typename Reference::PatchAccepterVec ghostAccepters[2], innerAccepters[2];
+    typename Reference::PatchProviderVec providers[2];
+    for (int s = 0; s < 2; ++s) {
+        ghostAccepters[s].push_back(setups[s].ghostAccepter);
+        innerAccepters[s].push_back(setups[s].innerAccepter);
+        providers[s].push_back(setups[s].provider);
+    }
+    Reference reference(setups[0].manager, setups[0].init, ghostAccepters[0], innerAccepters[0], providers[0]);
+    Device device(setups[1].manager, setups[1].init, ghostAccepters[1], innerAccepters[1], providers[1]);
+
+    long wrongVsWhole = 0, wrongVsReference = 0;
+    std::size_t pullsWithoutPatch = 0;
+    for (unsigned t = 1; t <= steps; ++t) {
+        std::size_t pullsBefore = device.pullCount(), recordsBefore = setups[1].ghostAccepter->records.size() + setups[1].innerAccepter->records.size();
+        std::size_t providerBefore = setups[1].provider->nextAvailableNanoStep();
+        reference.update(1);
+        device.update(1);
+        bool patchDue = setups[1].ghostAccepter->records.size() + setups[1].innerAccepter->records.size() != recordsBefore ||
+                        setups[1].provider->nextAvailableNanoStep() != providerBefore;
+        if (!patchDue && device.pullCount() != pullsBefore) {
+            ++pullsWithoutPatch;
+        }
+        CHECK(device.currentStep() == reference.currentStep());
+        /* the inner set that is valid now: shrunk by the nano steps since the last synchronisation */
+        unsigned shrink = t % ghostZoneWidth;
+        const Region<DIM>& valid = setups[0].manager->innerSet(shrink);
+        const GridType& want = reference.grid();
+        const GridType& got = device.grid();
+        for (typename Region<DIM>::Iterator i = valid.begin(); i != valid.end(); ++i) {
+            CELL g = got.get(*i);
+            if (!(g == want.get(*i))) ++wrongVsReference;
+            if (!(g == history[t][(*i - box.origin).toIndex(box.dimensions)])) ++wrongVsWhole;
+        }
+    }
+    CHECK(wrongVsWhole == 0);
+    CHECK(wrongVsReference == 0);
+    CHECK(pullsWithoutPatch == 0);
+
+    bool sameRecords = true;
+    std::size_t patches = 0;
+    for (int which = 0; which < 2; ++which) {
+        const std::vector<Record<CELL> >& a = which ? setups[0].innerAccepter->records : setups[0].ghostAccepter->records;
+        const std::vector<Record<CELL> >& b = which ? setups[1].innerAccepter->records : setups[1].ghostAccepter->records;
+        sameRecords &= a.size() == b.size() && !a.empty();
+        for (std::size_t k = 0; sameRecords && k < a.size(); ++k) {
+            sameRecords &= a[k].nanoStep == b[k].nanoStep && a[k].cells == b[k].cells && a[k].data.size() == b[k].data.size();
+            for (std::size_t c = 0; sameRecords && c < a[k].data.size(); ++c) {
+                sameRecords &= a[k].data[c] == b[k].data[c];
+            }
+            ++patches;
+        }
+    }
+    CHECK(sameRecords);
+    std::printf("%-13s ghost zone width %u, %u nano steps as rank 1 of 3: %ld / %ld cells differ from the whole-space run / VanillaStepper, "
+                "%zu patches %s, %zu launches, %zu pulls, %zu pushes\n",
+                name, ghostZoneWidth, steps, wrongVsWhole, wrongVsReference, patches, sameRecords ? "identical" : "DIFFERENT",
+                device.launchCount(), device.pullCount(), device.pushCount());
+}
+
+int main()
+{
+    try {
+        for (unsigned width = 1; width <= 4; ++width) {
+            runCase<ConwayCube>("ConwayCube", Coord<2>(17, 12), width, 9);        /* the reference test's 17 x 12 space */
+            runCase<Jacobi7Cube>("Jacobi7Cube", Coord<3>(11, 7, 13), width, 9);
+        }
+        runCase<Jacobi27Cube>("Jacobi27Cube", Coord<3>(9, 8, 14), 3, 8);
+        runCase<ConwayCube>("ConwayCube", Coord<2>(40, 30), 2, 7);
+        /* a Torus cell is refused */
+        bool refused = false;
+        try {
+            typedef Topologies::Torus<3>::Topology Topology;
+            SharedPtr<PartitionManager<Topology> >::Type manager(new PartitionManager<Topology>());
+            SharedPtr<SeededInitializer<Jacobi7Torus> >::Type init(new SeededInitializer<Jacobi7Torus>(Coord<3>(8, 8, 8), 2));
+            SharedPtr<Partition<3> >::Type partition(new StripingPartition<3>(Coord<3>(), Coord<3>(8, 8, 8), 0, std::vector<std::size_t>(1, 512)));
+            SharedPtr<AdjacencyManufacturer<3> >::Type adjacency(new DummyAdjacencyManufacturer<3>);
+            manager->resetRegions(adjacency, CoordBox<3>(Coord<3>(), Coord<3>(8, 8, 8)), partition, 0, 1);
+            manager->resetGhostZones(std::vector<CoordBox<3> >(1, CoordBox<3>(Coord<3>(), Coord<3>(8, 8, 8))),
+                                     std::vector<CoordBox<3> >(1, CoordBox<3>(Coord<3>(), Coord<3>(8, 8, 8))));
+            B200Stepper<Jacobi7Torus> stepper(manager, init);
+        } catch (const std::logic_error&) {
+            refused = true;
+        }
+        CHECK(refused);
+    } catch (const std::exception& e) {
+        std::printf("FAILED with exception: %s\n", e.what());
+        return 2;
+    }
+    if (failures) {
+        std::printf("%d check(s) FAILED\n", failures);
+        return 1;
+    }
+    std::printf("stepper_test: all checks passed\n");
+    return 0;
+}

@@ -6,7 +6,9 @@ exception mapping), B200StripedGrid / B200StripedBoxGrid (routing across slabs, 
 B200Simulator / B200StripingSimulator (event protocol against the reference's MockWriter / MockSteerer, step fusing,
 Steerer writes), the reference's SerialBOVWriter on both — each case beside the reference's SerialSimulator in the same
 process; generic_soa_host_test.cpp: the generic SoA path (b200genericsoa.h) with its kernel body run in a host loop —
-member table derived from LibFlatArray's generated accessors, stride dispatch, hood arithmetic over EDGE / WRAP ghosts. The kernels and the halo schedule themselves are GPU-tested (tests/test_facade_gpu.py)."""
+member table derived from LibFlatArray's generated accessors, stride dispatch, hood arithmetic over EDGE / WRAP ghosts;
+stepper_test.cpp: B200Stepper beside the reference's VanillaStepper as rank 1 of 3 of a ragged StripingPartition (the set-up
+of parallelization/nesting/test/parallel_mpi_1/vanillastepperregiontest.h), ghost zone widths 1-4. The kernels and the halo schedule themselves are GPU-tested (tests/test_facade_gpu.py)."""
 import os
 import subprocess
 
@@ -15,7 +17,7 @@ import pytest
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-@pytest.mark.parametrize("name", ["facade_test_cpu", "striping_test_cpu", "host_logic_test_cpu", "generic_soa_host_test_cpu"])
+@pytest.mark.parametrize("name", ["facade_test_cpu", "striping_test_cpu", "host_logic_test_cpu", "generic_soa_host_test_cpu", "stepper_test_cpu"])
 def test_cpp_facade_host_logic_on_the_mock_engine(name):
     binary = os.path.join(HERE, "facade", "_bin", name)
     if not os.access(binary, os.X_OK):

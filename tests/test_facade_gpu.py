@@ -107,7 +107,24 @@ def test_uniform_element_layout_round_trip():
         assert np.array_equal(want[1:-1, 1:-1, 1:-1], data[m])
 
 
+STEPPER_BIN = os.path.join(HERE, "facade", "_bin", "stepper_test")
+
+
+@pytest.mark.gpu
+def test_b200_stepper_beside_vanilla_stepper():
+    """tests/facade/stepper_test.cpp: B200Stepper as rank 1 of 3 of a ragged StripingPartition, ghost zone
+    widths 1-4, 2-D and 3-D, bit-identical to the reference's VanillaStepper and to the whole-space SerialSimulator;
+    patches handed to PatchAccepters identical. (The TestCell variant of the reference's own stepper test runs inside
+    generic_test.)"""
+    if not os.access(STEPPER_BIN, os.X_OK):
+        pytest.skip("tests/facade/_bin/stepper_test not built (needs /root/reference at build time)")
+    res = subprocess.run([STEPPER_BIN], capture_output=True, text=True, timeout=600)
+    print(res.stdout[-4000:], res.stderr[-2000:])
+    assert res.returncode == 0, res.stdout[-4000:] + res.stderr[-2000:]
+    assert "all checks passed" in res.stdout and "DIFFERENT" not in res.stdout
+
+
 def test_facade_header_has_no_oracle_dependency():
-    for name in ("b200simulator.h", "b200generic.h", "b200genericsoa.h", "b200boxgrid.h", "b200stripingsimulator.h"):
+    for name in ("b200simulator.h", "b200generic.h", "b200genericsoa.h", "b200boxgrid.h", "b200stripingsimulator.h", "b200stepper.h"):
         text = open(os.path.join(HERE, "..", "include", "libgeodecomp_b200", name)).read()
         assert "oracle" not in text

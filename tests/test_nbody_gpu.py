@@ -33,10 +33,10 @@ def run(model, counts, parts, steps):
 @pytest.fixture
 def nbody_kernel():
     """select the kernel variant ("nbody.kernel") for one test: 1 = re-bin + one-pass force kernels,
-    3 = fused re-bin / candidate-list kernel, 0 = fused kernel with per-container masks (default), 8 / 12 = the
+    3 = fused re-bin / candidate-list kernel (default), 0 = fused kernel with per-container masks, 8 / 12 = the
     default kernel with runs of 8 / 12 containers per CTA ("nbody.run")"""
     def set_(value):
-        capi.set_tuning("nbody.kernel", value if value in (1, 3) else 0)
+        capi.set_tuning("nbody.kernel", value if value in (1, 3) else 0)   # 0 / 8 / 12: the mask kernel
         capi.set_tuning("nbody.run", value if value in (8, 12) else -1)
     yield set_
     capi.set_tuning("nbody.kernel", -1)
