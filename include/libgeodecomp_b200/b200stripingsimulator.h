@@ -203,6 +203,43 @@ public:
         dirty = true;
     }
 
+    /* the AoS-buffer variants (storage/gridbase.h:157-180): streaks are ordered by the last axis first, so every
+     * slab's cells are one contiguous block of the buffer */
+    virtual void saveRegion(std::vector<CELL> *buffer, const Region<DIM>& region, const Coord<DIM>& offset = Coord<DIM>()) const
+    {
+        buffer->resize(region.size());
+        std::vector<Region<DIM> > parts = split(region, offset);
+        std::size_t before = 0;
+        std::vector<CELL> chunk;
+        for (std::size_t s = 0; s < slabs.size(); ++s) {
+            if (parts[s].size() == 0) {
+                continue;
+            }
+            slabs[s]->saveRegion(&chunk, parts[s]);
+            std::copy(chunk.begin(), chunk.end(), buffer->begin() + before);
+            before += chunk.size();
+        }
+    }
+
+    virtual void loadRegion(const std::vector<CELL>& buffer, const Region<DIM>& region, const Coord<DIM>& offset = Coord<DIM>())
+    {
+        if (buffer.size() != region.size()) {
+            throw std::invalid_argument("buffer size does not match region");
+        }
+        std::vector<Region<DIM> > parts = split(region, offset);
+        std::size_t before = 0;
+        for (std::size_t s = 0; s < slabs.size(); ++s) {
+            std::size_t count = parts[s].size();
+            if (count == 0) {
+                continue;
+            }
+            std::vector<CELL> chunk(buffer.begin() + before, buffer.begin() + before + count);
+            slabs[s]->loadRegion(chunk, parts[s]);
+            before += count;
+        }
+        dirty = true;
+    }
+
     /* sweeps x { update every slab; swap } with the halo exchanges they need */
     void update(unsigned firstNanoStep, unsigned sweeps)
     {

@@ -558,11 +558,13 @@ int main(int argc, char **argv)
 
         {
             std::vector<std::size_t> w2(3), w3(3);
-            w2[0] = 4 * 17 + 7; w2[1] = 2 * 17 - 1; w2[2] = 12 * 17 - w2[0] - w2[1];        // the reference test's weights
-            stepperRegionTest<TestCell2dCube, 2>("TestCell 2d Cube", Coord<2>(17, 12), w2, 3);
-            w3[0] = 3 * 66 + 2 * 11 + 5; w3[1] = 3 * 66 + 3 * 11 - 2; w3[2] = 11 * 6 * 10 - w3[0] - w3[1];
-            stepperRegionTest<TestCell3dCube, 3>("TestCell 3d Cube", Coord<3>(11, 6, 10), w3, 2);
-            stepperRegionTest<TestCell3dMooreCube, 3>("TestCell 3d Moore Cube", Coord<3>(11, 6, 10), w3, 3);
+            // the reference test's weights give rank 1 two rows: with ghost zone width 3 all its inner sets are empty
+            // and no cell is checked; here rank 1 is 10 rows / planes thick
+            w2[0] = 4 * 17 + 7; w2[1] = 10 * 17 - 1; w2[2] = 20 * 17 - w2[0] - w2[1];
+            stepperRegionTest<TestCell2dCube, 2>("TestCell 2d Cube", Coord<2>(17, 20), w2, 3);
+            w3[0] = 3 * 66 + 2 * 11 + 5; w3[1] = 10 * 66 + 3 * 11 - 2; w3[2] = 11 * 6 * 18 - w3[0] - w3[1];
+            stepperRegionTest<TestCell3dCube, 3>("TestCell 3d Cube", Coord<3>(11, 6, 18), w3, 2);
+            stepperRegionTest<TestCell3dMooreCube, 3>("TestCell 3d Moore Cube", Coord<3>(11, 6, 18), w3, 3);
         }
 
         compareWithSerialSimulator<LifeCell, 2>("LifeCell (Coord<2>)", Coord<2>(150, 67), 30);

@@ -98,25 +98,27 @@ private:
     Region<DIM> outerGhost;
 };
 
+/* The reference test gives rank 1 two rows (vanillastepperregiontest.h:57-61: 4 rows + 7 cells | 2 rows - 1 cell | the
+ * rest) — with ghost zone width 3 its kernel and all its inner sets are EMPTY, so that test checks no cell. Here rank 1
+ * gets 2 * ghostZoneWidth + 4 rows / planes (minus a cell), region borders still in the middle of rows. */
 template<int DIM> struct Weights;
 template<> struct Weights<2> {
-    /* vanillastepperregiontest.h:57-61: 4 rows + 7 cells | 2 rows - 1 cell | the rest */
-    static std::vector<std::size_t> make(const Coord<2>& dim)
+    static std::vector<std::size_t> make(const Coord<2>& dim, unsigned width)
     {
         std::vector<std::size_t> w(3);
         w[0] = 4 * dim.x() + 7;
-        w[1] = 2 * dim.x() - 1 + (dim.y() > 12 ? (dim.y() - 12) / 2 * dim.x() : 0);
+        w[1] = (2 * width + 4) * dim.x() - 1;
         w[2] = dim.prod() - w[0] - w[1];
         return w;
     }
 };
 template<> struct Weights<3> {
-    static std::vector<std::size_t> make(const Coord<3>& dim)
+    static std::vector<std::size_t> make(const Coord<3>& dim, unsigned width)
     {
         std::vector<std::size_t> w(3);
         std::size_t plane = (std::size_t)dim.x() * dim.y();
-        w[0] = (dim.z() / 3) * plane + 2 * dim.x() + 5;       /* ends in the middle of a row */
-        w[1] = (dim.z() / 3) * plane + 3 * dim.x() - 2;
+        w[0] = 3 * plane + 2 * dim.x() + 5;       /* ends in the middle of a row */
+        w[1] = (2 * width + 4) * plane + 3 * dim.x() - 2;
         w[2] = dim.prod() - w[0] - w[1];
         return w;
     }
@@ -157,7 +159,7 @@ static void runCase(const char *name, const Coord<APITraits::SelectTopology<CELL
     for (int s = 0; s < 2; ++s) {
         Setup& u = setups[s];
         u.init.reset(new SeededInitializer<CELL>(dim, last));
-        typename SharedPtr<Partition<DIM> >::Type partition(new StripingPartition<DIM>(Coord<DIM>(), dim, 0, Weights<DIM>::make(dim)));
+        typename SharedPtr<Partition<DIM> >::Type partition(new StripingPartition<DIM>(Coord<DIM>(), dim, 0, Weights<DIM>::make(dim, ghostZoneWidth)));
         typename SharedPtr<AdjacencyManufacturer<DIM> >::Type adjacency(new DummyAdjacencyManufacturer<DIM>);
         u.manager.reset(new PartitionManager<Topology>());
         u.manager->resetRegions(adjacency, box, partition, 1, ghostZoneWidth);
@@ -184,7 +186,7 @@ static void runCase(const char *name, const Coord<APITraits::SelectTopology<CELL
     Reference reference(setups[0].manager, setups[0].init, ghostAccepters[0], innerAccepters[0], providers[0]);
     Device device(setups[1].manager, setups[1].init, ghostAccepters[1], innerAccepters[1], providers[1]);
 
-    long wrongVsWhole = 0, wrongVsReference = 0;
+    long wrongVsWhole = 0, wrongVsReference = 0, compared = 0;
     std::size_t pullsWithoutPatch = 0;
     for (unsigned t = 1; t <= steps; ++t) {
         std::size_t pullsBefore = device.pullCount(), recordsBefore = setups[1].ghostAccepter->records.size() + setups[1].innerAccepter->records.size();
@@ -204,12 +206,14 @@ static void runCase(const char *name, const Coord<APITraits::SelectTopology<CELL
         const GridType& got = device.grid();
         for (typename Region<DIM>::Iterator i = valid.begin(); i != valid.end(); ++i) {
             CELL g = got.get(*i);
+            ++compared;
             if (!(g == want.get(*i))) ++wrongVsReference;
             if (!(g == history[t][(*i - box.origin).toIndex(box.dimensions)])) ++wrongVsWhole;
         }
     }
     CHECK(wrongVsWhole == 0);
     CHECK(wrongVsReference == 0);
+    CHECK(compared > 0);
     CHECK(pullsWithoutPatch == 0);
 
     bool sameRecords = true;
@@ -227,9 +231,9 @@ static void runCase(const char *name, const Coord<APITraits::SelectTopology<CELL
         }
     }
     CHECK(sameRecords);
-    std::printf("%-13s ghost zone width %u, %u nano steps as rank 1 of 3: %ld / %ld cells differ from the whole-space run / VanillaStepper, "
+    std::printf("%-13s ghost zone width %u, %u nano steps as rank 1 of 3: %ld / %ld of %ld cells differ from the whole-space run / VanillaStepper, "
                 "%zu patches %s, %zu launches, %zu pulls, %zu pushes\n",
-                name, ghostZoneWidth, steps, wrongVsWhole, wrongVsReference, patches, sameRecords ? "identical" : "DIFFERENT",
+                name, ghostZoneWidth, steps, wrongVsWhole, wrongVsReference, compared, patches, sameRecords ? "identical" : "DIFFERENT",
                 device.launchCount(), device.pullCount(), device.pushCount());
 }
 
@@ -237,10 +241,10 @@ int main()
 {
     try {
         for (unsigned width = 1; width <= 4; ++width) {
-            runCase<ConwayCube>("ConwayCube", Coord<2>(17, 12), width, 9);        /* the reference test's 17 x 12 space */
-            runCase<Jacobi7Cube>("Jacobi7Cube", Coord<3>(11, 7, 13), width, 9);
+            runCase<ConwayCube>("ConwayCube", Coord<2>(17, 2 * width + 14), width, 9);   /* the reference test's space is 17 x 12 */
+            runCase<Jacobi7Cube>("Jacobi7Cube", Coord<3>(11, 7, 2 * width + 13), width, 9);
         }
-        runCase<Jacobi27Cube>("Jacobi27Cube", Coord<3>(9, 8, 14), 3, 8);
+        runCase<Jacobi27Cube>("Jacobi27Cube", Coord<3>(9, 8, 19), 3, 8);
         runCase<ConwayCube>("ConwayCube", Coord<2>(40, 30), 2, 7);
         /* a Torus cell is refused */
         bool refused = false;

@@ -124,7 +124,24 @@ def test_b200_stepper_beside_vanilla_stepper():
     assert "all checks passed" in res.stdout and "DIFFERENT" not in res.stdout
 
 
+CHECKPOINT_BIN = os.path.join(HERE, "facade", "_bin", "checkpoint_test")
+
+
+@pytest.mark.gpu
+def test_checkpoints_in_the_mpiio_layout_from_the_device():
+    """tests/facade/checkpoint_test.cpp: B200CheckpointWriter / B200ParallelCheckpointWriter write the
+    reference's MPI-IO file layout (io/mpiio.h:82-130) from the device grid box by box, B200CheckpointInitializer restarts
+    from it; files identical to the ones written from the reference's host grid, restarted runs end where the
+    uninterrupted run does."""
+    if not os.access(CHECKPOINT_BIN, os.X_OK):
+        pytest.skip("tests/facade/_bin/checkpoint_test not built (needs /root/reference at build time)")
+    res = subprocess.run([CHECKPOINT_BIN], capture_output=True, text=True, timeout=600)
+    print(res.stdout[-4000:], res.stderr[-2000:])
+    assert res.returncode == 0, res.stdout[-4000:] + res.stderr[-2000:]
+    assert "all checks passed" in res.stdout and "DIFFERENT" not in res.stdout
+
+
 def test_facade_header_has_no_oracle_dependency():
-    for name in ("b200simulator.h", "b200generic.h", "b200genericsoa.h", "b200boxgrid.h", "b200stripingsimulator.h", "b200stepper.h"):
+    for name in ("b200simulator.h", "b200generic.h", "b200genericsoa.h", "b200boxgrid.h", "b200stripingsimulator.h", "b200stepper.h", "b200checkpoint.h"):
         text = open(os.path.join(HERE, "..", "include", "libgeodecomp_b200", name)).read()
         assert "oracle" not in text
