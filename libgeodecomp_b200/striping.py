@@ -224,7 +224,11 @@ class StripedSimulator:
                  overlap=True, stream_io=False, stream_depth=None, stream_chunks=16):
         """stream_io: let run() pipeline Initializer -> sweeps -> ParallelWriters chunk by chunk along the last axis
         (see _run_streamed) where that is possible; stream_depth = sweeps per launch there (default: what the
-        kernel family fuses), stream_chunks = number of chunks the axis is cut into."""
+        kernel family fuses), stream_chunks = number of chunks the axis is cut into.
+        On more than one rank run() can only be streamed when the ghost zones are as wide as the run is long
+        (ghost_width >= sweeps of the run): every rank then asks its Initializer for its slab PLUS the ghost zones,
+        recomputes the shrinking ghost zone redundantly and needs no exchange at all while the wavefront passes —
+        HiParSimulator's ghost zone of width k taken to k = run length (parallelization/hiparsimulator.h:60-66)."""
         self.initializer, self.model, self.rank, self.world = initializer, model, rank, world
         self.overlap = overlap
         self.stream_io, self.stream_depth, self.stream_chunks = stream_io, stream_depth, stream_chunks
@@ -346,10 +350,15 @@ class StripedSimulator:
 
     # ---- streamed run: host -> device -> host as a pipeline along the last axis -------------------------------
     def _stream_plan(self):
-        """(sweeps per level, ...) or None when run() cannot be streamed: one rank, a Cube topology (periodic images
-        would tie the first planes to the last), no Steerers, only ParallelWriters that fire at the very end."""
-        if not self.stream_io or self.world != 1 or self.model.wraps or self.steerers:
+        """(sweeps per level, ...) or None when run() cannot be streamed: a Cube topology (periodic images would tie
+        the first planes to the last), no Steerers, only ParallelWriters that fire at the very end, and on more than
+        one rank ghost zones as wide as the run is long."""
+        if not self.stream_io or self.model.wraps or self.steerers:
             return None
+        if self.world > 1:
+            total = (self.initializer.maxSteps() - self.initializer.startStep()) * self.NANO_STEPS
+            if self.ghost_width < total:
+                return None
         if not hasattr(self.grid.dev, "update_box") or not hasattr(self.model, "member_index"):
             return None
         steps = self.initializer.maxSteps() - self.initializer.startStep()
@@ -369,11 +378,19 @@ class StripedSimulator:
         depth = max(1, min(int(depth), 4, sweeps))
         # the shorter remainder level goes FIRST: a level may not be deeper than the one after it (see below)
         levels = ([sweeps % depth] if sweeps % depth else []) + [depth] * (sweeps // depth)
-        n = self.grid.dims[self.model.dim - 1]
-        chunk = max(2 * depth, -(-n // max(1, int(self.stream_chunks))))
-        chunk = -(-chunk // depth) * depth     # boxes that are cut off at plane 0 stay whole multiples of the depth
-        if n < 2 * chunk:
-            return None
+        # every rank must come to the same decision (a rank that falls back to the plain schedule exchanges halos,
+        # a streaming one does not): the test is made for the extents of ALL ranks
+        mine = None
+        for r in range(self.world):
+            lo, hi = self._stream_extent(r)
+            n = hi - lo
+            chunk = max(2 * depth, -(-n // max(1, int(self.stream_chunks))))
+            chunk = -(-chunk // depth) * depth     # boxes that are cut off at plane 0 stay whole multiples of the depth
+            if n < 2 * chunk:
+                return None
+            if r == self.rank:
+                mine = chunk
+        chunk = mine
         return levels, chunk
 
     def _run_streamed(self, levels, chunk):
@@ -394,13 +411,21 @@ class StripedSimulator:
         final."""
         g, dev, model = self.grid, self.grid.dev, self.model
         last = model.dim - 1
-        n = g.dims[last]
+        own = g.dims[last]
+        # the streamed axis: the slab plus, towards a neighbouring slab, the whole ghost zone (plane index s = z - zb)
+        zb, ze = self._stream_extent()
+        n = ze - zb
+        low_peer, high_peer = zb < 0, ze > own
         L = len(levels)
         off = [sum(levels[:l + 1]) for l in range(L)]
         first_nano = [(sum(levels[:l])) % self.NANO_STEPS for l in range(L)]
         streams = _NoStreams() if getattr(g.engine, "synchronous", False) else _CudaStreams(self.device)
         start, last_step = self.initializer.startStep(), self.initializer.maxSteps()
         parity = [0]
+        if low_peer:
+            dev.halo_mark_valid(0, self.ghost_width)   # filled by the Initializer below, never exchanged
+        if high_peer:
+            dev.halo_mark_valid(1, self.ghost_width)
 
         def want(p):
             # which buffer the C ABI calls "current" is a host-side flag; device work already enqueued keeps its pointers
@@ -410,12 +435,12 @@ class StripedSimulator:
 
         def box(a, b):
             origin, dim = [0, 0, 0], list(g.dims) + [1] * (3 - len(g.dims))
-            origin[last], dim[last] = a, b - a
+            origin[last], dim[last] = a + zb, b - a
             return origin, dim
 
         def region(a, b):
             o, d = list(g.origin), list(g.dims)
-            o[last], d[last] = g.origin[last] + a, b - a
+            o[last], d[last] = g.origin[last] + a + zb, b - a
             return (tuple(o), tuple(d))
 
         uploads = -(-n // chunk)
@@ -424,14 +449,23 @@ class StripedSimulator:
             if c < uploads:
                 a, b = c * chunk, min((c + 1) * chunk, n)
                 want(0)
-                window = GridWindow(g, a, b, stream=streams.handle(streams.up))
+                window = GridWindow(g, a + zb, b + zb, stream=streams.handle(streams.up))
                 self.initializer.grid(window)
-                for w in self.writers:
-                    w.stepFinishedRegion(window, region(a, b), g.global_dims, start, WRITER_INITIALIZED, self.rank,
-                                         b == n)
+                # writers see the rank's own cells only
+                wa, wb = max(a + zb, 0), min(b + zb, own)
+                if wb > wa:
+                    wwin = GridWindow(g, wa, wb, stream=streams.handle(streams.up))
+                    for w in self.writers:
+                        w.stepFinishedRegion(wwin, region(wa - zb, wb - zb), g.global_dims, start, WRITER_INITIALIZED, self.rank,
+                                             wb == own)
                 streams.wait(streams.run, streams.record(streams.up))
             for l in range(L):
                 a, b = max(c * chunk - off[l], 0), min((c + 1) * chunk - off[l], n)
+                # towards a neighbour the ghost zone shrinks by one plane per sweep: nobody delivers fresh planes
+                if low_peer:
+                    a = max(a, off[l])
+                if high_peer:
+                    b = min(b, n - off[l])
                 if b <= a:
                     continue
                 want(l % 2)
@@ -439,17 +473,34 @@ class StripedSimulator:
                 dev.update_box(model.kernel, origin, dim, nano_step=first_nano[l], params=model.step_params(l == L - 1),
                                n_sweeps=levels[l], stream=streams.handle(streams.run))
             a, b = max(c * chunk - off[-1], 0), min((c + 1) * chunk - off[-1], n)
+            a, b = max(a + zb, 0), min(b + zb, own)      # own planes that have reached the last time step
             if b > a and self.writers:
                 streams.wait(streams.down, streams.record(streams.run))
                 want(L % 2)
                 window = GridWindow(g, a, b, stream=streams.handle(streams.down))
                 for w in self.writers:
-                    w.stepFinishedRegion(window, region(a, b), g.global_dims, last_step, WRITER_ALL_DONE, self.rank,
-                                         b == n)
+                    w.stepFinishedRegion(window, region(a - zb, b - zb), g.global_dims, last_step, WRITER_ALL_DONE, self.rank,
+                                         b == own)
         want(L % 2)   # the final state is the current buffer from here on
         streams.join()
+        for side in (0, 1):
+            if (low_peer, high_peer)[side]:
+                dev.halo_mark_valid(side, 0)           # the ghost zones are used up
         self.stepNum = last_step
         self.streamed_runs += 1
+
+    def _stream_extent(self, rank=None):
+        """planes [lo, hi) of the last axis (local coordinates of that rank) a streamed run sweeps: the slab and its
+        PEER ghost zones"""
+        rank = self.rank if rank is None else rank
+        last = self.model.dim - 1
+        bounds = slab_bounds(self.grid.global_dims[last], self.world)
+        n = bounds[rank + 1] - bounds[rank]
+        if self.world == 1:
+            return 0, n
+        lo = -self.ghost_width if rank > 0 else 0
+        hi = n + self.ghost_width if rank < self.world - 1 else n
+        return lo, hi
 
     def run(self):
         plan = self._stream_plan()

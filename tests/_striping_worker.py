@@ -145,6 +145,43 @@ def main():
     if not np.array_equal(sim.getGrid().saveMember("temp"), oracle_py.jacobi(27, False, data, 25, edge=0.75)[b[rank]:b[rank + 1]]):
         failures.append("misaligned advance: result rank %d" % rank)
 
+    # streamed run on several ranks: ghost zones as wide as the run is long, filled by the Initializer (it is asked for
+    # the slab plus its ghost zones), no exchange while the wavefront passes; writers see the rank's own cells only
+    class WindowPull(ParallelWriter):
+        def __init__(self, shape, member):
+            ParallelWriter.__init__(self, "", 1 << 30)
+            self.out, self.member, self.regions = np.zeros(shape), member, []
+
+        def stepFinishedRegion(self, grid, validRegion, globalDimensions, step, event, rank_, lastCall):
+            (o, d) = validRegion
+            self.regions.append((event, o[-1], d[-1], lastCall))
+            if event == 2:
+                z = o[-1] - self.z0
+                grid.saveMember(self.member, origin=o, dims=d, out=self.out[z:z + d[-1]])
+
+    for kind, steps, shape, chunks, depth in [(27, 4, (36, 6, 7), 4, 2), (7, 5, (48, 5, 6), 3, 4), (6, 3, (24, 4, 5), 6, 1)]:
+        nz, ny, nx = shape
+        data = synth.jacobi_grid(nx, ny, nz, seed=kind + 7)
+        b = slab_bounds(nz, world)
+        sim = StripedSimulator(SlabInit(data, steps, 0.75), models.ALL["Jacobi%dCube" % kind], rank=rank, world=world,
+                               ghost_width=steps, dist=dist, engine=cpu_engine, stream_io=True, stream_depth=depth, stream_chunks=chunks)
+        pull = WindowPull((b[rank + 1] - b[rank], ny, nx), "temp")
+        pull.z0 = b[rank]
+        sim.addWriter(pull)
+        sim.run()
+        want = oracle_py.jacobi(kind, False, data, steps, edge=0.75)[b[rank]:b[rank + 1]]
+        done = [r for r in pull.regions if r[0] == 2]
+        if sim.streamed_runs != 1 or not np.array_equal(pull.out, want) or not np.array_equal(sim.getGrid().saveMember("temp"), want):
+            failures.append("streamed on %d ranks, kind %d rank %d" % (world, kind, rank))
+        if min(r[1] for r in pull.regions) < b[rank] or max(r[1] + r[2] for r in pull.regions) > b[rank + 1] or \
+                sum(r[2] for r in done) != b[rank + 1] - b[rank] or [r[3] for r in done].count(True) != 1 or not done[-1][3]:
+            failures.append("streamed on %d ranks: writer regions %r" % (world, pull.regions))
+        # the plain schedule still works on the same simulator afterwards (ghost zones were used up, not left 'valid')
+        sim.stream_io = False
+        sim.run()
+        if not np.array_equal(sim.getGrid().saveMember("temp"), want):
+            failures.append("plain run after a streamed one, kind %d rank %d" % (kind, rank))
+
     # n-body: slabs of BoxCell containers, one ghost plane of containers (counts + particles) per side and sweep;
     # velocities large enough that particles change containers and slabs
     class CellInit(SimpleInitializer):
