@@ -707,6 +707,28 @@ def gpu_reference(workload, args, torch):
             "cuda_status": ref.get("cuda")}
 
 
+def e2e_cpp(args):
+    """The same e2e measurement through the C++ facade, the reference's host language: tests/facade/_bin/e2e_bench (a
+    LibGeoDecomp program on B200Simulator: Initializer from / Writer into page-locked host memory, run() timed by the
+    program itself) — once handing the engine whole boxes, once going row by row as BOVOutput::writeGrid does."""
+    exe = os.path.join(ROOT, "tests", "facade", "_bin", "e2e_bench")
+    if args.workload != "jacobi27" or not os.access(exe, os.X_OK):
+        return None
+    out = {}
+    for mode in ("box", "rows"):
+        res = subprocess.run([exe, "1024", str(args.steps), "1", mode], capture_output=True, text=True, timeout=600)
+        lines = [ln for ln in res.stdout.splitlines() if ln.startswith("{")]
+        if res.returncode != 0 or not lines:
+            out[mode] = {"error": "e2e_bench exited with %d: %s" % (res.returncode, (res.stdout + res.stderr)[-200:])}
+            continue
+        out[mode] = json.loads(lines[0])
+    if "value" in out.get("box", {}):
+        out.update({"value": out["box"]["value"], "unit": "GLUPS"})
+        if "checksum" in out.get("rows", {}):
+            out["rows_equal_box"] = out["rows"]["checksum"] == out["box"]["checksum"]
+    return out
+
+
 def bench_nbody(args, rank, world, dist, torch, containers=108, with_e2e=True):
     """BASELINE.json configs[4]: short-range n-body in BoxCell containers, ~16.6 M particles per GPU
     (255^3 lattice sites in 108^3 containers of edge 2.5 = cutoff), slabs of containers along z.
@@ -874,6 +896,13 @@ def main():
         except Exception as e:  # a comparator, never required for the line
             gpu_ref = {"error": repr(e)}
 
+    cpp = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        try:
+            cpp = e2e_cpp(args)
+        except Exception as e:  # a comparator, never required for the line
+            cpp = {"error": repr(e)}
+
     if rank == 0:
         line = {
             "metric": "GLUPS (giga lattice updates/s)", "value": main_res["value"], "unit": "GLUPS",
@@ -895,6 +924,8 @@ def main():
             line["cpu_baseline"] = cpu
         if gpu_ref is not None:
             line["gpu_reference"] = gpu_ref
+        if cpp is not None:
+            line["e2e_cpp"] = cpp
         # the secondary workloads' headline numbers as flat top-level scalars (the full records follow in "others")
         for r in others:
             w = r.get("workload")

@@ -176,6 +176,11 @@ int b200geo_sync(void *stream);
  * _load_region with location = B200GEO_CUDA_DEVICE. */
 int b200geo_device_alloc(int device, uint64_t bytes, void **ptr);
 int b200geo_device_free(int device, void *ptr);
+/* Page-locked host memory: Initializers / Writers that hand the engine whole boxes (GridBase::loadMember /
+ * saveMember, storage/gridbase.h:217-261) out of such a buffer move them at the full speed of the link; pageable
+ * memory works as well, only slower (the driver stages it). */
+int b200geo_host_alloc(uint64_t bytes, void **ptr);
+int b200geo_host_free(void *ptr);
 
 /* ---- halo exchange (replaces PatchLink::Accepter::put / Provider::get,
  *      communication/patchlink.h:127-151,218-244, for slab partitions along the last axis,

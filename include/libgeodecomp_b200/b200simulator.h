@@ -259,7 +259,7 @@ public:
     {
         pendingCells.clear();
         pendingStreaks.clear();
-        rowCacheValid = false;
+        dropCaches();
         b200geo_grid_destroy(handle);
         handle = 0;
         box = newBox;
@@ -295,7 +295,7 @@ public:
         } else {
             pendingCells.insert(pendingCells.end(), cells, cells + n);
         }
-        rowCacheValid = false;
+        dropCaches();
         if (pendingCells.size() >= MAX_PENDING_CELLS) {
             flush();
         }
@@ -453,7 +453,7 @@ public:
             throw std::invalid_argument("buffer size does not match region");
         }
         flush();
-        rowCacheValid = false;
+        dropCaches();
         std::vector<int32_t> streaks = flatten(region, offset);
         B200Helpers::check(b200geo_grid_load_region(handle, streaks.data(), (int)(streaks.size() / 4), buffer.data(), B200GEO_HOST, 1, 0));
         B200Helpers::check(b200geo_sync(0));
@@ -463,7 +463,7 @@ public:
     void update(unsigned firstNanoStep, unsigned sweeps)
     {
         flush();
-        rowCacheValid = false;
+        dropCaches();
         int32_t dim[3] = {1, 1, 1};
         for (int i = 0; i < DIM; ++i) {
             dim[i] = box.dimensions[i];
@@ -484,7 +484,7 @@ public:
     std::size_t updateRegion(const Region<DIM>& region, unsigned nanoStep)
     {
         flush();
-        rowCacheValid = false;
+        dropCaches();
         B200Helpers::check(b200geo_refresh_ghosts(handle, 0));
         std::vector<B200Helpers::StreakBox> boxes = B200Helpers::mergeStreaks<DIM>(region.beginStreak(), region.endStreak(), box.origin);
         for (std::size_t k = 0; k < boxes.size(); ++k) {
@@ -497,7 +497,7 @@ public:
     void swapBuffers()
     {
         flush();
-        rowCacheValid = false;
+        dropCaches();
         B200Helpers::check(b200geo_swap(handle));
     }
 
@@ -512,7 +512,7 @@ public:
     void loadRegionFromDevice(const void *deviceBuffer, const Region<DIM>& region)
     {
         flush();
-        rowCacheValid = false;
+        dropCaches();
         std::vector<int32_t> streaks = flatten(region, Coord<DIM>());
         /* the current buffer only: a Stepper's two grids differ on purpose */
         B200Helpers::check(b200geo_grid_load_region(handle, streaks.data(), (int)(streaks.size() / 4), deviceBuffer, B200GEO_CUDA_DEVICE, 0, 0));
@@ -559,7 +559,7 @@ public:
             throw std::invalid_argument("buffer size does not match region");
         }
         flush();
-        rowCacheValid = false;
+        dropCaches();
         const std::size_t n = region.size();
         if (n == 0) {
             return;
@@ -590,7 +590,7 @@ public:
             throw std::invalid_argument("buffer size does not match region");
         }
         flush();
-        rowCacheValid = false;
+        dropCaches();
         std::vector<int32_t> streaks = flatten(region, offset);
         B200Helpers::check(b200geo_grid_load_region(handle, streaks.data(), (int)(streaks.size() / 4), buffer.data(), B200GEO_HOST, both, 0));
         B200Helpers::check(b200geo_sync(0));
@@ -604,7 +604,7 @@ public:
     /* the device grid was changed behind this object's back (slab group stepping): drop cached rows */
     void invalidateCache() const
     {
-        rowCacheValid = false;
+        dropCaches();
     }
 
     int bytesPerCell() const
@@ -654,6 +654,14 @@ protected:
              * MemoryLocation::CUDA_DEVICE (storage/gridbase.h:217-261) */
             const int loc = targetLocation == MemoryLocation::HOST ? B200GEO_HOST : B200GEO_CUDA_DEVICE;
             std::vector<B200Helpers::StreakBox> boxes = B200Helpers::mergeStreaks<DIM>(begin, end, box.origin);
+            /* Writers that pull a member ROW BY ROW (the reference's BOVOutput::writeGrid calls saveMemberUnchecked
+             * once per streak, io/bovoutput.h:83-95; so do PPM / VisIt writers): rows are served from a read-ahead
+             * block of up to 64 MiB of the rows that follow — one transfer per block instead of one per row */
+            if (boxes.size() == 1 && boxes[0].dim[1] == 1 && boxes[0].dim[2] == 1 && loc == B200GEO_HOST &&
+                boxes[0].origin[0] >= 0 && boxes[0].origin[0] + boxes[0].dim[0] <= box.dimensions.x() &&
+                boxes[0].origin[1] >= 0 && boxes[0].origin[2] >= 0 && serveRow(m, boxes[0], target)) {
+                return;
+            }
             for (std::size_t k = 0; k < boxes.size(); ++k) {
                 B200Helpers::check(b200geo_grid_save_member(handle, m, boxes[k].origin, boxes[k].dim, target, loc, 0));
                 target += selector.sizeOfExternal() * boxes[k].cells();
@@ -683,7 +691,7 @@ protected:
         const typename Region<DIM>::StreakIterator& end)
     {
         flush();
-        rowCacheValid = false;
+        dropCaches();
         int m = findMember(selector);
         if (m >= 0) {
             const int loc = sourceLocation == MemoryLocation::HOST ? B200GEO_HOST : B200GEO_CUDA_DEVICE;
@@ -728,6 +736,57 @@ private:
     mutable int rowCacheRows = 0;
     mutable bool rowCacheValid = false;
     mutable std::size_t memberCalls = 0;
+    mutable std::vector<char> memberCache;         /* read-ahead block of one member (saveMember row by row) */
+    mutable B200Helpers::StreakBox memberCacheBox;
+    mutable int memberCacheMember = -1;
+    mutable bool memberCacheValid = false;
+
+    void dropCaches() const
+    {
+        rowCacheValid = false;
+        memberCacheValid = false;
+    }
+
+    /* one row of member m out of the read-ahead block; the block is (re)filled with the rows from this one on:
+     * the rest of the plane, or — from the first row of a plane — as many whole planes as fit */
+    bool serveRow(int m, const B200Helpers::StreakBox& row, char *target) const
+    {
+        const int nx = box.dimensions.x();
+        const int ny = DIM > 1 ? box.dimensions[DIM > 1 ? 1 : 0] : 1;
+        const int nz = DIM > 2 ? box.dimensions[DIM > 2 ? 2 : 0] : 1;
+        const std::size_t bytes = members[m].bytes;
+        const int y = row.origin[1], z = row.origin[2];
+        if (y >= ny || z >= nz) {
+            return false;
+        }
+        bool hit = memberCacheValid && memberCacheMember == m && z >= memberCacheBox.origin[2] &&
+                   z < memberCacheBox.origin[2] + memberCacheBox.dim[2] && y >= memberCacheBox.origin[1] &&
+                   y < memberCacheBox.origin[1] + memberCacheBox.dim[1];
+        if (!hit) {
+            const std::size_t budget = (std::size_t)64 << 20, rowBytes = (std::size_t)nx * bytes;
+            B200Helpers::StreakBox b = {{0, y, z}, {nx, 1, 1}};
+            if (y == 0 && rowBytes * ny <= budget) {
+                b.dim[1] = ny;
+                b.dim[2] = (int)(std::min)((std::size_t)(nz - z), budget / (rowBytes * ny));
+            } else {
+                b.dim[1] = (int)(std::max)((std::size_t)1, (std::min)((std::size_t)(ny - y), budget / rowBytes));
+            }
+            if (b.cells() < 2 * (std::size_t)nx) {
+                return false;      /* nothing to read ahead: the plain path */
+            }
+            memberCache.resize(b.cells() * bytes);
+            B200Helpers::check(b200geo_grid_save_member(handle, m, b.origin, b.dim, memberCache.data(), B200GEO_HOST, 0));
+            B200Helpers::check(b200geo_sync(0));
+            ++memberCalls;
+            memberCacheBox = b;
+            memberCacheMember = m;
+            memberCacheValid = true;
+        }
+        const std::size_t at = (((std::size_t)(z - memberCacheBox.origin[2]) * memberCacheBox.dim[1] + (y - memberCacheBox.origin[1])) * nx +
+                                row.origin[0]) * bytes;
+        std::memcpy(target, &memberCache[at], (std::size_t)row.dim[0] * bytes);
+        return true;
+    }
 
     /* `rows` whole rows (same plane, consecutive y) starting at `origin` in ONE transfer */
     void fetchRows(const Coord<DIM>& origin, int rows, CELL *cells) const

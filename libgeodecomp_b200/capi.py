@@ -82,6 +82,8 @@ SYMBOLS = [
     ("b200geo_sync", ctypes.c_int, [_vp]),
     ("b200geo_device_alloc", ctypes.c_int, [ctypes.c_int, ctypes.c_uint64, ctypes.POINTER(ctypes.c_void_p)]),
     ("b200geo_device_free", ctypes.c_int, [ctypes.c_int, _vp]),
+    ("b200geo_host_alloc", ctypes.c_int, [ctypes.c_uint64, ctypes.POINTER(ctypes.c_void_p)]),
+    ("b200geo_host_free", ctypes.c_int, [_vp]),
     ("b200geo_halo_block", ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                           ctypes.POINTER(_vp), ctypes.POINTER(ctypes.c_uint64)]),
     ("b200geo_halo_block_in", ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,

@@ -137,7 +137,7 @@ int b200geo_grid_uniform_min_stride(const b200geo_grid_desc *desc, int64_t *min_
             return fail(B200GEO_ERR_INVALID, "member size must be 1, 2, 4 or 8 bytes");
     }
     for (int i = 0; i < 3; ++i)
-        if (desc->dim[i] < 1 || desc->ghost[i] < 0 || desc->ghost[i] > 16)
+        if (desc->dim[i] < 1 || desc->ghost[i] < 0 || desc->ghost[i] > (i == 0 ? 16 : 65536))
             return fail(B200GEO_ERR_INVALID, "grid dimension or ghost width out of range");
     int lead;
     int64_t pitch;
@@ -154,7 +154,9 @@ static int plan_layout(const b200geo_grid_desc *desc, int64_t uniform_stride, Me
         return fail(B200GEO_ERR_INVALID, "n_members out of range");
     for (int i = 0; i < 3; ++i) {
         if (desc->dim[i] < 1) return fail(B200GEO_ERR_INVALID, "grid dimension must be >= 1");
-        if (desc->ghost[i] < 0 || desc->ghost[i] > 16) return fail(B200GEO_ERR_INVALID, "ghost width out of range");
+        // x ghosts live in the 128-byte lead-in of a row; along y and z a ghost zone may be as wide as a whole run is
+        // long (streamed runs on slabs: no exchange while the wavefront passes)
+        if (desc->ghost[i] < 0 || desc->ghost[i] > (i == 0 ? 16 : 65536)) return fail(B200GEO_ERR_INVALID, "ghost width out of range");
         for (int s = 0; s < 2; ++s) {
             int mode = desc->ghost_mode[i][s];
             if (mode < B200GEO_GHOST_EDGE || mode > B200GEO_GHOST_PEER)
@@ -665,6 +667,25 @@ int b200geo_device_free(int device, void *ptr)
     if (!ptr) return B200GEO_OK;
     B200GEO_CUDA(cudaSetDevice(device));
     B200GEO_CUDA(cudaFree(ptr));
+    return B200GEO_OK;
+}
+
+int b200geo_host_alloc(uint64_t bytes, void **ptr)
+{
+    if (!ptr) return fail(B200GEO_ERR_INVALID, "null argument");
+    *ptr = 0;
+    cudaError_t e = cudaMallocHost(ptr, bytes ? (size_t)bytes : 1);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(B200GEO_ERR_NOMEM, std::string("cudaMallocHost failed: ") + cudaGetErrorString(e));
+    }
+    return B200GEO_OK;
+}
+
+int b200geo_host_free(void *ptr)
+{
+    if (!ptr) return B200GEO_OK;
+    B200GEO_CUDA(cudaFreeHost(ptr));
     return B200GEO_OK;
 }
 

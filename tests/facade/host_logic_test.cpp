@@ -209,6 +209,45 @@ static void testMemberBoxFastPath()
     std::printf("member I/O by boxes: 1 / 1 / 3 / 3 copies for a grid / a box / plane + box + streak / ragged rows\n");
 }
 
+/* Writers that pull a member row by row (BOVOutput::writeGrid, io/bovoutput.h:83-95): rows come out of a read-ahead
+ * block, a write in between drops it */
+static void testMemberReadAhead()
+{
+    typedef Jacobi7Cube CELL;
+    CoordBox<3> box(Coord<3>(1, 2, 3), Coord<3>(40, 9, 6));
+    B200Grid<CELL> grid(box);
+    for (CoordBox<3>::Iterator i = box.begin(); i != box.end(); ++i) {
+        grid.set(*i, CELL(0.25 + (*i - box.origin).toIndex(box.dimensions)));
+    }
+    Selector<CELL> sel(&CELL::temp, "temp");
+    std::vector<double> row(40);
+    long bad = 0;
+    std::size_t before = grid.memberCopyCalls();
+    for (CoordBox<3>::StreakIterator i = box.beginStreak(); i != box.endStreak(); ++i) {
+        Region<3> one;
+        one << *i;
+        grid.saveMemberUnchecked(reinterpret_cast<char*>(row.data()), MemoryLocation::HOST, sel, one);
+        for (int x = 0; x < 40; ++x) {
+            bad += row[x] != 0.25 + (Coord<3>(i->origin.x() + x, i->origin.y(), i->origin.z()) - box.origin).toIndex(box.dimensions);
+        }
+    }
+    std::size_t transfers = grid.memberCopyCalls() - before;
+    CHECK(bad == 0);
+    CHECK(transfers == 1);                       /* 54 rows, one block */
+    /* a partial row, then a write, then the same row again: the block is dropped, the new value is seen */
+    Region<3> part;
+    part << Streak<3>(Coord<3>(5, 4, 5), 9);
+    grid.saveMemberUnchecked(reinterpret_cast<char*>(row.data()), MemoryLocation::HOST, sel, part);
+    CHECK(row[0] == 0.25 + (Coord<3>(5, 4, 5) - box.origin).toIndex(box.dimensions));
+    grid.set(Coord<3>(6, 4, 5), CELL(-3.0));
+    grid.saveMemberUnchecked(reinterpret_cast<char*>(row.data()), MemoryLocation::HOST, sel, part);
+    CHECK(row[1] == -3.0);
+    grid.update(0, 1);
+    grid.saveMemberUnchecked(reinterpret_cast<char*>(row.data()), MemoryLocation::HOST, sel, part);
+    CHECK(row[1] != -3.0);
+    std::printf("member pulled row by row: %zu transfer(s) for 54 rows, %ld wrong values\n", transfers, bad);
+}
+
 /* The AoS form of the D3Q19 cell (oracle/models/lbm_aos.h, used by the GPU comparator and the generic-path test) is the
  * same model as the SoA / updateLineX cell the hand-written kernel is bound to: both through the reference's
  * SerialSimulator (VanillaUpdateFunctor-free FixedCoord path vs FixedNeighborhoodUpdateFunctor), member by member. */
@@ -420,6 +459,7 @@ int main()
         testResizeAndWriteOrder();
         testSelectorsAndErrors();
         testMemberBoxFastPath();
+        testMemberReadAhead();
     } catch (const std::exception& e) {
         std::printf("FAILED with exception: %s\n", e.what());
         return 2;

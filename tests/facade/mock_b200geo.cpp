@@ -212,7 +212,7 @@ static int create_grid(const b200geo_grid_desc *desc, int64_t stride, b200geo_gr
     int slab = (desc->dim[2] == 1 && desc->ghost[2] == 0) ? 1 : 2;
     for (int i = 0; i < 3; ++i) {
         if (desc->dim[i] < 1) return fail(B200GEO_ERR_INVALID, "grid dimension must be >= 1");
-        if (desc->ghost[i] < 0 || desc->ghost[i] > 16) return fail(B200GEO_ERR_INVALID, "ghost width out of range");
+        if (desc->ghost[i] < 0 || desc->ghost[i] > (i == 0 ? 16 : 65536)) return fail(B200GEO_ERR_INVALID, "ghost width out of range");
         for (int s = 0; s < 2; ++s) {
             int mode = desc->ghost_mode[i][s];
             if (mode < B200GEO_GHOST_EDGE || mode > B200GEO_GHOST_PEER) return fail(B200GEO_ERR_INVALID, "bad ghost mode");
@@ -443,6 +443,8 @@ int b200geo_refresh_ghosts(b200geo_grid *g, void *)
 int b200geo_sync(void *) { return B200GEO_OK; }
 int b200geo_device_alloc(int, uint64_t bytes, void **ptr) { *ptr = malloc(bytes ? (size_t)bytes : 1); return *ptr ? B200GEO_OK : fail(B200GEO_ERR_NOMEM, "out of memory"); }
 int b200geo_device_free(int, void *ptr) { free(ptr); return B200GEO_OK; }
+int b200geo_host_alloc(uint64_t bytes, void **ptr) { *ptr = malloc(bytes ? (size_t)bytes : 1); return *ptr ? B200GEO_OK : fail(B200GEO_ERR_NOMEM, "out of memory"); }
+int b200geo_host_free(void *ptr) { free(ptr); return B200GEO_OK; }
 int b200geo_halo_block(const b200geo_grid *, int, int, int, int, void **, uint64_t *) { return fail(B200GEO_ERR_LOGIC, "not in the mock"); }
 int b200geo_halo_block_in(const b200geo_grid *, int, int, int, int, int, void **, uint64_t *) { return fail(B200GEO_ERR_LOGIC, "not in the mock"); }
 int b200geo_grid_ipc_export(const b200geo_grid *, int, void *) { return fail(B200GEO_ERR_LOGIC, "not in the mock"); }

@@ -26,3 +26,20 @@ def test_cpp_facade_host_logic_on_the_mock_engine(name):
     assert res.returncode == 0, res.stdout[-4000:] + res.stderr[-2000:]
     assert "all checks passed" in res.stdout
     assert "MISMATCH" not in res.stdout and "DIFFERENT" not in res.stdout
+
+
+def test_cpp_e2e_driver_on_the_mock_engine():
+    """tests/facade/e2e_bench.cpp (bench.py: "e2e_cpp"): whole boxes and row by row, one simulator and slabs — the same
+    final grid in every mode"""
+    import json
+    binary = os.path.join(HERE, "facade", "_bin", "e2e_bench_cpu")
+    if not os.access(binary, os.X_OK):
+        pytest.skip("tests/facade/_bin/e2e_bench_cpu not built (needs /root/reference at build time)")
+    sums = set()
+    for argv in (["20", "3", "1", "box"], ["20", "3", "1", "rows"], ["20", "3", "3", "box"], ["20", "3", "2", "rows"]):
+        res = subprocess.run([binary] + argv, capture_output=True, text=True, timeout=300)
+        assert res.returncode == 0, res.stdout + res.stderr
+        d = json.loads(res.stdout.splitlines()[0])
+        assert d["value"] > 0 and "error" not in d
+        sums.add(d["checksum"])
+    assert len(sums) == 1
