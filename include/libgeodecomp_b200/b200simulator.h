@@ -275,7 +275,7 @@ public:
     /* Writes are combined on the host and shipped as ONE streak list (b200geo_grid_load_region) before the
      * next read, sweep or explicit flush: an Initializer that calls set(Coord, cell) for every cell of its box
      * (src/examples/jacobi3d/main.cpp:54-72, src/examples/gameoflife/main.cpp:69-108) costs one transfer per
-     * 64 Ki cells instead of one per cell. Later writes win, as they would one by one. */
+     * 32 MiB of cells instead of one per cell. Later writes win, as they would one by one. */
     virtual void set(const Streak<DIM>& streak, const CELL *cells)
     {
         int n = streak.length();
@@ -296,7 +296,7 @@ public:
             pendingCells.insert(pendingCells.end(), cells, cells + n);
         }
         dropCaches();
-        if (pendingCells.size() >= MAX_PENDING_CELLS) {
+        if (pendingCells.size() >= maxPendingCells) {
             flush();
         }
     }
@@ -601,6 +601,12 @@ public:
         return device;
     }
 
+    /* combined host writes are shipped when this many cells are pending (default: 32 MiB worth) */
+    void setMaxPendingCells(std::size_t cells)
+    {
+        maxPendingCells = cells > 0 ? cells : 1;
+    }
+
     /* the device grid was changed behind this object's back (slab group stepping): drop cached rows */
     void invalidateCache() const
     {
@@ -728,7 +734,7 @@ private:
     int slabGhost;
     bool lowPeer;
     bool highPeer;
-    static const std::size_t MAX_PENDING_CELLS = 1 << 16;
+    std::size_t maxPendingCells = ((std::size_t)32 << 20) / sizeof(CELL) > (1 << 16) ? ((std::size_t)32 << 20) / sizeof(CELL) : (1 << 16);   /* 32 MiB of combined writes per flush */
     mutable std::vector<CELL> pendingCells;        /* combined writes: cells ...                  */
     mutable std::vector<int32_t> pendingStreaks;   /* ... and where they go, {x, y, z, endX} each */
     mutable std::vector<CELL> rowCache;            /* rowCacheRows whole rows of one plane, starting at rowCacheOrigin */
@@ -736,6 +742,9 @@ private:
     mutable int rowCacheRows = 0;
     mutable bool rowCacheValid = false;
     mutable std::size_t memberCalls = 0;
+    mutable std::string lastSelectorName;          /* findMember: the selector asked for last and its member */
+    mutable std::size_t lastSelectorBytes = 0;
+    mutable int lastSelectorMember = -1;
     mutable std::vector<char> memberCache;         /* read-ahead block of one member (saveMember row by row) */
     mutable B200Helpers::StreakBox memberCacheBox;
     mutable int memberCacheMember = -1;
@@ -916,6 +925,21 @@ private:
         if (selector.sizeOfExternal() != selector.sizeOfMember() || selector.arity() != 1) {
             return -1;
         }
+        /* Writers ask again and again with the same selector (row by row): remember the last answer */
+        if (lastSelectorMember >= 0 && selector.name() == lastSelectorName && selector.sizeOfMember() == lastSelectorBytes) {
+            return lastSelectorMember;
+        }
+        int found = probeMember(selector);
+        if (found >= 0) {
+            lastSelectorName = selector.name();
+            lastSelectorBytes = selector.sizeOfMember();
+            lastSelectorMember = found;
+        }
+        return found;
+    }
+
+    int probeMember(const Selector<CELL>& selector) const
+    {
         CELL probe = CELL();
         for (std::size_t m = 0; m < members.size(); ++m) {
             if ((std::size_t)members[m].bytes != selector.sizeOfMember()) {

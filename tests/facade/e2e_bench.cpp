@@ -63,16 +63,23 @@ public:
             }
             return;
         }
-        Region<3> region;
-        region << box;
+        if (!(box == cachedBox)) {
+            /* grid() is called by the simulator's constructor and again by run(): the Region (a run-length list of
+             * 2^20 streaks for 1024^3) is built once */
+            cachedRegion.clear();
+            cachedRegion << box;
+            cachedBox = box;
+        }
         /* the box is contiguous in the host array when it spans whole planes (slabs along z do) */
         const double *first = field.data + (std::size_t)box.origin.z() * field.dim.y() * field.dim.x();
-        target->loadMember(first, MemoryLocation::HOST, Selector<Cell>(&Cell::temp, "temp"), region);
+        target->loadMember(first, MemoryLocation::HOST, Selector<Cell>(&Cell::temp, "temp"), cachedRegion);
     }
 
 private:
     HostField field;
     bool rows;
+    CoordBox<3> cachedBox;
+    Region<3> cachedRegion;
 };
 
 class PullWriter : public Clonable<Writer<Cell>, PullWriter>

@@ -95,6 +95,7 @@ static void testResizeAndWriteOrder()
     CHECK(grid.get(Coord<3>(10, 2, 1)) == CELL(408.0));
     // more than one automatic flush (64 Ki cells) with rewrites in between
     B200Grid<CELL> big(CoordBox<3>(Coord<3>(), Coord<3>(64, 64, 40)));
+    big.setMaxPendingCells(1 << 16);
     CoordBox<3> box = big.boundingBox();
     for (int pass = 0; pass < 2; ++pass) {
         for (CoordBox<3>::Iterator i = box.begin(); i != box.end(); ++i) {

@@ -12,7 +12,9 @@
  * Ghost zone widths 1-4, 2-D (Game of Life) and 3-D (Jacobi 7- and 27-point).
  * Linked against libb200geo.so (GPU box) or tests/facade/mock_b200geo.cpp (CPU suite). */
 #include <libgeodecomp/geometry/partitionmanager.h>
+#include <libgeodecomp/geometry/partitions/recursivebisectionpartition.h>
 #include <libgeodecomp/geometry/partitions/stripingpartition.h>
+#include <libgeodecomp/storage/patchbuffer.h>
 #include <libgeodecomp/parallelization/nesting/vanillastepper.h>
 #include <libgeodecomp/storage/patchaccepter.h>
 #include <libgeodecomp/storage/patchprovider.h>
@@ -237,6 +239,97 @@ static void runCase(const char *name, const Coord<APITraits::SelectTopology<CELL
                 device.launchCount(), device.pullCount(), device.pushCount());
 }
 
+/* Bricks: the simulation space cut by a RecursiveBisectionPartition (geometry/partitions/recursivebisectionpartition.h:
+ * 17,103-127 — what north_star calls the 2 x 2 x 2 brick partition) into `nodes` cuboids, ONE B200Stepper per brick, the
+ * ghost zones shipped between them through the reference's own in-memory PatchAccepter + PatchProvider, PatchBuffer
+ * (storage/patchbuffer.h:19-80) — wired the way UpdateGroup wires its PatchLinks (parallelization/nesting/updategroup.h:
+ * inner ghost zone fragment -> accepter on the sender, outer ghost zone fragment -> provider on the receiver, charged with
+ * ghostZoneWidth, 2 * ghostZoneWidth, ...). The steppers are advanced round-robin, ghostZoneWidth nano steps each; the
+ * union of their own regions must equal the whole-space SerialSimulator run. No MPI, no host-side simulator. */
+template<typename CELL>
+static void runBricks(const char *name, const Coord<3>& dim, int nodes, unsigned ghostZoneWidth, unsigned rounds)
+{
+    typedef typename APITraits::SelectTopology<CELL>::Value Topology;
+    typedef B200Stepper<CELL> StepperType;
+    typedef typename StepperType::GridType GridType;
+    typedef PatchBuffer<GridType, GridType> Link;
+    const unsigned steps = ghostZoneWidth * rounds;
+    CoordBox<3> box(Coord<3>(), dim);
+
+    SerialSimulator<CELL> whole(new SeededInitializer<CELL>(dim, steps));
+    whole.run();
+
+    std::vector<std::size_t> weights(nodes, dim.prod() / nodes);
+    weights.back() += dim.prod() % nodes;
+    typename SharedPtr<Partition<3> >::Type partition(new RecursiveBisectionPartition<3>(Coord<3>(), dim, 0, weights));
+    std::vector<CoordBox<3> > boundingBoxes, expandedBoundingBoxes;
+    bool cuboids = true;
+    for (int i = 0; i < nodes; ++i) {
+        Region<3> region = partition->getRegion(i);
+        cuboids &= region.size() == (std::size_t)region.boundingBox().dimensions.prod();
+        boundingBoxes.push_back(region.boundingBox());
+        expandedBoundingBoxes.push_back(region.expandWithTopology(ghostZoneWidth, dim, Topology()).boundingBox());
+    }
+    CHECK(cuboids);
+
+    std::vector<typename SharedPtr<PartitionManager<Topology> >::Type> managers(nodes);
+    for (int i = 0; i < nodes; ++i) {
+        typename SharedPtr<AdjacencyManufacturer<3> >::Type adjacency(new DummyAdjacencyManufacturer<3>);
+        managers[i].reset(new PartitionManager<Topology>());
+        managers[i]->resetRegions(adjacency, box, partition, i, ghostZoneWidth);
+        managers[i]->resetGhostZones(boundingBoxes, expandedBoundingBoxes);
+    }
+    /* link (i -> j): i's cells inside j's ghost zone */
+    std::vector<typename StepperType::PatchAccepterVec> accepters(nodes);
+    std::vector<typename StepperType::PatchProviderVec> providers(nodes);
+    std::size_t links = 0;
+    for (int i = 0; i < nodes; ++i) {
+        typename PartitionManager<Topology>::RegionVecMap& inner = managers[i]->getInnerGhostZoneFragments();
+        for (typename PartitionManager<Topology>::RegionVecMap::iterator f = inner.begin(); f != inner.end(); ++f) {
+            int j = f->first;
+            if (j < 0 || j >= nodes || f->second.back().empty()) {
+                continue;     /* OUTGROUP pseudo node */
+            }
+            const Region<3>& sent = f->second.back();
+            const Region<3>& received = managers[j]->getOuterGhostZoneFragments()[i].back();
+            CHECK(sent == received);
+            typename SharedPtr<Link>::Type link(new Link(sent));
+            for (unsigned t = ghostZoneWidth; t <= steps + ghostZoneWidth; t += ghostZoneWidth) {
+                link->pushRequest(t);
+            }
+            accepters[i].push_back(link);
+            providers[j].push_back(link);
+            ++links;
+        }
+    }
+    std::vector<typename SharedPtr<StepperType>::Type> steppers(nodes);
+    for (int i = 0; i < nodes; ++i) {
+        typename SharedPtr<SeededInitializer<CELL> >::Type init(new SeededInitializer<CELL>(dim, steps));
+        steppers[i].reset(new StepperType(managers[i], init, accepters[i], typename StepperType::PatchAccepterVec(), providers[i]));
+    }
+    for (unsigned r = 0; r < rounds; ++r) {
+        for (int i = 0; i < nodes; ++i) {
+            steppers[i]->update(ghostZoneWidth);
+        }
+    }
+    long bad = 0, cells = 0;
+    std::size_t launches = 0;
+    for (int i = 0; i < nodes; ++i) {
+        const GridType& grid = steppers[i]->grid();
+        const Region<3>& own = managers[i]->ownRegion();
+        for (typename Region<3>::Iterator c = own.begin(); c != own.end(); ++c) {
+            bad += !(grid.get(*c) == whole.getGrid()->get(*c));
+            ++cells;
+        }
+        launches += steppers[i]->launchCount();
+        CHECK(steppers[i]->currentStep().first == steps);
+    }
+    CHECK(bad == 0);
+    CHECK(cells == (long)dim.prod());
+    std::printf("%-13s %d bricks (RecursiveBisectionPartition), ghost zone width %u, %u nano steps, %zu PatchBuffer links: "
+                "%ld of %ld cells differ from the whole-space run, %zu launches\n", name, nodes, ghostZoneWidth, steps, links, bad, cells, launches);
+}
+
 int main()
 {
     try {
@@ -246,6 +339,9 @@ int main()
         }
         runCase<Jacobi27Cube>("Jacobi27Cube", Coord<3>(9, 8, 19), 3, 8);
         runCase<ConwayCube>("ConwayCube", Coord<2>(40, 30), 2, 7);
+        runBricks<Jacobi7Cube>("Jacobi7Cube", Coord<3>(20, 18, 16), 8, 2, 4);     /* 2 x 2 x 2 */
+        runBricks<Jacobi27Cube>("Jacobi27Cube", Coord<3>(21, 17, 19), 8, 3, 3);   /* corner and edge neighbours matter */
+        runBricks<Jacobi7Cube>("Jacobi7Cube", Coord<3>(24, 10, 9), 6, 1, 5);
         /* a Torus cell is refused */
         bool refused = false;
         try {
