@@ -128,14 +128,17 @@ static void fill(const HostField& f)
     }
 }
 
-static double checksum(const HostField& f)
+static unsigned long long checksum(const HostField& f)
 {
-    /* position-weighted, so that swapped planes or rows do not cancel */
+    /* over the bit patterns, position-weighted (swapped planes or rows do not cancel), in integer arithmetic
+     * (the same value whatever the thread count) */
     const std::size_t n = (std::size_t)f.dim.prod();
-    double s = 0;
+    unsigned long long s = 0;
 #pragma omp parallel for reduction(+ : s)
     for (long long i = 0; i < (long long)n; ++i) {
-        s += f.data[i] * (double)(1 + (i % 1021));
+        unsigned long long bits;
+        std::memcpy(&bits, &f.data[i], sizeof(bits));
+        s += bits * (unsigned long long)(1 + (i % 1021));
     }
     return s;
 }
@@ -150,7 +153,7 @@ static void timeRun(SIM& sim, const HostField& field, const char *what, int n, u
     double updates = (double)n * n * n * steps;
     std::printf("{\"impl\": \"%s\", \"cell\": \"Jacobi27Cube\", \"dims\": [%d, %d, %d], \"steps\": %u, \"slabs\": %d, \"mode\": \"%s\", "
                 "\"seconds\": %.4f, \"value\": %.2f, \"unit\": \"GLUPS\", \"h2d_bytes_per_step\": %.0f, \"d2h_bytes_per_step\": %.0f, "
-                "\"checksum\": %.17g, \"what\": \"C++ program: run() of the facade simulator, Initializer from / Writer into host memory, wall clock\"}\n",
+                "\"checksum\": \"%llu\", \"what\": \"C++ program: run() of the facade simulator, Initializer from / Writer into host memory, wall clock\"}\n",
                 what, n, n, n, steps, slabs, mode, s, updates / s * 1e-9, (double)n * n * n * 8 / steps, (double)n * n * n * 8 / steps,
                 checksum(field));
     std::fflush(stdout);
