@@ -65,6 +65,43 @@ def ncu_traffic(workload):
         return None
 
 
+def measure_traffic(workload, depth):
+    """DRAM bytes one launch of the dominant kernel moves, measured NOW on this box: a child process (tools/few_launches.py:
+    the same grid, the same kernel through the same C ABI call) under `ncu --metrics dram__bytes_read.sum,
+    dram__bytes_write.sum`, third launch. Only the byte counters are taken from the profiler, never a time."""
+    kernel = {"jacobi27": "jacobi_tb", "jacobi7": "jacobi_tb", "lbm": "lbm_kernel", "jacobi7_128": "jacobi"}.get(workload)
+    if kernel is None:
+        return None
+    cmd = ["ncu", "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum", "--clock-control", "none", "-k", "regex:" + kernel,
+           "-s", "2", "-c", "1", "--csv", sys.executable, os.path.join(ROOT, "tools", "few_launches.py"), workload,
+           "jacobi.tb=%d" % depth, "--sweeps", str(4 * max(1, depth))]
+    try:
+        res = subprocess.run(cmd, capture_output=True, text=True, timeout=240, cwd=ROOT)
+    except (OSError, subprocess.TimeoutExpired):
+        return None
+    read = written = None
+    for line in res.stdout.splitlines():
+        parts = [p.strip('"') for p in line.split('","')]
+        if len(parts) < 3:
+            continue
+        try:
+            value = float(parts[-1].replace(",", "").strip('"'))
+        except ValueError:
+            continue
+        unit = parts[-2].lower()
+        scale = {"byte": 1.0, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9, "tbyte": 1e12}.get(unit)
+        if scale is None:
+            continue
+        if "dram__bytes_read.sum" in line:
+            read = value * scale
+        elif "dram__bytes_write.sum" in line:
+            written = value * scale
+    if read is None or written is None:
+        return None
+    return {"dram_bytes_per_launch": read + written, "dram_bytes_read": read, "dram_bytes_written": written, "sweeps_per_launch": depth,
+            "source": "measured in this run: ncu --metrics dram__bytes_{read,write}.sum on one launch of %s (child process)" % kernel}
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -439,7 +476,10 @@ def bench_device(workload, args, rank, world, dist, torch, with_e2e=True, with_c
     kms = ev0.elapsed_time(ev1) / n_launch               # mean duration of one launch
     per_launch = n_roof / n_launch                       # sweeps per launch (temporal blocking depth)
     achieved = alg_bytes * cells_rank * per_launch / (1e-3 * kms) / 1e9
-    traffic = ncu_traffic(workload) or {}
+    traffic = None
+    if with_clocks and rank == 0 and world == 1 and not args.no_cpu:      # the headline workload of a default run
+        traffic = measure_traffic(workload, int(round(per_launch)))
+    traffic = traffic or ncu_traffic(workload) or {}
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic.get("dram_bytes_per_launch"), "traffic_source": traffic.get("source"),
                 "kernel_ms": kms, "sweeps_per_launch": per_launch, "updates_per_launch": cells_rank * per_launch,

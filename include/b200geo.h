@@ -86,7 +86,8 @@ int b200geo_device_count(void);
  * by the temporal-blocked Jacobi kernels, 1..4; 0 = automatic: 2 for the 27-point kernel, 4 for 6/7-point), "jacobi.tb_rows" (tile shape), "jacobi.tb_zchunk", "gol.bits" (fewest sweeps per call that run
  * bit-packed; 0 = never), "gol.bits_rows", "nbody.kernel", "jacobi.pdl" (programmatic dependent launch of the one-sweep Jacobi
  * kernel: 0, 1, < 0 = small grids only), "lbm.variant" (rows per thread of the LBM kernel: 1 or 2), "jacobi.tb_promo" (L2 promotion of the
- * temporal-blocked kernel's TMA loads), "jacobi.tb_raster" (its CTA order), "nbody.run" (containers per CTA).
+ * temporal-blocked kernel's TMA loads), "jacobi.tb_raster" (its CTA order), "nbody.run" (containers per CTA), "jacobi.resident" (1: small Cube grids take the
+ * SM-resident multi-sweep kernel).
  * value < 0 restores the default. */
 int b200geo_set_tuning(const char *key, int value);
 /* number of kernels this library has launched so far in this process (bench.py: gpu_launches). */

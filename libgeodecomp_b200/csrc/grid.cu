@@ -10,7 +10,7 @@
 
 namespace b200geo {
 
-static const Tuning g_tuning_default = {0, -1, 0, 128, 0, 33, 0, 4, 0, 3, -1, 1, 0, 0, 0};
+static const Tuning g_tuning_default = {0, -1, 0, 128, 0, 33, 0, 4, 0, 3, -1, 1, 0, 0, 0, 0, 0};
 Tuning g_tuning = g_tuning_default;
 static thread_local std::string g_last_error;
 static std::atomic<uint64_t> g_launches(0);
@@ -87,6 +87,8 @@ int b200geo_set_tuning(const char *key, int value)
     else if (k == "jacobi.pdl") g_tuning.jacobi_pdl = value;
     else if (k == "jacobi.tb_promo") g_tuning.jacobi_tb_promo = value < 0 ? g_tuning_default.jacobi_tb_promo : value;
     else if (k == "nbody.run") g_tuning.nbody_run = value < 0 ? g_tuning_default.nbody_run : value;
+    else if (k == "nbody.threads") g_tuning.nbody_threads = value < 0 ? g_tuning_default.nbody_threads : value;
+    else if (k == "jacobi.resident") g_tuning.jacobi_resident = value < 0 ? g_tuning_default.jacobi_resident : value;
     else if (k == "jacobi.tb_raster") g_tuning.jacobi_tb_raster = value < 0 ? g_tuning_default.jacobi_tb_raster : value;
     else if (k == "lbm.variant") g_tuning.lbm_variant = value < 0 ? g_tuning_default.lbm_variant : value;
     else return fail(B200GEO_ERR_INVALID, "unknown tuning key " + k);
@@ -533,6 +535,20 @@ int b200geo_step(b200geo_grid *g, int kernel, const void *params, uint32_t first
         n_steps = 0;
     }
     const bool jacobi = kernel == B200GEO_KERNEL_JACOBI6 || kernel == B200GEO_KERNEL_JACOBI7 || kernel == B200GEO_KERNEL_JACOBI27;
+    // Small grids (a few million cells: BASELINE.json configs[0]): all sweeps of this call in ONE cooperative launch
+    // that keeps every brick of the grid resident in an SM (jacobi_resident.cu). Off unless "jacobi.resident" = 1:
+    // measured no faster than the streaming kernel with dependent launches (profiles/r3i_r3j_r3k)
+    if (jacobi && n_steps >= 2 && g_tuning.jacobi_resident > 0) {
+        const int kind = kernel == B200GEO_KERNEL_JACOBI6 ? 6 : kernel == B200GEO_KERNEL_JACOBI7 ? 7 : 27;
+        const int planes = jacobi_resident_planes(g, kind);
+        if (planes > 0) {
+            rc = sweep_jacobi_resident(g, kind, planes, (int)n_steps, s);
+            if (rc) return rc;
+            g->cur ^= (int)(n_steps & 1);
+            g->sweeps += n_steps;
+            n_steps = 0;
+        }
+    }
     for (uint32_t t = 0; t < n_steps;) {
         // sweeps fused into this launch: the temporal-blocked Jacobi kernel takes `depth` sweeps per
         // HBM round trip when enough valid ghost cells are there (WRAP: ghost width, PEER: what the

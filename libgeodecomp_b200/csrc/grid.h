@@ -79,6 +79,8 @@ struct Tuning {
     int lbm_variant;      // rows per thread of the LBM kernel: 1 (default) or 2
     int jacobi_tb_promo;  // L2 promotion of the temporal-blocked kernel's TMA loads: 0 none (default: 5 % faster, 9 % fewer DRAM reads than 256 B, profiles/r3c), 1 64 B, 2 128 B, 3 256 B
     int nbody_run;        // containers per CTA of the fused n-body kernel: 8, 12 or 16 (0 = automatic: 16 for float, 8 for double)
+    int nbody_threads;    // threads per CTA of the fused n-body kernel (0 = automatic: 16 per container of a run)
+    int jacobi_resident;  // SM-resident multi-sweep kernel for small grids: 1 = whenever the grid qualifies, 0 = never (default: not faster, profiles/r3i_r3j_r3k)
     int jacobi_tb_raster; // CTA order of the temporal-blocked kernel: 0 = x fastest (default), n > 0 = y-panels of n tile rows, y fastest
 };
 extern Tuning g_tuning;
@@ -90,6 +92,8 @@ void count_launch(uint64_t n = 1);
 // kernel families (one translation unit each)
 int sweep_jacobi(b200geo_grid *g, int kind, const Box& box, cudaStream_t s);
 int sweep_jacobi_tb(b200geo_grid *g, int kind, int depth, const Box& box, cudaStream_t s);
+int jacobi_resident_planes(const b200geo_grid *g, int kind);
+int sweep_jacobi_resident(b200geo_grid *g, int kind, int planes, int sweeps, cudaStream_t s);
 int sweep_gol(b200geo_grid *g, const Box& box, cudaStream_t s);
 bool gol_bits_applicable(const b200geo_grid *g);
 int sweep_gol_bits(b200geo_grid *g, uint32_t sweeps, cudaStream_t s);

@@ -319,25 +319,39 @@ fused_kernel(const int32_t *__restrict__ cnt_old, const REAL *__restrict__ part_
                 round_up(ex + D.edge, qx);
                 round_up(ey + D.edge, qy);
                 round_up(ez + D.edge, qz);
-#pragma unroll
-                for (int k = 0; k < 27; ++k) {
-                    if (!rebin && k != 13) continue;
-                    const int cell = ((k / 9) * 3 + (k / 3) % 3) * (G + 2) + j + k % 3;
-                    const int cn = scnt[cell];
-                    for (int b = 0; b < cn; b += 32) {
-                        const int sl = b + lane;
-                        bool inside = false;
-                        if (sl < cn) {
-                            const REAL *q = spos + cell * SP + sl;
-                            const REAL px = q[0], py = q[cap], pz = q[2 * cap];
-                            inside = !rebin || (ox <= px && oy <= py && oz <= pz && px < qx && py < qy && pz < qz);
+                // the 27 source containers in reference order, TWO per warp iteration where both hold at most 16
+                // particles (lanes 0-15 the first, lanes 16-31 the second: the ordered compaction by ballot / popc keeps
+                // the order) — containers hold ~13 particles, so a scan of one container kept 13 of 32 lanes busy
+                auto scan = [&](int cell, int sl, bool use) {
+                    bool inside = false;
+                    if (use) {
+                        const REAL *q = spos + cell * SP + sl;
+                        const REAL px = q[0], py = q[cap], pz = q[2 * cap];
+                        inside = !rebin || (ox <= px && oy <= py && oz <= pz && px < qx && py < qy && pz < qz);
+                    }
+                    const unsigned mask = __ballot_sync(0xffffffffu, inside);
+                    if (inside) {
+                        const int dst = n + __popc(mask & ((1u << lane) - 1));
+                        if (dst < cap) newidx[j * cap + dst] = (unsigned short)(cell * SP + sl);
+                    }
+                    n += __popc(mask);
+                };
+                auto cell_of = [&](int k) { return ((k / 9) * 3 + (k / 3) % 3) * (G + 2) + j + k % 3; };
+                if (!rebin) {
+                    const int cell = cell_of(13), cn = scnt[cell];
+                    for (int b = 0; b < cn; b += 32) scan(cell, b + lane, b + lane < cn);
+                } else {
+#pragma unroll 1
+                    for (int k = 0; k < 27; k += 2) {
+                        const int c0 = cell_of(k), n0 = scnt[c0];
+                        const int c1 = k + 1 < 27 ? cell_of(k + 1) : c0, n1 = k + 1 < 27 ? scnt[c1] : 0;
+                        if (n0 <= 16 && n1 <= 16) {
+                            const int half = lane >> 4, sl = lane & 15;
+                            scan(half ? c1 : c0, sl, sl < (half ? n1 : n0));
+                        } else {
+                            for (int b = 0; b < n0; b += 32) scan(c0, b + lane, b + lane < n0);
+                            for (int b = 0; b < n1; b += 32) scan(c1, b + lane, b + lane < n1);
                         }
-                        const unsigned mask = __ballot_sync(0xffffffffu, inside);
-                        if (inside) {
-                            const int dst = n + __popc(mask & ((1u << lane) - 1));
-                            if (dst < cap) newidx[j * cap + dst] = (unsigned short)(cell * SP + sl);
-                        }
-                        n += __popc(mask);
                     }
                 }
                 if (lane == 0) {
@@ -681,21 +695,36 @@ int sweep(b200geo_boxgrid *g, const b200geo_nbody_params *p, int rebin, cudaStre
         }
         force_kernel<REAL, RUN><<<(unsigned)((int64_t)runs * D.ny * D.nz), 128, smem, s>>>(co, po, cn, pn, D, 0, runs, (REAL)p->dt, rc * rc);
     } else if (g_tuning.nbody_kernel == 3 || g->cap > 32) {
-        // first-generation fused kernel (per-thread candidate lists): any capacity up to 64
-        constexpr int G = sizeof(REAL) == 4 ? 16 : 8, NT = 16 * G, LMAX = 88, NC = (G + 2) * 9;
-        int runs = (D.nx + G - 1) / G;
-        size_t smem = (size_t)NC * (3 * g->cap + 4) * sizeof(REAL) + (NC + G + 2) * sizeof(int) + 8 +
-                      (size_t)(G * g->cap + 2) * sizeof(unsigned short) + (size_t)LMAX * NT * sizeof(unsigned short);
-        if (smem > 227 * 1024) return fail(B200GEO_ERR_LOGIC, "container capacity too large for the fused kernel's shared memory");
-        static bool attr3[64] = {false};  // per device
-        if (!attr3[g->device & 63]) {
-            B200GEO_CUDA(cudaFuncSetAttribute(fused_kernel<REAL, G, NT, LMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-            attr3[g->device & 63] = true;
-        }
-        // enlarged cutoff of the candidate filter
+        // first-generation fused kernel (per-thread candidate lists): any capacity up to 64. Runs of G containers hold
+        // ~13 G particles on 16 G threads; fewer threads ("nbody.threads") keep more lanes busy but send the runs that hold
+        // more particles than threads through the whole loop twice, and lose
+        constexpr int G = sizeof(REAL) == 4 ? 16 : 8, LMAX = 88, NC = (G + 2) * 9;
         REAL loose = rc * rc * (REAL)(1.0 + 1.0 / 65536.0);
-        fused_kernel<REAL, G, NT, LMAX><<<(unsigned)((int64_t)runs * D.ny * D.nz), NT, smem, s>>>(
-            co, po, cn, pn, D, 0, runs, (REAL)p->dt, rc * rc, loose, rebin, g->overflow);
+        int runs = (D.nx + G - 1) / G;
+#define NBODY_LAUNCH1(NT)                                                                                                   \
+        do {                                                                                                                \
+            size_t smem = (size_t)NC * (3 * g->cap + 4) * sizeof(REAL) + (NC + G + 2) * sizeof(int) + 8 +                   \
+                          (size_t)(G * g->cap + 2) * sizeof(unsigned short) + (size_t)LMAX * NT * sizeof(unsigned short);   \
+            if (smem > 227 * 1024) return fail(B200GEO_ERR_LOGIC, "container capacity too large for the fused kernel's shared memory"); \
+            static bool attr3[64] = {false};                                                                                \
+            if (!attr3[g->device & 63]) {                                                                                   \
+                B200GEO_CUDA(cudaFuncSetAttribute(fused_kernel<REAL, G, NT, LMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
+                attr3[g->device & 63] = true;                                                                               \
+            }                                                                                                               \
+            fused_kernel<REAL, G, NT, LMAX><<<(unsigned)((int64_t)runs * D.ny * D.nz), NT, smem, s>>>(                       \
+                co, po, cn, pn, D, 0, runs, (REAL)p->dt, rc * rc, loose, rebin, g->overflow);                               \
+        } while (0)
+        // (whole warps only: 14 per container for runs of 16, i.e. float)
+        constexpr bool LEAN = (14 * G) % 32 == 0;
+        const int threads = g_tuning.nbody_threads > 0 ? g_tuning.nbody_threads : 16 * G;   // measured: 256 / 224 / 192 threads = 14.1 / 16.2 / 17.0 ms (profiles/r3j)
+        if constexpr (LEAN) {
+            if (threads == 14 * G) NBODY_LAUNCH1(14 * G);
+            else if (threads == 12 * G) NBODY_LAUNCH1(12 * G);
+            else NBODY_LAUNCH1(16 * G);
+        } else {
+            NBODY_LAUNCH1(16 * G);
+        }
+#undef NBODY_LAUNCH1
     } else {
         // second-generation fused kernel (per-container masks); run length / CTA size: "nbody.run" = 8 or 16
         REAL loose = rc * rc * (REAL)(1.0 + 1.0 / 65536.0);

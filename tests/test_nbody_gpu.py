@@ -36,14 +36,16 @@ def nbody_kernel():
     3 = fused re-bin / candidate-list kernel (default), 0 = fused kernel with per-container masks, 8 / 12 = the
     default kernel with runs of 8 / 12 containers per CTA ("nbody.run")"""
     def set_(value):
-        capi.set_tuning("nbody.kernel", value if value in (1, 3) else 0)   # 0 / 8 / 12: the mask kernel
+        capi.set_tuning("nbody.kernel", value if value in (1, 3) else (3 if value in (192, 256) else 0))   # 0 / 8 / 12: the mask kernel
         capi.set_tuning("nbody.run", value if value in (8, 12) else -1)
+        capi.set_tuning("nbody.threads", value if value in (192, 256) else -1)   # of the candidate-list kernel (default 224 for float)
     yield set_
     capi.set_tuning("nbody.kernel", -1)
     capi.set_tuning("nbody.run", -1)
+    capi.set_tuning("nbody.threads", -1)
 
 
-@pytest.mark.parametrize("kernel", [0, 1, 3, 8, 12])
+@pytest.mark.parametrize("kernel", [0, 1, 3, 8, 12, 192, 256])
 @pytest.mark.parametrize("real", [np.float32, np.float64])
 @pytest.mark.parametrize("dims,steps,vel,dt", [((6, 5, 4), 10, 8.0, 0.01), ((9, 3, 2), 6, 20.0, 0.02), ((1, 1, 1), 5, 1.0, 0.01),
                                                ((17, 4, 3), 8, 10.0, 0.01), ((8, 8, 8), 10, 0.0, 0.005), ((2, 1, 7), 9, 15.0, 0.01)])
@@ -81,7 +83,7 @@ def test_nbody_golden_from_the_reference(key):
     assert np.array_equal(po.view(np.uint8), z[key + "_out_parts"].view(np.uint8))
 
 
-@pytest.mark.parametrize("kernel", [0, 1, 3, 8])
+@pytest.mark.parametrize("kernel", [0, 1, 3, 8, 256])
 @pytest.mark.parametrize("real", [np.float32, np.float64])
 def test_nbody_dense_containers_overflow_the_candidate_lists(oracle, nbody_kernel, kernel, real):
     """~27 (capacity 32) and ~33 (capacity 48) particles per container: more than 88 candidates pass the

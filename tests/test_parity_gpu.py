@@ -79,6 +79,27 @@ def test_jacobi_temporal_blocking_z_chunks(oracle, tuning):
         assert np.array_equal(got, oracle.jacobi(kind, False, data, 8, edge=-1.5))
 
 
+@pytest.mark.parametrize("kind", [6, 7])
+@pytest.mark.parametrize("shape,steps", [((128, 128, 128), 7), ((64, 128, 100), 4), ((128, 144, 128), 3), ((64, 128, 128), 2),
+                                         ((128, 128, 128), 1)])
+def test_jacobi_sm_resident_kernel(oracle, tuning, kind, shape, steps):
+    """small Cube grids: all sweeps of a step() call in one cooperative launch, bricks resident in the SMs
+    (csrc/jacobi_resident.cu; 8 or 4 planes per brick), odd and even sweep counts; == the streaming kernels == the oracle"""
+    tuning("jacobi.tb", 1)          # the streaming path beside it: one launch per sweep
+    tuning("jacobi.resident", 1)
+    before = capi.launch_count()
+    data, got = run_jacobi(kind, False, shape, steps, edge=0.25)
+    launches = capi.launch_count() - before
+    want = oracle.jacobi(kind, False, data, steps, edge=0.25)
+    assert np.array_equal(got, want)
+    tuning("jacobi.resident", 0)
+    before = capi.launch_count()
+    data, plain = run_jacobi(kind, False, shape, steps, edge=0.25)
+    assert np.array_equal(plain, want)
+    if steps >= 2:
+        assert capi.launch_count() - before - launches == steps - 1   # one launch for all sweeps instead of one per sweep
+
+
 @pytest.mark.parametrize("kind", [7, 27])
 def test_jacobi_config1_128cubed_100_steps(oracle, kind):
     """BASELINE.json config 1: 128^3 double, 100 steps, Cube and the example's Torus."""

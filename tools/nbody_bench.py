@@ -32,6 +32,8 @@ def main():
     model = (models.NBodyF if real == np.float32 else models.NBodyD)
     if os.environ.get("NBODY_KERNEL"):
         capi.set_tuning("nbody.kernel", int(os.environ["NBODY_KERNEL"]))
+    if os.environ.get("NBODY_THREADS"):
+        capi.set_tuning("nbody.threads", int(os.environ["NBODY_THREADS"]))
     if os.environ.get("NBODY_RUN"):
         capi.set_tuning("nbody.run", int(os.environ["NBODY_RUN"]))
     t0 = time.time()
