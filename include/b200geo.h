@@ -171,6 +171,9 @@ int b200geo_swap(b200geo_grid *g);
  * b200geo_step; needed before b200geo_update_box on Torus axes). */
 int b200geo_refresh_ghosts(b200geo_grid *g, void *stream);
 int b200geo_sync(void *stream);
+/* wait for `stream` of the device this grid lives on (b200geo_sync waits on the calling thread's CURRENT device: a host
+ * thread that drives several GPUs — slab groups — uses this one) */
+int b200geo_grid_sync(const b200geo_grid *g, void *stream);
 /* Plain device memory on `device` for region buffers that stay on the GPU: the device twins of the host-side
  * PatchBufferFixed a Stepper keeps for its rim and its volatile kernel (parallelization/nesting/commonstepper.h:
  * 29-30, 236-283; storage/patchbufferfixed.h) — filled and drained by b200geo_grid_save_region /

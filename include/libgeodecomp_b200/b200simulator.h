@@ -474,7 +474,7 @@ public:
     void sync() const
     {
         flush();
-        B200Helpers::check(b200geo_sync(0));
+        B200Helpers::check(b200geo_grid_sync(handle, 0));
     }
 
     /* UpdateFunctor over an arbitrary Region (storage/updatefunctor.h:403-428 takes a Region, too): one sweep of
@@ -601,6 +601,14 @@ public:
         return device;
     }
 
+    /* Member copies of plain selectors are enqueued without waiting for them (the caller synchronises): lets a slab
+     * group keep the links of all its GPUs busy at once (B200StripedGrid). Page-locked host memory only — pageable
+     * copies are synchronous anyway. */
+    void setDeferSync(bool defer) const
+    {
+        deferSync = defer;
+    }
+
     /* combined host writes are shipped when this many cells are pending (default: 2 MiB worth, at least 64 Ki cells) */
     void setMaxPendingCells(std::size_t cells)
     {
@@ -673,7 +681,9 @@ protected:
                 target += selector.sizeOfExternal() * boxes[k].cells();
             }
             memberCalls += boxes.size();
-            sync();
+            if (!deferSync) {
+                sync();
+            }
             return;
         }
         for (typename Region<DIM>::StreakIterator i = begin; i != end; ++i) {
@@ -707,7 +717,9 @@ protected:
                 source += selector.sizeOfExternal() * boxes[k].cells();
             }
             memberCalls += boxes.size();
-            sync();
+            if (!deferSync) {
+                sync();
+            }
             return;
         }
         for (typename Region<DIM>::StreakIterator i = begin; i != end; ++i) {
@@ -742,6 +754,7 @@ private:
     mutable int rowCacheRows = 0;
     mutable bool rowCacheValid = false;
     mutable std::size_t memberCalls = 0;
+    mutable bool deferSync = false;
     mutable std::string lastSelectorName;          /* findMember: the selector asked for last and its member */
     mutable std::size_t lastSelectorBytes = 0;
     mutable int lastSelectorMember = -1;

@@ -280,13 +280,19 @@ protected:
         const typename Region<DIM>::StreakIterator& begin,
         const typename Region<DIM>::StreakIterator& end) const
     {
+        /* all slabs' copies are enqueued first and awaited afterwards: the GPUs' links work at the same time */
         std::vector<Region<DIM> > parts = split(begin, end);
         for (std::size_t s = 0; s < slabs.size(); ++s) {
             if (parts[s].size() == 0) {
                 continue;
             }
+            slabs[s]->setDeferSync(true);
             slabs[s]->saveMemberStreaks(target, targetLocation, selector, parts[s].beginStreak(), parts[s].endStreak());
+            slabs[s]->setDeferSync(false);
             target += selector.sizeOfExternal() * parts[s].size();
+        }
+        for (std::size_t s = 0; s < slabs.size(); ++s) {
+            slabs[s]->sync();
         }
     }
 
@@ -302,8 +308,13 @@ protected:
             if (parts[s].size() == 0) {
                 continue;
             }
+            slabs[s]->setDeferSync(true);
             slabs[s]->loadMemberStreaks(source, sourceLocation, selector, parts[s].beginStreak(), parts[s].endStreak());
+            slabs[s]->setDeferSync(false);
             source += selector.sizeOfExternal() * parts[s].size();
+        }
+        for (std::size_t s = 0; s < slabs.size(); ++s) {
+            slabs[s]->sync();
         }
         dirty = true;
     }

@@ -80,6 +80,7 @@ SYMBOLS = [
     ("b200geo_swap", ctypes.c_int, [_vp]),
     ("b200geo_refresh_ghosts", ctypes.c_int, [_vp, _vp]),
     ("b200geo_sync", ctypes.c_int, [_vp]),
+    ("b200geo_grid_sync", ctypes.c_int, [_vp, _vp]),
     ("b200geo_device_alloc", ctypes.c_int, [ctypes.c_int, ctypes.c_uint64, ctypes.POINTER(ctypes.c_void_p)]),
     ("b200geo_device_free", ctypes.c_int, [ctypes.c_int, _vp]),
     ("b200geo_host_alloc", ctypes.c_int, [ctypes.c_uint64, ctypes.POINTER(ctypes.c_void_p)]),

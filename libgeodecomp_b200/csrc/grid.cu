@@ -665,6 +665,14 @@ int b200geo_sync(void *stream)
     return B200GEO_OK;
 }
 
+int b200geo_grid_sync(const b200geo_grid *g, void *stream)
+{
+    if (!g) return fail(B200GEO_ERR_INVALID, "null grid");
+    B200GEO_CUDA(cudaSetDevice(g->device));
+    B200GEO_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    return B200GEO_OK;
+}
+
 int b200geo_device_alloc(int device, uint64_t bytes, void **ptr)
 {
     if (!ptr) return fail(B200GEO_ERR_INVALID, "null argument");

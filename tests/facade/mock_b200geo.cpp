@@ -441,6 +441,7 @@ int b200geo_refresh_ghosts(b200geo_grid *g, void *)
     return B200GEO_OK;
 }
 int b200geo_sync(void *) { return B200GEO_OK; }
+int b200geo_grid_sync(const b200geo_grid *, void *) { return B200GEO_OK; }
 int b200geo_device_alloc(int, uint64_t bytes, void **ptr) { *ptr = malloc(bytes ? (size_t)bytes : 1); return *ptr ? B200GEO_OK : fail(B200GEO_ERR_NOMEM, "out of memory"); }
 int b200geo_device_free(int, void *ptr) { free(ptr); return B200GEO_OK; }
 int b200geo_host_alloc(uint64_t bytes, void **ptr) { *ptr = malloc(bytes ? (size_t)bytes : 1); return *ptr ? B200GEO_OK : fail(B200GEO_ERR_NOMEM, "out of memory"); }
