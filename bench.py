@@ -406,14 +406,19 @@ def bench_device(workload, args, rank, world, dist, torch, with_e2e=True, with_c
     gdims = list(dims)
     gdims[last] = dims[last] * world
     z0 = dims[last] * rank
-    keep = []
+    keep, padded = [], []
+    # slabs whose e2e leg will be streamed get their ghost zones (as wide as the run is long) in the SAME pinned
+    # allocation, around the slab: one page-locked buffer per member and rank, not two
+    pad_lo, pad_hi = stream_pads(workload, args, rank, world, dims) if with_e2e else (0, 0)
 
     def alloc(shape, dtype):
-        t = torch.empty(shape, dtype=getattr(torch, np.dtype(dtype).name), pin_memory=with_e2e)
+        t = torch.empty((shape[0] + pad_lo + pad_hi,) + tuple(shape[1:]), dtype=getattr(torch, np.dtype(dtype).name), pin_memory=with_e2e)
         keep.append(t)
-        return t.numpy()
+        padded.append(t.numpy())
+        return t.numpy()[pad_lo:pad_lo + shape[0]]
 
     model, members = synth_members(workload, dims, z0, gdims[last], alloc, share=not with_e2e)
+    ext = dict(zip(members.keys(), padded)) if with_e2e else None
     cells_rank = float(np.prod(dims))
     cells_all = cells_rank * world
     K, W = args.steps, args.warmup
@@ -496,7 +501,7 @@ def bench_device(workload, args, rank, world, dist, torch, with_e2e=True, with_c
 
     # ---- end to end through the public API with host buffers
     if with_e2e:
-        out.update(e2e_legs(workload, args, rank, world, dist, torch, sim, model, members, dims, gdims, z0, depth, barrier))
+        out.update(e2e_legs(workload, args, rank, world, dist, torch, sim, model, members, ext, (pad_lo, pad_hi), dims, gdims, z0, depth, barrier))
     del sim
     return out
 
@@ -525,6 +530,27 @@ def make_plugins(pinned, host_out, last, z0):
     return Init, PullWriter
 
 
+def stream_wanted(workload, args, world, dims):
+    """does the e2e leg of this workload get a streamed run? Large Jacobi grids on a Cube; on slabs only while ghost zones
+    as wide as the run add at most 25 % to the slab"""
+    from libgeodecomp_b200 import models
+    model = models.ALL[WORKLOADS[workload][0]]
+    nz = dims[-1]
+    grid_bytes = float(np.prod(dims)) * sum(t.itemsize for _, t in model.members)
+    if not getattr(model, "fuses_sweeps", False) or model.wraps or grid_bytes < (1 << 30) or args.no_stream:
+        return False
+    return world == 1 or 8 * args.steps * model.nano_steps <= nz
+
+
+def stream_pads(workload, args, rank, world, dims):
+    """ghost planes (low, high) a rank's pinned input arrays carry for the streamed leg"""
+    from libgeodecomp_b200 import models
+    if world == 1 or not stream_wanted(workload, args, world, dims):
+        return 0, 0
+    G = args.steps * models.ALL[WORKLOADS[workload][0]].nano_steps
+    return (G if rank > 0 else 0), (G if rank < world - 1 else 0)
+
+
 def all_ranks(flag, world, dist, torch):
     """[flag of rank 0, flag of rank 1, ...] on every rank"""
     t = torch.tensor([1 if flag else 0], dtype=torch.int64, device="cuda")
@@ -542,7 +568,42 @@ def max_over_ranks(ms, world, dist, torch):
     return float(t.item())
 
 
-def e2e_legs(workload, args, rank, world, dist, torch, sim, model, members, dims, gdims, z0, depth, barrier):
+def host_link(world, dist, torch, barrier, nbytes=1 << 30):
+    """What the links between host memory and the GPUs carry on THIS box with all ranks copying at once (page-locked
+    memory, CUDA events, max over ranks): the ceiling of every e2e number. One GiB per direction and rank."""
+    host = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+    host2 = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+    dev = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    dev2 = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    side = torch.cuda.Stream()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def timed(fn):
+        fn()                      # warm-up
+        barrier()
+        ev0.record()
+        fn()
+        ev1.record()
+        barrier()
+        return max_over_ranks(ev0.elapsed_time(ev1), world, dist, torch)
+
+    def duplex():
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            host2.copy_(dev2, non_blocking=True)
+        dev.copy_(host, non_blocking=True)
+        torch.cuda.current_stream().wait_stream(side)
+
+    up = timed(lambda: dev.copy_(host, non_blocking=True))
+    down = timed(lambda: host.copy_(dev, non_blocking=True))
+    both = timed(duplex)
+    gb = nbytes / 1e9
+    return {"ranks": world, "h2d_gbs_per_rank": gb / (1e-3 * up), "d2h_gbs_per_rank": gb / (1e-3 * down),
+            "duplex_gbs_per_rank": 2 * gb / (1e-3 * both), "aggregate_duplex_gbs": 2 * gb * world / (1e-3 * both),
+            "what": "1 GiB per direction and rank, page-locked, all ranks at once, max over ranks"}
+
+
+def e2e_legs(workload, args, rank, world, dist, torch, sim, model, members, ext, pads, dims, gdims, z0, depth, barrier):
     """The e2e legs of one workload: StripedSimulator.run() from pinned host arrays back into pinned host arrays,
     (1) with the plain schedule (upload, sweeps with halo exchanges, download), (2) — large Jacobi grids — with the
     streamed schedule. Every result is checked: windows against the oracle on every rank, and the two schedules'
@@ -600,6 +661,14 @@ def e2e_legs(workload, args, rank, world, dist, torch, sim, model, members, dims
         sim.initializer = Init(gdims, vsteps)
         sim.run()
         barrier()
+    try:
+        link = host_link(world, dist, torch, barrier)
+        # the time the run's host traffic alone takes at that rate: one way after the other (plain) / both ways at once (streamed)
+        link["plain_floor_ms"] = 1e3 * (grid_bytes / 1e9) * (1 / link["h2d_gbs_per_rank"] + 1 / link["d2h_gbs_per_rank"])
+        link["streamed_floor_ms"] = 1e3 * 2 * (grid_bytes / 1e9) / link["duplex_gbs_per_rank"]
+        res["host_link"] = link
+    except Exception as e:  # noqa: BLE001 - a diagnostic
+        res["host_link"] = {"error": repr(e)}
     ver = checked(members, vsteps)
     if ver is not None:
         ver["what"] = ("the timed e2e run's pulled result" if vsteps == K else "an untimed repeat of the e2e call with %d steps" % vsteps) + \
@@ -610,28 +679,16 @@ def e2e_legs(workload, args, rank, world, dist, torch, sim, model, members, dims
 
     # ---- (2) the streamed schedule
     G = K * model.nano_steps if world > 1 else 0     # ghost zones as wide as the run is long: no exchange while streaming
-    wanted = model.fuses_sweeps and not model.wraps and grid_bytes >= (1 << 30) and not args.no_stream
-    if wanted and world > 1 and 8 * G > nz:
+    pad_lo, pad_hi = pads
+    wanted = stream_wanted(workload, args, world, dims)
+    if not wanted and world > 1 and WORKLOADS[workload][0].startswith("Jacobi") and not args.no_stream and grid_bytes >= (1 << 30):
         res["e2e"]["streamed_schedule"] = {"skipped": "%d sweeps: ghost zones of that width would add more than 25 %% to a slab of %d planes" % (G, nz)}
-        wanted = False
     if not wanted:
         return res
     try:
         name = model.members[0][0]
         own = members[name]
-        # the plain result on the device, for the element-wise comparison (K > 40: recomputed below from the same input)
-        pad_lo = G if rank > 0 else 0
-        pad_hi = G if rank < world - 1 else 0
-        keep = []
-
-        def alloc(shape, dtype):
-            t = torch.empty(shape, dtype=getattr(torch, np.dtype(dtype).name), pin_memory=True)
-            keep.append(t)
-            return t.numpy()
-
-        # one rank: the arrays of the plain leg serve again; slabs: room for the ghost zones around the slab
-        ext = members if pad_lo + pad_hi == 0 else {n: alloc((nz + pad_lo + pad_hi,) + a.shape[1:], a.dtype) for n, a in members.items()}
-        own_view = {n: a[pad_lo:pad_lo + nz] for n, a in ext.items()}
+        own_view = members      # views into `ext` (bench_device allocated slab and ghost zones in one piece)
 
         def refill():
             spare = iter(list(own_view.values()))
@@ -960,6 +1017,8 @@ def main():
         }
         if main_res.get("verified") is not None:
             line["verified"] = main_res["verified"]
+        if main_res.get("host_link") is not None:
+            line["host_link"] = main_res["host_link"]
         if cpu is not None:
             line["cpu_baseline"] = cpu
         if gpu_ref is not None:
