@@ -10,7 +10,7 @@
 
 namespace b200geo {
 
-static const Tuning g_tuning_default = {0, -1, 0, 128, 0, 33, 0, 4, 0, 3, -1, 1, 0, 0, 0, 0, 0};
+static const Tuning g_tuning_default = {0, -1, 0, 128, 0, 33, 0, 4, 0, 3, -1, 1, 0, 0, 0, 0, 0, 2, 14, 0, 0};
 Tuning g_tuning = g_tuning_default;
 static thread_local std::string g_last_error;
 static std::atomic<uint64_t> g_launches(0);
@@ -91,6 +91,10 @@ int b200geo_set_tuning(const char *key, int value)
     else if (k == "jacobi.resident") g_tuning.jacobi_resident = value < 0 ? g_tuning_default.jacobi_resident : value;
     else if (k == "jacobi.tb_raster") g_tuning.jacobi_tb_raster = value < 0 ? g_tuning_default.jacobi_tb_raster : value;
     else if (k == "lbm.variant") g_tuning.lbm_variant = value < 0 ? g_tuning_default.lbm_variant : value;
+    else if (k == "lbm.tb") g_tuning.lbm_tb = value < 0 ? g_tuning_default.lbm_tb : value;
+    else if (k == "lbm.tb_rows") g_tuning.lbm_tb_rows = value < 0 ? g_tuning_default.lbm_tb_rows : value;
+    else if (k == "lbm.tb_promo") g_tuning.lbm_tb_promo = value < 0 ? g_tuning_default.lbm_tb_promo : value;
+    else if (k == "lbm.tb_zchunk") g_tuning.lbm_tb_zchunk = value < 0 ? g_tuning_default.lbm_tb_zchunk : value;
     else return fail(B200GEO_ERR_INVALID, "unknown tuning key " + k);
     return B200GEO_OK;
 }
@@ -466,6 +470,15 @@ int b200geo_grid_save_region(const b200geo_grid *g, const int32_t *streaks, int 
     return region_io(const_cast<b200geo_grid *>(g), streaks, n_streaks, buf, location, true, 0, (cudaStream_t)stream);
 }
 
+// LBM params: int32 macroscopic store mode: 0 (default) = only on the last sweep of this call, 1 = on every sweep
+// (what the reference cell does; liquid cells overwrite them sweep after sweep, wall cells never write them: the grid
+// after the call is the same as with mode 0), 2 = never (caller is mid-run)
+static bool lbm_stores_macroscopic(const void *params, bool last)
+{
+    int mode = params ? *(const int32_t *)params : 0;
+    return mode == 1 || (mode == 0 && last);
+}
+
 static int dispatch(b200geo_grid *g, int kernel, const void *params, const Box& box, bool last, cudaStream_t s)
 {
     if (box.x1 <= box.x0 || box.y1 <= box.y0 || box.z1 <= box.z0) return B200GEO_OK;
@@ -478,12 +491,8 @@ static int dispatch(b200geo_grid *g, int kernel, const void *params, const Box& 
         return sweep_jacobi(g, 27, box, s);
     case B200GEO_KERNEL_GOL:
         return sweep_gol(g, box, s);
-    case B200GEO_KERNEL_LBM_D3Q19: {
-        // params: int32 macroscopic store mode: 0 (default) = only on the last sweep of this call,
-        // 1 = on every sweep (what the reference cell does), 2 = never (caller is mid-run)
-        int mode = params ? *(const int32_t *)params : 0;
-        return sweep_lbm(g, box, mode == 1 || (mode == 0 && last), s);
-    }
+    case B200GEO_KERNEL_LBM_D3Q19:
+        return sweep_lbm(g, box, lbm_stores_macroscopic(params, last), s);
     default:
         return fail(B200GEO_ERR_LOGIC, "no kernel bound for this id");
     }
@@ -535,6 +544,7 @@ int b200geo_step(b200geo_grid *g, int kernel, const void *params, uint32_t first
         n_steps = 0;
     }
     const bool jacobi = kernel == B200GEO_KERNEL_JACOBI6 || kernel == B200GEO_KERNEL_JACOBI7 || kernel == B200GEO_KERNEL_JACOBI27;
+    const bool lbm = kernel == B200GEO_KERNEL_LBM_D3Q19;
     // Small grids (a few million cells: BASELINE.json configs[0]): all sweeps of this call in ONE cooperative launch
     // that keeps every brick of the grid resident in an SM (jacobi_resident.cu). Off unless "jacobi.resident" = 1:
     // measured no faster than the streaming kernel with dependent launches (profiles/r3i_r3j_r3k)
@@ -556,8 +566,10 @@ int b200geo_step(b200geo_grid *g, int kernel, const void *params, uint32_t first
         int depth = 1;
         // 0 = automatic (measured on B200, profiles/r1s_tuning.md): the 27-point kernel is fastest with two
         // fused sweeps (deeper blocking runs out of registers), the 6/7-point kernels with four
-        const int tb = g_tuning.jacobi_tb != 0 ? g_tuning.jacobi_tb : (kernel == B200GEO_KERNEL_JACOBI27 ? 2 : 4);
-        if (jacobi && tb > 1) {
+        // the LBM kernel fuses two (lbm_tb.cu)
+        const int tb = lbm ? (g_tuning.lbm_tb >= 2 ? 2 : 1) :
+            g_tuning.jacobi_tb != 0 ? g_tuning.jacobi_tb : (kernel == B200GEO_KERNEL_JACOBI27 ? 2 : 4);
+        if ((jacobi || lbm) && tb > 1) {
             depth = tb > 4 ? 4 : tb;
             if ((uint32_t)depth > n_steps - t) depth = (int)(n_steps - t);
             for (int i = 0; i < 3; ++i)
@@ -579,7 +591,8 @@ int b200geo_step(b200geo_grid *g, int kernel, const void *params, uint32_t first
         }
         rc = refresh_wrap(g, s);
         if (rc) return rc;
-        if (depth > 1) rc = sweep_jacobi_tb(g, kernel == B200GEO_KERNEL_JACOBI6 ? 6 : kernel == B200GEO_KERNEL_JACOBI7 ? 7 : 27, depth, box, s);
+        if (depth > 1 && lbm) rc = sweep_lbm_tb2(g, box, lbm_stores_macroscopic(params, t + depth == n_steps), s);
+        else if (depth > 1) rc = sweep_jacobi_tb(g, kernel == B200GEO_KERNEL_JACOBI6 ? 6 : kernel == B200GEO_KERNEL_JACOBI7 ? 7 : 27, depth, box, s);
         else rc = dispatch(g, kernel, params, box, t + 1 == n_steps, s);
         if (rc) return rc;
         g->cur ^= 1;
@@ -623,9 +636,10 @@ int b200geo_update_box_n(b200geo_grid *g, int kernel, const void *params, uint32
     if (!g || !origin || !dim) return fail(B200GEO_ERR_INVALID, "null argument");
     int rc = check_kernel_grid(g, kernel);
     if (rc) return rc;
-    if (kernel != B200GEO_KERNEL_JACOBI6 && kernel != B200GEO_KERNEL_JACOBI7 && kernel != B200GEO_KERNEL_JACOBI27)
+    const bool lbm = kernel == B200GEO_KERNEL_LBM_D3Q19;
+    if (!lbm && kernel != B200GEO_KERNEL_JACOBI6 && kernel != B200GEO_KERNEL_JACOBI7 && kernel != B200GEO_KERNEL_JACOBI27)
         return fail(B200GEO_ERR_LOGIC, "this kernel family cannot fuse sweeps");
-    if (n_sweeps < 1 || n_sweeps > 4) return fail(B200GEO_ERR_INVALID, "n_sweeps must be 1..4");
+    if (n_sweeps < 1 || n_sweeps > (lbm ? 2u : 4u)) return fail(B200GEO_ERR_INVALID, lbm ? "n_sweeps must be 1..2" : "n_sweeps must be 1..4");
     const int n = (int)n_sweeps;
     for (int i = 0; i < 3; ++i) {
         bool slab = i == g->slab_axis && g->g[i] > 0;
@@ -640,6 +654,7 @@ int b200geo_update_box_n(b200geo_grid *g, int kernel, const void *params, uint32
     if (dim[0] == 0 || dim[1] == 0 || dim[2] == 0) return B200GEO_OK;
     B200GEO_CUDA(cudaSetDevice(g->device));
     Box box = {origin[0], origin[1], origin[2], origin[0] + dim[0], origin[1] + dim[1], origin[2] + dim[2]};
+    if (lbm) return sweep_lbm_tb2(g, box, lbm_stores_macroscopic(params, true), (cudaStream_t)stream);
     return sweep_jacobi_tb(g, kernel == B200GEO_KERNEL_JACOBI6 ? 6 : kernel == B200GEO_KERNEL_JACOBI7 ? 7 : 27, n, box,
                            (cudaStream_t)stream);
 }

@@ -82,6 +82,10 @@ struct Tuning {
     int nbody_threads;    // threads per CTA of the fused n-body kernel (0 = automatic: 16 per container of a run)
     int jacobi_resident;  // SM-resident multi-sweep kernel for small grids: 1 = whenever the grid qualifies, 0 = never (default: not faster, profiles/r3i_r3j_r3k)
     int jacobi_tb_raster; // CTA order of the temporal-blocked kernel: 0 = x fastest (default), n > 0 = y-panels of n tile rows, y fastest
+    int lbm_tb;           // sweeps per launch of the LBM kernels: 2 = two fused sweeps wherever the ghost zones allow (default), 1 = one
+    int lbm_tb_rows;      // rows of the intermediate level per CTA of the fused LBM kernel: 14 (default), 16 or 8
+    int lbm_tb_zchunk;    // planes per CTA along z of the fused LBM kernel (0 = automatic)
+    int lbm_tb_promo;     // L2 promotion of the fused LBM kernel's TMA loads: 0 none, 1 64 B, 2 128 B, 3 256 B
 };
 extern Tuning g_tuning;
 
@@ -98,6 +102,7 @@ int sweep_gol(b200geo_grid *g, const Box& box, cudaStream_t s);
 bool gol_bits_applicable(const b200geo_grid *g);
 int sweep_gol_bits(b200geo_grid *g, uint32_t sweeps, cudaStream_t s);
 int sweep_lbm(b200geo_grid *g, const Box& box, bool store_macroscopic, cudaStream_t s);
+int sweep_lbm_tb2(b200geo_grid *g, const Box& box, bool store_macroscopic, cudaStream_t s);
 
 // ghost maintenance and (de)serialisation kernels (region.cu)
 int fill_edge(b200geo_grid *g, int which, cudaStream_t s);

@@ -84,6 +84,24 @@ jacobi_resident_kernel(double *buf_a, double *buf_b, int64_t pitch, int64_t plan
 #pragma unroll
         for (int r = 0; r < 2; ++r) c[k][r] = live ? lds2(s + sidx<BZ>(x, y0 + r, k)) : make_double2(0.0, 0.0);
 
+    // the shell pairs: (offset in the grid buffer relative to the brick, offset in shared memory)
+    int2 *shell = reinterpret_cast<int2 *>(s + (BZ + 2) * (BY + 2) * SP);
+    const int shell_pairs = (2 * (BZ + 2) + 2 * BY) * (nx / 2);
+    for (int i = threadIdx.x; i < shell_pairs; i += NT) {
+        const int pairs = nx / 2, row = i / pairs, px = 2 * (i % pairs);
+        int y, z;
+        if (row < 2 * (BZ + 2)) {
+            z = row / 2 - 1;
+            y = (row & 1) ? BY : -1;
+        } else {
+            const int q = row - 2 * (BZ + 2);
+            z = (q & 1) ? BZ : -1;
+            y = q / 2;
+        }
+        shell[i] = make_int2((int)(z * plane + y * pitch + px), sidx<BZ>(px, y, z));
+    }
+    __syncthreads();
+
     for (int t = 0; t < sweeps; ++t) {
         // ---- one sweep over the brick, in place: z neighbours are the thread's own registers
         if (live) {
@@ -143,24 +161,11 @@ jacobi_resident_kernel(double *buf_a, double *buf_b, int64_t pitch, int64_t plan
         }
         __syncthreads();
         // ---- the shell: rows y = -1 and y = BY of every plane, planes z = -1 and z = BZ (L2, not L1: the same
-        // addresses held another time step two sweeps ago)
-        {
-            const int pairs = nx / 2;
-            const int rows = 2 * (BZ + 2) + 2 * BY;
-            for (int i = threadIdx.x; i < rows * pairs; i += NT) {
-                const int row = i / pairs, px = 2 * (i % pairs);
-                int y, z;
-                if (row < 2 * (BZ + 2)) {
-                    z = row / 2 - 1;
-                    y = (row & 1) ? BY : -1;
-                } else {
-                    const int q = row - 2 * (BZ + 2);
-                    z = (q & 1) ? BZ : -1;
-                    y = q / 2;
-                }
-                const double2 v = __ldcg(reinterpret_cast<const double2 *>(buf_b + base + (int64_t)z * plane + (int64_t)y * pitch + px));
-                *reinterpret_cast<double2 *>(s + sidx<BZ>(px, y, z)) = v;
-            }
+        // addresses held another time step two sweeps ago); where each pair lies was worked out once, before the sweeps
+        for (int i = threadIdx.x; i < shell_pairs; i += NT) {
+            const int2 at = shell[i];
+            const double2 v = __ldcg(reinterpret_cast<const double2 *>(buf_b + base + at.x));
+            *reinterpret_cast<double2 *>(s + at.y) = v;
         }
         __syncthreads();
         double *tmp = buf_a;
@@ -188,7 +193,7 @@ int launch_resident(b200geo_grid *g, int sweeps, cudaStream_t s)
     }
     int *flags = (int *)g->scratch;
     B200GEO_CUDA(cudaMemsetAsync(flags, 0, (size_t)bricks * sizeof(int), s));
-    size_t smem = (size_t)(BZ + 2) * (BY + 2) * SP * sizeof(double);
+    size_t smem = (size_t)(BZ + 2) * (BY + 2) * SP * sizeof(double) + (size_t)(2 * (BZ + 2) + 2 * BY) * RX * sizeof(int2);
     auto kernel = jacobi_resident_kernel<KIND, BZ>;
     static bool attr_set[64] = {false};
     if (g->device < 0 || g->device >= 64 || !attr_set[g->device]) {

@@ -446,6 +446,11 @@ int launch_tb_depth(b200geo_grid *g, int depth, int rows, const Box& box, const 
 
 }
 
+void *tensor_map_encoder()
+{
+    return (void *)encode_tiled();
+}
+
 // TMA descriptor of member 0 of buffer `which` (absolute index): the whole padded array as a
 // rank-3 tensor of f64, box = one TX x TY x 1 tile.
 int tensor_map(b200geo_grid *g, int which, int tile_cols, int tile_rows, CUtensorMap *out)
