@@ -52,7 +52,7 @@ DESCRIPTION = {
 
 # temporal blocking depth per workload (b200geo_set_tuning "jacobi.tb"): sweeps fused into one launch of
 # the TMA-staged Jacobi kernel; with N > 1 the ghost zone must be that wide (one exchange per launch)
-TB_DEPTH = {"jacobi27": 2, "jacobi7": 4, "jacobi7_128": 1}
+TB_DEPTH = {"jacobi27": 2, "jacobi7": 4, "jacobi7_128": 1, "lbm": 2}
 
 
 def ncu_traffic(workload):
@@ -69,12 +69,13 @@ def measure_traffic(workload, depth):
     """DRAM bytes one launch of the dominant kernel moves, measured NOW on this box: a child process (tools/few_launches.py:
     the same grid, the same kernel through the same C ABI call) under `ncu --metrics dram__bytes_read.sum,
     dram__bytes_write.sum`, third launch. Only the byte counters are taken from the profiler, never a time."""
-    kernel = {"jacobi27": "jacobi_tb", "jacobi7": "jacobi_tb", "lbm": "lbm_kernel", "jacobi7_128": "jacobi"}.get(workload)
+    kernel = {"jacobi27": "jacobi_tb", "jacobi7": "jacobi_tb", "lbm": "lbm_tb2" if depth > 1 else "lbm_kernel",
+              "jacobi7_128": "jacobi"}.get(workload)
     if kernel is None:
         return None
     cmd = ["ncu", "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum", "--clock-control", "none", "-k", "regex:" + kernel,
            "-s", "2", "-c", "1", "--csv", sys.executable, os.path.join(ROOT, "tools", "few_launches.py"), workload,
-           "jacobi.tb=%d" % depth, "--sweeps", str(4 * max(1, depth))]
+           ("lbm.tb=%d" if workload == "lbm" else "jacobi.tb=%d") % depth, "--sweeps", str(4 * max(1, depth))]
     try:
         res = subprocess.run(cmd, capture_output=True, text=True, timeout=240, cwd=ROOT)
     except (OSError, subprocess.TimeoutExpired):

@@ -136,9 +136,11 @@ int mark_valid(b200geo_group *grp, int width)
     return B200GEO_OK;
 }
 
-bool fuses_sweeps(int kernel)
+// sweeps a kernel family can take per launch (b200geo_update_box_n): jacobi_tb.cu, lbm_tb.cu
+int max_fused_sweeps(int kernel)
 {
-    return kernel == B200GEO_KERNEL_JACOBI6 || kernel == B200GEO_KERNEL_JACOBI7 || kernel == B200GEO_KERNEL_JACOBI27;
+    if (kernel == B200GEO_KERNEL_JACOBI6 || kernel == B200GEO_KERNEL_JACOBI7 || kernel == B200GEO_KERNEL_JACOBI27) return 4;
+    return kernel == B200GEO_KERNEL_LBM_D3Q19 ? 2 : 1;
 }
 
 int ghost_width(const b200geo_group *grp)
@@ -347,7 +349,7 @@ int b200geo_group_step(b200geo_group *grp, int kernel, const void *params, uint3
     // LBM, default parameter block: density / velocity are stored by the last sweep of this call only
     const bool lbm_lazy = kernel == B200GEO_KERNEL_LBM_D3Q19 && (!params || *(const int32_t *)params == 0);
     const int32_t lbm_store = 0, lbm_skip = 2;
-    bool overlap = w == 1 || (fuses_sweeps(kernel) && w <= 4);
+    bool overlap = w == 1 || w <= max_fused_sweeps(kernel);
     for (int i = 0; i < grp->n; ++i)
         if (grp->g[i]->d[a] < 2 * w) overlap = false;
     uint32_t done = 0;

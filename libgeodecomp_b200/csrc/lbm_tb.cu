@@ -127,6 +127,21 @@ __device__ __forceinline__ void tma_load_window(void *dst, const CUtensorMap *ma
         : "memory");
 }
 
+__device__ __forceinline__ void tma_load_window_hint(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2, int c3,
+                                                     uint64_t policy)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5, %6}], [%2], %7;"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "l"(policy)
+        : "memory");
+}
+
+__device__ __forceinline__ void store_out(float *p, float v, bool streaming)
+{
+    if (streaming) __stcs(p, v);
+    else *p = v;
+}
+
 // sweep 1: a cell's neighbourhood as the TMA windows hold it. Window COMP holds, pull_x(COMP) beside the cell's own
 // place, the value the cell pulls for COMP; anything else a wall cell asks for (its own populations, EAST_NOSLIP's (-1, 0, 1) entry)
 // comes from the grid.
@@ -170,7 +185,7 @@ template<bool MACRO, int NR, int NST, int MINB>
 __global__ void __launch_bounds__((NR + 1) * 32, MINB)
 lbm_tb2_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restrict__ src, float *__restrict__ dst, int64_t pitch,
                int64_t plane, int64_t mstride, Box box, int xa, Limits lim, const __grid_constant__ EdgeCell edge, int zchunk, int pad_x,
-               int pad_y, int pad_z)
+               int pad_y, int pad_z, int hints)
 {
     static_assert(NR >= 3 && NR <= 16, "the ring cells of NR rows are one warp's work");
     typedef Shape<NR> SH;
@@ -190,17 +205,31 @@ lbm_tb2_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restrict
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    // hints (tuning, "lbm.tb_hints"): 1 = the results are stored with the streaming hint (first out of L2), 2 = the windows
+    // are loaded with the evict-last policy (the sectors two CTAs share stay until the second one has come by)
+    const bool stream_out = hints & 1;
+    uint64_t keep = 0;
+    if (hints & 2) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(keep));
     // the windows of sweep-1 plane `first + j` go to stage j % NST
     auto issue = [&](int j) {
         float *st = stage + (j % NST) * SH::STAGE;
         uint64_t *bar = &bars[j % NST];
         mbar_expect_tx(bar, SH::STAGE_TX);
         const int cx = X0 - WLEAD + pad_x, cy = Y0 - 1 + pad_y, cz = first + j + pad_z;
+        if (hints & 2) {
 #pragma unroll
-        for (int m = 0; m < 19; ++m) tma_load_window(st + m * WS, &tmap, bar, cx, cy + pull_y(m), cz + pull_z(m), m);
-        tma_load_window(st + 19 * WS, &tmap, bar, cx, cy, cz, STATE);
+            for (int m = 0; m < 19; ++m) tma_load_window_hint(st + m * WS, &tmap, bar, cx, cy + pull_y(m), cz + pull_z(m), m, keep);
+            tma_load_window_hint(st + 19 * WS, &tmap, bar, cx, cy, cz, STATE, keep);
+        } else {
+#pragma unroll
+            for (int m = 0; m < 19; ++m) tma_load_window(st + m * WS, &tmap, bar, cx, cy + pull_y(m), cz + pull_z(m), m);
+            tma_load_window(st + 19 * WS, &tmap, bar, cx, cy, cz, STATE);
+        }
     };
-    if (threadIdx.x == 0)
+    // the producer is the first thread of the ring warp: that warp has nothing to do in sweep 2, so refilling a stage
+    // (20 TMA instructions) is not on the path of a warp the others wait for at the barrier
+    const bool producer = threadIdx.x == NR * 32;
+    if (producer)
         for (int j = 0; j < NST && j < planes; ++j) issue(j);
 
     // this thread's cell of the intermediate level: (row, col) in the tile, (x, y) in the grid
@@ -250,7 +279,7 @@ lbm_tb2_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restrict
         }
         __syncthreads();
         // everybody is done with this stage: refill it with the windows of plane p + NST
-        if (threadIdx.x == 0 && k + NST < planes) issue(k + NST);
+        if (producer && k + NST < planes) issue(k + NST);
         // ---- sweep 2, plane p - 1, out of the tile
         if (act2 && p > zb) {
             TileHood<PS> hood;
@@ -270,14 +299,14 @@ lbm_tb2_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restrict
                 float rho, velX, velY, velZ;
                 liquid(in, out, rho, velX, velY, velZ);
                 if (MACRO) {
-                    dst[(int64_t)DENSITY * mstride + i] = rho;
-                    dst[(int64_t)VELX * mstride + i] = velX;
-                    dst[(int64_t)VELY * mstride + i] = velY;
-                    dst[(int64_t)VELZ * mstride + i] = velZ;
+                    store_out(dst + (int64_t)DENSITY * mstride + i, rho, stream_out);
+                    store_out(dst + (int64_t)VELX * mstride + i, velX, stream_out);
+                    store_out(dst + (int64_t)VELY * mstride + i, velY, stream_out);
+                    store_out(dst + (int64_t)VELZ * mstride + i, velZ, stream_out);
                 }
             }
 #pragma unroll
-            for (int m = 0; m < 19; ++m) dst[(int64_t)m * mstride + i] = out[m];
+            for (int m = 0; m < 19; ++m) store_out(dst + (int64_t)m * mstride + i, out[m], stream_out);
         }
         state_below = state;
         k3 = k3 == 2 ? 0 : k3 + 1;
@@ -345,7 +374,7 @@ int launch_tb2(b200geo_grid *g, const Box& box, const Limits& lim, bool store_ma
     }
     dim3 grid(gx, gy, gz);
     (which ? k1 : k0)<<<grid, (NR + 1) * 32, smem, s>>>(map, src, dst, L.pitch, L.plane, mstride, box, xa, lim, edge, zchunk, L.lead,
-                                                       g->g[1], g->g[2]);
+                                                       g->g[1], g->g[2], g_tuning.lbm_tb_hints);
     count_launch();
     return check_cuda(cudaGetLastError(), "fused lbm sweeps");
 }

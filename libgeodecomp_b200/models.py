@@ -35,9 +35,16 @@ class CellModel:
         return B200Grid
 
     @property
+    def max_fused_sweeps(self):
+        """sweeps the kernel family can take per launch (b200geo_update_box_n): 4 for the Jacobi kernels
+        (csrc/jacobi_tb.cu), 2 for LBM (csrc/lbm_tb.cu), else 1"""
+        if self.kernel in (capi.KERNEL_JACOBI6, capi.KERNEL_JACOBI7, capi.KERNEL_JACOBI27):
+            return 4
+        return 2 if self.kernel == capi.KERNEL_LBM_D3Q19 else 1
+
+    @property
     def fuses_sweeps(self):
-        """the kernel family can take several sweeps per launch (b200geo_update_box_n)"""
-        return self.kernel in (capi.KERNEL_JACOBI6, capi.KERNEL_JACOBI7, capi.KERNEL_JACOBI27)
+        return self.max_fused_sweeps > 1
 
     def halo_members(self, width):
         """(members read from the low-side ghost slices, ... high-side) or None = whole cells.
@@ -103,6 +110,7 @@ class NBodyModel:
         self.ref_model = "nbody"
         self.wraps = False
         self.fuses_sweeps = False
+        self.max_fused_sweeps = 1
 
     def with_params(self, **kw):
         args = dict(real=self.real, capacity=self.capacity, cell_edge=self.cell_edge, cutoff=self.cutoff, dt=self.dt)

@@ -315,7 +315,7 @@ class StripedSimulator:
         w, last = self.ghost_width, self.model.dim - 1
         if self.halo.packed or self._thinnest < 2 * w or not hasattr(self.grid.dev, "update_box"):
             return False
-        return w == 1 or (self.model.fuses_sweeps and w <= 4)
+        return w == 1 or w <= self.model.max_fused_sweeps
 
     def _overlapped_round(self, final, sweeps):
         """`sweeps` <= ghost_width sweeps fused per launch; the ghost zones are ghost_width deep again afterwards"""
@@ -372,10 +372,11 @@ class StripedSimulator:
                 return None
         depth = self.stream_depth
         if depth is None:
-            depth = {capi.KERNEL_JACOBI27: 2, capi.KERNEL_JACOBI6: 4, capi.KERNEL_JACOBI7: 4}.get(self.model.kernel, 1)
+            depth = {capi.KERNEL_JACOBI27: 2, capi.KERNEL_JACOBI6: 4, capi.KERNEL_JACOBI7: 4,
+                     capi.KERNEL_LBM_D3Q19: 2}.get(self.model.kernel, 1)
         if not self.model.fuses_sweeps:
             depth = 1
-        depth = max(1, min(int(depth), 4, sweeps))
+        depth = max(1, min(int(depth), self.model.max_fused_sweeps, sweeps))
         # the shorter remainder level goes FIRST: a level may not be deeper than the one after it (see below)
         levels = ([sweeps % depth] if sweeps % depth else []) + [depth] * (sweeps // depth)
         # every rank must come to the same decision (a rank that falls back to the plain schedule exchanges halos,
