@@ -174,6 +174,14 @@ int b200geo_sync(void *stream);
 /* wait for `stream` of the device this grid lives on (b200geo_sync waits on the calling thread's CURRENT device: a host
  * thread that drives several GPUs — slab groups — uses this one) */
 int b200geo_grid_sync(const b200geo_grid *g, void *stream);
+/* Streams of a device, for callers that overlap host <-> device copies with sweeps (a streamed run: the Initializer
+ * fills planes the sweeps have not reached while finished planes travel to the ParallelWriters — the reference hands
+ * both plugins sub-boxes of the grid, io/initializer.h:38-71, io/parallelwriter.h:92-99). Every entry point that takes
+ * a `stream` accepts these handles (they are cudaStream_t). b200geo_stream_wait: work enqueued on `waiter` from now
+ * on starts after everything enqueued on `signaller` so far; the host does not wait. */
+int b200geo_stream_create(int device, void **stream);
+int b200geo_stream_destroy(int device, void *stream);
+int b200geo_stream_wait(int device, void *waiter, void *signaller);
 /* Plain device memory on `device` for region buffers that stay on the GPU: the device twins of the host-side
  * PatchBufferFixed a Stepper keeps for its rim and its volatile kernel (parallelization/nesting/commonstepper.h:
  * 29-30, 236-283; storage/patchbufferfixed.h) — filled and drained by b200geo_grid_save_region /

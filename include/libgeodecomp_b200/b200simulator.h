@@ -72,6 +72,15 @@ struct B200KernelBinding;      /* specialise with B200GEO_BIND_CELL */
         {                                                                               \
             B200Helpers::check(b200geo_update_box(g, KERNEL_ID, 0, nanoStep, origin, dim, 0)); \
         }                                                                               \
+        /* n fused sweeps over a box on a stream of the caller (b200geo_update_box_n); `final`: the grid is  \
+         * observed afterwards (LBM: density / velocity are stored by the last sweep before an observation) */ \
+        static void updateBoxN(b200geo_grid *g, unsigned nanoStep, const int32_t origin[3], const int32_t dim[3], \
+                               unsigned sweeps, bool final, void *stream)                \
+        {                                                                               \
+            int32_t lbmMode = final ? 0 : 2;                                            \
+            B200Helpers::check(b200geo_update_box_n(g, KERNEL_ID, (KERNEL_ID) == B200GEO_KERNEL_LBM_D3Q19 ? &lbmMode : 0, \
+                                                    nanoStep, origin, dim, sweeps, stream)); \
+        }                                                                               \
         static std::vector<B200Member> members()                                        \
         {                                                                               \
             B200Member tab[] = { __VA_ARGS__ };                                         \
@@ -100,6 +109,29 @@ inline void check(int rc)
     default:
         throw std::runtime_error(msg.find("CUDA error") == 0 ? msg : "CUDA error: " + msg);
     }
+}
+
+/* sweeps a bound kernel family takes per launch (csrc/jacobi_tb.cu, csrc/lbm_tb.cu) and the depth a streamed run
+ * uses per level (what is fastest on the device: two for the 27-point and the LBM kernels, four for 6 / 7 points) */
+inline unsigned fusedSweeps(int kernel)
+{
+    switch (kernel) {
+    case B200GEO_KERNEL_JACOBI6:
+    case B200GEO_KERNEL_JACOBI7:
+        return 4;
+    case B200GEO_KERNEL_JACOBI27:
+    case B200GEO_KERNEL_LBM_D3Q19:
+        return 2;
+    default:
+        return 1;
+    }
+}
+
+/* members a kernel family never rewrites: every sweep reads them from whichever buffer is current, so an upload has
+ * to put them into BOTH buffers (LBM: csrc/lbm.cu leaves `state` and the wall cells' density / velocity alone) */
+inline bool invariantMember(int kernel, int member)
+{
+    return kernel == B200GEO_KERNEL_LBM_D3Q19 && member >= 19;
 }
 
 /* a binding may create the device grid itself (the generic SoA path asks for the uniform element layout,
@@ -609,6 +641,16 @@ public:
         deferSync = defer;
     }
 
+    /* Selector I/O (loadMember / saveMember of plain member selectors) goes through `stream` from now on and is
+     * not waited for; bothBuffers = false: a load writes the current buffer only, except for the members the
+     * kernel family never rewrites. (0, true) restores the default: the null stream, both buffers, synchronous.
+     * What B200GridWindow switches on around a plugin call of a streamed run. */
+    void setMemberIo(void *stream, bool bothBuffers) const
+    {
+        ioStream = stream;
+        ioBoth = bothBuffers;
+    }
+
     /* combined host writes are shipped when this many cells are pending (default: 2 MiB worth, at least 64 Ki cells) */
     void setMaxPendingCells(std::size_t cells)
     {
@@ -671,17 +713,17 @@ protected:
             /* Writers that pull a member ROW BY ROW (the reference's BOVOutput::writeGrid calls saveMemberUnchecked
              * once per streak, io/bovoutput.h:83-95; so do PPM / VisIt writers): rows are served from a read-ahead
              * block of up to 64 MiB of the rows that follow — one transfer per block instead of one per row */
-            if (boxes.size() == 1 && boxes[0].dim[1] == 1 && boxes[0].dim[2] == 1 && loc == B200GEO_HOST &&
+            if (ioStream == 0 && boxes.size() == 1 && boxes[0].dim[1] == 1 && boxes[0].dim[2] == 1 && loc == B200GEO_HOST &&
                 boxes[0].origin[0] >= 0 && boxes[0].origin[0] + boxes[0].dim[0] <= box.dimensions.x() &&
                 boxes[0].origin[1] >= 0 && boxes[0].origin[2] >= 0 && serveRow(m, boxes[0], target)) {
                 return;
             }
             for (std::size_t k = 0; k < boxes.size(); ++k) {
-                B200Helpers::check(b200geo_grid_save_member(handle, m, boxes[k].origin, boxes[k].dim, target, loc, 0));
+                B200Helpers::check(b200geo_grid_save_member(handle, m, boxes[k].origin, boxes[k].dim, target, loc, ioStream));
                 target += selector.sizeOfExternal() * boxes[k].cells();
             }
             memberCalls += boxes.size();
-            if (!deferSync) {
+            if (!deferSync && ioStream == 0) {
                 sync();
             }
             return;
@@ -713,11 +755,12 @@ protected:
             const int loc = sourceLocation == MemoryLocation::HOST ? B200GEO_HOST : B200GEO_CUDA_DEVICE;
             std::vector<B200Helpers::StreakBox> boxes = B200Helpers::mergeStreaks<DIM>(begin, end, box.origin);
             for (std::size_t k = 0; k < boxes.size(); ++k) {
-                B200Helpers::check(b200geo_grid_load_member(handle, m, boxes[k].origin, boxes[k].dim, source, loc, 1, 0));
+                const int both = (ioBoth || B200Helpers::invariantMember(B200KernelBinding<CELL>::kernel(), m)) ? 1 : 0;
+                B200Helpers::check(b200geo_grid_load_member(handle, m, boxes[k].origin, boxes[k].dim, source, loc, both, ioStream));
                 source += selector.sizeOfExternal() * boxes[k].cells();
             }
             memberCalls += boxes.size();
-            if (!deferSync) {
+            if (!deferSync && ioStream == 0) {
                 sync();
             }
             return;
@@ -755,6 +798,8 @@ private:
     mutable bool rowCacheValid = false;
     mutable std::size_t memberCalls = 0;
     mutable bool deferSync = false;
+    mutable void *ioStream = 0;                    /* setMemberIo */
+    mutable bool ioBoth = true;
     mutable std::string lastSelectorName;          /* findMember: the selector asked for last and its member */
     mutable std::size_t lastSelectorBytes = 0;
     mutable int lastSelectorMember = -1;
@@ -975,6 +1020,12 @@ private:
     }
 };
 
+}
+
+#include "b200streamedrun.h"
+
+namespace LibGeoDecomp {
+
 template<typename CELL>
 class B200Simulator : public MonolithicSimulator<CELL>
 {
@@ -1026,6 +1077,20 @@ public:
         initializer->grid(&grid);
     }
 
+    using MonolithicSimulator<CELL>::addWriter;
+
+    /* ParallelWriters (io/parallelwriter.h; what programs written for the reference's StripingSimulator /
+     * HiParSimulator register): called with the whole area, rank 0 and lastCall = true by a plain run — and chunk by
+     * chunk, while the sweeps go on, by a streamed one (b200streamedrun.h). The simulator takes ownership, like the
+     * reference. Writers that are BOTH a Writer and a ParallelWriter keep going through addWriter(Writer *). */
+    template<typename WRITER>
+    typename std::enable_if<std::is_base_of<ParallelWriter<CELL>, WRITER>::value &&
+                            !std::is_base_of<Writer<CELL>, WRITER>::value>::type
+    addWriter(WRITER *writer)
+    {
+        parallelWriters.push_back(typename SharedPtr<ParallelWriter<CELL> >::Type(writer));
+    }
+
     /* one step, exactly like the reference (serialsimulator.h:70-93) */
     virtual void step()
     {
@@ -1035,6 +1100,12 @@ public:
 
     virtual void run()
     {
+        for (std::size_t i = 0; i < parallelWriters.size(); ++i) {
+            parallelWriters[i]->setRegion(simArea);
+        }
+        if (streamIO && steerers.empty() && writers.empty() && runStreamed(&grid)) {
+            return;
+        }
         initializer->grid(&grid);
         stepNum = initializer->startStep();
         for (unsigned i = 0; i < steerers.size(); i++) {
@@ -1062,9 +1133,44 @@ public:
         return &grid;
     }
 
+    /* run() pipelines Initializer, sweeps and ParallelWriters chunk by chunk (b200streamedrun.h) when nothing but
+     * ParallelWriters with no call due inside the run is registered, the cell is bound to a kernel family that updates
+     * boxes, and the last axis does not wrap; false: always upload, sweep, download one after the other */
+    bool streamIO = true;
+    int streamChunks = 16;
+
+    /* how many run() calls took the streamed schedule */
+    std::size_t streamedRuns() const
+    {
+        return streamed;
+    }
+
 protected:
     GridType grid;
     Region<DIM> simArea;
+    std::vector<typename SharedPtr<ParallelWriter<CELL> >::Type> parallelWriters;
+    std::size_t streamed = 0;
+
+    bool runStreamed(B200Grid<CELL> *target)
+    {
+        B200StreamedRun<CELL> schedule;
+        if (!schedule.plan(target->boundingBox(), initializer->startStep(), initializer->maxSteps(), parallelWriters, streamChunks)) {
+            return false;
+        }
+        TimeTotal t(&chronometer);
+        stepNum = initializer->startStep();
+        schedule.run(target, &*initializer, parallelWriters, gridDim);
+        stepNum = initializer->maxSteps();
+        ++streamed;
+        return true;
+    }
+
+    /* container grids (n-body) have no streamed schedule */
+    template<typename OTHER_GRID>
+    bool runStreamed(OTHER_GRID *)
+    {
+        return false;
+    }
 
     void step(SteererFeedback *feedback, bool fuse)
     {
@@ -1077,7 +1183,7 @@ protected:
         {
             TimeCompute t(&chronometer);
             grid.update(0, steps * NANO_STEPS);
-            if (steps > 1 || !writers.empty()) {
+            if (steps > 1 || !writers.empty() || !parallelWriters.empty()) {
                 grid.sync();
             }
         }
@@ -1102,6 +1208,10 @@ protected:
             unsigned p = steerers[i]->getPeriod();
             n = (std::min)(n, p - stepNum % p);
         }
+        for (std::size_t i = 0; i < parallelWriters.size(); ++i) {
+            unsigned p = parallelWriters[i]->getPeriod();
+            n = (std::min)(n, p - stepNum % p);
+        }
         return n > 0 ? n : 1;
     }
 
@@ -1111,6 +1221,12 @@ protected:
         for (unsigned i = 0; i < writers.size(); i++) {
             if ((event != WRITER_STEP_FINISHED) || ((getStep() % writers[i]->getPeriod()) == 0)) {
                 writers[i]->stepFinished(grid, getStep(), event);
+            }
+        }
+        for (std::size_t i = 0; i < parallelWriters.size(); ++i) {
+            if ((event != WRITER_STEP_FINISHED) || ((getStep() % parallelWriters[i]->getPeriod()) == 0)) {
+                grid.sync();
+                parallelWriters[i]->stepFinished(grid, simArea, gridDim, getStep(), event, 0, true);
             }
         }
     }

@@ -81,6 +81,9 @@ SYMBOLS = [
     ("b200geo_refresh_ghosts", ctypes.c_int, [_vp, _vp]),
     ("b200geo_sync", ctypes.c_int, [_vp]),
     ("b200geo_grid_sync", ctypes.c_int, [_vp, _vp]),
+    ("b200geo_stream_create", ctypes.c_int, [ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]),
+    ("b200geo_stream_destroy", ctypes.c_int, [ctypes.c_int, _vp]),
+    ("b200geo_stream_wait", ctypes.c_int, [ctypes.c_int, _vp, _vp]),
     ("b200geo_device_alloc", ctypes.c_int, [ctypes.c_int, ctypes.c_uint64, ctypes.POINTER(ctypes.c_void_p)]),
     ("b200geo_device_free", ctypes.c_int, [ctypes.c_int, _vp]),
     ("b200geo_host_alloc", ctypes.c_int, [ctypes.c_uint64, ctypes.POINTER(ctypes.c_void_p)]),

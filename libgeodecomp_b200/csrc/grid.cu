@@ -681,6 +681,34 @@ int b200geo_sync(void *stream)
     return B200GEO_OK;
 }
 
+int b200geo_stream_create(int device, void **stream)
+{
+    if (!stream) return fail(B200GEO_ERR_INVALID, "null argument");
+    B200GEO_CUDA(cudaSetDevice(device));
+    cudaStream_t s;
+    B200GEO_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    *stream = (void *)s;
+    return B200GEO_OK;
+}
+
+int b200geo_stream_destroy(int device, void *stream)
+{
+    B200GEO_CUDA(cudaSetDevice(device));
+    B200GEO_CUDA(cudaStreamDestroy((cudaStream_t)stream));
+    return B200GEO_OK;
+}
+
+int b200geo_stream_wait(int device, void *waiter, void *signaller)
+{
+    B200GEO_CUDA(cudaSetDevice(device));
+    cudaEvent_t ev;
+    B200GEO_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    int rc = check_cuda(cudaEventRecord(ev, (cudaStream_t)signaller), "cudaEventRecord");
+    if (rc == 0) rc = check_cuda(cudaStreamWaitEvent((cudaStream_t)waiter, ev, 0), "cudaStreamWaitEvent");
+    cudaEventDestroy(ev);  // released by the runtime once the recorded work has completed
+    return rc;
+}
+
 int b200geo_grid_sync(const b200geo_grid *g, void *stream)
 {
     if (!g) return fail(B200GEO_ERR_INVALID, "null grid");

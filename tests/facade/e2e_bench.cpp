@@ -3,8 +3,11 @@
  * memory -> device -> host memory inside the timed region. What bench.py's e2e number is for the Python mirror, this is
  * for the C++ side (bench.py runs it and puts the line into "e2e_cpp").
  *
- *   e2e_bench [n = 1024] [steps = 20] [slabs = 1] [mode = box | rows] [--bov prefix]
+ *   e2e_bench [n = 1024] [steps = 20] [slabs = 1] [mode = box | rows | stream] [--bov prefix]
  *
+ * mode stream: as box, but the result goes to a ParallelWriter (io/parallelwriter.h) instead of a serial Writer: with
+ *            nothing but ParallelWriters registered B200Simulator::run() takes the streamed schedule
+ *            (b200streamedrun.h): Initializer, sweeps and writer work on different chunks of the grid at the same time;
  * mode box : the Initializer hands the engine its whole box with GridBase::loadMember, the Writer pulls the final grid
  *            with GridBase::saveMember (storage/gridbase.h:217-261) — one strided copy per box, page-locked host memory
  *            (b200geo_host_alloc);
@@ -15,6 +18,7 @@
  *
  * The grid is checked after the run: a position-weighted checksum of the pulled result against the same run through
  * bench's other modes is printed; parity itself is the business of the test binaries beside this one. */
+#include <libgeodecomp/io/parallelwriter.h>
 #include <libgeodecomp/io/serialbovwriter.h>
 #include <libgeodecomp/io/simpleinitializer.h>
 #include <libgeodecomp/misc/clonable.h>
@@ -126,6 +130,33 @@ private:
     Region<3> cachedRegion;
 };
 
+/* the same writer under the reference's ParallelWriter interface: pulls whatever validRegion it is handed */
+class ParallelPullWriter : public ParallelWriter<Cell>
+{
+public:
+    explicit ParallelPullWriter(const HostField& field) : ParallelWriter<Cell>("", 1u << 30), field(field) {}
+
+    virtual ParallelWriter<Cell> *clone() const
+    {
+        return new ParallelPullWriter(*this);
+    }
+
+    virtual void stepFinished(const GridType& grid, const RegionType& validRegion, const CoordType&, unsigned, WriterEvent event,
+                              std::size_t, bool)
+    {
+        if (event != WRITER_ALL_DONE) {
+            return;
+        }
+        /* whole planes (the simulator cuts along z): contiguous in the host array */
+        CoordBox<3> box = validRegion.boundingBox();
+        double *first = field.data + (std::size_t)box.origin.z() * field.dim.y() * field.dim.x();
+        grid.saveMember(first, MemoryLocation::HOST, Selector<Cell>(&Cell::temp, "temp"), validRegion);
+    }
+
+private:
+    HostField field;
+};
+
 static void fill(const HostField& f)
 {
     /* a 32-plane block of noise repeated along z (generation speed), as bench.py does */
@@ -159,9 +190,13 @@ static unsigned long long checksum(const HostField& f)
 template<typename SIM>
 static void timeRun(SIM& sim, const HostField& field, const char *what, int n, unsigned steps, int slabs, const char *mode)
 {
-    PullWriter *writer = new PullWriter(field, std::string(mode) == "rows");
-    writer->prepare(CoordBox<3>(Coord<3>(), field.dim));
-    sim.addWriter(writer);
+    if (std::string(mode) == "stream") {
+        sim.addWriter(new ParallelPullWriter(field));
+    } else {
+        PullWriter *writer = new PullWriter(field, std::string(mode) == "rows");
+        writer->prepare(CoordBox<3>(Coord<3>(), field.dim));
+        sim.addWriter(writer);
+    }
     auto t0 = std::chrono::steady_clock::now();
     sim.run();
     double s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();

@@ -361,6 +361,9 @@ int b200geo_update_box_n(b200geo_grid *g, int kernel, const void *, uint32_t, co
         const bool used = g->d[i] > 1 || g->g[i] > 0;
         lo[i] = o[i] - (used ? n : 0);
         hi[i] = o[i] + d[i] + (used ? n : 0);
+        // beyond a Cube boundary there is nothing but the constant edge cell: one ring of it is all a sweep reads
+        if (lo[i] < -g->g[i] && g->desc.ghost_mode[i][0] == B200GEO_GHOST_EDGE) lo[i] = -g->g[i];
+        if (hi[i] > g->d[i] + g->g[i] && g->desc.ghost_mode[i][1] == B200GEO_GHOST_EDGE) hi[i] = g->d[i] + g->g[i];
         if (lo[i] < -g->g[i] || hi[i] > g->d[i] + g->g[i]) return fail(B200GEO_ERR_INVALID, "box outside the updatable area");
     }
     const int ex = hi[0] - lo[0], ey = hi[1] - lo[1], ez = hi[2] - lo[2];
@@ -442,6 +445,11 @@ int b200geo_refresh_ghosts(b200geo_grid *g, void *)
 }
 int b200geo_sync(void *) { return B200GEO_OK; }
 int b200geo_grid_sync(const b200geo_grid *, void *) { return B200GEO_OK; }
+/* the mock engine executes every call synchronously: streams are tokens, waiting is a no-op */
+static int g_mock_streams = 0;
+int b200geo_stream_create(int, void **stream) { *stream = (void *)(intptr_t)(0x1000 + ++g_mock_streams); return B200GEO_OK; }
+int b200geo_stream_destroy(int, void *) { return B200GEO_OK; }
+int b200geo_stream_wait(int, void *, void *) { return B200GEO_OK; }
 int b200geo_device_alloc(int, uint64_t bytes, void **ptr) { *ptr = malloc(bytes ? (size_t)bytes : 1); return *ptr ? B200GEO_OK : fail(B200GEO_ERR_NOMEM, "out of memory"); }
 int b200geo_device_free(int, void *ptr) { free(ptr); return B200GEO_OK; }
 int b200geo_host_alloc(uint64_t bytes, void **ptr) { *ptr = malloc(bytes ? (size_t)bytes : 1); return *ptr ? B200GEO_OK : fail(B200GEO_ERR_NOMEM, "out of memory"); }

@@ -53,6 +53,23 @@ def test_cpp_striping_simulator_drop_in():
     assert "all checks passed" in res.stdout
 
 
+STREAMED_BIN = os.path.join(HERE, "facade", "_bin", "streamed_test")
+
+
+@pytest.mark.gpu
+def test_cpp_streamed_run():
+    """tests/facade/streamed_test.cpp: B200Simulator::run() with ParallelWriters only pipelines Initializer, sweeps and
+    writers chunk by chunk on three streams (b200streamedrun.h): bit-identical to SerialSimulator for Jacobi 6 / 7 / 27,
+    LBM and Game of Life, every cell handed to the writers exactly once; plain schedule where a plugin needs the whole
+    grid."""
+    if not os.access(STREAMED_BIN, os.X_OK):
+        pytest.skip("tests/facade/_bin/streamed_test not built (needs /root/reference at build time)")
+    res = subprocess.run([STREAMED_BIN], capture_output=True, text=True, timeout=600)
+    print(res.stdout[-4000:], res.stderr[-2000:])
+    assert res.returncode == 0, res.stdout[-4000:] + res.stderr[-2000:]
+    assert "all checks passed" in res.stdout
+
+
 GENERIC_SOA_BIN = os.path.join(HERE, "facade", "_bin", "generic_soa_test")
 
 
