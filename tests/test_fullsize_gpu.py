@@ -8,7 +8,7 @@ interior, across tile / z-chunk seams of the kernels. Game of Life is compared o
 
   configs[2]  Jacobi 27-point 1024^3 f64     4 and 5 sweeps (two fused launches; plus a one-sweep remainder)
   (and the 7-point kernel at 1024^3, 4 sweeps in one launch)
-  configs[3]  LBM D3Q19 512^3 f32, cavity     3 sweeps, whole x-y planes at the bottom, in the middle, at the top
+  configs[3]  LBM D3Q19 512^3 f32, cavity     3 and 6 sweeps (fused pairs + a one-sweep remainder), whole x-y planes at the bottom, in the middle, at the top
   configs[1]  Game of Life 16384^2 u8         8 sweeps, byte kernel and bit-packed path, whole grid
   configs[4]  n-body, 108^3 containers        2 sweeps, the corner window of 8^3 containers (16.6 M particles)
 """
@@ -65,8 +65,11 @@ def test_jacobi_1024_cubed_windows(oracle, kind, steps):
     gc.collect()
 
 
-def test_lbm_512_cubed_planes(oracle):
-    n, steps = 512, 3
+@pytest.mark.parametrize("steps", [3, 6])
+def test_lbm_512_cubed_planes(oracle, steps):
+    """3 sweeps = one launch of two fused sweeps + one single sweep; 6 = three fused launches. Whole x-y planes: every
+    tile seam of the fused kernel in x and y; planes 254..257 straddle a z-chunk seam (multiples of 64)"""
+    n = 512
     if not free_enough(32):
         pytest.skip("needs 32 GB of device memory")
     model = models.LBMCellF
