@@ -86,6 +86,7 @@ struct Tuning {
     int lbm_tb_rows;      // rows of the intermediate level per CTA of the fused LBM kernel: 14 (default), 16 or 8
     int lbm_tb_zchunk;    // planes per CTA along z of the fused LBM kernel (0 = automatic)
     int lbm_tb_promo;     // L2 promotion of the fused LBM kernel's TMA loads: 0 none, 1 64 B, 2 128 B, 3 256 B
+    int lbm_tb_warps;     // fused LBM kernel: 1 = sweep 1 and sweep 2 on different warps linked by mbarriers, 0 = all warps do both, two CTA-wide barriers per plane
     int lbm_tb_hints;     // L2 hints of the fused LBM kernel: bit 0 = streaming stores, bit 1 = evict-last window loads
 };
 extern Tuning g_tuning;

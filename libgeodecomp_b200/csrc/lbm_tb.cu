@@ -314,6 +314,224 @@ lbm_tb2_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restrict
     }
 }
 
+// ---- the same two sweeps with the two levels on DIFFERENT WARPS (the default): no CTA-wide barrier per plane.
+//
+// In lbm_tb2_kernel all warps compute sweep 1 of a plane, meet at a barrier, compute sweep 2, meet again: the issue
+// slots are 45 % busy, 28 % of the warp time is spent at the barriers (profiles/r4a_r4h). Here NR + 1 warps do
+// nothing but sweep 1 (plane after plane, out of the TMA windows into the rings), NR - 2 warps nothing but sweep 2
+// (out of the rings into the grid), one warp refills the TMA stages; they meet only through mbarriers:
+//   tma_full[s]  : the windows of a plane have landed                 (TMA unit -> sweep-1 warps)
+//   tma_empty[s] : every sweep-1 warp has read its row of the windows  (sweep-1 warps -> producer)
+//   l1_full[k%4] : sweep-1 plane k is in the rings                     (sweep-1 warps -> sweep-2 warps)
+//   l2_done[j%4] : sweep-2 plane j has been read out of the rings      (sweep-2 warps -> sweep-1 warps)
+// The rings are one plane deeper than in the kernel above (4 for the populations that travel up, 3 for the others, 3 for
+// the state), so sweep 1 may run two to three planes ahead of sweep 2 and neither waits for the other's slowest warp.
+constexpr int WSLOTS = 5 * 4 + 14 * 3 + 3;
+
+__host__ __device__ constexpr int wring_base(int comp)
+{
+    return comp == T ? 0 : comp == TW ? 4 : comp == TE ? 8 : comp == TN ? 12 : comp == TS ? 16 :
+           20 + 3 * (comp == C ? 0 : comp == N ? 1 : comp == E ? 2 : comp == W ? 3 : comp == S ? 4 : comp == B ? 5 :
+                     comp == NW ? 6 : comp == SW ? 7 : comp == NE ? 8 : comp == SE ? 9 : comp == BW ? 10 : comp == BE ? 11 :
+                     comp == BN ? 12 : comp == BS ? 13 : 14);   // 14: the state
+}
+
+template<int PS>
+struct WideTileHood {
+    const float *cell;  // the cell's place in plane slot 0
+    int up[3];          // element offsets of planes q - 1, q, q + 1 inside a ring of four
+    int flat[2];        // element offsets of planes q, q + 1 inside a ring of three
+    template<int X, int Y, int Z, int COMP>
+    __device__ __forceinline__ float get() const
+    {
+        static_assert(Z >= 0 || travels_up(COMP), "plane q - 1 only keeps the populations that travel up");
+        return cell[wring_base(COMP) * PS + (travels_up(COMP) ? up[Z + 1] : flat[Z]) + X + Y * ROW];
+    }
+};
+
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    while (!mbar_try_wait(bar, parity)) {}
+}
+
+template<int NR>
+struct WideShape {
+    static constexpr int PS = NR * ROW;
+    static constexpr int WS = Shape<NR>::WS;
+    static constexpr int STAGE = Shape<NR>::STAGE;
+    static constexpr int WARPS = 2 * NR;   // NR + 1 for sweep 1, NR - 2 for sweep 2, one producer
+    static constexpr size_t smem(int nst) { return (size_t)nst * STAGE * 4 + (size_t)WSLOTS * PS * 4 + (2 * nst + 8) * 8; }
+};
+
+template<bool MACRO, int NR, int NST>
+__global__ void __launch_bounds__(2 * NR * 32, 1)
+lbm_tb2w_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restrict__ src, float *__restrict__ dst, int64_t pitch,
+                int64_t plane, int64_t mstride, Box box, int xa, Limits lim, const __grid_constant__ EdgeCell edge, int zchunk, int pad_x,
+                int pad_y, int pad_z)
+{
+    static_assert(NR >= 3 && NR <= 16, "the ring cells of NR rows are one warp's work");
+    typedef WideShape<NR> SH;
+    constexpr int PS = SH::PS, WS = SH::WS;
+    extern __shared__ __align__(128) float smem[];
+    float *stage = smem;                         // [NST][WINDOWS][WS]
+    float *tile = smem + NST * SH::STAGE;        // [WSLOTS][NR][ROW]
+    uint64_t *tma_full = reinterpret_cast<uint64_t *>(tile + WSLOTS * PS);
+    uint64_t *tma_empty = tma_full + NST;
+    uint64_t *l1_full = tma_empty + NST;         // [4]
+    uint64_t *l2_done = l1_full + 4;             // [4]
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int X0 = xa + blockIdx.x * 32, Y0 = box.y0 + blockIdx.y * (NR - 2);
+    const int zb = box.z0 + blockIdx.z * zchunk, ze = min(zb + zchunk, box.z1);
+    const int first = zb - 1, planes = ze - zb + 2;  // sweep 1 covers planes first + k, k = 0 .. planes - 1
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NST; ++s) {
+            mbar_init(&tma_full[s], 1);
+            mbar_init(&tma_empty[s], NR + 1);
+        }
+        for (int i = 0; i < 4; ++i) {
+            mbar_init(&l1_full[i], NR + 1);
+            mbar_init(&l2_done[i], NR - 2);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp == 2 * NR - 1) {
+        // ---- the producer: refills stage k % NST with the windows of plane k as soon as the sweep-1 warps have read it
+        if (lane == 0) {
+            for (int k = 0; k < planes; ++k) {
+                const int s = k % NST;
+                if (k >= NST) mbar_wait(&tma_empty[s], ((k / NST) - 1) & 1);
+                float *st = stage + s * SH::STAGE;
+                mbar_expect_tx(&tma_full[s], Shape<NR>::STAGE_TX);
+                const int cx = X0 - WLEAD + pad_x, cy = Y0 - 1 + pad_y, cz = first + k + pad_z;
+#pragma unroll
+                for (int m = 0; m < 19; ++m) tma_load_window(st + m * WS, &tmap, &tma_full[s], cx, cy + pull_y(m), cz + pull_z(m), m);
+                tma_load_window(st + 19 * WS, &tmap, &tma_full[s], cx, cy, cz, STATE);
+            }
+        }
+        return;
+    }
+
+    if (warp <= NR) {
+        // ---- sweep 1: plane after plane out of the TMA windows into the rings
+        const bool ring = warp == NR;
+        const int row = ring ? lane >> 1 : warp;
+        const int col = ring ? ((lane & 1) ? ROW - 1 : 0) : lane + 1;
+        const int x = X0 - 1 + col, y = Y0 - 1 + row;
+        const bool act1 = row < NR && x >= box.x0 - 1 && x <= box.x1 && y >= box.y0 - 1 && y <= box.y1;
+        const bool outside_xy = x < lim.lo[0] || x >= lim.hi[0] || y < lim.lo[1] || y >= lim.hi[1];
+        float *const mine = tile + row * ROW + col;
+        const float *const window = stage + (row < NR ? row : 0) * WROW + (WLEAD - 1) + col;
+        int k3 = 0, k4 = 0, ks = 0;   // k % 3, k % 4, k % NST
+        for (int k = 0; k < planes; ++k) {
+            const int p = first + k;
+            // the ring slots of plane k held plane k - 4 / k - 3: sweep 2 must be through with plane k - 3
+            if (k >= 3) mbar_wait(&l2_done[(k4 + 1) & 3], ((k - 3) >> 2) & 1);
+            mbar_wait(&tma_full[ks], (k / NST) & 1);
+            float out[19];
+            int state = LIQUID;
+            if (act1) {
+                if (outside_xy || p < lim.lo[2] || p >= lim.hi[2]) {
+#pragma unroll
+                    for (int m = 0; m < 19; ++m) out[m] = edge.f[m];
+                } else {
+                    const float *cell = window + ks * SH::STAGE;
+                    state = __float_as_int(cell[19 * WS]);
+                    if (state != LIQUID) {
+                        // a wall cell reads its own populations from the grid (faces only). The strides go through an
+                        // empty asm so that the 19 member addresses are worked out HERE, not hoisted out of the plane loop
+                        // into registers every liquid cell would pay for
+                        int64_t ms = mstride, pl = plane, pi = pitch;
+                        asm volatile("" : "+l"(ms), "+l"(pl), "+l"(pi));
+                        const WindowHood<WS> hood = {cell, {src, (int64_t)p * pl + (int64_t)y * pi + x, pi, pl, ms}};
+                        wall(state, hood, out);
+                    } else {
+                        const WindowHood<WS> hood = {cell, {src, 0, 0, 0, 0}};
+                        Pulled in;
+                        pull(in, hood);
+                        float rho, velX, velY, velZ;
+                        liquid(in, out, rho, velX, velY, velZ);
+                    }
+                }
+            }
+            // this warp is done with its row of the windows
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tma_empty[ks]);
+            if (act1) {
+                const int r4 = k4 * PS, r3 = k3 * PS;
+#pragma unroll
+                for (int m = 0; m < 19; ++m) mine[wring_base(m) * PS + (travels_up(m) ? r4 : r3)] = out[m];
+                mine[wring_base(19) * PS + r3] = __int_as_float(state);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&l1_full[k4]);
+            k3 = k3 == 2 ? 0 : k3 + 1;
+            k4 = (k4 + 1) & 3;
+            ks = ks == NST - 1 ? 0 : ks + 1;
+        }
+        return;
+    }
+
+    // ---- sweep 2: plane j = k (ring index) out of the rings into the grid, for k = 1 .. planes - 2
+    {
+        const int row = warp - NR;   // 1 .. NR - 2
+        const int col = lane + 1;
+        const int x = X0 - 1 + col, y = Y0 - 1 + row;
+        const bool act2 = x >= box.x0 && x < box.x1 && y < box.y1;
+        const float *const mine = tile + row * ROW + col;
+        const int64_t ixy = (int64_t)y * pitch + x;
+        // plane 0 is nobody's second sweep: its slot of l2_done is completed right away so that parities stay uniform
+        if (lane == 0) mbar_arrive(&l2_done[0]);
+        int j3 = 1, j4 = 1;
+        for (int j = 1; j <= planes - 2; ++j) {
+            mbar_wait(&l1_full[(j4 + 1) & 3], ((j + 1) >> 2) & 1);   // planes j - 1, j, j + 1 of sweep 1 are there
+            float out[19];
+            const int64_t i = (int64_t)(first + j) * plane + ixy;
+            if (act2) {
+                WideTileHood<PS> hood;
+                hood.cell = mine;
+                hood.up[0] = ((j4 + 3) & 3) * PS;
+                hood.up[1] = j4 * PS;
+                hood.up[2] = ((j4 + 1) & 3) * PS;
+                hood.flat[0] = j3 * PS;
+                hood.flat[1] = (j3 == 2 ? 0 : j3 + 1) * PS;
+                const int state = __float_as_int(mine[wring_base(19) * PS + j3 * PS]);
+                if (state != LIQUID) {
+                    wall(state, hood, out);
+                } else {
+                    Pulled in;
+                    pull(in, hood);
+                    float rho, velX, velY, velZ;
+                    liquid(in, out, rho, velX, velY, velZ);
+                    if (MACRO) {
+                        dst[(int64_t)DENSITY * mstride + i] = rho;
+                        dst[(int64_t)VELX * mstride + i] = velX;
+                        dst[(int64_t)VELY * mstride + i] = velY;
+                        dst[(int64_t)VELZ * mstride + i] = velZ;
+                    }
+                }
+            }
+            // everything this plane needed from the rings is in registers now
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&l2_done[j4]);
+            if (act2) {
+#pragma unroll
+                for (int m = 0; m < 19; ++m) dst[(int64_t)m * mstride + i] = out[m];
+            }
+            j3 = j3 == 2 ? 0 : j3 + 1;
+            j4 = (j4 + 1) & 3;
+        }
+    }
+}
+
 typedef CUresult (*EncodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                 const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                 CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -379,6 +597,45 @@ int launch_tb2(b200geo_grid *g, const Box& box, const Limits& lim, bool store_ma
     return check_cuda(cudaGetLastError(), "fused lbm sweeps");
 }
 
+template<int NR, int NST>
+int launch_tb2w(b200geo_grid *g, const Box& box, const Limits& lim, bool store_macroscopic, cudaStream_t s)
+{
+    const MemberLayout& L = g->m[0];
+    for (int m = 1; m < 24; ++m)
+        if (g->m[m].offset != (int64_t)m * g->m[1].offset) return fail(B200GEO_ERR_LOGIC, "LBM member arrays are not equally spaced");
+    const int64_t mstride = g->m[1].offset / 4;
+    const float *src = (const float *)g->member_ptr(0, 0) + L.origin;
+    float *dst = (float *)g->member_ptr(0, 1) + L.origin;
+    const int ny = box.y1 - box.y0, nz = box.z1 - box.z0;
+    const int xa = box.x0 & ~3;
+    const int gx = (box.x1 - xa + 31) / 32, gy = (ny + NR - 3) / (NR - 2);
+    // short z chunks: neighbouring columns start together more often, so more of the rim rows they share are still in L2
+    // (13.7 GB read per launch at 512^3 with 32 planes, 15.2 GB with 64; profiles/r4f) — worth the two extra sweep-1 planes
+    int zchunk = g_tuning.lbm_tb_zchunk > 0 ? g_tuning.lbm_tb_zchunk : 32;
+    while (zchunk > 8 && (int64_t)gx * gy * ((nz + zchunk - 1) / zchunk) < 148 * 4) zchunk /= 2;
+    const int gz = (nz + zchunk - 1) / zchunk;
+    if (gy > 65535 || gz > 65535) return fail(B200GEO_ERR_OUT_OF_RANGE, "grid dimension too large");
+    CUtensorMap map;
+    int rc = window_map(g, NR, &map);
+    if (rc) return rc;
+    EdgeCell edge;
+    for (int m = 0; m < 19; ++m) memcpy(&edge.f[m], g->edge + g->m[m].edge_offset, 4);
+    const size_t smem = WideShape<NR>::smem(NST);
+    static bool attr_set[2][64] = {{false}};
+    auto k1 = lbm_tb2w_kernel<true, NR, NST>;
+    auto k0 = lbm_tb2w_kernel<false, NR, NST>;
+    const int which = store_macroscopic ? 1 : 0;
+    if (g->device < 0 || g->device >= 64 || !attr_set[which][g->device]) {
+        B200GEO_CUDA(cudaFuncSetAttribute(which ? k1 : k0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (g->device >= 0 && g->device < 64) attr_set[which][g->device] = true;
+    }
+    dim3 grid(gx, gy, gz);
+    (which ? k1 : k0)<<<grid, 2 * NR * 32, smem, s>>>(map, src, dst, L.pitch, L.plane, mstride, box, xa, lim, edge, zchunk, L.lead,
+                                                      g->g[1], g->g[2]);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "fused lbm sweeps");
+}
+
 }
 
 // Two sweeps over `box`; the grid's current buffer must hold valid cells two deep around it wherever the box does
@@ -389,6 +646,14 @@ int sweep_lbm_tb2(b200geo_grid *g, const Box& box, bool store_macroscopic, cudaS
     for (int i = 0; i < 3; ++i) {
         lim.lo[i] = g->desc.ghost_mode[i][0] == B200GEO_GHOST_EDGE ? 0 : INT_MIN;
         lim.hi[i] = g->desc.ghost_mode[i][1] == B200GEO_GHOST_EDGE ? g->d[i] : INT_MAX;
+    }
+    if (g_tuning.lbm_tb_warps) {   // sweep 1 and sweep 2 on different warps
+        switch (g_tuning.lbm_tb_rows) {
+        case 12: return launch_tb2w<12, 2>(g, box, lim, store_macroscopic, s);
+        case 123: return launch_tb2w<12, 3>(g, box, lim, store_macroscopic, s);
+        case 10: return launch_tb2w<10, 3>(g, box, lim, store_macroscopic, s);
+        default: return launch_tb2w<14, 2>(g, box, lim, store_macroscopic, s);
+        }
     }
     switch (g_tuning.lbm_tb_rows) {
     case 8: return launch_tb2<8, 2, 2>(g, box, lim, store_macroscopic, s);     // two small CTAs per SM

@@ -36,14 +36,21 @@ def assert_equal(grid, want, what=""):
         assert np.array_equal(got.view(np.int32), want[m].view(np.int32)), "%s member %s" % (what, name)
 
 
-@pytest.mark.parametrize("rows", [14, 142, 16, 8])
+# (lbm.tb_warps, lbm.tb_rows): all warps do both sweeps (two CTA-wide barriers per plane; 14 rows x 3 stages, 14 x 2, 16 x 2,
+# 8 x 2 with two CTAs per SM) / sweep 1 and sweep 2 on different warps linked by mbarriers (14 rows x 2 stages, 12 x 2, 12 x 3,
+# 10 x 3)
+VARIANTS = [(0, 14), (0, 142), (0, 16), (0, 8), (1, 14), (1, 12), (1, 123), (1, 10)]
+
+
+@pytest.mark.parametrize("warps,rows", VARIANTS)
 @pytest.mark.parametrize("zchunk", [0, 8])
 @pytest.mark.parametrize("shape,steps", [((16, 18, 20), 12), ((5, 4, 3), 5), ((3, 40, 70), 2), ((21, 31, 97), 7),
                                          ((40, 29, 33), 4), ((2, 2, 2), 6), ((64, 64, 64), 30)])
-def test_lbm_fused_bit_exact(oracle, tuning, rows, zchunk, shape, steps):
+def test_lbm_fused_bit_exact(oracle, tuning, warps, rows, zchunk, shape, steps):
     """the lid-driven cavity of configs[3] at small sizes: grids narrower and wider than a tile, ragged last tiles in x
     and y, z chunks of 8 planes (several CTAs along z, first-sweep planes recomputed at the seams)"""
     tuning("lbm.tb", 2)
+    tuning("lbm.tb_warps", warps)
     tuning("lbm.tb_rows", rows)
     tuning("lbm.tb_zchunk", zchunk)
     nz, ny, nx = shape
@@ -56,11 +63,12 @@ def test_lbm_fused_bit_exact(oracle, tuning, rows, zchunk, shape, steps):
     assert_equal(grid, oracle.lbm(raw, steps))
 
 
-@pytest.mark.parametrize("rows", [14, 142, 16, 8])
+@pytest.mark.parametrize("warps,rows", VARIANTS)
 @pytest.mark.parametrize("seed", [1, 2, 3])
-def test_lbm_fused_walls_anywhere(oracle, tuning, rows, seed):
+def test_lbm_fused_walls_anywhere(oracle, tuning, warps, rows, seed):
     """every wall state in random cells of the domain — inside tiles, on tile seams, in the ring of first-sweep cells
     that two CTAs compute — on top of the cavity's faces: both sweeps of a launch go through the wall rules"""
+    tuning("lbm.tb_warps", warps)
     tuning("lbm.tb_rows", rows)
     tuning("lbm.tb_zchunk", 8)
     nx, ny, nz = 75, 37, 19
@@ -78,11 +86,13 @@ def test_lbm_fused_walls_anywhere(oracle, tuning, rows, seed):
         assert_equal(grid, oracle.lbm(raw, 5), "tb %d" % tb)
 
 
-def test_lbm_fused_equals_one_sweep_per_launch(tuning):
+@pytest.mark.parametrize("warps", [0, 1])
+def test_lbm_fused_equals_one_sweep_per_launch(tuning, warps):
     """no oracle in between: the two schedules of the device path agree on a grid of several hundred tiles"""
     nx, ny, nz = 200, 150, 70
     raw = synth.lbm_grid(nx, ny, nz, noise=0.01)
     results = []
+    tuning("lbm.tb_warps", warps)
     for tb in (1, 2):
         tuning("lbm.tb", tb)
         grid = B200Grid(M, (nx, ny, nz))
@@ -115,11 +125,13 @@ def test_lbm_macroscopics_modes_fused(oracle, tuning):
 
 @pytest.mark.parametrize("origin,dim", [((0, 0, 0), (50, 30, 20)), ((3, 5, 2), (40, 17, 9)), ((31, 13, 7), (3, 2, 1)),
                                         ((1, 0, 11), (49, 30, 9)), ((17, 1, 0), (33, 28, 20))])
-def test_lbm_update_box_two_sweeps(oracle, tuning, origin, dim):
+@pytest.mark.parametrize("warps", [0, 1])
+def test_lbm_update_box_two_sweeps(oracle, tuning, origin, dim, warps):
     """b200geo_update_box_n(n_sweeps = 2) on boxes inside the grid: the box holds the cells of time step 2 (the ring of
     first-sweep cells around it is computed from the grid, cells outside the simulation area stay the edge cell),
     everything else in the scratch buffer is untouched"""
     tuning("lbm.tb_zchunk", 8)
+    tuning("lbm.tb_warps", warps)
     nx, ny, nz = 50, 30, 20
     raw = synth.lbm_grid(nx, ny, nz, noise=0.01)
     want = oracle.lbm(raw, 2)
