@@ -188,6 +188,11 @@ int b200geo_stream_wait(int device, void *waiter, void *signaller);
  * _load_region with location = B200GEO_CUDA_DEVICE. */
 int b200geo_device_alloc(int device, uint64_t bytes, void **ptr);
 int b200geo_device_free(int device, void *ptr);
+/* Copy between such buffers: device to device across GPUs (over NVLink where the GPUs are peers — what a PatchLink
+ * between two steppers of one process does instead of MPI_Isend / MPI_Irecv, communication/patchlink.h:127-151,
+ * 218-244), or to / from host memory (device index < 0). Ordered after everything enqueued so far on the null streams
+ * of both devices and before whatever is enqueued there afterwards. */
+int b200geo_device_copy(int dst_device, void *dst, int src_device, const void *src, uint64_t bytes);
 /* Page-locked host memory: Initializers / Writers that hand the engine whole boxes (GridBase::loadMember /
  * saveMember, storage/gridbase.h:217-261) out of such a buffer move them at the full speed of the link; pageable
  * memory works as well, only slower (the driver stages it). */

@@ -30,6 +30,7 @@
 #include <libgeodecomp/storage/serializationbuffer.h>
 
 #include "b200simulator.h"
+#include "b200patchlink.h"
 
 namespace LibGeoDecomp {
 
@@ -134,6 +135,9 @@ public:
     std::size_t launchCount() const { return launches; }
     std::size_t pullCount() const { return pulls; }
     std::size_t pushCount() const { return pushes; }
+    /* patches handed to / taken from accepters and providers that work on the device grid (B200PatchLink) */
+    std::size_t devicePutCount() const { return devicePuts; }
+    std::size_t deviceGetCount() const { return deviceGets; }
 
     /* Proceed the simulation exactly one nano step (vanillastepper.h:93-135) */
     virtual void update1()
@@ -145,6 +149,7 @@ public:
             launches += deviceGridPtr->updateRegion(innerSet(index), curNanoStep);
             deviceGridPtr->swapBuffers();
             hostIsCurrent = false;
+            lastPulledValid = false;
 
             ++curNanoStep;
             if (curNanoStep == NANO_STEPS) {
@@ -180,6 +185,10 @@ private:
     std::size_t launches;
     mutable std::size_t pulls;
     std::size_t pushes;
+    std::size_t devicePuts = 0, deviceGets = 0;
+    Region<DIM> lastPulled;
+    std::size_t lastPulledNanoStep = 0;
+    bool lastPulledValid = false;
 
     /* device (current buffer) -> host grid */
     void pull(const Region<DIM>& region) const
@@ -215,37 +224,62 @@ private:
         deviceGridPtr->loadRegionCells(buffer, region, Coord<DIM>(), 0);
     }
 
-    /* PatchAccepters read the HOST grid: bring the region over only if one of them is due at this nano step */
+    /* PatchAccepters read the HOST grid: bring the region over only if one of them is due at this nano step. Accepters
+     * that take the device grid (B200DevicePatchAccepter) get it as it is. Same order, same conditions as
+     * CommonStepper::notifyPatchAccepters (commonstepper.h:112-131). */
     void notifyAccepters(const Region<DIM>& region, const PatchType& patchType, std::size_t nanoStep)
     {
-        bool due = false;
+        TimePatchAccepters t(&chronometer);
         for (typename PatchAccepterList::iterator i = patchAccepters[patchType].begin(); i != patchAccepters[patchType].end(); ++i) {
-            due |= nanoStep == (*i)->nextRequiredNanoStep();
+            if (nanoStep != (*i)->nextRequiredNanoStep()) {
+                continue;
+            }
+            B200DevicePatchAccepter<CELL_TYPE> *direct = dynamic_cast<B200DevicePatchAccepter<CELL_TYPE>*>(&**i);
+            if (direct) {
+                direct->putDevice(*deviceGridPtr, region, partitionManager->getSimulationArea(), nanoStep, partitionManager->rank());
+                ++devicePuts;
+                continue;
+            }
+            if (!hostIsCurrent && !pulledFor(region, nanoStep)) {
+                pull(region);
+                lastPulled = region;
+                lastPulledNanoStep = nanoStep;
+                lastPulledValid = true;
+            }
+            (*i)->put(*oldGrid, region, partitionManager->getSimulationArea(), nanoStep, partitionManager->rank());
         }
-        if (!due) {
-            return;
-        }
-        if (!hostIsCurrent) {
-            pull(region);
-        }
-        ParentType::notifyPatchAccepters(region, patchType, nanoStep);
     }
 
-    /* PatchProviders write the HOST grid: hand them the current cells, take the region back afterwards */
+    /* PatchProviders write the HOST grid: hand them the current cells, take the region back afterwards; providers that
+     * take the device grid (B200DevicePatchProvider) write it directly (commonstepper.h:133-153) */
     void notifyProviders(const Region<DIM>& region, const PatchType& patchType, std::size_t nanoStep)
     {
-        bool due = false;
+        TimePatchProviders t(&chronometer);
         for (typename PatchProviderList::iterator i = patchProviders[patchType].begin(); i != patchProviders[patchType].end(); ++i) {
-            due |= nanoStep == (*i)->nextAvailableNanoStep();
+            if (nanoStep != (*i)->nextAvailableNanoStep()) {
+                continue;
+            }
+            B200DevicePatchProvider<CELL_TYPE> *direct = dynamic_cast<B200DevicePatchProvider<CELL_TYPE>*>(&**i);
+            if (direct) {
+                direct->getDevice(&*deviceGridPtr, region, partitionManager->getSimulationArea(), nanoStep, partitionManager->rank(), true);
+                hostIsCurrent = false;
+                lastPulledValid = false;
+                ++deviceGets;
+                continue;
+            }
+            if (!hostIsCurrent) {
+                pull(region);
+            }
+            (*i)->get(&*oldGrid, region, partitionManager->getSimulationArea(), nanoStep, partitionManager->rank(), true);
+            push(*oldGrid, region);
+            lastPulledValid = false;
         }
-        if (!due) {
-            return;
-        }
-        if (!hostIsCurrent) {
-            pull(region);
-        }
-        ParentType::notifyPatchProviders(region, patchType, nanoStep);
-        push(*oldGrid, region);
+    }
+
+    /* several host-side accepters due at the same nano step for the same region share one pull */
+    bool pulledFor(const Region<DIM>& region, std::size_t nanoStep) const
+    {
+        return lastPulledValid && lastPulledNanoStep == nanoStep && lastPulled == region;
     }
 
     void saveRim(std::size_t nanoStep)
@@ -267,6 +301,7 @@ private:
             if (rimPatch[i].used && rimPatch[i].nanoStep == globalNanoStep()) {
                 deviceGridPtr->loadRegionFromDevice(rimPatch[i].data, rim());
                 hostIsCurrent = false;
+                lastPulledValid = false;
                 if (remove) {
                     rimPatch[i].used = false;
                 }
@@ -285,6 +320,7 @@ private:
     {
         deviceGridPtr->loadRegionFromDevice(kernelPatch, getVolatileKernel());
         hostIsCurrent = false;
+        lastPulledValid = false;
     }
 
     inline void initGrids()
@@ -345,6 +381,7 @@ private:
 
                 deviceGridPtr->swapBuffers();
                 hostIsCurrent = false;
+                lastPulledValid = false;
                 ++curGlobalNanoStep;
             }
 

@@ -86,6 +86,7 @@ SYMBOLS = [
     ("b200geo_stream_wait", ctypes.c_int, [ctypes.c_int, _vp, _vp]),
     ("b200geo_device_alloc", ctypes.c_int, [ctypes.c_int, ctypes.c_uint64, ctypes.POINTER(ctypes.c_void_p)]),
     ("b200geo_device_free", ctypes.c_int, [ctypes.c_int, _vp]),
+    ("b200geo_device_copy", ctypes.c_int, [ctypes.c_int, _vp, ctypes.c_int, _vp, ctypes.c_uint64]),
     ("b200geo_host_alloc", ctypes.c_int, [ctypes.c_uint64, ctypes.POINTER(ctypes.c_void_p)]),
     ("b200geo_host_free", ctypes.c_int, [_vp]),
     ("b200geo_halo_block", ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,

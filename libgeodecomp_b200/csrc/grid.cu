@@ -739,6 +739,22 @@ int b200geo_device_free(int device, void *ptr)
     return B200GEO_OK;
 }
 
+int b200geo_device_copy(int dst_device, void *dst, int src_device, const void *src, uint64_t bytes)
+{
+    if (bytes == 0) return B200GEO_OK;
+    if (!dst || !src) return fail(B200GEO_ERR_INVALID, "null argument");
+    if (dst_device >= 0 && src_device >= 0 && dst_device != src_device) {
+        B200GEO_CUDA(cudaSetDevice(dst_device));
+        B200GEO_CUDA(cudaMemcpyPeer(dst, dst_device, src, src_device, (size_t)bytes));
+        return B200GEO_OK;
+    }
+    B200GEO_CUDA(cudaSetDevice(dst_device >= 0 ? dst_device : src_device >= 0 ? src_device : 0));
+    const cudaMemcpyKind kind = dst_device >= 0 ? (src_device >= 0 ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice) :
+                                                  (src_device >= 0 ? cudaMemcpyDeviceToHost : cudaMemcpyHostToHost);
+    B200GEO_CUDA(cudaMemcpy(dst, src, (size_t)bytes, kind));
+    return B200GEO_OK;
+}
+
 int b200geo_host_alloc(uint64_t bytes, void **ptr)
 {
     if (!ptr) return fail(B200GEO_ERR_INVALID, "null argument");

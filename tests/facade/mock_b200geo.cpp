@@ -452,6 +452,7 @@ int b200geo_stream_destroy(int, void *) { return B200GEO_OK; }
 int b200geo_stream_wait(int, void *, void *) { return B200GEO_OK; }
 int b200geo_device_alloc(int, uint64_t bytes, void **ptr) { *ptr = malloc(bytes ? (size_t)bytes : 1); return *ptr ? B200GEO_OK : fail(B200GEO_ERR_NOMEM, "out of memory"); }
 int b200geo_device_free(int, void *ptr) { free(ptr); return B200GEO_OK; }
+int b200geo_device_copy(int, void *dst, int, const void *src, uint64_t bytes) { memcpy(dst, src, (size_t)bytes); return B200GEO_OK; }
 int b200geo_host_alloc(uint64_t bytes, void **ptr) { *ptr = malloc(bytes ? (size_t)bytes : 1); return *ptr ? B200GEO_OK : fail(B200GEO_ERR_NOMEM, "out of memory"); }
 int b200geo_host_free(void *ptr) { free(ptr); return B200GEO_OK; }
 int b200geo_halo_block(const b200geo_grid *, int, int, int, int, void **, uint64_t *) { return fail(B200GEO_ERR_LOGIC, "not in the mock"); }

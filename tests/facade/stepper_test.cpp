@@ -246,13 +246,35 @@ static void runCase(const char *name, const Coord<APITraits::SelectTopology<CELL
  * inner ghost zone fragment -> accepter on the sender, outer ghost zone fragment -> provider on the receiver, charged with
  * ghostZoneWidth, 2 * ghostZoneWidth, ...). The steppers are advanced round-robin, ghostZoneWidth nano steps each; the
  * union of their own regions must equal the whole-space SerialSimulator run. No MPI, no host-side simulator. */
-template<typename CELL>
-static void runBricks(const char *name, const Coord<3>& dim, int nodes, unsigned ghostZoneWidth, unsigned rounds)
+template<typename LINK> struct LinkStats {
+    static std::size_t device(const LINK&) { return 0; }
+    static std::size_t peer(const LINK&) { return 0; }
+    static const char *name() { return "PatchBuffer"; }
+};
+template<typename CELL, typename GRID> struct LinkStats<B200PatchLink<CELL, GRID> > {
+    static std::size_t device(const B200PatchLink<CELL, GRID>& link) { return link.deviceTransferCount(); }
+    static std::size_t peer(const B200PatchLink<CELL, GRID>& link) { return link.peerCopyCount(); }
+    static const char *name() { return "B200PatchLink"; }
+};
+
+/* devices the bricks' steppers run on: every GPU of the box round-robin; the mock engine (one pretend device) is told
+ * about two, so that the copy between the GPUs of a link is part of the CPU suite as well */
+static int deviceFor(int node)
+{
+    static int count = 0;
+    if (count == 0) {
+        count = std::string(b200geo_version()).find("mock") != std::string::npos ? 2 : (std::max)(1, b200geo_device_count());
+    }
+    return node % count;
+}
+
+template<typename CELL, typename LINK>
+static void runBricksWith(const char *name, const Coord<3>& dim, int nodes, unsigned ghostZoneWidth, unsigned rounds)
 {
     typedef typename APITraits::SelectTopology<CELL>::Value Topology;
     typedef B200Stepper<CELL> StepperType;
     typedef typename StepperType::GridType GridType;
-    typedef PatchBuffer<GridType, GridType> Link;
+    typedef LINK Link;
     const unsigned steps = ghostZoneWidth * rounds;
     CoordBox<3> box(Coord<3>(), dim);
 
@@ -283,6 +305,7 @@ static void runBricks(const char *name, const Coord<3>& dim, int nodes, unsigned
     std::vector<typename StepperType::PatchAccepterVec> accepters(nodes);
     std::vector<typename StepperType::PatchProviderVec> providers(nodes);
     std::size_t links = 0;
+    std::vector<typename SharedPtr<Link>::Type> allLinks;
     for (int i = 0; i < nodes; ++i) {
         typename PartitionManager<Topology>::RegionVecMap& inner = managers[i]->getInnerGhostZoneFragments();
         for (typename PartitionManager<Topology>::RegionVecMap::iterator f = inner.begin(); f != inner.end(); ++f) {
@@ -299,13 +322,16 @@ static void runBricks(const char *name, const Coord<3>& dim, int nodes, unsigned
             }
             accepters[i].push_back(link);
             providers[j].push_back(link);
+            allLinks.push_back(link);
             ++links;
         }
     }
     std::vector<typename SharedPtr<StepperType>::Type> steppers(nodes);
     for (int i = 0; i < nodes; ++i) {
         typename SharedPtr<SeededInitializer<CELL> >::Type init(new SeededInitializer<CELL>(dim, steps));
-        steppers[i].reset(new StepperType(managers[i], init, accepters[i], typename StepperType::PatchAccepterVec(), providers[i]));
+        steppers[i].reset(new StepperType(managers[i], init, accepters[i], typename StepperType::PatchAccepterVec(), providers[i],
+                                          typename StepperType::PatchProviderVec(), typename StepperType::PatchProviderVec(), false,
+                                          deviceFor(i)));
     }
     for (unsigned r = 0; r < rounds; ++r) {
         for (int i = 0; i < nodes; ++i) {
@@ -313,7 +339,23 @@ static void runBricks(const char *name, const Coord<3>& dim, int nodes, unsigned
         }
     }
     long bad = 0, cells = 0;
-    std::size_t launches = 0;
+    std::size_t launches = 0, pullsBefore = 0, direct = 0, peer = 0, puts = 0, gets = 0;
+    for (int i = 0; i < nodes; ++i) {
+        pullsBefore += steppers[i]->pullCount();
+        puts += steppers[i]->devicePutCount();
+        gets += steppers[i]->deviceGetCount();
+    }
+    for (std::size_t k = 0; k < allLinks.size(); ++k) {
+        direct += LinkStats<Link>::device(*allLinks[k]);
+        peer += LinkStats<Link>::peer(*allLinks[k]);
+    }
+    const bool deviceLinks = std::string(LinkStats<Link>::name()) == "B200PatchLink";
+    if (deviceLinks) {
+        /* every ghost zone went device to device: the host grids saw nothing but the initial state */
+        CHECK(direct == links * (rounds + 1));
+        CHECK(puts == direct && gets == links * rounds);
+        CHECK(pullsBefore == 0);
+    }
     for (int i = 0; i < nodes; ++i) {
         const GridType& grid = steppers[i]->grid();
         const Region<3>& own = managers[i]->ownRegion();
@@ -326,8 +368,67 @@ static void runBricks(const char *name, const Coord<3>& dim, int nodes, unsigned
     }
     CHECK(bad == 0);
     CHECK(cells == (long)dim.prod());
-    std::printf("%-13s %d bricks (RecursiveBisectionPartition), ghost zone width %u, %u nano steps, %zu PatchBuffer links: "
-                "%ld of %ld cells differ from the whole-space run, %zu launches\n", name, nodes, ghostZoneWidth, steps, links, bad, cells, launches);
+    std::printf("%-13s %d bricks (RecursiveBisectionPartition), ghost zone width %u, %u nano steps, %zu %s links: "
+                "%ld of %ld cells differ from the whole-space run, %zu launches; %zu regions device to device (%zu across GPUs), "
+                "%zu host pulls during the run\n", name, nodes, ghostZoneWidth, steps, links, LinkStats<Link>::name(), bad, cells, launches,
+                direct, peer, pullsBefore);
+}
+
+template<typename CELL>
+static void runBricks(const char *name, const Coord<3>& dim, int nodes, unsigned ghostZoneWidth, unsigned rounds)
+{
+    typedef typename B200Stepper<CELL>::GridType GridType;
+    runBricksWith<CELL, PatchBuffer<GridType, GridType> >(name, dim, nodes, ghostZoneWidth, rounds);
+    runBricksWith<CELL, B200PatchLink<CELL> >(name, dim, nodes, ghostZoneWidth, rounds);
+}
+
+/* the two ends of a B200PatchLink need not both be B200Steppers: a region put from a host grid is taken by a device
+ * grid and the other way round (the bookkeeping of PatchBuffer either way) */
+static void testMixedLinkEnds()
+{
+    typedef Jacobi7Cube CELL;
+    typedef B200Stepper<CELL>::GridType HostGrid;
+    const Coord<3> dim(12, 6, 5);
+    CoordBox<3> box(Coord<3>(), dim);
+    HostGrid host(box, CELL(0.5), CELL(0.25), dim);
+    for (CoordBox<3>::Iterator i = box.begin(); i != box.end(); ++i) {
+        host.set(*i, Seed<CELL>::make(i->toIndex(dim)));
+    }
+    B200Grid<CELL> dev(box, CELL(0.25));
+    Region<3> region;
+    region << CoordBox<3>(Coord<3>(2, 1, 1), Coord<3>(7, 3, 2)) << Streak<3>(Coord<3>(0, 5, 4), 12);
+    B200PatchLink<CELL> link(region);
+    link.pushRequest(4);
+    link.pushRequest(8);
+    link.put(host, region, dim, 3, 0);      /* not asked for: ignored */
+    link.put(host, region, dim, 4, 0);
+    CHECK(link.nextAvailableNanoStep() == 4 && link.nextRequiredNanoStep() == 8);
+    link.getDevice(&dev, region, dim, 4, 0, true);
+    long bad = 0;
+    for (Region<3>::Iterator i = region.begin(); i != region.end(); ++i) {
+        bad += !(dev.get(*i) == host.get(*i));
+    }
+    CHECK(bad == 0);
+    CHECK(dev.get(Coord<3>(0, 0, 0)) == CELL());   /* nothing outside the region was touched */
+    dev.set(Coord<3>(3, 2, 1), CELL(7.5));
+    dev.set(Coord<3>(11, 5, 4), CELL(-2.25));
+    link.putDevice(dev, region, dim, 8, 0);
+    HostGrid back(box, CELL(0.5), CELL(0.25), dim);
+    link.get(&back, region, dim, 8, 0, true);
+    for (Region<3>::Iterator i = region.begin(); i != region.end(); ++i) {
+        bad += !(back.get(*i) == dev.get(*i));
+    }
+    CHECK(bad == 0);
+    CHECK(back.get(Coord<3>(3, 2, 1)) == CELL(7.5) && back.get(Coord<3>(0, 0, 0)) == CELL(0.5));
+    CHECK(link.hostTransferCount() == 1 && link.deviceTransferCount() == 1);
+    bool empty = false;
+    try {
+        link.getDevice(&dev, region, dim, 12, 0, true);
+    } catch (const std::logic_error&) {
+        empty = true;
+    }
+    CHECK(empty);
+    std::printf("B200PatchLink with a host grid at one end: %ld cells differ\n", bad);
 }
 
 int main()
@@ -342,6 +443,7 @@ int main()
         runBricks<Jacobi7Cube>("Jacobi7Cube", Coord<3>(20, 18, 16), 8, 2, 4);     /* 2 x 2 x 2 */
         runBricks<Jacobi27Cube>("Jacobi27Cube", Coord<3>(21, 17, 19), 8, 3, 3);   /* corner and edge neighbours matter */
         runBricks<Jacobi7Cube>("Jacobi7Cube", Coord<3>(24, 10, 9), 6, 1, 5);
+        testMixedLinkEnds();
         /* a Torus cell is refused */
         bool refused = false;
         try {
