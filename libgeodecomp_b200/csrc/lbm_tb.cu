@@ -453,6 +453,15 @@ lbm_tb2w_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restric
                         asm volatile("" : "+l"(ms), "+l"(pl), "+l"(pi));
                         const WindowHood<WS> hood = {cell, {src, (int64_t)p * pl + (int64_t)y * pi + x, pi, pl, ms}};
                         wall(state, hood, out);
+                        // The populations a wall cell bounces back go from the windows straight into `out`: no
+                        // arithmetic needs them, so nothing would make this warp wait for those shared-memory loads
+                        // before it tells the producer that the stage may be refilled (one row next to a wall plane was
+                        // wrong in about one launch of twenty at 512^3 that way, profiles/r4o_r4s). Fold every value
+                        // into a word the state below depends on: the loads have been performed when it is known.
+                        int seen = 0;
+#pragma unroll
+                        for (int m = 0; m < 19; ++m) seen ^= __float_as_int(out[m]);
+                        if (seen == 0x7fc5a5a5) state |= 0x40000000;   // (never: no finite population mix gives this NaN pattern; sweep 2 only tests state != LIQUID)
                     } else {
                         const WindowHood<WS> hood = {cell, {src, 0, 0, 0, 0}};
                         Pulled in;
@@ -462,7 +471,8 @@ lbm_tb2w_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restric
                     }
                 }
             }
-            // this warp is done with its row of the windows
+            // this warp has read its row of the windows (liquid cells: every pulled value has gone through arithmetic; wall
+            // cells: see above; `state` is known to all lanes after the branch on it)
             __syncwarp();
             if (lane == 0) mbar_arrive(&tma_empty[ks]);
             if (act1) {
@@ -471,6 +481,8 @@ lbm_tb2w_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restric
                 for (int m = 0; m < 19; ++m) mine[wring_base(m) * PS + (travels_up(m) ? r4 : r3)] = out[m];
                 mine[wring_base(19) * PS + r3] = __int_as_float(state);
             }
+            // the ring stores of all lanes are visible before lane 0 announces the plane
+            __threadfence_block();
             __syncwarp();
             if (lane == 0) mbar_arrive(&l1_full[k4]);
             k3 = k3 == 2 ? 0 : k3 + 1;
@@ -519,13 +531,14 @@ lbm_tb2w_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restric
                     }
                 }
             }
-            // everything this plane needed from the rings is in registers now
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&l2_done[j4]);
             if (act2) {
 #pragma unroll
                 for (int m = 0; m < 19; ++m) dst[(int64_t)m * mstride + i] = out[m];
             }
+            // the arrival comes after the stores: they need every value this plane took from the rings (a wall cell copies
+            // its own populations from the rings straight into `out`), so all those loads have been performed
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&l2_done[j4]);
             j3 = j3 == 2 ? 0 : j3 + 1;
             j4 = (j4 + 1) & 3;
         }
@@ -648,11 +661,15 @@ int sweep_lbm_tb2(b200geo_grid *g, const Box& box, bool store_macroscopic, cudaS
         lim.hi[i] = g->desc.ghost_mode[i][1] == B200GEO_GHOST_EDGE ? g->d[i] : INT_MAX;
     }
     if (g_tuning.lbm_tb_warps) {   // sweep 1 and sweep 2 on different warps
+        // rows of the intermediate level x TMA stages: what fits into 227 KB beside rings of 65 plane slots. Three stages
+        // beat two wider tiles (59 against 54 GLUPS at 512^3, profiles/r4t): the launch waits for its windows
         switch (g_tuning.lbm_tb_rows) {
-        case 12: return launch_tb2w<12, 2>(g, box, lim, store_macroscopic, s);
-        case 123: return launch_tb2w<12, 3>(g, box, lim, store_macroscopic, s);
-        case 10: return launch_tb2w<10, 3>(g, box, lim, store_macroscopic, s);
-        default: return launch_tb2w<14, 2>(g, box, lim, store_macroscopic, s);
+        case 142: return launch_tb2w<14, 2>(g, box, lim, store_macroscopic, s);
+        case 122: return launch_tb2w<12, 2>(g, box, lim, store_macroscopic, s);
+        case 113: return launch_tb2w<11, 3>(g, box, lim, store_macroscopic, s);
+        case 104: return launch_tb2w<10, 4>(g, box, lim, store_macroscopic, s);
+        case 103: return launch_tb2w<10, 3>(g, box, lim, store_macroscopic, s);
+        default: return launch_tb2w<12, 3>(g, box, lim, store_macroscopic, s);
         }
     }
     switch (g_tuning.lbm_tb_rows) {

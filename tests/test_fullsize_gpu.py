@@ -94,6 +94,59 @@ def test_lbm_512_cubed_planes(oracle, steps):
     gc.collect()
 
 
+def test_lbm_512_cubed_repeated_fused_launches():
+    """The fused LBM kernel hands planes from its sweep-1 warps to its sweep-2 warps through mbarriers; an arrival that
+    came before a wall cell's shared-memory loads had been performed made ONE row next to a wall plane wrong in about one
+    launch of twenty at this size — and only at this size (profiles/r4o_r4u). 40 launches from the same input, every
+    one compared on the device, value by value, with two single-sweep launches (themselves checked against the oracle
+    above)."""
+    import torch
+    n = 512
+    if not free_enough(60):
+        pytest.skip("needs 60 GB of device memory")
+    model = models.LBMCellF
+    noise = synth.lbm_grid(n, n, 16, noise=0.01, z0=16, nz_total=n)
+
+    def fresh():
+        grid = B200Grid(model, (n, n, n))
+        for z in range(0, n, 16):
+            states = synth.lbm_states(n, n, 16, z, n)
+            for m, (name, t) in enumerate(model.members):
+                grid.loadMember(name, states if name == "state" else noise[m].view(t), origin=(0, 0, z))
+        return grid
+
+    def populations(grid):
+        out = []
+        for m in range(19):
+            t = torch.empty((n, n, n), dtype=torch.float32, device="cuda")
+            grid.saveMember(model.members[m][0], out=t, location=capi.CUDA_DEVICE)
+            out.append(t.view(torch.int32))
+        return out
+
+    try:
+        capi.set_tuning("lbm.tb", 1)
+        grid = fresh()
+        grid.dev.step(model.kernel, 2)
+        want = populations(grid)
+        del grid
+        capi.set_tuning("lbm.tb", 2)
+        grid = fresh()
+        for launch in range(40):
+            before = capi.launch_count()
+            grid.dev.step(model.kernel, 2)      # current -> scratch buffer; the input stays where it is
+            assert capi.launch_count() - before == 1
+            got = populations(grid)
+            for m in range(19):
+                assert torch.equal(got[m], want[m]), (launch, model.members[m][0])
+            del got
+            grid.dev.swap()                     # the next launch starts from the same input
+    finally:
+        capi.set_tuning("lbm.tb", -1)
+    del grid, want
+    gc.collect()
+    torch.cuda.empty_cache()
+
+
 @pytest.mark.parametrize("bits", [0, 4])
 def test_gol_16384_squared_whole_grid(oracle, bits):
     n, steps = 16384, 8

@@ -37,9 +37,9 @@ def assert_equal(grid, want, what=""):
 
 
 # (lbm.tb_warps, lbm.tb_rows): all warps do both sweeps (two CTA-wide barriers per plane; 14 rows x 3 stages, 14 x 2, 16 x 2,
-# 8 x 2 with two CTAs per SM) / sweep 1 and sweep 2 on different warps linked by mbarriers (14 rows x 2 stages, 12 x 2, 12 x 3,
-# 10 x 3)
-VARIANTS = [(0, 14), (0, 142), (0, 16), (0, 8), (1, 14), (1, 12), (1, 123), (1, 10)]
+# 8 x 2 with two CTAs per SM) / sweep 1 and sweep 2 on different warps linked by mbarriers (12 rows x 3 stages = the default, 14 x 2,
+# 12 x 2, 11 x 3, 10 x 4, 10 x 3)
+VARIANTS = [(0, 14), (0, 142), (0, 16), (0, 8), (1, 123), (1, 142), (1, 122), (1, 113), (1, 104), (1, 103)]
 
 
 @pytest.mark.parametrize("warps,rows", VARIANTS)
