@@ -17,5 +17,5 @@ PY
 tail -3 gpurun_out/r4final_bench.err
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/r4final_launches.csv python bench.py --steps 20 --warmup 5 --no-cpu --no-verify --no-stream > gpurun_out/r4final_bench_under_ncu.log 2>&1; wc -l gpurun_out/r4final_launches.csv
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:jacobi_tb -s 2 -c 1 -o gpurun_out/r4final_tb27_full python tools/few_launches.py jacobi27 jacobi.tb=2 > /dev/null 2>&1; ls -la gpurun_out/r4final_tb27_full.ncu-rep
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:jacobi_tb -s 2 -c 1 -o gpurun_out/r4final_tb7_full python tools/few_launches.py jacobi7 jacobi.tb=4 > /dev/null 2>&1; ls -la gpurun_out/r4final_tb7_full.ncu-rep
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:jacobi_tb -s 2 -c 1 -o gpurun_out/r4final_tb7_full python tools/few_launches.py jacobi7 jacobi.tb=4 --sweeps 16 > /dev/null 2>&1; ls -la gpurun_out/r4final_tb7_full.ncu-rep
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:lbm_tb2w -s 1 -c 1 -o gpurun_out/r4final_lbm_full python tools/few_launches.py lbm lbm.tb=2 > /dev/null 2>&1; ls -la gpurun_out/r4final_lbm_full.ncu-rep
