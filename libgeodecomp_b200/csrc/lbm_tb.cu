@@ -365,7 +365,7 @@ struct WideShape {
     static constexpr int WS = Shape<NR>::WS;
     static constexpr int STAGE = Shape<NR>::STAGE;
     static constexpr int WARPS = 2 * NR;   // NR + 1 for sweep 1, NR - 2 for sweep 2, one producer
-    static constexpr size_t smem(int nst) { return (size_t)nst * STAGE * 4 + (size_t)WSLOTS * PS * 4 + (2 * nst + 8) * 8; }
+    static constexpr size_t smem(int nst) { return (size_t)nst * STAGE * 4 + (size_t)WSLOTS * PS * 4 + (2 * nst + 8) * 8 + 8; }
 };
 
 template<bool MACRO, int NR, int NST>
@@ -384,6 +384,7 @@ lbm_tb2w_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restric
     uint64_t *tma_empty = tma_full + NST;
     uint64_t *l1_full = tma_empty + NST;         // [4]
     uint64_t *l2_done = l1_full + 4;             // [4]
+    int *sink = reinterpret_cast<int *>(l2_done + 4);
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int X0 = xa + blockIdx.x * 32, Y0 = box.y0 + blockIdx.y * (NR - 2);
@@ -438,6 +439,7 @@ lbm_tb2w_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restric
             mbar_wait(&tma_full[ks], (k / NST) & 1);
             float out[19];
             int state = LIQUID;
+            int seen = 0, all_loaded = 0;
             if (act1) {
                 if (outside_xy || p < lim.lo[2] || p >= lim.hi[2]) {
 #pragma unroll
@@ -454,14 +456,9 @@ lbm_tb2w_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restric
                         const WindowHood<WS> hood = {cell, {src, (int64_t)p * pl + (int64_t)y * pi + x, pi, pl, ms}};
                         wall(state, hood, out);
                         // The populations a wall cell bounces back go from the windows straight into `out`: no
-                        // arithmetic needs them, so nothing would make this warp wait for those shared-memory loads
-                        // before it tells the producer that the stage may be refilled (one row next to a wall plane was
-                        // wrong in about one launch of twenty at 512^3 that way, profiles/r4o_r4s). Fold every value
-                        // into a word the state below depends on: the loads have been performed when it is known.
-                        int seen = 0;
+                        // arithmetic needs them. Fold them into `seen` (see the arrival on tma_empty below).
 #pragma unroll
                         for (int m = 0; m < 19; ++m) seen ^= __float_as_int(out[m]);
-                        if (seen == 0x7fc5a5a5) state |= 0x40000000;   // (never: no finite population mix gives this NaN pattern; sweep 2 only tests state != LIQUID)
                     } else {
                         const WindowHood<WS> hood = {cell, {src, 0, 0, 0, 0}};
                         Pulled in;
@@ -471,8 +468,16 @@ lbm_tb2w_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restric
                     }
                 }
             }
-            // this warp has read its row of the windows (liquid cells: every pulled value has gone through arithmetic; wall
-            // cells: see above; `state` is known to all lanes after the branch on it)
+            // This warp has read its row of the windows — but "has issued the loads" is not enough: the arrival lets the
+            // producer refill the stage, and a shared-memory load that is still in flight then returns the plane after
+            // next (one row beside a wall plane was wrong in about one launch of twenty at 512^3 that way, profiles/
+            // r4o_r4u: a wall cell's bounced-back populations feed no arithmetic). So an instruction that NEEDS every
+            // loaded value is put in front of the arrival — warps issue in order, and a warp-wide instruction waits for
+            // the producers of its operands in all lanes: `all_loaded` is known when out[C] (liquid cells: C's new value
+            // needs the density, i.e. all 19 pulled values) and `seen` (wall cells: everything they loaded) are. The
+            // store it guards goes to a word nobody reads and practically never happens.
+            if (act1) all_loaded = seen ^ __float_as_int(out[C]);
+            if (all_loaded == 0x7fc5a5a5) *sink = 1;
             __syncwarp();
             if (lane == 0) mbar_arrive(&tma_empty[ks]);
             if (act1) {
