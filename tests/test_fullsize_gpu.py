@@ -65,6 +65,55 @@ def test_jacobi_1024_cubed_windows(oracle, kind, steps):
     gc.collect()
 
 
+@pytest.mark.parametrize("kind,depth", [(27, 2), (7, 4)])
+def test_jacobi_1024_cubed_repeated_fused_launches(kind, depth):
+    """the WHOLE 1024^3 grid, not windows: launches of the temporal-blocked kernel (2 fused sweeps of the 27-point stencil,
+    4 of the 7-point one) from the same input, every one compared on the device, value by value, with the same number of
+    single-sweep launches (whose results the window tests above pin to the oracle). What the windows cannot see — a rare
+    ordering bug somewhere in 5000 CTAs — this does (it is how the LBM kernel's was found)."""
+    import torch
+    n = 1024
+    if not free_enough(40):
+        pytest.skip("needs 40 GB of device memory")
+    model = models.ALL["Jacobi%dCube" % kind]
+    block = torch.from_numpy(synth.jacobi_grid(n, n, 32, seed=5)).cuda()
+
+    def fresh():
+        grid = B200Grid(model, (n, n, n))
+        grid.setEdge(0.5)
+        for z in range(0, n, 32):
+            grid.loadMember("temp", block, origin=(0, 0, z), location=capi.CUDA_DEVICE)
+        return grid
+
+    def values(grid):
+        t = torch.empty((n, n, n), dtype=torch.float64, device="cuda")
+        grid.saveMember("temp", out=t, location=capi.CUDA_DEVICE)
+        return t.view(torch.int64)
+
+    try:
+        capi.set_tuning("jacobi.tb", 1)
+        grid = fresh()
+        grid.dev.step(model.kernel, depth)
+        want = values(grid)
+        del grid
+        capi.set_tuning("jacobi.tb", depth)
+        grid = fresh()
+        for launch in range(12):
+            before = capi.launch_count()
+            grid.dev.step(model.kernel, depth)
+            assert capi.launch_count() - before == 1
+            got = values(grid)
+            assert torch.equal(got, want), launch
+            del got
+            # back to the input: both buffers held it before the first launch, the launch wrote the other one only
+            grid.dev.swap()
+    finally:
+        capi.set_tuning("jacobi.tb", -1)
+    del grid, want, block
+    gc.collect()
+    torch.cuda.empty_cache()
+
+
 @pytest.mark.parametrize("steps", [3, 6])
 def test_lbm_512_cubed_planes(oracle, steps):
     """3 sweeps = one launch of two fused sweeps + one single sweep; 6 = three fused launches. Whole x-y planes: every
