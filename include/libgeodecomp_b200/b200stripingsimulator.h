@@ -83,14 +83,12 @@ public:
         b200geo_group_destroy(group);
     }
 
-    /* ghost zone width = sweeps between two halo exchanges; the temporal-blocked Jacobi kernels fuse the
-     * sweeps of one round into a single launch, so 2 is their default */
+    /* ghost zone width = sweeps between two halo exchanges; the kernel families that fuse sweeps (temporal-blocked
+     * Jacobi, two-sweep LBM) take the sweeps of one round in a single launch per rim / interior, so 2 is their default */
     static int defaultGhostWidth()
     {
-        int k = B200KernelBinding<CELL>::kernel();
-        bool jacobi = k == B200GEO_KERNEL_JACOBI6 || k == B200GEO_KERNEL_JACOBI7 || k == B200GEO_KERNEL_JACOBI27;
         int radius = APITraits::SelectStencil<CELL>::Value::RADIUS;
-        return std::max(radius, jacobi ? 2 : 1);
+        return std::max(radius, B200Helpers::fusedSweeps(B200KernelBinding<CELL>::kernel()) >= 2 ? 2 : 1);
     }
 
     std::size_t numSlabs() const
