@@ -76,6 +76,12 @@ int needed_members(const b200geo_grid *g, int kernel, int width, int side, int *
         memcpy(out, side == 0 ? low : high, n * sizeof(int));
         return n;
     }
+    if (kernel == B200GEO_KERNEL_LBM_D3Q19 && g->n == 24) {
+        // the rim is recomputed: 19 populations and the state; density / velocity of a ghost cell are never read
+        for (int m = 0; m < 19; ++m) out[m] = m;
+        out[19] = 23;
+        return 20;
+    }
     for (int m = 0; m < g->n; ++m) out[m] = m;
     return g->n;
 }

@@ -51,11 +51,17 @@ class CellModel:
         LBM, ghost width 1: only the populations that cross the face are read from a neighbour's
         plane (csrc/lbm.cu: T* from z-1; B* from z+1, plus SE which the EAST_NOSLIP rule of
         src/examples/latticeboltzmann/main.cpp takes from z+1); a wider ghost zone recomputes the rim
-        and needs the neighbours' whole cells."""
+        and needs the neighbours' cells (all that an update reads of them)."""
         if self.kernel == capi.KERNEL_LBM_D3Q19 and width == 1:
             ix = self.member_index
             return ([ix(n) for n in ("T", "TW", "TE", "TN", "TS")],
                     [ix(n) for n in ("B", "BW", "BE", "BN", "BS", "SE")])
+        if self.kernel == capi.KERNEL_LBM_D3Q19:
+            # the rim is recomputed (two fused sweeps per round): the ghost cells' 19 populations and their state, member by
+            # member and in place (no pack kernel, so the transfer overlaps the interior update); density / velocity of a
+            # ghost cell are never read
+            cell = list(range(19)) + [self.member_index("state")]
+            return (cell, cell)
         return None
 
     @property
