@@ -65,8 +65,10 @@ def main():
         if mine.shape != want.shape or not np.array_equal(mine, want):
             failures.append("torus kind %d ghost %d overlap %s rank %d" % (kind, ghost, overlap, rank))
 
-    # LBM D3Q19 (24 members): ghost width 1 ships only the populations that cross the face, member by member and in
-    # place, with the rim-first schedule; ghost width 2 packs whole cells with saveRegion / loadRegion
+    # LBM D3Q19 (24 members): ghost width 1 ships only the populations that cross the face, ghost width 2 (two fused sweeps
+    # per round, the rim recomputed) the 19 populations and the state — member by member and in place, with the rim-first
+    # schedule; the last case forces the packed transport (whole cells through saveRegion / loadRegion, exchange first,
+    # then step: what a multi-member model without a halo_members() list gets)
     class LBMInit(SimpleInitializer):
         def __init__(self, raw, steps):
             SimpleInitializer.__init__(self, raw.shape[1:][::-1], steps)
@@ -77,11 +79,17 @@ def main():
             for m, (name, t) in enumerate(models.LBMCellF.members):
                 target.loadMember(name, self.raw[m, oz:oz + dz, oy:oy + dy, ox:ox + dx].view(t), origin=(ox, oy, oz))
 
-    for ghost, steps, overlap in ((1, 5, True), (1, 4, False), (2, 5, True)):
+    for ghost, steps, overlap, packed in ((1, 5, True, False), (1, 4, False, False), (2, 5, True, False), (2, 4, False, False),
+                                         (2, 5, True, True)):
         nz, ny, nx = 12, 6, 7
         raw = synth.lbm_grid(nx, ny, nz, noise=0.01)
         sim = StripedSimulator(LBMInit(raw, steps), models.LBMCellF, rank=rank, world=world, ghost_width=ghost,
                                dist=dist, engine=cpu_engine, overlap=overlap)
+        if packed:
+            sim.halo.packed = True
+            sim.halo.need = (list(range(24)), list(range(24)))
+        elif sim.halo.packed or (overlap and not sim._can_overlap()):
+            failures.append("lbm ghost %d: halos are packed / rounds not overlapped" % ghost)
         sim.run()
         b = slab_bounds(nz, world)
         want = oracle_py.lbm(raw, steps)
