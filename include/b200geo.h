@@ -52,7 +52,8 @@ typedef enum {
     B200GEO_KERNEL_JACOBI27 = 3, /* 27-point mean over Moore<3,1>, f64; oracle/models/jacobi.h */
     B200GEO_KERNEL_GOL = 4,      /* Conway's Life, 1-byte cells; src/examples/gameoflife/main.cpp:36-59 */
     B200GEO_KERNEL_LBM_D3Q19 = 5,/* D3Q19 BGK + wall states, f32; src/examples/latticeboltzmann/main.cpp:62-229 */
-    B200GEO_KERNEL_NBODY = 6     /* BoxCell short-range n-body; storage/boxcell.h:112-174 */
+    B200GEO_KERNEL_NBODY = 6,    /* BoxCell short-range n-body; storage/boxcell.h:112-174 */
+    B200GEO_KERNEL_CONTAINER = 7 /* ContainerCell ID-keyed cargo (meshfree / unstructured); storage/containercell.h:170-200 */
 } b200geo_kernel;
 
 /* What a ghost (padding) layer on one side of one axis holds. */
@@ -314,6 +315,65 @@ int b200geo_boxgroup_step(b200geo_boxgroup *grp, const b200geo_nbody_params *par
 int b200geo_boxgroup_sync(b200geo_boxgroup *grp);
 /* out[0] = exchanges so far, out[1] = bytes shipped between devices */
 int b200geo_boxgroup_stats(const b200geo_boxgroup *grp, uint64_t out[2]);
+
+/* ---- ContainerCell grids: ID-keyed cargo (B200GEO_KERNEL_CONTAINER) ------------------------------
+ * Replaces Grid<ContainerCell<CARGO, SIZE, int> > (storage/containercell.h:24-218) and, on the step path,
+ * ContainerCell::update = copyOver + updateCargo (containercell.h:170-200) with the ID lookup of
+ * NeighborhoodAdapter::operator[] (storage/neighborhoodadapter.h:45-65: the container itself first, then the other
+ * containers of the 3^DIM Moore box in CoordBox order, x fastest; the first hit wins; each container searched by
+ * upper_bound over its ascending ids, containercell.h:107-121) for the bound cargo model: the mesh element of
+ * src/examples/voronoi/main.cpp:41-54 (oracle/models/container.h),
+ *     temperature' = influx + (sum over neighborIDs, in list order, of hood[id].temperature) / neighborIDs.size().
+ * The reference never adds or removes cargo during a run (containercell.h:44-46), so the engine resolves every
+ * neighbour ID to a cargo index ONCE after a load and sweeps over resolved links from then on.
+ * Interchange format of a box of containers (what GridBase::set/get(Coord, ContainerCell) carry, flattened; cells
+ * in [dz][dy][dx] order, 2-D grids use dim[2] = 1):
+ *   counts    int32  [cells]                            ContainerCell::size()
+ *   ids       int32  [cells][capacity]                  ContainerCell::getIDs(): ascending
+ *   values    double [cells][capacity]                  cargo.temperature
+ *   influx    double [cells][capacity]                  cargo.influx
+ *   nb_counts int32  [cells][capacity]                  cargo.neighborIDs.size()
+ *   nb_ids    int32  [cells][capacity][max_neighbors]   cargo.neighborIDs
+ * Slots >= count are ignored on load and zero on save. */
+typedef struct {
+    int32_t n_dims;           /* DIM of the cargo's topology, 2 or 3: the Moore box has 3^n_dims containers */
+    int32_t dim[3];           /* containers per axis; dim[2] = 1 for n_dims = 2 */
+    int32_t ghost_mode[3][2]; /* EDGE (Cube axis: lookups outside find the edge container) or WRAP (Torus axis), both sides alike */
+    int32_t capacity;         /* SIZE of ContainerCell<CARGO, SIZE>, 1..4096 */
+    int32_t max_neighbors;    /* capacity of the cargo's FixedArray<int, N> neighborIDs, 1..64 */
+} b200geo_containergrid_desc;
+
+typedef struct {
+    int32_t *counts;
+    int32_t *ids;
+    double *values;
+    double *influx;
+    int32_t *nb_counts;
+    int32_t *nb_ids;
+} b200geo_container_box;
+
+typedef struct b200geo_containergrid b200geo_containergrid;
+
+int b200geo_containergrid_create(const b200geo_containergrid_desc *desc, int device, b200geo_containergrid **out);
+int b200geo_containergrid_destroy(b200geo_containergrid *g);
+/* GridBase::set for a box of containers: every array of `box` is read (location: where they live). */
+int b200geo_containergrid_load(b200geo_containergrid *g, const int32_t origin[3], const int32_t dim[3],
+                               const b200geo_container_box *box, int location, void *stream);
+/* GridBase::get for a box of containers: arrays whose pointer is NULL are skipped (a Writer that only wants the
+ * temperatures passes `values` alone). Returns when the data is in place. */
+int b200geo_containergrid_save(const b200geo_containergrid *g, const int32_t origin[3], const int32_t dim[3],
+                               const b200geo_container_box *box, int location, void *stream);
+/* GridBase::setEdge / getEdge: one container (host arrays) found by lookups beyond a Cube boundary. */
+int b200geo_containergrid_set_edge(b200geo_containergrid *g, const b200geo_container_box *cell);
+int b200geo_containergrid_get_edge(const b200geo_containergrid *g, const b200geo_container_box *cell);
+/* n_steps x { every cargo of every container: update against the old grid; swap }. The first call after a load
+ * resolves the neighbour IDs: B200GEO_ERR_LOGIC ("id not found", neighborhoodadapter.h:63-64) if an ID a cargo
+ * lists is in none of the 3^DIM containers around it, B200GEO_ERR_INVALID if a container's ids do not ascend,
+ * B200GEO_ERR_OUT_OF_RANGE if a count exceeds its capacity; the grid is unchanged then. */
+int b200geo_containergrid_step(b200geo_containergrid *g, uint32_t first_nano_step, uint32_t n_steps, void *stream);
+/* out[0] = cargo items in the grid, out[1] = resolved neighbour links, out[2] = link resolutions so far,
+ * out[3] = sweeps so far (valid after the first step) */
+int b200geo_containergrid_stats(const b200geo_containergrid *g, uint64_t out[4]);
 
 /* ---- statistics: Simulator::gatherStatistics / Chronometer (misc/chronometer.h:142-150) ---- */
 /* out[0] = device seconds spent in update kernels (TimeComputeInner), out[1] = seconds in ghost

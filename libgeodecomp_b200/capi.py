@@ -15,6 +15,7 @@ MAX_MEMBERS = 32
 HOST, CUDA_DEVICE = 0, 1
 GHOST_EDGE, GHOST_WRAP, GHOST_PEER = 0, 1, 2
 KERNEL_JACOBI6, KERNEL_JACOBI7, KERNEL_JACOBI27, KERNEL_GOL, KERNEL_LBM_D3Q19, KERNEL_NBODY = 1, 2, 3, 4, 5, 6
+KERNEL_CONTAINER = 7
 
 _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libb200geo.so")
 
@@ -42,6 +43,20 @@ class BoxGridDesc(ctypes.Structure):
                 ("real_bytes", ctypes.c_int32),
                 ("cell_origin", ctypes.c_int32 * 3),
                 ("cell_edge", ctypes.c_double)]
+
+
+class ContainerGridDesc(ctypes.Structure):
+    _fields_ = [("n_dims", ctypes.c_int32),
+                ("dim", ctypes.c_int32 * 3),
+                ("ghost_mode", (ctypes.c_int32 * 2) * 3),
+                ("capacity", ctypes.c_int32),
+                ("max_neighbors", ctypes.c_int32)]
+
+
+class ContainerBox(ctypes.Structure):
+    """b200geo_container_box: the six arrays of a box of containers (interchange format of include/b200geo.h)"""
+    FIELDS = ("counts", "ids", "values", "influx", "nb_counts", "nb_ids")
+    _fields_ = [(n, ctypes.c_void_p) for n in FIELDS]
 
 
 class NBodyParams(ctypes.Structure):
@@ -119,6 +134,14 @@ SYMBOLS = [
     ("b200geo_boxgroup_step", ctypes.c_int, [_vp, ctypes.POINTER(NBodyParams), ctypes.c_uint32, ctypes.c_uint32]),
     ("b200geo_boxgroup_sync", ctypes.c_int, [_vp]),
     ("b200geo_boxgroup_stats", ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_uint64)]),
+    ("b200geo_containergrid_create", ctypes.c_int, [ctypes.POINTER(ContainerGridDesc), ctypes.c_int, ctypes.POINTER(_vp)]),
+    ("b200geo_containergrid_destroy", ctypes.c_int, [_vp]),
+    ("b200geo_containergrid_load", ctypes.c_int, [_vp, _i32p, _i32p, ctypes.POINTER(ContainerBox), ctypes.c_int, _vp]),
+    ("b200geo_containergrid_save", ctypes.c_int, [_vp, _i32p, _i32p, ctypes.POINTER(ContainerBox), ctypes.c_int, _vp]),
+    ("b200geo_containergrid_set_edge", ctypes.c_int, [_vp, ctypes.POINTER(ContainerBox)]),
+    ("b200geo_containergrid_get_edge", ctypes.c_int, [_vp, ctypes.POINTER(ContainerBox)]),
+    ("b200geo_containergrid_step", ctypes.c_int, [_vp, ctypes.c_uint32, ctypes.c_uint32, _vp]),
+    ("b200geo_containergrid_stats", ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_uint64)]),
     ("b200geo_stats_enable", ctypes.c_int, [_vp, ctypes.c_int]),
     ("b200geo_stats", ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_double)]),
 ]
@@ -467,6 +490,77 @@ class DeviceBoxGrid:
 
     def stats(self):
         return {}
+
+
+def container_box(arrays):
+    """ContainerBox from a dict / sequence of the six arrays (None entries = NULL: skipped by save)"""
+    if isinstance(arrays, dict):
+        arrays = [arrays.get(n) for n in ContainerBox.FIELDS]
+    box = ContainerBox()
+    for name, a in zip(ContainerBox.FIELDS, arrays):
+        p = _ptr(a)
+        setattr(box, name, p.value if p is not None else None)
+    return box
+
+
+class DeviceContainerGrid:
+    """Thin object wrapper around a b200geo_containergrid handle (ContainerCell grid of ID-keyed cargo)."""
+
+    def __init__(self, dim, capacity, max_neighbors, n_dims=3, ghost_mode=None, device=0):
+        self._h = None
+        desc = ContainerGridDesc()
+        desc.n_dims = int(n_dims)
+        for i in range(3):
+            desc.dim[i] = int(dim[i])
+            for s in range(2):
+                desc.ghost_mode[i][s] = int(ghost_mode[i][s]) if ghost_mode is not None else GHOST_EDGE
+        desc.capacity, desc.max_neighbors = int(capacity), int(max_neighbors)
+        h = ctypes.c_void_p()
+        check(lib().b200geo_containergrid_create(ctypes.byref(desc), int(device), ctypes.byref(h)))
+        self._h = h
+        self.dim, self.capacity, self.max_neighbors, self.device = tuple(dim), int(capacity), int(max_neighbors), device
+
+    def close(self):
+        if self._h is not None and _lib is not None:
+            _lib.b200geo_containergrid_destroy(self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def load(self, arrays, origin=(0, 0, 0), dim=None, location=HOST, stream=None):
+        dim = self.dim if dim is None else dim
+        box = container_box(arrays)
+        check(lib().b200geo_containergrid_load(self._h, _i3(origin), _i3(dim), ctypes.byref(box), location, stream))
+
+    def save(self, arrays, origin=(0, 0, 0), dim=None, location=HOST, stream=None):
+        dim = self.dim if dim is None else dim
+        box = container_box(arrays)
+        check(lib().b200geo_containergrid_save(self._h, _i3(origin), _i3(dim), ctypes.byref(box), location, stream))
+
+    def set_edge(self, arrays):
+        box = container_box(arrays)
+        check(lib().b200geo_containergrid_set_edge(self._h, ctypes.byref(box)))
+
+    def get_edge(self, arrays):
+        box = container_box(arrays)
+        check(lib().b200geo_containergrid_get_edge(self._h, ctypes.byref(box)))
+
+    def step(self, kernel, n_steps=1, first_nano_step=0, params=None, stream=None):
+        if kernel != KERNEL_CONTAINER:
+            raise LogicError("a ContainerCell grid steps with KERNEL_CONTAINER")
+        check(lib().b200geo_containergrid_step(self._h, first_nano_step, n_steps, stream))
+
+    def stats_enable(self, on=True):
+        pass
+
+    def stats(self):
+        out = (ctypes.c_uint64 * 4)()
+        check(lib().b200geo_containergrid_stats(self._h, out))
+        return {"cargo": int(out[0]), "links": int(out[1]), "resolutions": int(out[2]), "sweeps": int(out[3])}
 
 
 def sync(stream=None):

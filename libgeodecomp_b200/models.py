@@ -135,6 +135,34 @@ class NBodyModel:
         return BoxGrid
 
 
+class ContainerModel:
+    """Binding of ContainerCell<MeshElement<DIM, TORUS>, capacity> (oracle/models/container.h: the mesh element of
+    src/examples/voronoi/main.cpp:9-118, neighbours addressed by ID) to the container kernels: Moore<DIM, 1>,
+    NANO_STEPS 1."""
+
+    def __init__(self, name, dim=3, topology="cube", capacity=16, max_neighbors=20):
+        self.name, self.dim, self.topology, self.radius, self.nano_steps = name, dim, topology, 1, 1
+        self.capacity, self.max_neighbors = capacity, max_neighbors
+        self.kernel = capi.KERNEL_CONTAINER
+        self.ref_model = "container"
+        self.wraps = topology == "torus"
+        self.fuses_sweeps = False
+        self.max_fused_sweeps = 1
+
+    def with_params(self, **kw):
+        args = dict(dim=self.dim, topology=self.topology, capacity=self.capacity, max_neighbors=self.max_neighbors)
+        args.update(kw)
+        return ContainerModel(self.name, **args)
+
+    def step_params(self, final):
+        return None
+
+    @property
+    def grid_class(self):
+        from .containergrid import ContainerGrid
+        return ContainerGrid
+
+
 _F64 = [("temp", "f8")]
 _LBM = [(n, "f4") for n in ["C", "N", "E", "W", "S", "T", "B", "NW", "SW", "NE", "SE", "TW", "BW", "TE", "BE",
                             "TN", "BN", "TS", "BS", "density", "velocityX", "velocityY", "velocityZ"]] + [("state", "i4")]
@@ -154,5 +182,10 @@ LBMCellF = CellModel("LBMCellF", 3, "cube", _LBM, capi.KERNEL_LBM_D3Q19, edge={"
 NBodyF = NBodyModel("NBodyF", "f4")
 NBodyD = NBodyModel("NBodyD", "f8")
 
-ALL = {m.name: m for m in [NBodyF, NBodyD, Jacobi6Cube, Jacobi6Torus, Jacobi7Cube, Jacobi7Torus, Jacobi27Cube, Jacobi27Torus,
+Container2Cube = ContainerModel("Container2Cube", 2, "cube")
+Container2Torus = ContainerModel("Container2Torus", 2, "torus")
+Container3Cube = ContainerModel("Container3Cube", 3, "cube")
+Container3Torus = ContainerModel("Container3Torus", 3, "torus")
+
+ALL = {m.name: m for m in [NBodyF, NBodyD, Container2Cube, Container2Torus, Container3Cube, Container3Torus, Jacobi6Cube, Jacobi6Torus, Jacobi7Cube, Jacobi7Torus, Jacobi27Cube, Jacobi27Torus,
                            ConwayCube, ConwayTorus, LBMCellF]}

@@ -365,11 +365,13 @@ class B200Simulator:
     """MonolithicSimulator on one B200: same observable behaviour as SerialSimulator
     (parallelization/serialsimulator.h:48-187)."""
 
-    def __init__(self, initializer, model, device=0):
+    def __init__(self, initializer, model, device=0, engine=None):
         self.initializer, self.model = initializer, model
         self.NANO_STEPS = model.nano_steps
         dims = initializer.gridDimensions()
-        self.grid = model.grid_class(model, dims, device=device)
+        # engine: tests hand in a stand-in for the C ABI (tests/cpu_engine.py); the product always runs on capi
+        self.grid = model.grid_class(model, dims, device=device, **({"engine": engine} if engine is not None else {}))
+        self._sync = capi.sync if engine is None else getattr(engine, "sync", lambda: None)
         # SerialSimulator initialises both grids (serialsimulator.h:54-57); loads write both buffers
         initializer.grid(self.grid)
         self.stepNum = initializer.startStep()
@@ -387,7 +389,7 @@ class B200Simulator:
         return self.stepNum
 
     def getGrid(self):
-        capi.sync()
+        self._sync()
         return self.grid
 
     def gatherStatistics(self):
@@ -417,7 +419,7 @@ class B200Simulator:
             self._advance(n)
             self._afterStep()
         self._handleInput(STEERER_ALL_DONE, feedback)
-        capi.sync()
+        self._sync()
 
     # -- internals
     def _steps_to_next_event(self, maxSteps):

@@ -159,3 +159,96 @@ def nbody_cells(ncx, ncy, ncz, cap=32, edge=2.5, spacing=1.058, jitter=0.1, vel=
     parts[cell, slot, 0:3] = pos
     parts[cell, slot, 3:6] = v
     return counts.reshape(ncz, ncy, ncx), parts.reshape(ncz, ncy, ncx, cap, 6)
+
+
+def container_cells(nx, ny, nz=1, n_dims=3, torus=False, cap=16, maxnb=20, seed=77, edge=False, fill=0.75,
+                    min_neighbors=1, chunk=1 << 15):
+    """ContainerCell grids of ID-keyed mesh elements (oracle/models/container.h) in the interchange format of
+    include/b200geo.h: container c holds counts[c] elements (about `fill` of the capacity; some containers are empty)
+    with the ascending ids 1 + c * cap + slot, as the Voronoi example's initializer numbers them
+    (src/examples/voronoi/main.cpp:153-156); every element lists min_neighbors..maxnb neighbour ids, in random
+    order, drawn from its own container and the 3^n_dims - 1 around it (across the seam on a torus); with `edge` a
+    lookup beyond a Cube boundary names an element of the edge container. Returns (box, edge_box or None): dicts of
+    counts [nz][ny][nx], ids / values / influx / nb_counts [..][cap], nb_ids [..][cap][maxnb]."""
+    assert n_dims in (2, 3) and (n_dims == 3 or nz == 1)
+    ncont = nx * ny * nz
+    cidx = np.arange(ncont, dtype=np.uint64)
+
+    def h(x, salt):
+        return splitmix64(x ^ np.uint64((seed * 1000003 + salt) & 0xFFFFFFFFFFFF))
+
+    u = (h(cidx, 1) >> np.uint64(11)).astype(np.float64) / 9007199254740992.0
+    counts = np.minimum(cap, np.floor(u * (2 * fill * cap + 1))).astype(np.int32)
+    counts[(h(cidx, 2) % np.uint64(16)) == 0] = 0          # some empty containers
+    if ncont > 0 and counts.max() == 0:
+        counts[0] = 1
+    n_edge = max(1, cap // 2) if edge else 0
+    slot = np.arange(cap, dtype=np.int64)
+    ids = (1 + np.arange(ncont, dtype=np.int64)[:, None] * cap + slot[None, :]).astype(np.int32)
+    gslot = np.arange(ncont * cap, dtype=np.uint64).reshape(ncont, cap)
+    values = (h(gslot, 3) >> np.uint64(11)).astype(np.float64) / 9007199254740992.0
+    influx = np.where(h(gslot, 4) % np.uint64(8) == 0, (h(gslot, 5) >> np.uint64(11)).astype(np.float64) / 9007199254740992.0 * 0.125, 0.0)
+    nb_counts = (min_neighbors + h(gslot, 6) % np.uint64(maxnb - min_neighbors + 1)).astype(np.int32)
+    live = slot[None, :] < counts[:, None]
+    ids[~live] = 0
+    values[~live] = 0
+    influx[~live] = 0
+    nb_counts[~live] = 0
+    nb_ids = np.zeros((ncont, cap, maxnb), dtype=np.int32)
+    dims = np.array([nx, ny, nz], dtype=np.int64)
+    for c0 in range(0, ncont, chunk):
+        c1 = min(ncont, c0 + chunk)
+        c = np.arange(c0, c1, dtype=np.int64)
+        key = (np.arange(c0 * cap * maxnb, c1 * cap * maxnb, dtype=np.uint64)).reshape(c1 - c0, cap, maxnb)
+        r = h(key, 7)
+        coord = np.stack([c % nx, (c // nx) % ny, c // (nx * ny)], axis=-1)          # [n][3]
+        d = np.stack([(r % np.uint64(3)).astype(np.int64) - 1, ((r >> np.uint64(8)) % np.uint64(3)).astype(np.int64) - 1,
+                      ((r >> np.uint64(16)) % np.uint64(3)).astype(np.int64) - 1], axis=-1)   # [n][cap][maxnb][3]
+        if n_dims == 2:
+            d[..., 2] = 0
+        p = coord[:, None, None, :] + d
+        outside = ((p < 0) | (p >= dims)).any(axis=-1)
+        if torus:
+            p = (p + dims) % dims
+            outside[...] = False
+        else:
+            p = np.clip(p, 0, dims - 1)
+        t = (p[..., 2] * ny + p[..., 1]) * nx + p[..., 0]
+        own = np.broadcast_to(c[:, None, None], t.shape)
+        use_edge = outside & bool(edge)
+        # lookups that left a Cube grid without an edge container, or that hit an empty container, fall back on the own one
+        t = np.where(outside & ~use_edge, own, t)
+        t = np.where(counts[t] == 0, own, t)
+        pick = (r >> np.uint64(24)).astype(np.int64)
+        target = 1 + t * cap + pick % np.maximum(counts[t], 1)
+        if edge:
+            target = np.where(use_edge, 1 + ncont * cap + pick % n_edge, target)
+        j = np.arange(maxnb)[None, None, :]
+        target = np.where(j < nb_counts[c0:c1, :, None], target, 0)
+        nb_ids[c0:c1] = target.astype(np.int32)
+    shape = (nz, ny, nx) if n_dims == 3 else (ny, nx)
+    box = {"counts": counts.reshape(shape), "ids": ids.reshape(shape + (cap,)), "values": values.reshape(shape + (cap,)),
+           "influx": influx.reshape(shape + (cap,)), "nb_counts": nb_counts.reshape(shape + (cap,)),
+           "nb_ids": nb_ids.reshape(shape + (cap, maxnb))}
+    edge_box = None
+    if edge:
+        es = np.arange(cap, dtype=np.uint64)
+        edge_box = {"counts": np.array([n_edge], dtype=np.int32),
+                    "ids": np.where(np.arange(cap) < n_edge, 1 + ncont * cap + np.arange(cap), 0).astype(np.int32),
+                    "values": np.where(np.arange(cap) < n_edge, 2.0 + (h(es, 8) >> np.uint64(11)).astype(np.float64) / 9007199254740992.0, 0.0),
+                    "influx": np.zeros(cap, dtype=np.float64), "nb_counts": np.zeros(cap, dtype=np.int32),
+                    "nb_ids": np.zeros((cap, maxnb), dtype=np.int32)}
+    return box, edge_box
+
+
+def container_duplicate_ids(box):
+    """Renumbers the elements of a container_cells() grid IN PLACE so that the same id occurs in several containers
+    (id -> 1 + (id - 1) % (7 * cap)): which element hood[id] returns then depends on the search order of
+    NeighborhoodAdapter::operator[] (own container first, then CoordBox order; storage/neighborhoodadapter.h:45-65).
+    Ids stay ascending inside a container."""
+    cap = box["ids"].shape[-1]
+    m = 7 * cap
+    for name in ("ids", "nb_ids"):
+        a = box[name]
+        a[a > 0] = 1 + (a[a > 0] - 1) % m
+    return box

@@ -479,3 +479,107 @@ int oracle_nbody(int real_bytes, int nx, int ny, int nz, int cap, int steps, dou
     const int origin[3] = {0, 0, 0};
     return oracle_nbody_at(real_bytes, nx, ny, nz, cap, steps, dt, cutoff, edge, origin, counts_in, parts_in, counts_out, parts_out);
 }
+
+/* ---- ContainerCell: ID-keyed mesh elements ------------------------------------------------------ */
+
+/* ContainerCell::operator[](id), storage/containercell.h:107-121: upper_bound over the ascending ids, then the
+ * element before it */
+static int container_find(const int32_t *ids, int n, int32_t id)
+{
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        int mid = lo + (hi - lo) / 2;
+        if (id < ids[mid]) hi = mid;
+        else lo = mid + 1;
+    }
+    if (lo == 0) return -1;
+    return ids[lo - 1] == id ? lo - 1 : -1;
+}
+
+int oracle_container(int n_dims, int torus, int nx, int ny, int nz, int cap, int maxnb, int steps,
+                     const int32_t *counts, const int32_t *ids, const double *values, const double *influx,
+                     const int32_t *nb_counts, const int32_t *nb_ids,
+                     const int32_t *edge_count, const int32_t *edge_ids, const double *edge_values,
+                     double *values_out, int32_t *missing_id)
+{
+    if ((n_dims != 2 && n_dims != 3) || (n_dims == 2 && nz != 1) || nx < 1 || ny < 1 || nz < 1 || cap < 1 || maxnb < 1) return -1;
+    size_t cells = (size_t)nx * ny * nz;
+    double *cur = (double *)malloc(cells * cap * sizeof(double));
+    double *next = (double *)malloc(cells * cap * sizeof(double));
+    if (!cur || !next) {
+        free(cur);
+        free(next);
+        return -1;
+    }
+    memcpy(cur, values, cells * cap * sizeof(double));
+    int n_edge = edge_count ? edge_count[0] : 0;
+    int rc = 0;
+    int zlo = n_dims == 3 ? -1 : 0, zhi = n_dims == 3 ? 1 : 0;
+    for (int t = 0; t < steps && rc == 0; ++t) {
+        /* copyOver: *this = oldSelf (containercell.h:185-188); elements keep everything but the temperature */
+        memcpy(next, cur, cells * cap * sizeof(double));
+        for (int z = 0; z < nz && rc == 0; ++z) {
+            for (int y = 0; y < ny && rc == 0; ++y) {
+                for (int x = 0; x < nx && rc == 0; ++x) {
+                    size_t c = ((size_t)z * ny + y) * nx + x;
+                    /* updateCargo (containercell.h:195-200) */
+                    for (int s = 0; s < counts[c] && rc == 0; ++s) {
+                        size_t slot = c * cap + s;
+                        double temperature = 0;
+                        for (int j = 0; j < nb_counts[slot]; ++j) {
+                            int32_t id = nb_ids[slot * maxnb + j];
+                            /* NeighborhoodAdapter::operator[] (neighborhoodadapter.h:45-65): own container first */
+                            const double *hit = 0;
+                            int pos = container_find(ids + c * cap, counts[c], id);
+                            if (pos >= 0) hit = cur + c * cap + pos;
+                            for (int dz = zlo; dz <= zhi && !hit; ++dz) {
+                                for (int dy = -1; dy <= 1 && !hit; ++dy) {
+                                    for (int dx = -1; dx <= 1 && !hit; ++dx) {
+                                        if (!dx && !dy && !dz) continue;
+                                        int p[3] = {x + dx, y + dy, z + dz};
+                                        int d[3] = {nx, ny, nz};
+                                        int outside = 0;
+                                        for (int a = 0; a < 3; ++a) {
+                                            if (p[a] < 0 || p[a] >= d[a]) {
+                                                if (torus) p[a] = (p[a] + d[a]) % d[a];
+                                                else outside = 1;
+                                            }
+                                        }
+                                        if (outside) {
+                                            /* Cube: every coordinate outside is the edge cell (geometry/topologies.h:185-199) */
+                                            pos = container_find(edge_ids, n_edge, id);
+                                            if (pos >= 0) hit = edge_values + pos;
+                                        } else {
+                                            size_t o = ((size_t)p[2] * ny + p[1]) * nx + p[0];
+                                            pos = container_find(ids + o * cap, counts[o], id);
+                                            if (pos >= 0) hit = cur + o * cap + pos;
+                                        }
+                                    }
+                                }
+                            }
+                            if (!hit) {
+                                if (missing_id) *missing_id = id;
+                                rc = -2;
+                                break;
+                            }
+                            temperature += *hit;
+                        }
+                        if (rc) break;
+                        /* src/examples/voronoi/main.cpp:53: the size_t divisor converts to double */
+                        next[slot] = influx[slot] + temperature / (double)(size_t)nb_counts[slot];
+                    }
+                }
+            }
+        }
+        double *tmp = cur;
+        cur = next;
+        next = tmp;
+    }
+    if (rc == 0) {
+        for (size_t c = 0; c < cells; ++c)
+            for (int s = 0; s < cap; ++s) values_out[c * cap + s] = s < counts[c] ? cur[c * cap + s] : 0.0;
+    }
+    free(cur);
+    free(next);
+    return rc;
+}

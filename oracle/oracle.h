@@ -55,6 +55,19 @@ int oracle_nbody(int real_bytes, int nx, int ny, int nz, int cap, int steps, dou
 int oracle_nbody_at(int real_bytes, int nx, int ny, int nz, int cap, int steps, double dt, double cutoff, double edge,
                     const int origin[3], const int32_t *counts_in, const void *parts_in, int32_t *counts_out, void *parts_out);
 
+/* ID-keyed mesh elements in ContainerCell<MeshElement, cap> containers (oracle/models/container.h;
+ * storage/containercell.h:170-200, storage/neighborhoodadapter.h:45-65) on a Cube (torus = 0) or Torus grid of
+ * nx*ny*nz containers, n_dims 2 (nz = 1) or 3. Arrays in the interchange format of include/b200geo.h (counts, ids,
+ * values, influx, nb_counts, nb_ids [cells][cap][maxnb]); edge_*: the same six arrays for the ONE edge container, or
+ * NULL for an empty one. values_out: double [cells][cap], zero for unused slots. Returns -2 and the ID in
+ * *missing_id when an element lists an ID that none of the 3^n_dims containers around it holds (std::logic_error
+ * "id not found" in the reference), -1 for bad arguments. */
+int oracle_container(int n_dims, int torus, int nx, int ny, int nz, int cap, int maxnb, int steps,
+                     const int32_t *counts, const int32_t *ids, const double *values, const double *influx,
+                     const int32_t *nb_counts, const int32_t *nb_ids,
+                     const int32_t *edge_count, const int32_t *edge_ids, const double *edge_values,
+                     double *values_out, int32_t *missing_id);
+
 #ifdef __cplusplus
 }
 #endif

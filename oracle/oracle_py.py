@@ -116,6 +116,78 @@ def run_ref_nbody(counts, parts, steps, dt=0.005, cutoff=2.5, edge=2.5, omp=Fals
     return out, stats
 
 
+CONTAINER_FIELDS = ("counts", "ids", "values", "influx", "nb_counts", "nb_ids")
+_CONTAINER_TYPES = (np.int32, np.int32, np.float64, np.float64, np.int32, np.int32)
+
+
+def _container_arrays(box):
+    return [np.ascontiguousarray(box[n], dtype=t) for n, t in zip(CONTAINER_FIELDS, _CONTAINER_TYPES)]
+
+
+def container(box, steps, n_dims=3, torus=False, edge=None):
+    """box: dict of the six arrays of a whole grid (include/b200geo.h; counts [nz][ny][nx] or [ny][nx]); edge: the
+    same for the one edge container or None. Returns the temperatures [..][cap] after `steps`. Raises KeyError(id)
+    for an id that is not in the neighbourhood (std::logic_error "id not found" in the reference)."""
+    a = _container_arrays(box)
+    shape = a[0].shape
+    assert len(shape) == n_dims
+    nz, ny, nx = (shape if n_dims == 3 else (1,) + shape)
+    cap, maxnb = a[5].shape[-2], a[5].shape[-1]
+    out = np.empty_like(a[2])
+    missing = ctypes.c_int32(0)
+    e = _container_arrays(edge) if edge is not None else None
+    f = lib().oracle_container
+    f.argtypes = [ctypes.c_int] * 8 + [ctypes.c_void_p] * 10 + [ctypes.POINTER(ctypes.c_int32)]
+    rc = f(n_dims, int(torus), nx, ny, nz, cap, maxnb, steps, *[_p(v) for v in a],
+           _p(e[0]) if e else None, _p(e[1]) if e else None, _p(e[2]) if e else None, _p(out), ctypes.byref(missing))
+    if rc == -2:
+        raise KeyError(int(missing.value))
+    assert rc == 0, rc
+    return out
+
+
+def run_ref_container(box, steps, n_dims=3, torus=False, edge=None, omp=False, threads=None, want_output=True):
+    """The reference's own SerialSimulator / OpenMPSimulator over ContainerCell<MeshElement, 16> containers with
+    FixedArray<int, 20> neighbour lists (oracle/_ref/lgd_ref_container). Returns (dict of the six arrays or None, stats)."""
+    a = _container_arrays(box)
+    shape = a[0].shape
+    nz, ny, nx = (shape if n_dims == 3 else (1,) + shape)
+    assert a[5].shape[-2:] == (16, 20), "the reference binary is built for capacity 16 and 20 neighbour ids"
+    env = dict(os.environ)
+    if omp:
+        env["OMP_PROC_BIND"] = "true"
+        env["OMP_PLACES"] = "cores"
+        if threads:
+            env["OMP_NUM_THREADS"] = str(threads)
+    with tempfile.TemporaryDirectory() as tmp:
+        fin, fout = os.path.join(tmp, "in.raw"), os.path.join(tmp, "out.raw")
+        with open(fin, "wb") as f:
+            for v in a:
+                f.write(v.tobytes())
+            if edge is not None:
+                for v in _container_arrays(edge):
+                    f.write(v.tobytes())
+        cmd = [ref_binary("container"), "container", str(nx), str(ny), str(nz), str(steps), fin, fout if want_output else "-",
+               "--dims", str(n_dims)]
+        cmd += ["--torus"] if torus else []
+        cmd += ["--edge"] if edge is not None else []
+        cmd += ["--omp"] if omp else []
+        res = subprocess.run(cmd, env=env, capture_output=True, text=True)
+        if res.returncode == 4 and "id not found" in res.stderr:
+            raise KeyError(res.stderr.strip())
+        if res.returncode != 0:
+            raise RuntimeError(res.stderr[-2000:])
+        stats = json.loads(res.stdout.strip().splitlines()[-1])
+        out = None
+        if want_output:
+            raw = np.fromfile(fout, dtype=np.uint8)
+            out, pos = {}, 0
+            for n, v in zip(CONTAINER_FIELDS, a):
+                out[n] = raw[pos:pos + v.nbytes].view(v.dtype).reshape(v.shape)
+                pos += v.nbytes
+    return out, stats
+
+
 def _region(fn, grid_raw, dims, member_bytes, streaks, buf):
     nx, ny, nz = dims
     mb = np.asarray(member_bytes, dtype=np.int32)

@@ -18,6 +18,9 @@
 #if defined(B200_MODEL_NBODY)
 #include "models/nbody.h"
 #endif
+#if defined(B200_MODEL_CONTAINER)
+#include "models/container.h"
+#endif
 
 #if defined(B200_MODEL_JACOBI6CUBE)
 typedef b200models::Jacobi6Cube Model;
@@ -39,6 +42,8 @@ typedef b200models::ConwayTorus Model;
 typedef b200models::LBMCellF Model;
 #elif defined(B200_MODEL_NBODY)
 typedef b200models::NBodyCell Model;
+#elif defined(B200_MODEL_CONTAINER)
+typedef LibGeoDecomp::ContainerCell<b200models::MeshElement<3, false>, b200models::CONTAINER_CAPACITY> Model;
 #else
 #error "select a model with -DB200_MODEL_<NAME>"
 #endif
@@ -96,6 +101,8 @@ template<> struct Codec<Model> {
 
 #if defined(B200_MODEL_NBODY)
 int main(int argc, char **argv) { return b200models::nbodyMain(argc, argv); }
+#elif defined(B200_MODEL_CONTAINER)
+int main(int argc, char **argv) { return b200models::containerMain(argc, argv); }
 #else
 int main(int argc, char **argv)
 {

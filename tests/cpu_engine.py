@@ -255,3 +255,95 @@ class DeviceBoxGrid:
 
 def sync(stream=None):
     pass
+
+
+class DeviceContainerGrid:
+    """capi.DeviceContainerGrid on host arrays: the slot store in the interchange format, the sweep is the oracle's
+    (ContainerCell grids of ID-keyed mesh elements)."""
+    FIELDS = capi.ContainerBox.FIELDS
+    _TYPES = (np.int32, np.int32, np.float64, np.float64, np.int32, np.int32)
+
+    def __init__(self, dim, capacity, max_neighbors, n_dims=3, ghost_mode=None, device=0):
+        if n_dims not in (2, 3) or (n_dims == 2 and dim[2] != 1):
+            raise ValueError("n_dims must be 2 or 3")
+        self.dim, self.capacity, self.max_neighbors, self.n_dims = tuple(dim), int(capacity), int(max_neighbors), n_dims
+        self.torus = bool(ghost_mode is not None and ghost_mode[0][0] == capi.GHOST_WRAP)
+        nx, ny, nz = self.dim
+        self.store = self._empty((nz, ny, nx))
+        self.edge = self._empty((1, 1, 1))
+        self.sweeps, self.resolutions, self.dirty = 0, 0, True
+
+    def _empty(self, shape):
+        per = [(), (self.capacity,), (self.capacity,), (self.capacity,), (self.capacity,), (self.capacity, self.max_neighbors)]
+        return {n: np.zeros(shape + p, dtype=t) for n, t, p in zip(self.FIELDS, self._TYPES, per)}
+
+    @staticmethod
+    def _get(arrays, name):
+        return arrays.get(name) if isinstance(arrays, dict) else arrays[DeviceContainerGrid.FIELDS.index(name)]
+
+    def load(self, arrays, origin=(0, 0, 0), dim=None, location=0, stream=None):
+        dim = self.dim if dim is None else dim
+        (ox, oy, oz), (dx, dy, dz) = origin, dim
+        for n in self.FIELDS:
+            a = self._get(arrays, n)
+            if a is None:
+                raise ValueError("a load needs every array of the box")
+            tgt = self.store[n][oz:oz + dz, oy:oy + dy, ox:ox + dx]
+            tgt[...] = np.asarray(a).reshape(tgt.shape)
+        self.dirty = True
+
+    def save(self, arrays, origin=(0, 0, 0), dim=None, location=0, stream=None):
+        dim = self.dim if dim is None else dim
+        (ox, oy, oz), (dx, dy, dz) = origin, dim
+        counts = self.store["counts"][oz:oz + dz, oy:oy + dy, ox:ox + dx]
+        live = np.arange(self.capacity) < counts[..., None]
+        for n in self.FIELDS:
+            a = self._get(arrays, n)
+            if a is None:
+                continue
+            src = self.store[n][oz:oz + dz, oy:oy + dy, ox:ox + dx]
+            if n != "counts":
+                src = np.where(live if src.ndim == 4 else live[..., None], src, 0)
+            a.reshape(src.shape)[...] = src
+
+    def set_edge(self, arrays):
+        for n in self.FIELDS:
+            self.edge[n].reshape(-1)[...] = np.asarray(self._get(arrays, n)).reshape(-1)
+        self.dirty = True
+
+    def get_edge(self, arrays):
+        for n in self.FIELDS:
+            a = self._get(arrays, n)
+            if a is not None:
+                a.reshape(-1)[...] = self.edge[n].reshape(-1)
+
+    def step(self, kernel, n_steps=1, first_nano_step=0, params=None, stream=None):
+        if kernel != capi.KERNEL_CONTAINER:
+            raise capi.LogicError("a ContainerCell grid steps with KERNEL_CONTAINER")
+        if n_steps == 0:
+            return
+        c = self.store["counts"]
+        if c.max(initial=0) > self.capacity or self.edge["counts"].max() > self.capacity:
+            raise IndexError("ContainerCell capacity exeeded")
+        ids = self.store["ids"]
+        live = np.arange(self.capacity) < c[..., None]
+        if ((np.diff(ids, axis=-1) <= 0) & live[..., 1:]).any():
+            raise ValueError("the ids of a container must ascend")
+        box = {n: (v if self.n_dims == 3 else v[0]) for n, v in self.store.items()}
+        edge = {n: v.reshape(v.shape[3:]) if n != "counts" else v.reshape(1) for n, v in self.edge.items()}
+        try:
+            out = oracle_py.container(box, n_steps, n_dims=self.n_dims, torus=self.torus, edge=edge)
+        except KeyError as e:
+            raise capi.LogicError("id not found: could not find id %s in neighborhood" % e.args[0])
+        self.store["values"][...] = out.reshape(self.store["values"].shape)
+        self.resolutions += self.dirty
+        self.dirty = False
+        self.sweeps += n_steps
+
+    def stats_enable(self, on=True):
+        pass
+
+    def stats(self):
+        live = np.arange(self.capacity) < self.store["counts"][..., None]
+        return {"cargo": int(self.store["counts"].sum()), "links": int(self.store["nb_counts"][live].sum()), "resolutions": self.resolutions,
+                "sweeps": self.sweeps}

@@ -58,6 +58,26 @@ def main():
         cases[key + "_in_counts"], cases[key + "_in_parts"] = c, p
         cases[key + "_out_counts"], cases[key + "_out_parts"] = co, po
     np.savez_compressed(os.path.join(HERE, "nbody.npz"), **cases)
+    # ContainerCell grids of ID-keyed mesh elements (oracle/models/container.h): capacity 16, 20 neighbour ids.
+    # The last two cases hold the SAME id in several containers (first hit in the adapter's search order wins).
+    cases = {}
+    for key, (dims, nd, torus, edge, steps, dup) in {
+            "container_3cube_6x5x4_s9": ((6, 5, 4), 3, False, False, 9, False), "container_3torus_6x5x4_s9": ((6, 5, 4), 3, True, False, 9, False),
+            "container_3cube_edge_5x4x3_s6": ((5, 4, 3), 3, False, True, 6, False), "container_2cube_edge_9x7_s12": ((9, 7, 1), 2, False, True, 12, False),
+            "container_2torus_9x7_s12": ((9, 7, 1), 2, True, False, 12, False), "container_3torus_2x1x3_s5": ((2, 1, 3), 3, True, False, 5, False),
+            "container_3cube_dup_4x4x3_s4": ((4, 4, 3), 3, False, True, 4, True), "container_2torus_dup_5x5_s4": ((5, 5, 1), 2, True, False, 4, True)}.items():
+        box, eb = synth.container_cells(*dims, n_dims=nd, torus=torus, edge=edge, seed=500 + len(cases))
+        if dup:
+            synth.container_duplicate_ids(box)
+            if eb is not None:
+                synth.container_duplicate_ids(eb)
+        out, _ = oracle_py.run_ref_container(box, steps, n_dims=nd, torus=torus, edge=eb)
+        for n in oracle_py.CONTAINER_FIELDS:
+            cases[key + "_in_" + n] = box[n]
+            if eb is not None:
+                cases[key + "_edge_" + n] = eb[n]
+        cases[key + "_out_values"] = out["values"]
+    np.savez_compressed(os.path.join(HERE, "container.npz"), **cases)
     print("golden fixtures written to", HERE)
 
 
