@@ -220,6 +220,7 @@ inline std::vector<StreakBox> mergeStreaks(ITERATOR begin, const ITERATOR& end, 
 #endif
 
 #include "b200boxgrid.h"
+#include "b200containergrid.h"
 
 namespace LibGeoDecomp {
 
@@ -235,6 +236,12 @@ struct B200GridSelector {
 template<typename PARTICLE, int N>
 struct B200GridSelector<BoxCell<FixedArray<PARTICLE, N> > > {
     typedef B200BoxGrid<PARTICLE, N> Type;
+};
+
+/* ... or the ID-keyed container grid for ContainerCell<CARGO, SIZE> (the default int keys) */
+template<typename CARGO, std::size_t SIZE>
+struct B200GridSelector<ContainerCell<CARGO, SIZE, int> > {
+    typedef B200ContainerGrid<CARGO, SIZE> Type;
 };
 
 template<typename CELL>

@@ -201,7 +201,7 @@ int containerRun(int nx, int ny, int nz, unsigned steps, const char *in, const c
     }
     printf("{\"model\": \"container\", \"simulator\": \"%s\", \"threads\": %d, \"dims\": [%d, %d, %d], \"n_dims\": %d, \"torus\": %d, "
            "\"steps\": %u, \"elements\": %zu, \"links\": %zu, \"time_compute_s\": %.6f, \"wall_run_s\": %.6f, \"geups_compute\": %.6f}\n",
-           simName, threads, nx, ny, nz, DIM, (int)TORUS, steps, elements, links, compute, wall, 1e-9 * steps * elements / compute);
+           simName, threads, nx, ny, nz, DIM, (int)TORUS, steps, elements, links, compute, wall, compute > 0 ? 1e-9 * steps * elements / compute : 0.0);
     return 0;
 }
 

@@ -725,3 +725,165 @@ int b200geo_boxgroup_sync(b200geo_boxgroup *) { return B200GEO_OK; }
 int b200geo_boxgroup_stats(const b200geo_boxgroup *grp, uint64_t out[2]) { out[0] = grp->exchanges; out[1] = grp->bytes; return B200GEO_OK; }
 
 }
+
+/* ---- ContainerCell grids (ID-keyed cargo) ------------------------------------------------------------------- */
+struct b200geo_containergrid {
+    b200geo_containergrid_desc desc;
+    int d[3], cap, maxnb;
+    size_t cells;                       // interior containers; record `cells` is the edge container
+    std::vector<int32_t> counts, ids, nbc, nbids;
+    std::vector<double> values, influx;
+    bool dirty;
+    uint64_t rebuilds, sweeps, links;
+};
+
+template<typename T>
+static void container_array(std::vector<T>& store, T *user, const std::vector<int32_t>& counts, int per, int per_slot, size_t first,
+                            const int32_t o[3], const int32_t d[3], const int gd[3], bool edge, bool load)
+{
+    if (!user) return;
+    size_t b = 0;
+    for (int z = 0; z < d[2]; ++z) {
+        for (int y = 0; y < d[1]; ++y) {
+            for (int x = 0; x < d[0]; ++x, ++b) {
+                size_t c = edge ? first : ((size_t)(z + o[2]) * gd[1] + (y + o[1])) * gd[0] + (x + o[0]);
+                for (int e = 0; e < per; ++e) {
+                    if (load) store[c * per + e] = user[b * per + e];
+                    else user[b * per + e] = (per_slot > 0 && e / per_slot >= counts[c]) ? T(0) : store[c * per + e];
+                }
+            }
+        }
+    }
+}
+
+extern "C" {
+
+int b200geo_containergrid_create(const b200geo_containergrid_desc *desc, int, b200geo_containergrid **out)
+{
+    if (!desc || !out) return fail(B200GEO_ERR_INVALID, "null argument");
+    if ((desc->n_dims != 2 && desc->n_dims != 3) || (desc->n_dims == 2 && desc->dim[2] != 1))
+        return fail(B200GEO_ERR_INVALID, "n_dims must be 2 or 3");
+    if (desc->capacity < 1 || desc->capacity > 4096 || desc->max_neighbors < 1 || desc->max_neighbors > 64)
+        return fail(B200GEO_ERR_INVALID, "bad capacity / max_neighbors");
+    for (int i = 0; i < 3; ++i) {
+        if (desc->dim[i] < 1) return fail(B200GEO_ERR_INVALID, "grid dimension must be >= 1");
+        if (desc->ghost_mode[i][0] != desc->ghost_mode[i][1] || desc->ghost_mode[i][0] == B200GEO_GHOST_PEER)
+            return fail(B200GEO_ERR_INVALID, "ghost mode must be EDGE or WRAP, alike on both sides of an axis");
+    }
+    b200geo_containergrid *g = new b200geo_containergrid();
+    g->desc = *desc;
+    for (int i = 0; i < 3; ++i) g->d[i] = desc->dim[i];
+    g->cap = desc->capacity;
+    g->maxnb = desc->max_neighbors;
+    g->cells = (size_t)g->d[0] * g->d[1] * g->d[2];
+    size_t slots = (g->cells + 1) * g->cap;
+    g->counts.assign(g->cells + 1, 0);
+    g->ids.assign(slots, 0);
+    g->nbc.assign(slots, 0);
+    g->nbids.assign(slots * g->maxnb, 0);
+    g->values.assign(slots, 0);
+    g->influx.assign(slots, 0);
+    g->dirty = true;
+    g->rebuilds = g->sweeps = g->links = 0;
+    *out = g;
+    return B200GEO_OK;
+}
+
+int b200geo_containergrid_destroy(b200geo_containergrid *g) { delete g; return B200GEO_OK; }
+
+static int container_io(b200geo_containergrid *g, const int32_t o[3], const int32_t d[3], const b200geo_container_box *box, bool edge, bool load)
+{
+    container_array<int32_t>(g->counts, box->counts, g->counts, 1, 0, g->cells, o, d, g->d, edge, load);
+    container_array<int32_t>(g->ids, box->ids, g->counts, g->cap, 1, g->cells, o, d, g->d, edge, load);
+    container_array<double>(g->values, box->values, g->counts, g->cap, 1, g->cells, o, d, g->d, edge, load);
+    container_array<double>(g->influx, box->influx, g->counts, g->cap, 1, g->cells, o, d, g->d, edge, load);
+    container_array<int32_t>(g->nbc, box->nb_counts, g->counts, g->cap, 1, g->cells, o, d, g->d, edge, load);
+    container_array<int32_t>(g->nbids, box->nb_ids, g->counts, g->cap * g->maxnb, g->maxnb, g->cells, o, d, g->d, edge, load);
+    if (load) g->dirty = true;
+    return B200GEO_OK;
+}
+
+static bool container_box_ok(const b200geo_containergrid *g, const int32_t o[3], const int32_t d[3])
+{
+    for (int i = 0; i < 3; ++i)
+        if (o[i] < 0 || d[i] < 1 || o[i] + d[i] > g->d[i]) return false;
+    return true;
+}
+
+static bool container_box_complete(const b200geo_container_box *b)
+{
+    return b && b->counts && b->ids && b->values && b->influx && b->nb_counts && b->nb_ids;
+}
+
+int b200geo_containergrid_load(b200geo_containergrid *g, const int32_t o[3], const int32_t d[3], const b200geo_container_box *box, int, void *)
+{
+    if (!g || !o || !d) return fail(B200GEO_ERR_INVALID, "null argument");
+    if (!container_box_complete(box)) return fail(B200GEO_ERR_INVALID, "a load needs every array of the box");
+    if (!container_box_ok(g, o, d)) return fail(B200GEO_ERR_INVALID, "box outside the grid");
+    return container_io(g, o, d, box, false, true);
+}
+
+int b200geo_containergrid_save(const b200geo_containergrid *g, const int32_t o[3], const int32_t d[3], const b200geo_container_box *box, int, void *)
+{
+    if (!g || !o || !d || !box) return fail(B200GEO_ERR_INVALID, "null argument");
+    if (!container_box_ok(g, o, d)) return fail(B200GEO_ERR_INVALID, "box outside the grid");
+    return container_io(const_cast<b200geo_containergrid *>(g), o, d, box, false, false);
+}
+
+int b200geo_containergrid_set_edge(b200geo_containergrid *g, const b200geo_container_box *cell)
+{
+    if (!g || !container_box_complete(cell)) return fail(B200GEO_ERR_INVALID, "the edge container needs every array");
+    if (cell->counts[0] < 0 || cell->counts[0] > g->cap) return fail(B200GEO_ERR_OUT_OF_RANGE, "ContainerCell capacity exeeded");
+    const int32_t o[3] = {0, 0, 0}, d[3] = {1, 1, 1};
+    return container_io(g, o, d, cell, true, true);
+}
+
+int b200geo_containergrid_get_edge(const b200geo_containergrid *g, const b200geo_container_box *cell)
+{
+    if (!g || !cell) return fail(B200GEO_ERR_INVALID, "null argument");
+    const int32_t o[3] = {0, 0, 0}, d[3] = {1, 1, 1};
+    return container_io(const_cast<b200geo_containergrid *>(g), o, d, cell, true, false);
+}
+
+int b200geo_containergrid_step(b200geo_containergrid *g, uint32_t, uint32_t n_steps, void *)
+{
+    if (!g) return fail(B200GEO_ERR_INVALID, "null argument");
+    if (n_steps == 0) return B200GEO_OK;
+    uint64_t links = 0;
+    for (size_t c = 0; c <= g->cells; ++c) {
+        if (g->counts[c] < 0 || g->counts[c] > g->cap) return fail(B200GEO_ERR_OUT_OF_RANGE, "ContainerCell capacity exeeded");
+        for (int s = 0; s < g->counts[c]; ++s) {
+            if (s > 0 && g->ids[c * g->cap + s - 1] >= g->ids[c * g->cap + s])
+                return fail(B200GEO_ERR_INVALID, "the ids of a container must ascend (ContainerCell::insert keeps them sorted)");
+            if (c < g->cells) links += g->nbc[c * g->cap + s];
+        }
+    }
+    size_t e = g->cells * g->cap;
+    std::vector<double> out(e);
+    int32_t missing = 0;
+    int rc = oracle_container(g->desc.n_dims, g->desc.ghost_mode[0][0] == B200GEO_GHOST_WRAP, g->d[0], g->d[1], g->d[2], g->cap, g->maxnb,
+                              (int)n_steps, g->counts.data(), g->ids.data(), g->values.data(), g->influx.data(), g->nbc.data(),
+                              g->nbids.data(), &g->counts[g->cells], &g->ids[e], &g->values[e], out.data(), &missing);
+    if (rc == -2) return fail(B200GEO_ERR_LOGIC, "id not found: could not find id " + std::to_string(missing) + " in neighborhood");
+    if (rc) return fail(B200GEO_ERR_INVALID, "oracle_container failed");
+    memcpy(g->values.data(), out.data(), e * sizeof(double));
+    g->rebuilds += g->dirty;
+    g->dirty = false;
+    g->links = links;
+    g->sweeps += n_steps;
+    return B200GEO_OK;
+}
+
+int b200geo_containergrid_stats(const b200geo_containergrid *g, uint64_t out[4])
+{
+    if (!g || !out) return fail(B200GEO_ERR_INVALID, "null argument");
+    uint64_t cargo = 0;
+    for (size_t c = 0; c < g->cells; ++c) cargo += g->counts[c];
+    out[0] = cargo;
+    out[1] = g->links;
+    out[2] = g->rebuilds;
+    out[3] = g->sweeps;
+    return B200GEO_OK;
+}
+
+}

@@ -158,7 +158,23 @@ def test_checkpoints_in_the_mpiio_layout_from_the_device():
     assert "all checks passed" in res.stdout and "DIFFERENT" not in res.stdout
 
 
+CONTAINER_BIN = os.path.join(HERE, "facade", "_bin", "container_test")
+
+
+@pytest.mark.gpu
+def test_cpp_container_cell_drop_in():
+    """tests/facade/container_test.cpp: ContainerCell<MeshElement, 16> grids (ID-keyed cargo, the cell of the reference's
+    Voronoi example) through SerialSimulator and B200Simulator side by side, 2-D / 3-D, Cube / Torus, edge container:
+    temperatures bit-identical; B200ContainerGrid set / get / steering writes; std::logic_error for an unknown id."""
+    if not os.access(CONTAINER_BIN, os.X_OK):
+        pytest.skip("tests/facade/_bin/container_test not built (needs /root/reference at build time)")
+    res = subprocess.run([CONTAINER_BIN], capture_output=True, text=True, timeout=600)
+    print(res.stdout[-4000:], res.stderr[-2000:])
+    assert res.returncode == 0, res.stdout[-4000:] + res.stderr[-2000:]
+    assert "all checks passed" in res.stdout and "DIFFERENT" not in res.stdout
+
+
 def test_facade_header_has_no_oracle_dependency():
-    for name in ("b200simulator.h", "b200generic.h", "b200genericsoa.h", "b200boxgrid.h", "b200stripingsimulator.h", "b200stepper.h", "b200checkpoint.h"):
+    for name in ("b200containergrid.h", "b200simulator.h", "b200generic.h", "b200genericsoa.h", "b200boxgrid.h", "b200stripingsimulator.h", "b200stepper.h", "b200checkpoint.h"):
         text = open(os.path.join(HERE, "..", "include", "libgeodecomp_b200", name)).read()
         assert "oracle" not in text
