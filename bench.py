@@ -929,6 +929,119 @@ def bench_nbody(args, rank, world, dist, torch, containers=108, with_e2e=True):
     return out
 
 
+def replicate_mesh(torch, box, tile, reps, dev):
+    """A `tile`^2 torus mesh of synth.container_cells() replicated reps x reps times into one (tile * reps)^2 torus,
+    built with torch on `dev`: element ids follow the global container index (1 + container * cap + slot), neighbour
+    references keep their offset to the neighbour container and their slot. Returns (dict of the six arrays, the
+    function that replicates a per-tile array)."""
+    cap, maxnb = box["nb_ids"].shape[-2:]
+    n = tile * reps
+    t = {k: torch.from_numpy(np.ascontiguousarray(v)).to(dev) for k, v in box.items()}
+    # the tile's neighbour references as (offset to the neighbour container, slot), re-based on every copy of the tile
+    ly, lx = torch.meshgrid(torch.arange(tile, device=dev), torch.arange(tile, device=dev), indexing="ij")
+    ref = t["nb_ids"].long() - 1
+    tc, slot = ref // cap, ref % cap
+    dx = (tc % tile - lx[:, :, None, None] + 1) % tile - 1
+    dy = (tc // tile - ly[:, :, None, None] + 1) % tile - 1
+    live = torch.arange(maxnb, device=dev)[None, None, None, :] < t["nb_counts"][..., None]
+    gy, gx = torch.meshgrid(torch.arange(n, device=dev), torch.arange(n, device=dev), indexing="ij")
+
+    def rep(a):
+        return a.repeat((reps, reps) + (1,) * (a.dim() - 2))
+
+    g = {k: rep(t[k]).contiguous() for k in ("counts", "values", "influx", "nb_counts")}
+    g["ids"] = (1 + (gy * n + gx)[:, :, None] * cap + torch.arange(cap, device=dev)[None, None, :]).int()
+    g["ids"][torch.arange(cap, device=dev)[None, None, :] >= g["counts"][..., None]] = 0
+    tx = (gx[:, :, None, None] + rep(dx)) % n
+    ty = (gy[:, :, None, None] + rep(dy)) % n
+    g["nb_ids"] = torch.where(rep(live), 1 + (ty * n + tx) * cap + rep(slot), 0).int().contiguous()
+    return g, rep
+
+
+def bench_container(args, torch, tile=128, reps=8, with_e2e=True):
+    """ContainerCell grid of ID-keyed mesh elements (the cell of the reference's Voronoi example; SURVEY 8(a) a10's
+    ID-keyed variant): a 2-D torus of (tile * reps)^2 containers, capacity 16, up to 20 neighbour ids per element.
+    The mesh is a `tile`^2 torus replicated reps x reps times (built on the device), so the full-size result must
+    equal the small torus's result tile by tile, and THAT is checked against the oracle: a size-independent check of
+    every temperature. Metric: element updates/s; bound = HBM (the link table is read once per sweep)."""
+    from libgeodecomp_b200 import capi, models, synth
+    from libgeodecomp_b200.containergrid import ContainerGrid
+
+    model = models.Container2Torus
+    cap, maxnb = model.capacity, model.max_neighbors
+    K, W = max(10, args.steps // 2), 3
+    box, _ = synth.container_cells(tile, tile, 1, n_dims=2, torus=True, cap=cap, maxnb=maxnb, seed=11)
+    n = tile * reps
+    dev = "cuda"
+    g, rep = replicate_mesh(torch, box, tile, reps, dev)
+    elements = int(g["counts"].sum().item())
+    links = int(box["nb_counts"][np.arange(cap) < box["counts"][..., None]].sum()) * reps * reps
+
+    grid = ContainerGrid(model, (n, n))
+    grid.dev.load(g, location=capi.CUDA_DEVICE)
+    grid.dev.step(capi.KERNEL_CONTAINER, W)
+    torch.cuda.synchronize()
+    launches0 = capi.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    grid.dev.step(capi.KERNEL_CONTAINER, K)
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1) / K
+    launches = capi.launch_count() - launches0
+    stats = grid.dev.stats()
+    assert stats["cargo"] == elements and stats["links"] == links, (stats, elements, links)
+    # every temperature: the replicated mesh must evolve like the tile torus, which the oracle computes
+    out = torch.empty((n, n, cap), dtype=torch.float64, device=dev)
+    grid.dev.save({"values": out}, location=capi.CUDA_DEVICE)
+    verified = None
+    if not args.no_verify:
+        from oracle import oracle_py
+        want = torch.from_numpy(oracle_py.container(box, W + K, n_dims=2, torus=True)).to(dev)
+        verified = bool(torch.equal(out.view(torch.int64), rep(want).contiguous().view(torch.int64)))
+    # algorithmic bytes of one sweep: the link (4 B each), and per element its influx (8), neighbour count (4), the
+    # write (8) and one compulsory read of its own old temperature (8): the gathers re-read what other elements fetch
+    alg = 4.0 * links + 28.0 * elements
+    peak, peak_src = peaks()
+    res = {"workload": "container", "metric": "G element updates/s", "value": 1e-9 * elements / (1e-3 * ms), "unit": "Gelements/s",
+           "ms_per_step": ms, "elements": elements, "links": links, "containers": [n, n], "capacity": cap, "max_neighbors": maxnb,
+           "dtype": "f64", "gpu_launches": launches, "steps": K, "verified": verified,
+           "links_per_s": links / (1e-3 * ms),
+           "roofline": {"bound": "hbm", "achieved": alg / (1e-3 * ms) / 1e9, "peak": peak, "unit": "GB/s",
+                        "frac": alg / (1e-3 * ms) / 1e9 / peak, "traffic": None, "kernel_ms": ms,
+                        "algorithmic_bytes_per_launch": alg, "peak_source": peak_src,
+                        "note": "sweep_kernel of csrc/container.cu: 4 B per link + 28 B per element; working set %.0f MB >> L2" % (alg / 1e6)}}
+    if with_e2e:
+        host = {k: torch.empty(v.shape, dtype=v.dtype, pin_memory=True) for k, v in g.items()}
+        for k in g:
+            host[k].copy_(g[k])
+        res_host = torch.empty((n, n, cap), dtype=torch.float64, pin_memory=True)
+        torch.cuda.synchronize()
+        del g, out
+        hbox = {k: v.numpy() for k, v in host.items()}
+        nbytes = sum(v.nbytes for v in hbox.values())
+        t0 = time.perf_counter()
+        grid.loadCells(hbox)
+        grid.dev.step(capi.KERNEL_CONTAINER, K)
+        grid.dev.save({"values": res_host.numpy()})
+        e_s = time.perf_counter() - t0
+        res["e2e"] = {"value": 1e-9 * elements * K / e_s, "unit": "Gelements/s", "h2d_bytes_per_step": nbytes / K,
+                      "d2h_bytes_per_step": res_host.numpy().nbytes / K, "ms_per_run": 1e3 * e_s,
+                      "what": "ContainerGrid.loadCells (pinned host arrays, %.2f GB) -> link resolution -> %d sweeps -> temperatures "
+                              "back to the host" % (nbytes / 1e9, K)}
+    if not args.no_cpu:
+        try:   # the reference's own OpenMPSimulator over ContainerCell containers on the tile
+            from oracle import oracle_py
+            _, st = oracle_py.run_ref_container(box, 10, n_dims=2, torus=True, omp=True, threads=os.cpu_count(), want_output=False)
+            res["cpu_baseline"] = {"value": st["geups_compute"], "unit": "Gelements/s", "cores": os.cpu_count(), "kind": "reference",
+                                   "sample": "the %d^2 tile (%d elements) x 10 steps, reference OpenMPSimulator over "
+                                             "ContainerCell<MeshElement, 16>, TimeCompute interval" % (tile, st["elements"])}
+        except Exception as e:
+            res["cpu_baseline"] = {"value": None, "sample": "failed: %r" % (e,)}
+    del grid
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -985,6 +1098,12 @@ def main():
         except Exception as e:  # secondary workload: never take the headline line down with it
             others.append({"workload": "nbody", "error": repr(e)})
 
+    if not args.no_others and world == 1:
+        try:
+            others.append(bench_container(args, torch))
+        except Exception as e:  # secondary workload: never take the headline line down with it
+            others.append({"workload": "container", "error": repr(e)})
+
     os.sched_setaffinity(0, affinity)       # the CPU legs below use all host cores
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -1036,7 +1155,7 @@ def main():
         for r in others:
             w = r.get("workload")
             if w and "value" in r:
-                line["%s_%s" % (w, "gparticles_per_s" if w == "nbody" else "glups")] = r["value"]
+                line["%s_%s" % (w, {"nbody": "gparticles_per_s", "container": "gelements_per_s"}.get(w, "glups"))] = r["value"]
                 if "roofline" in r:
                     line["%s_roofline_frac" % w] = r["roofline"].get("frac")
                 if "e2e" in r:

@@ -195,37 +195,36 @@ def container_cells(nx, ny, nz=1, n_dims=3, torus=False, cap=16, maxnb=20, seed=
     influx[~live] = 0
     nb_counts[~live] = 0
     nb_ids = np.zeros((ncont, cap, maxnb), dtype=np.int32)
-    dims = np.array([nx, ny, nz], dtype=np.int64)
+    dims = (nx, ny, nz)
+    cnt64 = counts.astype(np.int64)
+    jj = np.arange(maxnb, dtype=np.int32)[None, None, :]
     for c0 in range(0, ncont, chunk):
         c1 = min(ncont, c0 + chunk)
         c = np.arange(c0, c1, dtype=np.int64)
-        key = (np.arange(c0 * cap * maxnb, c1 * cap * maxnb, dtype=np.uint64)).reshape(c1 - c0, cap, maxnb)
-        r = h(key, 7)
-        coord = np.stack([c % nx, (c // nx) % ny, c // (nx * ny)], axis=-1)          # [n][3]
-        d = np.stack([(r % np.uint64(3)).astype(np.int64) - 1, ((r >> np.uint64(8)) % np.uint64(3)).astype(np.int64) - 1,
-                      ((r >> np.uint64(16)) % np.uint64(3)).astype(np.int64) - 1], axis=-1)   # [n][cap][maxnb][3]
-        if n_dims == 2:
-            d[..., 2] = 0
-        p = coord[:, None, None, :] + d
-        outside = ((p < 0) | (p >= dims)).any(axis=-1)
-        if torus:
-            p = (p + dims) % dims
-            outside[...] = False
-        else:
-            p = np.clip(p, 0, dims - 1)
-        t = (p[..., 2] * ny + p[..., 1]) * nx + p[..., 0]
-        own = np.broadcast_to(c[:, None, None], t.shape)
-        use_edge = outside & bool(edge)
+        r = h(np.arange(c0 * cap * maxnb, c1 * cap * maxnb, dtype=np.uint64), 7).reshape(c1 - c0, cap, maxnb)
+        coord = (c % nx, (c // nx) % ny, c // (nx * ny))
+        t = np.zeros(r.shape, dtype=np.int64)
+        outside = np.zeros(r.shape, dtype=bool)
+        stride = 1
+        for a in range(n_dims):
+            p = coord[a][:, None, None] + ((r >> np.uint64(8 * a)) % np.uint64(3)).astype(np.int64) - 1
+            if torus:
+                p = (p + dims[a]) % dims[a]
+            else:
+                outside |= (p < 0) | (p >= dims[a])
+                np.clip(p, 0, dims[a] - 1, out=p)
+            t += p * stride
+            stride *= dims[a]
+        own = c[:, None, None]
         # lookups that left a Cube grid without an edge container, or that hit an empty container, fall back on the own one
-        t = np.where(outside & ~use_edge, own, t)
-        t = np.where(counts[t] == 0, own, t)
+        if not edge:
+            t = np.where(outside, own, t)
+        t = np.where(cnt64[t] == 0, own, t)
         pick = (r >> np.uint64(24)).astype(np.int64)
-        target = 1 + t * cap + pick % np.maximum(counts[t], 1)
+        target = 1 + t * cap + pick % np.maximum(cnt64[t], 1)
         if edge:
-            target = np.where(use_edge, 1 + ncont * cap + pick % n_edge, target)
-        j = np.arange(maxnb)[None, None, :]
-        target = np.where(j < nb_counts[c0:c1, :, None], target, 0)
-        nb_ids[c0:c1] = target.astype(np.int32)
+            target = np.where(outside, 1 + ncont * cap + pick % n_edge, target)
+        nb_ids[c0:c1] = np.where(jj < nb_counts[c0:c1, :, None], target, 0)
     shape = (nz, ny, nx) if n_dims == 3 else (ny, nx)
     box = {"counts": counts.reshape(shape), "ids": ids.reshape(shape + (cap,)), "values": values.reshape(shape + (cap,)),
            "influx": influx.reshape(shape + (cap,)), "nb_counts": nb_counts.reshape(shape + (cap,)),

@@ -53,3 +53,22 @@ def test_device_arm_line():
     assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(d["clocks"])
     cb = d["cpu_baseline"]
     assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["unit"] == "GLUPS"
+
+
+def test_container_bench_mesh_is_a_tiled_torus(oracle):
+    """bench.py's ContainerCell leg checks its full-size result through a size-independent property: the mesh is a small
+    torus replicated reps x reps times, so every tile must evolve like the small torus alone (which the oracle computes)."""
+    import numpy as np
+    import torch
+    sys.path.insert(0, ROOT)
+    import bench
+    from libgeodecomp_b200 import synth
+    tile, reps = 5, 3
+    box, _ = synth.container_cells(tile, tile, 1, n_dims=2, torus=True, seed=11)
+    g, rep = bench.replicate_mesh(torch, box, tile, reps, "cpu")
+    big = {k: v.numpy() for k, v in g.items()}
+    assert big["counts"].shape == (tile * reps, tile * reps) and big["nb_ids"].dtype == np.int32
+    live = np.arange(16) < big["counts"][..., None]
+    assert (np.diff(big["ids"], axis=-1)[live[..., 1:]] > 0).all()
+    want = np.tile(oracle.container(box, 6, n_dims=2, torus=True), (reps, reps, 1))
+    assert np.array_equal(oracle.container(big, 6, n_dims=2, torus=True).view(np.uint64), want.view(np.uint64))
