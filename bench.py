@@ -958,7 +958,7 @@ def replicate_mesh(torch, box, tile, reps, dev):
     return g, rep
 
 
-def bench_container(args, torch, tile=128, reps=8, with_e2e=True):
+def bench_container(args, torch, tile=128, reps=8, with_e2e=True, kernel=None):
     """ContainerCell grid of ID-keyed mesh elements (the cell of the reference's Voronoi example; SURVEY 8(a) a10's
     ID-keyed variant): a 2-D torus of (tile * reps)^2 containers, capacity 16, up to 20 neighbour ids per element.
     The mesh is a `tile`^2 torus replicated reps x reps times (built on the device), so the full-size result must
@@ -970,6 +970,8 @@ def bench_container(args, torch, tile=128, reps=8, with_e2e=True):
     model = models.Container2Torus
     cap, maxnb = model.capacity, model.max_neighbors
     K, W = max(10, args.steps // 2), 3
+    if kernel is not None:
+        capi.set_tuning("container.kernel", kernel)
     box, _ = synth.container_cells(tile, tile, 1, n_dims=2, torus=True, cap=cap, maxnb=maxnb, seed=11)
     n = tile * reps
     dev = "cuda"
@@ -1005,7 +1007,8 @@ def bench_container(args, torch, tile=128, reps=8, with_e2e=True):
     peak, peak_src = peaks()
     res = {"workload": "container", "metric": "G element updates/s", "value": 1e-9 * elements / (1e-3 * ms), "unit": "Gelements/s",
            "ms_per_step": ms, "elements": elements, "links": links, "containers": [n, n], "capacity": cap, "max_neighbors": maxnb,
-           "dtype": "f64", "gpu_launches": launches, "steps": K, "verified": verified,
+           "dtype": "f64", "gpu_launches": launches, "steps": K, "verified": verified, "layout": stats.get("kernel"),
+           "link_table_bytes": stats.get("link_table_bytes"),
            "links_per_s": links / (1e-3 * ms),
            "roofline": {"bound": "hbm", "achieved": alg / (1e-3 * ms) / 1e9, "peak": peak, "unit": "GB/s",
                         "frac": alg / (1e-3 * ms) / 1e9 / peak, "traffic": None, "kernel_ms": ms,

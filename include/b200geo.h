@@ -88,7 +88,8 @@ int b200geo_device_count(void);
  * bit-packed; 0 = never), "gol.bits_rows", "nbody.kernel", "jacobi.pdl" (programmatic dependent launch of the one-sweep Jacobi
  * kernel: 0, 1, < 0 = small grids only), "lbm.variant" (rows per thread of the LBM kernel: 1 or 2), "jacobi.tb_promo" (L2 promotion of the
  * temporal-blocked kernel's TMA loads), "jacobi.tb_raster" (its CTA order), "nbody.run" (containers per CTA), "jacobi.resident" (1: small Cube grids take the
- * SM-resident multi-sweep kernel).
+ * SM-resident multi-sweep kernel), "container.kernel" (ContainerCell sweeps: 0 = links into the global value array, 1 = tiles of
+ * containers with the neighbourhood's values staged in shared memory and 16-bit links; takes effect at the next link resolution).
  * value < 0 restores the default. */
 int b200geo_set_tuning(const char *key, int value);
 /* number of kernels this library has launched so far in this process (bench.py: gpu_launches). */
@@ -372,8 +373,9 @@ int b200geo_containergrid_get_edge(const b200geo_containergrid *g, const b200geo
  * B200GEO_ERR_OUT_OF_RANGE if a count exceeds its capacity; the grid is unchanged then. */
 int b200geo_containergrid_step(b200geo_containergrid *g, uint32_t first_nano_step, uint32_t n_steps, void *stream);
 /* out[0] = cargo items in the grid, out[1] = resolved neighbour links, out[2] = link resolutions so far,
- * out[3] = sweeps so far (valid after the first step) */
-int b200geo_containergrid_stats(const b200geo_containergrid *g, uint64_t out[4]);
+ * out[3] = sweeps so far, out[4] = layout of the link table ("container.kernel": 0 or 1), out[5] = its bytes
+ * (valid after the first step) */
+int b200geo_containergrid_stats(const b200geo_containergrid *g, uint64_t out[6]);
 
 /* ---- statistics: Simulator::gatherStatistics / Chronometer (misc/chronometer.h:142-150) ---- */
 /* out[0] = device seconds spent in update kernels (TimeComputeInner), out[1] = seconds in ghost

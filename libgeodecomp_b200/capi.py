@@ -558,9 +558,10 @@ class DeviceContainerGrid:
         pass
 
     def stats(self):
-        out = (ctypes.c_uint64 * 4)()
+        out = (ctypes.c_uint64 * 6)()
         check(lib().b200geo_containergrid_stats(self._h, out))
-        return {"cargo": int(out[0]), "links": int(out[1]), "resolutions": int(out[2]), "sweeps": int(out[3])}
+        return {"cargo": int(out[0]), "links": int(out[1]), "resolutions": int(out[2]), "sweeps": int(out[3]),
+                "kernel": int(out[4]), "link_table_bytes": int(out[5])}
 
 
 def sync(stream=None):

@@ -10,7 +10,7 @@
 
 namespace b200geo {
 
-static const Tuning g_tuning_default = {0, -1, 0, 128, 0, 33, 0, 4, 0, 3, -1, 1, 0, 0, 0, 0, 0, 2, 14, 0, 0, 1, 0};
+static const Tuning g_tuning_default = {0, -1, 0, 128, 0, 33, 0, 4, 0, 3, -1, 1, 0, 0, 0, 0, 0, 2, 14, 0, 0, 1, 0, 0};
 Tuning g_tuning = g_tuning_default;
 static thread_local std::string g_last_error;
 static std::atomic<uint64_t> g_launches(0);
@@ -97,6 +97,7 @@ int b200geo_set_tuning(const char *key, int value)
     else if (k == "lbm.tb_warps") g_tuning.lbm_tb_warps = value < 0 ? g_tuning_default.lbm_tb_warps : value;
     else if (k == "lbm.tb_hints") g_tuning.lbm_tb_hints = value < 0 ? g_tuning_default.lbm_tb_hints : value;
     else if (k == "lbm.tb_zchunk") g_tuning.lbm_tb_zchunk = value < 0 ? g_tuning_default.lbm_tb_zchunk : value;
+    else if (k == "container.kernel") g_tuning.container_kernel = value < 0 ? g_tuning_default.container_kernel : value;
     else return fail(B200GEO_ERR_INVALID, "unknown tuning key " + k);
     return B200GEO_OK;
 }

@@ -88,6 +88,7 @@ struct Tuning {
     int lbm_tb_promo;     // L2 promotion of the fused LBM kernel's TMA loads: 0 none, 1 64 B, 2 128 B, 3 256 B
     int lbm_tb_warps;     // fused LBM kernel: 1 = sweep 1 and sweep 2 on different warps linked by mbarriers, 0 = all warps do both, two CTA-wide barriers per plane
     int lbm_tb_hints;     // L2 hints of the fused LBM kernel: bit 0 = streaming stores, bit 1 = evict-last window loads
+    int container_kernel; // ContainerCell sweeps: 0 = links into the global value array (windows of 1024 sorted by neighbour count), 1 = tiles of containers with their neighbourhood's values staged in shared memory and 16-bit links (where the capacity allows)
 };
 extern Tuning g_tuning;
 

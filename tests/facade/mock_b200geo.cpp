@@ -874,7 +874,7 @@ int b200geo_containergrid_step(b200geo_containergrid *g, uint32_t, uint32_t n_st
     return B200GEO_OK;
 }
 
-int b200geo_containergrid_stats(const b200geo_containergrid *g, uint64_t out[4])
+int b200geo_containergrid_stats(const b200geo_containergrid *g, uint64_t out[6])
 {
     if (!g || !out) return fail(B200GEO_ERR_INVALID, "null argument");
     uint64_t cargo = 0;
@@ -883,6 +883,8 @@ int b200geo_containergrid_stats(const b200geo_containergrid *g, uint64_t out[4])
     out[1] = g->links;
     out[2] = g->rebuilds;
     out[3] = g->sweeps;
+    out[4] = 0;
+    out[5] = 4 * g->links;
     return B200GEO_OK;
 }
 

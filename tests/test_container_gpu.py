@@ -16,6 +16,16 @@ from test_container_cpu import CellInit, FIELDS, golden_case, golden_cases, mode
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True, params=[0, 1], ids=["windows", "tiles"])
+def container_kernel(request):
+    """every test runs with both layouts of the link table ("container.kernel"): 0 = windows of 1024 cargo items sorted
+    by neighbour count, 32-bit links into the global value array; 1 = tiles of containers, the neighbourhood's values
+    staged in shared memory, 16-bit links"""
+    capi.set_tuning("container.kernel", request.param)
+    yield request.param
+    capi.set_tuning("container.kernel", -1)
+
+
 def run(box, edge, nd, torus, steps, model=None):
     sim = B200Simulator(CellInit(box, edge, steps), model or model_for(nd, torus))
     sim.run()
@@ -38,7 +48,7 @@ def test_container_golden_from_the_reference(key):
                                                       ((1, 1, 1), 3, False, False, 3), ((1, 1, 1), 3, True, False, 3),
                                                       ((2, 3, 1), 3, True, False, 4), ((64, 1, 1), 2, False, False, 9),
                                                       ((24, 24, 24), 3, False, False, 6)])
-def test_container_bit_exact(oracle, dims, nd, torus, edge, steps):
+def test_container_bit_exact(oracle, container_kernel, dims, nd, torus, edge, steps):
     box, eb = synth.container_cells(*dims, n_dims=nd, torus=torus, edge=edge, seed=sum(dims))
     sim = run(box, eb, nd, torus, steps)
     got = sim.getGrid().saveCells(fields=("counts", "values"))
@@ -48,9 +58,10 @@ def test_container_bit_exact(oracle, dims, nd, torus, edge, steps):
     assert stats["cargo"] == int(box["counts"].sum()) and stats["links"] == int(box["nb_counts"][live].sum())
     # run() re-initialised the grid once and the constructor loaded it once: the links were resolved once, for run()
     assert stats["resolutions"] == 1 and stats["sweeps"] == steps
+    assert stats.get("kernel", container_kernel) == container_kernel
 
 
-@pytest.mark.parametrize("cap,maxnb", [(1, 1), (5, 3), (32, 8), (100, 20), (7, 64)])
+@pytest.mark.parametrize("cap,maxnb", [(1, 1), (5, 3), (32, 8), (40, 6), (100, 20), (7, 64), (1500, 2)])
 def test_container_capacities(oracle, cap, maxnb):
     box, eb = synth.container_cells(9, 8, 3, cap=cap, maxnb=maxnb, edge=True, seed=cap)
     model = models.Container3Cube.with_params(capacity=cap, max_neighbors=maxnb)

@@ -18,10 +18,11 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-verify", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--kernel", type=int, default=None, help='"container.kernel": 0 = windows / global gathers, 1 = tiles / staged values')
     args = ap.parse_args()
     import torch
     torch.cuda.set_device(0)
-    print(json.dumps(bench.bench_container(args, torch, tile=args.tile, reps=args.reps, with_e2e=not args.no_e2e)), flush=True)
+    print(json.dumps(bench.bench_container(args, torch, tile=args.tile, reps=args.reps, with_e2e=not args.no_e2e, kernel=args.kernel)), flush=True)
 
 
 if __name__ == "__main__":
