@@ -202,7 +202,7 @@ static void timeRun(SIM& sim, const HostField& field, const char *what, int n, u
     double s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     double updates = (double)n * n * n * steps;
     std::printf("{\"impl\": \"%s\", \"cell\": \"Jacobi27Cube\", \"dims\": [%d, %d, %d], \"steps\": %u, \"slabs\": %d, \"mode\": \"%s\", "
-                "\"seconds\": %.4f, \"value\": %.2f, \"unit\": \"GLUPS\", \"h2d_bytes_per_step\": %.0f, \"d2h_bytes_per_step\": %.0f, "
+                "\"seconds\": %.4f, \"value\": %.6f, \"unit\": \"GLUPS\", \"h2d_bytes_per_step\": %.0f, \"d2h_bytes_per_step\": %.0f, "
                 "\"checksum\": \"%llu\", \"what\": \"C++ program: run() of the facade simulator, Initializer from / Writer into host memory, wall clock\"}\n",
                 what, n, n, n, steps, slabs, mode, s, updates / s * 1e-9, (double)n * n * n * 8 / steps, (double)n * n * n * 8 / steps,
                 checksum(field));
