@@ -101,6 +101,12 @@ public:
         for (int i = 0; i < n; ++i) {
             Coord<DIM> c = streak.origin;
             c.x() += i;
+            // coordinates beyond the box address what Grid::operator[] does (Topology::locate, geometry/topologies.h:186-213):
+            // the periodic image on a Torus axis, the edge cell beyond a Cube boundary
+            if (!locate(&c)) {
+                setEdge(cells[i]);
+                continue;
+            }
             std::size_t at = index(c);
             shadow[at] = cells[i];
             written[at] = 1;
@@ -120,6 +126,19 @@ public:
         const_cast<B200ContainerGrid*>(this)->flush();
         int n = streak.length();
         if (n <= 0) {
+            return;
+        }
+        if (!box.inBounds(streak)) {
+            // cell by cell like Grid::get (storage/grid.h:225-240): periodic images and the edge cell
+            for (int i = 0; i < n; ++i) {
+                Coord<DIM> c = streak.origin;
+                c.x() += i;
+                if (locate(&c)) {
+                    get(Streak<DIM>(c, c.x() + 1), cells + i);
+                } else {
+                    cells[i] = edgeCell;
+                }
+            }
             return;
         }
         std::vector<double> values((std::size_t)n * SIZE);
@@ -236,6 +255,17 @@ private:
     std::vector<CELL> shadow;        /* every container as last written; the temperatures of record are the device's */
     bool dirty;
     int32_t dirtyLo[3], dirtyHi[3];  /* bounding box (local coordinates, half open) of the containers written since the last flush */
+
+    /* Topology::locate for a coordinate: false = the edge cell, else *c is moved to the cell inside the box */
+    bool locate(Coord<DIM> *c) const
+    {
+        Coord<DIM> rel = *c - box.origin;
+        if (Topology::isOutOfBounds(rel, box.dimensions)) {
+            return false;
+        }
+        *c = Topology::normalize(rel, box.dimensions) + box.origin;
+        return true;
+    }
 
     void local(const Coord<DIM>& c, int32_t *o) const
     {

@@ -111,6 +111,7 @@ __global__ void box_copy_kernel(T *store, T *buf, const int32_t *counts, int per
 
 const int WINDOW = 1024;   // sigma of SELL-C-sigma: cargo items sorted by neighbour count inside windows of this many
 const int CHUNK = 32;      // C: one warp
+const int MAX_STAGED = 9 * 34;   // containers a tile stages at most: 3 x 3 rows of (32 + 2)
 
 // every count within 0..capacity? (before anything is indexed with their prefix sums)
 __global__ void validate_counts_kernel(const int32_t *counts, int64_t n, int cap, int32_t *err)
@@ -461,11 +462,20 @@ __global__ void __launch_bounds__(256) tile_sweep_kernel(const double *__restric
         for (int v = 0; v < 4; ++v) a[u][v] = v < width[u] ? __ldg(l[u] + v * CHUNK) : (uint16_t)0;
     }
 
+    // where the staged containers' cargo starts and how many items they hold: one thread per container (the index
+    // arithmetic of a wrapped neighbourhood costs ~150 instructions; done warp by warp it made the kernel issue-bound,
+    // profiles/r6c), then one warp per container copies its values
+    __shared__ int s_first[MAX_STAGED], s_count[MAX_STAGED];
     const int staged = T.rows * (T.g + 2);
-    for (int q = warp; q < staged; q += 8) {
+    for (int q = threadIdx.x; q < staged; q += 256) {
         const int64_t c = staged_container(T, D, ncont, x0, cy, cz, q / (T.g + 2), q % (T.g + 2));
         const int o = __ldg(offsets + c);
-        const int n = __ldg(offsets + c + 1) - o;
+        s_first[q] = o;
+        s_count[q] = __ldg(offsets + c + 1) - o;
+    }
+    __syncthreads();
+    for (int q = warp; q < staged; q += 8) {
+        const int o = s_first[q], n = s_count[q];
         for (int s = lane; s < n; s += CHUNK) sval[q * T.cap + s] = old_val[o + s];
     }
     __syncthreads();

@@ -17,7 +17,7 @@ import pytest
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-@pytest.mark.parametrize("name", ["facade_test_cpu", "striping_test_cpu", "host_logic_test_cpu", "generic_soa_host_test_cpu", "stepper_test_cpu", "checkpoint_test_cpu", "streamed_test_cpu", "container_test_cpu"])
+@pytest.mark.parametrize("name", ["facade_test_cpu", "striping_test_cpu", "host_logic_test_cpu", "generic_soa_host_test_cpu", "stepper_test_cpu", "checkpoint_test_cpu", "streamed_test_cpu", "container_test_cpu", "voronoi_test_cpu"])
 def test_cpp_facade_host_logic_on_the_mock_engine(name):
     binary = os.path.join(HERE, "facade", "_bin", name)
     if not os.access(binary, os.X_OK):

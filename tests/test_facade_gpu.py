@@ -174,6 +174,22 @@ def test_cpp_container_cell_drop_in():
     assert "all checks passed" in res.stdout and "DIFFERENT" not in res.stdout
 
 
+VORONOI_BIN = os.path.join(HERE, "facade", "_bin", "voronoi_test")
+
+
+@pytest.mark.gpu
+def test_reference_voronoi_example_drop_in():
+    """tests/facade/voronoi_test.cpp: the reference's own src/examples/voronoi/main.cpp (SimpleCell in
+    ContainerCell<SimpleCell, 1000>, VoronoiInitializer / VoronoiMesher), compiled unchanged, on SerialSimulator and on
+    B200Simulator: one B200GEO_BIND_CARGO line and the simulator type are all that differs; every element bit-identical."""
+    if not os.access(VORONOI_BIN, os.X_OK):
+        pytest.skip("tests/facade/_bin/voronoi_test not built (needs /root/reference at build time)")
+    res = subprocess.run([VORONOI_BIN], capture_output=True, text=True, timeout=600)
+    print(res.stdout[-4000:], res.stderr[-2000:])
+    assert res.returncode == 0, res.stdout[-4000:] + res.stderr[-2000:]
+    assert "all checks passed" in res.stdout and "DIFFERENT" not in res.stdout
+
+
 def test_facade_header_has_no_oracle_dependency():
     for name in ("b200containergrid.h", "b200simulator.h", "b200generic.h", "b200genericsoa.h", "b200boxgrid.h", "b200stripingsimulator.h", "b200stepper.h", "b200checkpoint.h"):
         text = open(os.path.join(HERE, "..", "include", "libgeodecomp_b200", name)).read()
