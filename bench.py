@@ -1011,7 +1011,9 @@ def bench_container(args, torch, tile=128, reps=8, with_e2e=True, kernel=None):
            "link_table_bytes": stats.get("link_table_bytes"),
            "links_per_s": links / (1e-3 * ms),
            "roofline": {"bound": "hbm", "achieved": alg / (1e-3 * ms) / 1e9, "peak": peak, "unit": "GB/s",
-                        "frac": alg / (1e-3 * ms) / 1e9 / peak, "traffic": None, "kernel_ms": ms,
+                        "frac": alg / (1e-3 * ms) / 1e9 / peak,
+                        "traffic": (ncu_traffic("container") or {}).get("dram_bytes_per_launch") if stats.get("kernel") == 0 else None,
+                        "kernel_ms": ms,
                         "algorithmic_bytes_per_launch": alg, "peak_source": peak_src,
                         "note": "sweep_kernel of csrc/container.cu: 4 B per link + 28 B per element; working set %.0f MB >> L2" % (alg / 1e6)}}
     if with_e2e:
