@@ -525,6 +525,12 @@ struct B200StripedGridSelector<BoxCell<FixedArray<PARTICLE, N> > > {
     typedef B200StripedBoxGrid<PARTICLE, N> Type;
 };
 
+/* ContainerCell grids (ID-keyed cargo) live on one device: B200Simulator<ContainerCell<...> > */
+template<typename CARGO, std::size_t SIZE>
+struct B200StripedGridSelector<ContainerCell<CARGO, SIZE, int> > {
+    static_assert(sizeof(CARGO) == 0, "there is no slab partition for ContainerCell grids yet: use B200Simulator<ContainerCell<...> >");
+};
+
 template<typename CELL>
 class B200StripingSimulator : public MonolithicSimulator<CELL>
 {

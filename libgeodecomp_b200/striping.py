@@ -229,6 +229,8 @@ class StripedSimulator:
         (ghost_width >= sweeps of the run): every rank then asks its Initializer for its slab PLUS the ghost zones,
         recomputes the shrinking ghost zone redundantly and needs no exchange at all while the wavefront passes —
         HiParSimulator's ghost zone of width k taken to k = run length (parallelization/hiparsimulator.h:60-66)."""
+        if model.kernel == capi.KERNEL_CONTAINER:
+            raise capi.LogicError("ContainerCell grids run on one device (B200Simulator): there is no slab partition for them yet")
         self.initializer, self.model, self.rank, self.world = initializer, model, rank, world
         self.overlap = overlap
         self.stream_io, self.stream_depth, self.stream_chunks = stream_io, stream_depth, stream_chunks

@@ -155,3 +155,10 @@ def test_container_set_get_follow_containercell_insert():
     assert grid.getEdge() == back[:2]
     with pytest.raises(ValueError):
         ContainerGrid(models.Container3Cube, (3, 2), engine=cpu_engine)
+
+
+def test_striped_simulator_refuses_container_models():
+    from libgeodecomp_b200.striping import StripedSimulator
+    box, _ = synth.container_cells(4, 3, 1, n_dims=2)
+    with pytest.raises(capi.LogicError):
+        StripedSimulator(CellInit(box, None, 1), models.Container2Cube, engine=cpu_engine)
