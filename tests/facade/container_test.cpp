@@ -6,6 +6,9 @@
  * that is not in the neighbourhood (storage/neighborhoodadapter.h:63-64). Built twice by tests/facade/Makefile: against
  * libb200geo.so (run on the GPU box by tests/test_facade_gpu.py) and against the mock engine (CPU suite). */
 #include <libgeodecomp/io/simpleinitializer.h>
+#include <libgeodecomp/io/steerer.h>
+#include <libgeodecomp/io/writer.h>
+#include <libgeodecomp/misc/clonable.h>
 #include <libgeodecomp/parallelization/serialsimulator.h>
 
 #include <libgeodecomp_b200/b200simulator.h>
@@ -176,6 +179,84 @@ static void compare(const char *name, const Coord<DIM>& dim, unsigned steps, boo
                 bad == 0 ? "bit-identical to SerialSimulator" : "DIFFERENT");
 }
 
+/* a Steerer that heats every element of one container every third step, and a Writer that sums all temperatures at
+ * every step: both plugins see ContainerCells through GridBase, as with the reference's simulator */
+template<typename CELL, int DIM>
+class HeatSteerer : public Steerer<CELL>
+{
+public:
+    typedef typename Steerer<CELL>::GridType GridType;
+    typedef typename Steerer<CELL>::SteererFeedback SteererFeedback;
+    typedef typename Steerer<CELL>::CoordType CoordType;
+
+    HeatSteerer(unsigned period, const Coord<DIM>& where) : Steerer<CELL>(period), where(where) {}
+
+    virtual void nextStep(GridType *grid, const Region<DIM>&, const CoordType&, unsigned step, SteererEvent event, std::size_t, bool,
+                          SteererFeedback *)
+    {
+        if (event != STEERER_NEXT_STEP) {
+            return;
+        }
+        CELL cell = grid->get(where);
+        for (typename CELL::Iterator e = cell.begin(); e != cell.end(); ++e) {
+            e->temperature += 1.0 + step;
+        }
+        grid->set(where, cell);
+    }
+
+private:
+    Coord<DIM> where;
+};
+
+template<typename CELL, int DIM>
+class SumWriter : public Clonable<Writer<CELL>, SumWriter<CELL, DIM> >
+{
+public:
+    typedef typename Writer<CELL>::GridType GridType;
+
+    SumWriter(std::vector<double> *log, unsigned period) : Clonable<Writer<CELL>, SumWriter<CELL, DIM> >("", period), log(log) {}
+
+    virtual void stepFinished(const GridType& grid, unsigned step, WriterEvent)
+    {
+        double sum = 0;
+        CoordBox<DIM> box = grid.boundingBox();
+        for (typename CoordBox<DIM>::Iterator i = box.begin(); i != box.end(); ++i) {
+            CELL cell = grid.get(*i);
+            for (typename CELL::Iterator e = cell.begin(); e != cell.end(); ++e) {
+                sum += e->temperature;
+            }
+        }
+        log->push_back(step);
+        log->push_back(sum);
+    }
+
+private:
+    std::vector<double> *log;
+};
+
+static void testPlugins()
+{
+    typedef MeshInitializer<2, true> Init;
+    typedef Init::Cell Cell;
+    Coord<2> dim(9, 8);
+    unsigned steps = 11;
+    std::vector<double> logRef, logDev;
+    SerialSimulator<Cell> ref(new Init(dim, steps, false));
+    B200Simulator<Cell> dev(new Init(dim, steps, false));
+    ref.addSteerer(new HeatSteerer<Cell, 2>(3, Coord<2>(4, 4)));
+    dev.addSteerer(new HeatSteerer<Cell, 2>(3, Coord<2>(4, 4)));
+    ref.addWriter(new SumWriter<Cell, 2>(&logRef, 2));
+    dev.addWriter(new SumWriter<Cell, 2>(&logDev, 2));
+    ref.run();
+    dev.run();
+    CHECK(logRef.size() == logDev.size() && logRef.size() >= 12);
+    CHECK(!logRef.empty() && std::memcmp(logRef.data(), logDev.data(), logRef.size() * sizeof(double)) == 0);
+    CHECK(logRef.back() != logRef[1]);
+    std::printf("Steerer writes every third step + Writer every second: %zu log entries, %s\n", logRef.size() / 2,
+                (logRef.size() == logDev.size() && !std::memcmp(logRef.data(), logDev.data(), logRef.size() * sizeof(double)))
+                    ? "identical sums at every event" : "DIFFERENT");
+}
+
 static void testMissingID()
 {
     typedef MeshInitializer<2, false> Init;
@@ -282,6 +363,7 @@ int main()
     compare<3, false>("container 3-D cube", Coord<3>(7, 6, 5), 9, true);
     compare<3, true>("container 3-D torus", Coord<3>(7, 6, 5), 9, false);
     compare<3, true>("container 3-D torus", Coord<3>(2, 1, 3), 4, false);
+    testPlugins();
     testMissingID();
     testGridAccess();
     if (failures) {

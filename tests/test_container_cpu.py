@@ -162,3 +162,28 @@ def test_striped_simulator_refuses_container_models():
     box, _ = synth.container_cells(4, 3, 1, n_dims=2)
     with pytest.raises(capi.LogicError):
         StripedSimulator(CellInit(box, None, 1), models.Container2Cube, engine=cpu_engine)
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_container_random_meshes_against_the_reference(oracle, seed):
+    """seeded random grids — dimension, topology, extents down to one container, fill, shortest neighbour lists, an edge
+    container, the same id in several containers — C restatement against the reference binary, bit for bit"""
+    if not oracle.have_ref("container"):
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    rng = np.random.default_rng(1000 + seed)
+    nd = int(rng.integers(2, 4))
+    dims = [int(rng.integers(1, 7)) for _ in range(nd)] + [1] * (3 - nd)
+    torus = bool(rng.integers(0, 2))
+    edge = bool(rng.integers(0, 2)) and not torus
+    box, eb = synth.container_cells(*dims, n_dims=nd, torus=torus, edge=edge, seed=seed, fill=float(rng.uniform(0.2, 1.0)),
+                                    min_neighbors=int(rng.integers(0, 3)))
+    if rng.integers(0, 3) == 0:
+        synth.container_duplicate_ids(box)
+        if eb is not None:
+            synth.container_duplicate_ids(eb)
+    steps = int(rng.integers(1, 9))
+    ref, _ = oracle.run_ref_container(box, steps, n_dims=nd, torus=torus, edge=eb)
+    got = oracle.container(box, steps, n_dims=nd, torus=torus, edge=eb)
+    nan = np.isnan(got)
+    assert np.array_equal(nan, np.isnan(ref["values"]))           # elements without neighbours: 0 / 0 on both sides
+    assert np.array_equal(np.where(nan, 0, got).view(np.uint64), np.where(nan, 0, ref["values"]).view(np.uint64))
